@@ -1,0 +1,10 @@
+"""deepof_b200 — B200-native (sm_100a) trainer for DeepOF's VaDE pose-window embeddings.
+
+Only the hot path lives here: hand-written CUDA kernels behind a C-ABI
+(``include/deepof_b200.h``, ``libdeepof_b200.so``) and a thin Python host that mirrors the
+reference's model / step interface.  There is no CPU fallback.
+"""
+from ._lib import DofError, LIB_PATH, LOG_KEYS  # noqa: F401
+from .vade import VaDEB200, VadeLossCfg, graph_operators, state_layout  # noqa: F401
+
+__all__ = ["VaDEB200", "VadeLossCfg", "DofError", "graph_operators", "state_layout", "LIB_PATH", "LOG_KEYS"]

@@ -1,0 +1,897 @@
+// deepof_b200 C-ABI: state layout, workspace, and the orchestration of the VaDE / recurrent
+// forward, loss, backward and optimizer kernels.  See include/deepof_b200.h.
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/deepof_b200.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "gru.cuh"
+#include "layers.cuh"
+#include "loss.cuh"
+
+thread_local char g_dof_err[512] = {0};
+
+// ---------------------------------------------------------------------------
+// state layout  (reference VaDEPT.state_dict() order)
+// ---------------------------------------------------------------------------
+struct Entry {
+    std::string name;
+    int64_t off, numel;
+    int ndim;
+    int shape[4];
+    int group;
+};
+
+struct GruP { int64_t w_ih[2], w_hh[2], b_ih[2], b_hh[2]; };
+struct BlockP { int64_t conv; GruP g1, g2; int64_t n1w, n1b, n2w, n2b, pw, pb; };
+struct Layout {
+    std::vector<Entry> e;
+    int64_t total = 0;
+    int64_t lap, elap, inc;
+    BlockP blk[2];
+    int64_t node_kernel, edge_kernel, node_weights, edge_weights, node_bias, edge_bias;
+    int64_t final_w, final_b;
+    GruP dg1, dg2;
+    int64_t dn1w, dn1b, dn2w, dn2b, dconv, dn3w, dn3b, loc_w, loc_b;
+    int64_t gmm_mu, gmm_lv, prior, pretrain, Wm, bm, Wv, bv, lens_w, lens_b;
+};
+
+static int64_t add_entry(Layout& L, const std::string& name, int group, int d0, int d1 = -1, int d2 = -1) {
+    Entry en;
+    en.name = name;
+    en.off = L.total;
+    en.group = group;
+    en.shape[0] = en.shape[1] = en.shape[2] = en.shape[3] = 0;
+    if (d0 < 0) { en.ndim = 0; en.numel = 1; }
+    else if (d1 < 0) { en.ndim = 1; en.shape[0] = d0; en.numel = d0; }
+    else if (d2 < 0) { en.ndim = 2; en.shape[0] = d0; en.shape[1] = d1; en.numel = (int64_t)d0 * d1; }
+    else { en.ndim = 3; en.shape[0] = d0; en.shape[1] = d1; en.shape[2] = d2; en.numel = (int64_t)d0 * d1 * d2; }
+    L.total += en.numel;
+    L.e.push_back(en);
+    return en.off;
+}
+
+static void add_gru(Layout& L, const std::string& p, int group, int I, int H, GruP& g) {
+    const char* suf[2] = {"", "_reverse"};
+    for (int d = 0; d < 2; d++) {
+        g.w_ih[d] = add_entry(L, p + "weight_ih_l0" + suf[d], group, 3 * H, I);
+        g.w_hh[d] = add_entry(L, p + "weight_hh_l0" + suf[d], group, 3 * H, H);
+        g.b_ih[d] = add_entry(L, p + "bias_ih_l0" + suf[d], group, 3 * H);
+        g.b_hh[d] = add_entry(L, p + "bias_hh_l0" + suf[d], group, 3 * H);
+    }
+}
+
+static int dint(const dof_config& c) { return c.D < 64 ? c.D : 64; }
+
+static Layout build_layout(const dof_config& c) {
+    Layout L;
+    const int N = c.N, E = c.E, D = c.D, K = c.K, di = dint(c);
+    L.lap = add_entry(L, "encoder.laplacian", 0, N, N);
+    L.elap = add_entry(L, "encoder.edge_laplacian", 0, E, E);
+    L.inc = add_entry(L, "encoder.incidence", 0, N, E);
+    const char* bn[2] = {"encoder.node_recurrent_block.", "encoder.edge_recurrent_block."};
+    for (int b = 0; b < 2; b++) {
+        std::string p = bn[b];
+        int Fin = b == 0 ? c.F : c.Fe;
+        BlockP& B = L.blk[b];
+        B.conv = add_entry(L, p + "conv1d.weight", 1, 2 * di, Fin, 5);
+        add_gru(L, p + "gru1.", 1, 2 * di, 2 * di, B.g1);
+        B.n1w = add_entry(L, p + "norm1.weight", 1, 4 * di);
+        B.n1b = add_entry(L, p + "norm1.bias", 1, 4 * di);
+        add_gru(L, p + "gru2.", 1, 4 * di, di, B.g2);
+        B.n2w = add_entry(L, p + "norm2.weight", 1, 2 * di);
+        B.n2b = add_entry(L, p + "norm2.bias", 1, 2 * di);
+        int pg = (di != D) ? 1 : 0;   // dead parameter when internal_dim == latent_dim (models_new.py:274)
+        B.pw = add_entry(L, p + "projection.weight", pg, 2 * D, 2 * di);
+        B.pb = add_entry(L, p + "projection.bias", pg, 2 * D);
+    }
+    std::string g = "encoder.spatial_gnn_block.";
+    L.node_kernel = add_entry(L, g + "node_kernel", 1, 2 * D, D);
+    L.edge_kernel = add_entry(L, g + "edge_kernel", 1, 2 * D, D);
+    L.node_weights = add_entry(L, g + "node_weights", 1, 2 * D, 1);
+    L.edge_weights = add_entry(L, g + "edge_weights", 1, 2 * D, 1);
+    L.node_bias = add_entry(L, g + "node_bias", 1, D);
+    L.edge_bias = add_entry(L, g + "edge_bias", 1, D);
+    L.final_w = add_entry(L, "encoder.final_dense.weight", 1, D, (N + E) * D);
+    L.final_b = add_entry(L, "encoder.final_dense.bias", 1, D);
+    add_gru(L, "decoder.gru1.", 2, D, D, L.dg1);
+    L.dn1w = add_entry(L, "decoder.norm1.weight", 2, 2 * D);
+    L.dn1b = add_entry(L, "decoder.norm1.bias", 2, 2 * D);
+    add_gru(L, "decoder.gru2.", 2, 2 * D, 2 * D, L.dg2);
+    L.dn2w = add_entry(L, "decoder.norm2.weight", 2, 4 * D);
+    L.dn2b = add_entry(L, "decoder.norm2.bias", 2, 4 * D);
+    L.dconv = add_entry(L, "decoder.conv1d.weight", 2, 2 * D, 4 * D, 5);
+    L.dn3w = add_entry(L, "decoder.norm3.weight", 2, 2 * D);
+    L.dn3b = add_entry(L, "decoder.norm3.bias", 2, 2 * D);
+    L.loc_w = add_entry(L, "decoder.prob_decoder.loc_projection.weight", 2, N * c.F, 2 * D);
+    L.loc_b = add_entry(L, "decoder.prob_decoder.loc_projection.bias", 2, N * c.F);
+    L.gmm_mu = add_entry(L, "latent_space.gmm_means", 3, K, D);
+    L.gmm_lv = add_entry(L, "latent_space.gmm_log_vars", 3, K, D);
+    L.prior = add_entry(L, "latent_space.prior", 0, K);
+    L.pretrain = add_entry(L, "latent_space.pretrain", 0, -1);
+    L.Wm = add_entry(L, "latent_space.encoder_mean.weight", 1, D, D);
+    L.bm = add_entry(L, "latent_space.encoder_mean.bias", 1, D);
+    L.Wv = add_entry(L, "latent_space.encoder_log_var.weight", 1, D, D);
+    L.bv = add_entry(L, "latent_space.encoder_log_var.bias", 1, D);
+    L.lens_w = add_entry(L, "latent_space.lens.weight", 0, D, D);   // never receives a gradient
+    L.lens_b = add_entry(L, "latent_space.lens.bias", 0, D);
+    return L;
+}
+
+static int check_cfg(const dof_config* c) {
+    if (!c) DOF_FAIL(DOF_ERR_ARG, "null config");
+    if (c->T < 1 || c->N < 1 || c->E < 1 || c->F < 1 || c->Fe < 1 || c->D < 1 || c->K < 1)
+        DOF_FAIL(DOF_ERR_ARG, "bad geometry T=%d N=%d E=%d F=%d Fe=%d D=%d K=%d", c->T, c->N, c->E, c->F,
+                 c->Fe, c->D, c->K);
+    if (c->K > LOSS_MAXK) DOF_FAIL(DOF_ERR_UNSUPPORTED, "n_components %d > %d", c->K, LOSS_MAXK);
+    if (c->D > 32) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 32 not supported by the GRU kernels yet", c->D);
+    return DOF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------
+struct Bump {
+    char* base; size_t off, cap;
+    bool dry;
+    template <typename T> T* get(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
+        T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+struct BlockWS {
+    int S, Fin, G;
+    int* gidx;
+    float *Xs, *Cv; int* len;
+    float *Gi1[2], *H1, *Gt1[2], *mu1, *rs1, *Y1;
+    float *Gi2[2], *H2, *Gt2[2], *Hn, *mu2, *rs2, *Y2, *P;
+    float *dP, *dY2, *dHn, *dG2[2], *dY1, *dH1, *dG1[2], *dCv;
+};
+
+struct dof_handle {
+    dof_config cfg;
+    Layout L;
+    int device, sm_count, max_batch, training;
+    int di, H1, H2, C1;
+    BlockWS blk[2];
+    unsigned char* group;   // [state numel]
+    // mid
+    float *Pn, *Pe, *On, *Oe, *enc, *zm, *pre, *lv, *z, *q;
+    float *dOn, *dOe, *dPn, *dPe, *denc, *dzm, *dpre, *dz_dec;
+    // decoder
+    int* lenD;
+    float *GiD1[2], *HD1, *GtD1[2], *muD1, *rsD1, *YD1;
+    float *GiD2[2], *HD2, *GtD2[2], *muD2, *rsD2, *YD2, *Cd, *muD3, *rsD3, *YD3, *loc;
+    float *dloc, *dYD3, *dCd, *dYD2, *dHD2, *dGD2[2], *dYD1, *dHD1, *dGD1[2], *dGs[2], *Wt;
+    // loss
+    double* stats; float *coef, *dzm_kl, *dlv_kl, *distw;
+    int lastB;
+    std::map<std::string, std::pair<const void*, int64_t>> dbg;
+};
+
+static void plan_workspace(dof_handle* h, Bump& bp) {
+    const dof_config& c = h->cfg;
+    const int B = h->max_batch, T = c.T, D = c.D, K = c.K, N = c.N, E = c.E;
+    const int H1 = h->H1, H2 = h->H2, C1 = h->C1;
+    const bool tr = h->training != 0;
+    h->group = bp.get<unsigned char>((size_t)h->L.total);
+    for (int b = 0; b < 2; b++) {
+        BlockWS& w = h->blk[b];
+        w.G = b == 0 ? N : E;
+        w.Fin = b == 0 ? c.F : c.Fe;
+        w.S = B * w.G;
+        const size_t S = (size_t)w.S, ST = S * T;
+        w.gidx = bp.get<int>((size_t)w.G * T * w.Fin);
+        w.Xs = bp.get<float>(ST * w.Fin);
+        w.Cv = bp.get<float>(ST * C1);
+        w.len = bp.get<int>(S);
+        for (int d = 0; d < 2; d++) w.Gi1[d] = bp.get<float>(ST * 3 * H1);
+        w.H1 = bp.get<float>(ST * 2 * H1);
+        for (int d = 0; d < 2; d++) w.Gt1[d] = tr ? bp.get<float>(ST * 4 * H1) : nullptr;
+        w.mu1 = bp.get<float>(ST); w.rs1 = bp.get<float>(ST);
+        w.Y1 = bp.get<float>(ST * 2 * H1);
+        for (int d = 0; d < 2; d++) w.Gi2[d] = bp.get<float>(ST * 3 * H2);
+        w.H2 = tr ? bp.get<float>(ST * 2 * H2) : nullptr;
+        for (int d = 0; d < 2; d++) w.Gt2[d] = tr ? bp.get<float>(ST * 4 * H2) : nullptr;
+        w.Hn = bp.get<float>(S * 2 * H2);
+        w.mu2 = bp.get<float>(S); w.rs2 = bp.get<float>(S);
+        w.Y2 = bp.get<float>(S * 2 * H2);
+        w.P = (h->di != D) ? bp.get<float>(S * 2 * D) : w.Y2;
+        if (tr) {
+            w.dP = bp.get<float>(S * 2 * D);
+            w.dY2 = (h->di != D) ? bp.get<float>(S * 2 * H2) : w.dP;
+            w.dHn = bp.get<float>(S * 2 * H2);
+            for (int d = 0; d < 2; d++) w.dG2[d] = bp.get<float>(ST * 4 * H2);
+            w.dY1 = bp.get<float>(ST * 2 * H1);
+            w.dH1 = bp.get<float>(ST * 2 * H1);
+            for (int d = 0; d < 2; d++) w.dG1[d] = bp.get<float>(ST * 4 * H1);
+            w.dCv = bp.get<float>(ST * C1);
+        }
+    }
+    const size_t Bz = (size_t)B, BT = Bz * T;
+    h->Pn = bp.get<float>(Bz * N * 2 * D); h->Pe = bp.get<float>(Bz * E * 2 * D);
+    h->On = bp.get<float>(Bz * N * D); h->Oe = bp.get<float>(Bz * E * D);
+    h->enc = bp.get<float>(Bz * D); h->zm = bp.get<float>(Bz * D); h->pre = bp.get<float>(Bz * D);
+    h->lv = bp.get<float>(Bz * D); h->z = bp.get<float>(Bz * D); h->q = bp.get<float>(Bz * K);
+    h->lenD = bp.get<int>(Bz);
+    for (int d = 0; d < 2; d++) h->GiD1[d] = bp.get<float>(Bz * 3 * D);
+    h->HD1 = bp.get<float>(BT * 2 * D);
+    for (int d = 0; d < 2; d++) h->GtD1[d] = tr ? bp.get<float>(BT * 4 * D) : nullptr;
+    h->muD1 = bp.get<float>(BT); h->rsD1 = bp.get<float>(BT);
+    h->YD1 = bp.get<float>(BT * 2 * D);
+    for (int d = 0; d < 2; d++) h->GiD2[d] = bp.get<float>(BT * 6 * D);
+    h->HD2 = bp.get<float>(BT * 4 * D);
+    for (int d = 0; d < 2; d++) h->GtD2[d] = tr ? bp.get<float>(BT * 8 * D) : nullptr;
+    h->muD2 = bp.get<float>(BT); h->rsD2 = bp.get<float>(BT);
+    h->YD2 = bp.get<float>(BT * 4 * D);
+    h->Cd = bp.get<float>(BT * 2 * D);
+    h->muD3 = bp.get<float>(BT); h->rsD3 = bp.get<float>(BT);
+    h->YD3 = bp.get<float>(BT * 2 * D);
+    h->loc = bp.get<float>(BT * N * c.F);
+    if (tr) {
+        h->dOn = bp.get<float>(Bz * N * D); h->dOe = bp.get<float>(Bz * E * D);
+        h->dPn = bp.get<float>(Bz * N * 2 * D); h->dPe = bp.get<float>(Bz * E * 2 * D);
+        h->denc = bp.get<float>(Bz * D); h->dzm = bp.get<float>(Bz * D); h->dpre = bp.get<float>(Bz * D);
+        h->dz_dec = bp.get<float>(Bz * D);
+        h->dloc = bp.get<float>(BT * N * c.F);
+        h->dYD3 = bp.get<float>(BT * 2 * D); h->dCd = bp.get<float>(BT * 2 * D);
+        h->dYD2 = bp.get<float>(BT * 4 * D); h->dHD2 = bp.get<float>(BT * 4 * D);
+        for (int d = 0; d < 2; d++) h->dGD2[d] = bp.get<float>(BT * 8 * D);
+        h->dYD1 = bp.get<float>(BT * 2 * D); h->dHD1 = bp.get<float>(BT * 2 * D);
+        for (int d = 0; d < 2; d++) h->dGD1[d] = bp.get<float>(BT * 4 * D);
+        for (int d = 0; d < 2; d++) h->dGs[d] = bp.get<float>(Bz * 4 * D);
+        h->Wt = bp.get<float>((size_t)4 * D * 2 * D * 5);
+        StatsLayout SL = stats_layout(D, K);
+        CoefLayout CL = coef_layout(D, K);
+        h->stats = bp.get<double>(SL.total);
+        h->coef = bp.get<float>(CL.total);
+        h->dzm_kl = bp.get<float>(Bz * D); h->dlv_kl = bp.get<float>(Bz * D);
+        h->distw = bp.get<float>(Bz);
+    }
+}
+
+static void init_derived(dof_handle* h) {
+    h->di = dint(h->cfg);
+    h->H1 = 2 * h->di; h->H2 = h->di; h->C1 = 2 * h->di;
+}
+
+// index of (g,t',f) inside one window flattened [T,G,F]
+static void build_gidx(int T, int G, int F, std::vector<int>& out) {
+    out.resize((size_t)G * T * F);
+    for (int g = 0; g < G; g++)
+        for (int t2 = 0; t2 < T; t2++)
+            for (int f = 0; f < F; f++) {
+                long long lin = ((long long)f * T + t2) * G + g;
+                int j = (int)(lin / T), t = (int)(lin % T);
+                out[((size_t)g * T + t2) * F + f] = t * (G * F) + j;
+            }
+}
+
+extern "C" {
+
+int dof_abi_version(void) { return DOF_ABI_VERSION; }
+const char* dof_last_error(void) { return g_dof_err; }
+
+int64_t dof_state_numel(const dof_config* cfg) {
+    if (check_cfg(cfg) != DOF_OK) return -1;
+    return build_layout(*cfg).total;
+}
+int dof_state_num_entries(const dof_config* cfg) {
+    if (check_cfg(cfg) != DOF_OK) return -1;
+    return (int)build_layout(*cfg).e.size();
+}
+int dof_state_entry(const dof_config* cfg, int index, char* name_out, int64_t* offset_out, int64_t* numel_out,
+                    int* ndim_out, int* shape_out, int* group_out) {
+    DOF_TRY(check_cfg(cfg));
+    Layout L = build_layout(*cfg);
+    if (index < 0 || index >= (int)L.e.size()) DOF_FAIL(DOF_ERR_ARG, "entry index %d out of range", index);
+    const Entry& e = L.e[index];
+    if (name_out) { strncpy(name_out, e.name.c_str(), 127); name_out[127] = 0; }
+    if (offset_out) *offset_out = e.off;
+    if (numel_out) *numel_out = e.numel;
+    if (ndim_out) *ndim_out = e.ndim;
+    if (shape_out) for (int i = 0; i < 4; i++) shape_out[i] = e.shape[i];
+    if (group_out) *group_out = e.group;
+    return DOF_OK;
+}
+
+// censNetConv_pt.py:160-175 (gcn_filter :182-243, incidence :296-370, line graph :258-279)
+static void gcn_filter_host(const std::vector<double>& A, int n, std::vector<double>& out) {
+    std::vector<double> Ah(A), deg(n, 0.0);
+    for (int i = 0; i < n; i++) Ah[(size_t)i * n + i] += 1.0;
+    for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int j = 0; j < n; j++) s += Ah[(size_t)i * n + j];
+        deg[i] = (s == 0.0) ? 1.0 : s;
+    }
+    out.resize((size_t)n * n);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) out[(size_t)i * n + j] = pow(deg[i], -0.5) * Ah[(size_t)i * n + j] * pow(deg[j], -0.5);
+}
+
+int dof_graph_operators(const double* adjacency, int N, int max_edges, float* laplacian, float* edge_laplacian,
+                        float* incidence, int* n_edges_out) {
+    if (!adjacency || N < 1) DOF_FAIL(DOF_ERR_ARG, "bad adjacency");
+    std::vector<std::pair<int, int>> edges;
+    for (int i = 0; i < N; i++)
+        for (int j = i; j < N; j++)
+            if (adjacency[(size_t)i * N + j] != 0.0) edges.push_back({i, j});
+    const int E = (int)edges.size();
+    if (n_edges_out) *n_edges_out = E;
+    if (!laplacian) return DOF_OK;   // query only
+    if (E > max_edges) DOF_FAIL(DOF_ERR_ARG, "%d edges > max_edges %d", E, max_edges);
+    std::vector<double> A(adjacency, adjacency + (size_t)N * N), lap;
+    gcn_filter_host(A, N, lap);
+    for (size_t i = 0; i < lap.size(); i++) laplacian[i] = (float)lap[i];
+    std::vector<double> inc((size_t)N * E, 0.0);
+    for (int e = 0; e < E; e++) { inc[(size_t)edges[e].first * E + e] = 1.0; inc[(size_t)edges[e].second * E + e] = 1.0; }
+    for (size_t i = 0; i < inc.size(); i++) incidence[i] = (float)inc[i];
+    std::vector<double> line((size_t)E * E, 0.0), elap;
+    for (int e = 0; e < E; e++)
+        for (int f = 0; f < E; f++) {
+            double s = 0.0;
+            for (int n = 0; n < N; n++) s += inc[(size_t)n * E + e] * inc[(size_t)n * E + f];
+            line[(size_t)e * E + f] = s - (e == f ? 2.0 : 0.0);
+        }
+    gcn_filter_host(line, E, elap);
+    for (size_t i = 0; i < elap.size(); i++) edge_laplacian[i] = (float)elap[i];
+    return DOF_OK;
+}
+
+size_t dof_workspace_bytes(const dof_config* cfg, int max_batch, int training) {
+    if (check_cfg(cfg) != DOF_OK || max_batch < 1) return 0;
+    dof_handle h;
+    h.cfg = *cfg; h.L = build_layout(*cfg); h.max_batch = max_batch; h.training = training;
+    init_derived(&h);
+    Bump bp{nullptr, 0, 0, true};
+    plan_workspace(&h, bp);
+    return bp.off + 256;
+}
+
+int dof_create(const dof_config* cfg, int device, int max_batch, int training, void* workspace,
+               size_t workspace_bytes, dof_handle** out) {
+    DOF_TRY(check_cfg(cfg));
+    if (!out || !workspace || max_batch < 1) DOF_FAIL(DOF_ERR_ARG, "null output / workspace or bad max_batch");
+    int ndev = 0;
+    DOF_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) DOF_FAIL(DOF_ERR_ARG, "device %d not available (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    DOF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) DOF_FAIL(DOF_ERR_UNSUPPORTED, "deepof_b200 needs an sm_100-class GPU, found sm_%d%d", prop.major, prop.minor);
+    DOF_CUDA(cudaSetDevice(device));
+    dof_handle* h = new dof_handle();
+    h->cfg = *cfg; h->L = build_layout(*cfg); h->device = device; h->sm_count = prop.multiProcessorCount;
+    h->max_batch = max_batch; h->training = training; h->lastB = 0;
+    init_derived(h);
+    size_t need = dof_workspace_bytes(cfg, max_batch, training);
+    if (workspace_bytes < need) { delete h; DOF_FAIL(DOF_ERR_WORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, need); }
+    uintptr_t base = ((uintptr_t)workspace + 255) / 256 * 256;
+    Bump bp{reinterpret_cast<char*>(base), 0, workspace_bytes, false};
+    plan_workspace(h, bp);
+    // constant tables
+    std::vector<unsigned char> grp((size_t)h->L.total, 0);
+    for (const Entry& e : h->L.e)
+        for (int64_t i = 0; i < e.numel; i++) grp[(size_t)(e.off + i)] = (unsigned char)e.group;
+    cudaError_t ce = cudaMemcpy(h->group, grp.data(), grp.size(), cudaMemcpyHostToDevice);
+    for (int b = 0; b < 2 && ce == cudaSuccess; b++) {
+        std::vector<int> gi;
+        build_gidx(cfg->T, h->blk[b].G, h->blk[b].Fin, gi);
+        ce = cudaMemcpy(h->blk[b].gidx, gi.data(), gi.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (ce != cudaSuccess) { delete h; DOF_FAIL(DOF_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(ce)); }
+    *out = h;
+    return DOF_OK;
+}
+
+int dof_destroy(dof_handle* h) {
+    delete h;
+    return DOF_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+static int ln_fwd(const float* x, const float* w, const float* b, float* y, float* mu, float* rs, long long R,
+                  int W, int sm, cudaStream_t st) {
+    if (W > 32 * LN_MAXV) DOF_FAIL(DOF_ERR_UNSUPPORTED, "LayerNorm width %d > %d", W, 32 * LN_MAXV);
+    long long blocks = (R + 7) / 8;
+    int grid = (int)(blocks < (long long)sm * 16 ? blocks : (long long)sm * 16);
+    if (grid < 1) return DOF_OK;
+    ln_fwd_kernel<<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W);
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+static int ln_bwd(const float* dy, const float* x, const float* mu, const float* rs, const float* w, float* dx,
+                  float* dw, float* db, long long R, int W, int relu_in, int sm, cudaStream_t st) {
+    long long blocks = (R + 7) / 8;
+    int grid = (int)(blocks < (long long)sm * 4 ? blocks : (long long)sm * 4);
+    if (grid < 1) return DOF_OK;
+    ln_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+// two-direction input projection Gi[dir] = A . W_ih[dir]^T + b_ih[dir]
+static int gru_input_proj(const float* state, const GruP& g, MatView A, int M, int I, int H, float* const Gi[2],
+                          cudaStream_t st) {
+    GemmArgs ga[2];
+    for (int d = 0; d < 2; d++)
+        ga[d] = gemm_args(A, state + g.w_ih[d], I, 0, state + g.b_ih[d], Gi[d], 3 * H, M, 3 * H, I);
+    return launch_gemm_rows(ga, 2, st);
+}
+
+static int enc_block_forward(dof_handle* h, int b, const float* state, const float* xin, int B, bool train,
+                             cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    BlockWS& w = h->blk[b];
+    const BlockP& P = h->L.blk[b];
+    const int T = c.T, S = B * w.G, H1 = h->H1, H2 = h->H2, C1 = h->C1;
+    const int M = S * T;
+    EncConvArgs ca;
+    ca.x = xin; ca.gidx = w.gidx; ca.w = state + P.conv; ca.Xs = w.Xs; ca.Cv = w.Cv; ca.len = w.len;
+    ca.B = B; ca.T = T; ca.G = w.G; ca.F = w.Fin; ca.C = C1;
+    size_t smem = ((size_t)T * w.G * w.Fin + (size_t)C1 * w.Fin * 5 + (size_t)w.G * T) * 4;
+    enc_conv_kernel<<<B, 256, smem, st>>>(ca);
+    DOF_LAUNCH_CHECK();
+    DOF_TRY(gru_input_proj(state, P.g1, mv_plain(w.Cv, C1), M, C1, H1, w.Gi1, st));
+    GruFwdArgs f;
+    memset(&f, 0, sizeof(f));
+    for (int d = 0; d < 2; d++) {
+        f.Gi[d] = w.Gi1[d]; f.Whh[d] = state + P.g1.w_hh[d]; f.bhh[d] = state + P.g1.b_hh[d];
+        f.Gt[d] = train ? w.Gt1[d] : nullptr;
+    }
+    f.gi_ss = (long long)T * 3 * H1; f.gi_st = 3 * H1; f.len = w.len; f.Hout = w.H1; f.Hn = nullptr;
+    f.S = S; f.T = T; f.H = H1;
+    DOF_TRY(launch_gru_fwd(f, st));
+    DOF_TRY(ln_fwd(w.H1, state + P.n1w, state + P.n1b, w.Y1, w.mu1, w.rs1, M, 2 * H1, h->sm_count, st));
+    DOF_TRY(gru_input_proj(state, P.g2, mv_plain(w.Y1, 2 * H1), M, 2 * H1, H2, w.Gi2, st));
+    memset(&f, 0, sizeof(f));
+    for (int d = 0; d < 2; d++) {
+        f.Gi[d] = w.Gi2[d]; f.Whh[d] = state + P.g2.w_hh[d]; f.bhh[d] = state + P.g2.b_hh[d];
+        f.Gt[d] = train ? w.Gt2[d] : nullptr;
+    }
+    f.gi_ss = (long long)T * 3 * H2; f.gi_st = 3 * H2; f.len = w.len; f.Hout = train ? w.H2 : nullptr; f.Hn = w.Hn;
+    f.S = S; f.T = T; f.H = H2;
+    DOF_TRY(launch_gru_fwd(f, st));
+    DOF_TRY(ln_fwd(w.Hn, state + P.n2w, state + P.n2b, w.Y2, w.mu2, w.rs2, S, 2 * H2, h->sm_count, st));
+    if (h->di != c.D) {
+        GemmArgs g = gemm_args(mv_plain(w.Y2, 2 * H2), state + P.pw, 2 * H2, 0, state + P.pb, w.P, 2 * c.D, S,
+                               2 * c.D, 2 * H2);
+        DOF_TRY(launch_gemm_rows(&g, 1, st));
+    }
+    return DOF_OK;
+}
+
+static CensArgs cens_args(dof_handle* h, const float* state, int B) {
+    const dof_config& c = h->cfg;
+    CensArgs a;
+    memset(&a, 0, sizeof(a));
+    a.node = h->blk[0].P; a.edge = h->blk[1].P;
+    a.lap = state + h->L.lap; a.elap = state + h->L.elap; a.inc = state + h->L.inc;
+    a.wn = state + h->L.node_weights; a.we = state + h->L.edge_weights;
+    a.Pn = h->Pn; a.Pe = h->Pe;
+    a.B = B; a.N = c.N; a.E = c.E; a.C = 2 * c.D;
+    return a;
+}
+
+static int encoder_forward(dof_handle* h, const float* state, const float* x, const float* a, int B, bool train,
+                           const float* eps, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int N = c.N, E = c.E, D = c.D, K = c.K;
+    DOF_TRY(enc_block_forward(h, 0, state, x, B, train, st));
+    DOF_TRY(enc_block_forward(h, 1, state, a, B, train, st));
+    CensArgs ca = cens_args(h, state, B);
+    size_t smem = cens_smem_floats(N, E, 2 * D) * 4;
+    if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "graph too large for the CensNet kernel (%zu B smem)", smem);
+    static bool attr = false;
+    if (!attr) {
+        DOF_CUDA(cudaFuncSetAttribute(cens_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        DOF_CUDA(cudaFuncSetAttribute(cens_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    cens_fwd_kernel<<<B, 128, smem, st>>>(ca);
+    DOF_LAUNCH_CHECK();
+    GemmArgs g[2];
+    g[0] = gemm_args(mv_plain(h->Pn, 2 * D), state + L.node_kernel, D, 1, state + L.node_bias, h->On, D, B * N, D, 2 * D);
+    g[1] = gemm_args(mv_plain(h->Pe, 2 * D), state + L.edge_kernel, D, 1, state + L.edge_bias, h->Oe, D, B * E, D, 2 * D);
+    g[0].relu = g[1].relu = 1;
+    DOF_TRY(launch_gemm_rows(g, 2, st));
+    GemmArgs f0 = gemm_args(mv_plain(h->On, N * D), state + L.final_w, (N + E) * D, 0, state + L.final_b, h->enc, D, B, D, N * D);
+    DOF_TRY(launch_gemm_rows(&f0, 1, st));
+    GemmArgs f1 = gemm_args(mv_plain(h->Oe, E * D), state + L.final_w + (size_t)N * D, (N + E) * D, 0, nullptr, h->enc, D, B, D, E * D);
+    f1.accum = 1;
+    DOF_TRY(launch_gemm_rows(&f1, 1, st));
+    LatentArgs la;
+    la.enc = h->enc; la.Wm = state + L.Wm; la.bm = state + L.bm; la.Wv = state + L.Wv; la.bv = state + L.bv;
+    la.eps = eps; la.gmm_mu = state + L.gmm_mu; la.gmm_lv = state + L.gmm_lv; la.prior = state + L.prior;
+    la.zm = h->zm; la.pre = h->pre; la.lv = h->lv; la.z = h->z; la.q = h->q; la.B = B; la.D = D; la.K = K;
+    size_t lsm = ((size_t)2 * D * D + 2 * D + 2 * (size_t)K * D + K) * 4;
+    latent_fwd_kernel<<<cdiv(B, 64), 64, lsm, st>>>(la);
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+static int decoder_forward(dof_handle* h, const float* state, const float* x, int B, bool train, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T;
+    row_valid_len_kernel<<<cdiv(B, 128), 128, 0, st>>>(x, h->lenD, B, T, NF);
+    DOF_LAUNCH_CHECK();
+    DOF_TRY(gru_input_proj(state, L.dg1, mv_plain(h->z, D), B, D, D, h->GiD1, st));
+    GruFwdArgs f;
+    memset(&f, 0, sizeof(f));
+    for (int d = 0; d < 2; d++) {
+        f.Gi[d] = h->GiD1[d]; f.Whh[d] = state + L.dg1.w_hh[d]; f.bhh[d] = state + L.dg1.b_hh[d];
+        f.Gt[d] = train ? h->GtD1[d] : nullptr;
+    }
+    f.gi_ss = 3 * D; f.gi_st = 0; f.len = h->lenD; f.Hout = h->HD1; f.S = B; f.T = T; f.H = D;
+    DOF_TRY(launch_gru_fwd(f, st));
+    DOF_TRY(ln_fwd(h->HD1, state + L.dn1w, state + L.dn1b, h->YD1, h->muD1, h->rsD1, M, 2 * D, h->sm_count, st));
+    DOF_TRY(gru_input_proj(state, L.dg2, mv_plain(h->YD1, 2 * D), M, 2 * D, 2 * D, h->GiD2, st));
+    memset(&f, 0, sizeof(f));
+    for (int d = 0; d < 2; d++) {
+        f.Gi[d] = h->GiD2[d]; f.Whh[d] = state + L.dg2.w_hh[d]; f.bhh[d] = state + L.dg2.b_hh[d];
+        f.Gt[d] = train ? h->GtD2[d] : nullptr;
+    }
+    f.gi_ss = (long long)T * 6 * D; f.gi_st = 6 * D; f.len = h->lenD; f.Hout = h->HD2; f.S = B; f.T = T; f.H = 2 * D;
+    DOF_TRY(launch_gru_fwd(f, st));
+    DOF_TRY(ln_fwd(h->HD2, state + L.dn2w, state + L.dn2b, h->YD2, h->muD2, h->rsD2, M, 4 * D, h->sm_count, st));
+    GemmArgs gc = gemm_args(mv_conv5(h->YD2, 4 * D, T, +1), state + L.dconv, 20 * D, 0, nullptr, h->Cd, 2 * D, M, 2 * D, 20 * D);
+    gc.relu = 1;
+    DOF_TRY(launch_gemm_rows(&gc, 1, st));
+    DOF_TRY(ln_fwd(h->Cd, state + L.dn3w, state + L.dn3b, h->YD3, h->muD3, h->rsD3, M, 2 * D, h->sm_count, st));
+    GemmArgs gl = gemm_args(mv_plain(h->YD3, 2 * D), state + L.loc_w, 2 * D, 0, state + L.loc_b, h->loc, NF, M, NF, 2 * D);
+    DOF_TRY(launch_gemm_rows(&gl, 1, st));
+    return DOF_OK;
+}
+
+static void register_debug(dof_handle* h, int B) {
+    const dof_config& c = h->cfg;
+    h->dbg.clear();
+    h->dbg["node_out"] = {h->blk[0].P, (int64_t)B * c.N * 2 * c.D};
+    h->dbg["edge_out"] = {h->blk[1].P, (int64_t)B * c.E * 2 * c.D};
+    h->dbg["node_conv"] = {h->blk[0].Cv, (int64_t)B * c.N * c.T * h->C1};
+    h->dbg["node_gru1"] = {h->blk[0].H1, (int64_t)B * c.N * c.T * 2 * h->H1};
+    h->dbg["node_hn"] = {h->blk[0].Hn, (int64_t)B * c.N * 2 * h->H2};
+    h->dbg["len_node"] = {h->blk[0].len, (int64_t)B * c.N};
+    h->dbg["len_edge"] = {h->blk[1].len, (int64_t)B * c.E};
+    h->dbg["cens_node"] = {h->On, (int64_t)B * c.N * c.D};
+    h->dbg["cens_edge"] = {h->Oe, (int64_t)B * c.E * c.D};
+    h->dbg["enc"] = {h->enc, (int64_t)B * c.D};
+    h->dbg["z"] = {h->z, (int64_t)B * c.D};
+    h->dbg["z_mean"] = {h->zm, (int64_t)B * c.D};
+    h->dbg["z_log_var"] = {h->lv, (int64_t)B * c.D};
+    h->dbg["q"] = {h->q, (int64_t)B * c.K};
+    h->dbg["loc"] = {h->loc, (int64_t)B * c.T * c.N * c.F};
+    if (h->training) {
+        h->dbg["dloc"] = {h->dloc, (int64_t)B * c.T * c.N * c.F};
+        h->dbg["dz_dec"] = {h->dz_dec, (int64_t)B * c.D};
+        h->dbg["dzm"] = {h->dzm, (int64_t)B * c.D};
+        h->dbg["dpre"] = {h->dpre, (int64_t)B * c.D};
+        h->dbg["denc"] = {h->denc, (int64_t)B * c.D};
+        h->dbg["dnode_out"] = {h->blk[0].dP, (int64_t)B * c.N * 2 * c.D};
+        h->dbg["dedge_out"] = {h->blk[1].dP, (int64_t)B * c.E * 2 * c.D};
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------
+// gradients of one bidirectional GRU given dG[dir] [M rows x 4H] (layout da_r|da_z|da_n*r|da_n):
+//   dW_ih, db_ih (from X), dW_hh, db_hh (from time-shifted H), and optionally dX.
+static int gru_param_grads(dof_handle* h, const GruP& g, float* grad, const float* state, float* const dG[2],
+                           MatView X, int Mx, float* const dGx[2],   // dGx: rows matching X (== dG unless repeated input)
+                           const float* Hout, int M, int T, int I, int H, float* dX, const float* dXmask,
+                           cudaStream_t st) {
+    WGradArgs wa[2];
+    for (int d = 0; d < 2; d++)
+        wa[d] = wgrad_args(mv_split(dGx[d], 4 * H, 2 * H, H), X, grad + g.w_ih[d], I, 0, grad + g.b_ih[d], Mx, 3 * H, I);
+    DOF_TRY(launch_gemm_wgrad(wa, 2, st, h->sm_count));
+    for (int d = 0; d < 2; d++)
+        wa[d] = wgrad_args(mv_plain(dG[d], 4 * H), mv_tshift(Hout + d * H, 2 * H, T, d ? +1 : -1), grad + g.w_hh[d], H, 0,
+                           grad + g.b_hh[d], M, 3 * H, H);
+    DOF_TRY(launch_gemm_wgrad(wa, 2, st, h->sm_count));
+    if (dX) {
+        for (int d = 0; d < 2; d++) {
+            GemmArgs ga = gemm_args(mv_split(dGx[d], 4 * H, 2 * H, H), state + g.w_ih[d], I, 1, nullptr, dX, I, Mx, I, 3 * H);
+            ga.accum = d;
+            if (d == 1 && dXmask) { ga.mask = dXmask; ga.ldmask = I; }
+            DOF_TRY(launch_gemm_rows(&ga, 1, st));
+        }
+    }
+    return DOF_OK;
+}
+
+static int decoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T, sm = h->sm_count;
+    WGradArgs w0 = wgrad_args(mv_plain(h->dloc, NF), mv_plain(h->YD3, 2 * D), grad + L.loc_w, 2 * D, 0, grad + L.loc_b, M, NF, 2 * D);
+    DOF_TRY(launch_gemm_wgrad(&w0, 1, st, sm));
+    GemmArgs g0 = gemm_args(mv_plain(h->dloc, NF), state + L.loc_w, 2 * D, 1, nullptr, h->dYD3, 2 * D, M, 2 * D, NF);
+    DOF_TRY(launch_gemm_rows(&g0, 1, st));
+    DOF_TRY(ln_bwd(h->dYD3, h->Cd, h->muD3, h->rsD3, state + L.dn3w, h->dCd, grad + L.dn3w, grad + L.dn3b, M, 2 * D, 1, sm, st));
+    WGradArgs w1 = wgrad_args(mv_plain(h->dCd, 2 * D), mv_conv5(h->YD2, 4 * D, T, +1), grad + L.dconv, 20 * D, 0, nullptr, M, 2 * D, 20 * D);
+    DOF_TRY(launch_gemm_wgrad(&w1, 1, st, sm));
+    conv_w_transpose_kernel<<<cdiv(2 * D * 4 * D * 5, 256), 256, 0, st>>>(state + L.dconv, h->Wt, 2 * D, 4 * D);
+    DOF_LAUNCH_CHECK();
+    GemmArgs g1 = gemm_args(mv_conv5(h->dCd, 2 * D, T, -1), h->Wt, 10 * D, 0, nullptr, h->dYD2, 4 * D, M, 4 * D, 10 * D);
+    DOF_TRY(launch_gemm_rows(&g1, 1, st));
+    DOF_TRY(ln_bwd(h->dYD2, h->HD2, h->muD2, h->rsD2, state + L.dn2w, h->dHD2, grad + L.dn2w, grad + L.dn2b, M, 4 * D, 0, sm, st));
+    GruBwdArgs b;
+    memset(&b, 0, sizeof(b));
+    for (int d = 0; d < 2; d++) { b.Whh[d] = state + L.dg2.w_hh[d]; b.Gt[d] = h->GtD2[d]; b.dG[d] = h->dGD2[d]; }
+    b.len = h->lenD; b.Hout = h->HD2; b.dOut = h->dHD2; b.dHn = nullptr; b.S = B; b.T = T; b.H = 2 * D;
+    DOF_TRY(launch_gru_bwd(b, st));
+    DOF_TRY(gru_param_grads(h, L.dg2, grad, state, h->dGD2, mv_plain(h->YD1, 2 * D), M, h->dGD2, h->HD2, M, T, 2 * D, 2 * D,
+                            h->dYD1, nullptr, st));
+    DOF_TRY(ln_bwd(h->dYD1, h->HD1, h->muD1, h->rsD1, state + L.dn1w, h->dHD1, grad + L.dn1w, grad + L.dn1b, M, 2 * D, 0, sm, st));
+    memset(&b, 0, sizeof(b));
+    for (int d = 0; d < 2; d++) { b.Whh[d] = state + L.dg1.w_hh[d]; b.Gt[d] = h->GtD1[d]; b.dG[d] = h->dGD1[d]; }
+    b.len = h->lenD; b.Hout = h->HD1; b.dOut = h->dHD1; b.dHn = nullptr; b.S = B; b.T = T; b.H = D;
+    DOF_TRY(launch_gru_bwd(b, st));
+    for (int d = 0; d < 2; d++) {
+        sum_over_t_kernel<<<cdiv((long long)B * 4 * D, 256), 256, 0, st>>>(h->dGD1[d], h->dGs[d], B, T, 4 * D, 0);
+        DOF_LAUNCH_CHECK();
+    }
+    DOF_TRY(gru_param_grads(h, L.dg1, grad, state, h->dGD1, mv_plain(h->z, D), B, h->dGs, h->HD1, M, T, D, D, h->dz_dec,
+                            nullptr, st));
+    return DOF_OK;
+}
+
+static int enc_block_backward(dof_handle* h, int bi, const float* state, float* grad, int B, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    BlockWS& w = h->blk[bi];
+    const BlockP& P = h->L.blk[bi];
+    const int T = c.T, S = B * w.G, H1 = h->H1, H2 = h->H2, C1 = h->C1, M = S * T, sm = h->sm_count;
+    if (h->di != c.D) {
+        WGradArgs wp = wgrad_args(mv_plain(w.dP, 2 * c.D), mv_plain(w.Y2, 2 * H2), grad + P.pw, 2 * H2, 0, grad + P.pb, S, 2 * c.D, 2 * H2);
+        DOF_TRY(launch_gemm_wgrad(&wp, 1, st, sm));
+        GemmArgs gp = gemm_args(mv_plain(w.dP, 2 * c.D), state + P.pw, 2 * H2, 1, nullptr, w.dY2, 2 * H2, S, 2 * H2, 2 * c.D);
+        DOF_TRY(launch_gemm_rows(&gp, 1, st));
+    }
+    DOF_TRY(ln_bwd(w.dY2, w.Hn, w.mu2, w.rs2, state + P.n2w, w.dHn, grad + P.n2w, grad + P.n2b, S, 2 * H2, 0, sm, st));
+    GruBwdArgs b;
+    memset(&b, 0, sizeof(b));
+    for (int d = 0; d < 2; d++) { b.Whh[d] = state + P.g2.w_hh[d]; b.Gt[d] = w.Gt2[d]; b.dG[d] = w.dG2[d]; }
+    b.len = w.len; b.Hout = w.H2; b.dOut = nullptr; b.dHn = w.dHn; b.S = S; b.T = T; b.H = H2;
+    DOF_TRY(launch_gru_bwd(b, st));
+    DOF_TRY(gru_param_grads(h, P.g2, grad, state, w.dG2, mv_plain(w.Y1, 2 * H1), M, w.dG2, w.H2, M, T, 2 * H1, H2, w.dY1, nullptr, st));
+    DOF_TRY(ln_bwd(w.dY1, w.H1, w.mu1, w.rs1, state + P.n1w, w.dH1, grad + P.n1w, grad + P.n1b, M, 2 * H1, 0, sm, st));
+    memset(&b, 0, sizeof(b));
+    for (int d = 0; d < 2; d++) { b.Whh[d] = state + P.g1.w_hh[d]; b.Gt[d] = w.Gt1[d]; b.dG[d] = w.dG1[d]; }
+    b.len = w.len; b.Hout = w.H1; b.dOut = w.dH1; b.dHn = nullptr; b.S = S; b.T = T; b.H = H1;
+    DOF_TRY(launch_gru_bwd(b, st));
+    DOF_TRY(gru_param_grads(h, P.g1, grad, state, w.dG1, mv_plain(w.Cv, C1), M, w.dG1, w.H1, M, T, C1, H1, w.dCv, w.Cv, st));
+    WGradArgs wc = wgrad_args(mv_plain(w.dCv, C1), mv_conv5(w.Xs, w.Fin, T, +1), grad + P.conv, w.Fin * 5, 0, nullptr, M, C1, w.Fin * 5);
+    DOF_TRY(launch_gemm_wgrad(&wc, 1, st, sm));
+    return DOF_OK;
+}
+
+static int encoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int N = c.N, E = c.E, D = c.D, sm = h->sm_count;
+    // latent heads
+    WGradArgs wl[2];
+    wl[0] = wgrad_args(mv_plain(h->dzm, D), mv_plain(h->enc, D), grad + L.Wm, D, 0, grad + L.bm, B, D, D);
+    wl[1] = wgrad_args(mv_plain(h->dpre, D), mv_plain(h->enc, D), grad + L.Wv, D, 0, grad + L.bv, B, D, D);
+    DOF_TRY(launch_gemm_wgrad(wl, 2, st, sm));
+    GemmArgs ge = gemm_args(mv_plain(h->dzm, D), state + L.Wm, D, 1, nullptr, h->denc, D, B, D, D);
+    DOF_TRY(launch_gemm_rows(&ge, 1, st));
+    ge = gemm_args(mv_plain(h->dpre, D), state + L.Wv, D, 1, nullptr, h->denc, D, B, D, D);
+    ge.accum = 1;
+    DOF_TRY(launch_gemm_rows(&ge, 1, st));
+    // final dense
+    WGradArgs wf = wgrad_args(mv_plain(h->denc, D), mv_plain(h->On, N * D), grad + L.final_w, (N + E) * D, 0, grad + L.final_b, B, D, N * D);
+    DOF_TRY(launch_gemm_wgrad(&wf, 1, st, sm));
+    wf = wgrad_args(mv_plain(h->denc, D), mv_plain(h->Oe, E * D), grad + L.final_w + (size_t)N * D, (N + E) * D, 0, nullptr, B, D, E * D);
+    DOF_TRY(launch_gemm_wgrad(&wf, 1, st, sm));
+    GemmArgs gf = gemm_args(mv_plain(h->denc, D), state + L.final_w, (N + E) * D, 1, nullptr, h->dOn, N * D, B, N * D, D);
+    gf.mask = h->On; gf.ldmask = N * D;
+    DOF_TRY(launch_gemm_rows(&gf, 1, st));
+    gf = gemm_args(mv_plain(h->denc, D), state + L.final_w + (size_t)N * D, (N + E) * D, 1, nullptr, h->dOe, E * D, B, E * D, D);
+    gf.mask = h->Oe; gf.ldmask = E * D;
+    DOF_TRY(launch_gemm_rows(&gf, 1, st));
+    // CensNet dense kernels
+    WGradArgs wk[2];
+    wk[0] = wgrad_args(mv_plain(h->dOn, D), mv_plain(h->Pn, 2 * D), grad + L.node_kernel, D, 1, grad + L.node_bias, B * N, D, 2 * D);
+    wk[1] = wgrad_args(mv_plain(h->dOe, D), mv_plain(h->Pe, 2 * D), grad + L.edge_kernel, D, 1, grad + L.edge_bias, B * E, D, 2 * D);
+    DOF_TRY(launch_gemm_wgrad(wk, 2, st, sm));
+    GemmArgs gk[2];
+    gk[0] = gemm_args(mv_plain(h->dOn, D), state + L.node_kernel, D, 0, nullptr, h->dPn, 2 * D, B * N, 2 * D, D);
+    gk[1] = gemm_args(mv_plain(h->dOe, D), state + L.edge_kernel, D, 0, nullptr, h->dPe, 2 * D, B * E, 2 * D, D);
+    DOF_TRY(launch_gemm_rows(gk, 2, st));
+    CensArgs ca = cens_args(h, state, B);
+    ca.dPn = h->dPn; ca.dPe = h->dPe; ca.dnode = h->blk[0].dP; ca.dedge = h->blk[1].dP;
+    ca.dwn = grad + L.node_weights; ca.dwe = grad + L.edge_weights;
+    size_t smem = (cens_smem_floats(N, E, 2 * D) + (size_t)(N + E) * 2 * D + (size_t)N * N + (size_t)E * E + N + E) * 4;
+    if (smem > 220 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "graph too large for the CensNet backward kernel");
+    cens_bwd_kernel<<<B, 128, smem, st>>>(ca);
+    DOF_LAUNCH_CHECK();
+    DOF_TRY(enc_block_backward(h, 0, state, grad, B, st));
+    DOF_TRY(enc_block_backward(h, 1, state, grad, B, st));
+    return DOF_OK;
+}
+
+static int check_batch(dof_handle* h, int B) {
+    if (!h) DOF_FAIL(DOF_ERR_ARG, "null handle");
+    if (B < 1 || B > h->max_batch) DOF_FAIL(DOF_ERR_ARG, "batch %d outside [1, %d]", B, h->max_batch);
+    return DOF_OK;
+}
+
+extern "C" {
+
+int dof_vade_forward_eval(dof_handle* h, const float* state, const float* x, const float* a, int B, float* enc,
+                          float* emb, float* q, float* loc, void* stream) {
+    DOF_TRY(check_batch(h, B));
+    if (!state || !x || !a) DOF_FAIL(DOF_ERR_ARG, "null input");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dof_config& c = h->cfg;
+    DOF_TRY(encoder_forward(h, state, x, a, B, false, nullptr, st));
+    if (loc) DOF_TRY(decoder_forward(h, state, x, B, false, st));
+    if (enc) DOF_CUDA(cudaMemcpyAsync(enc, h->enc, (size_t)B * c.D * 4, cudaMemcpyDeviceToDevice, st));
+    if (emb) DOF_CUDA(cudaMemcpyAsync(emb, h->zm, (size_t)B * c.D * 4, cudaMemcpyDeviceToDevice, st));
+    if (q) DOF_CUDA(cudaMemcpyAsync(q, h->q, (size_t)B * c.K * 4, cudaMemcpyDeviceToDevice, st));
+    if (loc) DOF_CUDA(cudaMemcpyAsync(loc, h->loc, (size_t)B * c.T * c.N * c.F * 4, cudaMemcpyDeviceToDevice, st));
+    h->lastB = B;
+    register_debug(h, B);
+    return DOF_OK;
+}
+
+int dof_vade_embed(dof_handle* h, const float* state, const float* x, const float* a, int B, float* emb, float* q,
+                   void* stream) {
+    return dof_vade_forward_eval(h, state, x, a, B, nullptr, emb, q, nullptr, stream);
+}
+
+int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B,
+                       const float* eps, const float* mc_eps, const float* tau_batch, const float* class_weight,
+                       const float* floor_c, const dof_vade_loss_cfg* loss, float* logs, void* stream) {
+    DOF_TRY(check_batch(h, B));
+    if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
+    if (!state || !grad || !x || !a || !eps || !loss || !logs || !floor_c) DOF_FAIL(DOF_ERR_ARG, "null argument");
+    if (!loss->pretrain_mode && !mc_eps) DOF_FAIL(DOF_ERR_ARG, "mc_eps is required in main mode");
+    if (!loss->pretrain_mode && loss->mc_samples != 32) DOF_FAIL(DOF_ERR_UNSUPPORTED, "mc_samples must be 32, got %d", loss->mc_samples);
+    if (loss->tf_cluster_weight != 0.f) DOF_FAIL(DOF_ERR_UNSUPPORTED, "tf_cluster_weight != 0 is not supported");
+    if (loss->reg_scatter_weight != 0.f) DOF_FAIL(DOF_ERR_UNSUPPORTED, "reg_scatter_weight != 0 is not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int D = c.D, K = c.K, T = c.T, NF = c.N * c.F;
+    DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)L.total * 4, st));
+    DOF_TRY(encoder_forward(h, state, x, a, B, true, eps, st));
+    DOF_TRY(decoder_forward(h, state, x, B, true, st));
+    // ---- loss
+    StatsLayout SL = stats_layout(D, K);
+    DOF_CUDA(cudaMemsetAsync(h->stats, 0, (size_t)SL.total * sizeof(double), st));
+    const long long nrec = (long long)B * T * NF;
+    int rgrid = (int)((nrec + 255) / 256 < (long long)h->sm_count * 8 ? (nrec + 255) / 256 : (long long)h->sm_count * 8);
+    recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->stats);
+    DOF_LAUNCH_CHECK();
+    LossArgs la;
+    memset(&la, 0, sizeof(la));
+    la.cfg = *loss;
+    la.z = h->z; la.zm = h->zm; la.lv = h->lv; la.pre = h->pre; la.q = h->q; la.eps = eps; la.mc_eps = mc_eps;
+    la.gmm_mu = state + L.gmm_mu; la.gmm_lv = state + L.gmm_lv; la.prior = state + L.prior;
+    la.tau = (loss->lambda_distill > 0.f) ? tau_batch : nullptr;
+    la.class_weight = class_weight; la.floor_c = floor_c;
+    la.stats = h->stats; la.coef = h->coef; la.dzm_kl = h->dzm_kl; la.dlv_kl = h->dlv_kl; la.distw = h->distw;
+    la.dz_dec = h->dz_dec; la.dzm = h->dzm; la.dpre = h->dpre; la.g_mu = grad + L.gmm_mu; la.g_lv = grad + L.gmm_lv;
+    la.logs = logs; la.B = B; la.D = D; la.K = K; la.T = T; la.Dx = NF;
+    static bool attr = false;
+    if (!attr) {
+        DOF_CUDA(cudaFuncSetAttribute(loss_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        DOF_CUDA(cudaFuncSetAttribute(loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        DOF_CUDA(cudaFuncSetAttribute(loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    int lgrid = cdiv(B, LS_WARPS) < h->sm_count * 4 ? cdiv(B, LS_WARPS) : h->sm_count * 4;
+    loss_stats_kernel<<<lgrid, LS_WARPS * 32, loss_stats_smem_floats(D, K) * 4, st>>>(la);
+    DOF_LAUNCH_CHECK();
+    loss_finalize_kernel<<<1, 256, loss_finalize_smem_bytes(D, K), st>>>(la);
+    DOF_LAUNCH_CHECK();
+    // ---- backward
+    DOF_TRY(decoder_backward(h, state, grad, B, st));
+    loss_grad_kernel<<<lgrid, LS_WARPS * 32, loss_grad_smem_floats(D, K) * 4, st>>>(la);
+    DOF_LAUNCH_CHECK();
+    DOF_TRY(encoder_backward(h, state, grad, B, st));
+    h->lastB = B;
+    register_debug(h, B);
+    return DOF_OK;
+}
+
+int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m, float* adam_v, const dof_adam_cfg* opt,
+                  void* stream) {
+    if (!h || !state || !grad || !adam_m || !adam_v || !opt) DOF_FAIL(DOF_ERR_ARG, "null argument");
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = state; a.g = grad; a.m = adam_m; a.v = adam_v; a.group = h->group; a.n = h->L.total;
+    for (int g = 0; g < 4; g++) {
+        a.lr[g] = opt->lr[g];
+        a.active[g] = opt->active[g];
+        int s = opt->step[g] > 0 ? opt->step[g] : 1;
+        a.bc1[g] = (float)(1.0 - pow((double)opt->beta1, s));
+        a.bc2_sqrt[g] = (float)sqrt(1.0 - pow((double)opt->beta2, s));
+    }
+    a.clip = opt->clip_value; a.gscale = opt->grad_scale; a.beta1 = opt->beta1; a.beta2 = opt->beta2; a.eps = opt->eps;
+    clip_adam_kernel<<<cdiv(a.n, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+const void* dof_debug_tensor(dof_handle* h, const char* name, int64_t* numel_out) {
+    if (!h || !name) return nullptr;
+    auto it = h->dbg.find(name);
+    if (it == h->dbg.end()) return nullptr;
+    if (numel_out) *numel_out = it->second.second;
+    return it->second.first;
+}
+
+// ---- op-level test hooks -----------------------------------------------------
+static MatView make_view(const float* p, int ld, int mode, int p0, int p1) {
+    switch (mode) {
+        case A_SPLIT: return mv_split(p, ld, p0, p1);
+        case A_CONV5: return mv_conv5(p, ld, p0, p1);
+        case A_TSHIFT: return mv_tshift(p, ld, p0, p1);
+        default: return mv_plain(p, ld);
+    }
+}
+
+int dof_test_gemm_rows(const float* A, int lda, int mode, int p0, int p1, int p2, const float* W, int ldw, int wT,
+                       const float* bias, float* C, int ldc, int M, int N, int K, int relu, int accum,
+                       const float* mask, void* stream) {
+    (void)p2;
+    GemmArgs g = gemm_args(make_view(A, lda, mode, p0, p1), W, ldw, wT, bias, C, ldc, M, N, K);
+    g.relu = relu; g.accum = accum; g.mask = mask; g.ldmask = ldc;
+    return launch_gemm_rows(&g, 1, (cudaStream_t)stream);
+}
+
+int dof_test_gemm_wgrad(const float* P, int ldp, int pmode, int pp0, int pp1, const float* Q, int ldq, int qmode,
+                        int qp0, int qp1, float* dW, int ldo, int oT, float* db, int M, int N, int K, void* stream) {
+    WGradArgs g = wgrad_args(make_view(P, ldp, pmode, pp0, pp1), make_view(Q, ldq, qmode, qp0, qp1), dW, ldo, oT, db, M, N, K);
+    int dev = 0, sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    return launch_gemm_wgrad(&g, 1, (cudaStream_t)stream, sm);
+}
+
+int dof_test_gru_fwd(const float* gi_f, const float* gi_b, long long gi_ss, int gi_st, const float* whh_f,
+                     const float* whh_b, const float* bhh_f, const float* bhh_b, const int* len, float* hout,
+                     float* gt_f, float* gt_b, float* hn, int S, int T, int H, void* stream) {
+    GruFwdArgs f;
+    memset(&f, 0, sizeof(f));
+    f.Gi[0] = gi_f; f.Gi[1] = gi_b; f.gi_ss = gi_ss; f.gi_st = gi_st;
+    f.Whh[0] = whh_f; f.Whh[1] = whh_b; f.bhh[0] = bhh_f; f.bhh[1] = bhh_b;
+    f.len = len; f.Hout = hout; f.Gt[0] = gt_f; f.Gt[1] = gt_b; f.Hn = hn; f.S = S; f.T = T; f.H = H;
+    return launch_gru_fwd(f, (cudaStream_t)stream);
+}
+
+int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout, const float* gt_f,
+                     const float* gt_b, const float* dout, const float* dhn, float* dg_f, float* dg_b, int S, int T,
+                     int H, void* stream) {
+    GruBwdArgs b;
+    memset(&b, 0, sizeof(b));
+    b.Whh[0] = whh_f; b.Whh[1] = whh_b; b.len = len; b.Hout = hout; b.Gt[0] = gt_f; b.Gt[1] = gt_b;
+    b.dOut = dout; b.dHn = dhn; b.dG[0] = dg_f; b.dG[1] = dg_b; b.S = S; b.T = T; b.H = H;
+    return launch_gru_bwd(b, (cudaStream_t)stream);
+}
+
+int dof_test_layernorm(const float* x, const float* w, const float* b, float eps, float* y, float* mu, float* rstd,
+                       const float* dy, float* dx, float* dw, float* db, long long R, int W, int relu_in,
+                       void* stream) {
+    (void)eps;
+    cudaStream_t st = (cudaStream_t)stream;
+    DOF_TRY(ln_fwd(x, w, b, y, mu, rstd, R, W, 148, st));
+    if (dy) DOF_TRY(ln_bwd(dy, x, mu, rstd, w, dx, dw, db, R, W, relu_in, 148, st));
+    return DOF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,457 @@
+// Non-GEMM layers of the VaDE / recurrent path: the reference's group-reshape gather
+// fused with the encoder Conv1d+ReLU, LayerNorm fwd/bwd, the CensNet graph aggregation,
+// the Gaussian-mixture latent head, and fused clip+Adam.
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// Encoder stage 1: gather (SURVEY A.1 scramble; models_new.py:120-138) + Conv1d(F->C,
+// k=5, 'same', no bias) + ReLU (models_new.py:228-230) + valid-length count (:233-234).
+// One CTA per window.  Writes the gathered sequences Xs[S,T,F] (needed by the conv
+// weight gradient), Cv[S,T,C] and len[S], with s = b*G + g.
+// ---------------------------------------------------------------------------
+struct EncConvArgs {
+    const float* x;     // [B, T*G*F]
+    const int* gidx;    // [G*T*F] index into a window for (g,t',f)
+    const float* w;     // [C,F,5]
+    float* Xs; float* Cv; int* len;
+    int B, T, G, F, C;
+};
+
+__global__ void __launch_bounds__(256) enc_conv_kernel(const EncConvArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int T = a.T, G = a.G, F = a.F, C = a.C;
+    const int W = T * G * F;
+    float* seq = smem;                 // [G][T][F]
+    float* w = seq + W;                // [C][F*5]
+    int* flag = reinterpret_cast<int*>(w + C * F * 5);   // [G*T]
+    const int b = blockIdx.x;
+    const float* xw = a.x + (size_t)b * W;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        float v = __ldg(xw + __ldg(a.gidx + i));
+        seq[i] = v;
+        a.Xs[(size_t)b * W + i] = v;   // [b*G+g][t][f] is exactly b*W + i
+    }
+    for (int i = threadIdx.x; i < C * F * 5; i += blockDim.x) w[i] = __ldg(a.w + i);
+    for (int i = threadIdx.x; i < G * T; i += blockDim.x) flag[i] = 0;
+    __syncthreads();
+    float* out = a.Cv + (size_t)b * G * T * C;
+    for (int i = threadIdx.x; i < G * T * C; i += blockDim.x) {
+        int co = i % C, gt = i / C;
+        int t = gt % T, g = gt / T;
+        const float* sq = seq + (size_t)g * T * F;
+        const float* wc = w + co * F * 5;
+        float acc = 0.f;
+        for (int f = 0; f < F; f++) {
+#pragma unroll
+            for (int kk = 0; kk < 5; kk++) {
+                int tt = t + kk - 2;
+                if (tt >= 0 && tt < T) acc = fmaf(wc[f * 5 + kk], sq[tt * F + f], acc);
+            }
+        }
+        acc = fmaxf(acc, 0.f);
+        out[i] = acc;
+        if (acc > 0.f) flag[gt] = 1;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        int n = 0;
+        for (int t = 0; t < T; t++) n += flag[g * T + t];
+        a.len[(size_t)b * G + g] = n;
+    }
+}
+
+// decoder validity: len[b] = #time steps whose data row is not all-zero (models_new.py:330-331)
+__global__ void row_valid_len_kernel(const float* x, int* len, int B, int T, int Dx) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int n = 0;
+    for (int t = 0; t < T; t++) {
+        const float* r = x + ((size_t)b * T + t) * Dx;
+        bool any = false;
+        for (int d = 0; d < Dx; d++) any |= (r[d] != 0.f);
+        n += any ? 1 : 0;
+    }
+    len[b] = n;
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm over the last dim (biased variance), one warp per row, W <= 256.
+// ---------------------------------------------------------------------------
+#define LN_MAXV 8
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ b, float eps,
+                                                     float* __restrict__ y, float* __restrict__ mu_out,
+                                                     float* __restrict__ rstd_out, long long R, int W) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = warp; r < R; r += nwarps) {
+        const float* xr = x + r * W;
+        float v[LN_MAXV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; i++) {
+            int c = lane + 32 * i;
+            v[i] = (c < W) ? xr[c] : 0.f;
+            s += v[i];
+        }
+        float mu = warp_sum(s) / W;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; i++) {
+            int c = lane + 32 * i;
+            float d = (c < W) ? v[i] - mu : 0.f;
+            q += d * d;
+        }
+        float var = warp_sum(q) / W;
+        float rstd = rsqrtf(var + eps);
+        // one Newton step: rsqrtf is ~2 ulp; keep LayerNorm at full fp32 accuracy
+        rstd = rstd * (1.5f - 0.5f * (var + eps) * rstd * rstd);
+        float* yr = y + r * W;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; i++) {
+            int c = lane + 32 * i;
+            if (c < W) yr[c] = (v[i] - mu) * rstd * __ldg(w + c) + __ldg(b + c);
+        }
+        if (lane == 0 && mu_out) { mu_out[r] = mu; rstd_out[r] = rstd; }
+    }
+}
+
+// dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*w; dw += dy*xhat; db += dy.
+// relu_in: the LN input x is a ReLU output -> additionally mask dx by (x > 0).
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                     const float* __restrict__ mu_in,
+                                                     const float* __restrict__ rstd_in,
+                                                     const float* __restrict__ w, float* __restrict__ dx,
+                                                     float* __restrict__ dw, float* __restrict__ db,
+                                                     long long R, int W, int relu_in) {
+    __shared__ float sdw[256], sdb[256];
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sdw[i] = 0.f; sdb[i] = 0.f; }
+    __syncthreads();
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    float adw[LN_MAXV], adb[LN_MAXV], wv[LN_MAXV];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; i++) {
+        adw[i] = 0.f; adb[i] = 0.f;
+        int c = lane + 32 * i;
+        wv[i] = (c < W) ? __ldg(w + c) : 0.f;
+    }
+    for (long long r = warp; r < R; r += nwarps) {
+        const float mu = mu_in[r], rstd = rstd_in[r];
+        const float* xr = x + r * W;
+        const float* dyr = dy + r * W;
+        float xh[LN_MAXV], g[LN_MAXV], xv[LN_MAXV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; i++) {
+            int c = lane + 32 * i;
+            float d = 0.f;
+            xv[i] = 0.f;
+            if (c < W) { xv[i] = xr[c]; d = dyr[c]; }
+            xh[i] = (c < W) ? (xv[i] - mu) * rstd : 0.f;
+            g[i] = d * wv[i];
+            s1 += g[i];
+            s2 += g[i] * xh[i];
+            adw[i] += d * xh[i];
+            adb[i] += d;
+        }
+        s1 = warp_sum(s1) / W;
+        s2 = warp_sum(s2) / W;
+        float* dxr = dx + r * W;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; i++) {
+            int c = lane + 32 * i;
+            if (c < W) {
+                float o = rstd * (g[i] - s1 - xh[i] * s2);
+                if (relu_in && !(xv[i] > 0.f)) o = 0.f;
+                dxr[c] = o;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; i++) {
+        int c = lane + 32 * i;
+        if (c < W) { atomicAdd(&sdw[c], adw[i]); atomicAdd(&sdb[c], adb[i]); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        atomicAdd(dw + c, sdw[c]);
+        atomicAdd(db + c, sdb[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// CensNet aggregation (censNetConv_pt.py:92-136), one CTA per window:
+//   Mv = (T diag(He.we) T^T) o lap ;  Pn = Mv.Hn        Me = (T^T diag(Hn.wn) T) o elap ; Pe = Me.He
+// The dense kernels (Pn.node_kernel + bias, relu) go through gemm_rows.
+// ---------------------------------------------------------------------------
+struct CensArgs {
+    const float* node; const float* edge;       // [B,N,C], [B,E,C]
+    const float* lap; const float* elap; const float* inc;   // [N,N],[E,E],[N,E]
+    const float* wn; const float* we;           // [C]
+    float* Pn; float* Pe;                       // fwd outputs [B,N,C],[B,E,C]
+    // backward
+    const float* dPn; const float* dPe;
+    float* dnode; float* dedge;                 // [B,N,C],[B,E,C]
+    float* dwn; float* dwe;                     // [C] (atomic accumulate)
+    int B, N, E, C;
+};
+
+__device__ __forceinline__ void cens_load(const CensArgs& a, int b, float* nd, float* ed, float* sinc,
+                                          float* wev, float* wnv, float* Mv, float* Me) {
+    const int N = a.N, E = a.E, C = a.C;
+    for (int i = threadIdx.x; i < N * C; i += blockDim.x) nd[i] = __ldg(a.node + (size_t)b * N * C + i);
+    for (int i = threadIdx.x; i < E * C; i += blockDim.x) ed[i] = __ldg(a.edge + (size_t)b * E * C + i);
+    for (int i = threadIdx.x; i < N * E; i += blockDim.x) sinc[i] = __ldg(a.inc + i);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N + E; i += blockDim.x) {
+        float s = 0.f;
+        if (i < E) {
+            for (int c = 0; c < C; c++) s = fmaf(ed[i * C + c], __ldg(a.we + c), s);
+            wev[i] = s;
+        } else {
+            int n = i - E;
+            for (int c = 0; c < C; c++) s = fmaf(nd[n * C + c], __ldg(a.wn + c), s);
+            wnv[n] = s;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * N + E * E; i += blockDim.x) {
+        if (i < N * N) {
+            int r = i / N, c = i % N;
+            float s = 0.f;
+            for (int e = 0; e < E; e++) s = fmaf(sinc[r * E + e] * wev[e], sinc[c * E + e], s);
+            Mv[i] = s * __ldg(a.lap + i);
+        } else {
+            int k = i - N * N;
+            int e = k / E, f = k % E;
+            float s = 0.f;
+            for (int n = 0; n < N; n++) s = fmaf(sinc[n * E + e] * wnv[n], sinc[n * E + f], s);
+            Me[k] = s * __ldg(a.elap + k);
+        }
+    }
+    __syncthreads();
+}
+
+static inline size_t cens_smem_floats(int N, int E, int C) {
+    return (size_t)N * C + (size_t)E * C + (size_t)N * E + E + N + (size_t)N * N + (size_t)E * E;
+}
+
+__global__ void __launch_bounds__(128) cens_fwd_kernel(const CensArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int N = a.N, E = a.E, C = a.C;
+    float* nd = smem; float* ed = nd + N * C; float* sinc = ed + E * C;
+    float* wev = sinc + N * E; float* wnv = wev + E; float* Mv = wnv + N; float* Me = Mv + N * N;
+    const int b = blockIdx.x;
+    cens_load(a, b, nd, ed, sinc, wev, wnv, Mv, Me);
+    for (int i = threadIdx.x; i < (N + E) * C; i += blockDim.x) {
+        if (i < N * C) {
+            int r = i / C, c = i % C;
+            float s = 0.f;
+            for (int j = 0; j < N; j++) s = fmaf(Mv[r * N + j], nd[j * C + c], s);
+            a.Pn[(size_t)b * N * C + i] = s;
+        } else {
+            int k = i - N * C;
+            int r = k / C, c = k % C;
+            float s = 0.f;
+            for (int j = 0; j < E; j++) s = fmaf(Me[r * E + j], ed[j * C + c], s);
+            a.Pe[(size_t)b * E * C + k] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) cens_bwd_kernel(const CensArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int N = a.N, E = a.E, C = a.C;
+    float* nd = smem; float* ed = nd + N * C; float* sinc = ed + E * C;
+    float* wev = sinc + N * E; float* wnv = wev + E; float* Mv = wnv + N; float* Me = Mv + N * N;
+    float* dpn = Me + E * E;            // [N*C]
+    float* dpe = dpn + N * C;           // [E*C]
+    float* G1 = dpe + E * C;            // [N*N]
+    float* G2 = G1 + N * N;             // [E*E]
+    float* dwev = G2 + E * E;           // [E]
+    float* dwnv = dwev + E;             // [N]
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < N * C; i += blockDim.x) dpn[i] = __ldg(a.dPn + (size_t)b * N * C + i);
+    for (int i = threadIdx.x; i < E * C; i += blockDim.x) dpe[i] = __ldg(a.dPe + (size_t)b * E * C + i);
+    cens_load(a, b, nd, ed, sinc, wev, wnv, Mv, Me);
+    for (int i = threadIdx.x; i < N * N + E * E; i += blockDim.x) {
+        if (i < N * N) {
+            int r = i / N, c = i % N;
+            float s = 0.f;
+            for (int k = 0; k < C; k++) s = fmaf(dpn[r * C + k], nd[c * C + k], s);
+            G1[i] = s * __ldg(a.lap + i);
+        } else {
+            int k2 = i - N * N;
+            int e = k2 / E, f = k2 % E;
+            float s = 0.f;
+            for (int k = 0; k < C; k++) s = fmaf(dpe[e * C + k], ed[f * C + k], s);
+            G2[k2] = s * __ldg(a.elap + k2);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N + E; i += blockDim.x) {
+        float s = 0.f;
+        if (i < E) {
+            for (int r = 0; r < N; r++) {
+                float ir = sinc[r * E + i];
+                if (ir == 0.f) continue;
+                for (int c = 0; c < N; c++) s = fmaf(ir * sinc[c * E + i], G1[r * N + c], s);
+            }
+            dwev[i] = s;
+        } else {
+            int n = i - E;
+            for (int e = 0; e < E; e++) {
+                float ie = sinc[n * E + e];
+                if (ie == 0.f) continue;
+                for (int f = 0; f < E; f++) s = fmaf(ie * sinc[n * E + f], G2[e * E + f], s);
+            }
+            dwnv[n] = s;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (N + E) * C; i += blockDim.x) {
+        if (i < N * C) {
+            int j = i / C, c = i % C;
+            float s = dwnv[j] * __ldg(a.wn + c);
+            for (int r = 0; r < N; r++) s = fmaf(Mv[r * N + j], dpn[r * C + c], s);
+            a.dnode[(size_t)b * N * C + i] = s;
+        } else {
+            int k = i - N * C;
+            int f = k / C, c = k % C;
+            float s = dwev[f] * __ldg(a.we + c);
+            for (int e = 0; e < E; e++) s = fmaf(Me[e * E + f], dpe[e * C + c], s);
+            a.dedge[(size_t)b * E * C + k] = s;
+        }
+    }
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        float s = 0.f;
+        if (c < C) {
+            for (int e = 0; e < E; e++) s = fmaf(dwev[e], ed[e * C + c], s);
+            atomicAdd(a.dwe + c, s);
+        } else {
+            int cc = c - C;
+            for (int n = 0; n < N; n++) s = fmaf(dwnv[n], nd[n * C + cc], s);
+            atomicAdd(a.dwn + cc, s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Gaussian-mixture latent head (models_new.py:1761-1791, 1745-1759), one thread per window.
+// ---------------------------------------------------------------------------
+struct LatentArgs {
+    const float* enc;                      // [B,D]
+    const float *Wm, *bm, *Wv, *bv;        // encoder_mean / encoder_log_var Linear
+    const float* eps;                      // [B,D] reparam noise, null => eval (z = z_mean)
+    const float *gmm_mu, *gmm_lv, *prior;  // [K,D],[K,D],[K]
+    float *zm, *pre, *lv, *z, *q;          // [B,D] x4, [B,K]
+    int B, D, K;
+};
+
+#define LOG_2PI_F 1.8378770664093453f
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+__global__ void __launch_bounds__(64) latent_fwd_kernel(const LatentArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = a.D, K = a.K;
+    float* Wm = smem; float* Wv = Wm + D * D; float* bm = Wv + D * D; float* bv = bm + D;
+    float* mu = bv + D; float* isd = mu + K * D; float* lcst = isd + K * D;   // lcst[K]
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) { Wm[i] = __ldg(a.Wm + i); Wv[i] = __ldg(a.Wv + i); }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { bm[i] = __ldg(a.bm + i); bv[i] = __ldg(a.bv + i); }
+    for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+        mu[i] = __ldg(a.gmm_mu + i);
+        float sd = fmaxf(expf(0.5f * __ldg(a.gmm_lv + i)), 1e-3f);
+        isd[i] = 1.0f / sd;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        float s = logf(__ldg(a.prior + c) + 1e-9f);
+        for (int d = 0; d < D; d++) s += logf(isd[c * D + d]) - 0.5f * LOG_2PI_F;   // -log(sd) - .5 log 2pi
+        lcst[c] = s;
+    }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const float* e = a.enc + (size_t)b * D;
+    for (int d = 0; d < D; d++) {
+        float s1 = bm[d], s2 = bv[d];
+        for (int k = 0; k < D; k++) {
+            float ev = e[k];
+            s1 = fmaf(Wm[d * D + k], ev, s1);
+            s2 = fmaf(Wv[d * D + k], ev, s2);
+        }
+        float lv = softplus_f(s2);
+        float zz = a.eps ? s1 + expf(0.5f * lv) * a.eps[(size_t)b * D + d] : s1;
+        a.zm[(size_t)b * D + d] = s1;
+        a.pre[(size_t)b * D + d] = s2;
+        a.lv[(size_t)b * D + d] = lv;
+        a.z[(size_t)b * D + d] = zz;
+    }
+    float mx = -INFINITY;
+    float* qb = a.q + (size_t)b * K;
+    for (int c = 0; c < K; c++) {
+        float s = 0.f;
+        for (int d = 0; d < D; d++) {
+            float t = (a.z[(size_t)b * D + d] - mu[c * D + d]) * isd[c * D + d];
+            s = fmaf(t, t, s);
+        }
+        float lg = lcst[c] - 0.5f * s;
+        qb[c] = lg;
+        mx = fmaxf(mx, lg);
+    }
+    float sum = 0.f;
+    for (int c = 0; c < K; c++) { float v = expf(qb[c] - mx); qb[c] = v; sum += v; }
+    float inv = 1.0f / sum;
+    for (int c = 0; c < K; c++) qb[c] *= inv;
+}
+
+// out[b, :] = sum_t in[b, t, :]   (gradient of the decoder's RepeatVector)
+__global__ void sum_over_t_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int W,
+                                  int accum) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * W) return;
+    int b = (int)(i / W), c = (int)(i % W);
+    float s = accum ? out[i] : 0.f;
+    for (int t = 0; t < T; t++) s += in[((size_t)b * T + t) * W + c];
+    out[i] = s;
+}
+
+// dst[n][c*5+kk] = src[c][n][kk]   (Conv1d weight [Cout=c, Cin=n, 5] -> transposed-conv operand)
+__global__ void conv_w_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * Cin * 5) return;
+    int kk = i % 5, n = (i / 5) % Cin, c = i / (5 * Cin);
+    dst[(size_t)n * Cout * 5 + c * 5 + kk] = src[i];
+}
+
+// ---------------------------------------------------------------------------
+// clip_grad_value_ + Adam (training.py:164-166, losses.py:817-833; torch.optim.Adam
+// defaults beta=(0.9,0.999), eps=1e-8, no weight decay).  group[i]: 0 = not trained
+// (buffers, dead parameters), 1.. = parameter group with its own lr / step count.
+// ---------------------------------------------------------------------------
+struct AdamArgs {
+    float* p; const float* g; float* m; float* v; const unsigned char* group;
+    long long n;
+    float lr[4]; float bc1[4]; float bc2_sqrt[4]; int active[4];
+    float clip; float gscale; float beta1, beta2, eps;
+};
+
+__global__ void __launch_bounds__(256) clip_adam_kernel(const AdamArgs a) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    int grp = a.group[i];
+    if (grp == 0 || !a.active[grp]) return;
+    float g = a.g[i] * a.gscale;
+    if (a.clip > 0.f) g = fminf(fmaxf(g, -a.clip), a.clip);
+    float m = a.beta1 * a.m[i] + (1.0f - a.beta1) * g;
+    float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
+    a.m[i] = m;
+    a.v[i] = v;
+    float denom = sqrtf(v) / a.bc2_sqrt[grp] + a.eps;
+    a.p[i] = a.p[i] - (a.lr[grp] / a.bc1[grp]) * (m / denom);
+}

@@ -1,0 +1,170 @@
+/* deepof_b200 — C ABI of the B200-native pose-window embedding trainer.
+ *
+ * This is the drop-in boundary for the ONE hot path of mlfpm/deepof that this library
+ * replaces: forward / backward / optimizer step of the VaDE model with the recurrent
+ * (GRU + CensNet) encoder-decoder over sliding windows of keypoint trajectories, plus the
+ * eval-mode embedding used by inference.  The reference has no native boundary (its
+ * "operator API" is Python); each entry point cites the reference
+ * code it stands in for (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only, no torch / C++ types.
+ *  - every `float*` / `int*` data argument is a DEVICE pointer to a contiguous row-major
+ *    array that the CALLER owns (the Python host allocates them as torch tensors); the
+ *    library owns nothing but the handle and carves its activations out of the
+ *    caller-provided workspace.
+ *  - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*); no
+ *    call synchronises the device.
+ *  - returns 0 on success, a negative DOF_ERR_* code otherwise; dof_last_error() gives
+ *    the message (thread-local).  Nothing throws across the boundary.
+ *  - one handle per (process, device); not thread-safe.
+ *  - there is no CPU fallback: every entry point fails if no sm_100-class device is usable.
+ */
+#ifndef DEEPOF_B200_H
+#define DEEPOF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOF_ABI_VERSION 1
+
+/* Model geometry.  Mirrors the constructor arguments of VaDEPT / RecurrentEncoderPT /
+ * RecurrentDecoderPT (deepof/clustering/models_new.py:37-105, 281-324, 1794-1839). */
+typedef struct {
+    int T;   /* window length (time steps)                          */
+    int N;   /* graph nodes (body parts)                            */
+    int E;   /* graph edges                                         */
+    int F;   /* features per node  (x, y, speed) = 3                */
+    int Fe;  /* features per edge  (log1p length) = 1               */
+    int D;   /* latent_dim                                          */
+    int K;   /* n_components (GMM clusters)                         */
+} dof_config;
+
+/* One phase of VadeLoss (deepof/clustering/losses.py:383-457, 567-797).  Field names follow
+ * the reference attributes.  tf_cluster_weight and reg_scatter_weight must be 0 (their
+ * reference defaults); a non-zero value is rejected with DOF_ERR_UNSUPPORTED. */
+typedef struct {
+    int pretrain_mode;
+    float kl_weight;               /* Dynamic_weight_manager.get_weight() for this step */
+    float l1_activity_weight;
+    float kmeans_loss_weight;      /* VadeLoss.kmeans_loss_weight of the active mode    */
+    float model_kmeans_weight;     /* GaussianMixtureLatentPT.kmeans_weight             */
+    float repel_weight, repel_length_scale;
+    float nonempty_weight, nonempty_floor;
+    int nonempty_p;
+    float tf_cluster_weight;
+    float reg_cat_clusters_weight;
+    float temporal_cohesion_weight;
+    float reg_scatter_weight, reg_scatter_beta;
+    float gmm_logvar_clamp_lo, gmm_logvar_clamp_hi;
+    int mc_samples;                /* must be 32 (losses.py:526)                        */
+    float lambda_distill, distill_sharpen_T;
+    int distill_conf_weight;
+    float distill_conf_thresh;
+} dof_vade_loss_cfg;
+
+/* Per-step optimizer scalars: clip_grad_value_ + Adam with the parameter groups of
+ * build_optimizer_vade (deepof/clustering/losses.py:817-833; training.py:164-166).
+ * Groups: 1 = encoder + latent heads, 2 = decoder, 3 = GMM means/log-vars.  `step[g]` is the
+ * 1-based Adam step count of the group AFTER this update; `active[g]`=0 leaves the group
+ * untouched (requires_grad=False in the reference, training.py:1746-1767). */
+typedef struct {
+    float lr[4];
+    int step[4];
+    int active[4];
+    float clip_value;   /* 0.75 in the reference; <=0 disables clipping              */
+    float grad_scale;   /* 1/world_size after a summed all-reduce, else 1             */
+    float beta1, beta2, eps;
+} dof_adam_cfg;
+
+#define DOF_N_LOGS 16
+/* logs[] (device, DOF_N_LOGS floats) in the order of step_vade's log dict
+ * (deepof/clustering/training.py:292-306):
+ *  0 total_loss 1 reconstruct_loss 2 kl_div 3 cat_clust_loss 4 kmeans_loss 5 activity_l1
+ *  6 prior_loss 7 distill_loss 8 tf_clust_loss 9 nonempty_loss 10 temporal_loss
+ *  11 scatter_loss 12 repel_loss 13 kl_weight 14 raw MC-KL mean (before the clamp) */
+
+typedef struct dof_handle dof_handle;
+
+int dof_abi_version(void);
+const char* dof_last_error(void);
+
+/* ---- flat state buffer ----------------------------------------------------------------
+ * All parameters and buffers of the model live in ONE flat fp32 buffer whose segments are,
+ * in order, the entries of the reference VaDEPT.state_dict(), so a
+ * reference checkpoint maps onto it by name and vice versa (model_utils_new.py:263-329). */
+int64_t dof_state_numel(const dof_config* cfg);
+int dof_state_num_entries(const dof_config* cfg);
+/* name_out: caller buffer of >=128 bytes; shape_out: 4 ints (unused dims = 0);
+ * group_out: 0 buffer / never-trained parameter, 1..3 optimizer group. */
+int dof_state_entry(const dof_config* cfg, int index, char* name_out, int64_t* offset_out,
+                    int64_t* numel_out, int* ndim_out, int* shape_out, int* group_out);
+
+/* Graph operators of CensNetConvPT.preprocess (deepof/clustering/censNetConv_pt.py:160-175):
+ * HOST arrays. adjacency [N*N] -> laplacian [N*N], edge_laplacian [E*E], incidence [N*E].
+ * Returns E through n_edges_out (edges = non-zeros of triu(adjacency), row-major). */
+int dof_graph_operators(const double* adjacency, int N, int max_edges, float* laplacian,
+                        float* edge_laplacian, float* incidence, int* n_edges_out);
+
+/* ---- handle ---------------------------------------------------------------------------- */
+size_t dof_workspace_bytes(const dof_config* cfg, int max_batch, int training);
+int dof_create(const dof_config* cfg, int device, int max_batch, int training, void* workspace,
+               size_t workspace_bytes, dof_handle** out);
+int dof_destroy(dof_handle* h);
+
+/* ---- eval-mode embedding: what embedding_per_video reads as model(x,a)[1], [2]
+ * (deepof/clustering/model_utils_new.py:610-617; VaDEPT.forward models_new.py:1841-1891).
+ * x [B,T,N,F], a [B,T,E,Fe] -> emb [B,D] (= z_mean), q [B,K]. */
+int dof_vade_embed(dof_handle* h, const float* state, const float* x, const float* a, int B,
+                   float* emb, float* q, void* stream);
+
+/* Full eval forward incl. decoder mean (tests / reconstruction): also enc [B,D] and
+ * loc [B,T,N*F]; any output pointer may be NULL. */
+int dof_vade_forward_eval(dof_handle* h, const float* state, const float* x, const float* a, int B,
+                          float* enc, float* emb, float* q, float* loc, void* stream);
+
+/* ---- one training step, split at the gradient all-reduce
+ * dof_vade_loss_grad  = step_vade forward + criterion + loss.backward()
+ *                       (deepof/clustering/training.py:231-309, 159-163)
+ * dof_clip_adam       = clip_grad_value_(0.75) + optimizer.step()  (training.py:164-166)
+ * grad is overwritten (zeroed first).  eps [B,D] is the reparameterisation noise, mc_eps
+ * [32,B,D] the Monte-Carlo KL noise (main mode only; may be NULL in pretrain mode),
+ * tau_batch [B,K] = tau_star[batch_indices] or NULL, class_weight [K] or NULL,
+ * floor_c [K] = per-cluster non-empty floor (losses.py:672-680). */
+int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a,
+                       int B, const float* eps, const float* mc_eps, const float* tau_batch,
+                       const float* class_weight, const float* floor_c, const dof_vade_loss_cfg* loss,
+                       float* logs, void* stream);
+int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m, float* adam_v,
+                  const dof_adam_cfg* opt, void* stream);
+
+/* Debug / test access to intermediate activations of the last forward (device pointers into
+ * the workspace; NULL if unknown).  Names: "node_out","edge_out","enc","z","z_mean",
+ * "z_log_var","q","loc","len_node","len_edge". */
+const void* dof_debug_tensor(dof_handle* h, const char* name, int64_t* numel_out);
+
+/* ---- op-level test hooks (used by tests/ to check single kernels against torch) ---------- */
+int dof_test_gemm_rows(const float* A, int lda, int mode, int p0, int p1, int p2, const float* W, int ldw,
+                       int wT, const float* bias, float* C, int ldc, int M, int N, int K, int relu,
+                       int accum, const float* mask, void* stream);
+int dof_test_gemm_wgrad(const float* P, int ldp, int pmode, int pp0, int pp1, const float* Q, int ldq,
+                        int qmode, int qp0, int qp1, float* dW, int ldo, int oT, float* db, int M, int N,
+                        int K, void* stream);
+int dof_test_gru_fwd(const float* gi_f, const float* gi_b, long long gi_ss, int gi_st, const float* whh_f,
+                     const float* whh_b, const float* bhh_f, const float* bhh_b, const int* len,
+                     float* hout, float* gt_f, float* gt_b, float* hn, int S, int T, int H, void* stream);
+int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout,
+                     const float* gt_f, const float* gt_b, const float* dout, const float* dhn,
+                     float* dg_f, float* dg_b, int S, int T, int H, void* stream);
+int dof_test_layernorm(const float* x, const float* w, const float* b, float eps, float* y, float* mu,
+                       float* rstd, const float* dy, float* dx, float* dw, float* db, long long R, int W,
+                       int relu_in, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPOF_B200_H */

@@ -1,0 +1,77 @@
+"""CPU: the C-ABI library loads, exports every symbol include/deepof_b200.h declares, and its
+host-side logic (state layout, graph operators) matches the reference golden files.
+No compute entry point is called (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import golden_cases, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    from deepof_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "deepof_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dof_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    raw = C.CDLL(built.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+    assert declared == set(built.EXPORTS), declared ^ set(built.EXPORTS)
+    assert built.lib().dof_abi_version() == 1
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_state_layout_is_reference_state_dict(built, case):
+    from deepof_b200.vade import state_layout
+    g = load_golden(case)
+    d = g["dims"]
+    cfg = built.DofConfig(d["T"], d["N"], d["E"], 3, 1, d["D"], d["K"])
+    lay = state_layout(cfg)
+    names = [k[2:] for k in g if k.startswith("p/")]
+    assert [l[0] for l in lay] == names
+    off = 0
+    for name, o, numel, shape, grp in lay:
+        assert tuple(g["p/" + name].shape) == shape, name
+        assert o == off
+        off += numel
+        has_grad = ("g/" + name) in g
+        assert (grp > 0) == has_grad, (name, grp)   # dead parameters / buffers are group 0
+    assert off == built.lib().dof_state_numel(C.byref(cfg))
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_graph_operators_match_reference(built, case):
+    from deepof_b200.vade import graph_operators
+    g = load_golden(case)
+    lap, elap, inc = graph_operators(g["adjacency"])
+    assert np.array_equal(inc, g["p/encoder.incidence"])
+    np.testing.assert_allclose(lap, g["p/encoder.laplacian"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(elap, g["p/encoder.edge_laplacian"], rtol=0, atol=1e-7)
+
+
+def test_bad_config_is_rejected(built):
+    cfg = built.DofConfig(25, 14, 14, 3, 1, 16, 64)   # K > 32
+    assert built.lib().dof_state_numel(C.byref(cfg)) < 0
+    assert b"n_components" in built.lib().dof_last_error()
+    assert built.lib().dof_workspace_bytes(C.byref(cfg), 16, 1) == 0
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "deepof_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"import\s+oracle|from\s+oracle|oracle[/.]\w", src), f

@@ -1,0 +1,230 @@
+"""GPU: single CUDA kernels, called through the C-ABI test hooks, against torch fp64 on the
+same device (oracle building blocks where they exist)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import vade_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+A_PLAIN, A_SPLIT, A_CONV5, A_TSHIFT = 0, 1, 2, 3
+
+
+@pytest.fixture(scope="module")
+def L():
+    from deepof_b200 import _lib
+    return _lib.lib()
+
+
+def P(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def S():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g)
+
+
+@pytest.mark.parametrize("M,N,K,wT", [(1000, 96, 32, 0), (777, 48, 64, 0), (300, 16, 448, 0), (515, 18, 12, 0),
+                                      (640, 224, 16, 1), (129, 32, 96, 1), (4096, 42, 32, 0), (50, 6, 6, 1)])
+def test_gemm_rows_plain(L, M, N, K, wT):
+    A = rnd(M, K, seed=1)
+    W = rnd(N, K, seed=2) if wT == 0 else rnd(K, N, seed=2)
+    bias = rnd(N, seed=3)
+    Cout = torch.zeros(M, N, device="cuda")
+    rc = L.dof_test_gemm_rows(P(A), K, A_PLAIN, 0, 0, 0, P(W), W.shape[1], wT, P(bias), P(Cout), N, M, N, K, 0, 0,
+                              None, S())
+    assert rc == 0, L.dof_last_error()
+    ref = A.double() @ (W.double().t() if wT == 0 else W.double()) + bias.double()
+    assert rel(Cout, ref) < 2e-6
+    # relu + accumulate + mask
+    C2 = rnd(M, N, seed=4)
+    base = C2.clone()
+    mask = rnd(M, N, seed=5)
+    rc = L.dof_test_gemm_rows(P(A), K, A_PLAIN, 0, 0, 0, P(W), W.shape[1], wT, P(bias), P(C2), N, M, N, K, 1, 1,
+                              P(mask), S())
+    assert rc == 0
+    ref2 = torch.relu(ref + base.double()) * (mask > 0)
+    assert rel(C2, ref2) < 2e-6
+
+
+def test_gemm_rows_views(L):
+    S_, T, Cc, N = 37, 25, 64, 32
+    M = S_ * T
+    X = rnd(S_, T, Cc, seed=1)
+    # conv5 'same' forward == oracle conv
+    W = rnd(N, Cc, 5, seed=2)
+    out = torch.zeros(M, N, device="cuda")
+    rc = L.dof_test_gemm_rows(P(X), Cc, A_CONV5, T, 1, 0, P(W), Cc * 5, 0, None, P(out), N, M, N, Cc * 5, 0, 0, None, S())
+    assert rc == 0
+    ref = O.conv1d_same_k5(X.double(), W.double()).reshape(M, N)
+    assert rel(out, ref) < 2e-6
+    # split view: columns [0,2H) u [3H,4H)
+    H = 16
+    G = rnd(M, 4 * H, seed=3)
+    Wi = rnd(3 * H, 20, seed=4)
+    dX = torch.zeros(M, 20, device="cuda")
+    rc = L.dof_test_gemm_rows(P(G), 4 * H, A_SPLIT, 2 * H, H, 0, P(Wi), 20, 1, None, P(dX), 20, M, 20, 3 * H, 0, 0, None, S())
+    assert rc == 0
+    Gi = torch.cat([G[:, :2 * H], G[:, 3 * H:]], 1).double()
+    assert rel(dX, Gi @ Wi.double()) < 2e-6
+    # time-shift view
+    for shift in (-1, 1):
+        out = torch.zeros(M, N, device="cuda")
+        Wt = rnd(N, Cc, seed=5)
+        rc = L.dof_test_gemm_rows(P(X), Cc, A_TSHIFT, T, shift, 0, P(Wt), Cc, 0, None, P(out), N, M, N, Cc, 0, 0, None, S())
+        assert rc == 0
+        Xs = torch.zeros_like(X)
+        if shift == -1:
+            Xs[:, 1:] = X[:, :-1]
+        else:
+            Xs[:, :-1] = X[:, 1:]
+        assert rel(out, Xs.reshape(M, Cc).double() @ Wt.double().t()) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,oT", [(5000, 96, 32, 0), (3333, 48, 64, 0), (257, 16, 448, 0), (999, 16, 32, 1),
+                                      (100000, 32, 15, 0), (64, 18, 6, 0)])
+def test_gemm_wgrad(L, M, N, K, oT):
+    Pm, Q = rnd(M, N, seed=1), rnd(M, K, seed=2)
+    dW = torch.zeros(N, K, device="cuda") if oT == 0 else torch.zeros(K, N, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    rc = L.dof_test_gemm_wgrad(P(Pm), N, A_PLAIN, 0, 0, P(Q), K, A_PLAIN, 0, 0, P(dW), dW.shape[1], oT, P(db), M, N, K, S())
+    assert rc == 0, L.dof_last_error()
+    ref = Pm.double().t() @ Q.double()
+    assert rel(dW if oT == 0 else dW.t(), ref) < 5e-6
+    assert rel(db, Pm.double().sum(0)) < 5e-6
+
+
+def test_gemm_wgrad_views(L):
+    S_, T, Cc, N = 41, 24, 12, 20
+    M = S_ * T
+    X = rnd(S_, T, Cc, seed=1)
+    dY = rnd(M, N, seed=2)
+    dW = torch.zeros(N, Cc * 5, device="cuda")
+    rc = L.dof_test_gemm_wgrad(P(dY), N, A_PLAIN, 0, 0, P(X), Cc, A_CONV5, T, 1, P(dW), Cc * 5, 0, None, M, N, Cc * 5, S())
+    assert rc == 0
+    Xd = X.double().requires_grad_(False)
+    Wd = torch.zeros(N, Cc, 5, device="cuda", dtype=torch.float64, requires_grad=True)
+    (O.conv1d_same_k5(Xd, Wd).reshape(M, N) * dY.double()).sum().backward()
+    assert rel(dW, Wd.grad.reshape(N, Cc * 5)) < 5e-6
+    # split P + shifted Q (the dW_hh pattern)
+    H = 8
+    G = rnd(M, 4 * H, seed=3)
+    Hs = rnd(S_, T, 2 * H, seed=4)
+    for d, shift in ((0, -1), (1, 1)):
+        dWh = torch.zeros(3 * H, H, device="cuda")
+        dbh = torch.zeros(3 * H, device="cuda")
+        Hd = Hs[:, :, d * H:(d + 1) * H]
+        rc = L.dof_test_gemm_wgrad(P(G), 4 * H, A_PLAIN, 0, 0, C.c_void_p(Hs.data_ptr() + d * H * 4), 2 * H, A_TSHIFT, T,
+                                   shift, P(dWh), H, 0, P(dbh), M, 3 * H, H, S())
+        assert rc == 0
+        Hsh = torch.zeros_like(Hd)
+        if shift == -1:
+            Hsh[:, 1:] = Hd[:, :-1]
+        else:
+            Hsh[:, :-1] = Hd[:, 1:]
+        ref = G[:, :3 * H].double().t() @ Hsh.reshape(M, H).double()
+        assert rel(dWh, ref) < 5e-6
+        assert rel(dbh, G[:, :3 * H].double().sum(0)) < 5e-6
+
+
+@pytest.mark.parametrize("R,W,relu_in", [(1000, 64, 0), (4097, 32, 1), (33, 12, 0), (500, 128, 0), (10, 256, 0)])
+def test_layernorm(L, R, W, relu_in):
+    x = rnd(R, W, seed=1)
+    if relu_in:
+        x = torch.relu(x)
+    w, b, dy = rnd(W, seed=2), rnd(W, seed=3), rnd(R, W, seed=4)
+    y, dx = torch.zeros_like(x), torch.zeros_like(x)
+    mu, rs = torch.zeros(R, device="cuda"), torch.zeros(R, device="cuda")
+    dw, db = torch.zeros(W, device="cuda"), torch.zeros(W, device="cuda")
+    rc = L.dof_test_layernorm(P(x), P(w), P(b), 1e-3, P(y), P(mu), P(rs), P(dy), P(dx), P(dw), P(db), R, W, relu_in, S())
+    assert rc == 0, L.dof_last_error()
+    xd = x.double().requires_grad_(True)
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = O.layer_norm(xd, wd, bd, 1e-3)
+    (yr * dy.double()).sum().backward()
+    assert rel(y, yr) < 2e-6
+    gx = xd.grad * (x > 0) if relu_in else xd.grad
+    assert rel(dx, gx) < 1e-5
+    assert rel(dw, wd.grad) < 1e-5 and rel(db, bd.grad) < 1e-5
+
+
+def _gru_case(L, S_, T, I, H, lens, final_only, seed):
+    dev = "cuda"
+    X = rnd(S_, T, I, seed=seed)
+    k = 1.0 / H ** 0.5
+    prm = {}
+    for d in ("", "_reverse"):
+        prm["weight_ih_l0" + d] = rnd(3 * H, I, seed=seed + 1 + len(d)) * k
+        prm["weight_hh_l0" + d] = rnd(3 * H, H, seed=seed + 2 + len(d)) * k
+        prm["bias_ih_l0" + d] = rnd(3 * H, seed=seed + 3 + len(d)) * k
+        prm["bias_hh_l0" + d] = rnd(3 * H, seed=seed + 4 + len(d)) * k
+    len_t = torch.full((S_,), T, dtype=torch.int32, device=dev) if lens is None else lens.to(dev).int()
+    # ---- reference (fp64, oracle building block)
+    Xd = X.double().requires_grad_(True)
+    pd = {k_: v.double().requires_grad_(True) for k_, v in prm.items()}
+    out_ref, hn_ref = O.bigru(Xd, len_t.long(), pd, "")
+    R1, R2 = rnd(S_, T, 2 * H, seed=seed + 9).double(), rnd(S_, 2 * H, seed=seed + 10).double()
+    loss = (hn_ref * R2).sum() if final_only else (out_ref * R1).sum()
+    loss.backward()
+    # ---- ours
+    gi = [(X @ prm["weight_ih_l0" + d].t() + prm["bias_ih_l0" + d]).contiguous() for d in ("", "_reverse")]
+    hout = torch.full((S_, T, 2 * H), 7.0, device=dev)
+    gt = [torch.zeros(S_, T, 4 * H, device=dev) for _ in range(2)]
+    hn = torch.zeros(S_, 2 * H, device=dev)
+    rc = L.dof_test_gru_fwd(P(gi[0]), P(gi[1]), T * 3 * H, 3 * H, P(prm["weight_hh_l0"]), P(prm["weight_hh_l0_reverse"]),
+                            P(prm["bias_hh_l0"]), P(prm["bias_hh_l0_reverse"]), P(len_t), P(hout), P(gt[0]), P(gt[1]),
+                            P(hn), S_, T, H, S())
+    assert rc == 0, L.dof_last_error()
+    assert rel(hout, out_ref) < 5e-6, ("hout", rel(hout, out_ref))
+    assert rel(hn, hn_ref) < 5e-6, ("hn", rel(hn, hn_ref))
+    dg = [torch.full((S_, T, 4 * H), 3.0, device=dev) for _ in range(2)]
+    dout = None if final_only else R1.float().contiguous()
+    dhn = R2.float().contiguous() if final_only else None
+    rc = L.dof_test_gru_bwd(P(prm["weight_hh_l0"]), P(prm["weight_hh_l0_reverse"]), P(len_t), P(hout), P(gt[0]), P(gt[1]),
+                            P(dout), P(dhn), P(dg[0]), P(dg[1]), S_, T, H, S())
+    assert rc == 0, L.dof_last_error()
+    dX = torch.zeros(S_, T, I, device=dev, dtype=torch.float64)
+    for di, d in enumerate(("", "_reverse")):
+        G = dg[di].double()
+        dGi = torch.cat([G[..., :2 * H], G[..., 3 * H:]], -1)
+        dGh = G[..., :3 * H]
+        dX += dGi @ prm["weight_ih_l0" + d].double()
+        assert rel(dGi.sum((0, 1)), pd["bias_ih_l0" + d].grad) < 2e-5, ("db_ih", d)
+        assert rel(dGh.sum((0, 1)), pd["bias_hh_l0" + d].grad) < 2e-5, ("db_hh", d)
+        assert rel(torch.einsum("stg,sti->gi", dGi, X.double()), pd["weight_ih_l0" + d].grad) < 2e-5, ("dW_ih", d)
+        Hd = hout[..., di * H:(di + 1) * H].double()
+        Hp = torch.zeros_like(Hd)
+        if di == 0:
+            Hp[:, 1:] = Hd[:, :-1]
+        else:
+            Hp[:, :-1] = Hd[:, 1:]
+        assert rel(torch.einsum("stg,sth->gh", dGh, Hp), pd["weight_hh_l0" + d].grad) < 2e-5, ("dW_hh", d)
+    assert rel(dX, Xd.grad) < 2e-5, ("dX", rel(dX, Xd.grad))
+
+
+@pytest.mark.parametrize("S_,T,I,H", [(300, 25, 32, 32), (130, 25, 64, 16), (77, 24, 12, 12), (50, 24, 24, 6),
+                                      (64, 25, 16, 8), (40, 10, 20, 64), (33, 25, 48, 24), (20, 7, 9, 5)])
+def test_gru_full_sequences(L, S_, T, I, H):
+    _gru_case(L, S_, T, I, H, None, False, seed=10)
+    _gru_case(L, S_, T, I, H, None, True, seed=20)
+
+
+def test_gru_packed_lengths(L):
+    S_, T = 97, 25
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(0, T + 1, (S_,), generator=g)
+    lens[0], lens[1], lens[2] = 0, 1, T
+    _gru_case(L, S_, T, 32, 32, lens, False, seed=30)
+    _gru_case(L, S_, T, 64, 16, lens, True, seed=40)
