@@ -12,6 +12,7 @@
 #include "loss.cuh"
 
 thread_local char g_dof_err[512] = {0};
+DofProf g_prof;
 
 // ---------------------------------------------------------------------------
 // state layout  (reference VaDEPT.state_dict() order)
@@ -404,7 +405,8 @@ static int ln_fwd(const float* x, const float* w, const float* b, float* y, floa
     long long blocks = (R + 7) / 8;
     int grid = (int)(blocks < (long long)sm * 16 ? blocks : (long long)sm * 16);
     if (grid < 1) return DOF_OK;
-    ln_fwd_kernel<<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W);
+    { ProfScope ps("ln_fwd", st, 0.0, 8.0 * R * W);
+    ln_fwd_kernel<<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -413,7 +415,8 @@ static int ln_bwd(const float* dy, const float* x, const float* mu, const float*
     long long blocks = (R + 7) / 8;
     int grid = (int)(blocks < (long long)sm * 4 ? blocks : (long long)sm * 4);
     if (grid < 1) return DOF_OK;
-    ln_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
+    { ProfScope ps("ln_bwd", st, 0.0, 12.0 * R * W);
+    ln_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -438,7 +441,8 @@ static int enc_block_forward(dof_handle* h, int b, const float* state, const flo
     ca.x = xin; ca.gidx = w.gidx; ca.w = state + P.conv; ca.Xs = w.Xs; ca.Cv = w.Cv; ca.len = w.len;
     ca.B = B; ca.T = T; ca.G = w.G; ca.F = w.Fin; ca.C = C1;
     size_t smem = ((size_t)T * w.G * w.Fin + (size_t)C1 * w.Fin * 5 + (size_t)w.G * T) * 4;
-    enc_conv_kernel<<<B, 256, smem, st>>>(ca);
+    { ProfScope ps("enc_conv", st);
+    enc_conv_kernel<<<B, 256, smem, st>>>(ca); }
     DOF_LAUNCH_CHECK();
     DOF_TRY(gru_input_proj(state, P.g1, mv_plain(w.Cv, C1), M, C1, H1, w.Gi1, st));
     GruFwdArgs f;
@@ -497,7 +501,8 @@ static int encoder_forward(dof_handle* h, const float* state, const float* x, co
         DOF_CUDA(cudaFuncSetAttribute(cens_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr = true;
     }
-    cens_fwd_kernel<<<B, 128, smem, st>>>(ca);
+    { ProfScope ps("cens_fwd", st);
+    cens_fwd_kernel<<<B, 128, smem, st>>>(ca); }
     DOF_LAUNCH_CHECK();
     GemmArgs g[2];
     g[0] = gemm_args(mv_plain(h->Pn, 2 * D), state + L.node_kernel, D, 1, state + L.node_bias, h->On, D, B * N, D, 2 * D);
@@ -514,7 +519,8 @@ static int encoder_forward(dof_handle* h, const float* state, const float* x, co
     la.eps = eps; la.gmm_mu = state + L.gmm_mu; la.gmm_lv = state + L.gmm_lv; la.prior = state + L.prior;
     la.zm = h->zm; la.pre = h->pre; la.lv = h->lv; la.z = h->z; la.q = h->q; la.B = B; la.D = D; la.K = K;
     size_t lsm = ((size_t)2 * D * D + 2 * D + 2 * (size_t)K * D + K) * 4;
-    latent_fwd_kernel<<<cdiv(B, 64), 64, lsm, st>>>(la);
+    { ProfScope ps("latent_fwd", st);
+    latent_fwd_kernel<<<cdiv(B, 64), 64, lsm, st>>>(la); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -523,7 +529,8 @@ static int decoder_forward(dof_handle* h, const float* state, const float* x, in
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T;
-    row_valid_len_kernel<<<cdiv(B, 128), 128, 0, st>>>(x, h->lenD, B, T, NF);
+    { ProfScope ps("row_valid_len", st);
+    row_valid_len_kernel<<<cdiv(B, 128), 128, 0, st>>>(x, h->lenD, B, T, NF); }
     DOF_LAUNCH_CHECK();
     DOF_TRY(gru_input_proj(state, L.dg1, mv_plain(h->z, D), B, D, D, h->GiD1, st));
     GruFwdArgs f;
@@ -621,7 +628,8 @@ static int decoder_backward(dof_handle* h, const float* state, float* grad, int 
     DOF_TRY(ln_bwd(h->dYD3, h->Cd, h->muD3, h->rsD3, state + L.dn3w, h->dCd, grad + L.dn3w, grad + L.dn3b, M, 2 * D, 1, sm, st));
     WGradArgs w1 = wgrad_args(mv_plain(h->dCd, 2 * D), mv_conv5(h->YD2, 4 * D, T, +1), grad + L.dconv, 20 * D, 0, nullptr, M, 2 * D, 20 * D);
     DOF_TRY(launch_gemm_wgrad(&w1, 1, st, sm));
-    conv_w_transpose_kernel<<<cdiv(2 * D * 4 * D * 5, 256), 256, 0, st>>>(state + L.dconv, h->Wt, 2 * D, 4 * D);
+    { ProfScope ps("conv_w_transpose", st);
+    conv_w_transpose_kernel<<<cdiv(2 * D * 4 * D * 5, 256), 256, 0, st>>>(state + L.dconv, h->Wt, 2 * D, 4 * D); }
     DOF_LAUNCH_CHECK();
     GemmArgs g1 = gemm_args(mv_conv5(h->dCd, 2 * D, T, -1), h->Wt, 10 * D, 0, nullptr, h->dYD2, 4 * D, M, 4 * D, 10 * D);
     DOF_TRY(launch_gemm_rows(&g1, 1, st));
@@ -639,7 +647,8 @@ static int decoder_backward(dof_handle* h, const float* state, float* grad, int 
     b.len = h->lenD; b.Hout = h->HD1; b.dOut = h->dHD1; b.dHn = nullptr; b.S = B; b.T = T; b.H = D;
     DOF_TRY(launch_gru_bwd(b, st));
     for (int d = 0; d < 2; d++) {
-        sum_over_t_kernel<<<cdiv((long long)B * 4 * D, 256), 256, 0, st>>>(h->dGD1[d], h->dGs[d], B, T, 4 * D, 0);
+        { ProfScope ps("sum_over_t", st);
+        sum_over_t_kernel<<<cdiv((long long)B * 4 * D, 256), 256, 0, st>>>(h->dGD1[d], h->dGs[d], B, T, 4 * D, 0); }
         DOF_LAUNCH_CHECK();
     }
     DOF_TRY(gru_param_grads(h, L.dg1, grad, state, h->dGD1, mv_plain(h->z, D), B, h->dGs, h->HD1, M, T, D, D, h->dz_dec,
@@ -715,7 +724,8 @@ static int encoder_backward(dof_handle* h, const float* state, float* grad, int 
     ca.dwn = grad + L.node_weights; ca.dwe = grad + L.edge_weights;
     size_t smem = (cens_smem_floats(N, E, 2 * D) + (size_t)(N + E) * 2 * D + (size_t)N * N + (size_t)E * E + N + E) * 4;
     if (smem > 220 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "graph too large for the CensNet backward kernel");
-    cens_bwd_kernel<<<B, 128, smem, st>>>(ca);
+    { ProfScope ps("cens_bwd", st);
+    cens_bwd_kernel<<<B, 128, smem, st>>>(ca); }
     DOF_LAUNCH_CHECK();
     DOF_TRY(enc_block_backward(h, 0, state, grad, B, st));
     DOF_TRY(enc_block_backward(h, 1, state, grad, B, st));
@@ -774,7 +784,8 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
     DOF_CUDA(cudaMemsetAsync(h->stats, 0, (size_t)SL.total * sizeof(double), st));
     const long long nrec = (long long)B * T * NF;
     int rgrid = (int)((nrec + 255) / 256 < (long long)h->sm_count * 8 ? (nrec + 255) / 256 : (long long)h->sm_count * 8);
-    recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->stats);
+    { ProfScope ps("recon", st, 0.0, 12.0 * nrec);
+    recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->stats); }
     DOF_LAUNCH_CHECK();
     LossArgs la;
     memset(&la, 0, sizeof(la));
@@ -794,13 +805,16 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
         attr = true;
     }
     int lgrid = cdiv(B, LS_WARPS) < h->sm_count * 4 ? cdiv(B, LS_WARPS) : h->sm_count * 4;
-    loss_stats_kernel<<<lgrid, LS_WARPS * 32, loss_stats_smem_floats(D, K) * 4, st>>>(la);
+    { ProfScope ps("loss_stats", st);
+    loss_stats_kernel<<<lgrid, LS_WARPS * 32, loss_stats_smem_floats(D, K) * 4, st>>>(la); }
     DOF_LAUNCH_CHECK();
-    loss_finalize_kernel<<<1, 256, loss_finalize_smem_bytes(D, K), st>>>(la);
+    { ProfScope ps("loss_finalize", st);
+    loss_finalize_kernel<<<1, 256, loss_finalize_smem_bytes(D, K), st>>>(la); }
     DOF_LAUNCH_CHECK();
     // ---- backward
     DOF_TRY(decoder_backward(h, state, grad, B, st));
-    loss_grad_kernel<<<lgrid, LS_WARPS * 32, loss_grad_smem_floats(D, K) * 4, st>>>(la);
+    { ProfScope ps("loss_grad", st);
+    loss_grad_kernel<<<lgrid, LS_WARPS * 32, loss_grad_smem_floats(D, K) * 4, st>>>(la); }
     DOF_LAUNCH_CHECK();
     DOF_TRY(encoder_backward(h, state, grad, B, st));
     h->lastB = B;
@@ -822,7 +836,8 @@ int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m,
         a.bc2_sqrt[g] = (float)sqrt(1.0 - pow((double)opt->beta2, s));
     }
     a.clip = opt->clip_value; a.gscale = opt->grad_scale; a.beta1 = opt->beta1; a.beta2 = opt->beta2; a.eps = opt->eps;
-    clip_adam_kernel<<<cdiv(a.n, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    { ProfScope ps("clip_adam", (cudaStream_t)stream, 0.0, 28.0 * a.n);
+    clip_adam_kernel<<<cdiv(a.n, 256), 256, 0, (cudaStream_t)stream>>>(a); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -833,6 +848,41 @@ const void* dof_debug_tensor(dof_handle* h, const char* name, int64_t* numel_out
     if (it == h->dbg.end()) return nullptr;
     if (numel_out) *numel_out = it->second.second;
     return it->second.first;
+}
+
+long long dof_launch_count(void) { return g_prof.launches; }
+
+int dof_profile_begin(void) {
+    for (auto& r : g_prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.recs.clear();
+    g_prof.enabled = true;
+    return DOF_OK;
+}
+
+// Synchronises the device, aggregates the recorded launches per kernel class and writes
+// "name count total_ms algorithmic_flops algorithmic_bytes\n" lines into out.
+int dof_profile_end(char* out, size_t cap) {
+    g_prof.enabled = false;
+    DOF_CUDA(cudaDeviceSynchronize());
+    struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : g_prof.recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        Agg& e = agg[r.name];
+        e.n++; e.ms += ms; e.flops += r.flops; e.bytes += r.bytes;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.recs.clear();
+    std::string txt;
+    char line[160];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s %lld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms,
+                 kv.second.flops, kv.second.bytes);
+        txt += line;
+    }
+    if (out && cap > 0) { strncpy(out, txt.c_str(), cap - 1); out[cap - 1] = 0; }
+    return DOF_OK;
 }
 
 // ---- op-level test hooks -----------------------------------------------------

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <vector>
 
 #define DOF_OK 0
 #define DOF_ERR_ARG -1
@@ -35,6 +36,27 @@ extern thread_local char g_dof_err[512];
         int _r = (expr);           \
         if (_r != DOF_OK) return _r; \
     } while (0)
+
+// ---- optional per-kernel-class CUDA-event timing + launch counting ---------------
+struct DofProfRec { const char* name; cudaEvent_t a, b; double flops, bytes; };
+struct DofProf {
+    bool enabled = false;
+    long long launches = 0;
+    std::vector<DofProfRec> recs;
+};
+extern DofProf g_prof;
+struct ProfScope {
+    const char* name; cudaStream_t st; cudaEvent_t a, b; bool on; double flops, bytes;
+    // flops / bytes: ALGORITHMIC work of this launch (unpadded), used for roofline reporting
+    ProfScope(const char* n, cudaStream_t s, double fl = 0.0, double by = 0.0)
+        : name(n), st(s), on(g_prof.enabled), flops(fl), bytes(by) {
+        g_prof.launches++;
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(b, st); g_prof.recs.push_back({name, a, b, flops, bytes}); }
+    }
+};
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

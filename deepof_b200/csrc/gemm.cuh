@@ -182,6 +182,9 @@ static int launch_gemm_rows(const GemmArgs* gs, int nbatch, cudaStream_t st) {
     if (M <= 0 || N <= 0) return DOF_OK;
     int BN = N <= 16 ? 16 : N <= 32 ? 32 : N <= 48 ? 48 : N <= 64 ? 64 : 96;
     dim3 grid(cdiv(M, GEMM_BM), cdiv(N, BN), nbatch);
+    double fl = 0.0;
+    for (int i = 0; i < nbatch; i++) fl += 2.0 * gs[i].M * gs[i].N * gs[i].K;
+    ProfScope ps("gemm_rows", st, fl);
     switch (BN) {
         case 16: gemm_rows_kernel<16><<<grid, 16 * 4, 0, st>>>(gb); break;
         case 32: gemm_rows_kernel<32><<<grid, 16 * 8, 0, st>>>(gb); break;
@@ -298,6 +301,9 @@ static int launch_gemm_wgrad(const WGradArgs* gs, int nbatch, cudaStream_t st, i
     int msplit = want < maxsplit ? want : maxsplit;
     if (msplit < 1) msplit = 1;
     dim3 grid(msplit, ntiles * ktiles, nbatch);
+    double fl = 0.0;
+    for (int i = 0; i < nbatch; i++) fl += 2.0 * gs[i].M * gs[i].N * gs[i].K;
+    ProfScope ps("gemm_wgrad", st, fl);
     gemm_wgrad_kernel<<<grid, 256, 0, st>>>(wb, ktiles);
     DOF_LAUNCH_CHECK();
     return DOF_OK;

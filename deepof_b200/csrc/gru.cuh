@@ -56,7 +56,7 @@ gru_fwd_kernel(const GruFwdArgs a) {
     const int jg = tid % NJ, mg = tid / NJ;
     const int j0 = jg * 4;
     const int s0 = blockIdx.x * MT + mg * GRU_TM;
-    const bool vec = (H & 3) == 0;
+    const bool vec = ((H & 3) == 0) && (j0 + 3 < H);   // HP may exceed H: idle j-groups use the guarded path
     const float* Whh = a.Whh[dir];
     const float* bhh = a.bhh[dir];
     for (int i = tid; i < HP * 3 * HP; i += NT) {
@@ -205,7 +205,7 @@ gru_bwd_kernel(const GruBwdArgs a) {
     const int jg = tid % NJ, mg = tid / NJ;
     const int j0 = jg * 4;
     const int s0 = blockIdx.x * MT + mg * GRU_TM;
-    const bool vec = (H & 3) == 0;
+    const bool vec = ((H & 3) == 0) && (j0 + 3 < H);   // HP may exceed H: idle j-groups use the guarded path
     const float* Whh = a.Whh[dir];
     for (int i = tid; i < 3 * HP * HP; i += NT) {
         int c = i / HP, k = i % HP;
@@ -313,6 +313,8 @@ static int gru_fwd_launch_t(const GruFwdArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid(cdiv(a.S, MT), 2);
+    ProfScope ps(HP == 32 ? "gru_fwd_h32" : HP == 16 ? "gru_fwd_h16" : "gru_fwd_other", st,
+                 2.0 * 2.0 * a.S * a.T * 3.0 * a.H * a.H);
     gru_fwd_kernel<HP, MT><<<grid, (MT / GRU_TM) * (HP / 4), smem, st>>>(a);
     DOF_LAUNCH_CHECK();
     return DOF_OK;
@@ -326,6 +328,8 @@ static int gru_bwd_launch_t(const GruBwdArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid(cdiv(a.S, MT), 2);
+    ProfScope ps(HP == 32 ? "gru_bwd_h32" : HP == 16 ? "gru_bwd_h16" : "gru_bwd_other", st,
+                 2.0 * 2.0 * a.S * a.T * 3.0 * a.H * a.H);
     gru_bwd_kernel<HP, MT><<<grid, (MT / GRU_TM) * (HP / 4), smem, st>>>(a);
     DOF_LAUNCH_CHECK();
     return DOF_OK;

@@ -1,0 +1,146 @@
+"""Host-side training loop pieces for the B200-native VaDE path.
+
+``VaDETrainer`` plays the role of the reference's ``step_vade`` + ``train_one_epoch_indexed``
+body (reference ``deepof/clustering/training.py:104-187, 231-309``): per batch
+forward -> VadeLoss -> backward -> [gradient all-reduce] -> clip_grad_value_(0.75) -> Adam,
+with the KL weight schedule of ``Dynamic_weight_manager`` (``losses.py:290-351``).
+
+Data parallel contract = the reference's DDP (``model_utils_new.py:196-226``):
+one process per GPU, replicas hold identical parameters, every batch statistic is
+rank-local, ONE all-reduce(sum) of the flat fp32 gradient buffer per step; the 1/world
+scaling is folded into the fused clip+Adam kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from .vade import VaDEB200, VadeLossCfg
+
+
+class KLSchedule:
+    """``Dynamic_weight_manager`` (reference losses.py:290-351), stepped once per batch."""
+
+    def __init__(self, n_batches_per_epoch: int, mode: str = "tf_sigmoid", warmup_epochs: int = 5,
+                 max_weight: float = 1.0, cooldown_epochs: int = 5, end_weight: float = 0.2,
+                 at_max_epochs: int = 0):
+        self.mode = mode
+        self.warm = max(1, warmup_epochs * n_batches_per_epoch)
+        self.atmax = max(0, at_max_epochs * n_batches_per_epoch)
+        self.cool = max(0, cooldown_epochs * n_batches_per_epoch)
+        self.max_weight, self.end_weight = float(max_weight), float(end_weight)
+        self.current_iteration = 0
+
+    def _shape(self, p: float) -> float:
+        p = float(max(0.0, min(1.0, p)))
+        if self.mode == "sigmoid":
+            return 1.0 / (1.0 + math.exp(-12.0 * (p - 0.5)))
+        if self.mode == "tf_sigmoid":
+            return 1.0 / (1.0 + math.exp(-((2.0 * p - 1.0) / max(1e-2, p - p * p))))
+        return p
+
+    def get_weight(self) -> float:
+        it = self.current_iteration
+        total = self.warm + self.atmax + self.cool
+        if it >= total:
+            return self.end_weight
+        if self.atmax > 0 and self.warm <= it < self.warm + self.atmax:
+            return self.max_weight
+        if it <= self.warm:
+            return self.max_weight * self._shape(it / self.warm)
+        if self.cool <= 0:
+            return self.max_weight
+        pc = (it - (self.warm + self.atmax)) / self.cool
+        return (1.0 - pc) * self.max_weight + pc * self.end_weight
+
+    def step(self):
+        self.current_iteration += 1
+
+
+class VaDETrainer:
+    def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
+                 max_batch: int = 4096, seed: Optional[int] = None, world_size: int = 1, rank: int = 0,
+                 kmeans_loss: float = 1.0, device: Optional[int] = None):
+        self.model = VaDEB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, n_components,
+                              kmeans_loss=kmeans_loss, device=device, max_batch=max_batch, training=True, seed=seed)
+        self.world_size, self.rank = int(world_size), int(rank)
+        self.loss_cfg = VadeLossCfg.pretrain_defaults(n_components)
+        self.loss_cfg.model_kmeans_weight = float(kmeans_loss)
+        self.lr_base, self.lr_gmm = 1e-3, 0.0
+        self.kl_schedule: Optional[KLSchedule] = None
+        self.active = (True, True, True)   # encoder+latent / decoder / GMM groups
+        self.tau_star = None
+        self.class_weight = None
+        self.teacher_marginal = None
+        dev = self.model.device
+        T, N, F = self.model.input_shape
+        _, E, Fe = self.model.edge_feature_shape
+        self._xs = torch.empty(max_batch, T, N, F, device=dev)
+        self._as = torch.empty(max_batch, T, E, Fe, device=dev)
+        self._loss_host = torch.zeros(16, pin_memory=True)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.model.state, src=0)   # DDP constructor broadcast (reference training.py:1567)
+
+    # ---- phase control (reference training.py:1579-1653, 1746-1767)
+    def set_phase(self, phase: str, kl_weight: Optional[float] = None, lr_base: Optional[float] = None,
+                  lr_gmm: Optional[float] = None, kl_schedule: Optional[KLSchedule] = None):
+        K = self.model.n_components
+        mk = self.loss_cfg.model_kmeans_weight
+        self.loss_cfg = VadeLossCfg.pretrain_defaults(K) if phase == "pretrain" else VadeLossCfg.main_defaults(K)
+        self.loss_cfg.model_kmeans_weight = mk
+        self.model.set_pretrain_mode(phase == "pretrain")
+        if kl_weight is not None:
+            self.loss_cfg.kl_weight = float(kl_weight)
+        self.kl_schedule = kl_schedule
+        if lr_base is not None:
+            self.lr_base = float(lr_base)
+        if lr_gmm is not None:
+            self.lr_gmm = float(lr_gmm)
+        # rebuilding the optimizer resets Adam state in the reference (training.py:1648-1653)
+        self.model.adam_m.zero_()
+        self.model.adam_v.zero_()
+        self.model.adam_steps = [0, 0, 0, 0]
+
+    def set_teacher(self, tau_star: torch.Tensor, lambda_distill: float, class_weight=None, teacher_marginal=None):
+        self.tau_star = torch.as_tensor(tau_star, dtype=torch.float32).to(self.model.device)
+        self.loss_cfg.lambda_distill = float(lambda_distill)
+        self.class_weight, self.teacher_marginal = class_weight, teacher_marginal
+
+    # ---- one step
+    def train_step_device(self, x: torch.Tensor, a: torch.Tensor, idx: Optional[torch.Tensor] = None, eps=None,
+                          mc_eps=None) -> torch.Tensor:
+        """x, a already on the device.  Returns the device log vector (no host sync)."""
+        m = self.model
+        if self.kl_schedule is not None:
+            self.loss_cfg.kl_weight = self.kl_schedule.get_weight()
+        tau = None
+        if self.tau_star is not None and self.loss_cfg.lambda_distill > 0.0 and idx is not None:
+            tau = self.tau_star[idx.to(m.device)]
+        logs = m.loss_grad(x, a, self.loss_cfg, eps=eps, mc_eps=mc_eps, tau_batch=tau, class_weight=self.class_weight,
+                           teacher_marginal=self.teacher_marginal)
+        scale = 1.0
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(m.grad, op=dist.ReduceOp.SUM)
+            scale = 1.0 / self.world_size
+        m.adam_step(self.lr_base, self.lr_gmm, grad_scale=scale, active=self.active)
+        if self.kl_schedule is not None:
+            self.kl_schedule.step()
+        return logs
+
+    def train_step(self, x_host: torch.Tensor, a_host: torch.Tensor, idx: Optional[torch.Tensor] = None) -> float:
+        """Public end-to-end step from HOST tensors: H2D copy, step, D2H read of total_loss."""
+        B = x_host.shape[0]
+        xs, as_ = self._xs[:B], self._as[:B]
+        xs.copy_(x_host, non_blocking=True)
+        as_.copy_(a_host, non_blocking=True)
+        logs = self.train_step_device(xs, as_, idx)
+        self._loss_host.copy_(logs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_host[0])
+
+    def logs(self) -> Dict[str, float]:
+        return self.model.logs_dict()

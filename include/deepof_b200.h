@@ -147,6 +147,12 @@ int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m,
  * "z_log_var","q","loc","len_node","len_edge". */
 const void* dof_debug_tensor(dof_handle* h, const char* name, int64_t* numel_out);
 
+/* ---- measurement support: number of kernels this library has launched so far, and optional
+ * per-kernel-class CUDA-event timing (events bracket each launch on its stream). */
+long long dof_launch_count(void);
+int dof_profile_begin(void);
+int dof_profile_end(char* out, size_t cap);
+
 /* ---- op-level test hooks (used by tests/ to check single kernels against torch) ---------- */
 int dof_test_gemm_rows(const float* A, int lda, int mode, int p0, int p1, int p2, const float* W, int ldw,
                        int wT, const float* bias, float* C, int ldc, int M, int N, int K, int relu,

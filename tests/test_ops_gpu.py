@@ -215,7 +215,7 @@ def _gru_case(L, S_, T, I, H, lens, final_only, seed):
 
 
 @pytest.mark.parametrize("S_,T,I,H", [(300, 25, 32, 32), (130, 25, 64, 16), (77, 24, 12, 12), (50, 24, 24, 6),
-                                      (64, 25, 16, 8), (40, 10, 20, 64), (33, 25, 48, 24), (20, 7, 9, 5)])
+                                      (64, 25, 16, 8), (40, 10, 20, 64), (33, 25, 48, 24), (20, 7, 9, 5), (45, 12, 8, 4), (45, 12, 8, 8)])
 def test_gru_full_sequences(L, S_, T, I, H):
     _gru_case(L, S_, T, I, H, None, False, seed=10)
     _gru_case(L, S_, T, I, H, None, True, seed=20)

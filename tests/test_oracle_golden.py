@@ -117,3 +117,28 @@ def test_group_reshape_law_examples():
     assert got == [(0, 0), (14, 0), (3, 1), (17, 1), (6, 2), (20, 2)]
     # it is a permutation of the window
     assert sorted(idx.flatten().tolist()) == list(range(25 * 14 * 3))
+
+
+@pytest.mark.parametrize("case", ["cfg2_main", "odd_pretrain"])
+def test_aten_gru_variant_matches_golden(case):
+    """The ATen-GRU variant of the oracle (used only as the timed CPU baseline in bench.py)
+    reproduces the reference's logged loss terms and raw gradient too."""
+    g = load_golden(case)
+    p = sub(g, "p/")
+    x, a = torch.from_numpy(g["x"]), torch.from_numpy(g["a"])
+    graph = O.graph_operators(g["adjacency"])
+    cfg = _cfg(g)
+    cfg.kl_weight = float(g["s0/klw"])
+    mc = torch.from_numpy(g["s0/mc_eps"]) if "s0/mc_eps" in g else None
+    O.USE_ATEN_GRU = True
+    try:
+        logs, grads, _ = O.train_step(x, a, p, graph, g["dims"]["D"], cfg, eps=torch.from_numpy(g["s0/eps"]), mc_eps=mc)
+    finally:
+        O.USE_ATEN_GRU = False
+    for k in O.LOG_KEYS:
+        ref = float(g[f"s0/log/{k}"])
+        assert abs(logs[k] - ref) <= 2e-5 * max(1.0, abs(ref)), (k, logs[k], ref)
+    gref = sub(g, "g/")
+    flat = torch.cat([grads[k].flatten() for k in gref])
+    flat_ref = torch.cat([gref[k].flatten() for k in gref])
+    assert rel_l2(flat, flat_ref) < 1e-5
