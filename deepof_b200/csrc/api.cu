@@ -7,6 +7,7 @@
 #include "../../include/deepof_b200.h"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "tc_gemm.cuh"
 #include "gru.cuh"
 #include "layers.cuh"
 #include "loss.cuh"
@@ -368,6 +369,7 @@ int dof_create(const dof_config* cfg, int device, int max_batch, int training, v
     dof_handle* h = new dof_handle();
     h->cfg = *cfg; h->L = build_layout(*cfg); h->device = device; h->sm_count = prop.multiProcessorCount;
     h->max_batch = max_batch; h->training = training; h->lastB = 0;
+    g_sm_count = h->sm_count;
     init_derived(h);
     size_t need = dof_workspace_bytes(cfg, max_batch, training);
     if (workspace_bytes < need) { delete h; DOF_FAIL(DOF_ERR_WORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, need); }
@@ -851,6 +853,14 @@ const void* dof_debug_tensor(dof_handle* h, const char* name, int64_t* numel_out
 }
 
 long long dof_launch_count(void) { return g_prof.launches; }
+
+// 1 = use the tcgen05 GEMM kernels where eligible (default), 0 = fp32 SIMT kernels only
+int dof_set_tensor_cores(int enable) {
+    tc_enabled();
+    int old = g_tc_enabled ? 1 : 0;
+    g_tc_enabled = enable != 0;
+    return old;
+}
 
 int dof_profile_begin(void) {
     for (auto& r : g_prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

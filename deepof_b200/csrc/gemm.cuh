@@ -170,7 +170,7 @@ gemm_rows_kernel(const GemmBatch gb) {
     }
 }
 
-static int launch_gemm_rows(const GemmArgs* gs, int nbatch, cudaStream_t st) {
+static int launch_gemm_rows_simt(const GemmArgs* gs, int nbatch, cudaStream_t st) {
     GemmBatch gb;
     memset(&gb, 0, sizeof(gb));
     int M = 0, N = 0;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const WGradBatch wb, in
     }
 }
 
-static int launch_gemm_wgrad(const WGradArgs* gs, int nbatch, cudaStream_t st, int sm_count) {
+static int launch_gemm_wgrad_simt(const WGradArgs* gs, int nbatch, cudaStream_t st, int sm_count) {
     WGradBatch wb;
     memset(&wb, 0, sizeof(wb));
     int M = 0, N = 0, K = 0;

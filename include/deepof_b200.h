@@ -150,6 +150,9 @@ const void* dof_debug_tensor(dof_handle* h, const char* name, int64_t* numel_out
 /* ---- measurement support: number of kernels this library has launched so far, and optional
  * per-kernel-class CUDA-event timing (events bracket each launch on its stream). */
 long long dof_launch_count(void);
+/* 1 (default): GEMMs run on tcgen05 tensor cores (3xTF32, fp32-class accuracy) where eligible;
+ * 0: fp32 SIMT kernels only.  Returns the previous setting.  Env DOF_DISABLE_TC=1 sets 0. */
+int dof_set_tensor_cores(int enable);
 int dof_profile_begin(void);
 int dof_profile_end(char* out, size_t cap);
 

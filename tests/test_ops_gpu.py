@@ -228,3 +228,103 @@ def test_gru_packed_lengths(L):
     lens[0], lens[1], lens[2] = 0, 1, T
     _gru_case(L, S_, T, 32, 32, lens, False, seed=30)
     _gru_case(L, S_, T, 64, 16, lens, True, seed=40)
+
+
+# ---------------------------------------------------------------------------
+# tcgen05 (3xTF32) GEMMs: same hooks, shapes large enough to be dispatched to the
+# tensor-core kernels; the per-kernel profile proves which kernel ran.
+# ---------------------------------------------------------------------------
+def _ran(L, fn):
+    L.dof_profile_begin()
+    fn()
+    buf = C.create_string_buffer(4096)
+    L.dof_profile_end(buf, 4096)
+    return {ln.split()[0] for ln in buf.value.decode().strip().split("\n") if ln}
+
+
+@pytest.mark.parametrize("M,N,K,wT", [(20000, 96, 32, 0), (20000, 48, 64, 0), (20000, 64, 48, 1), (20000, 32, 96, 1),
+                                      (5000, 42, 32, 0), (4097, 16, 8, 0), (3000, 256, 128, 0), (2048, 8, 4, 0)])
+def test_tc_gemm_rows(L, M, N, K, wT):
+    L.dof_set_tensor_cores(1)
+    A = rnd(M, K, seed=1)
+    W = rnd(N, K, seed=2) if wT == 0 else rnd(K, N, seed=2)
+    bias = rnd(N, seed=3)
+    Cout = torch.zeros(M, N, device="cuda")
+    names = _ran(L, lambda: L.dof_test_gemm_rows(P(A), K, A_PLAIN, 0, 0, 0, P(W), W.shape[1], wT, P(bias), P(Cout), N, M,
+                                                 N, K, 0, 0, None, S()))
+    assert "gemm_rows_tc" in names, names
+    ref = A.double() @ (W.double().t() if wT == 0 else W.double()) + bias.double()
+    print("tc rows", (M, N, K, wT), rel(Cout, ref))
+    assert rel(Cout, ref) < 5e-6
+    C2 = rnd(M, N, seed=4)
+    base, mask = C2.clone(), rnd(M, N, seed=5)
+    rc = L.dof_test_gemm_rows(P(A), K, A_PLAIN, 0, 0, 0, P(W), W.shape[1], wT, P(bias), P(C2), N, M, N, K, 1, 1, P(mask), S())
+    assert rc == 0
+    assert rel(C2, torch.relu(ref + base.double()) * (mask > 0)) < 5e-6
+    # the SIMT kernel must agree
+    L.dof_set_tensor_cores(0)
+    C3 = torch.zeros(M, N, device="cuda")
+    names = _ran(L, lambda: L.dof_test_gemm_rows(P(A), K, A_PLAIN, 0, 0, 0, P(W), W.shape[1], wT, P(bias), P(C3), N, M,
+                                                 N, K, 0, 0, None, S()))
+    L.dof_set_tensor_cores(1)
+    assert "gemm_rows" in names and "gemm_rows_tc" not in names
+    assert rel(C3, ref) < 5e-6
+
+
+def test_tc_gemm_rows_split_view(L):
+    L.dof_set_tensor_cores(1)
+    M, H, I = 30000, 16, 64
+    G = rnd(M, 4 * H, seed=3)
+    Wi = rnd(3 * H, I, seed=4)
+    dX = torch.zeros(M, I, device="cuda")
+    names = _ran(L, lambda: L.dof_test_gemm_rows(P(G), 4 * H, A_SPLIT, 2 * H, H, 0, P(Wi), I, 1, None, P(dX), I, M, I, 3 * H,
+                                                 0, 0, None, S()))
+    assert "gemm_rows_tc" in names
+    Gi = torch.cat([G[:, :2 * H], G[:, 3 * H:]], 1).double()
+    assert rel(dX, Gi @ Wi.double()) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K,oT", [(50000, 96, 32, 0), (50000, 48, 64, 0), (50000, 48, 16, 0), (20000, 16, 16, 1),
+                                      (8192, 128, 64, 0), (4100, 4, 4, 0), (30000, 32, 96, 0)])
+def test_tc_gemm_wgrad(L, M, N, K, oT):
+    L.dof_set_tensor_cores(1)
+    Pm, Q = rnd(M, N, seed=1), rnd(M, K, seed=2)
+    dW = torch.zeros(N, K, device="cuda") if oT == 0 else torch.zeros(K, N, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    names = _ran(L, lambda: L.dof_test_gemm_wgrad(P(Pm), N, A_PLAIN, 0, 0, P(Q), K, A_PLAIN, 0, 0, P(dW), dW.shape[1], oT,
+                                                  P(db), M, N, K, S()))
+    assert "gemm_wgrad_tc" in names, names
+    ref = Pm.double().t() @ Q.double()
+    print("tc wgrad", (M, N, K, oT), rel(dW if oT == 0 else dW.t(), ref), rel(db, Pm.double().sum(0)))
+    assert rel(dW if oT == 0 else dW.t(), ref) < 1e-5
+    assert rel(db, Pm.double().sum(0)) < 1e-5
+
+
+def test_tc_gemm_wgrad_views(L):
+    L.dof_set_tensor_cores(1)
+    S_, T, H = 400, 25, 16
+    M = S_ * T
+    G = rnd(M, 4 * H, seed=3)
+    X = rnd(M, 32, seed=5)
+    dWi = torch.zeros(3 * H, 32, device="cuda")
+    dbi = torch.zeros(3 * H, device="cuda")
+    names = _ran(L, lambda: L.dof_test_gemm_wgrad(P(G), 4 * H, A_SPLIT, 2 * H, H, P(X), 32, A_PLAIN, 0, 0, P(dWi), 32, 0,
+                                                  P(dbi), M, 3 * H, 32, S()))
+    assert "gemm_wgrad_tc" in names
+    Gi = torch.cat([G[:, :2 * H], G[:, 3 * H:]], 1).double()
+    assert rel(dWi, Gi.t() @ X.double()) < 1e-5 and rel(dbi, Gi.sum(0)) < 1e-5
+    Hs = rnd(S_, T, 2 * H, seed=4)
+    for d, shift in ((0, -1), (1, 1)):
+        dWh = torch.zeros(3 * H, H, device="cuda")
+        dbh = torch.zeros(3 * H, device="cuda")
+        Hd = Hs[:, :, d * H:(d + 1) * H]
+        names = _ran(L, lambda: L.dof_test_gemm_wgrad(P(G), 4 * H, A_PLAIN, 0, 0, C.c_void_p(Hs.data_ptr() + d * H * 4),
+                                                      2 * H, A_TSHIFT, T, shift, P(dWh), H, 0, P(dbh), M, 3 * H, H, S()))
+        assert "gemm_wgrad_tc" in names
+        Hsh = torch.zeros_like(Hd)
+        if shift == -1:
+            Hsh[:, 1:] = Hd[:, :-1]
+        else:
+            Hsh[:, :-1] = Hd[:, 1:]
+        ref = G[:, :3 * H].double().t() @ Hsh.reshape(M, H).double()
+        assert rel(dWh, ref) < 1e-5 and rel(dbh, G[:, :3 * H].double().sum(0)) < 1e-5
