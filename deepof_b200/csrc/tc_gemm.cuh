@@ -16,8 +16,13 @@
 //   gemm_rows_tc  : C[M,N] = epi(A[M,K] . W^T + b)     A row tile [128 x K] is operand A
 //                   (K-major), W [N x K] operand B (K-major), persistent CTAs over row tiles.
 //   gemm_wgrad_tc : dW[N,K] += P[M,N]^T . Q[M,K]       reduction over rows = MMA K dimension;
-//                   P^T / Q^T are MN-major operands (rows of P/Q are contiguous along n/k);
-//                   a constant-one column appended to Q yields the bias gradient for free.
+//                   P^T / Q^T are staged TRANSPOSED into K-major tiles (bank-conflict free);
+//                   a constant-one row appended to Q^T yields the bias gradient for free.
+// Both kernels are warp-specialised and persistent: 4 producer warps stream tiles from HBM
+// (register double-buffered float4 loads -> hi/lo split -> shared-memory ring; the split needs
+// a register pass, so TMA cannot stage these operands), one thread issues the MMAs, and (rows
+// kernel) 4 epilogue warps drain a double-buffered TMEM accumulator; all hand-offs are
+// mbarriers, there is no block-wide barrier in the steady state.
 #pragma once
 #include "common.cuh"
 #include "gemm.cuh"
@@ -41,6 +46,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (unsigned long long i = 0; i < (1ull << 31); i++)
         if (mbar_try_wait(bar, parity)) return;
     __trap();
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -100,30 +108,36 @@ static inline int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n 
 // gemm_rows on tcgen05
 // ---------------------------------------------------------------------------
 #define TC_A_LBO (128 * 16 + 16)    // K-chunk (4 floats) stride of the A tile; +16 B breaks STS bank conflicts
+#define TCR_THREADS 288             // warps 0-3 producers, 4-7 epilogue (TMEM lane group = warp & 3), warp 8 MMA
 
-struct TcRowsGeom { int KP, NP, tmem_cols, w_lbo; uint32_t a_bytes, w_bytes; };
+struct TcRowsGeom { int KP, NP, tmem_cols, w_lbo, stages; uint32_t a_bytes, w_bytes; };
 
-__global__ void __launch_bounds__(128) gemm_rows_tc_kernel(const GemmBatch gb, const TcRowsGeom geo) {
+// KQM: float4 chunks per row held in registers per producer thread and per set; NSET register sets
+template <int KQM, int NSET>
+__global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBatch gb, const TcRowsGeom geo) {
     const GemmArgs& g = gb.g[blockIdx.z];
     extern __shared__ __align__(128) unsigned char tsm[];
-    unsigned char* A_hi = tsm;
-    unsigned char* A_lo = A_hi + geo.a_bytes;
-    unsigned char* W_hi = A_lo + geo.a_bytes;
+    const int S = geo.stages;
+    unsigned char* W_hi = tsm;
     unsigned char* W_lo = W_hi + geo.w_bytes;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(W_lo + geo.w_bytes);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    unsigned char* A_base = W_lo + geo.w_bytes;                       // S x (A_hi | A_lo)
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(A_base + (size_t)S * 2 * geo.a_bytes);
+    // mbar[0..S) full, [S..2S) empty, [2S..2S+2) tmem full, [2S+2..2S+4) tmem empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * S + 4);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);          // [NP]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KP = geo.KP, NP = geo.NP, KQ = KP >> 2;
     const int ntiles = (g.M + 127) / 128;
     if ((int)blockIdx.x >= ntiles) return;
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), geo.tmem_cols);
-    if (tid == 0) {
-        mbar_init(smem_u32(mbar), 1);
+    if (tid == 32) {
+        for (int i = 0; i < S; i++) { mbar_init(smem_u32(mbar + i), 128); mbar_init(smem_u32(mbar + S + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(mbar + 2 * S + i), 1); mbar_init(smem_u32(mbar + 2 * S + 2 + i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // stage W (hi/lo) once: canonical K-major, rows n at 16 B, K-chunks at w_lbo
-    for (int i = tid; i < NP * KP; i += 128) {
+    for (int i = tid; i < NP * KP; i += TCR_THREADS) {
         int n, k;
         if (g.wT == 0) { n = i / KP; k = i % KP; } else { k = i / NP; n = i % NP; }
         float v = 0.f;
@@ -134,98 +148,155 @@ __global__ void __launch_bounds__(128) gemm_rows_tc_kernel(const GemmBatch gb, c
         *reinterpret_cast<float*>(W_hi + off) = hi;
         *reinterpret_cast<float*>(W_lo + off) = lo;
     }
+    for (int i = tid; i < NP; i += TCR_THREADS) bias_s[i] = (g.bias && i < g.N) ? __ldg(g.bias + i) : 0.f;
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t idesc = umma_idesc_tf32(NP, 0, 0);
-    const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), w_hi_s = smem_u32(W_hi), w_lo_s = smem_u32(W_lo);
-    const uint32_t bar = smem_u32(mbar);
-    uint32_t phase = 0;
-    const bool split = g.A.mode == A_SPLIT;
+    const uint32_t bar_full = smem_u32(mbar), bar_empty = smem_u32(mbar + S);
+    const uint32_t bar_tfull = smem_u32(mbar + 2 * S), bar_tempty = smem_u32(mbar + 2 * S + 2);
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = tile * 128;
-        // ---- stage the A tile: coalesced float4 loads -> hi/lo -> canonical K-major smem
-        for (int i = tid; i < 128 * KQ; i += 128) {
-            int row = i / KQ, kq = i - row * KQ;
-            int m = m0 + row, c = kq * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < g.M && c < g.K) {
-                if (split && c >= g.A.split) c += g.A.skip;
-                v = __ldg(reinterpret_cast<const float4*>(g.A.p + (size_t)m * g.A.ld + c));
+    if (warp < 4) {
+        // ===================== producers =====================
+        const bool split = g.A.mode == A_SPLIT;
+        float4 pre[NSET][KQM];
+        auto load_regs = [&](float4 (&r)[KQM], int tile) {
+            const int m0 = tile * 128;
+#pragma unroll
+            for (int j = 0; j < KQM; j++) {
+                int i = tid + j * 128;
+                r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < KQ) {
+                    int row = i / KQ, kq = i - row * KQ;
+                    int m = m0 + row, c = kq * 4;
+                    if (m < g.M && c < g.K) {
+                        if (split && c >= g.A.split) c += g.A.skip;
+                        r[j] = __ldg(reinterpret_cast<const float4*>(g.A.p + (size_t)m * g.A.ld + c));
+                    }
+                }
             }
-            float4 hi, lo;
-            split_tf32x4(v, hi, lo);
-            uint32_t off = (uint32_t)row * 16 + (uint32_t)kq * TC_A_LBO;
-            *reinterpret_cast<float4*>(A_hi + off) = hi;
-            *reinterpret_cast<float4*>(A_lo + off) = lo;
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            for (int ks = 0; ks < (KP >> 3); ks++) {
-                uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * geo.w_lbo;
-                uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
-                uint64_t dbh = umma_desc(w_hi_s + wo, geo.w_lbo, 128), dbl = umma_desc(w_lo_s + wo, geo.w_lbo, 128);
-                umma_tf32(tmem, dah, dbh, idesc, ks > 0 ? 1u : 0u);
-                umma_tf32(tmem, dal, dbh, idesc, 1u);
-                umma_tf32(tmem, dah, dbl, idesc, 1u);
+        };
+        auto store_smem = [&](const float4 (&r)[KQM], int stage) {
+            unsigned char* A_hi = A_base + (size_t)stage * 2 * geo.a_bytes;
+            unsigned char* A_lo = A_hi + geo.a_bytes;
+#pragma unroll
+            for (int j = 0; j < KQM; j++) {
+                if (j < KQ) {
+                    int i = tid + j * 128;
+                    int row = i / KQ, kq = i - row * KQ;
+                    float4 hi, lo;
+                    split_tf32x4(r[j], hi, lo);
+                    uint32_t off = (uint32_t)row * 16 + (uint32_t)kq * TC_A_LBO;
+                    *reinterpret_cast<float4*>(A_hi + off) = hi;
+                    *reinterpret_cast<float4*>(A_lo + off) = lo;
+                }
             }
-            umma_commit(bar);
+        };
+        int tile = blockIdx.x, it = 0;
+        if (NSET == 2) load_regs(pre[0], tile);
+        for (; tile < ntiles; tile += gridDim.x, it++) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)((it / S) & 1);
+            const int next = tile + gridDim.x;
+            if (NSET == 2) {
+                // alternate register sets: set (it&1) holds this tile, set (it&1)^1 receives the next
+                if ((it & 1) == 0) {
+                    if (next < ntiles) load_regs(pre[1 % NSET], next);
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    store_smem(pre[0], s);
+                } else {
+                    if (next < ntiles) load_regs(pre[0], next);
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    store_smem(pre[1 % NSET], s);
+                }
+            } else {
+                load_regs(pre[0], tile);
+                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                store_smem(pre[0], s);
+            }
+            fence_async_smem();
+            mbar_arrive(bar_full + 8u * s);
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        // ---- epilogue: thread = row
-        const int m = m0 + warp * 32 + lane;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    } else if (warp < 8) {
+        // ===================== epilogue: thread = row =====================
+        const int ew = warp & 3;
         const bool vec = ((g.ldc & 3) == 0) && ((g.N & 3) == 0) && (g.mask == nullptr || (g.ldmask & 3) == 0);
-        for (int c0 = 0; c0 < NP; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
-            if (m < g.M) {
-                float* cp = g.C + (size_t)m * g.ldc + c0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int a = it & 1;
+            mbar_wait(bar_tfull + 8u * a, (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const int m = tile * 128 + ew * 32 + lane;
+            const uint32_t trow = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * (uint32_t)NP;
+            for (int c0 = 0; c0 < NP; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+                if (m < g.M) {
+                    float* cp = g.C + (size_t)m * g.ldc + c0;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    int n = c0 + q * 4;
-                    if (n >= g.N) break;
-                    float o[4];
+                    for (int q = 0; q < 4; q++) {
+                        int n = c0 + q * 4;
+                        if (n >= g.N) break;
+                        float4 b4 = *reinterpret_cast<const float4*>(bias_s + n);
+                        float o[4] = {v[q * 4] + b4.x, v[q * 4 + 1] + b4.y, v[q * 4 + 2] + b4.z, v[q * 4 + 3] + b4.w};
+                        if (vec) {
+                            if (g.accum) {
+                                float4 c = *reinterpret_cast<const float4*>(cp + q * 4);
+                                o[0] += c.x; o[1] += c.y; o[2] += c.z; o[3] += c.w;
+                            }
+                            if (g.relu) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) o[j] = v[q * 4 + j] + ((g.bias && n + j < g.N) ? __ldg(g.bias + n + j) : 0.f);
-                    if (vec) {
-                        if (g.accum) {
-                            float4 c = *reinterpret_cast<const float4*>(cp + q * 4);
-                            o[0] += c.x; o[1] += c.y; o[2] += c.z; o[3] += c.w;
-                        }
-                        if (g.relu) {
+                                for (int j = 0; j < 4; j++) o[j] = fmaxf(o[j], 0.f);
+                            }
+                            if (g.mask) {
+                                float4 mk = *reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldmask + n);
+                                o[0] = mk.x > 0.f ? o[0] : 0.f; o[1] = mk.y > 0.f ? o[1] : 0.f;
+                                o[2] = mk.z > 0.f ? o[2] : 0.f; o[3] = mk.w > 0.f ? o[3] : 0.f;
+                            }
+                            *reinterpret_cast<float4*>(cp + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
 #pragma unroll
-                            for (int j = 0; j < 4; j++) o[j] = fmaxf(o[j], 0.f);
-                        }
-                        if (g.mask) {
-                            float4 mk = *reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldmask + n);
-                            o[0] = mk.x > 0.f ? o[0] : 0.f; o[1] = mk.y > 0.f ? o[1] : 0.f;
-                            o[2] = mk.z > 0.f ? o[2] : 0.f; o[3] = mk.w > 0.f ? o[3] : 0.f;
-                        }
-                        *reinterpret_cast<float4*>(cp + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if (n + j >= g.N) continue;
-                            float x = o[j];
-                            if (g.accum) x += cp[q * 4 + j];
-                            if (g.relu) x = fmaxf(x, 0.f);
-                            if (g.mask) x = g.mask[(size_t)m * g.ldmask + n + j] > 0.f ? x : 0.f;
-                            cp[q * 4 + j] = x;
+                            for (int j = 0; j < 4; j++) {
+                                if (n + j >= g.N) continue;
+                                float x = o[j];
+                                if (g.accum) x += cp[q * 4 + j];
+                                if (g.relu) x = fmaxf(x, 0.f);
+                                if (g.mask) x = g.mask[(size_t)m * g.ldmask + n + j] > 0.f ? x : 0.f;
+                                cp[q * 4 + j] = x;
+                            }
                         }
                     }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8u * a);
         }
-        tc_fence_before();   // TMEM reads done before the next tile's MMAs (ordered by the next __syncthreads)
+    } else if (lane == 0) {
+        // ===================== MMA issuer (one thread) =====================
+        const uint32_t idesc = umma_idesc_tf32(NP, 0, 0);
+        const uint32_t w_hi_s = smem_u32(W_hi), w_lo_s = smem_u32(W_lo);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int s = it % S, a = it & 1;
+            mbar_wait(bar_tempty + 8u * a, (uint32_t)(((it >> 1) & 1) ^ 1));
+            mbar_wait(bar_full + 8u * s, (uint32_t)((it / S) & 1));
+            tc_fence_after();
+            const uint32_t a_hi_s = smem_u32(A_base + (size_t)s * 2 * geo.a_bytes), a_lo_s = a_hi_s + geo.a_bytes;
+            const uint32_t acc = tmem + (uint32_t)a * (uint32_t)NP;
+            for (int ks = 0; ks < (KP >> 3); ks++) {
+                uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * geo.w_lbo;
+                uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
+                uint64_t dbh = umma_desc(w_hi_s + wo, geo.w_lbo, 128), dbl = umma_desc(w_lo_s + wo, geo.w_lbo, 128);
+                umma_tf32(acc, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+                umma_tf32(acc, dal, dbh, idesc, 1u);
+                umma_tf32(acc, dah, dbl, idesc, 1u);
+            }
+            umma_commit(bar_empty + 8u * s);    // smem stage may be refilled once these MMAs retire
+            umma_commit(bar_tfull + 8u * a);    // accumulator ready for the epilogue warps
+        }
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, geo.tmem_cols);
 }
@@ -243,13 +314,43 @@ static inline bool tc_enabled() {
 
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+#define TC_SMEM_MAX (200 * 1024)
+
+static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem) {
+    geo.KP = round_up(K, 8);
+    geo.NP = round_up(N, 16);
+    if (2 * geo.NP > 512) return false;
+    geo.tmem_cols = tmem_cols_for(2 * geo.NP);
+    geo.w_lbo = geo.NP * 16 + 16;
+    geo.a_bytes = (uint32_t)(geo.KP / 4) * TC_A_LBO;
+    geo.w_bytes = (uint32_t)(geo.KP / 4) * geo.w_lbo;
+    for (int S = 2; S >= 1; S--) {
+        smem = 2 * (size_t)geo.w_bytes + (size_t)S * 2 * geo.a_bytes + (2 * S + 4) * 8 + 16 + (size_t)geo.NP * 4 + 128;
+        if (smem <= TC_SMEM_MAX) { geo.stages = S; return true; }
+    }
+    return false;
+}
+
 static bool tc_rows_eligible(const GemmArgs& g) {
     if (g.M < 2048 || g.N > 256 || g.K > 128 || g.N < 8) return false;
     if (g.A.mode != A_PLAIN && g.A.mode != A_SPLIT) return false;
     if ((g.A.ld & 3) || (g.K & 3) || !aligned16(g.A.p)) return false;
     if (g.A.mode == A_SPLIT && ((g.A.split & 3) || (g.A.skip & 3))) return false;
     if (!aligned16(g.C) || (g.mask && !aligned16(g.mask))) return false;
-    return true;
+    TcRowsGeom geo; size_t smem;
+    return tc_rows_geom(g.N, g.K, geo, smem);
+}
+
+template <int KQM, int NSET>
+static int launch_rows_tc_t(const GemmBatch& gb, const TcRowsGeom& geo, size_t smem, dim3 grid, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        DOF_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<KQM, NSET>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        attr = true;
+    }
+    gemm_rows_tc_kernel<KQM, NSET><<<grid, TCR_THREADS, smem, st>>>(gb, geo);
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
 }
 
 static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, int sm_count) {
@@ -262,169 +363,242 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
         if (gs[i].N != gs[0].N || gs[i].K != gs[0].K) DOF_FAIL(DOF_ERR_ARG, "batched TC GEMMs must share N and K");
     }
     TcRowsGeom geo;
-    geo.KP = round_up(gs[0].K, 8);
-    geo.NP = round_up(gs[0].N, 16);
-    geo.tmem_cols = tmem_cols_for(geo.NP);
-    geo.w_lbo = geo.NP * 16 + 16;
-    geo.a_bytes = (uint32_t)(geo.KP / 4) * TC_A_LBO;
-    geo.w_bytes = (uint32_t)(geo.KP / 4) * geo.w_lbo;
-    size_t smem = 2 * (size_t)geo.a_bytes + 2 * (size_t)geo.w_bytes + 64;
-    static size_t attr_max = 0;
-    if (smem > attr_max) {
-        DOF_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_max = 200 * 1024;
-    }
-    if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC GEMM tile does not fit shared memory");
+    size_t smem = 0;
+    if (!tc_rows_geom(gs[0].N, gs[0].K, geo, smem)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC GEMM tile does not fit");
+    const int KQ = geo.KP / 4;
     int occ = (int)((220 * 1024) / (smem + 1024));
     int by_tmem = 512 / geo.tmem_cols;
     if (occ > by_tmem) occ = by_tmem;
-    if (occ > 4) occ = 4;
+    int by_regs = KQ <= 8 ? 2 : 1;                     // register budget of the 288-thread CTA
+    if (occ > by_regs) occ = by_regs;
     if (occ < 1) occ = 1;
     int ntiles = cdiv(M, 128);
     int ctas = sm_count * occ / nbatch;
     if (ctas < 1) ctas = 1;
     if (ctas > ntiles) ctas = ntiles;
-    double fl = 0.0;
-    for (int i = 0; i < nbatch; i++) fl += 2.0 * gs[i].M * gs[i].N * gs[i].K;
-    ProfScope ps("gemm_rows_tc", st, fl);
-    gemm_rows_tc_kernel<<<dim3(ctas, 1, nbatch), 128, smem, st>>>(gb, geo);
-    DOF_LAUNCH_CHECK();
-    return DOF_OK;
+    double fl = 0.0, by = 0.0;
+    for (int i = 0; i < nbatch; i++) {
+        fl += 2.0 * gs[i].M * gs[i].N * gs[i].K;
+        by += 4.0 * gs[i].M * ((double)gs[i].K + (double)gs[i].N * (1 + (gs[i].accum ? 1 : 0) + (gs[i].mask ? 1 : 0)));
+    }
+    ProfScope ps("gemm_rows_tc", st, fl, by);
+    dim3 grid(ctas, 1, nbatch);
+    if (KQ <= 8) return launch_rows_tc_t<8, 2>(gb, geo, smem, grid, st);
+    if (KQ <= 16) return launch_rows_tc_t<16, 2>(gb, geo, smem, grid, st);
+    return launch_rows_tc_t<32, 1>(gb, geo, smem, grid, st);
 }
 
 // ---------------------------------------------------------------------------
-// gemm_wgrad on tcgen05:  D[n, k] (+ ones column) accumulated in TMEM over this CTA's rows
+// gemm_wgrad on tcgen05:  D[n, k] = sum_m P[m,n] Q[m,k]  accumulated in TMEM over the CTA's rows.
+// Both operands are K-major with the reduction index m as the MMA K dimension: the row-major
+// [m, n] / [m, k] tiles are TRANSPOSED while they are staged (float4 global loads, 4 scalar
+// shared stores per float4).  Bank-conflict-free staging: a warp covers 8 rows x 4 float4
+// (64 B contiguous per row -> full sectors), the K-chunk stride LBO = 144 B (== 4 words mod 32)
+// and the 8-row-group stride SBO == 8 words mod 32.  A constant-one row appended to Q^T yields
+// the bias gradient.  Rows of A beyond N (and of B beyond K+1) hold don't-care data: they only
+// reach accumulator rows / columns that are never read.
 // ---------------------------------------------------------------------------
-#define TCW_BM 64                       // rows (MMA-K) per stage
-#define TCW_SBO (TCW_BM * 16 + 16)      // stride between 4-wide n (or k) blocks; +16 B vs bank conflicts
+#define TCW_BM 32                      // rows (MMA-K) per stage
+#define TCW_LBO 144
+#define TCW_SBO ((TCW_BM / 4) * TCW_LBO + 32)   // 1184 B
+#define TCW_MAXPRE 12                  // float4 prefetch registers per producer thread and set
+#define TCW_THREADS 160                // warps 0-3 producers (+ final epilogue), warp 4 MMA issuer
+#define TCW_STAGES 2
 
-struct TcWgradGeom { int KWP, tmem_cols; uint32_t p_bytes, q_bytes; };
+struct TcWgradGeom { int KWP, tmem_cols, ptasks, qtasks; uint32_t p_bytes, q_bytes; };
 
-__global__ void __launch_bounds__(128) gemm_wgrad_tc_kernel(const WGradBatch wb, const TcWgradGeom geo) {
+__global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGradBatch wb, const TcWgradGeom geo) {
     const WGradArgs& g = wb.g[blockIdx.z];
     extern __shared__ __align__(128) unsigned char tsm[];
-    unsigned char* P_hi = tsm;
-    unsigned char* P_lo = P_hi + geo.p_bytes;
-    unsigned char* Q_hi = P_lo + geo.p_bytes;
-    unsigned char* Q_lo = Q_hi + geo.q_bytes;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(Q_lo + geo.q_bytes);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    const uint32_t stage_bytes = 2 * geo.p_bytes + 2 * geo.q_bytes;     // P_hi | P_lo | Q_hi | Q_lo
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(tsm + (size_t)TCW_STAGES * stage_bytes);
+    // mbar[0..S) full (128 arrivals), [S..2S) empty (1 commit), [2S] all MMAs done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * TCW_STAGES + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int rows_per = (g.M + gridDim.x - 1) / gridDim.x;
     rows_per = (rows_per + TCW_BM - 1) / TCW_BM * TCW_BM;
     const int mbeg = blockIdx.x * rows_per;
     const int mend = min(g.M, mbeg + rows_per);
     if (mbeg >= mend) return;
+    const int nstage = (mend - mbeg + TCW_BM - 1) / TCW_BM;
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), geo.tmem_cols);
-    if (tid == 0) {
-        mbar_init(smem_u32(mbar), 1);
+    if (tid == 32) {
+        for (int i = 0; i < TCW_STAGES; i++) { mbar_init(smem_u32(mbar + i), 128); mbar_init(smem_u32(mbar + TCW_STAGES + i), 1); }
+        mbar_init(smem_u32(mbar + 2 * TCW_STAGES), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // zero everything once: padded n rows (>= N) and k columns (> K) stay zero forever
-    for (uint32_t i = tid * 16; i < 2 * geo.p_bytes + 2 * geo.q_bytes; i += 128 * 16)
+    // zero the operand tiles once (padding rows stay finite), then the constant-one row k = K of Q^T
+    for (uint32_t i = tid * 16; i < TCW_STAGES * stage_bytes; i += TCW_THREADS * 16)
         *reinterpret_cast<float4*>(tsm + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (tid < TCW_BM * TCW_STAGES) {
+        int sidx = tid / TCW_BM, mm = tid % TCW_BM;
+        uint32_t off = (uint32_t)(g.K >> 3) * TCW_SBO + (uint32_t)(g.K & 7) * 16 + (uint32_t)(mm >> 2) * TCW_LBO + (mm & 3) * 4;
+        *reinterpret_cast<float*>(tsm + (size_t)sidx * stage_bytes + 2 * geo.p_bytes + off) = 1.0f;
+    }
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t idesc = umma_idesc_tf32(geo.KWP, 1, 1);
-    const uint32_t p_hi_s = smem_u32(P_hi), p_lo_s = smem_u32(P_lo), q_hi_s = smem_u32(Q_hi), q_lo_s = smem_u32(Q_lo);
-    const uint32_t bar = smem_u32(mbar);
-    uint32_t phase = 0;
-    const int NQ = g.N >> 2, KQ = g.K >> 2;
-    const bool psplit = g.P.mode == A_SPLIT;
-    const bool qshift = g.Q.mode == A_TSHIFT;
-    bool first = true;
+    const uint32_t bar_full = smem_u32(mbar), bar_empty = smem_u32(mbar + TCW_STAGES), bar_done = smem_u32(mbar + 2 * TCW_STAGES);
 
-    for (int mb = mbeg; mb < mend; mb += TCW_BM) {
-        // ---- stage P (as A^T: n-blocks of 4 at TCW_SBO, rows at 16 B) and Q likewise
-        for (int i = tid; i < TCW_BM * NQ; i += 128) {
-            int r = i / NQ, nq = i - r * NQ;
-            int m = mb + r, c = nq * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < mend) {
-                if (psplit && c >= g.P.split) c += g.P.skip;
-                v = __ldg(reinterpret_cast<const float4*>(g.P.p + (size_t)m * g.P.ld + c));
-            }
-            float4 hi, lo;
-            split_tf32x4(v, hi, lo);
-            uint32_t off = (uint32_t)nq * TCW_SBO + (uint32_t)r * 16;
-            *reinterpret_cast<float4*>(P_hi + off) = hi;
-            *reinterpret_cast<float4*>(P_lo + off) = lo;
-        }
-        for (int i = tid; i < TCW_BM * (KQ + 1); i += 128) {
-            int r = i / (KQ + 1), kq = i - r * (KQ + 1);
-            int m = mb + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < mend) {
-                if (kq == KQ) {
-                    v.x = 1.0f;                       // ones column -> bias gradient
-                } else if (qshift) {
-                    int t = m % g.Q.T, tt = t + g.Q.shift;
-                    if (tt >= 0 && tt < g.Q.T)
-                        v = __ldg(reinterpret_cast<const float4*>(g.Q.p + (size_t)(m + g.Q.shift) * g.Q.ld + kq * 4));
-                } else {
-                    v = __ldg(reinterpret_cast<const float4*>(g.Q.p + (size_t)m * g.Q.ld + kq * 4));
+    if (warp < 4) {
+        // ===================== producers =====================
+        const int NQ = g.N >> 2, KQ = g.K >> 2;
+        const bool psplit = g.P.mode == A_SPLIT;
+        const bool qshift = g.Q.mode == A_TSHIFT;
+        const int r8 = lane & 7, c4 = lane >> 3;
+        const int ntask = geo.ptasks + geo.qtasks;
+        // task t: operand (P if t < ptasks), 8-row block mblk = t % (BM/8), 4-float4 column block cb
+        float4 pre[2][TCW_MAXPRE];
+        auto load_regs = [&](float4 (&r)[TCW_MAXPRE], int mb0) {
+#pragma unroll
+            for (int j = 0; j < TCW_MAXPRE; j++) {
+                int t = warp + 4 * j;
+                r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < ntask) {
+                    const bool isP = t < geo.ptasks;
+                    int tt = isP ? t : t - geo.ptasks;
+                    int mblk = tt % (TCW_BM / 8), cb = tt / (TCW_BM / 8);
+                    int m = mb0 + mblk * 8 + r8, cq = cb * 4 + c4;
+                    if (m < mend) {
+                        if (isP) {
+                            if (cq < NQ) {
+                                int c = cq * 4;
+                                if (psplit && c >= g.P.split) c += g.P.skip;
+                                r[j] = __ldg(reinterpret_cast<const float4*>(g.P.p + (size_t)m * g.P.ld + c));
+                            }
+                        } else if (cq < KQ) {
+                            if (qshift) {
+                                int tq = m % g.Q.T, t2 = tq + g.Q.shift;
+                                if (t2 >= 0 && t2 < g.Q.T)
+                                    r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (size_t)(m + g.Q.shift) * g.Q.ld + cq * 4));
+                            } else {
+                                r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (size_t)m * g.Q.ld + cq * 4));
+                            }
+                        }
+                    }
                 }
             }
-            float4 hi, lo;
-            split_tf32x4(v, hi, lo);
-            uint32_t off = (uint32_t)kq * TCW_SBO + (uint32_t)r * 16;
-            *reinterpret_cast<float4*>(Q_hi + off) = hi;
-            *reinterpret_cast<float4*>(Q_lo + off) = lo;
+        };
+        auto store_smem = [&](const float4 (&r)[TCW_MAXPRE], int stage) {
+            unsigned char* P_hi = tsm + (size_t)stage * stage_bytes;
+            unsigned char* P_lo = P_hi + geo.p_bytes;
+            unsigned char* Q_hi = P_lo + geo.p_bytes;
+            unsigned char* Q_lo = Q_hi + geo.q_bytes;
+#pragma unroll
+            for (int j = 0; j < TCW_MAXPRE; j++) {
+                int t = warp + 4 * j;
+                if (t < ntask) {
+                    const bool isP = t < geo.ptasks;
+                    int tt = isP ? t : t - geo.ptasks;
+                    int mblk = tt % (TCW_BM / 8), cb = tt / (TCW_BM / 8);
+                    int ml = mblk * 8 + r8, cq = cb * 4 + c4;
+                    if (cq < (isP ? NQ : KQ)) {
+                        float4 hi, lo;
+                        split_tf32x4(r[j], hi, lo);
+                        // rows 4cq..4cq+3 of the transposed tile: 8-row group cq>>1, row-in-group 4*(cq&1)+e
+                        uint32_t off = (uint32_t)(cq >> 1) * TCW_SBO + (uint32_t)(4 * (cq & 1)) * 16 + (uint32_t)(ml >> 2) * TCW_LBO + (ml & 3) * 4;
+                        unsigned char* bh = (isP ? P_hi : Q_hi) + off;
+                        unsigned char* bl = (isP ? P_lo : Q_lo) + off;
+                        *reinterpret_cast<float*>(bh) = hi.x; *reinterpret_cast<float*>(bh + 16) = hi.y;
+                        *reinterpret_cast<float*>(bh + 32) = hi.z; *reinterpret_cast<float*>(bh + 48) = hi.w;
+                        *reinterpret_cast<float*>(bl) = lo.x; *reinterpret_cast<float*>(bl + 16) = lo.y;
+                        *reinterpret_cast<float*>(bl + 32) = lo.z; *reinterpret_cast<float*>(bl + 48) = lo.w;
+                    }
+                }
+            }
+        };
+        load_regs(pre[0], mbeg);
+        for (int it = 0; it < nstage; it++) {
+            const int s = it % TCW_STAGES;
+            const uint32_t ph = (uint32_t)((it / TCW_STAGES) & 1);
+            const int mnext = mbeg + (it + 1) * TCW_BM;
+            if ((it & 1) == 0) {
+                if (it + 1 < nstage) load_regs(pre[1], mnext);
+                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                store_smem(pre[0], s);
+            } else {
+                if (it + 1 < nstage) load_regs(pre[0], mnext);
+                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                store_smem(pre[1], s);
+            }
+            fence_async_smem();
+            mbar_arrive(bar_full + 8u * s);
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        // ---- epilogue: thread = output row n; atomics into dW / db
+        mbar_wait(bar_done, 0u);
+        tc_fence_after();
+        const int n = warp * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < geo.KWP; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+            if (n < g.N) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    int k = c0 + j;
+                    if (k < g.K) {
+                        float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + k;
+                        atomicAdd(o, v[j]);
+                    } else if (k == g.K && g.db) {
+                        atomicAdd(g.db + n, v[j]);
+                    }
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ===================== MMA issuer (one thread) =====================
+        const uint32_t idesc = umma_idesc_tf32(geo.KWP, 0, 0);
+        for (int it = 0; it < nstage; it++) {
+            const int s = it % TCW_STAGES;
+            mbar_wait(bar_full + 8u * s, (uint32_t)((it / TCW_STAGES) & 1));
             tc_fence_after();
+            const uint32_t p_hi_s = smem_u32(tsm + (size_t)s * stage_bytes), p_lo_s = p_hi_s + geo.p_bytes;
+            const uint32_t q_hi_s = p_lo_s + geo.p_bytes, q_lo_s = q_hi_s + geo.q_bytes;
             for (int kb = 0; kb < TCW_BM / 8; kb++) {
-                uint32_t o = (uint32_t)kb * 128;
-                uint64_t dah = umma_desc(p_hi_s + o, 128, TCW_SBO), dal = umma_desc(p_lo_s + o, 128, TCW_SBO);
-                uint64_t dbh = umma_desc(q_hi_s + o, 128, TCW_SBO), dbl = umma_desc(q_lo_s + o, 128, TCW_SBO);
-                umma_tf32(tmem, dah, dbh, idesc, (first && kb == 0) ? 0u : 1u);
+                uint32_t o = (uint32_t)kb * 2 * TCW_LBO;
+                uint64_t dah = umma_desc(p_hi_s + o, TCW_LBO, TCW_SBO), dal = umma_desc(p_lo_s + o, TCW_LBO, TCW_SBO);
+                uint64_t dbh = umma_desc(q_hi_s + o, TCW_LBO, TCW_SBO), dbl = umma_desc(q_lo_s + o, TCW_LBO, TCW_SBO);
+                umma_tf32(tmem, dah, dbh, idesc, (it == 0 && kb == 0) ? 0u : 1u);
                 umma_tf32(tmem, dal, dbh, idesc, 1u);
                 umma_tf32(tmem, dah, dbl, idesc, 1u);
             }
-            umma_commit(bar);
+            umma_commit(bar_empty + 8u * s);
         }
-        first = false;
-        mbar_wait(bar, phase);   // MMAs done reading smem -> safe to restage
-        phase ^= 1;
-    }
-    tc_fence_after();
-    // ---- epilogue: thread = output row n; atomics into dW / db
-    const int n = warp * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < geo.KWP; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + c0, v);
-        if (n < g.N) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                int k = c0 + j;
-                if (k < g.K) {
-                    float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + k;
-                    atomicAdd(o, v[j]);
-                } else if (k == g.K && g.db) {
-                    atomicAdd(g.db + n, v[j]);
-                }
-            }
-        }
+        umma_commit(bar_done);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, geo.tmem_cols);
 }
 
+static void tc_wgrad_geom(int N, int K, TcWgradGeom& geo) {
+    geo.KWP = round_up(K + 1, 16);
+    geo.tmem_cols = tmem_cols_for(geo.KWP);
+    geo.ptasks = (TCW_BM / 8) * cdiv(N >> 2, 4);
+    geo.qtasks = (TCW_BM / 8) * cdiv(K >> 2, 4);
+    geo.p_bytes = 16u * TCW_SBO;                          // 128 rows of P^T (MMA M = 128)
+    geo.q_bytes = (uint32_t)(geo.KWP / 8) * TCW_SBO;
+}
+
+static size_t tc_wgrad_smem(const TcWgradGeom& geo) {
+    return (size_t)TCW_STAGES * (2 * (size_t)geo.p_bytes + 2 * (size_t)geo.q_bytes) + (2 * TCW_STAGES + 1) * 8 + 16 + 128;
+}
+
 static bool tc_wgrad_eligible(const WGradArgs& g) {
-    if (g.M < 4096 || g.N > 128 || g.K + 4 > 256 || g.N < 4 || g.K < 4) return false;
+    if (g.M < 4096 || g.N > 128 || g.K + 1 > 256 || g.N < 4 || g.K < 4) return false;
     if ((g.N & 3) || (g.K & 3)) return false;
     if (g.P.mode != A_PLAIN && g.P.mode != A_SPLIT) return false;
     if (g.Q.mode != A_PLAIN && g.Q.mode != A_TSHIFT) return false;
     if ((g.P.ld & 3) || (g.Q.ld & 3) || !aligned16(g.P.p) || !aligned16(g.Q.p)) return false;
     if (g.P.mode == A_SPLIT && ((g.P.split & 3) || (g.P.skip & 3))) return false;
+    TcWgradGeom geo;
+    tc_wgrad_geom(g.N, g.K, geo);
+    if (cdiv(geo.ptasks + geo.qtasks, 4) > TCW_MAXPRE) return false;
+    if (tc_wgrad_smem(geo) > TC_SMEM_MAX) return false;
     return true;
 }
 
@@ -438,30 +612,30 @@ static int launch_gemm_wgrad_tc(const WGradArgs* gs, int nbatch, cudaStream_t st
         if (gs[i].N != gs[0].N || gs[i].K != gs[0].K) DOF_FAIL(DOF_ERR_ARG, "batched TC wgrads must share N and K");
     }
     TcWgradGeom geo;
-    geo.KWP = round_up(gs[0].K + 4, 16);
-    geo.tmem_cols = tmem_cols_for(geo.KWP);
-    geo.p_bytes = 32u * TCW_SBO;                       // 128 n rows
-    geo.q_bytes = (uint32_t)(geo.KWP / 4) * TCW_SBO;
-    size_t smem = 2 * (size_t)geo.p_bytes + 2 * (size_t)geo.q_bytes + 64;
+    tc_wgrad_geom(gs[0].N, gs[0].K, geo);
+    size_t smem = tc_wgrad_smem(geo);
     static bool attr = false;
     if (!attr) {
-        DOF_CUDA(cudaFuncSetAttribute(gemm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        DOF_CUDA(cudaFuncSetAttribute(gemm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         attr = true;
     }
-    if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC wgrad tile does not fit shared memory");
+    if (smem > TC_SMEM_MAX) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC wgrad tile does not fit shared memory");
     int occ = (int)((220 * 1024) / (smem + 1024));
     int by_tmem = 512 / geo.tmem_cols;
     if (occ > by_tmem) occ = by_tmem;
-    if (occ > 3) occ = 3;
+    if (occ > 2) occ = 2;
     if (occ < 1) occ = 1;
     int ctas = sm_count * occ / nbatch;
-    int maxsplit = cdiv(M, 4 * TCW_BM);
+    int maxsplit = cdiv(M, 8 * TCW_BM);
     if (ctas > maxsplit) ctas = maxsplit;
     if (ctas < 1) ctas = 1;
-    double fl = 0.0;
-    for (int i = 0; i < nbatch; i++) fl += 2.0 * gs[i].M * gs[i].N * gs[i].K;
-    ProfScope ps("gemm_wgrad_tc", st, fl);
-    gemm_wgrad_tc_kernel<<<dim3(ctas, 1, nbatch), 128, smem, st>>>(wb, geo);
+    double fl = 0.0, by = 0.0;
+    for (int i = 0; i < nbatch; i++) {
+        fl += 2.0 * gs[i].M * gs[i].N * gs[i].K;
+        by += 4.0 * gs[i].M * ((double)gs[i].N + gs[i].K);
+    }
+    ProfScope ps("gemm_wgrad_tc", st, fl, by);
+    gemm_wgrad_tc_kernel<<<dim3(ctas, 1, nbatch), TCW_THREADS, smem, st>>>(wb, geo);
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }

@@ -243,7 +243,7 @@ def _ran(L, fn):
 
 
 @pytest.mark.parametrize("M,N,K,wT", [(20000, 96, 32, 0), (20000, 48, 64, 0), (20000, 64, 48, 1), (20000, 32, 96, 1),
-                                      (5000, 42, 32, 0), (4097, 16, 8, 0), (3000, 256, 128, 0), (2048, 8, 4, 0)])
+                                      (5000, 42, 32, 0), (4097, 16, 8, 0), (3000, 32, 128, 0), (3000, 64, 96, 0), (2048, 8, 4, 0)])
 def test_tc_gemm_rows(L, M, N, K, wT):
     L.dof_set_tensor_cores(1)
     A = rnd(M, K, seed=1)
