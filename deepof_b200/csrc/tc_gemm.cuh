@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
     // mbar[0..S) full, [S..2S) empty, [2S..2S+2) tmem full, [2S+2..2S+4) tmem empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * S + 4);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);          // [NP]
+    float* epi_s = bias_s + geo.NP;                                     // [4 warps][32 rows][36]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KP = geo.KP, NP = geo.NP, KQ = KP >> 2;
     const int ntiles = (g.M + 127) / 128;
@@ -219,30 +220,46 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
             mbar_arrive(bar_full + 8u * s);
         }
     } else if (warp < 8) {
-        // ===================== epilogue: thread = row =====================
+        // ===================== epilogue =====================
+        // TMEM lane = row.  Each warp moves its 32 rows in 32-column chunks through a private padded
+        // smem buffer so that every global access is a full 128 B line per row (4 rows / instruction).
         const int ew = warp & 3;
-        const bool vec = ((g.ldc & 3) == 0) && ((g.N & 3) == 0) && (g.mask == nullptr || (g.ldmask & 3) == 0);
+        float* stg = epi_s + ew * (32 * 36);
+        const bool vec = ((g.ldc & 3) == 0) && (((uintptr_t)g.C & 15) == 0) &&
+                         (g.mask == nullptr || ((g.ldmask & 3) == 0 && ((uintptr_t)g.mask & 15) == 0));
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             const int a = it & 1;
             mbar_wait(bar_tfull + 8u * a, (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            const int m = tile * 128 + ew * 32 + lane;
+            const int mw = tile * 128 + ew * 32;
             const uint32_t trow = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * (uint32_t)NP;
-            for (int c0 = 0; c0 < NP; c0 += 16) {
+            for (int c0 = 0; c0 < NP; c0 += 32) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
-                if (m < g.M) {
-                    float* cp = g.C + (size_t)m * g.ldc + c0;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        int n = c0 + q * 4;
-                        if (n >= g.N) break;
+                for (int q = 0; q < 4; q++)
+                    *reinterpret_cast<float4*>(stg + lane * 36 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                if (c0 + 16 < NP) {
+                    tmem_ld16(trow + c0 + 16, v);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        *reinterpret_cast<float4*>(stg + lane * 36 + 16 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                }
+                __syncwarp();
+                const int cq = lane & 7, n = c0 + cq * 4;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int r = i * 4 + (lane >> 3);
+                    const int m = mw + r;
+                    if (m < g.M && n < g.N) {
+                        float4 o4 = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
                         float4 b4 = *reinterpret_cast<const float4*>(bias_s + n);
-                        float o[4] = {v[q * 4] + b4.x, v[q * 4 + 1] + b4.y, v[q * 4 + 2] + b4.z, v[q * 4 + 3] + b4.w};
-                        if (vec) {
+                        float o[4] = {o4.x + b4.x, o4.y + b4.y, o4.z + b4.z, o4.w + b4.w};
+                        float* cp = g.C + (size_t)m * g.ldc + n;
+                        if (vec && n + 3 < g.N) {
                             if (g.accum) {
-                                float4 c = *reinterpret_cast<const float4*>(cp + q * 4);
+                                float4 c = *reinterpret_cast<const float4*>(cp);
                                 o[0] += c.x; o[1] += c.y; o[2] += c.z; o[3] += c.w;
                             }
                             if (g.relu) {
@@ -254,20 +271,21 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                                 o[0] = mk.x > 0.f ? o[0] : 0.f; o[1] = mk.y > 0.f ? o[1] : 0.f;
                                 o[2] = mk.z > 0.f ? o[2] : 0.f; o[3] = mk.w > 0.f ? o[3] : 0.f;
                             }
-                            *reinterpret_cast<float4*>(cp + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
                                 if (n + j >= g.N) continue;
                                 float x = o[j];
-                                if (g.accum) x += cp[q * 4 + j];
+                                if (g.accum) x += cp[j];
                                 if (g.relu) x = fmaxf(x, 0.f);
                                 if (g.mask) x = g.mask[(size_t)m * g.ldmask + n + j] > 0.f ? x : 0.f;
-                                cp[q * 4 + j] = x;
+                                cp[j] = x;
                             }
                         }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(bar_tempty + 8u * a);
@@ -325,7 +343,8 @@ static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem) {
     geo.a_bytes = (uint32_t)(geo.KP / 4) * TC_A_LBO;
     geo.w_bytes = (uint32_t)(geo.KP / 4) * geo.w_lbo;
     for (int S = 2; S >= 1; S--) {
-        smem = 2 * (size_t)geo.w_bytes + (size_t)S * 2 * geo.a_bytes + (2 * S + 4) * 8 + 16 + (size_t)geo.NP * 4 + 128;
+        smem = 2 * (size_t)geo.w_bytes + (size_t)S * 2 * geo.a_bytes + (2 * S + 4) * 8 + 16 + (size_t)geo.NP * 4 +
+               4 * 32 * 36 * 4 + 128;
         if (smem <= TC_SMEM_MAX) { geo.stages = S; return true; }
     }
     return false;
@@ -366,7 +385,7 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     size_t smem = 0;
     if (!tc_rows_geom(gs[0].N, gs[0].K, geo, smem)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC GEMM tile does not fit");
     const int KQ = geo.KP / 4;
-    int occ = (int)((220 * 1024) / (smem + 1024));
+    int occ = (int)((228 * 1024) / (smem + 1024));
     int by_tmem = 512 / geo.tmem_cols;
     if (occ > by_tmem) occ = by_tmem;
     int by_regs = KQ <= 8 ? 2 : 1;                     // register budget of the 288-thread CTA
@@ -401,8 +420,9 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
 #define TCW_BM 32                      // rows (MMA-K) per stage
 #define TCW_LBO 144
 #define TCW_SBO ((TCW_BM / 4) * TCW_LBO + 32)   // 1184 B
-#define TCW_MAXPRE 12                  // float4 prefetch registers per producer thread and set
-#define TCW_THREADS 160                // warps 0-3 producers (+ final epilogue), warp 4 MMA issuer
+#define TCW_MAXPRE 6                   // float4 prefetch registers per producer thread and set
+#define TCW_PW 8                       // producer warps
+#define TCW_THREADS 288                // warps 0-7 producers (0-3 also run the final epilogue), warp 8 MMA issuer
 #define TCW_STAGES 2
 
 struct TcWgradGeom { int KWP, tmem_cols, ptasks, qtasks; uint32_t p_bytes, q_bytes; };
@@ -424,7 +444,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), geo.tmem_cols);
     if (tid == 32) {
-        for (int i = 0; i < TCW_STAGES; i++) { mbar_init(smem_u32(mbar + i), 128); mbar_init(smem_u32(mbar + TCW_STAGES + i), 1); }
+        for (int i = 0; i < TCW_STAGES; i++) { mbar_init(smem_u32(mbar + i), TCW_PW * 32); mbar_init(smem_u32(mbar + TCW_STAGES + i), 1); }
         mbar_init(smem_u32(mbar + 2 * TCW_STAGES), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -444,7 +464,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
     const uint32_t tmem = *tmem_slot;
     const uint32_t bar_full = smem_u32(mbar), bar_empty = smem_u32(mbar + TCW_STAGES), bar_done = smem_u32(mbar + 2 * TCW_STAGES);
 
-    if (warp < 4) {
+    if (warp < TCW_PW) {
         // ===================== producers =====================
         const int NQ = g.N >> 2, KQ = g.K >> 2;
         const bool psplit = g.P.mode == A_SPLIT;
@@ -456,7 +476,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
         auto load_regs = [&](float4 (&r)[TCW_MAXPRE], int mb0) {
 #pragma unroll
             for (int j = 0; j < TCW_MAXPRE; j++) {
-                int t = warp + 4 * j;
+                int t = warp + TCW_PW * j;
                 r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t < ntask) {
                     const bool isP = t < geo.ptasks;
@@ -490,7 +510,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
             unsigned char* Q_lo = Q_hi + geo.q_bytes;
 #pragma unroll
             for (int j = 0; j < TCW_MAXPRE; j++) {
-                int t = warp + 4 * j;
+                int t = warp + TCW_PW * j;
                 if (t < ntask) {
                     const bool isP = t < geo.ptasks;
                     int tt = isP ? t : t - geo.ptasks;
@@ -528,7 +548,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
             fence_async_smem();
             mbar_arrive(bar_full + 8u * s);
         }
-        // ---- epilogue: thread = output row n; atomics into dW / db
+        // ---- epilogue (warps 0-3): thread = output row n; atomics into dW / db
+        if (warp < 4) {
         mbar_wait(bar_done, 0u);
         tc_fence_after();
         const int n = warp * 32 + lane;
@@ -548,6 +569,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
                     }
                 }
             }
+        }
         }
     } else if (lane == 0) {
         // ===================== MMA issuer (one thread) =====================
@@ -597,7 +619,7 @@ static bool tc_wgrad_eligible(const WGradArgs& g) {
     if (g.P.mode == A_SPLIT && ((g.P.split & 3) || (g.P.skip & 3))) return false;
     TcWgradGeom geo;
     tc_wgrad_geom(g.N, g.K, geo);
-    if (cdiv(geo.ptasks + geo.qtasks, 4) > TCW_MAXPRE) return false;
+    if (cdiv(geo.ptasks + geo.qtasks, TCW_PW) > TCW_MAXPRE) return false;
     if (tc_wgrad_smem(geo) > TC_SMEM_MAX) return false;
     return true;
 }
@@ -620,7 +642,7 @@ static int launch_gemm_wgrad_tc(const WGradArgs* gs, int nbatch, cudaStream_t st
         attr = true;
     }
     if (smem > TC_SMEM_MAX) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC wgrad tile does not fit shared memory");
-    int occ = (int)((220 * 1024) / (smem + 1024));
+    int occ = (int)((228 * 1024) / (smem + 1024));
     int by_tmem = 512 / geo.tmem_cols;
     if (occ > by_tmem) occ = by_tmem;
     if (occ > 2) occ = 2;
