@@ -6,5 +6,7 @@ reference's model / step interface.  There is no CPU fallback.
 """
 from ._lib import DofError, LIB_PATH, LOG_KEYS  # noqa: F401
 from .vade import VaDEB200, VadeLossCfg, graph_operators, state_layout  # noqa: F401
+from .loader import WindowLoader, GlobalScalers, VideoConstants, batch_starts, reference_divisors  # noqa: F401
 
-__all__ = ["VaDEB200", "VadeLossCfg", "DofError", "graph_operators", "state_layout", "LIB_PATH", "LOG_KEYS"]
+__all__ = ["VaDEB200", "VadeLossCfg", "DofError", "graph_operators", "state_layout", "LIB_PATH", "LOG_KEYS",
+           "WindowLoader", "GlobalScalers", "VideoConstants", "batch_starts", "reference_divisors"]

@@ -41,6 +41,15 @@ class DofAdamCfg(C.Structure):
                 ("beta2", C.c_float), ("eps", C.c_float)]
 
 
+class DofLoaderCfg(C.Structure):
+    _fields_ = [("T", C.c_int), ("step", C.c_int), ("N", C.c_int), ("E", C.c_int), ("center_node", C.c_int),
+                ("align_node", C.c_int), ("cx", C.c_double), ("cy", C.c_double), ("fps", C.c_double),
+                ("clip", C.c_double), ("coord_scale", C.c_double), ("coord_shift", C.c_double),
+                ("speed_scale", C.POINTER(C.c_double)), ("speed_shift", C.POINTER(C.c_double)),
+                ("dist_div", C.POINTER(C.c_double)), ("dist_scale", C.POINTER(C.c_double)),
+                ("dist_shift", C.POINTER(C.c_double)), ("edges", C.POINTER(C.c_int))]
+
+
 class DofError(RuntimeError):
     pass
 
@@ -66,6 +75,10 @@ _SIGS = {
     "dof_vade_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P,
                                      C.POINTER(DofVadeLossCfg), _P, _P]),
     "dof_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(DofAdamCfg), _P]),
+    "dof_loader_num_windows": (C.c_longlong, [C.c_longlong, C.c_int, C.c_int]),
+    "dof_load_windows": (C.c_int, [C.POINTER(DofLoaderCfg), _P, C.c_longlong, C.c_longlong, C.c_int, _P, _P, _P]),
+    "dof_loader_pair_length": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dof_loader_moments": (C.c_int, [C.POINTER(DofLoaderCfg), _P, C.c_longlong, C.POINTER(C.c_double), _P, _P]),
     "dof_debug_tensor": (_P, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "dof_launch_count": (C.c_longlong, []),
     "dof_set_tensor_cores": (C.c_int, [C.c_int]),

@@ -11,6 +11,7 @@
 #include "gru.cuh"
 #include "layers.cuh"
 #include "loss.cuh"
+#include "loader.cuh"
 
 thread_local char g_dof_err[512] = {0};
 DofProf g_prof;
@@ -892,6 +893,100 @@ int dof_profile_end(char* out, size_t cap) {
         txt += line;
     }
     if (out && cap > 0) { strncpy(out, txt.c_str(), cap - 1); out[cap - 1] = 0; }
+    return DOF_OK;
+}
+
+// ---- window loader -----------------------------------------
+static int loader_params(const dof_loader_cfg* c, const float* frames, long long n_frames, LoaderP& p) {
+    if (!c || !frames) DOF_FAIL(DOF_ERR_ARG, "null loader config / frame table");
+    if (c->T < 1 || c->step < 1 || c->N < 1 || c->E < 0 || n_frames < 0)
+        DOF_FAIL(DOF_ERR_ARG, "bad loader geometry T=%d step=%d N=%d E=%d frames=%lld", c->T, c->step, c->N, c->E, n_frames);
+    if (c->N > LD_MAXN || c->E > LD_MAXE) DOF_FAIL(DOF_ERR_UNSUPPORTED, "loader supports N <= %d, E <= %d (got %d, %d)", LD_MAXN, LD_MAXE, c->N, c->E);
+    if (c->center_node >= c->N || c->align_node >= c->N) DOF_FAIL(DOF_ERR_ARG, "centre / align node out of range");
+    if (!c->speed_scale || !c->speed_shift || (c->E > 0 && (!c->dist_div || !c->dist_scale || !c->dist_shift || !c->edges)))
+        DOF_FAIL(DOF_ERR_ARG, "null per-column constants");
+    memset(&p, 0, sizeof(p));
+    p.frames = frames; p.n_frames = n_frames;
+    p.T = c->T; p.step = c->step; p.N = c->N; p.E = c->E; p.center_node = c->center_node; p.align_node = c->align_node;
+    p.cx = c->cx; p.cy = c->cy; p.fps = c->fps; p.clip = c->clip; p.coord_scale = c->coord_scale; p.coord_shift = c->coord_shift;
+    for (int n = 0; n < c->N; n++) { p.speed_scale[n] = c->speed_scale[n]; p.speed_shift[n] = c->speed_shift[n]; }
+    for (int e = 0; e < c->E; e++) {
+        if (c->edges[2 * e] < 0 || c->edges[2 * e] >= c->N || c->edges[2 * e + 1] < 0 || c->edges[2 * e + 1] >= c->N)
+            DOF_FAIL(DOF_ERR_ARG, "edge %d = (%d, %d) out of range", e, c->edges[2 * e], c->edges[2 * e + 1]);
+        if (!(c->dist_div[e] > 0.0)) DOF_FAIL(DOF_ERR_ARG, "dist_div[%d] must be > 0", e);
+        p.dist_div[e] = c->dist_div[e]; p.dist_scale[e] = c->dist_scale[e]; p.dist_shift[e] = c->dist_shift[e];
+        p.e0[e] = (short)c->edges[2 * e]; p.e1[e] = (short)c->edges[2 * e + 1];
+    }
+    return DOF_OK;
+}
+
+static int loader_device_check() {
+    int dev = 0;
+    DOF_CUDA(cudaGetDevice(&dev));
+    int major = 0;
+    DOF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major < 10) DOF_FAIL(DOF_ERR_UNSUPPORTED, "deepof_b200 needs an sm_100-class GPU");
+    if (g_sm_count <= 0) DOF_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    return DOF_OK;
+}
+
+long long dof_loader_num_windows(long long n_frames, int T, int step) {
+    if (T < 1 || step < 1 || n_frames < T) return 0;
+    return (n_frames - T) / step + 1;                       // utils.py:3354-3377
+}
+
+int dof_load_windows(const dof_loader_cfg* cfg, const float* frames, long long n_frames, long long first_window,
+                     int count, float* x, float* a, void* stream) {
+    LoaderP p;
+    DOF_TRY(loader_params(cfg, frames, n_frames, p));
+    if (count == 0) return DOF_OK;
+    if (!x || (cfg->E > 0 && !a)) DOF_FAIL(DOF_ERR_ARG, "null output");
+    const long long nw = dof_loader_num_windows(n_frames, cfg->T, cfg->step);
+    if (first_window < 0 || count < 0 || first_window + count > nw)
+        DOF_FAIL(DOF_ERR_ARG, "windows [%lld, %lld) outside [0, %lld)", first_window, first_window + count, nw);
+    DOF_TRY(loader_device_check());
+    int wpb = 8;
+    LoaderSmem so = loader_smem(p.T, p.step, p.N, p.E, wpb);
+    while (so.total > 100 * 1024 && wpb > 4) { wpb -= 4; so = loader_smem(p.T, p.step, p.N, p.E, wpb); }
+    if (so.total > 220 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "window tile needs %zu B of shared memory", so.total);
+    p.w_start = first_window; p.B = count; p.wpb = wpb; p.x = x; p.a = a;
+    p.bulk_in = ((uintptr_t)frames % 16 == 0) ? 1 : 0;
+    p.bulk_out = ((uintptr_t)x % 16 == 0 && (uintptr_t)a % 16 == 0) ? 1 : 0;
+    static size_t attr_set = 0;
+    if (so.total > 48 * 1024 && so.total > attr_set) {
+        DOF_CUDA(cudaFuncSetAttribute(load_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)so.total));
+        attr_set = so.total;
+    }
+    const double C = 3.0 * p.N + p.E;
+    { ProfScope ps("load_windows", (cudaStream_t)stream, 0.0, ((double)(count - 1) * p.step + p.T) * 2 * p.N * 4 + (double)count * p.T * C * 4);
+    load_windows_kernel<<<cdiv(count, wpb), LD_THREADS, so.total, (cudaStream_t)stream>>>(p, so); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+int dof_loader_pair_length(const float* frames, long long n_frames, int N, int node_a, int node_b, double* out, void* stream) {
+    if (!frames || !out || N < 1 || node_a < 0 || node_a >= N || node_b < 0 || node_b >= N) DOF_FAIL(DOF_ERR_ARG, "bad argument");
+    if (n_frames <= 0) return DOF_OK;
+    DOF_TRY(loader_device_check());
+    int grid = cdiv(n_frames, 256) < g_sm_count * 8 ? cdiv(n_frames, 256) : g_sm_count * 8;
+    { ProfScope ps("loader_pair_length", (cudaStream_t)stream);
+    loader_pair_length_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, n_frames, N, node_a, node_b, out); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+int dof_loader_moments(const dof_loader_cfg* cfg, const float* frames, long long n_frames, const double* shift3, double* out9,
+                       void* stream) {
+    LoaderP p;
+    DOF_TRY(loader_params(cfg, frames, n_frames, p));
+    if (!shift3 || !out9) DOF_FAIL(DOF_ERR_ARG, "null argument");
+    if (n_frames <= 0) return DOF_OK;
+    DOF_TRY(loader_device_check());
+    const long long total = n_frames * (3LL * p.N + p.E);
+    int grid = cdiv(total, 256) < g_sm_count * 8 ? cdiv(total, 256) : g_sm_count * 8;
+    { ProfScope ps("loader_moments", (cudaStream_t)stream);
+    loader_moments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, shift3[0], shift3[1], shift3[2], out9); }
+    DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
 

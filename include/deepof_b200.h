@@ -142,6 +142,46 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
 int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m, float* adam_v,
                   const dof_adam_cfg* opt, void* stream);
 
+/* ---- window loader: raw pose frames -> x [B,T,N,3], a [B,T,E,1]   -------------
+ * Replaces, for one video, the reference's CPU chain between a pose table and its window store:
+ * centre (deepof/data.py:1844-1869), align (data.py:1878-1928 -> deepof/utils.py:2097-2142, 1298-1319),
+ * rolling_speed (utils.py:3788-3857), edge lengths (utils.py:863-881), scale_table (utils.py:2425-2566),
+ * _pp_apply_global (utils.py:2866-2921), clip + interpolate + sanitize (utils.py:2990-3004, 2577-2583),
+ * rolling_window (utils.py:3354-3377) and reorder_and_reshape (deepof/clustering/dataset.py:16-26).
+ * Every scaler is affine, so the host folds them into one (scale, shift) per column:
+ *   coords  z = r * coord_scale + coord_shift          r = centred, aligned coordinate
+ *   speeds  z = v * speed_scale[n] + speed_shift[n]    v = round(mean3(|p_t - p_{t-2}| / 2), 3) * fps
+ *   edges   z = log1p(max(d / dist_div[e], 0)) * dist_scale[e] + dist_shift[e]
+ * then |z| > clip -> linear interpolation along the frame axis (nearest valid frames on both sides,
+ * edge-filled at the ends, 0 if a column has no valid frame).  The per-column arrays and `edges` are
+ * HOST arrays (copied into the launch); `frames` [n_frames,N,2], x, a are DEVICE arrays.
+ * Window w covers frames w*step .. w*step + T - 1. */
+typedef struct {
+    int T, step, N, E;
+    int center_node;           /* body part to centre on, or -1: arena centre (cx, cy) */
+    int align_node;            /* body part rotated onto +y, or -1: no alignment       */
+    double cx, cy, fps;
+    double clip;               /* 10 in the reference (interpolate_normalized); <= 0 disables */
+    double coord_scale, coord_shift;
+    const double* speed_scale; const double* speed_shift;                       /* [N] */
+    const double* dist_div; const double* dist_scale; const double* dist_shift; /* [E] */
+    const int* edges;                                                           /* [E,2] */
+} dof_loader_cfg;
+
+long long dof_loader_num_windows(long long n_frames, int T, int step);
+int dof_load_windows(const dof_loader_cfg* cfg, const float* frames, long long n_frames, long long first_window,
+                     int count, float* x, float* a, void* stream);
+/* out[f] = |p_a(f) - p_b(f)| (fp64, DEVICE [n_frames]); the size factor of scale_table is its nanmedian
+ * (utils.py:2478-2489). */
+int dof_loader_pair_length(const float* frames, long long n_frames, int N, int node_a, int node_b, double* out,
+                           void* stream);
+/* Moments of the columns as configured by cfg (clip is honoured; pass clip <= 0 for scaler fits), NaNs
+ * skipped, per group g in {coords, speeds, edges}: out9[3g] += count, out9[3g+1] += sum(z - shift3[g]),
+ * out9[3g+2] += sum((z - shift3[g])^2).  out9 (DEVICE, fp64) is accumulated into, not cleared: this is
+ * what the groupwise StandardScaler fits of scale_table / _pp_fit_global_scaler see. */
+int dof_loader_moments(const dof_loader_cfg* cfg, const float* frames, long long n_frames, const double* shift3,
+                       double* out9, void* stream);
+
 /* Debug / test access to intermediate activations of the last forward (device pointers into
  * the workspace; NULL if unknown).  Names: "node_out","edge_out","enc","z","z_mean",
  * "z_log_var","q","loc","len_node","len_edge". */
