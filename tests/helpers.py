@@ -34,3 +34,13 @@ def rel_l2(a, b):
     a = torch.as_tensor(a, dtype=torch.float64).flatten()
     b = torch.as_tensor(b, dtype=torch.float64).flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def golden_cases_of(kind):
+    return sorted(os.path.basename(f)[len(kind) + 1:-len(".npz")]
+                  for f in glob.glob(os.path.join(GOLDEN_DIR, f"{kind}_*.npz")))
+
+
+def load_golden_of(kind, name):
+    z = np.load(os.path.join(GOLDEN_DIR, f"{kind}_{name}.npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
