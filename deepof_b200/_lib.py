@@ -17,7 +17,10 @@ LOG_KEYS = ("total_loss", "reconstruct_loss", "kl_div", "cat_clust_loss", "kmean
 
 
 class DofConfig(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("T", "N", "E", "F", "Fe", "D", "K")]
+    _fields_ = [(n, C.c_int) for n in ("T", "N", "E", "F", "Fe", "D", "K", "model")]
+
+
+MODEL_VADE, MODEL_VQVAE, MODEL_CONTRASTIVE = 0, 1, 2
 
 
 class DofVadeLossCfg(C.Structure):
@@ -37,7 +40,7 @@ class DofVadeLossCfg(C.Structure):
 
 class DofAdamCfg(C.Structure):
     _fields_ = [("lr", C.c_float * 4), ("step", C.c_int * 4), ("active", C.c_int * 4),
-                ("clip_value", C.c_float), ("grad_scale", C.c_float), ("beta1", C.c_float),
+                ("weight_decay", C.c_float * 4), ("clip_value", C.c_float), ("grad_scale", C.c_float), ("beta1", C.c_float),
                 ("beta2", C.c_float), ("eps", C.c_float)]
 
 
@@ -48,6 +51,13 @@ class DofLoaderCfg(C.Structure):
                 ("speed_scale", C.POINTER(C.c_double)), ("speed_shift", C.POINTER(C.c_double)),
                 ("dist_div", C.POINTER(C.c_double)), ("dist_scale", C.POINTER(C.c_double)),
                 ("dist_shift", C.POINTER(C.c_double)), ("edges", C.POINTER(C.c_int))]
+
+
+class DofViewsCfg(C.Structure):
+    _fields_ = [("T_full", C.c_int), ("N", C.c_int), ("E", C.c_int), ("edges", C.POINTER(C.c_int)),
+                ("start", C.c_void_p), ("n_rot", C.c_int), ("rot_pivot", C.c_int * 8), ("rot_mask", C.c_uint * 8),
+                ("rot_theta", C.c_void_p), ("interp_t0", C.c_void_p), ("interp_len", C.c_void_p),
+                ("noise", C.c_void_p)]
 
 
 class DofError(RuntimeError):
@@ -75,6 +85,11 @@ _SIGS = {
     "dof_vade_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P,
                                      C.POINTER(DofVadeLossCfg), _P, _P]),
     "dof_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(DofAdamCfg), _P]),
+    "dof_encode": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
+    "dof_vqvae_forward_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "dof_vqvae_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P, _P]),
+    "dof_contrastive_views": (C.c_int, [C.POINTER(DofViewsCfg), _P, C.c_int, _P, _P, _P]),
+    "dof_contrastive_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P]),
     "dof_loader_num_windows": (C.c_longlong, [C.c_longlong, C.c_int, C.c_int]),
     "dof_load_windows": (C.c_int, [C.POINTER(DofLoaderCfg), _P, C.c_longlong, C.c_longlong, C.c_int, _P, _P, _P]),
     "dof_loader_pair_length": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -12,9 +12,11 @@
 #include "layers.cuh"
 #include "loss.cuh"
 #include "loader.cuh"
+#include "models.cuh"
 
 thread_local char g_dof_err[512] = {0};
 DofProf g_prof;
+extern "C" { static int loader_device_check(); }
 
 // ---------------------------------------------------------------------------
 // state layout  (reference VaDEPT.state_dict() order)
@@ -39,6 +41,7 @@ struct Layout {
     GruP dg1, dg2;
     int64_t dn1w, dn1b, dn2w, dn2b, dconv, dn3w, dn3b, loc_w, loc_b;
     int64_t gmm_mu, gmm_lv, prior, pretrain, Wm, bm, Wv, bv, lens_w, lens_b;
+    int64_t codebook;
 };
 
 static int64_t add_entry(Layout& L, const std::string& name, int group, int d0, int d1 = -1, int d2 = -1) {
@@ -99,6 +102,7 @@ static Layout build_layout(const dof_config& c) {
     L.edge_bias = add_entry(L, g + "edge_bias", 1, D);
     L.final_w = add_entry(L, "encoder.final_dense.weight", 1, D, (N + E) * D);
     L.final_b = add_entry(L, "encoder.final_dense.bias", 1, D);
+    if (c.model == DOF_MODEL_CONTRASTIVE) return L;          // ContrastivePT: encoder only (models_new.py:2030-2057)
     add_gru(L, "decoder.gru1.", 2, D, D, L.dg1);
     L.dn1w = add_entry(L, "decoder.norm1.weight", 2, 2 * D);
     L.dn1b = add_entry(L, "decoder.norm1.bias", 2, 2 * D);
@@ -110,6 +114,10 @@ static Layout build_layout(const dof_config& c) {
     L.dn3b = add_entry(L, "decoder.norm3.bias", 2, 2 * D);
     L.loc_w = add_entry(L, "decoder.prob_decoder.loc_projection.weight", 2, N * c.F, 2 * D);
     L.loc_b = add_entry(L, "decoder.prob_decoder.loc_projection.bias", 2, N * c.F);
+    if (c.model == DOF_MODEL_VQVAE) {                        // VQVAEPT: vq_layer.codebook [D,K] (models_new.py:1349-1351)
+        L.codebook = add_entry(L, "vq_layer.codebook", 3, D, K);
+        return L;
+    }
     L.gmm_mu = add_entry(L, "latent_space.gmm_means", 3, K, D);
     L.gmm_lv = add_entry(L, "latent_space.gmm_log_vars", 3, K, D);
     L.prior = add_entry(L, "latent_space.prior", 0, K);
@@ -128,7 +136,9 @@ static int check_cfg(const dof_config* c) {
     if (c->T < 1 || c->N < 1 || c->E < 1 || c->F < 1 || c->Fe < 1 || c->D < 1 || c->K < 1)
         DOF_FAIL(DOF_ERR_ARG, "bad geometry T=%d N=%d E=%d F=%d Fe=%d D=%d K=%d", c->T, c->N, c->E, c->F,
                  c->Fe, c->D, c->K);
-    if (c->K > LOSS_MAXK) DOF_FAIL(DOF_ERR_UNSUPPORTED, "n_components %d > %d", c->K, LOSS_MAXK);
+    if (c->model < DOF_MODEL_VADE || c->model > DOF_MODEL_CONTRASTIVE) DOF_FAIL(DOF_ERR_ARG, "unknown model kind %d", c->model);
+    if (c->model == DOF_MODEL_VADE && c->K > LOSS_MAXK) DOF_FAIL(DOF_ERR_UNSUPPORTED, "n_components %d > %d", c->K, LOSS_MAXK);
+    if (c->model == DOF_MODEL_VQVAE && (size_t)c->D * c->K * 4 > 96 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "codebook %d x %d does not fit in shared memory", c->D, c->K);
     if (c->D > 32) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 32 not supported by the GRU kernels yet", c->D);
     return DOF_OK;
 }
@@ -173,6 +183,10 @@ struct dof_handle {
     float *dloc, *dYD3, *dCd, *dYD2, *dHD2, *dGD2[2], *dYD1, *dHD1, *dGD1[2], *dGs[2], *Wt;
     // loss
     double* stats; float *coef, *dzm_kl, *dlv_kl, *distw;
+    // VQ-VAE
+    float *quant, *soft; int* vidx; double* vstats;
+    // contrastive
+    float *zn, *nrm, *lse; double* nstats;
     int lastB;
     std::map<std::string, std::pair<const void*, int64_t>> dbg;
 };
@@ -217,10 +231,27 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
         }
     }
     const size_t Bz = (size_t)B, BT = Bz * T;
+    const int model = c.model;
     h->Pn = bp.get<float>(Bz * N * 2 * D); h->Pe = bp.get<float>(Bz * E * 2 * D);
     h->On = bp.get<float>(Bz * N * D); h->Oe = bp.get<float>(Bz * E * D);
-    h->enc = bp.get<float>(Bz * D); h->zm = bp.get<float>(Bz * D); h->pre = bp.get<float>(Bz * D);
-    h->lv = bp.get<float>(Bz * D); h->z = bp.get<float>(Bz * D); h->q = bp.get<float>(Bz * K);
+    h->enc = bp.get<float>(Bz * D);
+    if (tr) {
+        h->dOn = bp.get<float>(Bz * N * D); h->dOe = bp.get<float>(Bz * E * D);
+        h->dPn = bp.get<float>(Bz * N * 2 * D); h->dPe = bp.get<float>(Bz * E * 2 * D);
+        h->denc = bp.get<float>(Bz * D);
+    }
+    if (model == DOF_MODEL_CONTRASTIVE) {
+        h->zn = bp.get<float>(Bz * D); h->nrm = bp.get<float>(Bz); h->lse = bp.get<float>(Bz);
+        h->nstats = bp.get<double>(8);
+        return;
+    }
+    if (model == DOF_MODEL_VADE) {
+        h->zm = bp.get<float>(Bz * D); h->pre = bp.get<float>(Bz * D);
+        h->lv = bp.get<float>(Bz * D); h->z = bp.get<float>(Bz * D); h->q = bp.get<float>(Bz * K);
+    } else {
+        h->quant = bp.get<float>(Bz * D); h->soft = bp.get<float>(Bz * K); h->vidx = bp.get<int>(Bz);
+        h->vstats = bp.get<double>((size_t)VQ_ST_GRAM + (size_t)D * D + K);
+    }
     h->lenD = bp.get<int>(Bz);
     for (int d = 0; d < 2; d++) h->GiD1[d] = bp.get<float>(Bz * 3 * D);
     h->HD1 = bp.get<float>(BT * 2 * D);
@@ -237,9 +268,7 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
     h->YD3 = bp.get<float>(BT * 2 * D);
     h->loc = bp.get<float>(BT * N * c.F);
     if (tr) {
-        h->dOn = bp.get<float>(Bz * N * D); h->dOe = bp.get<float>(Bz * E * D);
-        h->dPn = bp.get<float>(Bz * N * 2 * D); h->dPe = bp.get<float>(Bz * E * 2 * D);
-        h->denc = bp.get<float>(Bz * D); h->dzm = bp.get<float>(Bz * D); h->dpre = bp.get<float>(Bz * D);
+        if (model == DOF_MODEL_VADE) { h->dzm = bp.get<float>(Bz * D); h->dpre = bp.get<float>(Bz * D); }
         h->dz_dec = bp.get<float>(Bz * D);
         h->dloc = bp.get<float>(BT * N * c.F);
         h->dYD3 = bp.get<float>(BT * 2 * D); h->dCd = bp.get<float>(BT * 2 * D);
@@ -249,6 +278,7 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
         for (int d = 0; d < 2; d++) h->dGD1[d] = bp.get<float>(BT * 4 * D);
         for (int d = 0; d < 2; d++) h->dGs[d] = bp.get<float>(Bz * 4 * D);
         h->Wt = bp.get<float>((size_t)4 * D * 2 * D * 5);
+        if (model != DOF_MODEL_VADE) return;
         StatsLayout SL = stats_layout(D, K);
         CoefLayout CL = coef_layout(D, K);
         h->stats = bp.get<double>(SL.total);
@@ -489,10 +519,10 @@ static CensArgs cens_args(dof_handle* h, const float* state, int B) {
 }
 
 static int encoder_forward(dof_handle* h, const float* state, const float* x, const float* a, int B, bool train,
-                           const float* eps, cudaStream_t st) {
+                           cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
-    const int N = c.N, E = c.E, D = c.D, K = c.K;
+    const int N = c.N, E = c.E, D = c.D;
     DOF_TRY(enc_block_forward(h, 0, state, x, B, train, st));
     DOF_TRY(enc_block_forward(h, 1, state, a, B, train, st));
     CensArgs ca = cens_args(h, state, B);
@@ -517,6 +547,14 @@ static int encoder_forward(dof_handle* h, const float* state, const float* x, co
     GemmArgs f1 = gemm_args(mv_plain(h->Oe, E * D), state + L.final_w + (size_t)N * D, (N + E) * D, 0, nullptr, h->enc, D, B, D, E * D);
     f1.accum = 1;
     DOF_TRY(launch_gemm_rows(&f1, 1, st));
+    return DOF_OK;
+}
+
+// GaussianMixtureLatentPT (models_new.py:1679-1791): latent heads, reparameterisation, GMM posterior
+static int vade_latent_forward(dof_handle* h, const float* state, int B, const float* eps, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int D = c.D, K = c.K;
     LatentArgs la;
     la.enc = h->enc; la.Wm = state + L.Wm; la.bm = state + L.bm; la.Wv = state + L.Wv; la.bv = state + L.bv;
     la.eps = eps; la.gmm_mu = state + L.gmm_mu; la.gmm_lv = state + L.gmm_lv; la.prior = state + L.prior;
@@ -528,14 +566,15 @@ static int encoder_forward(dof_handle* h, const float* state, const float* x, co
     return DOF_OK;
 }
 
-static int decoder_forward(dof_handle* h, const float* state, const float* x, int B, bool train, cudaStream_t st) {
+static int decoder_forward(dof_handle* h, const float* state, const float* zin, const float* x, int B, bool train,
+                           cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T;
     { ProfScope ps("row_valid_len", st);
     row_valid_len_kernel<<<cdiv(B, 128), 128, 0, st>>>(x, h->lenD, B, T, NF); }
     DOF_LAUNCH_CHECK();
-    DOF_TRY(gru_input_proj(state, L.dg1, mv_plain(h->z, D), B, D, D, h->GiD1, st));
+    DOF_TRY(gru_input_proj(state, L.dg1, mv_plain(zin, D), B, D, D, h->GiD1, st));
     GruFwdArgs f;
     memset(&f, 0, sizeof(f));
     for (int d = 0; d < 2; d++) {
@@ -576,6 +615,8 @@ static void register_debug(dof_handle* h, int B) {
     h->dbg["cens_node"] = {h->On, (int64_t)B * c.N * c.D};
     h->dbg["cens_edge"] = {h->Oe, (int64_t)B * c.E * c.D};
     h->dbg["enc"] = {h->enc, (int64_t)B * c.D};
+    h->dbg["quant"] = {h->quant, (int64_t)B * c.D};
+    h->dbg["soft"] = {h->soft, (int64_t)B * c.K};
     h->dbg["z"] = {h->z, (int64_t)B * c.D};
     h->dbg["z_mean"] = {h->zm, (int64_t)B * c.D};
     h->dbg["z_log_var"] = {h->lv, (int64_t)B * c.D};
@@ -620,7 +661,7 @@ static int gru_param_grads(dof_handle* h, const GruP& g, float* grad, const floa
     return DOF_OK;
 }
 
-static int decoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
+static int decoder_backward(dof_handle* h, const float* state, float* grad, const float* zin, int B, cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T, sm = h->sm_count;
@@ -654,7 +695,7 @@ static int decoder_backward(dof_handle* h, const float* state, float* grad, int 
         sum_over_t_kernel<<<cdiv((long long)B * 4 * D, 256), 256, 0, st>>>(h->dGD1[d], h->dGs[d], B, T, 4 * D, 0); }
         DOF_LAUNCH_CHECK();
     }
-    DOF_TRY(gru_param_grads(h, L.dg1, grad, state, h->dGD1, mv_plain(h->z, D), B, h->dGs, h->HD1, M, T, D, D, h->dz_dec,
+    DOF_TRY(gru_param_grads(h, L.dg1, grad, state, h->dGD1, mv_plain(zin, D), B, h->dGs, h->HD1, M, T, D, D, h->dz_dec,
                             nullptr, st));
     return DOF_OK;
 }
@@ -688,11 +729,11 @@ static int enc_block_backward(dof_handle* h, int bi, const float* state, float* 
     return DOF_OK;
 }
 
-static int encoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
+// gradient of the latent heads: dzm, dpre -> parameter gradients and d enc
+static int vade_latent_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
-    const int N = c.N, E = c.E, D = c.D, sm = h->sm_count;
-    // latent heads
+    const int D = c.D, sm = h->sm_count;
     WGradArgs wl[2];
     wl[0] = wgrad_args(mv_plain(h->dzm, D), mv_plain(h->enc, D), grad + L.Wm, D, 0, grad + L.bm, B, D, D);
     wl[1] = wgrad_args(mv_plain(h->dpre, D), mv_plain(h->enc, D), grad + L.Wv, D, 0, grad + L.bv, B, D, D);
@@ -702,6 +743,14 @@ static int encoder_backward(dof_handle* h, const float* state, float* grad, int 
     ge = gemm_args(mv_plain(h->dpre, D), state + L.Wv, D, 1, nullptr, h->denc, D, B, D, D);
     ge.accum = 1;
     DOF_TRY(launch_gemm_rows(&ge, 1, st));
+    return DOF_OK;
+}
+
+// backward of RecurrentEncoderPT from h->denc (gradient wrt the encoder output)
+static int encoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int N = c.N, E = c.E, D = c.D, sm = h->sm_count;
     // final dense
     WGradArgs wf = wgrad_args(mv_plain(h->denc, D), mv_plain(h->On, N * D), grad + L.final_w, (N + E) * D, 0, grad + L.final_b, B, D, N * D);
     DOF_TRY(launch_gemm_wgrad(&wf, 1, st, sm));
@@ -749,8 +798,10 @@ int dof_vade_forward_eval(dof_handle* h, const float* state, const float* x, con
     if (!state || !x || !a) DOF_FAIL(DOF_ERR_ARG, "null input");
     cudaStream_t st = (cudaStream_t)stream;
     const dof_config& c = h->cfg;
-    DOF_TRY(encoder_forward(h, state, x, a, B, false, nullptr, st));
-    if (loc) DOF_TRY(decoder_forward(h, state, x, B, false, st));
+    if (c.model != DOF_MODEL_VADE) DOF_FAIL(DOF_ERR_ARG, "handle is not a VaDE model");
+    DOF_TRY(encoder_forward(h, state, x, a, B, false, st));
+    DOF_TRY(vade_latent_forward(h, state, B, nullptr, st));
+    if (loc) DOF_TRY(decoder_forward(h, state, h->z, x, B, false, st));
     if (enc) DOF_CUDA(cudaMemcpyAsync(enc, h->enc, (size_t)B * c.D * 4, cudaMemcpyDeviceToDevice, st));
     if (emb) DOF_CUDA(cudaMemcpyAsync(emb, h->zm, (size_t)B * c.D * 4, cudaMemcpyDeviceToDevice, st));
     if (q) DOF_CUDA(cudaMemcpyAsync(q, h->q, (size_t)B * c.K * 4, cudaMemcpyDeviceToDevice, st));
@@ -780,15 +831,17 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
     const Layout& L = h->L;
     const int D = c.D, K = c.K, T = c.T, NF = c.N * c.F;
     DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)L.total * 4, st));
-    DOF_TRY(encoder_forward(h, state, x, a, B, true, eps, st));
-    DOF_TRY(decoder_forward(h, state, x, B, true, st));
+    if (c.model != DOF_MODEL_VADE) DOF_FAIL(DOF_ERR_ARG, "handle is not a VaDE model");
+    DOF_TRY(encoder_forward(h, state, x, a, B, true, st));
+    DOF_TRY(vade_latent_forward(h, state, B, eps, st));
+    DOF_TRY(decoder_forward(h, state, h->z, x, B, true, st));
     // ---- loss
     StatsLayout SL = stats_layout(D, K);
     DOF_CUDA(cudaMemsetAsync(h->stats, 0, (size_t)SL.total * sizeof(double), st));
     const long long nrec = (long long)B * T * NF;
     int rgrid = (int)((nrec + 255) / 256 < (long long)h->sm_count * 8 ? (nrec + 255) / 256 : (long long)h->sm_count * 8);
     { ProfScope ps("recon", st, 0.0, 12.0 * nrec);
-    recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->stats); }
+    recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->stats + ST_RECON); }
     DOF_LAUNCH_CHECK();
     LossArgs la;
     memset(&la, 0, sizeof(la));
@@ -815,13 +868,204 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
     loss_finalize_kernel<<<1, 256, loss_finalize_smem_bytes(D, K), st>>>(la); }
     DOF_LAUNCH_CHECK();
     // ---- backward
-    DOF_TRY(decoder_backward(h, state, grad, B, st));
+    DOF_TRY(decoder_backward(h, state, grad, h->z, B, st));
     { ProfScope ps("loss_grad", st);
     loss_grad_kernel<<<lgrid, LS_WARPS * 32, loss_grad_smem_floats(D, K) * 4, st>>>(la); }
     DOF_LAUNCH_CHECK();
+    DOF_TRY(vade_latent_backward(h, state, grad, B, st));
     DOF_TRY(encoder_backward(h, state, grad, B, st));
     h->lastB = B;
     register_debug(h, B);
+    return DOF_OK;
+}
+
+// ---- encoder only: model.encoder(x, a)  (RecurrentEncoderPT.forward, models_new.py:140-181) -------------
+int dof_encode(dof_handle* h, const float* state, const float* x, const float* a, int B, float* enc, void* stream) {
+    DOF_TRY(check_batch(h, B));
+    if (!state || !x || !a || !enc) DOF_FAIL(DOF_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DOF_TRY(encoder_forward(h, state, x, a, B, false, st));
+    DOF_CUDA(cudaMemcpyAsync(enc, h->enc, (size_t)B * h->cfg.D * 4, cudaMemcpyDeviceToDevice, st));
+    h->lastB = B;
+    register_debug(h, B);
+    return DOF_OK;
+}
+
+// ---- VQ-VAE --------------------------------------------------------------------------------------------
+static int vq_forward(dof_handle* h, const float* state, int B, bool want_gram, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    VqArgs v;
+    v.z = h->enc; v.codebook = state + h->L.codebook; v.quant = h->quant; v.soft = h->soft; v.idx = h->vidx;
+    v.stats = h->vstats; v.B = B; v.D = c.D; v.K = c.K; v.want_gram = want_gram ? 1 : 0;
+    if (c.D > VQ_MAXD) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > %d", c.D, VQ_MAXD);
+    DOF_CUDA(cudaMemsetAsync(h->vstats, 0, ((size_t)VQ_ST_GRAM + (size_t)c.D * c.D + c.K) * sizeof(double), st));
+    size_t smem = ((size_t)c.D * c.K + c.K + (size_t)c.D * c.D) * 4;
+    static size_t attr = 48 * 1024;
+    if (smem > attr) { DOF_CUDA(cudaFuncSetAttribute(vq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    { ProfScope ps("vq_fwd", st, 0.0, (double)B * (8.0 * c.D + 4.0 + 4.0 * c.K));
+    vq_fwd_kernel<<<cdiv(B, 128), 128, smem, st>>>(v); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+int dof_vqvae_forward_eval(dof_handle* h, const float* state, const float* x, const float* a, int B, float* enc, float* quant,
+                           float* soft, int* idx, float* loc_q, float* loc_e, void* stream) {
+    DOF_TRY(check_batch(h, B));
+    const dof_config& c = h->cfg;
+    if (c.model != DOF_MODEL_VQVAE) DOF_FAIL(DOF_ERR_ARG, "handle is not a VQ-VAE model");
+    if (!state || !x || !a) DOF_FAIL(DOF_ERR_ARG, "null input");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nl = (size_t)B * c.T * c.N * c.F * 4;
+    DOF_TRY(encoder_forward(h, state, x, a, B, false, st));
+    DOF_TRY(vq_forward(h, state, B, false, st));
+    if (enc) DOF_CUDA(cudaMemcpyAsync(enc, h->enc, (size_t)B * c.D * 4, cudaMemcpyDeviceToDevice, st));
+    if (quant) DOF_CUDA(cudaMemcpyAsync(quant, h->quant, (size_t)B * c.D * 4, cudaMemcpyDeviceToDevice, st));
+    if (soft) DOF_CUDA(cudaMemcpyAsync(soft, h->soft, (size_t)B * c.K * 4, cudaMemcpyDeviceToDevice, st));
+    if (idx) DOF_CUDA(cudaMemcpyAsync(idx, h->vidx, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    if (loc_q) {
+        DOF_TRY(decoder_forward(h, state, h->quant, x, B, false, st));
+        DOF_CUDA(cudaMemcpyAsync(loc_q, h->loc, nl, cudaMemcpyDeviceToDevice, st));
+    }
+    if (loc_e) {
+        DOF_TRY(decoder_forward(h, state, h->enc, x, B, false, st));
+        DOF_CUDA(cudaMemcpyAsync(loc_e, h->loc, nl, cudaMemcpyDeviceToDevice, st));
+    }
+    h->lastB = B;
+    register_debug(h, B);
+    return DOF_OK;
+}
+
+// step_vqvae_distill forward + backward without teacher (training.py:312-389): loss = NLL(decoder(quantized)) +
+// NLL(decoder(encoder output)) + float(vq_loss) + float(kmeans_loss).  The encoder learns through the bypass
+// decoder only; the codebook through the one-hot matmul of the quantized path (there is no straight-through).
+int dof_vqvae_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B, float beta,
+                        float kmeans_weight, float* logs, void* stream) {
+    DOF_TRY(check_batch(h, B));
+    const dof_config& c = h->cfg;
+    if (c.model != DOF_MODEL_VQVAE) DOF_FAIL(DOF_ERR_ARG, "handle is not a VQ-VAE model");
+    if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
+    if (!state || !grad || !x || !a || !logs) DOF_FAIL(DOF_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    const int D = c.D, K = c.K, T = c.T, NF = c.N * c.F;
+    DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)L.total * 4, st));
+    DOF_TRY(encoder_forward(h, state, x, a, B, true, st));
+    DOF_TRY(vq_forward(h, state, B, kmeans_weight != 0.f, st));
+    const long long nrec = (long long)B * T * NF;
+    int rgrid = (int)((nrec + 255) / 256 < (long long)h->sm_count * 8 ? (nrec + 255) / 256 : (long long)h->sm_count * 8);
+    for (int pass = 0; pass < 2; pass++) {
+        const float* zin = pass == 0 ? h->quant : h->enc;
+        DOF_TRY(decoder_forward(h, state, zin, x, B, true, st));
+        { ProfScope ps("recon", st, 0.0, 12.0 * nrec);
+        recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->vstats + (pass == 0 ? VQ_ST_REC_Q : VQ_ST_REC_E)); }
+        DOF_LAUNCH_CHECK();
+        DOF_TRY(decoder_backward(h, state, grad, zin, B, st));
+        if (pass == 0) {
+            { ProfScope ps("vq_codebook_grad", st);
+            vq_codebook_grad_kernel<<<cdiv((long long)B * D, 256), 256, 0, st>>>(h->dz_dec, h->vidx, grad + L.codebook, B, D, K); }
+            DOF_LAUNCH_CHECK();
+        }
+    }
+    DOF_CUDA(cudaMemcpyAsync(h->denc, h->dz_dec, (size_t)B * D * 4, cudaMemcpyDeviceToDevice, st));
+    DOF_TRY(encoder_backward(h, state, grad, B, st));
+    VqFinalArgs f;
+    f.stats = h->vstats; f.logs = logs; f.B = B; f.T = T; f.Dx = NF; f.D = D; f.K = K; f.beta = beta; f.kmeans_w = kmeans_weight;
+    { ProfScope ps("vq_finalize", st);
+    vq_finalize_kernel<<<1, 32, (size_t)2 * D * D * sizeof(double), st>>>(f); }
+    DOF_LAUNCH_CHECK();
+    h->lastB = B;
+    register_debug(h, B);
+    return DOF_OK;
+}
+
+// ---- contrastive -------------------------------------------------------------------------------------------
+int dof_contrastive_views(const dof_views_cfg* v, const float* x_full, int B, float* x2, float* a2, void* stream) {
+    if (!v || !x_full || !x2 || !a2 || !v->start || B < 1) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    if (v->T_full < 2 || v->N < 1 || v->N > VW_MAXN || v->E < 0 || v->E > LD_MAXE || v->n_rot < 0 || v->n_rot > VW_MAXROT)
+        DOF_FAIL(DOF_ERR_UNSUPPORTED, "views: T_full=%d N=%d (<= %d) E=%d (<= %d) n_rot=%d (<= %d)", v->T_full, v->N, VW_MAXN, v->E,
+                 LD_MAXE, v->n_rot, VW_MAXROT);
+    if (v->E > 0 && !v->edges) DOF_FAIL(DOF_ERR_ARG, "null edges");
+    if (v->n_rot > 0 && !v->rot_theta) DOF_FAIL(DOF_ERR_ARG, "null rot_theta");
+    if ((v->interp_t0 == nullptr) != (v->interp_len == nullptr)) DOF_FAIL(DOF_ERR_ARG, "interp_t0 / interp_len must both be given");
+    DOF_TRY(loader_device_check());
+    ViewsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x_full = x_full; a.x2 = x2; a.a2 = a2; a.start = v->start; a.rot_theta = v->rot_theta; a.interp_t0 = v->interp_t0;
+    a.interp_len = v->interp_len; a.noise = v->noise; a.B = B; a.Tf = v->T_full; a.Th = v->T_full / 2; a.N = v->N; a.E = v->E;
+    a.n_rot = v->n_rot;
+    a.mid_start = a.Th / 2;                                            // training.py:518-519
+    for (int k = 0; k < v->n_rot; k++) {
+        if (v->rot_pivot[k] < 0 || v->rot_pivot[k] >= v->N) DOF_FAIL(DOF_ERR_ARG, "rotation pivot out of range");
+        a.rot_pivot[k] = v->rot_pivot[k]; a.rot_mask[k] = v->rot_mask[k];
+    }
+    for (int e = 0; e < v->E; e++) {
+        if (v->edges[2 * e] < 0 || v->edges[2 * e] >= v->N || v->edges[2 * e + 1] < 0 || v->edges[2 * e + 1] >= v->N)
+            DOF_FAIL(DOF_ERR_ARG, "edge %d out of range", e);
+        a.e0[e] = (short)v->edges[2 * e]; a.e1[e] = (short)v->edges[2 * e + 1];
+    }
+    const long long total = 2LL * B * a.Th;
+    int grid = cdiv(total, 128) < g_sm_count * 16 ? cdiv(total, 128) : g_sm_count * 16;
+    { ProfScope ps("views", (cudaStream_t)stream, 0.0, (double)B * (1.5 * a.Tf * a.N * 3 * 4 + 2.0 * a.Th * (3 * a.N + a.E) * 4));
+    views_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+}  // extern "C"
+
+template <int DP>
+static int ntx_launch(const NtxArgs& n, int B, cudaStream_t st) {
+    const size_t smem = ((size_t)NTX_TILE * (DP + 1) + NTX_TILE + (size_t)NTX_WARPS * DP) * 4;
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+        DOF_CUDA(cudaFuncSetAttribute(ntx_kernel<0, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DOF_CUDA(cudaFuncSetAttribute(ntx_kernel<1, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    const int nb = cdiv(B, NTX_WARPS);
+    const double fl = 2.0 * B * (double)B * n.D;
+    { ProfScope ps("ntxent_rows", st, fl, 0.0);
+    ntx_kernel<0, DP><<<nb, NTX_WARPS * 32, smem, st>>>(n); }
+    DOF_LAUNCH_CHECK();
+    { ProfScope ps("ntxent_grad", st, 4.0 * fl, 0.0);
+    ntx_kernel<1, DP><<<2 * nb, NTX_WARPS * 32, smem, st>>>(n); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+extern "C" {
+
+// step_contrastive_distill forward + backward without teacher (training.py:527-545, 159-163) on the two views
+// produced by dof_contrastive_views: x2 / a2 rows 0..B-1 = main view, B..2B-1 = augmented view.
+int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
+                              float temperature, float* logs, float* z_out, void* stream) {
+    DOF_TRY(check_batch(h, 2 * B));
+    const dof_config& c = h->cfg;
+    if (c.model != DOF_MODEL_CONTRASTIVE) DOF_FAIL(DOF_ERR_ARG, "handle is not a contrastive model");
+    if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
+    if (!state || !grad || !x2 || !a2 || !logs || !(temperature > 0.f)) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    if (c.D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 64", c.D);
+    cudaStream_t st = (cudaStream_t)stream;
+    DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)h->L.total * 4, st));
+    DOF_TRY(encoder_forward(h, state, x2, a2, 2 * B, true, st));
+    if (z_out) DOF_CUDA(cudaMemcpyAsync(z_out, h->enc, (size_t)2 * B * c.D * 4, cudaMemcpyDeviceToDevice, st));
+    NtxArgs n;
+    n.enc = h->enc; n.zn = h->zn; n.nrm = h->nrm; n.lse = h->lse; n.denc = h->denc; n.stats = h->nstats; n.logs = logs;
+    n.B = B; n.D = c.D; n.inv_tau = 1.0f / temperature;
+    DOF_CUDA(cudaMemsetAsync(h->nstats, 0, 8 * sizeof(double), st));
+    { ProfScope ps("ntxent_norm", st);
+    ntx_norm_kernel<<<cdiv(2LL * B * 32, 256), 256, 0, st>>>(n); }
+    DOF_LAUNCH_CHECK();
+    if (c.D <= 8) DOF_TRY(ntx_launch<8>(n, B, st));
+    else if (c.D <= 16) DOF_TRY(ntx_launch<16>(n, B, st));
+    else if (c.D <= 32) DOF_TRY(ntx_launch<32>(n, B, st));
+    else DOF_TRY(ntx_launch<64>(n, B, st));
+    { ProfScope ps("ntxent_finalize", st);
+    ntx_finalize_kernel<<<1, 1, 0, st>>>(n, temperature); }
+    DOF_LAUNCH_CHECK();
+    DOF_TRY(encoder_backward(h, state, grad, 2 * B, st));
+    h->lastB = 2 * B;
+    register_debug(h, 2 * B);
     return DOF_OK;
 }
 
@@ -833,6 +1077,7 @@ int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m,
     a.p = state; a.g = grad; a.m = adam_m; a.v = adam_v; a.group = h->group; a.n = h->L.total;
     for (int g = 0; g < 4; g++) {
         a.lr[g] = opt->lr[g];
+        a.wd[g] = opt->weight_decay[g];
         a.active[g] = opt->active[g];
         int s = opt->step[g] > 0 ? opt->step[g] : 1;
         a.bc1[g] = (float)(1.0 - pow((double)opt->beta1, s));

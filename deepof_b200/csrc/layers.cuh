@@ -437,7 +437,7 @@ __global__ void conv_w_transpose_kernel(const float* __restrict__ src, float* __
 struct AdamArgs {
     float* p; const float* g; float* m; float* v; const unsigned char* group;
     long long n;
-    float lr[4]; float bc1[4]; float bc2_sqrt[4]; int active[4];
+    float lr[4]; float wd[4]; float bc1[4]; float bc2_sqrt[4]; int active[4];
     float clip; float gscale; float beta1, beta2, eps;
 };
 
@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(const AdamArgs a) {
     if (grp == 0 || !a.active[grp]) return;
     float g = a.g[i] * a.gscale;
     if (a.clip > 0.f) g = fminf(fmaxf(g, -a.clip), a.clip);
+    g += a.wd[grp] * a.p[i];          // torch.optim.Adam(weight_decay): L2 term added after clip_grad_value_
     float m = a.beta1 * a.m[i] + (1.0f - a.beta1) * g;
     float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
     a.m[i] = m;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ lo
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
-        atomicAdd(stats + ST_RECON, t);
+        atomicAdd(stats, t);          // `stats` points at the slot
     }
 }
 

@@ -1,0 +1,357 @@
+// Kernels of the VQ-VAE and contrastive paths that sit around the shared recurrent encoder / decoder.
+//
+//   vq_fwd_kernel          VectorQuantizerPT.forward  (deepof/clustering/models_new.py:1358-1423):
+//                          squared distances to the codebook, argmin, soft counts (1/d)^2 / sum, quantized
+//                          latents, sum (q - z)^2 for the (gradient-free) vq loss, Gram matrix for the
+//                          (gradient-free) kmeans loss, populated-code flags.  HBM-bound: D*4 B in,
+//                          (4 + K*4 + D*4) B out per window; the codebook lives in shared memory.
+//   vq_codebook_grad_kernel  d quantized -> d codebook (one-hot matmul backward, models_new.py:1382-1383)
+//   vq_finalize_kernel     the 7 logged scalars of step_vqvae_distill (deepof/clustering/training.py:380-388)
+//   views_kernel           step_contrastive_distill's inputs (training.py:497-525): recompute_edges,
+//                          middle half-window, and the augmented view of _make_augmented_view
+//                          (training.py:2128-2402: time shift, joint rotations, segment interpolation, offsets)
+//   ntx_*                  normalize + cosine similarity / temperature + cross-entropy against the diagonal
+//                          (training.py:532-545, deepof/clustering/losses.py:59-63, 130-141), value and gradient,
+//                          without materialising the [B,B] similarity matrix.
+#pragma once
+#include "common.cuh"
+#include "loss.cuh"
+#include "loader.cuh"
+
+#define VQ_MAXD 64
+#define VQ_ST_SQ 0       // sum (q - z)^2
+#define VQ_ST_REC_Q 1    // reconstruction NLL sum, decoder(quantized)
+#define VQ_ST_REC_E 2    // reconstruction NLL sum, decoder(encoder output)
+#define VQ_ST_GRAM 4     // D*D Gram sums, then K populated flags
+
+struct VqArgs {
+    const float* z;          // [B,D] encoder output
+    const float* codebook;   // [D,K]
+    float* quant;            // [B,D]
+    float* soft;             // [B,K]
+    int* idx;                // [B]
+    double* stats;           // VQ_ST_* (zeroed by the caller)
+    int B, D, K, want_gram;
+};
+
+// one thread per window; codebook and its column norms in shared memory
+__global__ void __launch_bounds__(128) vq_fwd_kernel(const VqArgs a) {
+    extern __shared__ float vsm[];
+    float* cb = vsm;                  // [D][K]
+    float* ee = cb + a.D * a.K;       // [K]
+    float* gram = ee + a.K;           // [D][D] block partial (want_gram)
+    const int D = a.D, K = a.K, tid = threadIdx.x;
+    for (int i = tid; i < D * K; i += blockDim.x) cb[i] = __ldg(a.codebook + i);
+    if (a.want_gram) for (int i = tid; i < D * D; i += blockDim.x) gram[i] = 0.f;
+    __syncthreads();
+    for (int k = tid; k < K; k += blockDim.x) {
+        float s = 0.f;
+        for (int d = 0; d < D; d++) s += cb[d * K + k] * cb[d * K + k];
+        ee[k] = s;
+    }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + tid;
+    double sq = 0.0;
+    float z[VQ_MAXD];
+    if (b < a.B) {
+        float zz = 0.f;
+#pragma unroll 4
+        for (int d = 0; d < D; d++) { z[d] = __ldg(a.z + (size_t)b * D + d); zz += z[d] * z[d]; }
+        int best = 0;
+        float bestd = INFINITY, ssum = 0.f;
+        for (int k = 0; k < K; k++) {
+            float dot = 0.f;
+            for (int d = 0; d < D; d++) dot += z[d] * cb[d * K + k];
+            const float dist = zz + ee[k] - 2.f * dot;                    // models_new.py:1407-1411
+            if (dist < bestd) { bestd = dist; best = k; }                 // argmin keeps the first minimum
+            const float inv = 1.f / dist;
+            ssum += inv * inv;                                            // :1416
+        }
+        for (int k = 0; k < K; k++) {
+            float dot = 0.f;
+            for (int d = 0; d < D; d++) dot += z[d] * cb[d * K + k];
+            const float inv = 1.f / (zz + ee[k] - 2.f * dot);
+            a.soft[(size_t)b * K + k] = inv * inv / ssum;
+        }
+        a.idx[b] = best;
+        for (int d = 0; d < D; d++) {
+            const float q = cb[d * K + best];
+            a.quant[(size_t)b * D + d] = q;
+            const float df = q - z[d];
+            sq += (double)(df * df);
+        }
+        a.stats[VQ_ST_GRAM + D * D + best] = 1.0;                         // benign race: all writers store 1
+        if (a.want_gram)
+            for (int i = 0; i < D; i++)
+                for (int j = 0; j < D; j++) atomicAdd(gram + i * D + j, z[i] * z[j]);
+    }
+    sq = warp_sum_d(sq);
+    if ((tid & 31) == 0 && sq != 0.0) atomicAdd(a.stats + VQ_ST_SQ, sq);
+    if (a.want_gram) {
+        __syncthreads();
+        for (int i = tid; i < D * D; i += blockDim.x) atomicAdd(a.stats + VQ_ST_GRAM + i, (double)gram[i]);
+    }
+}
+
+__global__ void vq_codebook_grad_kernel(const float* __restrict__ dquant, const int* __restrict__ idx, float* __restrict__ gcb,
+                                        int B, int D, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * D) return;
+    const int b = i / D, d = i - b * D;
+    atomicAdd(gcb + (size_t)d * K + idx[b], dquant[i]);
+}
+
+struct VqFinalArgs {
+    double* stats; float* logs;
+    int B, T, Dx, D, K;
+    float beta, kmeans_w;
+};
+
+// logs: 0 total 1 enc_rec 2 reconstruct 3 vq 4 kmeans 5 populated 6 distill (training.py:380-388)
+__global__ void __launch_bounds__(32) vq_finalize_kernel(const VqFinalArgs a) {
+    extern __shared__ __align__(16) double fsm[];
+    const int D = a.D, lane = threadIdx.x;
+    double* A = fsm;
+    double* V = A + D * D;
+    double km = 0.0;
+    if (a.kmeans_w != 0.f) {
+        for (int i = lane; i < D * D; i += 32) A[i] = a.stats[VQ_ST_GRAM + i] / (double)a.B;
+        __syncwarp();
+        jacobi_eig_warp(A, V, D);
+        double s = 0.0;
+        for (int i = lane; i < D; i += 32) { double ev = fabs(A[i * D + i]); s += sqrt(ev > 1e-9 ? ev : 1e-9); }
+        s = warp_sum_d(s);
+        km = (double)a.kmeans_w * s / D;                                   // losses.py:257-287
+    }
+    double pop = 0.0;
+    for (int k = lane; k < a.K; k += 32) pop += a.stats[VQ_ST_GRAM + D * D + k];
+    pop = warp_sum_d(pop);
+    if (lane == 0) {
+        const double cst = 0.5 * (double)a.Dx * 1.8378770664093453;        // Dx/2 * log(2 pi)
+        const double bt = (double)a.B * a.T;
+        const double encrec = a.stats[VQ_ST_REC_Q] / bt + cst, rec = a.stats[VQ_ST_REC_E] / bt + cst;
+        const double vq = (1.0 + (double)a.beta) * a.stats[VQ_ST_SQ] / ((double)a.B * D);   // models_new.py:1387-1391
+        a.logs[0] = (float)(encrec + rec + vq + km);
+        a.logs[1] = (float)encrec; a.logs[2] = (float)rec; a.logs[3] = (float)vq; a.logs[4] = (float)km;
+        a.logs[5] = (float)pop; a.logs[6] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// contrastive views
+// ---------------------------------------------------------------------------
+#define VW_MAXN 32
+#define VW_MAXROT 8
+struct ViewsArgs {
+    const float* x_full;     // [B, Tf, N, 3]
+    float* x2;               // [2B, Th, N, 3]: rows 0..B-1 the middle half window, B..2B-1 the augmented view
+    float* a2;               // [2B, Th, E, 1]
+    const int* start;        // [B] slice start of the augmented view
+    const float* rot_theta;  // [n_rot, B] radians
+    const int* interp_t0;    // [B] or null
+    const int* interp_len;   // [B] (0 = off)
+    const float* noise;      // [B, N, 3] or null
+    int B, Tf, Th, N, E, n_rot, mid_start;
+    int rot_pivot[VW_MAXROT];
+    unsigned rot_mask[VW_MAXROT];
+    short e0[LD_MAXE], e1[LD_MAXE];
+};
+
+// one row (all nodes of one time step) of the rotated view: training.py:2224-2249, rotations applied in order,
+// each around the CURRENT position of its pivot
+__device__ __forceinline__ void vw_rotated_row(const ViewsArgs& a, int b, int tsrc, float (&px)[VW_MAXN], float (&py)[VW_MAXN],
+                                               float (&ps)[VW_MAXN]) {
+    const float* r = a.x_full + ((size_t)b * a.Tf + tsrc) * a.N * 3;
+    for (int n = 0; n < a.N; n++) { px[n] = r[3 * n]; py[n] = r[3 * n + 1]; ps[n] = r[3 * n + 2]; }
+    for (int k = 0; k < a.n_rot; k++) {
+        const float th = a.rot_theta[(size_t)k * a.B + b];
+        float sn, cs;
+        sincosf(th, &sn, &cs);
+        const float cx = px[a.rot_pivot[k]], cy = py[a.rot_pivot[k]];
+        const unsigned m = a.rot_mask[k];
+        for (int n = 0; n < a.N; n++)
+            if ((m >> n) & 1u) {
+                const float rx = px[n] - cx, ry = py[n] - cy;
+                px[n] = (rx * cs - ry * sn) + cx;
+                py[n] = (rx * sn + ry * cs) + cy;
+            }
+    }
+}
+
+__device__ __forceinline__ void vw_write_row(const ViewsArgs& a, size_t row, const float (&px)[VW_MAXN], const float (&py)[VW_MAXN],
+                                             const float (&ps)[VW_MAXN]) {
+    float* xo = a.x2 + row * a.N * 3;
+    for (int n = 0; n < a.N; n++) { xo[3 * n] = px[n]; xo[3 * n + 1] = py[n]; xo[3 * n + 2] = ps[n]; }
+    float* ao = a.a2 + row * a.E;
+    for (int e = 0; e < a.E; e++) {
+        const float dx = px[a.e0[e]] - px[a.e1[e]], dy = py[a.e0[e]] - py[a.e1[e]];
+        ao[e] = sqrtf(fmaxf(dx * dx + dy * dy, 1e-12f));                   // model_utils_new.py:359-362
+    }
+}
+
+// one thread per (view, window, time step)
+__global__ void __launch_bounds__(128) views_kernel(const ViewsArgs a) {
+    const long long total = 2LL * a.B * a.Th;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % a.Th);
+        const int vb = (int)(i / a.Th);
+        const int b = vb % a.B, view = vb / a.B;
+        float px[VW_MAXN], py[VW_MAXN], ps[VW_MAXN];
+        if (view == 0) {
+            const float* r = a.x_full + ((size_t)b * a.Tf + a.mid_start + t) * a.N * 3;      // training.py:518-522
+            for (int n = 0; n < a.N; n++) { px[n] = r[3 * n]; py[n] = r[3 * n + 1]; ps[n] = r[3 * n + 2]; }
+        } else {
+            const int st = a.start[b];
+            const int L = a.interp_len ? a.interp_len[b] : 0;
+            const int t0 = L > 0 ? a.interp_t0[b] : 0;
+            if (L > 0 && t >= t0 && t < t0 + L) {                                          // training.py:2330-2357
+                float qx[VW_MAXN], qy[VW_MAXN], qs[VW_MAXN];
+                vw_rotated_row(a, b, st + t0 - 1, px, py, ps);
+                vw_rotated_row(a, b, st + t0 + L, qx, qy, qs);
+                float al = ((float)t - ((float)t0 - 1.f)) / ((float)L + 1.f);
+                al = fminf(fmaxf(al, 0.f), 1.f);
+                for (int n = 0; n < a.N; n++) {
+                    px[n] = (1.f - al) * px[n] + al * qx[n];
+                    py[n] = (1.f - al) * py[n] + al * qy[n];
+                    ps[n] = (1.f - al) * ps[n] + al * qs[n];
+                }
+            } else {
+                vw_rotated_row(a, b, st + t, px, py, ps);
+            }
+            if (a.noise) {
+                const float* nz = a.noise + (size_t)b * a.N * 3;
+                for (int n = 0; n < a.N; n++) { px[n] += nz[3 * n]; py[n] += nz[3 * n + 1]; ps[n] += nz[3 * n + 2]; }
+            }
+        }
+        vw_write_row(a, (size_t)vb * a.Th + t, px, py, ps);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// NT-Xent (nce, cosine)
+// ---------------------------------------------------------------------------
+#define NTX_ST_LOSS 0
+#define NTX_ST_POS 1
+#define NTX_ST_ALL 2
+#define NTX_TILE 128
+#define NTX_WARPS 8
+struct NtxArgs {
+    const float* enc;   // [2B, D] encoder outputs: rows 0..B-1 = z, B..2B-1 = z_aug
+    float* zn;          // [2B, D] row-normalised
+    float* nrm;         // [2B]
+    float* lse;         // [B] log-sum-exp of every row of sim
+    float* denc;        // [2B, D] gradient wrt enc
+    double* stats;
+    float* logs;
+    int B, D;
+    float inv_tau;
+};
+
+__global__ void ntx_norm_kernel(const NtxArgs a) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= 2 * a.B) return;
+    float s = 0.f;
+    for (int d = lane; d < a.D; d += 32) { float v = a.enc[(size_t)w * a.D + d]; s += v * v; }
+    s = warp_sum(s);
+    const float n = fmaxf(sqrtf(s), 1e-12f);                               // F.normalize eps
+    for (int d = lane; d < a.D; d += 32) a.zn[(size_t)w * a.D + d] = a.enc[(size_t)w * a.D + d] / n;
+    if (lane == 0) a.nrm[w] = n;
+}
+
+// PHASE 0: row statistics of sim = zn . an^T / tau (lse_i, s_ii, sum_j s_ij), one warp per row of z.
+// PHASE 1: gradients; blocks [0, nb) own rows of z (d loss / d zn_i = sum_j g_ij an_j), blocks [nb, 2 nb) rows of
+// z_aug (d loss / d an_j = sum_i g_ij zn_i), g_ij = (softmax_ij - delta_ij) / (B tau); then back through the row
+// normalisation.  The opposite matrix streams through shared memory in 128-row tiles; lanes own rows of the tile
+// and keep a private D-vector accumulator that is warp-reduced once at the end.
+template <int PHASE, int DP>
+__global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
+    extern __shared__ float nsm[];
+    const int D = a.D, B = a.B, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = nsm;                               // [NTX_TILE][DP+1]
+    float* tl = tile + NTX_TILE * (DP + 1);          // [NTX_TILE] lse of the tile rows (column blocks)
+    float* mine = tl + NTX_TILE + warp * DP;         // this warp's own row
+    const int nb = (B + NTX_WARPS - 1) / NTX_WARPS;
+    const bool col = PHASE == 1 && (int)blockIdx.x >= nb;
+    const int self = ((int)blockIdx.x % nb) * NTX_WARPS + warp;      // index inside its own matrix
+    const bool active = self < B;
+    const int w = self + (col ? B : 0);                               // row of enc / zn
+    const float* other = a.zn + (col ? 0 : (size_t)B * D);
+    if (active) for (int d = lane; d < D; d += 32) mine[d] = a.zn[(size_t)w * D + d];
+    __syncwarp();
+    float m = -INFINITY, l = 0.f, sall = 0.f, sdiag = 0.f;
+    float acc[DP];
+#pragma unroll
+    for (int d = 0; d < DP; d++) acc[d] = 0.f;
+    const float my_lse = (PHASE == 1 && active && !col) ? a.lse[self] : 0.f;
+    const float gs = a.inv_tau / (float)B;
+    for (int j0 = 0; j0 < B; j0 += NTX_TILE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < NTX_TILE * D; i += blockDim.x) {
+            const int r = i / D, d = i - r * D;
+            tile[r * (DP + 1) + d] = (j0 + r < B) ? other[(size_t)(j0 + r) * D + d] : 0.f;
+        }
+        if (col) for (int i = threadIdx.x; i < NTX_TILE; i += blockDim.x) tl[i] = (j0 + i < B) ? a.lse[j0 + i] : 0.f;
+        __syncthreads();
+        if (!active) continue;
+        for (int r = lane; r < NTX_TILE && j0 + r < B; r += 32) {
+            const float* tr = tile + r * (DP + 1);
+            float dot = 0.f;
+#pragma unroll
+            for (int d = 0; d < DP; d++) if (d < D) dot += mine[d] * tr[d];
+            const float s = dot * a.inv_tau;
+            if (PHASE == 0) {
+                sall += s;
+                if (j0 + r == self) sdiag = s;
+                const float mn = fmaxf(m, s);
+                l = l * __expf(m - mn) + __expf(s - mn);
+                m = mn;
+            } else {
+                float g = __expf(s - (col ? tl[r] : my_lse));
+                if (j0 + r == self) g -= 1.f;
+                g *= gs;
+#pragma unroll
+                for (int d = 0; d < DP; d++) if (d < D) acc[d] += g * tr[d];
+            }
+        }
+    }
+    if (!active) return;
+    if (PHASE == 0) {
+        const float mall = warp_max(m);
+        l = warp_sum(l * __expf(m - mall));
+        sall = warp_sum(sall);
+        sdiag = warp_sum(sdiag);
+        if (lane == 0) {
+            const float lse = mall + logf(l);
+            a.lse[self] = lse;
+            atomicAdd(a.stats + NTX_ST_LOSS, (double)(lse - sdiag));
+            atomicAdd(a.stats + NTX_ST_POS, (double)sdiag);
+            atomicAdd(a.stats + NTX_ST_ALL, (double)sall);
+        }
+    } else {
+        float dotg = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; d++) {
+            if (d < D) {
+                acc[d] = warp_sum(acc[d]);
+                dotg += acc[d] * mine[d];
+            }
+        }
+        // through zn = e / max(|e|, eps): de = (dzn - (dzn . zn) zn) / |e|
+        const float inv = 1.f / a.nrm[w];
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < DP; d++) if (d < D) a.denc[(size_t)w * D + d] = (acc[d] - dotg * mine[d]) * inv;
+        }
+    }
+}
+
+// logs: 0 total 1 pos_similarity 2 neg_similarity 3 distill 4 seperability (training.py:582-588)
+__global__ void ntx_finalize_kernel(const NtxArgs a, float tau) {
+    const double B = (double)a.B;
+    a.logs[0] = (float)(a.stats[NTX_ST_LOSS] / B);
+    a.logs[1] = (float)(a.stats[NTX_ST_POS] / B * tau);
+    a.logs[2] = a.B > 1 ? (float)((a.stats[NTX_ST_ALL] - a.stats[NTX_ST_POS]) * tau / (B * (B - 1.0))) : 0.f;
+    a.logs[3] = 0.f;
+    a.logs[4] = 0.f;
+}

@@ -123,6 +123,9 @@ class _Named:
 
 class VaDEB200:
     """B200-native stand-in for ``VaDEPT(encoder_type="recurrent", use_gnn=True)``."""
+    _MODEL = _lib.MODEL_VADE
+    _BUFFERS = ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence", "latent_space.prior",
+                "latent_space.pretrain")
 
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
                  encoder_type: str = "recurrent", use_gnn: bool = True, kmeans_loss: float = 1.0,
@@ -141,7 +144,7 @@ class VaDEB200:
         self.adjacency_matrix = np.asarray(adjacency_matrix, dtype=np.float64)
         lap, elap, inc = graph_operators(self.adjacency_matrix)
         assert inc.shape[1] == E, f"adjacency has {inc.shape[1]} edges, edge_feature_shape says {E}"
-        self.cfg = DofConfig(T, N, E, F, Fe, int(latent_dim), int(n_components))
+        self.cfg = DofConfig(T, N, E, F, Fe, int(latent_dim), int(n_components), self._MODEL)
         self.window_size = T
         self.latent_dim, self.n_components = int(latent_dim), int(n_components)
         self.kmeans_weight = float(kmeans_loss)
@@ -169,7 +172,8 @@ class VaDEB200:
         self._training = False
         # surfaces poked by reference helper code
         self.encoder = self._Encoder(self)
-        self.latent_space = self._Latent(self)
+        if self._MODEL == _lib.MODEL_VADE:
+            self.latent_space = self._Latent(self)
         self.reset_parameters(seed)
         with torch.no_grad():
             self._views["encoder.laplacian"].copy_(torch.from_numpy(lap))
@@ -244,6 +248,8 @@ class VaDEB200:
                 else:
                     fan_out, fan_in = shape[0], shape[1]
                     val = uni(shape, math.sqrt(6.0 / (fan_in + fan_out)))
+            elif name == "vq_layer.codebook":      # uniform_(0, 1), models_new.py:1349-1351
+                val = torch.rand(shape, generator=g)
             elif name in ("latent_space.gmm_means", "latent_space.gmm_log_vars"):
                 val = torch.randn(shape, generator=g) * math.sqrt(2.0 / (K + D))
             elif leaf == "weight":     # nn.Linear
@@ -277,9 +283,7 @@ class VaDEB200:
         return [v for (name, *_r, grp), v in zip(self.layout, self._views.values()) if grp > 0]
 
     def named_parameters(self):
-        return [(name, v) for (name, *_r, grp), v in zip(self.layout, self._views.values())
-                if name not in ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence",
-                                "latent_space.prior", "latent_space.pretrain")]
+        return [(name, v) for (name, *_r, grp), v in zip(self.layout, self._views.values()) if name not in self._BUFFERS]
 
     def to(self, *a, **k):
         return self
@@ -370,8 +374,9 @@ class VaDEB200:
         return self.logs
 
     def adam_step(self, lr_base: float, lr_gmm: float, lr_decoder: Optional[float] = None, clip: float = 0.75,
-                  grad_scale: float = 1.0, active=(True, True, True), betas=(0.9, 0.999), eps: float = 1e-8):
-        """clip_grad_value_ + Adam.  Groups: encoder+latent heads / decoder / GMM."""
+                  grad_scale: float = 1.0, active=(True, True, True), betas=(0.9, 0.999), eps: float = 1e-8,
+                  weight_decay: float = 0.0):
+        """clip_grad_value_ + Adam.  Groups: encoder+latent heads / decoder / GMM (or VQ codebook)."""
         o = DofAdamCfg()
         lrs = (0.0, lr_base, lr_base if lr_decoder is None else lr_decoder, lr_gmm)
         for g in range(1, 4):
@@ -380,6 +385,7 @@ class VaDEB200:
             o.lr[g] = lrs[g]
             o.step[g] = max(1, self.adam_steps[g])
             o.active[g] = int(bool(active[g - 1]))
+            o.weight_decay[g] = weight_decay
         o.clip_value, o.grad_scale, o.beta1, o.beta2, o.eps = clip, grad_scale, betas[0], betas[1], eps
         check(self.L.dof_clip_adam(self.handle, ptr(self.state), ptr(self.grad), ptr(self.adam_m),
                                    ptr(self.adam_v), C.byref(o), _stream()))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DOF_ABI_VERSION 1
+#define DOF_ABI_VERSION 2
 
 /* Model geometry.  Mirrors the constructor arguments of VaDEPT / RecurrentEncoderPT /
  * RecurrentDecoderPT (deepof/clustering/models_new.py:37-105, 281-324, 1794-1839). */
@@ -41,8 +41,18 @@ typedef struct {
     int F;   /* features per node  (x, y, speed) = 3                */
     int Fe;  /* features per edge  (log1p length) = 1               */
     int D;   /* latent_dim                                          */
-    int K;   /* n_components (GMM clusters)                         */
+    int K;   /* n_components (GMM clusters / VQ codebook size)      */
+    int model; /* DOF_MODEL_*: which reference model the state buffer lays out */
 } dof_config;
+
+/* Model kinds (all with encoder_type="recurrent", use_gnn=True):
+ *  VADE         VaDEPT        deepof/clustering/models_new.py:1794-1976  encoder + decoder + latent_space
+ *  VQVAE        VQVAEPT       models_new.py:1510-1635                    encoder + decoder + vq_layer.codebook [D,K]
+ *  CONTRASTIVE  ContrastivePT models_new.py:1978-2069                    encoder only; T is the HALF window the
+ *                                                                         encoder sees (window_size = T_full // 2) */
+#define DOF_MODEL_VADE 0
+#define DOF_MODEL_VQVAE 1
+#define DOF_MODEL_CONTRASTIVE 2
 
 /* One phase of VadeLoss (deepof/clustering/losses.py:383-457, 567-797).  Field names follow
  * the reference attributes.  tf_cluster_weight and reg_scatter_weight must be 0 (their
@@ -76,6 +86,8 @@ typedef struct {
     float lr[4];
     int step[4];
     int active[4];
+    float weight_decay[4]; /* torch.optim.Adam L2 term per group: 0 for build_optimizer_vade, 1e-4 for
+                            * build_optimizer_generic (losses.py:805-814), added after the clip     */
     float clip_value;   /* 0.75 in the reference; <=0 disables clipping              */
     float grad_scale;   /* 1/world_size after a summed all-reduce, else 1             */
     float beta1, beta2, eps;
@@ -181,6 +193,53 @@ int dof_loader_pair_length(const float* frames, long long n_frames, int N, int n
  * what the groupwise StandardScaler fits of scale_table / _pp_fit_global_scaler see. */
 int dof_loader_moments(const dof_loader_cfg* cfg, const float* frames, long long n_frames, const double* shift3,
                        double* out9, void* stream);
+
+/* ---- encoder only: model.encoder(x, a) -> enc [B,D] (RecurrentEncoderPT.forward, models_new.py:140-181);
+ * this is ContrastivePT.forward (models_new.py:2063-2069) and VQVAEPT.encode (:1637-1640).  Any model kind. */
+int dof_encode(dof_handle* h, const float* state, const float* x, const float* a, int B, float* enc, void* stream);
+
+/* ---- VQ-VAE (DOF_MODEL_VQVAE) ------------------------------------------------------------------------
+ * Eval forward of VQVAEPT(x, a, return_all_outputs=True) (models_new.py:1575-1635): enc [B,D] encoder output,
+ * quant [B,D] quantized latents, soft [B,K] soft counts, idx [B] code indices (VectorQuantizerPT.get_code_indices,
+ * :1406-1423), loc_q / loc_e [B,T,N*F] decoder means from the quantized / the encoder latents.  Outputs may be NULL. */
+int dof_vqvae_forward_eval(dof_handle* h, const float* state, const float* x, const float* a, int B, float* enc,
+                           float* quant, float* soft, int* idx, float* loc_q, float* loc_e, void* stream);
+/* step_vqvae_distill forward + loss.backward() with the teacher off (deepof/clustering/training.py:312-389, 159-163).
+ * grad is overwritten.  logs (DEVICE, DOF_N_LOGS floats): 0 total_loss 1 enc_rec_loss 2 reconstruct_loss 3 vq_loss
+ * 4 kmeans_loss 5 number_of_populated_clusters 6 distill_loss (= 0). */
+int dof_vqvae_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B,
+                        float beta, float kmeans_weight, float* logs, void* stream);
+
+/* ---- contrastive (DOF_MODEL_CONTRASTIVE) --------------------------------------------------------------
+ * dof_contrastive_views builds what step_contrastive_distill feeds its encoder (training.py:497-525): from
+ * x_full [B,T_full,N,3] the middle half window and the augmented view of _make_augmented_view (training.py:2128-2402)
+ * with edge lengths recomputed from the coordinates (recompute_edges, model_utils_new.py:332-364):
+ *   x2 [2B,T_full/2,N,3], a2 [2B,T_full/2,E,1]; rows 0..B-1 the main view, B..2B-1 the augmented view.
+ * The random decisions of the augmentation are INPUTS (drawn by the host RNG): start [B] slice start of the
+ * augmented view; n_rot rotations applied in order, rotation k turning the nodes of bit mask rot_mask[k] around node
+ * rot_pivot[k] by rot_theta[k*B + b] radians; interp_t0 / interp_len [B]: frames t0 .. t0+len-1 of the half window are
+ * replaced by the linear interpolation between frames t0-1 and t0+len (len 0 = off; both NULL = off); noise [B,N,3]
+ * additive per-node offsets (NULL = off).  start, rot_theta, interp_*, noise are DEVICE arrays; edges is HOST. */
+typedef struct {
+    int T_full, N, E;
+    const int* edges;          /* HOST [E,2] */
+    const int* start;          /* DEVICE [B] */
+    int n_rot;
+    int rot_pivot[8];
+    unsigned int rot_mask[8];
+    const float* rot_theta;    /* DEVICE [n_rot,B] */
+    const int* interp_t0;      /* DEVICE [B] or NULL */
+    const int* interp_len;     /* DEVICE [B] or NULL */
+    const float* noise;        /* DEVICE [B,N,3] or NULL */
+} dof_views_cfg;
+int dof_contrastive_views(const dof_views_cfg* v, const float* x_full, int B, float* x2, float* a2, void* stream);
+/* step_contrastive_distill forward + loss.backward() with the teacher off (training.py:527-545, 159-163):
+ * z = encoder(main view), z_aug = encoder(augmented view) (one pass over the 2B windows: the handle needs
+ * max_batch >= 2B), F.normalize, cosine similarity / temperature, cross-entropy against the diagonal
+ * (nce_loss_pt, deepof/clustering/losses.py:130-141).  logs: 0 total_loss 1 pos_similarity 2 neg_similarity
+ * 3 distill_loss (= 0) 4 seperability (= 0).  z_out [2B,D] (may be NULL) receives the raw encoder outputs. */
+int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
+                              float temperature, float* logs, float* z_out, void* stream);
 
 /* Debug / test access to intermediate activations of the last forward (device pointers into
  * the workspace; NULL if unknown).  Names: "node_out","edge_out","enc","z","z_mean",
