@@ -39,6 +39,18 @@ import torch
 CFG = dict(T=25, N=14, E=14, F=3, Fe=1, D=16, K=8, batch=4096, pool_windows=1 << 20)
 FLOPS_PER_WINDOW = 88.6e6        # useful matmul/conv FLOPs fwd+bwd, cfg2
 WORKLOAD = "cfg2: VaDE GRU encoder, 1M synthetic windows (25x14x3 + 25x14x1), latent=16, 8 clusters, batch 4096/GPU, main phase (MC-KL S=32)"
+# secondary workloads (python bench.py --workload ...): same contract, not the headline
+WORKLOADS = {
+    "cfg2": dict(CFG, kind="vade", flops=88.6e6, name=WORKLOAD, metric="pose-windows/sec trained (VaDE, win=25x28)"),
+    "vqvae": dict(CFG, K=64, kind="vqvae", flops=92.6e6,
+                  name="cfg3r: VQ-VAE with the RECURRENT encoder/decoder (the transformer of cfg3 is not built yet), 1M synthetic "
+                       "windows (25x14x3 + 25x14x1), latent=16, codebook=64, batch 4096/GPU",
+                  metric="pose-windows/sec trained (VQ-VAE recurrent, win=25x28)"),
+    "cfg4": dict(T=50, N=22, E=26, F=3, Fe=1, D=16, K=1, batch=4096, pool_windows=1 << 19, kind="contrastive", flops=290.4e6,
+                 name="cfg4: contrastive NT-Xent (nce, cosine, tau=0.1), recurrent encoder, 2 animals x 11 body parts (N=22, E=26), "
+                      "win=50 (encoder sees 25), latent=16, batch 4096/GPU, reference-default augmentations",
+                 metric="pose-windows/sec trained (contrastive NT-Xent, win=50x44)"),
+}
 
 
 def adjacency(n):
@@ -47,6 +59,19 @@ def adjacency(n):
         A[i, i + 1] = A[i + 1, i] = 1.0
     if n > 5:
         A[0, 5] = A[5, 0] = 1.0
+    return A
+
+
+def adjacency_two_animals():
+    """2 x 11 body parts, 12 within-animal edges each + 2 cross-animal edges = 26 (cfg4 sizes)."""
+    A = np.zeros((22, 22))
+    for o in (0, 11):
+        for i in range(10):
+            A[o + i, o + i + 1] = A[o + i + 1, o + i] = 1.0
+        for i, j in ((0, 5), (2, 8)):
+            A[o + i, o + j] = A[o + j, o + i] = 1.0
+    for i, j in ((0, 11), (0, 21)):
+        A[i, j] = A[j, i] = 1.0
     return A
 
 
@@ -74,7 +99,7 @@ def synth_frames(n_frames, N, seed, device):
     standardised windows the model trains on."""
     g = torch.Generator(device=device).manual_seed(seed)
     rn = lambda *s: torch.randn(*s, generator=g, device=device, dtype=torch.float64)
-    centre = torch.cumsum(rn(n_frames, 2) * 1.5, 0)
+    centre = torch.cumsum(rn(2, n_frames) * 1.5, 1).t().contiguous()    # scan along the contiguous axis
     centre = centre - centre.mean(0) + 300.0
     heading = torch.cumsum(rn(n_frames) * 0.08, 0)
     body = rn(N, 2) * 18.0
@@ -125,19 +150,22 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-def cpu_reference_arm(steps, warmup, batch=256):
+def cpu_reference_arm(steps, warmup, batch=256, workload="cfg2"):
     """The reference path restated on CPU (oracle, ATen GRU like the reference's nn.GRU):
-    forward + VadeLoss + backward + clip + Adam on `batch` windows per step."""
+    forward + loss + backward + clip + Adam on `batch` windows per step."""
     from oracle import vade_oracle as O
+    from oracle import models_oracle as MO
     O.USE_ATEN_GRU = True
-    c = CFG
+    c = WORKLOADS[workload]
+    kind = c["kind"]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    adj = adjacency(c["N"])
+    adj = adjacency_two_animals() if kind == "contrastive" else adjacency(c["N"])
     graph = O.graph_operators(adj)
     from deepof_b200.vade import state_layout
     from deepof_b200._lib import DofConfig
-    lay = state_layout(DofConfig(c["T"], c["N"], c["E"], c["F"], c["Fe"], c["D"], c["K"]))
+    Tenc = c["T"] // 2 if kind == "contrastive" else c["T"]
+    lay = state_layout(DofConfig(Tenc, c["N"], c["E"], c["F"], c["Fe"], c["D"], c["K"], {"vade": 0, "vqvae": 1, "contrastive": 2}[kind]))
     g = torch.Generator().manual_seed(1234 + 2)
     p = {}
     for name, off, numel, shape, grp in lay:
@@ -149,20 +177,33 @@ def cpu_reference_arm(steps, warmup, batch=256):
             p[name] = torch.randn(shape, generator=g) * 0.1
     lap, elap, inc = graph
     p["encoder.laplacian"], p["encoder.edge_laplacian"], p["encoder.incidence"] = lap, elap, inc
+    if kind == "vqvae":
+        p["vq_layer.codebook"] = torch.rand(c["D"], c["K"], generator=g)
     x, a = synth_pool(batch * 4, c["T"], adj, 1234 + 2, "cpu")
     cfg = O.LossCfg.main_defaults(c["K"], 0.8)
+    rows, cols = np.nonzero(np.triu(adj))
+    ei = torch.from_numpy(np.stack([rows, cols], 1))
+    rot = MO.rotation_table(ei.numpy(), c["N"])
     state = {}
     times = []
     for i in range(warmup + steps):
         s = (i % 4) * batch
         t0 = time.perf_counter()
-        logs, grads, _ = O.train_step(x[s:s + batch], a[s:s + batch], p, graph, c["D"], cfg)
-        O.adam_step(p, grads, state, 5e-4, 2e-4)
+        if kind == "vade":
+            logs, grads, _ = O.train_step(x[s:s + batch], a[s:s + batch], p, graph, c["D"], cfg)
+            O.adam_step(p, grads, state, 5e-4, 2e-4)
+        elif kind == "vqvae":
+            logs, grads, _ = MO.vqvae_train_step(x[s:s + batch], a[s:s + batch], p, graph, c["D"], 1.0, 0.0)
+            MO.adam_step_generic(p, grads, state, 1e-3)
+        else:
+            prm = MO.draw_aug_params(batch, c["T"], c["N"], MO.AugCfg(), rot)
+            logs, grads, _ = MO.contrastive_train_step(x[s:s + batch], p, graph, c["D"], ei, prm, 0.1)
+            MO.adam_step_generic(p, grads, state, 1e-3)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.median(times))
     return {"value": batch / (ms / 1e3), "ms_per_step": ms, "cores": cores, "batch": batch,
-            "sample": f"median of {steps} steps x {batch} windows of the cfg2 workload (fwd+loss+bwd+clip+Adam) after {warmup} warm-up steps, torch {torch.__version__} CPU, {cores} threads"}
+            "sample": f"median of {steps} steps x {batch} windows of the {workload} workload (fwd+loss+bwd+clip+Adam) after {warmup} warm-up steps, torch {torch.__version__} CPU, {cores} threads"}
 
 
 def main():
@@ -173,22 +214,26 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    c = dict(CFG, batch=args.batch)
+    c = dict(WORKLOADS[args.workload])
+    if args.batch != CFG["batch"] or args.workload == "cfg2":
+        c["batch"] = args.batch
+    kind, METRIC, WORKLOAD_NAME, FLOPS = c["kind"], c["metric"], c["name"], c["flops"]
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_arm(max(1, args.steps), max(3, args.warmup))
-        line = {"impl": "reference", "metric": "pose-windows/sec trained (VaDE, win=25x28)", "value": r["value"],
+        r = cpu_reference_arm(max(1, args.steps), max(3, args.warmup), workload=args.workload)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"],
                 "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_step": r["batch"], "note": "reference CPU path restated (oracle port; the Python reference cannot travel to the GPU box)"},
+                "config": {"workload": WORKLOAD_NAME, "batch_per_step": r["batch"], "note": "reference CPU path restated (oracle port; the Python reference cannot travel to the GPU box)"},
                 "cpu_baseline": {"value": r["value"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -201,14 +246,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from deepof_b200 import _lib
-    from deepof_b200.training import VaDETrainer
+    from deepof_b200.training import VaDETrainer, VQVAETrainer, ContrastiveTrainer
     from deepof_b200 import WindowLoader
 
-    adj = adjacency(c["N"])
+    adj = adjacency_two_animals() if kind == "contrastive" else adjacency(c["N"])
     B, T, D, K = c["batch"], c["T"], c["D"], c["K"]
-    trainer = VaDETrainer((T, c["N"], c["F"]), (T, c["E"], c["Fe"]), adj, D, K, max_batch=B, seed=1234 + 2,
-                          world_size=world, rank=rank)
-    trainer.set_phase("main", kl_weight=0.8, lr_base=5e-4, lr_gmm=2e-4)
+    shapes = ((T, c["N"], c["F"]), (T, c["E"], c["Fe"]))
+    if kind == "vade":
+        trainer = VaDETrainer(*shapes, adj, D, K, max_batch=B, seed=1234 + 2, world_size=world, rank=rank)
+        trainer.set_phase("main", kl_weight=0.8, lr_base=5e-4, lr_gmm=2e-4)
+    elif kind == "vqvae":
+        trainer = VQVAETrainer(*shapes, adj, D, K, max_batch=B, seed=1234 + 2, world_size=world, rank=rank)
+    else:
+        trainer = ContrastiveTrainer(*shapes, adj, D, max_batch=B, seed=1234 + 2, world_size=world, rank=rank)
+    xbuf = trainer._xf if kind == "contrastive" else trainer._xs
+    abuf = torch.empty(B, T, c["E"], c["Fe"], device=dev) if kind == "contrastive" else trainer._as
     pool_n = c["pool_windows"] // world
     pool_n = max(B, pool_n // B * B)
     # one synthetic video per rank, resident in HBM as RAW frames; the loader kernel produces each batch
@@ -237,7 +289,7 @@ def main():
     def run_resident(n, first):
         for i in range(n):
             s = ((first + i) % nb) * B
-            xb, ab = loader.load(s, B, trainer._xs, trainer._as)      # frames -> windows on the device
+            xb, ab = loader.load(s, B, xbuf, abuf)      # frames -> windows on the device
             trainer.train_step_device(xb, ab)
 
     def run_e2e(n, first):
@@ -279,7 +331,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
-    h2d = (xh[:B].numel() + ah[:B].numel()) * 4
+    h2d = (xh[:B].numel() + (0 if kind == "contrastive" else ah[:B].numel())) * 4   # contrastive recomputes the edges
     e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "windows/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss}
 
@@ -312,19 +364,19 @@ def main():
         top = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
         roof = roofline_for(top, kernels[top], peaks)
         sustained = peaks.get("bf16_tflops_sustained", 1400.0)
-        roof["step_useful_tflops"] = FLOPS_PER_WINDOW * B / (ms / 1e3) / 1e12
+        roof["step_useful_tflops"] = FLOPS * B / (ms / 1e3) / 1e12
         roof["step_tensor_frac"] = roof["step_useful_tflops"] / sustained
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_arm(3, 3)
+        r = cpu_reference_arm(3, 3, workload=args.workload)
         cpu = {"value": r["value"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
-        line = {"metric": "pose-windows/sec trained (VaDE, win=25x28)", "value": value, "unit": "windows/s",
+        line = {"metric": METRIC, "value": value, "unit": "windows/s",
                 "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                "config": {"workload": WORKLOAD_NAME, "batch_per_gpu": B, "global_batch": B * world,
                            "parallelism": f"dp{world}", "pool_windows_per_gpu": pool_n,
                            "inputs": "raw pose frames resident in HBM; windows built per step by the loader kernel",
                            "l2": "inputs+activations per step (~16 GB) exceed the 126 MB L2; consecutive batches of the video"},

@@ -144,3 +144,96 @@ class VaDETrainer:
 
     def logs(self) -> Dict[str, float]:
         return self.model.logs_dict()
+
+
+class _GenericTrainer:
+    """Shared step plumbing of ``fit_VQVAE`` / ``fit_contrastive`` (reference training.py:1087-1200, 1321-1460):
+    loss.backward -> [all-reduce(sum) of the flat gradient] -> clip_grad_value_(0.75) -> Adam(lr, weight_decay=1e-4)
+    (``build_optimizer_generic``, losses.py:805-814)."""
+
+    def __init__(self, model, world_size: int = 1, rank: int = 0, lr: float = 1e-3, weight_decay: float = 1e-4):
+        self.model, self.world_size, self.rank = model, int(world_size), int(rank)
+        self.lr, self.weight_decay = float(lr), float(weight_decay)
+        self._loss_host = torch.zeros(16, pin_memory=True)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.model.state, src=0)
+
+    def _finish(self, logs):
+        m = self.model
+        scale = 1.0
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(m.grad, op=dist.ReduceOp.SUM)
+            scale = 1.0 / self.world_size
+        m.adam_step(self.lr, grad_scale=scale, weight_decay=self.weight_decay)
+        return logs
+
+    def _read_loss(self, logs) -> float:
+        self._loss_host.copy_(logs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_host[0])
+
+    def logs(self) -> Dict[str, float]:
+        return self.model.logs_dict()
+
+
+class VQVAETrainer(_GenericTrainer):
+    """``step_vqvae_distill`` + the optimizer step (teacher off)."""
+
+    def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
+                 max_batch: int = 4096, seed: Optional[int] = None, world_size: int = 1, rank: int = 0,
+                 kmeans_loss: float = 0.0, beta: float = 1.0, lr: float = 1e-3, device: Optional[int] = None):
+        from .models import VQVAEB200
+        m = VQVAEB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, n_components, kmeans_loss=kmeans_loss,
+                      beta=beta, device=device, max_batch=max_batch, training=True, seed=seed)
+        super().__init__(m, world_size, rank, lr)
+        T, N, F = m.input_shape
+        _, E, Fe = m.edge_feature_shape
+        self._xs = torch.empty(max_batch, T, N, F, device=m.device)
+        self._as = torch.empty(max_batch, T, E, Fe, device=m.device)
+
+    def train_step_device(self, x: torch.Tensor, a: torch.Tensor, idx=None) -> torch.Tensor:
+        return self._finish(self.model.loss_grad(x, a))
+
+    def train_step(self, x_host: torch.Tensor, a_host: torch.Tensor, idx=None) -> float:
+        B = x_host.shape[0]
+        xs, as_ = self._xs[:B], self._as[:B]
+        xs.copy_(x_host, non_blocking=True)
+        as_.copy_(a_host, non_blocking=True)
+        return self._read_loss(self.train_step_device(xs, as_))
+
+
+class ContrastiveTrainer(_GenericTrainer):
+    """``step_contrastive_distill`` + the optimizer step (teacher off): per batch draw the augmentation decisions,
+    build both views on the device, encode them in one pass, NT-Xent, backward, clip + Adam."""
+
+    def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, max_batch: int = 4096,
+                 seed: Optional[int] = None, world_size: int = 1, rank: int = 0, temperature: float = 0.1,
+                 aug=None, lr: float = 1e-3, edge_index=None, edge_index_local=None, device: Optional[int] = None):
+        from .models import ContrastiveAugCfg, ContrastiveB200
+        m = ContrastiveB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, temperature=temperature,
+                            edge_index=edge_index, edge_index_local=edge_index_local, device=device, max_batch=max_batch,
+                            training=True, seed=seed)
+        super().__init__(m, world_size, rank, lr)
+        self.aug = aug if aug is not None else ContrastiveAugCfg()
+        self.gen = torch.Generator(device=m.device)
+        self.host_gen = torch.Generator()
+        s = (seed if seed is not None else 0) + 7919 * rank
+        self.gen.manual_seed(s)
+        self.host_gen.manual_seed(s)
+        Tf, N = m.full_time_steps, m.input_shape[1]
+        self._xf = torch.empty(max_batch, Tf, N, 3, device=m.device)
+
+    def train_step_device(self, x_full: torch.Tensor, a_full=None, idx=None, aug_params=None) -> torch.Tensor:
+        """a_full is accepted for signature parity and ignored: the reference recomputes the edge lengths from
+        the coordinates (training.py:497)."""
+        m = self.model
+        prm = aug_params if aug_params is not None else m.draw_augmentation(x_full.shape[0], self.aug, self.gen, self.host_gen)
+        return self._finish(m.loss_grad(x_full, prm))
+
+    def train_step(self, x_host: torch.Tensor, a_host=None, idx=None) -> float:
+        B = x_host.shape[0]
+        xf = self._xf[:B]
+        xf.copy_(x_host, non_blocking=True)
+        return self._read_loss(self.train_step_device(xf))
