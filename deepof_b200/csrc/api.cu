@@ -9,6 +9,7 @@
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
 #include "gru.cuh"
+#include "gru_tc.cuh"
 #include "layers.cuh"
 #include "loss.cuh"
 #include "loader.cuh"
@@ -463,6 +464,36 @@ static int gru_input_proj(const float* state, const GruP& g, MatView A, int M, i
     return launch_gemm_rows(ga, 2, st);
 }
 
+// One bidirectional GRU layer.  Eligible shapes run the fused tcgen05 kernel (input projection + recurrence +
+// gates, gru_tc.cuh); the rest fall back to the projection GEMM (into Gi) + the SIMT recurrent kernel.
+// X rows: sequence s, step t at X + s*x_ss + t*x_st (x_st = 0: the same input at every step).
+static int gru_layer_forward(const float* state, const GruP& g, const float* X, long long x_ss, int x_st, int I, int H, int S,
+                             int T, const int* len, float* Hout, float* const Gt[2], float* Hn, float* const Gi[2],
+                             cudaStream_t st) {
+    if (gru_tc_eligible(S, H, I)) {
+        GruTcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.X = X; a.x_ss = x_ss; a.x_st = x_st;
+        for (int d = 0; d < 2; d++) {
+            a.Wih[d] = state + g.w_ih[d]; a.Whh[d] = state + g.w_hh[d]; a.bih[d] = state + g.b_ih[d]; a.bhh[d] = state + g.b_hh[d];
+            a.Gt[d] = Gt ? Gt[d] : nullptr;
+        }
+        a.len = len; a.Hout = Hout; a.Hn = Hn; a.S = S; a.T = T; a.H = H; a.I = I;
+        return launch_gru_fwd_tc(a, st);
+    }
+    const int M = x_st == 0 ? S : S * T;
+    DOF_TRY(gru_input_proj(state, g, mv_plain(X, I), M, I, H, Gi, st));
+    GruFwdArgs f;
+    memset(&f, 0, sizeof(f));
+    for (int d = 0; d < 2; d++) {
+        f.Gi[d] = Gi[d]; f.Whh[d] = state + g.w_hh[d]; f.bhh[d] = state + g.b_hh[d];
+        f.Gt[d] = Gt ? Gt[d] : nullptr;
+    }
+    f.gi_ss = x_st == 0 ? 3 * H : (long long)T * 3 * H; f.gi_st = x_st == 0 ? 0 : 3 * H;
+    f.len = len; f.Hout = Hout; f.Hn = Hn; f.S = S; f.T = T; f.H = H;
+    return launch_gru_fwd(f, st);
+}
+
 static int enc_block_forward(dof_handle* h, int b, const float* state, const float* xin, int B, bool train,
                              cudaStream_t st) {
     const dof_config& c = h->cfg;
@@ -477,26 +508,11 @@ static int enc_block_forward(dof_handle* h, int b, const float* state, const flo
     { ProfScope ps("enc_conv", st);
     enc_conv_kernel<<<B, 256, smem, st>>>(ca); }
     DOF_LAUNCH_CHECK();
-    DOF_TRY(gru_input_proj(state, P.g1, mv_plain(w.Cv, C1), M, C1, H1, w.Gi1, st));
-    GruFwdArgs f;
-    memset(&f, 0, sizeof(f));
-    for (int d = 0; d < 2; d++) {
-        f.Gi[d] = w.Gi1[d]; f.Whh[d] = state + P.g1.w_hh[d]; f.bhh[d] = state + P.g1.b_hh[d];
-        f.Gt[d] = train ? w.Gt1[d] : nullptr;
-    }
-    f.gi_ss = (long long)T * 3 * H1; f.gi_st = 3 * H1; f.len = w.len; f.Hout = w.H1; f.Hn = nullptr;
-    f.S = S; f.T = T; f.H = H1;
-    DOF_TRY(launch_gru_fwd(f, st));
+    DOF_TRY(gru_layer_forward(state, P.g1, w.Cv, (long long)T * C1, C1, C1, H1, S, T, w.len, w.H1, train ? w.Gt1 : nullptr, nullptr,
+                              w.Gi1, st));
     DOF_TRY(ln_fwd(w.H1, state + P.n1w, state + P.n1b, w.Y1, w.mu1, w.rs1, M, 2 * H1, h->sm_count, st));
-    DOF_TRY(gru_input_proj(state, P.g2, mv_plain(w.Y1, 2 * H1), M, 2 * H1, H2, w.Gi2, st));
-    memset(&f, 0, sizeof(f));
-    for (int d = 0; d < 2; d++) {
-        f.Gi[d] = w.Gi2[d]; f.Whh[d] = state + P.g2.w_hh[d]; f.bhh[d] = state + P.g2.b_hh[d];
-        f.Gt[d] = train ? w.Gt2[d] : nullptr;
-    }
-    f.gi_ss = (long long)T * 3 * H2; f.gi_st = 3 * H2; f.len = w.len; f.Hout = train ? w.H2 : nullptr; f.Hn = w.Hn;
-    f.S = S; f.T = T; f.H = H2;
-    DOF_TRY(launch_gru_fwd(f, st));
+    DOF_TRY(gru_layer_forward(state, P.g2, w.Y1, (long long)T * 2 * H1, 2 * H1, 2 * H1, H2, S, T, w.len, train ? w.H2 : nullptr,
+                              train ? w.Gt2 : nullptr, w.Hn, w.Gi2, st));
     DOF_TRY(ln_fwd(w.Hn, state + P.n2w, state + P.n2b, w.Y2, w.mu2, w.rs2, S, 2 * H2, h->sm_count, st));
     if (h->di != c.D) {
         GemmArgs g = gemm_args(mv_plain(w.Y2, 2 * H2), state + P.pw, 2 * H2, 0, state + P.pb, w.P, 2 * c.D, S,
@@ -574,24 +590,10 @@ static int decoder_forward(dof_handle* h, const float* state, const float* zin, 
     { ProfScope ps("row_valid_len", st);
     row_valid_len_kernel<<<cdiv(B, 128), 128, 0, st>>>(x, h->lenD, B, T, NF); }
     DOF_LAUNCH_CHECK();
-    DOF_TRY(gru_input_proj(state, L.dg1, mv_plain(zin, D), B, D, D, h->GiD1, st));
-    GruFwdArgs f;
-    memset(&f, 0, sizeof(f));
-    for (int d = 0; d < 2; d++) {
-        f.Gi[d] = h->GiD1[d]; f.Whh[d] = state + L.dg1.w_hh[d]; f.bhh[d] = state + L.dg1.b_hh[d];
-        f.Gt[d] = train ? h->GtD1[d] : nullptr;
-    }
-    f.gi_ss = 3 * D; f.gi_st = 0; f.len = h->lenD; f.Hout = h->HD1; f.S = B; f.T = T; f.H = D;
-    DOF_TRY(launch_gru_fwd(f, st));
+    DOF_TRY(gru_layer_forward(state, L.dg1, zin, D, 0, D, D, B, T, h->lenD, h->HD1, train ? h->GtD1 : nullptr, nullptr, h->GiD1, st));
     DOF_TRY(ln_fwd(h->HD1, state + L.dn1w, state + L.dn1b, h->YD1, h->muD1, h->rsD1, M, 2 * D, h->sm_count, st));
-    DOF_TRY(gru_input_proj(state, L.dg2, mv_plain(h->YD1, 2 * D), M, 2 * D, 2 * D, h->GiD2, st));
-    memset(&f, 0, sizeof(f));
-    for (int d = 0; d < 2; d++) {
-        f.Gi[d] = h->GiD2[d]; f.Whh[d] = state + L.dg2.w_hh[d]; f.bhh[d] = state + L.dg2.b_hh[d];
-        f.Gt[d] = train ? h->GtD2[d] : nullptr;
-    }
-    f.gi_ss = (long long)T * 6 * D; f.gi_st = 6 * D; f.len = h->lenD; f.Hout = h->HD2; f.S = B; f.T = T; f.H = 2 * D;
-    DOF_TRY(launch_gru_fwd(f, st));
+    DOF_TRY(gru_layer_forward(state, L.dg2, h->YD1, (long long)T * 2 * D, 2 * D, 2 * D, 2 * D, B, T, h->lenD, h->HD2,
+                              train ? h->GtD2 : nullptr, nullptr, h->GiD2, st));
     DOF_TRY(ln_fwd(h->HD2, state + L.dn2w, state + L.dn2b, h->YD2, h->muD2, h->rsD2, M, 4 * D, h->sm_count, st));
     GemmArgs gc = gemm_args(mv_conv5(h->YD2, 4 * D, T, +1), state + L.dconv, 20 * D, 0, nullptr, h->Cd, 2 * D, M, 2 * D, 20 * D);
     gc.relu = 1;
@@ -1272,6 +1274,18 @@ int dof_test_gru_fwd(const float* gi_f, const float* gi_b, long long gi_ss, int 
     f.Whh[0] = whh_f; f.Whh[1] = whh_b; f.bhh[0] = bhh_f; f.bhh[1] = bhh_b;
     f.len = len; f.Hout = hout; f.Gt[0] = gt_f; f.Gt[1] = gt_b; f.Hn = hn; f.S = S; f.T = T; f.H = H;
     return launch_gru_fwd(f, (cudaStream_t)stream);
+}
+
+// fused tcgen05 GRU layer (input projection + recurrence + gates); fails if the shape is not eligible
+int dof_test_gru_layer_fwd(const float* X, long long x_ss, int x_st, const float* const* w8, const int* len, float* hout,
+                           float* gt_f, float* gt_b, float* hn, int S, int T, int H, int I, void* stream) {
+    if (!gru_tc_eligible(S, H, I)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "shape S=%d H=%d I=%d is not eligible for the fused GRU kernel", S, H, I);
+    GruTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = X; a.x_ss = x_ss; a.x_st = x_st;
+    for (int d = 0; d < 2; d++) { a.Wih[d] = w8[d]; a.Whh[d] = w8[2 + d]; a.bih[d] = w8[4 + d]; a.bhh[d] = w8[6 + d]; }
+    a.len = len; a.Hout = hout; a.Gt[0] = gt_f; a.Gt[1] = gt_b; a.Hn = hn; a.S = S; a.T = T; a.H = H; a.I = I;
+    return launch_gru_fwd_tc(a, (cudaStream_t)stream);
 }
 
 int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout, const float* gt_f,

@@ -230,6 +230,58 @@ def test_gru_packed_lengths(L):
     _gru_case(L, S_, T, 64, 16, lens, True, seed=40)
 
 
+@pytest.mark.parametrize("S_,T,I,H,packed,repeat", [(300, 25, 32, 32, False, False), (1000, 25, 64, 16, True, False),
+                                                     (128, 24, 16, 16, False, True), (257, 7, 32, 32, True, False),
+                                                     (200, 25, 48, 32, True, False)])
+def test_gru_fused_tc_layer(L, S_, T, I, H, packed, repeat):
+    """Fused tcgen05 GRU layer (projection + recurrence + gates in one kernel) vs the fp64 oracle GRU, and its saved
+    gates vs the SIMT kernel's (they feed the same backward kernel)."""
+    dev = "cuda"
+    X = rnd(S_, 1 if repeat else T, I, seed=50)
+    Xfull = X.expand(S_, T, I).contiguous() if repeat else X
+    k = 1.0 / H ** 0.5
+    prm = {}
+    for d in ("", "_reverse"):
+        prm["weight_ih_l0" + d] = rnd(3 * H, I, seed=51 + len(d)) * k
+        prm["weight_hh_l0" + d] = rnd(3 * H, H, seed=52 + len(d)) * k
+        prm["bias_ih_l0" + d] = rnd(3 * H, seed=53 + len(d)) * k
+        prm["bias_hh_l0" + d] = rnd(3 * H, seed=54 + len(d)) * k
+    if packed:
+        g = torch.Generator().manual_seed(1)
+        lens = torch.randint(0, T + 1, (S_,), generator=g)
+        lens[0], lens[1], lens[2] = 0, 1, T
+        len_t = lens.to(dev).int()
+    else:
+        len_t = torch.full((S_,), T, dtype=torch.int32, device=dev)
+    out_ref, hn_ref = O.bigru(Xfull.double(), len_t.long(), {k_: v.double() for k_, v in prm.items()}, "")
+    hout = torch.full((S_, T, 2 * H), 7.0, device=dev)
+    gt = [torch.zeros(S_, T, 4 * H, device=dev) for _ in range(2)]
+    hn = torch.zeros(S_, 2 * H, device=dev)
+    names = ["weight_ih_l0", "weight_ih_l0_reverse", "weight_hh_l0", "weight_hh_l0_reverse", "bias_ih_l0", "bias_ih_l0_reverse",
+             "bias_hh_l0", "bias_hh_l0_reverse"]
+    w8 = (C.c_void_p * 8)(*[prm[n].data_ptr() for n in names])
+    ran = _ran(L, lambda: check_rc(L, L.dof_test_gru_layer_fwd(P(X), 0 if False else (I if repeat else T * I), 0 if repeat else I, w8,
+                                                               P(len_t), P(hout), P(gt[0]), P(gt[1]), P(hn), S_, T, H, I, S())))
+    assert any(n.startswith("gru_fwd_tc") for n in ran), ran
+    print("fused gru", (S_, T, I, H), rel(hout, out_ref), rel(hn, hn_ref))
+    assert rel(hout, out_ref) < 5e-6 and rel(hn, hn_ref) < 5e-6
+    # saved gates == what the SIMT kernel saves
+    gi = [(Xfull @ prm["weight_ih_l0" + d].t() + prm["bias_ih_l0" + d]).contiguous() for d in ("", "_reverse")]
+    hout2 = torch.zeros_like(hout)
+    gt2 = [torch.zeros(S_, T, 4 * H, device=dev) for _ in range(2)]
+    hn2 = torch.zeros_like(hn)
+    rc = L.dof_test_gru_fwd(P(gi[0]), P(gi[1]), T * 3 * H, 3 * H, P(prm["weight_hh_l0"]), P(prm["weight_hh_l0_reverse"]),
+                            P(prm["bias_hh_l0"]), P(prm["bias_hh_l0_reverse"]), P(len_t), P(hout2), P(gt2[0]), P(gt2[1]),
+                            P(hn2), S_, T, H, S())
+    assert rc == 0, L.dof_last_error()
+    for d in range(2):
+        assert rel(gt[d], gt2[d]) < 1e-5, ("gates", d, rel(gt[d], gt2[d]))
+
+
+def check_rc(L, rc):
+    assert rc == 0, L.dof_last_error()
+
+
 # ---------------------------------------------------------------------------
 # tcgen05 (3xTF32) GEMMs: same hooks, shapes large enough to be dispatched to the
 # tensor-core kernels; the per-kernel profile proves which kernel ran.
