@@ -440,17 +440,23 @@ static int ln_fwd(const float* x, const float* w, const float* b, float* y, floa
     int grid = (int)(blocks < (long long)sm * 16 ? blocks : (long long)sm * 16);
     if (grid < 1) return DOF_OK;
     { ProfScope ps("ln_fwd", st, 0.0, 8.0 * R * W);
-    ln_fwd_kernel<<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W); }
+    if (W <= 32) ln_fwd_kernel<1, 4><<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W);
+    else if (W <= 64) ln_fwd_kernel<2, 4><<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W);
+    else if (W <= 128) ln_fwd_kernel<4, 2><<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W);
+    else ln_fwd_kernel<8, 1><<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
 static int ln_bwd(const float* dy, const float* x, const float* mu, const float* rs, const float* w, float* dx,
                   float* dw, float* db, long long R, int W, int relu_in, int sm, cudaStream_t st) {
     long long blocks = (R + 7) / 8;
-    int grid = (int)(blocks < (long long)sm * 4 ? blocks : (long long)sm * 4);
+    int grid = (int)(blocks < (long long)sm * 8 ? blocks : (long long)sm * 8);
     if (grid < 1) return DOF_OK;
     { ProfScope ps("ln_bwd", st, 0.0, 12.0 * R * W);
-    ln_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in); }
+    if (W <= 32) ln_bwd_kernel<1, 4><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
+    else if (W <= 64) ln_bwd_kernel<2, 4><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
+    else if (W <= 128) ln_bwd_kernel<4, 2><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
+    else ln_bwd_kernel<8, 1><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -588,7 +594,7 @@ static int decoder_forward(dof_handle* h, const float* state, const float* zin, 
     const Layout& L = h->L;
     const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T;
     { ProfScope ps("row_valid_len", st);
-    row_valid_len_kernel<<<cdiv(B, 128), 128, 0, st>>>(x, h->lenD, B, T, NF); }
+    row_valid_len_kernel<<<cdiv((long long)B * 32, 256), 256, 0, st>>>(x, h->lenD, B, T, NF); }
     DOF_LAUNCH_CHECK();
     DOF_TRY(gru_layer_forward(state, L.dg1, zin, D, 0, D, D, B, T, h->lenD, h->HD1, train ? h->GtD1 : nullptr, nullptr, h->GiD1, st));
     DOF_TRY(ln_fwd(h->HD1, state + L.dn1w, state + L.dn1b, h->YD1, h->muD1, h->rsD1, M, 2 * D, h->sm_count, st));
@@ -653,12 +659,13 @@ static int gru_param_grads(dof_handle* h, const GruP& g, float* grad, const floa
                            grad + g.b_hh[d], M, 3 * H, H);
     DOF_TRY(launch_gemm_wgrad(wa, 2, st, h->sm_count));
     if (dX) {
-        for (int d = 0; d < 2; d++) {
-            GemmArgs ga = gemm_args(mv_split(dGx[d], 4 * H, 2 * H, H), state + g.w_ih[d], I, 1, nullptr, dX, I, Mx, I, 3 * H);
-            ga.accum = d;
-            if (d == 1 && dXmask) { ga.mask = dXmask; ga.ldmask = I; }
-            DOF_TRY(launch_gemm_rows(&ga, 1, st));
-        }
+        // dX = dGi_fwd . W_ih_fwd + dGi_bwd . W_ih_bwd as ONE two-K-block GEMM (no read-modify-write of dX)
+        GemmArgs ga = gemm_args(mv_split(dGx[0], 4 * H, 2 * H, H), state + g.w_ih[0], I, 1, nullptr, dX, I, Mx, I, 3 * H);
+        ga.nkb = 2;
+        ga.A2 = mv_split(dGx[1], 4 * H, 2 * H, H);
+        ga.W2 = state + g.w_ih[1];
+        if (dXmask) { ga.mask = dXmask; ga.ldmask = I; }
+        DOF_TRY(launch_gemm_rows(&ga, 1, st));
     }
     return DOF_OK;
 }

@@ -68,6 +68,10 @@ struct GemmArgs {
     int relu;                          // relu(acc + bias (+C))
     int accum;                         // C += ...
     const float* mask; int ldmask;     // if set: out = mask[m,n] > 0 ? out : 0  (ReLU backward)
+    // optional second K block: C = A.W + A2.W2 (same N, K) in one pass, e.g. the input gradient of a
+    // bidirectional GRU  dX = dG_fwd.W_ih_fwd + dG_bwd.W_ih_bwd  without a read-modify-write of C
+    int nkb;                           // 0/1: single block, 2: A2/W2 are valid
+    MatView A2; const float* W2;
 };
 struct GemmBatch { GemmArgs g[2]; };
 

@@ -61,118 +61,170 @@ __global__ void __launch_bounds__(256) enc_conv_kernel(const EncConvArgs a) {
     }
 }
 
-// decoder validity: len[b] = #time steps whose data row is not all-zero (models_new.py:330-331)
-__global__ void row_valid_len_kernel(const float* x, int* len, int B, int T, int Dx) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+// decoder validity: len[b] = #time steps whose data row is not all-zero (models_new.py:330-331).
+// One warp per window; a time step's row (Dx floats, contiguous) is read by the whole warp.
+__global__ void row_valid_len_kernel(const float* __restrict__ x, int* __restrict__ len, int B, int T, int Dx) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     int n = 0;
     for (int t = 0; t < T; t++) {
         const float* r = x + ((size_t)b * T + t) * Dx;
         bool any = false;
-        for (int d = 0; d < Dx; d++) any |= (r[d] != 0.f);
-        n += any ? 1 : 0;
+        for (int d = lane; d < Dx; d += 32) any |= (r[d] != 0.f);
+        n += __any_sync(0xffffffffu, any) ? 1 : 0;
     }
-    len[b] = n;
+    if (lane == 0) len[b] = n;
 }
 
 // ---------------------------------------------------------------------------
 // LayerNorm over the last dim (biased variance), one warp per row, W <= 256.
 // ---------------------------------------------------------------------------
 #define LN_MAXV 8
+// VPL values per lane (W <= 32*VPL), R rows per warp iteration: the R rows' loads are issued together so that
+// each warp keeps R*W*4 bytes in flight (these kernels are pure HBM streams).
+template <int VPL, int R>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ b, float eps,
                                                      float* __restrict__ y, float* __restrict__ mu_out,
-                                                     float* __restrict__ rstd_out, long long R, int W) {
+                                                     float* __restrict__ rstd_out, long long Rows, int W) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long r = warp; r < R; r += nwarps) {
-        const float* xr = x + r * W;
-        float v[LN_MAXV];
-        float s = 0.f;
+    float wv[VPL], bv[VPL];
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; i++) {
-            int c = lane + 32 * i;
-            v[i] = (c < W) ? xr[c] : 0.f;
-            s += v[i];
-        }
-        float mu = warp_sum(s) / W;
-        float q = 0.f;
+    for (int i = 0; i < VPL; i++) {
+        const int c = lane + 32 * i;
+        wv[i] = (c < W) ? __ldg(w + c) : 0.f;
+        bv[i] = (c < W) ? __ldg(b + c) : 0.f;
+    }
+    for (long long r0 = warp; r0 < Rows; r0 += nwarps * R) {
+        float v[R][VPL], s[R];
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; i++) {
-            int c = lane + 32 * i;
-            float d = (c < W) ? v[i] - mu : 0.f;
-            q += d * d;
-        }
-        float var = warp_sum(q) / W;
-        float rstd = rsqrtf(var + eps);
-        // one Newton step: rsqrtf is ~2 ulp; keep LayerNorm at full fp32 accuracy
-        rstd = rstd * (1.5f - 0.5f * (var + eps) * rstd * rstd);
-        float* yr = y + r * W;
+        for (int q = 0; q < R; q++) {
+            const long long r = r0 + q * nwarps;
+            s[q] = 0.f;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; i++) {
-            int c = lane + 32 * i;
-            if (c < W) yr[c] = (v[i] - mu) * rstd * __ldg(w + c) + __ldg(b + c);
+            for (int i = 0; i < VPL; i++) {
+                const int c = lane + 32 * i;
+                v[q][i] = (r < Rows && c < W) ? x[r * W + c] : 0.f;
+                s[q] += v[q][i];
+            }
         }
-        if (lane == 0 && mu_out) { mu_out[r] = mu; rstd_out[r] = rstd; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < R; q++) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        float mu[R], var[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            mu[q] = s[q] / W;
+            var[q] = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                const int c = lane + 32 * i;
+                const float d = (c < W) ? v[q][i] - mu[q] : 0.f;
+                var[q] += d * d;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < R; q++) var[q] += __shfl_xor_sync(0xffffffffu, var[q], o);
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const long long r = r0 + q * nwarps;
+            if (r >= Rows) continue;
+            const float vv = var[q] / W;
+            float rstd = rsqrtf(vv + eps);
+            // one Newton step: rsqrtf is ~2 ulp; keep LayerNorm at full fp32 accuracy
+            rstd = rstd * (1.5f - 0.5f * (vv + eps) * rstd * rstd);
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                const int c = lane + 32 * i;
+                if (c < W) y[r * W + c] = (v[q][i] - mu[q]) * rstd * wv[i] + bv[i];
+            }
+            if (lane == 0 && mu_out) { mu_out[r] = mu[q]; rstd_out[r] = rstd; }
+        }
     }
 }
 
 // dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*w; dw += dy*xhat; db += dy.
 // relu_in: the LN input x is a ReLU output -> additionally mask dx by (x > 0).
+template <int VPL, int R>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ mu_in,
                                                      const float* __restrict__ rstd_in,
                                                      const float* __restrict__ w, float* __restrict__ dx,
                                                      float* __restrict__ dw, float* __restrict__ db,
-                                                     long long R, int W, int relu_in) {
+                                                     long long Rows, int W, int relu_in) {
     __shared__ float sdw[256], sdb[256];
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { sdw[i] = 0.f; sdb[i] = 0.f; }
     __syncthreads();
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    float adw[LN_MAXV], adb[LN_MAXV], wv[LN_MAXV];
+    float adw[VPL], adb[VPL], wv[VPL];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < VPL; i++) {
         adw[i] = 0.f; adb[i] = 0.f;
-        int c = lane + 32 * i;
+        const int c = lane + 32 * i;
         wv[i] = (c < W) ? __ldg(w + c) : 0.f;
     }
-    for (long long r = warp; r < R; r += nwarps) {
-        const float mu = mu_in[r], rstd = rstd_in[r];
-        const float* xr = x + r * W;
-        const float* dyr = dy + r * W;
-        float xh[LN_MAXV], g[LN_MAXV], xv[LN_MAXV];
-        float s1 = 0.f, s2 = 0.f;
+    for (long long r0 = warp; r0 < Rows; r0 += nwarps * R) {
+        float xv[R][VPL], dv[R][VPL], mu[R], rstd[R], s1[R], s2[R];
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; i++) {
-            int c = lane + 32 * i;
-            float d = 0.f;
-            xv[i] = 0.f;
-            if (c < W) { xv[i] = xr[c]; d = dyr[c]; }
-            xh[i] = (c < W) ? (xv[i] - mu) * rstd : 0.f;
-            g[i] = d * wv[i];
-            s1 += g[i];
-            s2 += g[i] * xh[i];
-            adw[i] += d * xh[i];
-            adb[i] += d;
+        for (int q = 0; q < R; q++) {
+            const long long r = r0 + q * nwarps;
+            const bool ok = r < Rows;
+            mu[q] = ok ? mu_in[r] : 0.f;
+            rstd[q] = ok ? rstd_in[r] : 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                const int c = lane + 32 * i;
+                xv[q][i] = (ok && c < W) ? x[r * W + c] : 0.f;
+                dv[q][i] = (ok && c < W) ? dy[r * W + c] : 0.f;
+            }
         }
-        s1 = warp_sum(s1) / W;
-        s2 = warp_sum(s2) / W;
-        float* dxr = dx + r * W;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; i++) {
-            int c = lane + 32 * i;
-            if (c < W) {
-                float o = rstd * (g[i] - s1 - xh[i] * s2);
-                if (relu_in && !(xv[i] > 0.f)) o = 0.f;
-                dxr[c] = o;
+        for (int q = 0; q < R; q++) {
+            s1[q] = 0.f; s2[q] = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                const int c = lane + 32 * i;
+                const float xh = (c < W) ? (xv[q][i] - mu[q]) * rstd[q] : 0.f;
+                const float g = dv[q][i] * wv[i];
+                s1[q] += g;
+                s2[q] += g * xh;
+                adw[i] += dv[q][i] * xh;
+                adb[i] += dv[q][i];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
+                s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o);
+            }
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const long long r = r0 + q * nwarps;
+            if (r >= Rows) continue;
+            const float m1 = s1[q] / W, m2 = s2[q] / W;
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                const int c = lane + 32 * i;
+                if (c < W) {
+                    const float xh = (xv[q][i] - mu[q]) * rstd[q];
+                    float o = rstd[q] * (dv[q][i] * wv[i] - m1 - xh * m2);
+                    if (relu_in && !(xv[q][i] > 0.f)) o = 0.f;
+                    dx[r * W + c] = o;
+                }
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < VPL; i++) {
         int c = lane + 32 * i;
         if (c < W) { atomicAdd(&sdw[c], adw[i]); atomicAdd(&sdb[c], adb[i]); }
     }

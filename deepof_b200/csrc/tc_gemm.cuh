@@ -118,9 +118,10 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
     const GemmArgs& g = gb.g[blockIdx.z];
     extern __shared__ __align__(128) unsigned char tsm[];
     const int S = geo.stages;
-    unsigned char* W_hi = tsm;
+    const int nkb = g.nkb == 2 ? 2 : 1;                               // K blocks per tile (second block: A2 / W2)
+    unsigned char* W_hi = tsm;                                        // [nkb] x (W_hi | W_lo)
     unsigned char* W_lo = W_hi + geo.w_bytes;
-    unsigned char* A_base = W_lo + geo.w_bytes;                       // S x (A_hi | A_lo)
+    unsigned char* A_base = tsm + (size_t)nkb * 2 * geo.w_bytes;      // S x (A_hi | A_lo)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(A_base + (size_t)S * 2 * geo.a_bytes);
     // mbar[0..S) full, [S..2S) empty, [2S..2S+2) tmem full, [2S+2..2S+4) tmem empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * S + 4);
@@ -138,16 +139,19 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // stage W (hi/lo) once: canonical K-major, rows n at 16 B, K-chunks at w_lbo
-    for (int i = tid; i < NP * KP; i += TCR_THREADS) {
-        int n, k;
-        if (g.wT == 0) { n = i / KP; k = i % KP; } else { k = i / NP; n = i % NP; }
-        float v = 0.f;
-        if (n < g.N && k < g.K) v = g.wT == 0 ? __ldg(g.W + (size_t)n * g.ldw + k) : __ldg(g.W + (size_t)k * g.ldw + n);
-        float hi, lo;
-        split_tf32(v, hi, lo);
-        uint32_t off = (uint32_t)n * 16 + (uint32_t)(k >> 2) * geo.w_lbo + (k & 3) * 4;
-        *reinterpret_cast<float*>(W_hi + off) = hi;
-        *reinterpret_cast<float*>(W_lo + off) = lo;
+    for (int kb = 0; kb < nkb; kb++) {
+        const float* Wp = kb ? g.W2 : g.W;
+        for (int i = tid; i < NP * KP; i += TCR_THREADS) {
+            int n, k;
+            if (g.wT == 0) { n = i / KP; k = i % KP; } else { k = i / NP; n = i % NP; }
+            float v = 0.f;
+            if (n < g.N && k < g.K) v = g.wT == 0 ? __ldg(Wp + (size_t)n * g.ldw + k) : __ldg(Wp + (size_t)k * g.ldw + n);
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            uint32_t off = (uint32_t)kb * 2 * geo.w_bytes + (uint32_t)n * 16 + (uint32_t)(k >> 2) * geo.w_lbo + (k & 3) * 4;
+            *reinterpret_cast<float*>(W_hi + off) = hi;
+            *reinterpret_cast<float*>(W_lo + off) = lo;
+        }
     }
     for (int i = tid; i < NP; i += TCR_THREADS) bias_s[i] = (g.bias && i < g.N) ? __ldg(g.bias + i) : 0.f;
     fence_async_smem();
@@ -162,7 +166,10 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
         // ===================== producers =====================
         const bool split = g.A.mode == A_SPLIT;
         float4 pre[NSET][KQM];
-        auto load_regs = [&](float4 (&r)[KQM], int tile) {
+        // work item w = (local tile index) * nkb + kb
+        auto load_regs = [&](float4 (&r)[KQM], int w) {
+            const int tile = blockIdx.x + (w / nkb) * gridDim.x;
+            const MatView& Av = (w % nkb) ? g.A2 : g.A;
             const int m0 = tile * 128;
 #pragma unroll
             for (int j = 0; j < KQM; j++) {
@@ -172,8 +179,8 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                     int row = i / KQ, kq = i - row * KQ;
                     int m = m0 + row, c = kq * 4;
                     if (m < g.M && c < g.K) {
-                        if (split && c >= g.A.split) c += g.A.skip;
-                        r[j] = __ldg(reinterpret_cast<const float4*>(g.A.p + (size_t)m * g.A.ld + c));
+                        if (split && c >= Av.split) c += Av.skip;
+                        r[j] = __ldg(reinterpret_cast<const float4*>(Av.p + (size_t)m * Av.ld + c));
                     }
                 }
             }
@@ -194,25 +201,25 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                 }
             }
         };
-        int tile = blockIdx.x, it = 0;
-        if (NSET == 2) load_regs(pre[0], tile);
-        for (; tile < ntiles; tile += gridDim.x, it++) {
+        const int mytiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int nwork = mytiles * nkb;
+        if (NSET == 2) load_regs(pre[0], 0);
+        for (int it = 0; it < nwork; it++) {
             const int s = it % S;
             const uint32_t ph = (uint32_t)((it / S) & 1);
-            const int next = tile + gridDim.x;
             if (NSET == 2) {
-                // alternate register sets: set (it&1) holds this tile, set (it&1)^1 receives the next
+                // alternate register sets: set (it&1) holds this work item, set (it&1)^1 receives the next
                 if ((it & 1) == 0) {
-                    if (next < ntiles) load_regs(pre[1 % NSET], next);
+                    if (it + 1 < nwork) load_regs(pre[1 % NSET], it + 1);
                     mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                     store_smem(pre[0], s);
                 } else {
-                    if (next < ntiles) load_regs(pre[0], next);
+                    if (it + 1 < nwork) load_regs(pre[0], it + 1);
                     mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                     store_smem(pre[1 % NSET], s);
                 }
             } else {
-                load_regs(pre[0], tile);
+                load_regs(pre[0], it);
                 mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                 store_smem(pre[0], s);
             }
@@ -294,24 +301,28 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
         // ===================== MMA issuer (one thread) =====================
         const uint32_t idesc = umma_idesc_tf32(NP, 0, 0);
         const uint32_t w_hi_s = smem_u32(W_hi), w_lo_s = smem_u32(W_lo);
-        int it = 0;
+        int it = 0, wk = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-            const int s = it % S, a = it & 1;
+            const int a = it & 1;
             mbar_wait(bar_tempty + 8u * a, (uint32_t)(((it >> 1) & 1) ^ 1));
-            mbar_wait(bar_full + 8u * s, (uint32_t)((it / S) & 1));
-            tc_fence_after();
-            const uint32_t a_hi_s = smem_u32(A_base + (size_t)s * 2 * geo.a_bytes), a_lo_s = a_hi_s + geo.a_bytes;
             const uint32_t acc = tmem + (uint32_t)a * (uint32_t)NP;
-            for (int ks = 0; ks < (KP >> 3); ks++) {
-                uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * geo.w_lbo;
-                uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
-                uint64_t dbh = umma_desc(w_hi_s + wo, geo.w_lbo, 128), dbl = umma_desc(w_lo_s + wo, geo.w_lbo, 128);
-                umma_tf32(acc, dah, dbh, idesc, ks > 0 ? 1u : 0u);
-                umma_tf32(acc, dal, dbh, idesc, 1u);
-                umma_tf32(acc, dah, dbl, idesc, 1u);
+            for (int kb = 0; kb < nkb; kb++, wk++) {
+                const int s = wk % S;
+                mbar_wait(bar_full + 8u * s, (uint32_t)((wk / S) & 1));
+                tc_fence_after();
+                const uint32_t a_hi_s = smem_u32(A_base + (size_t)s * 2 * geo.a_bytes), a_lo_s = a_hi_s + geo.a_bytes;
+                const uint32_t wkb = (uint32_t)kb * 2 * geo.w_bytes;
+                for (int ks = 0; ks < (KP >> 3); ks++) {
+                    uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = wkb + (uint32_t)ks * 2 * geo.w_lbo;
+                    uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
+                    uint64_t dbh = umma_desc(w_hi_s + wo, geo.w_lbo, 128), dbl = umma_desc(w_lo_s + wo, geo.w_lbo, 128);
+                    umma_tf32(acc, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                    umma_tf32(acc, dal, dbh, idesc, 1u);
+                    umma_tf32(acc, dah, dbl, idesc, 1u);
+                }
+                umma_commit(bar_empty + 8u * s);    // smem stage may be refilled once these MMAs retire
             }
-            umma_commit(bar_empty + 8u * s);    // smem stage may be refilled once these MMAs retire
-            umma_commit(bar_tfull + 8u * a);    // accumulator ready for the epilogue warps
+            umma_commit(bar_tfull + 8u * a);        // accumulator ready for the epilogue warps
         }
     }
     tc_fence_before();
@@ -334,7 +345,7 @@ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0;
 
 #define TC_SMEM_MAX (200 * 1024)
 
-static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem) {
+static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem, int nkb = 1) {
     geo.KP = round_up(K, 8);
     geo.NP = round_up(N, 16);
     if (2 * geo.NP > 512) return false;
@@ -343,7 +354,7 @@ static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem) {
     geo.a_bytes = (uint32_t)(geo.KP / 4) * TC_A_LBO;
     geo.w_bytes = (uint32_t)(geo.KP / 4) * geo.w_lbo;
     for (int S = 2; S >= 1; S--) {
-        smem = 2 * (size_t)geo.w_bytes + (size_t)S * 2 * geo.a_bytes + (2 * S + 4) * 8 + 16 + (size_t)geo.NP * 4 +
+        smem = (size_t)nkb * 2 * geo.w_bytes + (size_t)S * 2 * geo.a_bytes + (2 * S + 4) * 8 + 16 + (size_t)geo.NP * 4 +
                4 * 32 * 36 * 4 + 128;
         if (smem <= TC_SMEM_MAX) { geo.stages = S; return true; }
     }
@@ -356,8 +367,12 @@ static bool tc_rows_eligible(const GemmArgs& g) {
     if ((g.A.ld & 3) || (g.K & 3) || !aligned16(g.A.p)) return false;
     if (g.A.mode == A_SPLIT && ((g.A.split & 3) || (g.A.skip & 3))) return false;
     if (!aligned16(g.C) || (g.mask && !aligned16(g.mask))) return false;
+    if (g.nkb == 2) {
+        if (g.A2.mode != g.A.mode || g.A2.ld != g.A.ld || g.A2.split != g.A.split || g.A2.skip != g.A.skip) return false;
+        if (!aligned16(g.A2.p) || !g.W2) return false;
+    }
     TcRowsGeom geo; size_t smem;
-    return tc_rows_geom(g.N, g.K, geo, smem);
+    return tc_rows_geom(g.N, g.K, geo, smem, g.nkb == 2 ? 2 : 1);
 }
 
 template <int KQM, int NSET>
@@ -379,11 +394,13 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     for (int i = 0; i < nbatch; i++) {
         gb.g[i] = gs[i];
         if (gs[i].M > M) M = gs[i].M;
-        if (gs[i].N != gs[0].N || gs[i].K != gs[0].K) DOF_FAIL(DOF_ERR_ARG, "batched TC GEMMs must share N and K");
+        if (gs[i].N != gs[0].N || gs[i].K != gs[0].K || (gs[i].nkb == 2) != (gs[0].nkb == 2))
+            DOF_FAIL(DOF_ERR_ARG, "batched TC GEMMs must share N, K and the K-block count");
     }
     TcRowsGeom geo;
     size_t smem = 0;
-    if (!tc_rows_geom(gs[0].N, gs[0].K, geo, smem)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC GEMM tile does not fit");
+    const int nkb = gs[0].nkb == 2 ? 2 : 1;
+    if (!tc_rows_geom(gs[0].N, gs[0].K, geo, smem, nkb)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC GEMM tile does not fit");
     const int KQ = geo.KP / 4;
     int occ = (int)((228 * 1024) / (smem + 1024));
     int by_tmem = 512 / geo.tmem_cols;
@@ -397,8 +414,8 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     if (ctas > ntiles) ctas = ntiles;
     double fl = 0.0, by = 0.0;
     for (int i = 0; i < nbatch; i++) {
-        fl += 2.0 * gs[i].M * gs[i].N * gs[i].K;
-        by += 4.0 * gs[i].M * ((double)gs[i].K + (double)gs[i].N * (1 + (gs[i].accum ? 1 : 0) + (gs[i].mask ? 1 : 0)));
+        fl += 2.0 * gs[i].M * gs[i].N * gs[i].K * nkb;
+        by += 4.0 * gs[i].M * ((double)gs[i].K * nkb + (double)gs[i].N * (1 + (gs[i].accum ? 1 : 0) + (gs[i].mask ? 1 : 0)));
     }
     ProfScope ps("gemm_rows_tc", st, fl, by);
     dim3 grid(ctas, 1, nbatch);
@@ -672,7 +689,19 @@ static int launch_gemm_rows(const GemmArgs* gs, int nbatch, cudaStream_t st) {
     for (int i = 0; i < nbatch && tc; i++)
         tc = tc_rows_eligible(gs[i]) && gs[i].N == gs[0].N && gs[i].K == gs[0].K;
     if (tc) return launch_gemm_rows_tc(gs, nbatch, st, g_sm_count);
-    return launch_gemm_rows_simt(gs, nbatch, st);
+    bool any2 = false;
+    for (int i = 0; i < nbatch; i++) any2 = any2 || gs[i].nkb == 2;
+    if (!any2) return launch_gemm_rows_simt(gs, nbatch, st);
+    for (int i = 0; i < nbatch; i++) {
+        if (gs[i].nkb != 2) { DOF_TRY(launch_gemm_rows_simt(gs + i, 1, st)); continue; }
+        // not eligible for the tensor-core kernel: two passes, the second accumulating onto the first
+        GemmArgs a = gs[i], b = gs[i];
+        a.nkb = 0; a.mask = nullptr; a.relu = 0;
+        b.nkb = 0; b.A = gs[i].A2; b.W = gs[i].W2; b.bias = nullptr; b.accum = 1;
+        DOF_TRY(launch_gemm_rows(&a, 1, st));
+        DOF_TRY(launch_gemm_rows(&b, 1, st));
+    }
+    return DOF_OK;
 }
 
 static int launch_gemm_wgrad(const WGradArgs* gs, int nbatch, cudaStream_t st, int sm_count) {
