@@ -337,11 +337,13 @@ def main():
 
     # ---- per-kernel-class timing (library-side CUDA events around each launch), 3 extra steps
     kernels, roof = None, None
+    psteps = 3
+    if rank == 0:
+        L.dof_profile_begin()
+    run_resident(psteps, 0)          # every rank steps (the gradient all-reduce is collective); rank 0 records events
+    barrier()
     if rank == 0:
         import ctypes as C
-        psteps = 3
-        L.dof_profile_begin()
-        run_resident(psteps, 0)
         buf = C.create_string_buffer(8192)
         L.dof_profile_end(buf, 8192)
         kernels = {}
