@@ -390,27 +390,35 @@ def main():
 
 
 def roofline_for(name, k, peaks):
-    """Roofline of the dominant kernel class: ALGORITHMIC (unpadded) FLOPs or bytes per launch,
-    counted by the library at launch time, over the CUDA-event duration of
-    that class.  GEMM / GRU classes are compute-bound ("tensor pipe"); they are
-    fp32 FFMA kernels in this round, so the fraction of the measured bf16 tensor peak is small
-    by construction and is reported as is."""
+    """Roofline of the dominant kernel class: ALGORITHMIC (unpadded) FLOPs and bytes per launch, counted by the
+    library at launch time, over the CUDA-event duration of that class.  A class that counts
+    both is reported against the roof it sits closer to (the tall-skinny GEMMs and the fused GRU layers move
+    <= 12 flop/B, far left of the 211 flop/B ridge, so that is the HBM roof); the other fraction is kept next to it.
+    `traffic` is the DRAM traffic of the class's dominant launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json), per launch."""
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     n = max(1.0, k["launches_per_step"])
-    if k["flops_per_step"] > 0:
-        peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        ach = k["tflops"]
-        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "peak_source": src + ", sustained bf16", "fp32_ffma_peak_tflops": 148 * 128 * 2 * 1.965e-3,
-                "frac_of_fp32_ffma_peak": ach / (148 * 128 * 2 * 1.965e-3),
-                "algorithmic_flops_per_launch": k["flops_per_step"] / n, "launch_ms": k["ms_per_step"] / n,
-                "kernel_share_of_step": k["share"]}
-    peak = peaks.get("hbm_gbs", 6650.0)
-    ach = k.get("gbs")
-    return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": src,
-            "algorithmic_bytes_per_launch": k["bytes_per_step"] / n, "launch_ms": k["ms_per_step"] / n,
-            "kernel_share_of_step": k["share"]}
+    tpeak, hpeak = peaks.get("bf16_tflops_sustained", 1400.0), peaks.get("hbm_gbs", 6650.0)
+    tfrac = (k["tflops"] / tpeak) if k.get("tflops") else None
+    hfrac = (k["gbs"] / hpeak) if k.get("gbs") else None
+    traffic, tnote = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if name in tj:
+            traffic, tnote = tj[name]["dram_bytes_per_launch"], tj[name]["note"]
+    except Exception:
+        pass
+    common = {"kernel": name, "traffic": traffic, "traffic_note": tnote, "launch_ms": k["ms_per_step"] / n,
+              "kernel_share_of_step": k["share"], "tensor_frac_of_sustained_bf16": tfrac, "hbm_frac_of_measured_copy": hfrac}
+    if hfrac is not None and (tfrac is None or hfrac >= tfrac):
+        return dict(common, bound="hbm", achieved=k["gbs"], peak=hpeak, unit="GB/s", frac=hfrac, peak_source=src,
+                    algorithmic_bytes_per_launch=k["bytes_per_step"] / n)
+    if tfrac is not None:
+        return dict(common, bound="tensor", achieved=k["tflops"], peak=tpeak, unit="TFLOP/s", frac=tfrac,
+                    peak_source=src + ", sustained bf16", fp32_ffma_peak_tflops=148 * 128 * 2 * 1.965e-3,
+                    frac_of_fp32_ffma_peak=k["tflops"] / (148 * 128 * 2 * 1.965e-3),
+                    algorithmic_flops_per_launch=k["flops_per_step"] / n)
+    return dict(common, bound="hbm", achieved=None, peak=hpeak, unit="GB/s", frac=None, peak_source=src)
 
 
 if __name__ == "__main__":

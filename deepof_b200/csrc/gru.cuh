@@ -232,6 +232,23 @@ gru_bwd_kernel(const GruBwdArgs a) {
         float* dgs = dGT + cur * 3 * HP * MT + mg * GRU_TM;
         float part[GRU_TM][4];
         float dar[GRU_TM][4], daz[GRU_TM][4], dah[GRU_TM][4];
+        // pull the rows of the NEXT step towards L2 while this step computes (the saved gates were written a whole
+        // forward pass ago and are cold); one thread per 128-byte line
+        if (step + 1 < T && (j0 & 31) == 0) {
+            const int tn = dir ? t + 1 : t - 1;
+            const int tpn = dir ? tn + 1 : tn - 1;
+#pragma unroll
+            for (int m = 0; m < GRU_TM; m++) {
+                const int s = s0 + m;
+                if (s < a.S && tn < len[m]) {
+                    const float* gp = Gt + ((size_t)s * T + tn) * 4 * H + j0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + q * H));
+                    if (tpn >= 0 && tpn < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Hout + ((size_t)s * T + tpn) * 2 * H + dir * H + j0));
+                    if (a.dOut) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dOut + ((size_t)s * T + tn) * 2 * H + dir * H + j0));
+                }
+            }
+        }
 #pragma unroll
         for (int m = 0; m < GRU_TM; m++) {
             int s = s0 + m;

@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const LossArgs a) {
         for (int i = tid; i < K * D; i += blockDim.x) a.coef[CL.R + i] = 0.f;
     }
     // ---- "kmeans" loss: mean sqrt singular values of Gram z^T z / B (losses.py:257-287)
-    if (cfg.model_kmeans_weight > 0.f) {
+    // (skipped when its weight is zero, e.g. the main phase: value and gradient are exactly 0 then)
+    if (cfg.model_kmeans_weight > 0.f && cfg.kmeans_loss_weight != 0.f) {
         for (int i = tid; i < D * D; i += blockDim.x) A[i] = (double)((float)(a.stats[SL.gram + i]) / (float)B);
         __syncthreads();
         if (tid < 32) {
