@@ -7,7 +7,8 @@ reference's model / step interface.  There is no CPU fallback.
 from ._lib import DofError, LIB_PATH, LOG_KEYS  # noqa: F401
 from .vade import VaDEB200, VadeLossCfg, graph_operators, state_layout  # noqa: F401
 from .models import VQVAEB200, ContrastiveB200, ContrastiveAugCfg, AugParams, RotationTable  # noqa: F401
+from .inference import embedding_per_video  # noqa: F401
 from .loader import WindowLoader, GlobalScalers, VideoConstants, batch_starts, reference_divisors  # noqa: F401
 
 __all__ = ["VaDEB200", "VadeLossCfg", "DofError", "graph_operators", "state_layout", "LIB_PATH", "LOG_KEYS",
-           "VQVAEB200", "ContrastiveB200", "ContrastiveAugCfg", "AugParams", "RotationTable", "WindowLoader", "GlobalScalers", "VideoConstants", "batch_starts", "reference_divisors"]
+           "VQVAEB200", "ContrastiveB200", "ContrastiveAugCfg", "AugParams", "RotationTable", "embedding_per_video", "WindowLoader", "GlobalScalers", "VideoConstants", "batch_starts", "reference_divisors"]

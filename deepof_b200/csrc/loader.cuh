@@ -167,61 +167,68 @@ __global__ void __launch_bounds__(LD_THREADS) load_windows_kernel(const __grid_c
     }
     __syncthreads();
 
-    // ---- phase 2: per-frame rotation, then every feature of every frame once --------------------
-    for (int fr = tid; fr < nfr; fr += LD_THREADS) {
-        double cs, sn;
-        ld_rot(R, f_raw, f_lo + fr, p, cs, sn);
-        rot[2 * fr] = cs; rot[2 * fr + 1] = sn;
-    }
-    __syncthreads();
-    for (int i = tid; i < nfr * C; i += LD_THREADS) {
-        const int fr = i / C, col = i - fr * C;
-        const double z = ld_feat(R, f_raw, f_lo + fr, col, p, rot[2 * fr], rot[2 * fr + 1]);
-        Z[i] = z;
-        valid[i] = (z == z) ? 1 : 0;
+    // ---- phase 2: every feature of every frame once; one warp per frame, lanes over the columns ---------
+    const int warp = tid >> 5, lane = tid & 31, nwarp = LD_THREADS / 32;
+    for (int fr = warp; fr < nfr; fr += nwarp) {
+        double cs = 1.0, sn = 0.0;
+        if (p.align_node >= 0) {
+            if (lane == 0) ld_rot(R, f_raw, f_lo + fr, p, cs, sn);
+            cs = __shfl_sync(0xffffffffu, cs, 0);
+            sn = __shfl_sync(0xffffffffu, sn, 0);
+        }
+        for (int col = lane; col < C; col += 32) {
+            const double z = ld_feat(R, f_raw, f_lo + fr, col, p, cs, sn);
+            Z[fr * C + col] = z;
+            valid[fr * C + col] = (z == z) ? 1 : 0;
+        }
     }
     __syncthreads();
 
     // ---- phase 3: clipped / undefined entries -> linear interpolation between the nearest valid
     // frames of the same column (pandas interpolate(limit_direction="both"), then fillna(0)).
     // Anchors are searched in the tile first, then in the frame table itself.
-    for (int i = tid; i < nfr * C; i += LD_THREADS) {
-        if (valid[i]) continue;
-        const int fr = i / C, col = i - fr * C;
-        long long fp = -1, fn = -1;
-        double zp = 0.0, zn = 0.0;
-        for (int g = fr - 1; g >= 0; g--)
-            if (valid[g * C + col]) { fp = f_lo + g; zp = Z[g * C + col]; break; }
-        if (fp < 0)
-            for (long long f = f_lo - 1; f >= 0; f--) {
-                const double z = ld_feat_global(f, col, p);
-                if (z == z) { fp = f; zp = z; break; }
-            }
-        for (int g = fr + 1; g < nfr; g++)
-            if (valid[g * C + col]) { fn = f_lo + g; zn = Z[g * C + col]; break; }
-        if (fn < 0)
-            for (long long f = f_lo + nfr; f < p.n_frames; f++) {
-                const double z = ld_feat_global(f, col, p);
-                if (z == z) { fn = f; zn = z; break; }
-            }
-        double v = 0.0;
-        if (fp >= 0 && fn >= 0) v = zp + (zn - zp) / (double)(fn - fp) * (double)(f_lo + fr - fp);
-        else if (fp >= 0) v = zp;
-        else if (fn >= 0) v = zn;
-        Z[i] = v;
+    for (int fr = warp; fr < nfr; fr += nwarp) {
+        for (int col = lane; col < C; col += 32) {
+            const int i = fr * C + col;
+            if (valid[i]) continue;
+            long long fp = -1, fn = -1;
+            double zp = 0.0, zn = 0.0;
+            for (int g = fr - 1; g >= 0; g--)
+                if (valid[g * C + col]) { fp = f_lo + g; zp = Z[g * C + col]; break; }
+            if (fp < 0)
+                for (long long f = f_lo - 1; f >= 0; f--) {
+                    const double z = ld_feat_global(f, col, p);
+                    if (z == z) { fp = f; zp = z; break; }
+                }
+            for (int g = fr + 1; g < nfr; g++)
+                if (valid[g * C + col]) { fn = f_lo + g; zn = Z[g * C + col]; break; }
+            if (fn < 0)
+                for (long long f = f_lo + nfr; f < p.n_frames; f++) {
+                    const double z = ld_feat_global(f, col, p);
+                    if (z == z) { fn = f; zn = z; break; }
+                }
+            double v = 0.0;
+            if (fp >= 0 && fn >= 0) v = zp + (zn - zp) / (double)(fn - fp) * (double)(f_lo + fr - fp);
+            else if (fp >= 0) v = zp;
+            else if (fn >= 0) v = zn;
+            Z[i] = v;
+        }
     }
     __syncthreads();
 
-    // ---- phase 4: expand the overlapping windows in output order, then TMA bulk stores -----------
+    // ---- phase 4: expand the overlapping windows in output order (one warp per (window, step) row, lanes over
+    // the row's columns; x column q = 3n + c reads feature 2n + c or 2N + n), then TMA bulk stores -----------
     const int NX = T * 3 * N, NA = T * E;
-    for (int o = tid; o < nw * NX; o += LD_THREADS) {
-        const int w = o / NX, r = o - w * NX, t = r / (3 * N), q = r - t * 3 * N, n = q / 3, c = q - 3 * n;
-        const int col = c < 2 ? 2 * n + c : 2 * N + n;
-        outx[o] = (float)Z[(w * p.step + t) * C + col];
-    }
-    for (int o = tid; o < nw * NA; o += LD_THREADS) {
-        const int w = o / NA, r = o - w * NA, t = r / E, e = r - t * E;
-        outa[o] = (float)Z[(w * p.step + t) * C + 3 * N + e];
+    for (int row = warp; row < nw * T; row += nwarp) {
+        const int w = row / T, t = row - w * T;
+        const double* zr = Z + (size_t)(w * p.step + t) * C;
+        float* ox = outx + (size_t)row * 3 * N;
+        for (int q = lane; q < 3 * N; q += 32) {
+            const int n = q / 3, c = q - 3 * n;
+            ox[q] = (float)zr[c < 2 ? 2 * n + c : 2 * N + n];
+        }
+        float* oa = outa + (size_t)row * E;
+        for (int e = lane; e < E; e += 32) oa[e] = (float)zr[3 * N + e];
     }
     float* gx = p.x + (size_t)wl0 * NX;
     float* ga = p.a + (size_t)wl0 * NA;

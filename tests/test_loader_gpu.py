@@ -172,3 +172,24 @@ def test_full_size_sliding_window_properties():
         chk = float((per_frame * mult).sum())
         got = float(x.double().sum() + a.double().sum())
         assert abs(chk - got) <= 1e-6 * max(1.0, abs(got))
+
+
+def test_streaming_embedding_per_video_equals_materialised_windows():
+    """embedding_per_video over the frame table == model.embed on the materialised windows of each video
+    (reference model_utils_new.py:452-748), for a VaDE and a VQ-VAE model."""
+    from deepof_b200 import VaDEB200, VQVAEB200, WindowLoader, embedding_per_video
+    from oracle import vade_oracle as O
+    N, T = 14, 25
+    adj = O.default_adjacency(N)
+    r, c = np.nonzero(np.triu(adj))
+    edges = np.stack([r, c], 1).astype(np.int32)
+    vids = [_synthetic(300, N, 5), _synthetic(T + 10, N, 6), _synthetic(20, N, 7)]
+    ld = WindowLoader(vids, edges, T, nose=1, tail_base=2, align_node=0, arena_center=(250.0, 250.0))
+    for cls, K in ((VaDEB200, 6), (VQVAEB200, 12)):
+        m = cls((T, N, 3), (T, len(edges), 1), adj, 8, K, max_batch=128, training=False, seed=2)
+        embs, softs = embedding_per_video(m, ld, batch_size=100)
+        assert [e.shape[0] for e in embs] == ld.n_windows_per_video and embs[2].shape == (0, 8)
+        x, a = ld.load(0, len(ld))
+        e_all, q_all = m.embed(x, a)
+        assert torch.equal(torch.cat(embs), e_all) and torch.equal(torch.cat([s for s in softs if s is not None]), q_all)
+        assert softs[0].shape == (ld.n_windows_per_video[0], K)
