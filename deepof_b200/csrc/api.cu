@@ -564,11 +564,24 @@ static int encoder_forward(dof_handle* h, const float* state, const float* x, co
     g[1] = gemm_args(mv_plain(h->Pe, 2 * D), state + L.edge_kernel, D, 1, state + L.edge_bias, h->Oe, D, B * E, D, 2 * D);
     g[0].relu = g[1].relu = 1;
     DOF_TRY(launch_gemm_rows(g, 2, st));
-    GemmArgs f0 = gemm_args(mv_plain(h->On, N * D), state + L.final_w, (N + E) * D, 0, state + L.final_b, h->enc, D, B, D, N * D);
-    DOF_TRY(launch_gemm_rows(&f0, 1, st));
-    GemmArgs f1 = gemm_args(mv_plain(h->Oe, E * D), state + L.final_w + (size_t)N * D, (N + E) * D, 0, nullptr, h->enc, D, B, D, E * D);
-    f1.accum = 1;
-    DOF_TRY(launch_gemm_rows(&f1, 1, st));
+    // final dense over the concatenated node / edge embeddings.  K = G*D (224 at cfg2) is split into two K blocks
+    // so the problem fits the tensor-core kernel's tile (the SIMT kernel would run it on B/128 = 32 CTAs).
+    for (int part = 0; part < 2; part++) {
+        const float* X = part == 0 ? h->On : h->Oe;
+        const int GD = (part == 0 ? N : E) * D;
+        const float* W = state + L.final_w + (part == 0 ? 0 : (size_t)N * D);
+        GemmArgs f;
+        if (GD % 8 == 0) {
+            f = gemm_args(mv_plain(X, GD), W, (N + E) * D, 0, part == 0 ? state + L.final_b : nullptr, h->enc, D, B, D, GD / 2);
+            f.nkb = 2;
+            f.A2 = mv_plain(X + GD / 2, GD);
+            f.W2 = W + GD / 2;
+        } else {
+            f = gemm_args(mv_plain(X, GD), W, (N + E) * D, 0, part == 0 ? state + L.final_b : nullptr, h->enc, D, B, D, GD);
+        }
+        f.accum = part;
+        DOF_TRY(launch_gemm_rows(&f, 1, st));
+    }
     return DOF_OK;
 }
 

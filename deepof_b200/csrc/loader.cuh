@@ -61,7 +61,8 @@ __device__ __forceinline__ void ld_rot(const float* R, long long fb, long long f
 
 // standardised feature `col` of frame f (NaN = undefined or clipped).  Columns: [0,2N) coords (node-major,
 // x then y), [2N,3N) speeds, [3N,3N+E) log1p edge lengths.  R/fb: frame f lives at R[(f-fb)*2N ...].
-__device__ __forceinline__ double ld_feat(const float* R, long long fb, long long f, int col, const LoaderP& p, double cs, double sn) {
+template <typename COLS>
+__device__ __forceinline__ double ld_feat(const float* R, long long fb, long long f, int col, const LoaderP& p, const COLS& cc, double cs, double sn) {
     const int N = p.N;
     double z;
     if (col < 2 * N) {
@@ -85,26 +86,34 @@ __device__ __forceinline__ double ld_feat(const float* R, long long fb, long lon
             s += sqrt(dx * dx + dy * dy);                                 // utils.py:3826-3838
         }
         const double v = rint(s / 3.0 * 1000.0) / 1000.0 * p.fps;         // np.round(., 3) * frame_rate
-        z = v * p.speed_scale[n] + p.speed_shift[n];
+        z = v * cc.speed_scale[n] + cc.speed_shift[n];
     } else {
         const int e = col - 3 * N;
-        const float* qa = R + (f - fb) * 2 * N + 2 * p.e0[e];
-        const float* qb = R + (f - fb) * 2 * N + 2 * p.e1[e];
+        const float* qa = R + (f - fb) * 2 * N + 2 * cc.e0[e];
+        const float* qb = R + (f - fb) * 2 * N + 2 * cc.e1[e];
         const double dx = (double)qa[0] - (double)qb[0], dy = (double)qa[1] - (double)qb[1];
-        double d = sqrt(dx * dx + dy * dy) / p.dist_div[e];               // utils.py:877-880, 2520-2526
+        double d = sqrt(dx * dx + dy * dy) / cc.dist_div[e];               // utils.py:877-880, 2520-2526
         if (d < 0.0) d = 0.0;
-        z = log1p(d) * p.dist_scale[e] + p.dist_shift[e];                 // utils.py:2528-2531
+        z = log1p(d) * cc.dist_scale[e] + cc.dist_shift[e];                 // utils.py:2528-2531
     }
     if (p.clip > 0.0 && fabs(z) > p.clip) z = nan("");                    // utils.py:2996-2999
     return z;
 }
 
-__device__ __forceinline__ double ld_feat_global(long long f, int col, const LoaderP& p) {
+template <typename COLS>
+__device__ __forceinline__ double ld_feat_global(long long f, int col, const LoaderP& p, const COLS& cc) {
     double cs = 1.0, sn = 0.0;
     if (col < 2 * p.N) ld_rot(p.frames, 0, f, p, cs, sn);
-    return ld_feat(p.frames, 0, f, col, p, cs, sn);
+    return ld_feat(p.frames, 0, f, col, p, cc, cs, sn);
 }
 
+// per-column constants as the kernels index them (shared-memory copy: a lane-dependent index into the kernel
+// parameter space would serialise on the constant cache)
+struct LoaderCols {
+    double speed_scale[LD_MAXN], speed_shift[LD_MAXN];
+    double dist_div[LD_MAXE], dist_scale[LD_MAXE], dist_shift[LD_MAXE];
+    short e0[LD_MAXE], e1[LD_MAXE];
+};
 struct LoaderSmem { size_t raw, z, valid, rot, out, total; };
 static inline LoaderSmem loader_smem(int T, int step, int N, int E, int wpb) {
     const size_t nf = (size_t)(wpb - 1) * step + T, C = 3 * (size_t)N + E;
@@ -121,7 +130,13 @@ static inline LoaderSmem loader_smem(int T, int step, int N, int E, int wpb) {
 
 __global__ void __launch_bounds__(LD_THREADS) load_windows_kernel(const __grid_constant__ LoaderP p, const LoaderSmem so) {
     extern __shared__ __align__(128) unsigned char ld_smem[];
+    __shared__ LoaderCols cc;
     const int N = p.N, E = p.E, T = p.T, C = 3 * N + E, tid = threadIdx.x;
+    for (int i = tid; i < LD_MAXN; i += LD_THREADS) { cc.speed_scale[i] = p.speed_scale[i]; cc.speed_shift[i] = p.speed_shift[i]; }
+    for (int i = tid; i < LD_MAXE; i += LD_THREADS) {
+        cc.dist_div[i] = p.dist_div[i]; cc.dist_scale[i] = p.dist_scale[i]; cc.dist_shift[i] = p.dist_shift[i];
+        cc.e0[i] = p.e0[i]; cc.e1[i] = p.e1[i];
+    }
     const int wl0 = blockIdx.x * p.wpb;                     // first window of this CTA inside the batch
     const int nw = min(p.wpb, p.B - wl0);
     const long long f_lo = (p.w_start + wl0) * (long long)p.step;
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(LD_THREADS) load_windows_kernel(const __grid_c
             sn = __shfl_sync(0xffffffffu, sn, 0);
         }
         for (int col = lane; col < C; col += 32) {
-            const double z = ld_feat(R, f_raw, f_lo + fr, col, p, cs, sn);
+            const double z = ld_feat(R, f_raw, f_lo + fr, col, p, cc, cs, sn);
             Z[fr * C + col] = z;
             valid[fr * C + col] = (z == z) ? 1 : 0;
         }
@@ -197,14 +212,14 @@ __global__ void __launch_bounds__(LD_THREADS) load_windows_kernel(const __grid_c
                 if (valid[g * C + col]) { fp = f_lo + g; zp = Z[g * C + col]; break; }
             if (fp < 0)
                 for (long long f = f_lo - 1; f >= 0; f--) {
-                    const double z = ld_feat_global(f, col, p);
+                    const double z = ld_feat_global(f, col, p, cc);
                     if (z == z) { fp = f; zp = z; break; }
                 }
             for (int g = fr + 1; g < nfr; g++)
                 if (valid[g * C + col]) { fn = f_lo + g; zn = Z[g * C + col]; break; }
             if (fn < 0)
                 for (long long f = f_lo + nfr; f < p.n_frames; f++) {
-                    const double z = ld_feat_global(f, col, p);
+                    const double z = ld_feat_global(f, col, p, cc);
                     if (z == z) { fn = f; zn = z; break; }
                 }
             double v = 0.0;
@@ -273,7 +288,7 @@ __global__ void __launch_bounds__(256) loader_moments_kernel(const __grid_consta
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long f = i / C;
         const int col = (int)(i - f * C);
-        const double z = ld_feat_global(f, col, p);
+        const double z = ld_feat_global(f, col, p, p);
         if (z != z) continue;
         const int g = col < 2 * N ? 0 : (col < 3 * N ? 1 : 2);
         const double d = z - (g == 0 ? s0 : (g == 1 ? s1 : s2));
