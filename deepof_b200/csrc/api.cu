@@ -746,8 +746,18 @@ static int enc_block_backward(dof_handle* h, int bi, const float* state, float* 
     b.len = w.len; b.Hout = w.H1; b.dOut = w.dH1; b.dHn = nullptr; b.S = S; b.T = T; b.H = H1;
     DOF_TRY(launch_gru_bwd(b, st));
     DOF_TRY(gru_param_grads(h, P.g1, grad, state, w.dG1, mv_plain(w.Cv, C1), M, w.dG1, w.H1, M, T, C1, H1, w.dCv, w.Cv, st));
-    WGradArgs wc = wgrad_args(mv_plain(w.dCv, C1), mv_conv5(w.Xs, w.Fin, T, +1), grad + P.conv, w.Fin * 5, 0, nullptr, M, C1, w.Fin * 5);
-    DOF_TRY(launch_gemm_wgrad(&wc, 1, st, sm));
+    if (C1 * w.Fin <= 256) {
+        ConvWgradArgs ca;
+        ca.dCv = w.dCv; ca.Xs = w.Xs; ca.dW = grad + P.conv; ca.S = S; ca.T = T; ca.C = C1; ca.F = w.Fin;
+        const int pairs = C1 * w.Fin, slots = 256 / pairs, threads = pairs * slots;
+        int grid = cdiv(S, slots) < sm * 16 ? cdiv(S, slots) : sm * 16;
+        { ProfScope ps("conv_wgrad", st, 2.0 * M * C1 * w.Fin * 5, 4.0 * M * (C1 + w.Fin));
+        conv_wgrad_kernel<<<grid, threads, 0, st>>>(ca); }
+        DOF_LAUNCH_CHECK();
+    } else {
+        WGradArgs wc = wgrad_args(mv_plain(w.dCv, C1), mv_conv5(w.Xs, w.Fin, T, +1), grad + P.conv, w.Fin * 5, 0, nullptr, M, C1, w.Fin * 5);
+        DOF_TRY(launch_gemm_wgrad(&wc, 1, st, sm));
+    }
     return DOF_OK;
 }
 

@@ -72,6 +72,8 @@ struct GemmArgs {
     // bidirectional GRU  dX = dG_fwd.W_ih_fwd + dG_bwd.W_ih_bwd  without a read-modify-write of C
     int nkb;                           // 0/1: single block, 2: A2/W2 are valid
     MatView A2; const float* W2;
+    int ksplit;                        // tensor-core kernel only: K of every matrix is staged in `ksplit` column
+                                       // blocks (smaller smem stages -> double buffering for K > 64); 0/1 = off
 };
 struct GemmBatch { GemmArgs g[2]; };
 

@@ -61,6 +61,51 @@ __global__ void __launch_bounds__(256) enc_conv_kernel(const EncConvArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Weight gradient of the encoder Conv1d(F -> C, k=5, 'same', no bias):
+//   dW[c][f][kk] += sum_{s,t} dCv[s,t,c] * Xs[s, t+kk-2, f]      (zero outside [0,T))
+// One thread per (c, f) pair and sequence slot; the 5-tap window of Xs slides through registers, so a step costs
+// one coalesced read of dCv (lanes = consecutive c) and one broadcast read of Xs for 5 FMAs.  No shared-memory
+// staging, no tensor core: 32 x 15 outputs over 1.4 M rows is a pure stream of dCv (HBM-bound).
+// ---------------------------------------------------------------------------
+struct ConvWgradArgs { const float* dCv; const float* Xs; float* dW; int S, T, C, F; };
+
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const ConvWgradArgs a) {
+    __shared__ float red[256 * 5];
+    const int pairs = a.C * a.F, slots = blockDim.x / pairs;
+    const int tid = threadIdx.x;
+    const int pair = tid % pairs, slot = tid / pairs;
+    const int c = pair % a.C, f = pair / a.C;
+    const int T = a.T, C = a.C, F = a.F;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (slot < slots) {
+        for (long long seq = (long long)blockIdx.x * slots + slot; seq < a.S; seq += (long long)gridDim.x * slots) {
+            const float* xs = a.Xs + seq * T * F + f;
+            const float* dc = a.dCv + seq * T * C + c;
+            float xm2 = 0.f, xm1 = 0.f, x0 = xs[0], xp1 = T > 1 ? xs[F] : 0.f, xp2 = T > 2 ? xs[2 * F] : 0.f;
+#pragma unroll 5
+            for (int t = 0; t < T; t++) {
+                const float d = dc[(size_t)t * C];
+                acc[0] = fmaf(d, xm2, acc[0]); acc[1] = fmaf(d, xm1, acc[1]); acc[2] = fmaf(d, x0, acc[2]);
+                acc[3] = fmaf(d, xp1, acc[3]); acc[4] = fmaf(d, xp2, acc[4]);
+                xm2 = xm1; xm1 = x0; x0 = xp1; xp1 = xp2;
+                xp2 = (t + 3 < T) ? xs[(size_t)(t + 3) * F] : 0.f;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) red[tid * 5 + k] = (slot < slots) ? acc[k] : 0.f;
+    __syncthreads();
+    if (tid < pairs) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            float s = 0.f;
+            for (int q = 0; q < slots; q++) s += red[(q * pairs + tid) * 5 + k];
+            atomicAdd(a.dW + (size_t)c * F * 5 + f * 5 + k, s);
+        }
+    }
+}
+
 // decoder validity: len[b] = #time steps whose data row is not all-zero (models_new.py:330-331).
 // One warp per window; a time step's row (Dx floats, contiguous) is read by the whole warp.
 __global__ void row_valid_len_kernel(const float* __restrict__ x, int* __restrict__ len, int B, int T, int Dx) {

@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
     const GemmArgs& g = gb.g[blockIdx.z];
     extern __shared__ __align__(128) unsigned char tsm[];
     const int S = geo.stages;
-    const int nkb = g.nkb == 2 ? 2 : 1;                               // K blocks per tile (second block: A2 / W2)
+    const int ksp = g.ksplit > 1 ? g.ksplit : 1;                      // column blocks per matrix
+    const int nkb = (g.nkb == 2 ? 2 : 1) * ksp;                       // K blocks per tile: (A | A2) x column block
+    const int Kb = g.K / ksp;                                         // K of one block
     unsigned char* W_hi = tsm;                                        // [nkb] x (W_hi | W_lo)
     unsigned char* W_lo = W_hi + geo.w_bytes;
     unsigned char* A_base = tsm + (size_t)nkb * 2 * geo.w_bytes;      // S x (A_hi | A_lo)
@@ -140,12 +142,13 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
     }
     // stage W (hi/lo) once: canonical K-major, rows n at 16 B, K-chunks at w_lbo
     for (int kb = 0; kb < nkb; kb++) {
-        const float* Wp = kb ? g.W2 : g.W;
+        const float* Wp = (kb / ksp) ? g.W2 : g.W;
+        const int k0 = (kb % ksp) * Kb;
         for (int i = tid; i < NP * KP; i += TCR_THREADS) {
             int n, k;
             if (g.wT == 0) { n = i / KP; k = i % KP; } else { k = i / NP; n = i % NP; }
             float v = 0.f;
-            if (n < g.N && k < g.K) v = g.wT == 0 ? __ldg(Wp + (size_t)n * g.ldw + k) : __ldg(Wp + (size_t)k * g.ldw + n);
+            if (n < g.N && k < Kb) v = g.wT == 0 ? __ldg(Wp + (size_t)n * g.ldw + k0 + k) : __ldg(Wp + (size_t)(k0 + k) * g.ldw + n);
             float hi, lo;
             split_tf32(v, hi, lo);
             uint32_t off = (uint32_t)kb * 2 * geo.w_bytes + (uint32_t)n * 16 + (uint32_t)(k >> 2) * geo.w_lbo + (k & 3) * 4;
@@ -169,7 +172,9 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
         // work item w = (local tile index) * nkb + kb
         auto load_regs = [&](float4 (&r)[KQM], int w) {
             const int tile = blockIdx.x + (w / nkb) * gridDim.x;
-            const MatView& Av = (w % nkb) ? g.A2 : g.A;
+            const int kb = w % nkb;
+            const MatView& Av = (kb / ksp) ? g.A2 : g.A;
+            const int k0 = (kb % ksp) * Kb;
             const int m0 = tile * 128;
 #pragma unroll
             for (int j = 0; j < KQM; j++) {
@@ -178,7 +183,8 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                 if (j < KQ) {
                     int row = i / KQ, kq = i - row * KQ;
                     int m = m0 + row, c = kq * 4;
-                    if (m < g.M && c < g.K) {
+                    if (m < g.M && c < Kb) {
+                        c += k0;
                         if (split && c >= Av.split) c += Av.skip;
                         r[j] = __ldg(reinterpret_cast<const float4*>(Av.p + (size_t)m * Av.ld + c));
                     }
@@ -362,7 +368,7 @@ static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem, int nkb = 
 }
 
 static bool tc_rows_eligible(const GemmArgs& g) {
-    if (g.M < 2048 || g.N > 256 || g.K > 128 || g.N < 8) return false;
+    if (g.M < 2048 || g.N > 256 || g.K > 128 * (g.ksplit > 1 ? g.ksplit : 1) || g.N < 8) return false;
     if (g.A.mode != A_PLAIN && g.A.mode != A_SPLIT) return false;
     if ((g.A.ld & 3) || (g.K & 3) || !aligned16(g.A.p)) return false;
     if (g.A.mode == A_SPLIT && ((g.A.split & 3) || (g.A.skip & 3))) return false;
@@ -371,8 +377,10 @@ static bool tc_rows_eligible(const GemmArgs& g) {
         if (g.A2.mode != g.A.mode || g.A2.ld != g.A.ld || g.A2.split != g.A.split || g.A2.skip != g.A.skip) return false;
         if (!aligned16(g.A2.p) || !g.W2) return false;
     }
+    const int ksp = g.ksplit > 1 ? g.ksplit : 1;
+    if (g.K % ksp || ((g.K / ksp) & 3)) return false;
     TcRowsGeom geo; size_t smem;
-    return tc_rows_geom(g.N, g.K, geo, smem, g.nkb == 2 ? 2 : 1);
+    return tc_rows_geom(g.N, g.K / ksp, geo, smem, (g.nkb == 2 ? 2 : 1) * ksp);
 }
 
 template <int KQM, int NSET>
@@ -399,8 +407,14 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     }
     TcRowsGeom geo;
     size_t smem = 0;
-    const int nkb = gs[0].nkb == 2 ? 2 : 1;
-    if (!tc_rows_geom(gs[0].N, gs[0].K, geo, smem, nkb)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC GEMM tile does not fit");
+    const int nmat = gs[0].nkb == 2 ? 2 : 1;
+    // ksplit > 1 stages every matrix in column blocks (smaller stages, register prefetch).  Measured on B200 for the
+    // K = 96 / N = 32 input-gradient GEMM: two 48-column blocks were 11 % SLOWER than one 96-column stage (the
+    // per-stage barrier round trips outweigh the overlap), so it is opt-in only.
+    int ksp = gs[0].ksplit > 1 ? gs[0].ksplit : 1;
+    for (int i = 0; i < nbatch; i++) gb.g[i].ksplit = ksp;
+    const int nkb = nmat * ksp;
+    if (!tc_rows_geom(gs[0].N, gs[0].K / ksp, geo, smem, nkb)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC GEMM tile does not fit");
     const int KQ = geo.KP / 4;
     int occ = (int)((228 * 1024) / (smem + 1024));
     int by_tmem = 512 / geo.tmem_cols;
@@ -414,8 +428,8 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     if (ctas > ntiles) ctas = ntiles;
     double fl = 0.0, by = 0.0;
     for (int i = 0; i < nbatch; i++) {
-        fl += 2.0 * gs[i].M * gs[i].N * gs[i].K * nkb;
-        by += 4.0 * gs[i].M * ((double)gs[i].K * nkb + (double)gs[i].N * (1 + (gs[i].accum ? 1 : 0) + (gs[i].mask ? 1 : 0)));
+        fl += 2.0 * gs[i].M * gs[i].N * gs[i].K * nmat;
+        by += 4.0 * gs[i].M * ((double)gs[i].K * nmat + (double)gs[i].N * (1 + (gs[i].accum ? 1 : 0) + (gs[i].mask ? 1 : 0)));
     }
     ProfScope ps("gemm_rows_tc", st, fl, by);
     dim3 grid(ctas, 1, nbatch);
