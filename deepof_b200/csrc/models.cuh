@@ -239,7 +239,10 @@ struct NtxArgs {
     const float* enc;   // [2B, D] encoder outputs: rows 0..B-1 = z, B..2B-1 = z_aug
     float* zn;          // [2B, D] row-normalised
     float* nrm;         // [2B]
-    float* lse;         // [B] log-sum-exp of every row of sim
+    float* lse;         // [4,B] per-row coefficients of the gradient pass: m_i | A_i | P_i | Dg_i with
+                        //   d loss_i / d s_ij = e_ij (A_i + P_i e_ij), e_ij = exp(s_ij - m_i), for j != i;  Dg_i for j == i
+    int kind;           // 0 nce (losses.py:130-141), 1 dcl debiased (:144-173), 2 hard_dcl debiased (:213-249)
+    float tau_plus, beta, temperature;
     float* denc;        // [2B, D] gradient wrt enc
     double* stats;
     float* logs;
@@ -268,8 +271,8 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
     extern __shared__ float nsm[];
     const int D = a.D, B = a.B, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = nsm;                               // [NTX_TILE][DP+1]
-    float* tl = tile + NTX_TILE * (DP + 1);          // [NTX_TILE] lse of the tile rows (column blocks)
-    float* mine = tl + NTX_TILE + warp * DP;         // this warp's own row
+    float* tl = tile + NTX_TILE * (DP + 1);          // [4][NTX_TILE] gradient coefficients of the tile rows (column blocks)
+    float* mine = tl + 4 * NTX_TILE + warp * DP;     // this warp's own row
     const int nb = (B + NTX_WARPS - 1) / NTX_WARPS;
     const bool col = PHASE == 1 && (int)blockIdx.x >= nb;
     const int self = ((int)blockIdx.x % nb) * NTX_WARPS + warp;      // index inside its own matrix
@@ -282,7 +285,9 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
     float acc[DP];
 #pragma unroll
     for (int d = 0; d < DP; d++) acc[d] = 0.f;
-    const float my_lse = (PHASE == 1 && active && !col) ? a.lse[self] : 0.f;
+    float my_m = 0.f, my_A = 0.f, my_P = 0.f, my_D = 0.f;
+    if (PHASE == 1 && active && !col) { my_m = a.lse[self]; my_A = a.lse[B + self]; my_P = a.lse[2 * B + self]; my_D = a.lse[3 * B + self]; }
+    float l2 = 0.f;
     const float gs = a.inv_tau / (float)B;
     for (int j0 = 0; j0 < B; j0 += NTX_TILE) {
         __syncthreads();
@@ -290,7 +295,11 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
             const int r = i / D, d = i - r * D;
             tile[r * (DP + 1) + d] = (j0 + r < B) ? other[(size_t)(j0 + r) * D + d] : 0.f;
         }
-        if (col) for (int i = threadIdx.x; i < NTX_TILE; i += blockDim.x) tl[i] = (j0 + i < B) ? a.lse[j0 + i] : 0.f;
+        if (col)
+            for (int i = threadIdx.x; i < 4 * NTX_TILE; i += blockDim.x) {
+                const int q = i / NTX_TILE, r = i - q * NTX_TILE;
+                tl[i] = (j0 + r < B) ? a.lse[q * B + j0 + r] : 0.f;
+            }
         __syncthreads();
         if (!active) continue;
         for (int r = lane; r < NTX_TILE && j0 + r < B; r += 32) {
@@ -303,11 +312,15 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
                 sall += s;
                 if (j0 + r == self) sdiag = s;
                 const float mn = fmaxf(m, s);
-                l = l * __expf(m - mn) + __expf(s - mn);
+                const float sc = __expf(m - mn), e = __expf(s - mn);
+                l = l * sc + e;
+                l2 = l2 * sc * sc + e * e;
                 m = mn;
             } else {
-                float g = __expf(s - (col ? tl[r] : my_lse));
-                if (j0 + r == self) g -= 1.f;
+                const float rm = col ? tl[r] : my_m, rA = col ? tl[NTX_TILE + r] : my_A, rP = col ? tl[2 * NTX_TILE + r] : my_P,
+                            rD = col ? tl[3 * NTX_TILE + r] : my_D;
+                const float e = __expf(s - rm);
+                float g = (j0 + r == self) ? rD : e * (rA + rP * e);
                 g *= gs;
 #pragma unroll
                 for (int d = 0; d < DP; d++) if (d < D) acc[d] += g * tr[d];
@@ -317,13 +330,41 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
     if (!active) return;
     if (PHASE == 0) {
         const float mall = warp_max(m);
-        l = warp_sum(l * __expf(m - mall));
+        const float rs = __expf(m - mall);
+        l = warp_sum(l * rs);
+        l2 = warp_sum(l2 * rs * rs);
         sall = warp_sum(sall);
         sdiag = warp_sum(sdiag);
         if (lane == 0) {
-            const float lse = mall + logf(l);
-            a.lse[self] = lse;
-            atomicAdd(a.stats + NTX_ST_LOSS, (double)(lse - sdiag));
+            // per-row loss and gradient coefficients (fp64: exp(s) reaches e^(1/temperature))
+            const double E = exp((double)mall), pos = exp((double)sdiag), ed = exp((double)sdiag - (double)mall);
+            const double Neff = (double)(B - 1), tp = (double)a.tau_plus;
+            double loss, A, P = 0.0, Dg;
+            if (a.kind == 0) {
+                loss = (double)mall + log((double)l) - (double)sdiag;
+                A = 1.0 / (double)l;
+                Dg = ed / (double)l - 1.0;
+            } else {
+                const double S = fmax((double)l - ed, 0.0) * E;                      // sum of the negatives exp(s_ij)
+                const double Q = fmax((double)l2 - ed * ed, 0.0) * E * E;            // sum of their squares
+                double raw, clip;
+                if (a.kind == 1) { raw = (-tp * Neff * pos + S) / (1.0 - tp); clip = Neff * exp(-1.0 / (double)a.temperature); }
+                else {
+                    const double R = a.beta != 0.f ? (double)a.beta * Neff * Q / fmax(S, 1e-300) : S;
+                    raw = (-tp * Neff * pos + R) / (1.0 - tp); clip = exp(-1.0 / (double)a.temperature);
+                }
+                const double act = raw > clip ? 1.0 : 0.0, Ng = fmax(raw, clip);
+                const double den = (1.0 - tp) * (pos + Ng);
+                loss = log(pos + Ng) - (double)sdiag;
+                Dg = (pos - act * tp * Neff * pos / (1.0 - tp)) / (pos + Ng) - 1.0;
+                if (a.kind == 1 || a.beta == 0.f) A = act * E / den;
+                else {
+                    A = -act * (double)a.beta * Neff * Q * E / (fmax(S, 1e-300) * fmax(S, 1e-300)) / den;
+                    P = act * 2.0 * (double)a.beta * Neff * E * E / fmax(S, 1e-300) / den;
+                }
+            }
+            a.lse[self] = mall; a.lse[B + self] = (float)A; a.lse[2 * B + self] = (float)P; a.lse[3 * B + self] = (float)Dg;
+            atomicAdd(a.stats + NTX_ST_LOSS, loss);
             atomicAdd(a.stats + NTX_ST_POS, (double)sdiag);
             atomicAdd(a.stats + NTX_ST_ALL, (double)sall);
         }

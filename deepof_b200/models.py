@@ -154,10 +154,12 @@ class ContrastiveB200(VaDEB200):
 
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int = 8,
                  encoder_type: str = "recurrent", use_gnn: bool = True, temperature: float = 0.1,
-                 similarity_function: str = "cosine", loss_function: str = "nce", edge_index=None,
-                 edge_index_local=None, max_batch: int = 4096, **kw):
-        if similarity_function != "cosine" or loss_function != "nce":
-            raise NotImplementedError("deepof_b200 implements the cosine / nce contrastive loss only")
+                 similarity_function: str = "cosine", loss_function: str = "nce", beta: float = 0.1, tau: float = 0.1,
+                 edge_index=None, edge_index_local=None, max_batch: int = 4096, **kw):
+        if similarity_function != "cosine" or loss_function not in ("nce", "dcl", "hard_dcl"):
+            raise NotImplementedError("deepof_b200 implements the cosine similarity with the nce / dcl / hard_dcl losses "
+                                      f"(got {similarity_function!r}, {loss_function!r})")
+        self.loss_function, self.beta, self.tau = loss_function, float(beta), float(tau)
         Tf, N, F = (int(v) for v in input_shape)
         _, E, Fe = (int(v) for v in edge_feature_shape)
         self.full_time_steps = Tf
@@ -272,8 +274,10 @@ class ContrastiveB200(VaDEB200):
             raise _lib.DofError("model was created with training=False")
         x2, a2 = self.views(x_full, prm)
         B = x2.shape[0] // 2
-        check(self.L.dof_contrastive_loss_grad(self.handle, ptr(self.state), ptr(self.grad), ptr(x2), ptr(a2), B,
-                                               self.temperature, ptr(self.logs), ptr(self.z_all[:2 * B]), _stream()))
+        kind = {"nce": 0, "dcl": 1, "hard_dcl": 2}[self.loss_function]
+        check(self.L.dof_contrastive_loss_grad(self.handle, ptr(self.state), ptr(self.grad), ptr(x2), ptr(a2), B, kind,
+                                               self.temperature, self.tau, self.beta, ptr(self.logs),
+                                               ptr(self.z_all[:2 * B]), _stream()))
         return self.logs
 
     def adam_step(self, lr: float, clip: float = 0.75, grad_scale: float = 1.0, weight_decay: float = 1e-4, **kw):

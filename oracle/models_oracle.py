@@ -85,7 +85,7 @@ def vqvae_train_step(x: Tensor, a: Tensor, p: Dict[str, Tensor], graph, latent_d
     rec = -(V.recon_log_prob(out["loc_e"], out["mask"], xf)).mean()       # :332
     total = enc_rec + rec + (out["vq"]["vq_loss"] + out["vq"]["kmeans_loss"])
     glist = torch.autograd.grad(total, [leaf[k] for k in names], allow_unused=True)
-    logs = {"total_loss": float(total), "enc_rec_loss": float(enc_rec), "reconstruct_loss": float(rec),
+    logs = {"total_loss": float(total.detach()), "enc_rec_loss": float(enc_rec.detach()), "reconstruct_loss": float(rec.detach()),
             "vq_loss": out["vq"]["vq_loss"], "kmeans_loss": out["vq"]["kmeans_loss"],
             "number_of_populated_clusters": float(out["soft"].argmax(dim=-1).unique().numel()), "distill_loss": 0.0}
     return logs, dict(zip(names, glist)), {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
@@ -301,18 +301,70 @@ def nce_loss(z: Tensor, z_aug: Tensor, temperature: float):
     return loss, pos, neg
 
 
+def _cos_sim(z: Tensor, z_aug: Tensor) -> Tensor:
+    zn = torch.nn.functional.normalize(z, dim=1)
+    an = torch.nn.functional.normalize(z_aug, dim=1)
+    return torch.nn.functional.cosine_similarity(zn.unsqueeze(1), an.unsqueeze(0), dim=2)
+
+
+def _off_diag(sim: Tensor) -> Tensor:
+    n = sim.shape[0]
+    return sim[~torch.eye(n, dtype=torch.bool)].reshape(n, n - 1)
+
+
+def dcl_loss(z: Tensor, z_aug: Tensor, temperature: float, tau_plus: float):
+    """dcl_loss_pt, debiased (losses.py:144-173)."""
+    sim = _cos_sim(z, z_aug)
+    n = sim.shape[0]
+    pos = torch.exp(torch.diag(sim) / temperature)
+    neg = _off_diag(sim)
+    neg_sim = torch.exp(neg / temperature)
+    n_eff = n - 1
+    ng = (-tau_plus * n_eff * pos + neg_sim.sum(dim=-1)) / (1.0 - tau_plus)
+    ng = torch.clamp(ng, min=n_eff * math.e ** (-1.0 / temperature), max=torch.finfo(z.dtype).max)
+    loss = (-torch.log(pos / (pos + ng))).mean()
+    return loss, torch.diag(sim).mean(), neg.mean()
+
+
+def hard_loss(z: Tensor, z_aug: Tensor, temperature: float, tau_plus: float, beta: float):
+    """hard_loss_pt, debiased (losses.py:213-249)."""
+    sim = _cos_sim(z, z_aug)
+    n = sim.shape[0]
+    pos = torch.exp(torch.diag(sim) / temperature)
+    neg = _off_diag(sim)
+    neg_sim = torch.exp(neg / temperature)
+    reweight = torch.ones_like(neg_sim) if beta == 0.0 else (beta * neg_sim) / neg_sim.mean(dim=1, keepdim=True)
+    n_eff = n - 1
+    ng = (-tau_plus * n_eff * pos + (reweight * neg_sim).sum(dim=-1)) / (1.0 - tau_plus)
+    ng = torch.clamp(ng, min=math.e ** (-1.0 / temperature), max=torch.finfo(z.dtype).max)
+    loss = (-torch.log(pos / (pos + ng))).mean()
+    return loss, torch.diag(sim).mean(), neg.mean()
+
+
+def contrastive_loss(z, z_aug, loss_fn: str, temperature: float, tau_plus: float = 0.1, beta: float = 0.1):
+    """select_contrastive_loss_pt (losses.py:35-56) for the cosine similarity."""
+    if loss_fn == "nce":
+        return nce_loss(z, z_aug, temperature)
+    if loss_fn == "dcl":
+        return dcl_loss(z, z_aug, temperature, tau_plus)
+    if loss_fn == "hard_dcl":
+        return hard_loss(z, z_aug, temperature, tau_plus, beta)
+    raise ValueError(loss_fn)
+
+
 CON_LOG_KEYS = ("total_loss", "pos_similarity", "neg_similarity", "distill_loss", "seperability")
 
 
 def contrastive_train_step(x_full: Tensor, p: Dict[str, Tensor], graph, latent_dim: int, edge_index: Tensor,
-                           prm: AugParams, temperature: float = 0.1):
+                           prm: AugParams, temperature: float = 0.1, loss_fn: str = "nce", tau_plus: float = 0.1,
+                           beta: float = 0.1):
     """step_contrastive_distill forward + backward without teacher / labels."""
     names = [k for k in p if k not in V.BUFFER_NAMES]
     leaf = {k: (v.detach().clone().requires_grad_(True) if k in names and v.dtype.is_floating_point else v) for k, v in p.items()}
     x, a, xa, aa = contrastive_views(x_full, edge_index, prm)
     z = V.encoder_forward(x, a, leaf, graph, latent_dim)
     za = V.encoder_forward(xa, aa, leaf, graph, latent_dim)
-    loss, pos, neg = nce_loss(z, za, temperature)
+    loss, pos, neg = contrastive_loss(z, za, loss_fn, temperature, tau_plus, beta)
     glist = torch.autograd.grad(loss, [leaf[k] for k in names], allow_unused=True)
     logs = {"total_loss": float(loss), "pos_similarity": float(pos), "neg_similarity": float(neg), "distill_loss": 0.0,
             "seperability": 0.0}

@@ -38,6 +38,8 @@ CON_CASES = {
     "cfg4": dict(T=50, N=22, D=16, B=12, seed=31, aug=dict(p_rot=0.7, p_noise=1.0, p_interp=0.6, n_rot=3)),
     "defaults": dict(T=50, N=14, D=8, B=16, seed=32, aug=dict()),
     "odd": dict(T=24, N=11, D=6, B=9, seed=33, aug=dict(p_rot=1.0, p_noise=0.5, p_interp=1.0, max_shift=3)),
+    "dcl": dict(T=50, N=14, D=8, B=16, seed=34, aug=dict(p_interp=0.6), loss="dcl"),
+    "hard": dict(T=50, N=14, D=8, B=16, seed=35, aug=dict(p_interp=0.6), loss="hard_dcl"),
 }
 
 
@@ -110,7 +112,7 @@ def run_con(name, c):
     E = len(rows)
     x_full, a_full = synthetic_windows(c["B"], c["T"], adj, seed=3000 + c["seed"])
     model = M.ContrastivePT((c["T"], N, 3), (c["T"], E, 1), adj, c["D"], encoder_type="recurrent", use_gnn=True,
-                            temperature=0.1, similarity_function="cosine", loss_function="nce")
+                            temperature=0.1, similarity_function="cosine", loss_function=c.get("loss", "nce"))
     names = ([f"B_n{i}" for i in range(N // 2)] + [f"W_n{i}" for i in range(N - N // 2)]) if name == "cfg4" \
         else [f"B_n{i}" for i in range(N)]
     meta = {"node_columns": [(n, "x") for n in names] + [(n, "y") for n in names] + names,
@@ -122,7 +124,8 @@ def run_con(name, c):
         setattr(ccfg, "aug_" + k, v)
     out = {"adjacency": adj, "x_full": x_full.numpy(), "a_full": a_full.numpy(), "edge_index": eg.numpy(),
            "edge_index_local": el.numpy(), "meta": np.array([c["T"], N, E, c["D"], c["B"]], dtype=np.int64),
-           "temperature": np.array(0.1)}
+           "temperature": np.array(0.1), "loss_function": np.array(c.get("loss", "nce")), "tau": np.array(model.tau),
+           "beta": np.array(model.beta)}
     for f in ("min_shift", "max_shift", "p_shift", "max_rot", "n_rot", "p_rot", "max_interp", "min_interp", "p_interp",
               "noise_sigma", "p_noise"):
         out["aug/" + f] = np.array(getattr(ccfg, "aug_" + f), dtype=np.float64)

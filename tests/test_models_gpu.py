@@ -148,6 +148,8 @@ def _con_model(g, max_batch=None):
     from deepof_b200 import ContrastiveB200
     Tf, N, E, D, B = (int(v) for v in g["meta"])
     m = ContrastiveB200((Tf, N, 3), (Tf, E, 1), g["adjacency"], D, temperature=float(g["temperature"]),
+                        loss_function=str(g["loss_function"]) if "loss_function" in g else "nce",
+                        tau=float(g["tau"]) if "tau" in g else 0.1, beta=float(g["beta"]) if "beta" in g else 0.1,
                         edge_index=g["edge_index"], edge_index_local=g["edge_index_local"], max_batch=max_batch or B, seed=0)
     assert list(m.state_dict().keys()) == [k[2:] for k in g if k.startswith("p/")]
     return _load(m, g)
@@ -220,6 +222,33 @@ def test_contrastive_vs_oracle_multi_tile_batch():
         assert abs(got[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, got[k], v)
     bad = []
     _check_grads(m, {k: v for k, v in grads.items() if v is not None}, bad, "oracle-B300")
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("loss_fn,beta", [("dcl", 0.1), ("hard_dcl", 0.1), ("hard_dcl", 0.0), ("hard_dcl", 1.0)])
+def test_contrastive_debiased_losses_vs_oracle(loss_fn, beta):
+    """dcl / hard_dcl (losses.py:144-249) on a multi-tile batch, incl. beta = 0 (no re-weighting)."""
+    from deepof_b200 import ContrastiveB200
+    Tf, N, D, B = 50, 14, 16, 200
+    adj = O.default_adjacency(N)
+    r, c = np.nonzero(np.triu(adj))
+    ei = np.stack([r, c], 1)
+    x_full, _ = O.synthetic_windows(B, Tf, adj, seed=78)
+    m = ContrastiveB200((Tf, N, 3), (Tf, len(r), 1), adj, D, temperature=0.1, loss_function=loss_fn, tau=0.1, beta=beta,
+                        max_batch=B, seed=7)
+    p = {k: v.cpu() for k, v in m.state_dict().items()}
+    graph = O.graph_operators(adj)
+    rot = MO.rotation_table(ei, N)
+    torch.manual_seed(6)
+    prm = MO.draw_aug_params(B, Tf, N, MO.AugCfg(), rot)
+    logs, grads, out = MO.contrastive_train_step(x_full, p, graph, D, torch.from_numpy(ei), prm, 0.1, loss_fn=loss_fn,
+                                                 tau_plus=0.1, beta=beta)
+    m.loss_grad(x_full, _to_product_params(prm))
+    got = m.logs_dict()
+    for k, v in logs.items():
+        assert abs(got[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, got[k], v)
+    bad = []
+    _check_grads(m, {k: v for k, v in grads.items() if v is not None}, bad, f"{loss_fn}-beta{beta}")
     assert not bad, bad
 
 
