@@ -106,6 +106,8 @@ _SIGS = {
     "dof_test_gru_fwd": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int,
                                    C.c_int, C.c_int, _P]),
     "dof_test_gru_layer_fwd": (C.c_int, [_P, C.c_longlong, C.c_int, C.POINTER(C.c_void_p), _P, _P, _P, _P, _P, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, _P]),
+    "dof_test_gru_layer_bwd": (C.c_int, [C.POINTER(C.c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int,
                                          C.c_int, C.c_int, _P]),
     "dof_test_gru_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "dof_test_layernorm": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, C.c_longlong, C.c_int,

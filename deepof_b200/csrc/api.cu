@@ -10,6 +10,7 @@
 #include "tc_gemm.cuh"
 #include "gru.cuh"
 #include "gru_tc.cuh"
+#include "gru_bwd_tc.cuh"
 #include "layers.cuh"
 #include "loss.cuh"
 #include "loader.cuh"
@@ -210,12 +211,12 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
         w.len = bp.get<int>(S);
         for (int d = 0; d < 2; d++) w.Gi1[d] = bp.get<float>(ST * 3 * H1);
         w.H1 = bp.get<float>(ST * 2 * H1);
-        for (int d = 0; d < 2; d++) w.Gt1[d] = tr ? bp.get<float>(ST * 4 * H1) : nullptr;
+        for (int d = 0; d < 2; d++) w.Gt1[d] = tr ? bp.get<float>((size_t)round_up(w.S, 128) * T * 4 * H1) : nullptr;   // tiled layout: whole tiles
         w.mu1 = bp.get<float>(ST); w.rs1 = bp.get<float>(ST);
         w.Y1 = bp.get<float>(ST * 2 * H1);
         for (int d = 0; d < 2; d++) w.Gi2[d] = bp.get<float>(ST * 3 * H2);
         w.H2 = tr ? bp.get<float>(ST * 2 * H2) : nullptr;
-        for (int d = 0; d < 2; d++) w.Gt2[d] = tr ? bp.get<float>(ST * 4 * H2) : nullptr;
+        for (int d = 0; d < 2; d++) w.Gt2[d] = tr ? bp.get<float>((size_t)round_up(w.S, 128) * T * 4 * H2) : nullptr;
         w.Hn = bp.get<float>(S * 2 * H2);
         w.mu2 = bp.get<float>(S); w.rs2 = bp.get<float>(S);
         w.Y2 = bp.get<float>(S * 2 * H2);
@@ -256,12 +257,12 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
     h->lenD = bp.get<int>(Bz);
     for (int d = 0; d < 2; d++) h->GiD1[d] = bp.get<float>(Bz * 3 * D);
     h->HD1 = bp.get<float>(BT * 2 * D);
-    for (int d = 0; d < 2; d++) h->GtD1[d] = tr ? bp.get<float>(BT * 4 * D) : nullptr;
+    for (int d = 0; d < 2; d++) h->GtD1[d] = tr ? bp.get<float>((size_t)round_up(B, 128) * T * 4 * D) : nullptr;
     h->muD1 = bp.get<float>(BT); h->rsD1 = bp.get<float>(BT);
     h->YD1 = bp.get<float>(BT * 2 * D);
     for (int d = 0; d < 2; d++) h->GiD2[d] = bp.get<float>(BT * 6 * D);
     h->HD2 = bp.get<float>(BT * 4 * D);
-    for (int d = 0; d < 2; d++) h->GtD2[d] = tr ? bp.get<float>(BT * 8 * D) : nullptr;
+    for (int d = 0; d < 2; d++) h->GtD2[d] = tr ? bp.get<float>((size_t)round_up(B, 128) * T * 8 * D) : nullptr;
     h->muD2 = bp.get<float>(BT); h->rsD2 = bp.get<float>(BT);
     h->YD2 = bp.get<float>(BT * 4 * D);
     h->Cd = bp.get<float>(BT * 2 * D);
@@ -485,6 +486,7 @@ static int gru_layer_forward(const float* state, const GruP& g, const float* X, 
             a.Gt[d] = Gt ? Gt[d] : nullptr;
         }
         a.len = len; a.Hout = Hout; a.Hn = Hn; a.S = S; a.T = T; a.H = H; a.I = I;
+        a.gt_tiled = (Gt && gru_bwd_tc_eligible(H, I)) ? 1 : 0;     // the fused backward kernel reads tiled gates
         return launch_gru_fwd_tc(a, st);
     }
     const int M = x_st == 0 ? S : S * T;
@@ -683,6 +685,27 @@ static int gru_param_grads(dof_handle* h, const GruP& g, float* grad, const floa
     return DOF_OK;
 }
 
+// BPTT of one bidirectional GRU layer -> dG[dir] (and, on the fused path, the input gradient dX).  Returns through
+// *dx_done whether dX has been produced (otherwise gru_param_grads runs the input-gradient GEMM).
+static int gru_layer_backward(const float* state, const GruP& g, int S, int T, int I, int H, const int* len, const float* Hout,
+                              float* const Gt[2], const float* dOut, const float* dHn, float* const dG[2], float* dX,
+                              const float* dXmask, bool* dx_done, cudaStream_t st) {
+    *dx_done = false;
+    if (gru_bwd_tc_eligible(H, I)) {
+        GruBwdTcArgs b;
+        memset(&b, 0, sizeof(b));
+        for (int d = 0; d < 2; d++) { b.Whh[d] = state + g.w_hh[d]; b.Wih[d] = state + g.w_ih[d]; b.GtT[d] = Gt[d]; b.dG[d] = dG[d]; }
+        b.len = len; b.Hout = Hout; b.dOut = dOut; b.dHn = dHn; b.dX = dX; b.dXmask = dXmask; b.S = S; b.T = T; b.H = H; b.I = I;
+        if (dX) { DOF_CUDA(cudaMemsetAsync(dX, 0, (size_t)S * T * I * 4, st)); *dx_done = true; }
+        return launch_gru_bwd_tc(b, st);
+    }
+    GruBwdArgs b;
+    memset(&b, 0, sizeof(b));
+    for (int d = 0; d < 2; d++) { b.Whh[d] = state + g.w_hh[d]; b.Gt[d] = Gt[d]; b.dG[d] = dG[d]; }
+    b.len = len; b.Hout = Hout; b.dOut = dOut; b.dHn = dHn; b.S = S; b.T = T; b.H = H;
+    return launch_gru_bwd(b, st);
+}
+
 static int decoder_backward(dof_handle* h, const float* state, float* grad, const float* zin, int B, cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
@@ -700,18 +723,14 @@ static int decoder_backward(dof_handle* h, const float* state, float* grad, cons
     GemmArgs g1 = gemm_args(mv_conv5(h->dCd, 2 * D, T, -1), h->Wt, 10 * D, 0, nullptr, h->dYD2, 4 * D, M, 4 * D, 10 * D);
     DOF_TRY(launch_gemm_rows(&g1, 1, st));
     DOF_TRY(ln_bwd(h->dYD2, h->HD2, h->muD2, h->rsD2, state + L.dn2w, h->dHD2, grad + L.dn2w, grad + L.dn2b, M, 4 * D, 0, sm, st));
-    GruBwdArgs b;
-    memset(&b, 0, sizeof(b));
-    for (int d = 0; d < 2; d++) { b.Whh[d] = state + L.dg2.w_hh[d]; b.Gt[d] = h->GtD2[d]; b.dG[d] = h->dGD2[d]; }
-    b.len = h->lenD; b.Hout = h->HD2; b.dOut = h->dHD2; b.dHn = nullptr; b.S = B; b.T = T; b.H = 2 * D;
-    DOF_TRY(launch_gru_bwd(b, st));
+    bool dxd = false;
+    DOF_TRY(gru_layer_backward(state, L.dg2, B, T, 2 * D, 2 * D, h->lenD, h->HD2, h->GtD2, h->dHD2, nullptr, h->dGD2, h->dYD1, nullptr, &dxd, st));
     DOF_TRY(gru_param_grads(h, L.dg2, grad, state, h->dGD2, mv_plain(h->YD1, 2 * D), M, h->dGD2, h->HD2, M, T, 2 * D, 2 * D,
-                            h->dYD1, nullptr, st));
+                            dxd ? nullptr : h->dYD1, nullptr, st));
     DOF_TRY(ln_bwd(h->dYD1, h->HD1, h->muD1, h->rsD1, state + L.dn1w, h->dHD1, grad + L.dn1w, grad + L.dn1b, M, 2 * D, 0, sm, st));
-    memset(&b, 0, sizeof(b));
-    for (int d = 0; d < 2; d++) { b.Whh[d] = state + L.dg1.w_hh[d]; b.Gt[d] = h->GtD1[d]; b.dG[d] = h->dGD1[d]; }
-    b.len = h->lenD; b.Hout = h->HD1; b.dOut = h->dHD1; b.dHn = nullptr; b.S = B; b.T = T; b.H = D;
-    DOF_TRY(launch_gru_bwd(b, st));
+    // the decoder's first GRU sees the SAME input (z) at every step: its input gradient is the sum over time and
+    // stays on the GEMM path below (dGs), only dG comes from the fused kernel
+    DOF_TRY(gru_layer_backward(state, L.dg1, B, T, D, D, h->lenD, h->HD1, h->GtD1, h->dHD1, nullptr, h->dGD1, nullptr, nullptr, &dxd, st));
     for (int d = 0; d < 2; d++) {
         { ProfScope ps("sum_over_t", st);
         sum_over_t_kernel<<<cdiv((long long)B * 4 * D, 256), 256, 0, st>>>(h->dGD1[d], h->dGs[d], B, T, 4 * D, 0); }
@@ -734,18 +753,13 @@ static int enc_block_backward(dof_handle* h, int bi, const float* state, float* 
         DOF_TRY(launch_gemm_rows(&gp, 1, st));
     }
     DOF_TRY(ln_bwd(w.dY2, w.Hn, w.mu2, w.rs2, state + P.n2w, w.dHn, grad + P.n2w, grad + P.n2b, S, 2 * H2, 0, sm, st));
-    GruBwdArgs b;
-    memset(&b, 0, sizeof(b));
-    for (int d = 0; d < 2; d++) { b.Whh[d] = state + P.g2.w_hh[d]; b.Gt[d] = w.Gt2[d]; b.dG[d] = w.dG2[d]; }
-    b.len = w.len; b.Hout = w.H2; b.dOut = nullptr; b.dHn = w.dHn; b.S = S; b.T = T; b.H = H2;
-    DOF_TRY(launch_gru_bwd(b, st));
-    DOF_TRY(gru_param_grads(h, P.g2, grad, state, w.dG2, mv_plain(w.Y1, 2 * H1), M, w.dG2, w.H2, M, T, 2 * H1, H2, w.dY1, nullptr, st));
+    bool dxd = false;
+    DOF_TRY(gru_layer_backward(state, P.g2, S, T, 2 * H1, H2, w.len, w.H2, w.Gt2, nullptr, w.dHn, w.dG2, w.dY1, nullptr, &dxd, st));
+    DOF_TRY(gru_param_grads(h, P.g2, grad, state, w.dG2, mv_plain(w.Y1, 2 * H1), M, w.dG2, w.H2, M, T, 2 * H1, H2,
+                            dxd ? nullptr : w.dY1, nullptr, st));
     DOF_TRY(ln_bwd(w.dY1, w.H1, w.mu1, w.rs1, state + P.n1w, w.dH1, grad + P.n1w, grad + P.n1b, M, 2 * H1, 0, sm, st));
-    memset(&b, 0, sizeof(b));
-    for (int d = 0; d < 2; d++) { b.Whh[d] = state + P.g1.w_hh[d]; b.Gt[d] = w.Gt1[d]; b.dG[d] = w.dG1[d]; }
-    b.len = w.len; b.Hout = w.H1; b.dOut = w.dH1; b.dHn = nullptr; b.S = S; b.T = T; b.H = H1;
-    DOF_TRY(launch_gru_bwd(b, st));
-    DOF_TRY(gru_param_grads(h, P.g1, grad, state, w.dG1, mv_plain(w.Cv, C1), M, w.dG1, w.H1, M, T, C1, H1, w.dCv, w.Cv, st));
+    DOF_TRY(gru_layer_backward(state, P.g1, S, T, C1, H1, w.len, w.H1, w.Gt1, w.dH1, nullptr, w.dG1, w.dCv, w.Cv, &dxd, st));
+    DOF_TRY(gru_param_grads(h, P.g1, grad, state, w.dG1, mv_plain(w.Cv, C1), M, w.dG1, w.H1, M, T, C1, H1, dxd ? nullptr : w.dCv, w.Cv, st));
     if (C1 * w.Fin <= 256) {
         ConvWgradArgs ca;
         ca.dCv = w.dCv; ca.Xs = w.Xs; ca.dW = grad + P.conv; ca.S = S; ca.T = T; ca.C = C1; ca.F = w.Fin;
@@ -1312,14 +1326,29 @@ int dof_test_gru_fwd(const float* gi_f, const float* gi_b, long long gi_ss, int 
 
 // fused tcgen05 GRU layer (input projection + recurrence + gates); fails if the shape is not eligible
 int dof_test_gru_layer_fwd(const float* X, long long x_ss, int x_st, const float* const* w8, const int* len, float* hout,
-                           float* gt_f, float* gt_b, float* hn, int S, int T, int H, int I, void* stream) {
+                           float* gt_f, float* gt_b, float* hn, int S, int T, int H, int I, int gt_tiled, void* stream) {
     if (!gru_tc_eligible(S, H, I)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "shape S=%d H=%d I=%d is not eligible for the fused GRU kernel", S, H, I);
     GruTcArgs a;
     memset(&a, 0, sizeof(a));
     a.X = X; a.x_ss = x_ss; a.x_st = x_st;
     for (int d = 0; d < 2; d++) { a.Wih[d] = w8[d]; a.Whh[d] = w8[2 + d]; a.bih[d] = w8[4 + d]; a.bhh[d] = w8[6 + d]; }
     a.len = len; a.Hout = hout; a.Gt[0] = gt_f; a.Gt[1] = gt_b; a.Hn = hn; a.S = S; a.T = T; a.H = H; a.I = I;
+    a.gt_tiled = gt_tiled;
     return launch_gru_fwd_tc(a, (cudaStream_t)stream);
+}
+
+// fused tcgen05 BPTT (gate gradients + recurrent matmul + input gradient); gates in the tiled layout
+int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* hout, const float* gtT_f, const float* gtT_b,
+                           const float* dout, const float* dhn, float* dg_f, float* dg_b, float* dx, const float* dxmask,
+                           int S, int T, int H, int I, void* stream) {
+    if (!gru_bwd_tc_eligible(H, I)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "shape H=%d I=%d is not eligible for the fused GRU backward kernel", H, I);
+    GruBwdTcArgs b;
+    memset(&b, 0, sizeof(b));
+    for (int d = 0; d < 2; d++) { b.Wih[d] = w8[d]; b.Whh[d] = w8[2 + d]; }
+    b.GtT[0] = gtT_f; b.GtT[1] = gtT_b; b.dG[0] = dg_f; b.dG[1] = dg_b;
+    b.len = len; b.Hout = hout; b.dOut = dout; b.dHn = dhn; b.dX = dx; b.dXmask = dxmask; b.S = S; b.T = T; b.H = H; b.I = I;
+    if (dx) DOF_CUDA(cudaMemsetAsync(dx, 0, (size_t)S * T * I * 4, (cudaStream_t)stream));
+    return launch_gru_bwd_tc(b, (cudaStream_t)stream);
 }
 
 int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout, const float* gt_f,

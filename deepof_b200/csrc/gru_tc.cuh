@@ -29,6 +29,8 @@ struct GruTcArgs {
     float* Gt[2];        // [S,T,4H] = r|z|n|hn per direction, or null
     float* Hn;           // [S,2H] final states [fwd|bwd] or null
     int S, T, H, I;
+    int gt_tiled;        // 1: Gt is written in the tiled layout the fused backward kernel reads (gru_bwd_tc.cuh):
+                         //    Gt[((tile*T + t) * H + c) * 128 + row][4 floats], c = 16-byte chunk of r|z|n|hn
 };
 
 struct GruTcGeom { int wih_lbo, whh_lbo, tmem_cols, gs, os, xst; uint32_t wih_bytes, whh_bytes, x_bytes, h_bytes; };
@@ -294,7 +296,25 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
         for (int step = 0; step < T; step++) {
             const int t = dir ? (T - 1 - step) : step;
             mbar_wait(bar_sfull, (uint32_t)(step & 1));
-            if (want_g) {
+            if (want_g && a.gt_tiled) {
+                // chunk-major tiles: one warp instruction = one 16-byte chunk of 32 consecutive rows (512 B contiguous)
+                float* gtile = Gt + ((size_t)blockIdx.x * T + t) * H * 512;
+                for (int q0 = sw; q0 < 4 * H; q0 += GTC_NSTORE * CH) {
+                    float4 v[CH];
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const int q = q0 + k * GTC_NSTORE;
+                        const int c = q >> 2, r = (q & 3) * 32 + lane;
+                        if (q < 4 * H) v[k] = *reinterpret_cast<const float4*>(Gs + (size_t)r * geo.gs + c * 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const int q = q0 + k * GTC_NSTORE;
+                        const int c = q >> 2, r = (q & 3) * 32 + lane;
+                        if (q < 4 * H && t < lens_s[r]) *reinterpret_cast<float4*>(gtile + ((size_t)c * 128 + r) * 4) = v[k];
+                    }
+                }
+            } else if (want_g) {
                 for (int c = sw; c < NG; c += GTC_NSTORE * CH) {
                     float4 v[CH];
 #pragma unroll

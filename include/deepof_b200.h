@@ -269,7 +269,13 @@ int dof_test_gru_fwd(const float* gi_f, const float* gi_b, long long gi_ss, int 
                      float* hout, float* gt_f, float* gt_b, float* hn, int S, int T, int H, void* stream);
 /* w8 (HOST array of 8 DEVICE pointers): W_ih fwd, W_ih bwd, W_hh fwd, W_hh bwd, b_ih fwd, b_ih bwd, b_hh fwd, b_hh bwd */
 int dof_test_gru_layer_fwd(const float* X, long long x_ss, int x_st, const float* const* w8, const int* len,
-                           float* hout, float* gt_f, float* gt_b, float* hn, int S, int T, int H, int I, void* stream);
+                           float* hout, float* gt_f, float* gt_b, float* hn, int S, int T, int H, int I, int gt_tiled,
+                           void* stream);
+/* fused BPTT: gates in the tiled layout written by dof_test_gru_layer_fwd(gt_tiled = 1) (buffers of
+ * ceil(S/128)*128*T*4H floats); dx [S,T,I] may be NULL, dxmask [S,T,I] may be NULL */
+int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* hout, const float* gtT_f,
+                           const float* gtT_b, const float* dout, const float* dhn, float* dg_f, float* dg_b, float* dx,
+                           const float* dxmask, int S, int T, int H, int I, void* stream);
 int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout,
                      const float* gt_f, const float* gt_b, const float* dout, const float* dhn,
                      float* dg_f, float* dg_b, int S, int T, int H, void* stream);

@@ -261,7 +261,7 @@ def test_gru_fused_tc_layer(L, S_, T, I, H, packed, repeat):
              "bias_hh_l0", "bias_hh_l0_reverse"]
     w8 = (C.c_void_p * 8)(*[prm[n].data_ptr() for n in names])
     ran = _ran(L, lambda: check_rc(L, L.dof_test_gru_layer_fwd(P(X), 0 if False else (I if repeat else T * I), 0 if repeat else I, w8,
-                                                               P(len_t), P(hout), P(gt[0]), P(gt[1]), P(hn), S_, T, H, I, S())))
+                                                               P(len_t), P(hout), P(gt[0]), P(gt[1]), P(hn), S_, T, H, I, 0, S())))
     assert any(n.startswith("gru_fwd_tc") for n in ran), ran
     print("fused gru", (S_, T, I, H), rel(hout, out_ref), rel(hn, hn_ref))
     assert rel(hout, out_ref) < 5e-6 and rel(hn, hn_ref) < 5e-6
@@ -276,6 +276,58 @@ def test_gru_fused_tc_layer(L, S_, T, I, H, packed, repeat):
     assert rc == 0, L.dof_last_error()
     for d in range(2):
         assert rel(gt[d], gt2[d]) < 1e-5, ("gates", d, rel(gt[d], gt2[d]))
+
+
+@pytest.mark.parametrize("S_,T,I,H,packed,final_only,mask", [(300, 25, 32, 32, False, False, True), (1000, 25, 64, 16, True, True, False),
+                                                              (257, 7, 32, 32, True, False, False), (130, 24, 16, 16, True, False, False)])
+def test_gru_fused_tc_backward(L, S_, T, I, H, packed, final_only, mask):
+    """Fused tcgen05 BPTT (dG + dX) vs the SIMT BPTT kernel fed by the same forward, and dX vs dGi . W_ih in fp64."""
+    dev = "cuda"
+    X = rnd(S_, T, I, seed=60)
+    k = 1.0 / H ** 0.5
+    names = ["weight_ih_l0", "weight_ih_l0_reverse", "weight_hh_l0", "weight_hh_l0_reverse", "bias_ih_l0", "bias_ih_l0_reverse",
+             "bias_hh_l0", "bias_hh_l0_reverse"]
+    prm = {n: rnd(*((3 * H, I) if "weight_ih" in n else (3 * H, H) if "weight_hh" in n else (3 * H,)), seed=61 + i) * k for i, n in enumerate(names)}
+    w8 = (C.c_void_p * 8)(*[prm[n].data_ptr() for n in names])
+    if packed:
+        g = torch.Generator().manual_seed(2)
+        lens = torch.randint(0, T + 1, (S_,), generator=g)
+        lens[0], lens[1], lens[2] = 0, 1, T
+        len_t = lens.to(dev).int()
+    else:
+        len_t = torch.full((S_,), T, dtype=torch.int32, device=dev)
+    Sp = (S_ + 127) // 128 * 128
+    hout = torch.zeros(S_, T, 2 * H, device=dev)
+    hn = torch.zeros(S_, 2 * H, device=dev)
+    gt_rm = [torch.zeros(S_, T, 4 * H, device=dev) for _ in range(2)]
+    gt_ti = [torch.zeros(Sp * T * 4 * H, device=dev) for _ in range(2)]
+    for tiled, gt in ((0, gt_rm), (1, gt_ti)):
+        check_rc(L, L.dof_test_gru_layer_fwd(P(X), T * I, I, w8, P(len_t), P(hout), P(gt[0]), P(gt[1]), P(hn), S_, T, H, I, tiled, S()))
+    dout = None if final_only else rnd(S_, T, 2 * H, seed=70)
+    dhn = rnd(S_, 2 * H, seed=71) if final_only else None
+    # SIMT reference path
+    dg_ref = [torch.full((S_, T, 4 * H), 3.0, device=dev) for _ in range(2)]
+    rc = L.dof_test_gru_bwd(P(prm["weight_hh_l0"]), P(prm["weight_hh_l0_reverse"]), P(len_t), P(hout), P(gt_rm[0]), P(gt_rm[1]),
+                            P(dout), P(dhn), P(dg_ref[0]), P(dg_ref[1]), S_, T, H, S())
+    assert rc == 0, L.dof_last_error()
+    # fused path
+    dg = [torch.full((S_, T, 4 * H), 5.0, device=dev) for _ in range(2)]
+    dx = torch.full((S_, T, I), 9.0, device=dev)
+    mk = (rnd(S_, T, I, seed=72) if mask else None)
+    ran = _ran(L, lambda: check_rc(L, L.dof_test_gru_layer_bwd(w8, P(len_t), P(hout), P(gt_ti[0]), P(gt_ti[1]), P(dout), P(dhn), P(dg[0]),
+                                                               P(dg[1]), P(dx), P(mk), S_, T, H, I, S())))
+    assert any(n.startswith("gru_bwd_tc") for n in ran), ran
+    for d in range(2):
+        print("fused bwd dG", (S_, T, I, H), d, rel(dg[d], dg_ref[d]))
+        assert rel(dg[d], dg_ref[d]) < 1e-5, (d, rel(dg[d], dg_ref[d]))
+    dx_ref = torch.zeros(S_, T, I, device=dev, dtype=torch.float64)
+    for di, sfx in enumerate(("", "_reverse")):
+        G = dg_ref[di].double()
+        dx_ref += torch.cat([G[..., :2 * H], G[..., 3 * H:]], -1) @ prm["weight_ih_l0" + sfx].double()
+    if mask:
+        dx_ref = dx_ref * (mk > 0)
+    print("fused bwd dX", rel(dx, dx_ref))
+    assert rel(dx, dx_ref) < 1e-5
 
 
 def check_rc(L, rc):

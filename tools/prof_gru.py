@@ -30,7 +30,7 @@ for it in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = L.dof_test_gru_layer_fwd(P(X), T * I, I, w8, None, None if MODE == "nostore" else P(hout),
-                                  P(gt[0]) if MODE == "all" else None, P(gt[1]) if MODE == "all" else None, P(hn), S_, T, H, I, st)
+                                  P(gt[0]) if MODE == "all" else None, P(gt[1]) if MODE == "all" else None, P(hn), S_, T, H, I, 0, st)
     e1.record()
     torch.cuda.synchronize()
     assert rc == 0, L.dof_last_error()
