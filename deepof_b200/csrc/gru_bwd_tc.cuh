@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
     unsigned char* A_hi = Wih_lo + geo.wih_bytes;                     // dG tile [128][4H], H chunks of 4 floats
     unsigned char* A_lo = A_hi + geo.a_bytes;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(A_lo + geo.a_bytes);
-    // mbar: [0] a_full (256 gate threads) [1] dh_full (commit) [2] dx_full (commit) [3] st_done (128 store threads)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4);
+    // mbar: [0] a_full (256 gate threads) [1] dh_full (commit) [2] dx_full (commit) [3] st_done (128 store threads: dG rows
+    // copied out of the operand tile) [4] dx_read (128 store threads: acc_dx read out of TMEM)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 6);
     int* lens_s = reinterpret_cast<int*>(tmem_slot + 4);              // [128]
     const int s0 = blockIdx.x * 128;
     const bool want_dx = a.dX != nullptr;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), geo.tmem_cols);
     if (tid == 32) {
         mbar_init(smem_u32(mbar + 0), 256); mbar_init(smem_u32(mbar + 1), 1);
-        mbar_init(smem_u32(mbar + 2), 1); mbar_init(smem_u32(mbar + 3), 128);
+        mbar_init(smem_u32(mbar + 2), 1); mbar_init(smem_u32(mbar + 3), 128); mbar_init(smem_u32(mbar + 4), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t bar_afull = smem_u32(mbar), bar_dh = smem_u32(mbar + 1), bar_dx = smem_u32(mbar + 2), bar_st = smem_u32(mbar + 3);
+    const uint32_t bar_afull = smem_u32(mbar), bar_dh = smem_u32(mbar + 1), bar_dx = smem_u32(mbar + 2), bar_st = smem_u32(mbar + 3),
+                   bar_dxr = smem_u32(mbar + 4);
     const uint32_t acc_dh = tmem, acc_dx = tmem + H;
 
     if (warp >= 4 && warp < GBT_MMA_WARP) {
@@ -121,18 +123,24 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
             const int t = dir ? step : (T - 1 - step);
             const int tp = dir ? t + 1 : t - 1;
             const bool valid = t < len;
-            // recurrent term of the previous step: dh = part + dG_{prev} . W_hh
-            float dh[HC];
-            if (step > 0) {
-                mbar_wait(bar_dh, (uint32_t)((step - 1) & 1));
-                tc_fence_after();
-                float v[HC];
-                tmem_ld_hc<HC>(acc_dh + ((uint32_t)(ew * 32) << 16) + (uint32_t)j0, v);
+            // all global loads of this step first (they do not depend on dh): their latency hides behind the MMAs of
+            // the previous step
+            const float* gt = GtT + ((tile_base + t) * H) * 512 + row * 4;      // chunk c at gt + c*512
+            float4 r4[HC / 4], z4[HC / 4], n4[HC / 4], q4[HC / 4], hp4[HC / 4], do4[HC / 4];
 #pragma unroll
-                for (int j = 0; j < HC; j++) dh[j] = part[j] + v[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < HC; j++) dh[j] = part[j];
+            for (int q = 0; q < HC / 4; q++) {
+                const int cq = (j0 >> 2) + q;
+                hp4[q] = make_float4(0.f, 0.f, 0.f, 0.f); do4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {
+                    r4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)cq * 512));
+                    z4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(H / 4 + cq) * 512));
+                    n4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(2 * (H / 4) + cq) * 512));
+                    q4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(3 * (H / 4) + cq) * 512));
+                    if (tp >= 0 && tp < len) hp4[q] = __ldg(reinterpret_cast<const float4*>(a.Hout + ((size_t)s * T + tp) * 2 * H + dir * H + j0 + q * 4));
+                    if (a.dOut) do4[q] = __ldg(reinterpret_cast<const float4*>(a.dOut + ((size_t)s * T + t) * 2 * H + dir * H + j0 + q * 4));
+                } else {
+                    r4[q] = z4[q] = n4[q] = q4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             // pull the next step's saved gates towards L2 while this step computes
             if (step + 1 < T) {
@@ -146,27 +154,32 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)(q * (H / 4) + qq) * 512));
                 }
             }
+            // recurrent term of the previous step: dh = part + dG_{prev} . W_hh
+            float dh[HC];
+            if (step > 0) {
+                mbar_wait(bar_dh, (uint32_t)((step - 1) & 1));
+                tc_fence_after();
+                float v[HC];
+                tmem_ld_hc<HC>(acc_dh + ((uint32_t)(ew * 32) << 16) + (uint32_t)j0, v);
+#pragma unroll
+                for (int j = 0; j < HC; j++) dh[j] = part[j] + v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < HC; j++) dh[j] = part[j];
+            }
             // the operand tile is free again once the MMAs of the previous step retired and its rows were stored
             if (step > 0) {
                 if (want_dx) mbar_wait(bar_dx, (uint32_t)((step - 1) & 1));
                 mbar_wait(bar_st, (uint32_t)((step - 1) & 1));
             }
-            const float* gt = GtT + ((tile_base + t) * H) * 512 + row * 4;      // chunk c at gt + c*512
 #pragma unroll
             for (int q = 0; q < HC / 4; q++) {
                 const int cq = (j0 >> 2) + q;                                 // chunk inside a gate block
                 float o_r[4] = {0.f, 0.f, 0.f, 0.f}, o_z[4] = {0.f, 0.f, 0.f, 0.f}, o_h[4] = {0.f, 0.f, 0.f, 0.f}, o_n[4] = {0.f, 0.f, 0.f, 0.f};
                 if (valid) {
-                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(gt + (size_t)cq * 512));
-                    const float4 z4 = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(H / 4 + cq) * 512));
-                    const float4 n4 = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(2 * (H / 4) + cq) * 512));
-                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(3 * (H / 4) + cq) * 512));
-                    float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f), do4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (tp >= 0 && tp < len) hp4 = __ldg(reinterpret_cast<const float4*>(a.Hout + ((size_t)s * T + tp) * 2 * H + dir * H + j0 + q * 4));
-                    if (a.dOut) do4 = __ldg(reinterpret_cast<const float4*>(a.dOut + ((size_t)s * T + t) * 2 * H + dir * H + j0 + q * 4));
-                    const float r[4] = {r4.x, r4.y, r4.z, r4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w};
-                    const float n[4] = {n4.x, n4.y, n4.z, n4.w}, hn[4] = {q4.x, q4.y, q4.z, q4.w};
-                    const float hp[4] = {hp4.x, hp4.y, hp4.z, hp4.w}, dov[4] = {do4.x, do4.y, do4.z, do4.w};
+                    const float r[4] = {r4[q].x, r4[q].y, r4[q].z, r4[q].w}, z[4] = {z4[q].x, z4[q].y, z4[q].z, z4[q].w};
+                    const float n[4] = {n4[q].x, n4[q].y, n4[q].z, n4[q].w}, hn[4] = {q4[q].x, q4[q].y, q4[q].z, q4[q].w};
+                    const float hp[4] = {hp4[q].x, hp4[q].y, hp4[q].z, hp4[q].w}, dov[4] = {do4[q].x, do4[q].y, do4[q].z, do4[q].w};
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const float d = dh[q * 4 + e] + dov[e];
@@ -218,6 +231,7 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
                 }
                 umma_commit(bar_dh);
                 if (want_dx) {
+                    if (step > 0) { mbar_wait(bar_dxr, (uint32_t)((step - 1) & 1)); tc_fence_after(); }   // acc_dx of the previous step read out
                     // dX part: K = 3H = tile chunks [0, 2H/4) (da_r, da_z) and [3H/4, H) (da_n) against W_ih rows r, z, n
                     for (int ks = 0; ks < (3 * H) >> 3; ks++) {
                         const int ca = ks < (2 * H) >> 3 ? 2 * ks : 2 * ks + (H >> 2);       // first A chunk of this K step
@@ -249,6 +263,7 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
                     *reinterpret_cast<float4*>(dG + ((size_t)(s0 + r) * T + t) * 4 * H + c * 4) =
                         make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
             }
+            mbar_arrive(bar_st);                          // the operand tile may be refilled (its MMAs are tracked by dh / dx_full)
             if (want_dx) {
                 mbar_wait(bar_dx, (uint32_t)(step & 1));
                 tc_fence_after();
@@ -274,8 +289,8 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
                     }
                 }
                 tc_fence_before();
+                mbar_arrive(bar_dxr);
             }
-            mbar_arrive(bar_st);
         }
     }
     tc_fence_before();
@@ -290,7 +305,7 @@ static bool gru_bwd_tc_geom(int H, int I, bool want_dx, GruBwdTcGeom& g, size_t&
     g.wih_bytes = want_dx ? (uint32_t)(3 * H / 4) * g.wih_lbo : 0;
     g.a_bytes = (uint32_t)H * TC_A_LBO;                     // 4H / 4 = H chunks
     g.tmem_cols = tmem_cols_for(H + (want_dx ? I : 0));
-    smem = 2 * (size_t)g.whh_bytes + 2 * (size_t)g.wih_bytes + 2 * (size_t)g.a_bytes + 4 * 8 + 16 + 128 * 4 + 128;
+    smem = 2 * (size_t)g.whh_bytes + 2 * (size_t)g.wih_bytes + 2 * (size_t)g.a_bytes + 6 * 8 + 16 + 128 * 4 + 128;
     return smem <= 227 * 1024;
 }
 
