@@ -56,7 +56,7 @@ __device__ __forceinline__ void tmem_ld_hc(uint32_t taddr, float (&v)[HC]) {
     if constexpr (HC == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
 }
 
-template <int H, int KQM>
+template <int H, int KQM, bool TILED>
 __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs a, const GruTcGeom geo) {
     constexpr int HC = H / 2;                                         // hidden units per gate thread
     extern __shared__ __align__(128) unsigned char gsm[];
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
         for (int step = 0; step < T; step++) {
             const int t = dir ? (T - 1 - step) : step;
             mbar_wait(bar_sfull, (uint32_t)(step & 1));
-            if (want_g && a.gt_tiled) {
+            if (want_g && TILED) {
                 // chunk-major tiles: one warp instruction = one 16-byte chunk of 32 consecutive rows (512 B contiguous)
                 float* gtile = Gt + ((size_t)blockIdx.x * T + t) * H * 512;
                 for (int q0 = sw; q0 < 4 * H; q0 += GTC_NSTORE * CH) {
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                         if (q < 4 * H && t < lens_s[r]) *reinterpret_cast<float4*>(gtile + ((size_t)c * 128 + r) * 4) = v[k];
                     }
                 }
-            } else if (want_g) {
+            } else if (want_g && !TILED) {
                 for (int c = sw; c < NG; c += GTC_NSTORE * CH) {
                     float4 v[CH];
 #pragma unroll
@@ -385,17 +385,21 @@ static bool gru_tc_geom(int H, int I, GruTcGeom& g, size_t& smem) {
     return false;
 }
 
-template <int H, int KQM>
-static int gru_tc_launch_t(const GruTcArgs& a, const GruTcGeom& geo, size_t smem, cudaStream_t st) {
+template <int H, int KQM, bool TILED>
+static int gru_tc_launch_tt(const GruTcArgs& a, const GruTcGeom& geo, size_t smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        DOF_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<H, KQM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DOF_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<H, KQM, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     dim3 grid(cdiv(a.S, 128), 2);
-    gru_fwd_tc_kernel<H, KQM><<<grid, GTC_THREADS, smem, st>>>(a, geo);
+    gru_fwd_tc_kernel<H, KQM, TILED><<<grid, GTC_THREADS, smem, st>>>(a, geo);
     DOF_LAUNCH_CHECK();
     return DOF_OK;
+}
+template <int H, int KQM>
+static int gru_tc_launch_t(const GruTcArgs& a, const GruTcGeom& geo, size_t smem, cudaStream_t st) {
+    return a.gt_tiled ? gru_tc_launch_tt<H, KQM, true>(a, geo, smem, st) : gru_tc_launch_tt<H, KQM, false>(a, geo, smem, st);
 }
 
 // one bidirectional GRU layer, both directions (blockIdx.y)

@@ -11,6 +11,7 @@ from deepof_b200 import _lib
 H, I = int(sys.argv[1]), int(sys.argv[2])
 S_ = int(sys.argv[3]) if len(sys.argv) > 3 else 57344
 MODE = sys.argv[4] if len(sys.argv) > 4 else "all"      # all | nogt | nostore
+TILED = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 T = 25
 L = _lib.lib()
 dev = "cuda"
@@ -30,8 +31,8 @@ for it in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = L.dof_test_gru_layer_fwd(P(X), T * I, I, w8, None, None if MODE == "nostore" else P(hout),
-                                  P(gt[0]) if MODE == "all" else None, P(gt[1]) if MODE == "all" else None, P(hn), S_, T, H, I, 0, st)
+                                  P(gt[0]) if MODE == "all" else None, P(gt[1]) if MODE == "all" else None, P(hn), S_, T, H, I, TILED, st)
     e1.record()
     torch.cuda.synchronize()
     assert rc == 0, L.dof_last_error()
-    print("fused gru layer H=%d I=%d S=%d mode=%s: %.3f ms" % (H, I, S_, MODE, e0.elapsed_time(e1)))
+    print("fused gru layer H=%d I=%d S=%d mode=%s tiled=%d: %.3f ms" % (H, I, S_, MODE, TILED, e0.elapsed_time(e1)))
