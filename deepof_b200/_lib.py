@@ -97,6 +97,7 @@ _SIGS = {
     "dof_debug_tensor": (_P, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "dof_launch_count": (C.c_longlong, []),
     "dof_set_tensor_cores": (C.c_int, [C.c_int]),
+    "dof_set_concurrency": (C.c_int, [C.c_int]),
     "dof_profile_begin": (C.c_int, []),
     "dof_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
     "dof_test_gemm_rows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P,

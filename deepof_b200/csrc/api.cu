@@ -190,8 +190,26 @@ struct dof_handle {
     // contrastive
     float *zn, *nrm, *lse; double* nstats;
     int lastB;
+    // the node and the edge recurrent blocks are independent until CensNet: the edge block runs on a second stream
+    // so that its kernels fill the SMs the node block's last wave leaves idle (896 CTAs on 148 SMs)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::map<std::string, std::pair<const void*, int64_t>> dbg;
 };
+
+static bool g_concurrent = true;
+
+template <typename F>
+static int fork_join_blocks(dof_handle* h, cudaStream_t st, F fn) {
+    if (!h->aux || !g_concurrent) { DOF_TRY(fn(0, st)); return fn(1, st); }
+    DOF_CUDA(cudaEventRecord(h->ev_fork, st));
+    DOF_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    int r0 = fn(0, st);
+    int r1 = fn(1, h->aux);
+    DOF_CUDA(cudaEventRecord(h->ev_join, h->aux));
+    DOF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    return r0 != DOF_OK ? r0 : r1;
+}
 
 static void plan_workspace(dof_handle* h, Bump& bp) {
     const dof_config& c = h->cfg;
@@ -420,11 +438,25 @@ int dof_create(const dof_config* cfg, int device, int max_batch, int training, v
         ce = cudaMemcpy(h->blk[b].gidx, gi.data(), gi.size() * sizeof(int), cudaMemcpyHostToDevice);
     }
     if (ce != cudaSuccess) { delete h; DOF_FAIL(DOF_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(ce)); }
+    const char* ss = getenv("DOF_SINGLE_STREAM");
+    if (!(ss && ss[0] == '1')) {
+        if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            delete h;
+            DOF_FAIL(DOF_ERR_CUDA, "could not create the auxiliary stream");
+        }
+    }
     *out = h;
     return DOF_OK;
 }
 
 int dof_destroy(dof_handle* h) {
+    if (h) {
+        if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
+        if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+        if (h->ev_join) cudaEventDestroy(h->ev_join);
+    }
     delete h;
     return DOF_OK;
 }
@@ -547,8 +579,7 @@ static int encoder_forward(dof_handle* h, const float* state, const float* x, co
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int N = c.N, E = c.E, D = c.D;
-    DOF_TRY(enc_block_forward(h, 0, state, x, B, train, st));
-    DOF_TRY(enc_block_forward(h, 1, state, a, B, train, st));
+    DOF_TRY(fork_join_blocks(h, st, [&](int b, cudaStream_t s) { return enc_block_forward(h, b, state, b == 0 ? x : a, B, train, s); }));
     CensArgs ca = cens_args(h, state, B);
     size_t smem = cens_smem_floats(N, E, 2 * D) * 4;
     if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "graph too large for the CensNet kernel (%zu B smem)", smem);
@@ -825,8 +856,7 @@ static int encoder_backward(dof_handle* h, const float* state, float* grad, int 
     { ProfScope ps("cens_bwd", st);
     cens_bwd_kernel<<<B, 128, smem, st>>>(ca); }
     DOF_LAUNCH_CHECK();
-    DOF_TRY(enc_block_backward(h, 0, state, grad, B, st));
-    DOF_TRY(enc_block_backward(h, 1, state, grad, B, st));
+    DOF_TRY(fork_join_blocks(h, st, [&](int b, cudaStream_t s) { return enc_block_backward(h, b, state, grad, B, s); }));
     return DOF_OK;
 }
 
@@ -1155,6 +1185,14 @@ int dof_set_tensor_cores(int enable) {
     tc_enabled();
     int old = g_tc_enabled ? 1 : 0;
     g_tc_enabled = enable != 0;
+    return old;
+}
+
+// 1 (default): the node and edge recurrent blocks of the encoder run concurrently on two streams; 0: one stream
+// (per-kernel event timing is only meaningful when kernels do not overlap).  Returns the previous setting.
+int dof_set_concurrency(int enable) {
+    int old = g_concurrent ? 1 : 0;
+    g_concurrent = enable != 0;
     return old;
 }
 

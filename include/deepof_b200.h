@@ -254,6 +254,11 @@ long long dof_launch_count(void);
 /* 1 (default): GEMMs run on tcgen05 tensor cores (3xTF32, fp32-class accuracy) where eligible;
  * 0: fp32 SIMT kernels only.  Returns the previous setting.  Env DOF_DISABLE_TC=1 sets 0. */
 int dof_set_tensor_cores(int enable);
+/* 1 (default): the two independent recurrent blocks of the encoder (nodes, edges) run concurrently on the caller's
+ * stream and a library-owned auxiliary stream (fork / join with events, nothing synchronises the host); 0: everything
+ * on the caller's stream.  Env DOF_SINGLE_STREAM=1 disables the auxiliary stream at dof_create.  Returns the previous
+ * setting. */
+int dof_set_concurrency(int enable);
 int dof_profile_begin(void);
 int dof_profile_end(char* out, size_t cap);
 
