@@ -89,7 +89,8 @@ _SIGS = {
     "dof_vqvae_forward_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "dof_vqvae_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P, _P]),
     "dof_contrastive_views": (C.c_int, [C.POINTER(DofViewsCfg), _P, C.c_int, _P, _P, _P]),
-    "dof_contrastive_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
+    "dof_contrastive_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P,
+                                            _P]),
     "dof_loader_num_windows": (C.c_longlong, [C.c_longlong, C.c_int, C.c_int]),
     "dof_load_windows": (C.c_int, [C.POINTER(DofLoaderCfg), _P, C.c_longlong, C.c_longlong, C.c_int, _P, _P, _P]),
     "dof_loader_pair_length": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, _P, _P]),

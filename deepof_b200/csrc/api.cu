@@ -1114,13 +1114,14 @@ extern "C" {
 // step_contrastive_distill forward + backward without teacher (training.py:527-545, 159-163) on the two views
 // produced by dof_contrastive_views: x2 / a2 rows 0..B-1 = main view, B..2B-1 = augmented view.
 int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
-                              int loss_kind, float temperature, float tau_plus, float beta, float* logs, float* z_out,
-                              void* stream) {
+                              int loss_kind, int sim_kind, float temperature, float tau_plus, float beta, float* logs,
+                              float* z_out, void* stream) {
     DOF_TRY(check_batch(h, 2 * B));
     const dof_config& c = h->cfg;
     if (c.model != DOF_MODEL_CONTRASTIVE) DOF_FAIL(DOF_ERR_ARG, "handle is not a contrastive model");
     if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
     if (!state || !grad || !x2 || !a2 || !logs || !(temperature > 0.f)) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    if (sim_kind < 0 || sim_kind > 1) DOF_FAIL(DOF_ERR_UNSUPPORTED, "similarity kind %d (0 cosine / dot, 1 euclidean / edit)", sim_kind);
     if (loss_kind < 0 || loss_kind > 2) DOF_FAIL(DOF_ERR_UNSUPPORTED, "contrastive loss kind %d (0 nce, 1 dcl, 2 hard_dcl)", loss_kind);
     if (loss_kind > 0 && !(tau_plus >= 0.f && tau_plus < 1.f)) DOF_FAIL(DOF_ERR_ARG, "tau_plus must be in [0, 1)");
     if (c.D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 64", c.D);
@@ -1131,7 +1132,7 @@ int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, co
     NtxArgs n;
     n.enc = h->enc; n.zn = h->zn; n.nrm = h->nrm; n.lse = h->lse; n.denc = h->denc; n.stats = h->nstats; n.logs = logs;
     n.B = B; n.D = c.D; n.inv_tau = 1.0f / temperature;
-    n.kind = loss_kind; n.tau_plus = tau_plus; n.beta = beta; n.temperature = temperature;
+    n.kind = loss_kind; n.sim = sim_kind; n.tau_plus = tau_plus; n.beta = beta; n.temperature = temperature;
     DOF_CUDA(cudaMemsetAsync(h->nstats, 0, 8 * sizeof(double), st));
     { ProfScope ps("ntxent_norm", st);
     ntx_norm_kernel<<<cdiv(2LL * B * 32, 256), 256, 0, st>>>(n); }

@@ -242,6 +242,7 @@ struct NtxArgs {
     float* lse;         // [4,B] per-row coefficients of the gradient pass: m_i | A_i | P_i | Dg_i with
                         //   d loss_i / d s_ij = e_ij (A_i + P_i e_ij), e_ij = exp(s_ij - m_i), for j != i;  Dg_i for j == i
     int kind;           // 0 nce (losses.py:130-141), 1 dcl debiased (:144-173), 2 hard_dcl debiased (:213-249)
+    int sim;            // 0 cosine / dot on the normalised rows (losses.py:59-67), 1 euclidean / edit 1/(1+|x-y|) (:70-82)
     float tau_plus, beta, temperature;
     float* denc;        // [2B, D] gradient wrt enc
     double* stats;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
     for (int d = 0; d < DP; d++) acc[d] = 0.f;
     float my_m = 0.f, my_A = 0.f, my_P = 0.f, my_D = 0.f;
     if (PHASE == 1 && active && !col) { my_m = a.lse[self]; my_A = a.lse[B + self]; my_P = a.lse[2 * B + self]; my_D = a.lse[3 * B + self]; }
-    float l2 = 0.f;
+    float l2 = 0.f, wsum = 0.f;
     const float gs = a.inv_tau / (float)B;
     for (int j0 = 0; j0 < B; j0 += NTX_TILE) {
         __syncthreads();
@@ -304,10 +305,18 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
         if (!active) continue;
         for (int r = lane; r < NTX_TILE && j0 + r < B; r += 32) {
             const float* tr = tile + r * (DP + 1);
-            float dot = 0.f;
+            float dot = 0.f, dist = 0.f, sv = 0.f;
+            if (a.sim == 0) {
 #pragma unroll
-            for (int d = 0; d < DP; d++) if (d < D) dot += mine[d] * tr[d];
-            const float s = dot * a.inv_tau;
+                for (int d = 0; d < DP; d++) if (d < D) dot += mine[d] * tr[d];
+                sv = dot;
+            } else {
+#pragma unroll
+                for (int d = 0; d < DP; d++) if (d < D) { const float df = mine[d] - tr[d]; dot += df * df; }
+                dist = sqrtf(fmaxf(dot, 0.f));
+                sv = 1.0f / (1.0f + dist);
+            }
+            const float s = sv * a.inv_tau;
             if (PHASE == 0) {
                 sall += s;
                 if (j0 + r == self) sdiag = s;
@@ -322,6 +331,11 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
                 const float e = __expf(s - rm);
                 float g = (j0 + r == self) ? rD : e * (rA + rP * e);
                 g *= gs;
+                if (a.sim != 0) {
+                    // d sim / d mine = -(mine - other) / ((1 + dist)^2 dist): accumulate w*other and sum(w)
+                    g = dist > 0.f ? -g * sv * sv / dist : 0.f;
+                    wsum += g;
+                }
 #pragma unroll
                 for (int d = 0; d < DP; d++) if (d < D) acc[d] += g * tr[d];
             }
@@ -370,10 +384,12 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
         }
     } else {
         float dotg = 0.f;
+        wsum = warp_sum(wsum);
 #pragma unroll
         for (int d = 0; d < DP; d++) {
             if (d < D) {
                 acc[d] = warp_sum(acc[d]);
+                if (a.sim != 0) acc[d] = wsum * mine[d] - acc[d];
                 dotg += acc[d] * mine[d];
             }
         }

@@ -156,9 +156,10 @@ class ContrastiveB200(VaDEB200):
                  encoder_type: str = "recurrent", use_gnn: bool = True, temperature: float = 0.1,
                  similarity_function: str = "cosine", loss_function: str = "nce", beta: float = 0.1, tau: float = 0.1,
                  edge_index=None, edge_index_local=None, max_batch: int = 4096, **kw):
-        if similarity_function != "cosine" or loss_function not in ("nce", "dcl", "hard_dcl"):
-            raise NotImplementedError("deepof_b200 implements the cosine similarity with the nce / dcl / hard_dcl losses "
-                                      f"(got {similarity_function!r}, {loss_function!r})")
+        if similarity_function not in ("cosine", "dot", "euclidean", "edit") or loss_function not in ("nce", "dcl", "hard_dcl"):
+            raise NotImplementedError("deepof_b200 implements the cosine / dot / euclidean / edit similarities with the nce / "
+                                      f"dcl / hard_dcl losses (got {similarity_function!r}, {loss_function!r}); fc is not built")
+        self.similarity_function = similarity_function
         self.loss_function, self.beta, self.tau = loss_function, float(beta), float(tau)
         Tf, N, F = (int(v) for v in input_shape)
         _, E, Fe = (int(v) for v in edge_feature_shape)
@@ -275,7 +276,8 @@ class ContrastiveB200(VaDEB200):
         x2, a2 = self.views(x_full, prm)
         B = x2.shape[0] // 2
         kind = {"nce": 0, "dcl": 1, "hard_dcl": 2}[self.loss_function]
-        check(self.L.dof_contrastive_loss_grad(self.handle, ptr(self.state), ptr(self.grad), ptr(x2), ptr(a2), B, kind,
+        sim = 0 if self.similarity_function in ("cosine", "dot") else 1
+        check(self.L.dof_contrastive_loss_grad(self.handle, ptr(self.state), ptr(self.grad), ptr(x2), ptr(a2), B, kind, sim,
                                                self.temperature, self.tau, self.beta, ptr(self.logs),
                                                ptr(self.z_all[:2 * B]), _stream()))
         return self.logs

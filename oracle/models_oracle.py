@@ -290,9 +290,7 @@ def contrastive_views(x_full: Tensor, edge_index: Tensor, prm: AugParams):
 def nce_loss(z: Tensor, z_aug: Tensor, temperature: float):
     """normalize (training.py:532-533) -> cosine similarity / temperature -> cross-entropy against the diagonal
     (losses.py:130-141).  Returns loss, mean positive similarity, mean negative similarity."""
-    zn = torch.nn.functional.normalize(z, dim=1)
-    an = torch.nn.functional.normalize(z_aug, dim=1)
-    sim = torch.nn.functional.cosine_similarity(zn.unsqueeze(1), an.unsqueeze(0), dim=2) / temperature
+    sim = _cos_sim(z, z_aug) / temperature
     n = sim.shape[0]
     loss = torch.nn.functional.cross_entropy(sim, torch.arange(n))
     pos = torch.diag(sim).mean() * temperature
@@ -301,9 +299,17 @@ def nce_loss(z: Tensor, z_aug: Tensor, temperature: float):
     return loss, pos, neg
 
 
+SIMILARITY = "cosine"     # module-level switch used by the tests: cosine | dot | euclidean | edit (losses.py:59-89)
+
+
 def _cos_sim(z: Tensor, z_aug: Tensor) -> Tensor:
-    zn = torch.nn.functional.normalize(z, dim=1)
+    zn = torch.nn.functional.normalize(z, dim=1)                          # training.py:532-533
     an = torch.nn.functional.normalize(z_aug, dim=1)
+    if SIMILARITY == "dot":
+        return zn @ an.t()                                                # losses.py:66-67
+    if SIMILARITY in ("euclidean", "edit"):                               # losses.py:70-82
+        d = torch.sqrt(torch.clamp(((zn.unsqueeze(1) - an.unsqueeze(0)) ** 2).sum(dim=2), min=0.0))
+        return 1.0 / (1.0 + d)
     return torch.nn.functional.cosine_similarity(zn.unsqueeze(1), an.unsqueeze(0), dim=2)
 
 

@@ -40,6 +40,10 @@ CON_CASES = {
     "odd": dict(T=24, N=11, D=6, B=9, seed=33, aug=dict(p_rot=1.0, p_noise=0.5, p_interp=1.0, max_shift=3)),
     "dcl": dict(T=50, N=14, D=8, B=16, seed=34, aug=dict(p_interp=0.6), loss="dcl"),
     "hard": dict(T=50, N=14, D=8, B=16, seed=35, aug=dict(p_interp=0.6), loss="hard_dcl"),
+    # p_noise=1: with the euclidean similarity a window that draws no augmentation has distance 0 to its own view and
+    # the reference's sqrt backward turns every gradient into NaN (seen with p_noise=0.5, seed 36, step 2)
+    "euclid": dict(T=50, N=14, D=8, B=16, seed=36, aug=dict(p_interp=0.6, p_noise=1.0), loss="nce", sim="euclidean"),
+    "dot_dcl": dict(T=24, N=11, D=6, B=9, seed=37, aug=dict(p_interp=0.6), loss="dcl", sim="dot"),
 }
 
 
@@ -112,7 +116,7 @@ def run_con(name, c):
     E = len(rows)
     x_full, a_full = synthetic_windows(c["B"], c["T"], adj, seed=3000 + c["seed"])
     model = M.ContrastivePT((c["T"], N, 3), (c["T"], E, 1), adj, c["D"], encoder_type="recurrent", use_gnn=True,
-                            temperature=0.1, similarity_function="cosine", loss_function=c.get("loss", "nce"))
+                            temperature=0.1, similarity_function=c.get("sim", "cosine"), loss_function=c.get("loss", "nce"))
     names = ([f"B_n{i}" for i in range(N // 2)] + [f"W_n{i}" for i in range(N - N // 2)]) if name == "cfg4" \
         else [f"B_n{i}" for i in range(N)]
     meta = {"node_columns": [(n, "x") for n in names] + [(n, "y") for n in names] + names,
@@ -124,7 +128,8 @@ def run_con(name, c):
         setattr(ccfg, "aug_" + k, v)
     out = {"adjacency": adj, "x_full": x_full.numpy(), "a_full": a_full.numpy(), "edge_index": eg.numpy(),
            "edge_index_local": el.numpy(), "meta": np.array([c["T"], N, E, c["D"], c["B"]], dtype=np.int64),
-           "temperature": np.array(0.1), "loss_function": np.array(c.get("loss", "nce")), "tau": np.array(model.tau),
+           "temperature": np.array(0.1), "loss_function": np.array(c.get("loss", "nce")),
+           "similarity_function": np.array(c.get("sim", "cosine")), "tau": np.array(model.tau),
            "beta": np.array(model.beta)}
     for f in ("min_shift", "max_shift", "p_shift", "max_rot", "n_rot", "p_rot", "max_interp", "min_interp", "p_interp",
               "noise_sigma", "p_noise"):

@@ -149,6 +149,7 @@ def _con_model(g, max_batch=None):
     Tf, N, E, D, B = (int(v) for v in g["meta"])
     m = ContrastiveB200((Tf, N, 3), (Tf, E, 1), g["adjacency"], D, temperature=float(g["temperature"]),
                         loss_function=str(g["loss_function"]) if "loss_function" in g else "nce",
+                        similarity_function=str(g["similarity_function"]) if "similarity_function" in g else "cosine",
                         tau=float(g["tau"]) if "tau" in g else 0.1, beta=float(g["beta"]) if "beta" in g else 0.1,
                         edge_index=g["edge_index"], edge_index_local=g["edge_index_local"], max_batch=max_batch or B, seed=0)
     assert list(m.state_dict().keys()) == [k[2:] for k in g if k.startswith("p/")]
@@ -250,6 +251,55 @@ def test_contrastive_debiased_losses_vs_oracle(loss_fn, beta):
     bad = []
     _check_grads(m, {k: v for k, v in grads.items() if v is not None}, bad, f"{loss_fn}-beta{beta}")
     assert not bad, bad
+
+
+@pytest.mark.parametrize("sim,loss_fn", [("dot", "nce"), ("euclidean", "nce"), ("edit", "dcl"), ("euclidean", "hard_dcl")])
+def test_contrastive_similarities_vs_oracle(sim, loss_fn):
+    """dot / euclidean / edit similarities (losses.py:66-89) under the three losses."""
+    from deepof_b200 import ContrastiveB200
+    Tf, N, D, B = 24, 11, 8, 150
+    adj = O.default_adjacency(N)
+    r, c = np.nonzero(np.triu(adj))
+    ei = np.stack([r, c], 1)
+    x_full, _ = O.synthetic_windows(B, Tf, adj, seed=79)
+    m = ContrastiveB200((Tf, N, 3), (Tf, len(r), 1), adj, D, temperature=0.2, similarity_function=sim, loss_function=loss_fn,
+                        tau=0.1, beta=0.5, max_batch=B, seed=8)
+    p = {k: v.cpu() for k, v in m.state_dict().items()}
+    graph = O.graph_operators(adj)
+    rot = MO.rotation_table(ei, N)
+    torch.manual_seed(9)
+    prm = MO.draw_aug_params(B, Tf, N, MO.AugCfg(max_shift=3), rot)
+    MO.SIMILARITY = sim
+    try:
+        logs, grads, out = MO.contrastive_train_step(x_full, p, graph, D, torch.from_numpy(ei), prm, 0.2, loss_fn=loss_fn,
+                                                     tau_plus=0.1, beta=0.5)
+    finally:
+        MO.SIMILARITY = "cosine"
+    m.loss_grad(x_full, _to_product_params(prm))
+    got = m.logs_dict()
+    for k, v in logs.items():
+        assert abs(got[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, got[k], v)
+    bad = []
+    _check_grads(m, {k: v for k, v in grads.items() if v is not None}, bad, f"{sim}-{loss_fn}")
+    assert not bad, bad
+
+
+def test_contrastive_euclidean_zero_distance_is_finite():
+    """A window that draws no augmentation has distance 0 to its own view.  The reference's sqrt backward makes every
+    gradient NaN there (losses.py:70-82; seen while generating contrastive_euclid.npz); the kernel takes the zero
+    sub-gradient for that pair instead, so the step stays finite.  Documented deviation."""
+    from deepof_b200 import AugParams, ContrastiveB200
+    Tf, N, D, B = 24, 11, 6, 20
+    adj = O.default_adjacency(N)
+    x_full, _ = O.synthetic_windows(B, Tf, adj, seed=80)
+    m = ContrastiveB200((Tf, N, 3), (Tf, int(np.count_nonzero(np.triu(adj))), 1), adj, D, similarity_function="euclidean",
+                        max_batch=B, seed=3)
+    base = (Tf - Tf // 2) // 2
+    prm = AugParams(start=torch.full((B,), base, dtype=torch.int32, device="cuda"))      # the view IS the centre crop
+    m.loss_grad(x_full, prm)
+    logs = m.logs_dict()
+    assert abs(logs["pos_similarity"] - 1.0) < 1e-6 and np.isfinite(logs["total_loss"])
+    assert all(bool(torch.isfinite(v).all()) for v in m.grad_dict().values())
 
 
 def test_contrastive_draw_augmentation_ranges():

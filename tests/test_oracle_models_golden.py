@@ -76,7 +76,7 @@ def _aug_cfg(g):
 
 
 @pytest.mark.parametrize("case", CON)
-def test_contrastive_views_and_two_steps(case):
+def test_contrastive_views_and_two_steps(case, monkeypatch):
     g = load_golden_of("contrastive", case)
     Tf, N, E, D, B = (int(v) for v in g["meta"])
     p = sub(g, "p/")
@@ -86,6 +86,7 @@ def test_contrastive_views_and_two_steps(case):
     rot = MO.rotation_table(g["edge_index_local"], N)
     cfg = _aug_cfg(g)
     state = {}
+    monkeypatch.setattr(MO, "SIMILARITY", str(g["similarity_function"]) if "similarity_function" in g else "cosine")
     for step in range(2):
         torch.manual_seed(int(g[f"s{step}/seed"]))
         prm = MO.draw_aug_params(B, Tf, N, cfg, rot)
