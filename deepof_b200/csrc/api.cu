@@ -11,6 +11,7 @@
 #include "gru.cuh"
 #include "gru_tc.cuh"
 #include "gru_bwd_tc.cuh"
+#include "gru_wgrad_tc.cuh"
 #include "layers.cuh"
 #include "loss.cuh"
 #include "loader.cuh"
@@ -692,18 +693,30 @@ static void register_debug(dof_handle* h, int B) {
 // ---------------------------------------------------------------------------
 // gradients of one bidirectional GRU given dG[dir] [M rows x 4H] (layout da_r|da_z|da_n*r|da_n):
 //   dW_ih, db_ih (from X), dW_hh, db_hh (from time-shifted H), and optionally dX.
+static bool g_gru_wgrad_merged = getenv("DOF_GRU_WGRAD_SPLIT") == nullptr;   // env switch for A/B measurements
+
 static int gru_param_grads(dof_handle* h, const GruP& g, float* grad, const float* state, float* const dG[2],
                            MatView X, int Mx, float* const dGx[2],   // dGx: rows matching X (== dG unless repeated input)
                            const float* Hout, int M, int T, int I, int H, float* dX, const float* dXmask,
                            cudaStream_t st) {
-    WGradArgs wa[2];
-    for (int d = 0; d < 2; d++)
-        wa[d] = wgrad_args(mv_split(dGx[d], 4 * H, 2 * H, H), X, grad + g.w_ih[d], I, 0, grad + g.b_ih[d], Mx, 3 * H, I);
-    DOF_TRY(launch_gemm_wgrad(wa, 2, st, h->sm_count));
-    for (int d = 0; d < 2; d++)
-        wa[d] = wgrad_args(mv_plain(dG[d], 4 * H), mv_tshift(Hout + d * H, 2 * H, T, d ? +1 : -1), grad + g.w_hh[d], H, 0,
-                           grad + g.b_hh[d], M, 3 * H, H);
-    DOF_TRY(launch_gemm_wgrad(wa, 2, st, h->sm_count));
+    if (g_gru_wgrad_merged && Mx == M && dGx[0] == dG[0] && dGx[1] == dG[1] && X.mode == A_PLAIN &&
+        gru_wgrad_tc_eligible(M, H, I, X.ld, dG[0], dG[1], X.p, Hout)) {
+        // all four parameter gradients of both directions in one pass over dG (gru_wgrad_tc.cuh)
+        float* dWih[2] = {grad + g.w_ih[0], grad + g.w_ih[1]};
+        float* dWhh[2] = {grad + g.w_hh[0], grad + g.w_hh[1]};
+        float* dbih[2] = {grad + g.b_ih[0], grad + g.b_ih[1]};
+        float* dbhh[2] = {grad + g.b_hh[0], grad + g.b_hh[1]};
+        DOF_TRY(launch_gru_wgrad_tc(dG, X.p, X.ld, Hout, dWih, dWhh, dbih, dbhh, M, T, I, H, h->sm_count, st));
+    } else {
+        WGradArgs wa[2];
+        for (int d = 0; d < 2; d++)
+            wa[d] = wgrad_args(mv_split(dGx[d], 4 * H, 2 * H, H), X, grad + g.w_ih[d], I, 0, grad + g.b_ih[d], Mx, 3 * H, I);
+        DOF_TRY(launch_gemm_wgrad(wa, 2, st, h->sm_count));
+        for (int d = 0; d < 2; d++)
+            wa[d] = wgrad_args(mv_plain(dG[d], 4 * H), mv_tshift(Hout + d * H, 2 * H, T, d ? +1 : -1), grad + g.w_hh[d], H, 0,
+                               grad + g.b_hh[d], M, 3 * H, H);
+        DOF_TRY(launch_gemm_wgrad(wa, 2, st, h->sm_count));
+    }
     if (dX) {
         // dX = dGi_fwd . W_ih_fwd + dGi_bwd . W_ih_bwd as ONE two-K-block GEMM (no read-modify-write of dX)
         GemmArgs ga = gemm_args(mv_split(dGx[0], 4 * H, 2 * H, H), state + g.w_ih[0], I, 1, nullptr, dX, I, Mx, I, 3 * H);
@@ -1388,6 +1401,22 @@ int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* 
     b.len = len; b.Hout = hout; b.dOut = dout; b.dHn = dhn; b.dX = dx; b.dXmask = dxmask; b.S = S; b.T = T; b.H = H; b.I = I;
     if (dx) DOF_CUDA(cudaMemsetAsync(dx, 0, (size_t)S * T * I * 4, (cudaStream_t)stream));
     return launch_gru_bwd_tc(b, (cudaStream_t)stream);
+}
+
+int dof_test_gru_wgrad(const float* dg_f, const float* dg_b, const float* x, int ldx, const float* hout, float* out, int M, int T,
+                       int I, int H, void* stream) {
+    if (!gru_wgrad_tc_eligible(M, H, I, ldx, dg_f, dg_b, x, hout))
+        DOF_FAIL(DOF_ERR_UNSUPPORTED, "merged GRU weight gradient: shape M=%d H=%d I=%d pitch=%d is not eligible", M, H, I, ldx);
+    float* dG[2] = {const_cast<float*>(dg_f), const_cast<float*>(dg_b)};
+    const size_t per = (size_t)3 * H * I + (size_t)3 * H * H + 6 * H;
+    float *dWih[2], *dWhh[2], *dbih[2], *dbhh[2];
+    for (int d = 0; d < 2; d++) {
+        dWih[d] = out + d * per; dWhh[d] = dWih[d] + 3 * H * I; dbih[d] = dWhh[d] + 3 * H * H; dbhh[d] = dbih[d] + 3 * H;
+    }
+    int dev = 0, sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    return launch_gru_wgrad_tc(dG, x, ldx, hout, dWih, dWhh, dbih, dbhh, M, T, I, H, sm, (cudaStream_t)stream);
 }
 
 int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout, const float* gt_f,

@@ -102,7 +102,7 @@ __device__ __forceinline__ void split_tf32x4(const float4 v, float4& hi, float4&
     split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
 }
 
-static inline int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+__host__ __device__ static inline int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 // ---------------------------------------------------------------------------
 // gemm_rows on tcgen05

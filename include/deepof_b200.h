@@ -282,6 +282,11 @@ int dof_test_gru_layer_fwd(const float* X, long long x_ss, int x_st, const float
 int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* hout, const float* gtT_f,
                            const float* gtT_b, const float* dout, const float* dhn, float* dg_f, float* dg_b, float* dx,
                            const float* dxmask, int S, int T, int H, int I, void* stream);
+/* merged GRU parameter gradients (gru_wgrad_tc.cuh): dg_f / dg_b [M,4H] = [dr, dz, dn*r, dn], x [M,I] (pitch ldx),
+ * hout [M,2H]; out (zeroed by the caller, accumulated into) = per direction dW_ih [3H,I] | dW_hh [3H,H] | db_ih [3H] |
+ * db_hh [3H].  Returns DOF_ERR_UNSUPPORTED when the shape is not eligible for the tensor-core kernel. */
+int dof_test_gru_wgrad(const float* dg_f, const float* dg_b, const float* x, int ldx, const float* hout, float* out,
+                       int M, int T, int I, int H, void* stream);
 int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout,
                      const float* gt_f, const float* gt_b, const float* dout, const float* dhn,
                      float* dg_f, float* dg_b, int S, int T, int H, void* stream);

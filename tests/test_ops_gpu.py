@@ -139,6 +139,38 @@ def test_gemm_wgrad_views(L):
         assert rel(dbh, G[:, :3 * H].double().sum(0)) < 5e-6
 
 
+@pytest.mark.parametrize("S_,T,H,I,ldx,off", [(200, 25, 32, 64, 64, 0), (333, 24, 16, 32, 32, 0), (411, 11, 32, 16, 48, 1),
+                                              (180, 25, 16, 64, 64, 3), (1000, 5, 32, 48, 48, 0)])
+def test_gru_wgrad_merged(L, S_, T, H, I, ldx, off):
+    """All four parameter gradients of both directions from one pass over dG (TMA + MN-major tf32 operands)."""
+    M = S_ * T
+    G = [rnd(M, 4 * H, seed=3 + d) for d in range(2)]
+    Xfull = rnd(M, ldx, seed=5)
+    X = Xfull[:, :I]
+    Hs = rnd(S_, T, 2 * H, seed=6)
+    per = 3 * H * I + 3 * H * H + 6 * H
+    out = torch.zeros(2 * per + off, device="cuda")[off:]        # off != 0: gradient tensors that are not 16-byte aligned
+    rc = L.dof_test_gru_wgrad(P(G[0]), P(G[1]), P(Xfull), ldx, P(Hs), P(out), M, T, I, H, S())
+    assert rc == 0, L.dof_last_error()
+    torch.cuda.synchronize()
+    for d in range(2):
+        o = out[d * per:(d + 1) * per]
+        dWih, dWhh = o[:3 * H * I].view(3 * H, I), o[3 * H * I:3 * H * I + 3 * H * H].view(3 * H, H)
+        dbih, dbhh = o[-6 * H:-3 * H], o[-3 * H:]
+        Gd = G[d].double()
+        Gi = torch.cat([Gd[:, :2 * H], Gd[:, 3 * H:]], 1)
+        Gh = Gd[:, :3 * H]
+        Hd = Hs[:, :, d * H:(d + 1) * H].double()
+        Hsh = torch.zeros_like(Hd)
+        if d == 0:
+            Hsh[:, 1:] = Hd[:, :-1]
+        else:
+            Hsh[:, :-1] = Hd[:, 1:]
+        assert rel(dWih, Gi.t() @ X.double()) < 5e-6, d
+        assert rel(dWhh, Gh.t() @ Hsh.reshape(M, H)) < 5e-6, d
+        assert rel(dbih, Gi.sum(0)) < 5e-6 and rel(dbhh, Gh.sum(0)) < 5e-6, d
+
+
 @pytest.mark.parametrize("R,W,relu_in", [(1000, 64, 0), (4097, 32, 1), (33, 12, 0), (500, 128, 0), (10, 256, 0)])
 def test_layernorm(L, R, W, relu_in):
     x = rnd(R, W, seed=1)
