@@ -60,6 +60,11 @@ class DofViewsCfg(C.Structure):
                 ("noise", C.c_void_p)]
 
 
+class DofDistillCfg(C.Structure):
+    _fields_ = [("head", C.c_void_p), ("head_grad", C.c_void_p), ("tau_batch", C.c_void_p), ("K", C.c_int),
+                ("lambda_", C.c_float), ("sharpen_T", C.c_float), ("conf_weight", C.c_int), ("conf_thresh", C.c_float)]
+
+
 class DofError(RuntimeError):
     pass
 
@@ -89,6 +94,11 @@ _SIGS = {
     "dof_vqvae_forward_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "dof_vqvae_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P, _P]),
     "dof_contrastive_views": (C.c_int, [C.POINTER(DofViewsCfg), _P, C.c_int, _P, _P, _P]),
+    "dof_vqvae_loss_grad_distill": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.POINTER(DofDistillCfg), _P, _P]),
+    "dof_contrastive_loss_grad_distill": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                                    C.POINTER(DofDistillCfg), _P, _P, _P]),
+    "dof_adam_flat": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                C.c_float, _P]),
     "dof_contrastive_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P,
                                             _P]),
     "dof_loader_num_windows": (C.c_longlong, [C.c_longlong, C.c_int, C.c_int]),

@@ -24,7 +24,8 @@ import numpy as np
 import torch
 
 from .loader import batch_starts
-from .models import AugParams, CON_LOG_KEYS, ContrastiveAugCfg, ContrastiveB200, VQ_LOG_KEYS, VQVAEB200
+from .models import (AugParams, CON_LOG_KEYS, ContrastiveAugCfg, ContrastiveB200, DistillHeadB200, Distillation, VQ_LOG_KEYS,
+                     VQVAEB200)
 from .training import KLSchedule
 from .vade import VaDEB200, VadeLossCfg
 
@@ -74,11 +75,25 @@ def step_vade(model: VaDEB200, batch, ctx: SimpleNamespace) -> StepResult:
     return StepResult(loss=_Loss(logs[0]), logs=_logs(model) if getattr(ctx, "read_logs", True) else {})
 
 
+def _distillation(model, idx, ctx: SimpleNamespace) -> Optional[Distillation]:
+    """The teacher part of ``ctx`` exactly as ``step_vqvae_distill`` / ``step_contrastive_distill`` read it
+    (training.py:341-370, 550-578): ``distill_head`` (:class:`DistillHeadB200`), ``tau_star`` [Nw,K],
+    ``lambda_scheduler.get_weight()``, ``distill_sharpen_T`` (0.5), ``distill_conf_weight`` / ``distill_conf_thresh``."""
+    sched = getattr(ctx, "lambda_scheduler", None)
+    lam = float(sched.get_weight()) if sched is not None else 0.0
+    head = getattr(ctx, "distill_head", None)
+    if not getattr(ctx, "apply_distill", True) or head is None or lam <= 0.0:
+        return None
+    if not isinstance(head, DistillHeadB200):
+        raise TypeError("ctx.distill_head must be a deepof_b200.DistillHeadB200")
+    tau = ctx.tau_star.to(model.device)[idx.to(model.device).long()]
+    return Distillation(head, tau, lam, float(getattr(ctx, "distill_sharpen_T", 0.5)),
+                        bool(getattr(ctx, "distill_conf_weight", False)), float(getattr(ctx, "distill_conf_thresh", 0.6)))
+
+
 def step_vqvae_distill(model: VQVAEB200, batch, ctx: SimpleNamespace) -> StepResult:
-    if getattr(ctx, "apply_distill", False) and getattr(ctx, "distill_head", None) is not None:
-        raise NotImplementedError("the distillation head of step_vqvae_distill is not implemented; pass apply_distill=False")
     x, a, idx = batch
-    logs = model.loss_grad(x, a)
+    logs = model.loss_grad(x, a, distill=_distillation(model, idx, ctx))
     return StepResult(loss=_Loss(logs[0]), logs=_logs(model) if getattr(ctx, "read_logs", True) else {})
 
 
@@ -86,14 +101,12 @@ def step_contrastive_distill(model: ContrastiveB200, batch, ctx: SimpleNamespace
     """``batch[0]`` is the FULL window ``x_full`` [B,T,N,3]; the edge tensor is recomputed from it like the reference
     (``training.py:497``).  ``ctx.contrastive_cfg`` is a :class:`ContrastiveAugCfg`; ``ctx.aug_params`` injects the
     augmentation decisions (tests), otherwise they are drawn from ``ctx.generator`` / ``ctx.host_generator``."""
-    if getattr(ctx, "apply_distill", False) and getattr(ctx, "distill_head", None) is not None:
-        raise NotImplementedError("the distillation head of step_contrastive_distill is not implemented; pass apply_distill=False")
     x_full = batch[0]
     prm: Optional[AugParams] = getattr(ctx, "aug_params", None)
     if prm is None:
         cfg = getattr(ctx, "contrastive_cfg", None) or ContrastiveAugCfg()
         prm = model.draw_augmentation(x_full.shape[0], cfg, getattr(ctx, "generator", None), getattr(ctx, "host_generator", None))
-    logs = model.loss_grad(x_full, prm)
+    logs = model.loss_grad(x_full, prm, distill=_distillation(model, batch[2] if len(batch) > 2 else None, ctx))
     return StepResult(loss=_Loss(logs[0]), logs=_logs(model) if getattr(ctx, "read_logs", True) else {})
 
 
@@ -109,10 +122,10 @@ def train_one_epoch_indexed(model, model_name: str, dataloader, optimizer, step_
                             world_size: int = 1, log_every: int = 0):
     """One epoch (reference ``training.py:104-187``).  ``dataloader`` yields ``(x, a, idx)``; ``optimizer`` is a dict of
     the Adam hyper-parameters: ``{"lr": .., "gmm_lr": .., "weight_decay": ..}``.  Returns
-    ``(averaged logs, kl weight at mid epoch, 0.0)`` like the reference.  Logs are read back every ``log_every``
+    ``(averaged logs, kl weight at mid epoch, distillation weight at mid epoch)`` like the reference.  Logs are read back every ``log_every``
     steps (0: only the last step of the epoch) so the loop does not synchronise per step."""
     ctx = ctx or SimpleNamespace()
-    logs_accum, mid_kl = [], 0.0
+    logs_accum, mid_kl, mid_lambda = [], 0.0, 0.0
     batches = list(dataloader) if not hasattr(dataloader, "__len__") else dataloader
     n = len(batches)
     for step, batch in enumerate(batches):
@@ -136,9 +149,20 @@ def train_one_epoch_indexed(model, model_name: str, dataloader, optimizer, step_
         else:
             model.adam_step(optimizer["lr"], clip=grad_clip_value or 0.0, grad_scale=scale,
                             weight_decay=optimizer.get("weight_decay", 1e-4))
+            head = getattr(ctx, "distill_head", None)
+            sched = getattr(ctx, "lambda_scheduler", None)
+            if head is not None and getattr(ctx, "apply_distill", True) and sched is not None and sched.get_weight() > 0.0:
+                # build_optimizer_generic puts the head into the same Adam (losses.py:811-814); DDP averages its gradient
+                if world_size > 1:
+                    dist.all_reduce(head.grad, op=dist.ReduceOp.SUM)
+                head.adam_step(optimizer["lr"], weight_decay=optimizer.get("weight_decay", 1e-4), grad_scale=scale)
+            if sched is not None:
+                sched.step()                                              # training.py:177-181
+                if step == n // 2:
+                    mid_lambda = sched.get_weight()
         if res.logs:
             logs_accum.append(res.logs)
-    return average_logs(logs_accum), mid_kl, 0.0
+    return average_logs(logs_accum), mid_kl, mid_lambda
 
 
 # ---- data -----------------------------------------------------------------------------------------------------

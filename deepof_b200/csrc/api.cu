@@ -1027,8 +1027,29 @@ int dof_vqvae_forward_eval(dof_handle* h, const float* state, const float* x, co
 // step_vqvae_distill forward + backward without teacher (training.py:312-389): loss = NLL(decoder(quantized)) +
 // NLL(decoder(encoder output)) + float(vq_loss) + float(kmeans_loss).  The encoder learns through the bypass
 // decoder only; the codebook through the one-hot matmul of the quantized path (there is no straight-through).
+// the distillation head on the first B rows of the encoder output: adds its gradient to denc, its loss sum to *stat
+static int distill_head_step(dof_handle* h, const dof_distill_cfg* dc, int B, double* stat, bool normalised, cudaStream_t st) {
+    const int D = h->cfg.D, K = dc->K;
+    if (!dc->head || !dc->head_grad || !dc->tau_batch) DOF_FAIL(DOF_ERR_ARG, "distillation: null head / head_grad / tau_batch");
+    if (K < 1 || K > DH_MAXK || D > DH_MAXD) DOF_FAIL(DOF_ERR_UNSUPPORTED, "distillation head: K=%d (<= %d), D=%d (<= %d)", K, DH_MAXK, D, DH_MAXD);
+    DOF_CUDA(cudaMemsetAsync(dc->head_grad, 0, ((size_t)K * D + K) * 4, st));
+    DistillArgs a;
+    a.z = normalised ? h->zn : h->enc; a.nrm = normalised ? h->nrm : nullptr; a.head = dc->head; a.head_grad = dc->head_grad; a.tau = dc->tau_batch; a.denc = h->denc; a.stat = stat;
+    a.B = B; a.D = D; a.K = K; a.lambda = dc->lambda; a.sharpen_T = dc->sharpen_T; a.conf_thresh = dc->conf_thresh;
+    a.conf_weight = dc->conf_weight;
+    { ProfScope ps("distill_head", st);
+    distill_head_kernel<<<cdiv(B, 128), 128, (size_t)2 * (K * D + K) * 4, st>>>(a); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
 int dof_vqvae_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B, float beta,
                         float kmeans_weight, float* logs, void* stream) {
+    return dof_vqvae_loss_grad_distill(h, state, grad, x, a, B, beta, kmeans_weight, nullptr, logs, stream);
+}
+
+int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B, float beta,
+                                float kmeans_weight, const dof_distill_cfg* distill, float* logs, void* stream) {
     DOF_TRY(check_batch(h, B));
     const dof_config& c = h->cfg;
     if (c.model != DOF_MODEL_VQVAE) DOF_FAIL(DOF_ERR_ARG, "handle is not a VQ-VAE model");
@@ -1056,9 +1077,12 @@ int dof_vqvae_loss_grad(dof_handle* h, const float* state, float* grad, const fl
         }
     }
     DOF_CUDA(cudaMemcpyAsync(h->denc, h->dz_dec, (size_t)B * D * 4, cudaMemcpyDeviceToDevice, st));
+    const bool dist_on = distill && distill->lambda > 0.f;               // training.py:346
+    if (dist_on) DOF_TRY(distill_head_step(h, distill, B, h->vstats + VQ_ST_DISTILL, false, st));
     DOF_TRY(encoder_backward(h, state, grad, B, st));
     VqFinalArgs f;
     f.stats = h->vstats; f.logs = logs; f.B = B; f.T = T; f.Dx = NF; f.D = D; f.K = K; f.beta = beta; f.kmeans_w = kmeans_weight;
+    f.lambda_distill = dist_on ? distill->lambda : 0.f;
     { ProfScope ps("vq_finalize", st);
     vq_finalize_kernel<<<1, 32, (size_t)2 * D * D * sizeof(double), st>>>(f); }
     DOF_LAUNCH_CHECK();
@@ -1129,6 +1153,13 @@ extern "C" {
 int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
                               int loss_kind, int sim_kind, float temperature, float tau_plus, float beta, float* logs,
                               float* z_out, void* stream) {
+    return dof_contrastive_loss_grad_distill(h, state, grad, x2, a2, B, loss_kind, sim_kind, temperature, tau_plus, beta, nullptr,
+                                             logs, z_out, stream);
+}
+
+int dof_contrastive_loss_grad_distill(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
+                                      int loss_kind, int sim_kind, float temperature, float tau_plus, float beta,
+                                      const dof_distill_cfg* distill, float* logs, float* z_out, void* stream) {
     DOF_TRY(check_batch(h, 2 * B));
     const dof_config& c = h->cfg;
     if (c.model != DOF_MODEL_CONTRASTIVE) DOF_FAIL(DOF_ERR_ARG, "handle is not a contrastive model");
@@ -1154,8 +1185,11 @@ int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, co
     else if (c.D <= 16) DOF_TRY(ntx_launch<16>(n, B, st));
     else if (c.D <= 32) DOF_TRY(ntx_launch<32>(n, B, st));
     else DOF_TRY(ntx_launch<64>(n, B, st));
+    // training.py:533-557: the head sees the row-NORMALISED embedding of the MAIN view (z is reassigned before z_main = z)
+    const bool dist_on = distill && distill->lambda > 0.f;
+    if (dist_on) DOF_TRY(distill_head_step(h, distill, B, h->nstats + NTX_ST_DISTILL, true, st));
     { ProfScope ps("ntxent_finalize", st);
-    ntx_finalize_kernel<<<1, 1, 0, st>>>(n, temperature); }
+    ntx_finalize_kernel<<<1, 1, 0, st>>>(n, temperature, dist_on ? distill->lambda : 0.f); }
     DOF_LAUNCH_CHECK();
     DOF_TRY(encoder_backward(h, state, grad, 2 * B, st));
     h->lastB = 2 * B;
@@ -1180,6 +1214,25 @@ int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m,
     a.clip = opt->clip_value; a.gscale = opt->grad_scale; a.beta1 = opt->beta1; a.beta2 = opt->beta2; a.eps = opt->eps;
     { ProfScope ps("clip_adam", (cudaStream_t)stream, 0.0, 28.0 * a.n);
     clip_adam_kernel<<<cdiv(a.n, 256), 256, 0, (cudaStream_t)stream>>>(a); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+// Adam on a caller-owned flat buffer (the distillation head): no clipping (clip_grad_value_ only sees the model,
+// training.py:165), weight decay as in build_optimizer_generic (losses.py:805-814)
+int dof_adam_flat(float* param, const float* grad, float* adam_m, float* adam_v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    if (!param || !grad || !adam_m || !adam_v || n < 1) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = param; a.g = grad; a.m = adam_m; a.v = adam_v; a.group = nullptr; a.n = n;
+    const int s = step > 0 ? step : 1;
+    a.lr[1] = lr; a.wd[1] = weight_decay; a.active[1] = 1;
+    a.bc1[1] = (float)(1.0 - pow((double)beta1, s));
+    a.bc2_sqrt[1] = (float)sqrt(1.0 - pow((double)beta2, s));
+    a.clip = 0.f; a.gscale = grad_scale; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    { ProfScope ps("clip_adam", (cudaStream_t)stream, 0.0, 28.0 * n);
+    clip_adam_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }

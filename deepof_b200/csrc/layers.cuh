@@ -541,7 +541,7 @@ struct AdamArgs {
 __global__ void __launch_bounds__(256) clip_adam_kernel(const AdamArgs a) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    int grp = a.group[i];
+    int grp = a.group ? a.group[i] : 1;          // no group map: one flat buffer in group 1
     if (grp == 0 || !a.active[grp]) return;
     float g = a.g[i] * a.gscale;
     if (a.clip > 0.f) g = fminf(fmaxf(g, -a.clip), a.clip);

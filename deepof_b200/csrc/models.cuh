@@ -101,10 +101,11 @@ __global__ void vq_codebook_grad_kernel(const float* __restrict__ dquant, const 
     atomicAdd(gcb + (size_t)d * K + idx[b], dquant[i]);
 }
 
+#define VQ_ST_DISTILL 3  // sum_b w_b * soft-CE_b of the distillation head (0 without a teacher)
 struct VqFinalArgs {
     double* stats; float* logs;
     int B, T, Dx, D, K;
-    float beta, kmeans_w;
+    float beta, kmeans_w, lambda_distill;
 };
 
 // logs: 0 total 1 enc_rec 2 reconstruct 3 vq 4 kmeans 5 populated 6 distill (training.py:380-388)
@@ -131,9 +132,10 @@ __global__ void __launch_bounds__(32) vq_finalize_kernel(const VqFinalArgs a) {
         const double bt = (double)a.B * a.T;
         const double encrec = a.stats[VQ_ST_REC_Q] / bt + cst, rec = a.stats[VQ_ST_REC_E] / bt + cst;
         const double vq = (1.0 + (double)a.beta) * a.stats[VQ_ST_SQ] / ((double)a.B * D);   // models_new.py:1387-1391
-        a.logs[0] = (float)(encrec + rec + vq + km);
+        const double dist = (double)a.lambda_distill * a.stats[VQ_ST_DISTILL] / (double)a.B;
+        a.logs[0] = (float)(encrec + rec + vq + km + dist);
         a.logs[1] = (float)encrec; a.logs[2] = (float)rec; a.logs[3] = (float)vq; a.logs[4] = (float)km;
-        a.logs[5] = (float)pop; a.logs[6] = 0.f;
+        a.logs[5] = (float)pop; a.logs[6] = (float)dist;
     }
 }
 
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(128) views_kernel(const ViewsArgs a) {
 #define NTX_ST_LOSS 0
 #define NTX_ST_POS 1
 #define NTX_ST_ALL 2
+#define NTX_ST_DISTILL 7
 #define NTX_TILE 128
 #define NTX_WARPS 8
 struct NtxArgs {
@@ -404,11 +407,97 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
 }
 
 // logs: 0 total 1 pos_similarity 2 neg_similarity 3 distill 4 seperability (training.py:582-588)
-__global__ void ntx_finalize_kernel(const NtxArgs a, float tau) {
+__global__ void ntx_finalize_kernel(const NtxArgs a, float tau, float lambda_distill) {
     const double B = (double)a.B;
-    a.logs[0] = (float)(a.stats[NTX_ST_LOSS] / B);
+    const double dist = (double)lambda_distill * a.stats[NTX_ST_DISTILL] / B;
+    a.logs[0] = (float)(a.stats[NTX_ST_LOSS] / B + dist);
     a.logs[1] = (float)(a.stats[NTX_ST_POS] / B * tau);
     a.logs[2] = a.B > 1 ? (float)((a.stats[NTX_ST_ALL] - a.stats[NTX_ST_POS]) * tau / (B * (B - 1.0))) : 0.f;
-    a.logs[3] = 0.f;
+    a.logs[3] = (float)dist;
     a.logs[4] = 0.f;
+}
+
+// ---------------------------------------------------------------------------
+// distillation head of step_vqvae_distill / step_contrastive_distill (deepof/clustering/training.py:341-370, 550-578):
+// logits = DiscriminativeHead(z) = z W^T + b (teacher_model.py:795-808); targets = softmax(log(clamp_min(tau, 1e-8)) / T)
+// when T > 0; per-sample soft cross-entropy -sum_k clamp(t_k, 1e-8, 1) log_softmax(logits)_k (_soft_ce_logits,
+// training.py:392-400), optionally weighted by the teacher confidence; loss = lambda * mean_b.  One thread per window:
+// the head gradient is reduced in shared memory first, the encoder-output gradient is ADDED to denc.
+// ---------------------------------------------------------------------------
+#define DH_MAXK 64
+#define DH_MAXD 64
+struct DistillArgs {
+    const float* z;          // [B, D] what the head sees: encoder output (VQ-VAE) or its row-normalised copy (contrastive)
+    const float* nrm;        // [B] row norms when z is the normalised copy (the gradient goes back through F.normalize), else NULL
+    const float* head;       // W [K, D] | b [K]
+    float* head_grad;        // same layout, zeroed by the caller
+    const float* tau;        // [B, K] teacher posteriors of the batch
+    float* denc;             // [B, D] += d loss / d z
+    double* stat;            // += sum_b w_b * ce_b (the caller scales by lambda / B)
+    int B, D, K;
+    float lambda, sharpen_T, conf_thresh;
+    int conf_weight;
+};
+
+__global__ void __launch_bounds__(128) distill_head_kernel(const DistillArgs a) {
+    extern __shared__ __align__(16) float dhsm[];
+    const int D = a.D, K = a.K, tid = threadIdx.x;
+    float* Ws = dhsm;                  // [K*D + K]
+    float* Gs = Ws + K * D + K;       // [K*D + K] block-level gradient
+    for (int i = tid; i < K * D + K; i += blockDim.x) { Ws[i] = a.head[i]; Gs[i] = 0.f; }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + tid;
+    double mine = 0.0;
+    if (b < a.B) {
+        float z[DH_MAXD], t[DH_MAXK], lg[DH_MAXK];
+        for (int d = 0; d < D; d++) z[d] = a.z[(size_t)b * D + d];
+        float mx = -INFINITY;
+        for (int k = 0; k < K; k++) {
+            float s = Ws[K * D + k];
+            for (int d = 0; d < D; d++) s += Ws[k * D + d] * z[d];
+            lg[k] = s;
+            mx = fmaxf(mx, s);
+        }
+        float se = 0.f;
+        for (int k = 0; k < K; k++) se += expf(lg[k] - mx);
+        const float lse = mx + logf(se);
+        // teacher targets
+        for (int k = 0; k < K; k++) t[k] = a.tau[(size_t)b * K + k];
+        if (a.sharpen_T > 0.f) {
+            float tm = -INFINITY;
+            for (int k = 0; k < K; k++) { t[k] = logf(fmaxf(t[k], 1e-8f)) / a.sharpen_T; tm = fmaxf(tm, t[k]); }
+            float ts = 0.f;
+            for (int k = 0; k < K; k++) { t[k] = expf(t[k] - tm); ts += t[k]; }
+            for (int k = 0; k < K; k++) t[k] /= ts;
+        }
+        float w = 1.f;
+        if (a.conf_weight) {
+            float conf = -INFINITY;
+            for (int k = 0; k < K; k++) conf = fmaxf(conf, t[k]);
+            w = fminf(fmaxf((conf - a.conf_thresh) / fmaxf(1e-6f, 1.0f - a.conf_thresh), 0.f), 1.f);
+        }
+        float ce = 0.f, tsum = 0.f;
+        for (int k = 0; k < K; k++) { t[k] = fminf(fmaxf(t[k], 1e-8f), 1.0f); ce -= t[k] * (lg[k] - lse); tsum += t[k]; }
+        mine = (double)(w * ce);
+        const float gs = a.lambda * w / (float)a.B;
+        float dz[DH_MAXD];
+        for (int d = 0; d < D; d++) dz[d] = 0.f;
+        for (int k = 0; k < K; k++) {
+            const float dl = gs * (expf(lg[k] - lse) * tsum - t[k]);
+            atomicAdd(Gs + K * D + k, dl);
+            for (int d = 0; d < D; d++) { atomicAdd(Gs + k * D + d, dl * z[d]); dz[d] += dl * Ws[k * D + d]; }
+        }
+        if (a.nrm) {
+            // z = e / |e|:  d loss / d e = (dz - (dz . z) z) / |e|
+            float dot = 0.f;
+            for (int d = 0; d < D; d++) dot += dz[d] * z[d];
+            const float inv = 1.0f / a.nrm[b];
+            for (int d = 0; d < D; d++) dz[d] = (dz[d] - dot * z[d]) * inv;
+        }
+        for (int d = 0; d < D; d++) a.denc[(size_t)b * D + d] += dz[d];
+    }
+    mine = warp_sum_d(mine);
+    if ((tid & 31) == 0 && mine != 0.0) atomicAdd(a.stat, mine);
+    __syncthreads();
+    for (int i = tid; i < K * D + K; i += blockDim.x) if (Gs[i] != 0.f) atomicAdd(a.head_grad + i, Gs[i]);
 }

@@ -24,6 +24,74 @@ VQ_LOG_KEYS = ("total_loss", "enc_rec_loss", "reconstruct_loss", "vq_loss", "kme
 CON_LOG_KEYS = ("total_loss", "pos_similarity", "neg_similarity", "distill_loss", "seperability")   # :582-588
 
 
+class DistillHeadB200:
+    """``DiscriminativeHead`` (teacher_model.py:795-808): one ``Linear(latent_dim, n_components)`` on the encoder output,
+    trained together with the VQ-VAE / contrastive model by ``build_optimizer_generic`` (losses.py:805-814) and NOT
+    clipped (training.py:165 clips ``model.parameters()`` only).  Its forward + soft cross-entropy + backward run inside
+    ``dof_*_loss_grad_distill``; this object owns the parameters, their gradient and the Adam moments."""
+
+    def __init__(self, latent_dim: int, n_components: int, device="cuda", seed: Optional[int] = None):
+        self.latent_dim, self.n_components = int(latent_dim), int(n_components)
+        self.device = torch.device(device)
+        n = self.n_components * self.latent_dim + self.n_components
+        g = torch.Generator().manual_seed(int(seed)) if seed is not None else None
+        bound = 1.0 / math.sqrt(self.latent_dim)                       # nn.Linear's default init
+        self.state = ((torch.rand(n, generator=g) * 2.0 - 1.0) * bound).to(self.device)
+        self.grad = torch.zeros(n, device=self.device)
+        self.adam_m, self.adam_v = torch.zeros_like(self.state), torch.zeros_like(self.state)
+        self.step = 0
+        self.L = _lib.lib()
+
+    @property
+    def weight(self) -> torch.Tensor:
+        return self.state[: self.n_components * self.latent_dim].view(self.n_components, self.latent_dim)
+
+    @property
+    def bias(self) -> torch.Tensor:
+        return self.state[self.n_components * self.latent_dim:]
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {"fc.weight": self.weight.clone(), "fc.bias": self.bias.clone()}
+
+    def load_state_dict(self, sd) -> None:
+        self.weight.copy_(torch.as_tensor(sd["fc.weight"]).to(self.device, torch.float32))
+        self.bias.copy_(torch.as_tensor(sd["fc.bias"]).to(self.device, torch.float32))
+
+    def grad_dict(self) -> Dict[str, torch.Tensor]:
+        kd = self.n_components * self.latent_dim
+        return {"fc.weight": self.grad[:kd].view(self.n_components, self.latent_dim), "fc.bias": self.grad[kd:]}
+
+    def __call__(self, z: torch.Tensor) -> torch.Tensor:
+        """Logits for inference-time cluster read-outs (``get_q_vqvae``): plain torch on the device, off the step path."""
+        return z.to(self.device, torch.float32) @ self.weight.t() + self.bias
+
+    def adam_step(self, lr: float, weight_decay: float = 1e-4, grad_scale: float = 1.0, beta1: float = 0.9,
+                  beta2: float = 0.999, eps: float = 1e-8) -> None:
+        self.step += 1
+        check(self.L.dof_adam_flat(ptr(self.state), ptr(self.grad), ptr(self.adam_m), ptr(self.adam_v), self.state.numel(),
+                                   float(lr), beta1, beta2, eps, float(weight_decay), self.step, float(grad_scale), _stream()))
+
+
+@dataclass
+class Distillation:
+    """What ``step_*_distill`` reads from ``ctx`` when the teacher is on (training.py:341-370)."""
+    head: DistillHeadB200
+    tau_batch: torch.Tensor              # [B, K] = ctx.tau_star[idx]
+    lambda_distill: float
+    sharpen_T: float = 0.5
+    conf_weight: bool = False
+    conf_thresh: float = 0.6
+
+    def cfg(self, B: int) -> "_lib.DofDistillCfg":
+        tau = self.tau_batch.to(self.head.device, torch.float32).contiguous()
+        if tuple(tau.shape) != (B, self.head.n_components):
+            raise ValueError(f"tau_batch must be [{B}, {self.head.n_components}], got {tuple(tau.shape)}")
+        self._keep = tau
+        return _lib.DofDistillCfg(self.head.state.data_ptr(), self.head.grad.data_ptr(), tau.data_ptr(), self.head.n_components,
+                                  float(self.lambda_distill), float(self.sharpen_T or 0.0), int(bool(self.conf_weight)),
+                                  float(self.conf_thresh))
+
+
 class VQVAEB200(VaDEB200):
     """Stand-in for ``VQVAEPT(encoder_type="recurrent", use_gnn=True)``."""
     _MODEL = _lib.MODEL_VQVAE
@@ -71,12 +139,14 @@ class VQVAEB200(VaDEB200):
         enc, quant, soft, idx, _, _ = self.forward_eval(x, a, want_loc=False)
         return enc, soft
 
-    def loss_grad(self, x, a):
+    def loss_grad(self, x, a, distill: Optional["Distillation"] = None):
         if not self.training_capable:
             raise _lib.DofError("model was created with training=False")
         x, a = self._prep(x, a)
-        check(self.L.dof_vqvae_loss_grad(self.handle, ptr(self.state), ptr(self.grad), ptr(x), ptr(a), x.shape[0],
-                                         self.beta, self.kmeans_weight, ptr(self.logs), _stream()))
+        dc = distill.cfg(x.shape[0]) if distill is not None and distill.lambda_distill > 0.0 else None
+        check(self.L.dof_vqvae_loss_grad_distill(self.handle, ptr(self.state), ptr(self.grad), ptr(x), ptr(a), x.shape[0],
+                                                 self.beta, self.kmeans_weight, C.byref(dc) if dc is not None else None,
+                                                 ptr(self.logs), _stream()))
         return self.logs
 
     def adam_step(self, lr: float, clip: float = 0.75, grad_scale: float = 1.0, weight_decay: float = 1e-4, **kw):
@@ -269,17 +339,20 @@ class ContrastiveB200(VaDEB200):
         self._keep = (start, th, t0, ln, nz)      # keep the device arrays alive until the stream has consumed them
         return x2, a2
 
-    def loss_grad(self, x_full, prm: AugParams):
-        """views + encoder on both + NT-Xent + backward into ``self.grad``; returns the device log vector."""
+    def loss_grad(self, x_full, prm: AugParams, distill: Optional["Distillation"] = None):
+        """views + encoder on both + NT-Xent (+ distillation head on the main view) + backward into ``self.grad``;
+        returns the device log vector."""
         if not self.training_capable:
             raise _lib.DofError("model was created with training=False")
         x2, a2 = self.views(x_full, prm)
         B = x2.shape[0] // 2
         kind = {"nce": 0, "dcl": 1, "hard_dcl": 2}[self.loss_function]
         sim = 0 if self.similarity_function in ("cosine", "dot") else 1
-        check(self.L.dof_contrastive_loss_grad(self.handle, ptr(self.state), ptr(self.grad), ptr(x2), ptr(a2), B, kind, sim,
-                                               self.temperature, self.tau, self.beta, ptr(self.logs),
-                                               ptr(self.z_all[:2 * B]), _stream()))
+        dc = distill.cfg(B) if distill is not None and distill.lambda_distill > 0.0 else None
+        check(self.L.dof_contrastive_loss_grad_distill(self.handle, ptr(self.state), ptr(self.grad), ptr(x2), ptr(a2), B, kind, sim,
+                                                       self.temperature, self.tau, self.beta,
+                                                       C.byref(dc) if dc is not None else None, ptr(self.logs),
+                                                       ptr(self.z_all[:2 * B]), _stream()))
         return self.logs
 
     def adam_step(self, lr: float, clip: float = 0.75, grad_scale: float = 1.0, weight_decay: float = 1e-4, **kw):

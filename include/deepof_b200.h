@@ -210,6 +210,32 @@ int dof_vqvae_forward_eval(dof_handle* h, const float* state, const float* x, co
 int dof_vqvae_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B,
                         float beta, float kmeans_weight, float* logs, void* stream);
 
+/* ---- distillation head of step_vqvae_distill / step_contrastive_distill -------------------------------
+ * (deepof/clustering/training.py:341-370, 550-578): DiscriminativeHead (teacher_model.py:795-808) = one Linear(D, K) on
+ * the encoder output (VQ-VAE: z_e; contrastive: the row-normalised z of the MAIN view, training.py:533, 556), soft cross-entropy (_soft_ce_logits,
+ * training.py:392-400) against tau_batch [B,K] = tau_star[batch_indices], sharpened with temperature sharpen_T when
+ * > 0 and optionally confidence-weighted; loss += lambda * mean_b.  head = W [K,D] | b [K] is CALLER-owned (it is not
+ * part of the model's state_dict in the reference either); head_grad has the same layout and is overwritten.
+ * lambda <= 0 or distill == NULL is the teacher-off step.  logs slot distill_loss receives lambda * mean_b. */
+typedef struct dof_distill_cfg {
+    const float* head;
+    float* head_grad;
+    const float* tau_batch;
+    int K;
+    float lambda;
+    float sharpen_T;
+    int conf_weight;
+    float conf_thresh;
+} dof_distill_cfg;
+int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B,
+                                float beta, float kmeans_weight, const dof_distill_cfg* distill, float* logs,
+                                void* stream);
+/* Adam on a caller-owned flat buffer (the head): torch.optim.Adam(lr, weight_decay) of build_optimizer_generic
+ * (losses.py:805-814) WITHOUT clip_grad_value_ (training.py:165 clips model.parameters() only); step >= 1 is the
+ * bias-correction count, grad_scale = 1 / world after a sum all-reduce. */
+int dof_adam_flat(float* param, const float* grad, float* adam_m, float* adam_v, long long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 /* ---- contrastive (DOF_MODEL_CONTRASTIVE) --------------------------------------------------------------
  * dof_contrastive_views builds what step_contrastive_distill feeds its encoder (training.py:497-525): from
  * x_full [B,T_full,N,3] the middle half window and the augmented view of _make_augmented_view (training.py:2128-2402)
@@ -243,6 +269,10 @@ int dof_contrastive_views(const dof_views_cfg* v, const float* x_full, int B, fl
 int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
                               int loss_kind, int sim_kind, float temperature, float tau_plus, float beta, float* logs,
                               float* z_out, void* stream);
+/* the same step with the distillation head (see dof_distill_cfg) */
+int dof_contrastive_loss_grad_distill(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2,
+                                      int B, int loss_kind, int sim_kind, float temperature, float tau_plus, float beta,
+                                      const dof_distill_cfg* distill, float* logs, float* z_out, void* stream);
 
 /* Debug / test access to intermediate activations of the last forward (device pointers into
  * the workspace; NULL if unknown).  Names: "node_out","edge_out","enc","z","z_mean",

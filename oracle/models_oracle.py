@@ -73,9 +73,33 @@ def vqvae_forward(x: Tensor, a: Tensor, p: Dict[str, Tensor], graph, latent_dim:
     return dict(enc=enc, quant=quant, soft=soft, idx=idx, loc_q=loc_q, loc_e=loc_e, mask=mask, vq=vql)
 
 
+def distill_loss(z: Tensor, head_w: Tensor, head_b: Tensor, tau_b: Tensor, lam: float, sharpen_T: float = 0.5,
+                 conf_weight: bool = False, conf_thresh: float = 0.6) -> Tensor:
+    """The teacher term shared by step_vqvae_distill (training.py:346-370) and step_contrastive_distill (:555-578):
+    DiscriminativeHead logits (teacher_model.py:795-808), sharpened targets, _soft_ce_logits (training.py:392-400)."""
+    logits = z @ head_w.t() + head_b
+    if sharpen_T > 0.0:
+        tau_b = torch.softmax(tau_b.clamp_min(1e-8).log() / sharpen_T, dim=-1)
+    logp = torch.log_softmax(logits, dim=-1)
+    per = -(tau_b.clamp(min=1e-8, max=1.0) * logp).sum(dim=-1)
+    if conf_weight:
+        conf = tau_b.max(dim=1).values
+        w = ((conf - conf_thresh) / max(1e-6, 1.0 - conf_thresh)).clamp(0.0, 1.0).detach()
+        return lam * (w * per).mean()
+    return lam * per.mean()
+
+
+def _distill_leaves(distill):
+    """distill = dict(head_w, head_b, tau, lam, sharpen_T, conf_weight, conf_thresh) -> leaf copies of the head."""
+    w = distill["head_w"].detach().clone().requires_grad_(True)
+    b = distill["head_b"].detach().clone().requires_grad_(True)
+    return w, b
+
+
 def vqvae_train_step(x: Tensor, a: Tensor, p: Dict[str, Tensor], graph, latent_dim: int, beta: float = 1.0,
-                     kmeans_w: float = 0.0):
-    """step_vqvae_distill forward + backward without teacher.  Returns (logs, grads, outputs)."""
+                     kmeans_w: float = 0.0, distill: Optional[dict] = None):
+    """step_vqvae_distill forward + backward (teacher off unless `distill` is given: then the gradients of the head
+    come back under the keys "head/fc.weight", "head/fc.bias").  Returns (logs, grads, outputs)."""
     names = [k for k in p if k not in V.BUFFER_NAMES]
     leaf = {k: (v.detach().clone().requires_grad_(True) if k in names and v.dtype.is_floating_point else v) for k, v in p.items()}
     B, T, N, F = x.shape
@@ -84,11 +108,21 @@ def vqvae_train_step(x: Tensor, a: Tensor, p: Dict[str, Tensor], graph, latent_d
     enc_rec = -(V.recon_log_prob(out["loc_q"], out["mask"], xf)).mean()   # training.py:331
     rec = -(V.recon_log_prob(out["loc_e"], out["mask"], xf)).mean()       # :332
     total = enc_rec + rec + (out["vq"]["vq_loss"] + out["vq"]["kmeans_loss"])
-    glist = torch.autograd.grad(total, [leaf[k] for k in names], allow_unused=True)
+    dl, extra = 0.0, []
+    if distill is not None and distill["lam"] > 0.0:
+        hw, hb = _distill_leaves(distill)
+        dlt = distill_loss(out["enc"], hw, hb, distill["tau"], distill["lam"], distill.get("sharpen_T", 0.5),
+                           distill.get("conf_weight", False), distill.get("conf_thresh", 0.6))
+        total = total + dlt
+        dl, extra = float(dlt.detach()), [hw, hb]
+    glist = torch.autograd.grad(total, [leaf[k] for k in names] + extra, allow_unused=True)
     logs = {"total_loss": float(total.detach()), "enc_rec_loss": float(enc_rec.detach()), "reconstruct_loss": float(rec.detach()),
             "vq_loss": out["vq"]["vq_loss"], "kmeans_loss": out["vq"]["kmeans_loss"],
-            "number_of_populated_clusters": float(out["soft"].argmax(dim=-1).unique().numel()), "distill_loss": 0.0}
-    return logs, dict(zip(names, glist)), {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
+            "number_of_populated_clusters": float(out["soft"].argmax(dim=-1).unique().numel()), "distill_loss": dl}
+    grads = dict(zip(names, glist[:len(names)]))
+    if extra:
+        grads["head/fc.weight"], grads["head/fc.bias"] = glist[len(names)], glist[len(names) + 1]
+    return logs, grads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
 
 
 def adam_step_generic(p: Dict[str, Tensor], grads: Dict[str, Optional[Tensor]], state: Dict[str, dict], lr: float,
@@ -363,15 +397,27 @@ CON_LOG_KEYS = ("total_loss", "pos_similarity", "neg_similarity", "distill_loss"
 
 def contrastive_train_step(x_full: Tensor, p: Dict[str, Tensor], graph, latent_dim: int, edge_index: Tensor,
                            prm: AugParams, temperature: float = 0.1, loss_fn: str = "nce", tau_plus: float = 0.1,
-                           beta: float = 0.1):
-    """step_contrastive_distill forward + backward without teacher / labels."""
+                           beta: float = 0.1, distill: Optional[dict] = None):
+    """step_contrastive_distill forward + backward without labels; teacher off unless `distill` is given (the head sees
+    the row-normalised embedding of the MAIN view, training.py:533, 556-557)."""
     names = [k for k in p if k not in V.BUFFER_NAMES]
     leaf = {k: (v.detach().clone().requires_grad_(True) if k in names and v.dtype.is_floating_point else v) for k, v in p.items()}
     x, a, xa, aa = contrastive_views(x_full, edge_index, prm)
     z = V.encoder_forward(x, a, leaf, graph, latent_dim)
     za = V.encoder_forward(xa, aa, leaf, graph, latent_dim)
     loss, pos, neg = contrastive_loss(z, za, loss_fn, temperature, tau_plus, beta)
-    glist = torch.autograd.grad(loss, [leaf[k] for k in names], allow_unused=True)
-    logs = {"total_loss": float(loss), "pos_similarity": float(pos), "neg_similarity": float(neg), "distill_loss": 0.0,
-            "seperability": 0.0}
-    return logs, dict(zip(names, glist)), dict(z=z.detach(), z_aug=za.detach(), x=x, a=a, x_aug=xa, a_aug=aa)
+    dl, extra = 0.0, []
+    if distill is not None and distill["lam"] > 0.0:
+        hw, hb = _distill_leaves(distill)
+        # training.py:533, 556: z has been REASSIGNED to its row-normalised copy before `z_main = z`
+        dlt = distill_loss(torch.nn.functional.normalize(z, dim=1), hw, hb, distill["tau"], distill["lam"],
+                           distill.get("sharpen_T", 0.5), distill.get("conf_weight", False), distill.get("conf_thresh", 0.6))
+        loss = loss + dlt
+        dl, extra = float(dlt.detach()), [hw, hb]
+    glist = torch.autograd.grad(loss, [leaf[k] for k in names] + extra, allow_unused=True)
+    logs = {"total_loss": float(loss.detach()), "pos_similarity": float(pos.detach()), "neg_similarity": float(neg.detach()),
+            "distill_loss": dl, "seperability": 0.0}
+    grads = dict(zip(names, glist[:len(names)]))
+    if extra:
+        grads["head/fc.weight"], grads["head/fc.bias"] = glist[len(names)], glist[len(names) + 1]
+    return logs, grads, dict(z=z.detach(), z_aug=za.detach(), x=x, a=a, x_aug=xa, a_aug=aa)

@@ -29,6 +29,11 @@ from oracle.vade_oracle import default_adjacency, synthetic_windows  # noqa: E40
 M, L, T, U = refshim.load()
 
 VQ_CASES = {
+    # distill: teacher on — ctx.distill_head (DiscriminativeHead), tau_star, lambda_scheduler (training.py:341-370)
+    "distill": dict(T=25, N=14, D=8, K=6, B=16, seed=24, beta=1.0, kmeans=0.0,
+                    distill=dict(Kt=5, lam=0.7, T=0.5, conf_weight=False, thr=0.6)),
+    "distill_conf": dict(T=24, N=11, D=6, K=5, B=9, seed=25, beta=1.0, kmeans=0.0,
+                         distill=dict(Kt=4, lam=1.3, T=0.0, conf_weight=True, thr=0.3)),
     "cfg3r": dict(T=25, N=14, D=16, K=64, B=12, seed=21, beta=1.0, kmeans=0.0),
     "small_kmeans": dict(T=25, N=14, D=8, K=6, B=16, seed=22, beta=0.25, kmeans=1.0),
     "odd": dict(T=24, N=11, D=6, K=5, B=9, seed=23, beta=1.0, kmeans=0.0),
@@ -42,9 +47,39 @@ CON_CASES = {
     "hard": dict(T=50, N=14, D=8, B=16, seed=35, aug=dict(p_interp=0.6), loss="hard_dcl"),
     # p_noise=1: with the euclidean similarity a window that draws no augmentation has distance 0 to its own view and
     # the reference's sqrt backward turns every gradient into NaN (seen with p_noise=0.5, seed 36, step 2)
+    "distill": dict(T=50, N=14, D=8, B=16, seed=38, aug=dict(p_interp=0.6),
+                    distill=dict(Kt=5, lam=0.9, T=0.5, conf_weight=True, thr=0.25)),
     "euclid": dict(T=50, N=14, D=8, B=16, seed=36, aug=dict(p_interp=0.6, p_noise=1.0), loss="nce", sim="euclidean"),
     "dot_dcl": dict(T=24, N=11, D=6, B=9, seed=37, aug=dict(p_interp=0.6), loss="dcl", sim="dot"),
 }
+
+
+class _Lambda:
+    """stands in for the reference's lambda scheduler: only get_weight() is read by the step functions"""
+
+    def __init__(self, w):
+        self.w = float(w)
+
+    def get_weight(self):
+        return self.w
+
+
+def distill_ctx(c, out, n_windows, seed):
+    """ctx fields of the teacher-on step + the head module; everything the tests need goes into `out`."""
+    d = c.get("distill")
+    if d is None:
+        return {}, None
+    import deepof.clustering.teacher_model as TM
+    g = torch.Generator().manual_seed(9000 + seed)
+    tau = torch.softmax(2.0 * torch.randn(n_windows, d["Kt"], generator=g), dim=-1)
+    head = TM.DiscriminativeHead(c["D"], d["Kt"])
+    out["distill/tau_star"] = tau.numpy()
+    out["distill/meta"] = np.array([d["Kt"], d["lam"], d["T"], float(d["conf_weight"]), d["thr"]], dtype=np.float64)
+    for k, v in head.state_dict().items():
+        out["distill/p/" + k] = v.detach().numpy().copy()
+    ctx = dict(apply_distill=True, distill_head=head, tau_star=tau, lambda_scheduler=_Lambda(d["lam"]), distill_sharpen_T=d["T"],
+               distill_conf_weight=d["conf_weight"], distill_conf_thresh=d["thr"])
+    return ctx, head
 
 
 def two_animal_adjacency(n_half):
@@ -83,11 +118,13 @@ def run_vq(name, c):
         out["eval/loc_q"] = enc_rec.base_dist.base_dist.loc.numpy()
         out["eval/loc_e"] = rec.base_dist.base_dist.loc.numpy()
     lr = 1e-3
-    opt = L.build_optimizer_generic(model, None, base_lr=lr, weight_decay=1e-4)
+    dctx, head = distill_ctx(c, out, c["B"] + 5, c["seed"])
+    opt = L.build_optimizer_generic(model, head, base_lr=lr, weight_decay=1e-4)
     out["lr"] = np.array(lr)
     model.train()
-    ctx = types.SimpleNamespace(apply_distill=False)
-    idx = torch.arange(c["B"])
+    ctx = types.SimpleNamespace(**(dctx or dict(apply_distill=False)))
+    idx = torch.arange(c["B"]) if head is None else torch.randperm(c["B"] + 5)[:c["B"]]
+    out["idx"] = idx.numpy()
     for step in range(2):
         res = T.step_vqvae_distill(model, (x, a, idx), ctx)
         opt.zero_grad(set_to_none=True)
@@ -98,10 +135,16 @@ def run_vq(name, c):
             for k, prm in model.named_parameters():
                 if prm.grad is not None:
                     out["g/" + k] = prm.grad.detach().numpy().copy()
+            if head is not None:
+                for k, prm in head.named_parameters():
+                    out["distill/g/" + k] = prm.grad.detach().numpy().copy()
         torch.nn.utils.clip_grad_value_(model.parameters(), 0.75)
         opt.step()
     for k, v in model.state_dict().items():
         out["p2/" + k] = v.detach().numpy().copy()
+    if head is not None:
+        for k, v in head.state_dict().items():
+            out["distill/p2/" + k] = v.detach().numpy().copy()
     path = os.path.join(HERE, f"vqvae_{name}.npz")
     np.savez_compressed(path, **out)
     print("vqvae", name, "%.1f KB" % (os.path.getsize(path) / 1024), {k: round(v, 5) for k, v in res.logs.items()})
@@ -137,11 +180,14 @@ def run_con(name, c):
     for k, v in model.state_dict().items():
         out["p/" + k] = v.detach().numpy().copy()
     lr = 1e-3
-    opt = L.build_optimizer_generic(model, None, base_lr=lr, weight_decay=1e-4)
+    dctx, head = distill_ctx(c, out, c["B"] + 5, c["seed"])
+    opt = L.build_optimizer_generic(model, head, base_lr=lr, weight_decay=1e-4)
     out["lr"] = np.array(lr)
     model.train()
-    ctx = types.SimpleNamespace(apply_distill=False, edge_index=eg, edge_index_local=el, contrastive_cfg=ccfg, rot_precomp=rot)
-    idx = torch.arange(c["B"])
+    ctx = types.SimpleNamespace(**{**(dctx or dict(apply_distill=False)), "edge_index": eg, "edge_index_local": el,
+                                   "contrastive_cfg": ccfg, "rot_precomp": rot})
+    idx = torch.arange(c["B"]) if head is None else torch.randperm(c["B"] + 5)[:c["B"]]
+    out["idx"] = idx.numpy()
     seen = []
     orig_forward = model.forward
 
@@ -168,10 +214,16 @@ def run_con(name, c):
             for k, prm in model.named_parameters():
                 if prm.grad is not None:
                     out["g/" + k] = prm.grad.detach().numpy().copy()
+            if head is not None:
+                for k, prm in head.named_parameters():
+                    out["distill/g/" + k] = prm.grad.detach().numpy().copy()
         torch.nn.utils.clip_grad_value_(model.parameters(), 0.75)
         opt.step()
     for k, v in model.state_dict().items():
         out["p2/" + k] = v.detach().numpy().copy()
+    if head is not None:
+        for k, v in head.state_dict().items():
+            out["distill/p2/" + k] = v.detach().numpy().copy()
     path = os.path.join(HERE, f"contrastive_{name}.npz")
     np.savez_compressed(path, **out)
     print("contrastive", name, "%.1f KB" % (os.path.getsize(path) / 1024), {k: round(v, 5) for k, v in res.logs.items()})

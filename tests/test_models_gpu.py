@@ -76,16 +76,59 @@ def test_vqvae_eval_vs_reference_golden(case):
     assert torch.equal(out[3], soft) and torch.equal(out[4], enc)                    # reference tuple positions [3], [4]
 
 
+class _Lambda:
+    def __init__(self, w):
+        self.w = w
+
+    def get_weight(self):
+        return self.w
+
+    def step(self):
+        pass
+
+
+def _distill_ctx(g):
+    """Teacher-on goldens (distill/*): the ctx fields step_*_distill reads, with a DistillHeadB200 holding the
+    reference head's parameters.  Teacher-off goldens give apply_distill=False."""
+    from types import SimpleNamespace
+    from deepof_b200 import DistillHeadB200
+    if "distill/meta" not in g:
+        return SimpleNamespace(apply_distill=False), None
+    Kt, lam, Tsh, cw, thr = (float(v) for v in g["distill/meta"])
+    D = g["distill/p/fc.weight"].shape[1]
+    head = DistillHeadB200(D, int(Kt))
+    head.load_state_dict(sub(g, "distill/p/"))
+    ctx = SimpleNamespace(apply_distill=True, distill_head=head, tau_star=torch.from_numpy(g["distill/tau_star"]),
+                          lambda_scheduler=_Lambda(lam), distill_sharpen_T=Tsh, distill_conf_weight=bool(cw),
+                          distill_conf_thresh=thr)
+    return ctx, head
+
+
+def _check_head(head, g, lr, step, bad):
+    if step == 0:
+        for k, v in head.grad_dict().items():
+            if rel_l2(v.cpu(), g["distill/g/" + k]) > 1e-4:
+                bad.append(("head grad", k, rel_l2(v.cpu(), g["distill/g/" + k])))
+    head.adam_step(lr)                                                      # same Adam, weight_decay 1e-4, NOT clipped
+    if step == 1:
+        for k, v in head.state_dict().items():
+            ref = torch.from_numpy(g["distill/p2/" + k])
+            assert float((v.cpu() - ref).abs().max()) <= 0.1 * lr and rel_l2(v.cpu(), ref) < 1e-4, k
+
+
 @pytest.mark.parametrize("case", VQ)
 def test_vqvae_two_training_steps_vs_reference_golden(case):
+    from deepof_b200 import step_vqvae_distill
     from deepof_b200.models import VQ_LOG_KEYS
     g = load_golden_of("vqvae", case)
     m = _vq_model(g)
     x, a = torch.from_numpy(g["x"]), torch.from_numpy(g["a"])
+    idx = torch.from_numpy(g["idx"]) if "idx" in g else torch.arange(x.shape[0])
+    ctx, head = _distill_ctx(g)
     lr = float(g["lr"])
     bad = []
     for step in range(2):
-        m.loss_grad(x, a)
+        step_vqvae_distill(m, (x, a, idx), ctx)
         logs = m.logs_dict()
         for k in VQ_LOG_KEYS:
             ref = float(g[f"s{step}/log/{k}"])
@@ -94,6 +137,8 @@ def test_vqvae_two_training_steps_vs_reference_golden(case):
         if step == 0:
             _check_grads(m, sub(g, "g/"), bad, case)
         m.adam_step(lr)
+        if head is not None:
+            _check_head(head, g, lr, step, bad)
     assert not bad, bad
     _check_params(m, sub(g, "p2/"), lr)
 
@@ -171,14 +216,17 @@ def test_contrastive_two_training_steps_vs_reference_golden(case):
     # the rotation table the product builds == the reference's (same triplets / branches)
     rot = MO.rotation_table(g["edge_index_local"], N)
     assert m.rotations.triplets == rot.triplets and m.rotations.branches_a == rot.branches_a and m.rotations.branches_c == rot.branches_c
+    from deepof_b200 import step_contrastive_distill
     x_full = torch.from_numpy(g["x_full"])
+    idx = torch.from_numpy(g["idx"]) if "idx" in g else torch.arange(B)
+    ctx, head = _distill_ctx(g)
     cfg = _aug_cfg(g, MO.AugCfg)
     lr = float(g["lr"])
     bad = []
     for step in range(2):
         torch.manual_seed(int(g[f"s{step}/seed"]))                      # replay the reference's draws (CPU generator)
-        prm = _to_product_params(MO.draw_aug_params(B, Tf, N, cfg, rot))
-        m.loss_grad(x_full, prm)
+        ctx.aug_params = _to_product_params(MO.draw_aug_params(B, Tf, N, cfg, rot))
+        step_contrastive_distill(m, (x_full, None, idx), ctx)
         x2, a2 = m._x2[:2 * B].cpu(), m._a2[:2 * B].cpu()
         for name, got in (("x", x2[:B]), ("a", a2[:B]), ("x_aug", x2[B:]), ("a_aug", a2[B:])):
             np.testing.assert_allclose(got.numpy(), g[f"s{step}/{name}"], rtol=0, atol=1e-5, err_msg=f"{case} {name}")
@@ -192,6 +240,8 @@ def test_contrastive_two_training_steps_vs_reference_golden(case):
         if step == 0:
             _check_grads(m, sub(g, "g/"), bad, case)
         m.adam_step(lr)
+        if head is not None:
+            _check_head(head, g, lr, step, bad)
     assert not bad, bad
     _check_params(m, sub(g, "p2/"), lr)
     # ContrastivePT.forward on half windows == the z of the main view

@@ -39,6 +39,24 @@ def _check_params(p, p2, lr=1e-3):
             assert rel_l2(p[k], p2[k]) < 5e-5, k
 
 
+def _distill_of(g, hp):
+    """Teacher-on goldens carry distill/*: the oracle's `distill` argument for the current head parameters."""
+    if "distill/meta" not in g:
+        return None
+    Kt, lam, Tsh, cw, thr = (float(v) for v in g["distill/meta"])
+    tau = torch.from_numpy(g["distill/tau_star"])[torch.from_numpy(g["idx"]).long()]
+    return dict(head_w=hp["fc.weight"], head_b=hp["fc.bias"], tau=tau, lam=lam, sharpen_T=Tsh, conf_weight=bool(cw), conf_thresh=thr)
+
+
+def _head_step(g, hp, grads, hstate, step):
+    """gradient of the head after step 0, then its Adam step: same optimizer, but NOT clipped (training.py:165)."""
+    hg = {"fc.weight": grads.pop("head/fc.weight"), "fc.bias": grads.pop("head/fc.bias")}
+    if step == 0:
+        for k, v in hg.items():
+            assert rel_l2(v, g["distill/g/" + k]) < 1e-5, k
+    MO.adam_step_generic(hp, hg, hstate, float(g["lr"]), clip=None)
+
+
 @pytest.mark.parametrize("case", VQ)
 def test_vqvae_eval_and_two_steps(case):
     g = load_golden_of("vqvae", case)
@@ -54,16 +72,20 @@ def test_vqvae_eval_and_two_steps(case):
     assert rel_l2(out["soft"], g["eval/soft"]) < 2e-5
     assert rel_l2(out["quant"], g["eval/quant"]) < 1e-6
     assert rel_l2(out["loc_q"], g["eval/loc_q"]) < 5e-6 and rel_l2(out["loc_e"], g["eval/loc_e"]) < 5e-6
-    state = {}
+    state, hstate, hp = {}, {}, sub(g, "distill/p/")
     for step in range(2):
-        logs, grads, _ = MO.vqvae_train_step(x, a, p, graph, D, beta, km)
+        logs, grads, _ = MO.vqvae_train_step(x, a, p, graph, D, beta, km, distill=_distill_of(g, hp))
         for k in MO.VQ_LOG_KEYS:
             ref = float(g[f"s{step}/log/{k}"])
             assert abs(logs[k] - ref) <= 2e-5 * max(1.0, abs(ref)), (step, k, logs[k], ref)
+        if hp:
+            _head_step(g, hp, grads, hstate, step)
         if step == 0:
             _check_grads(grads, sub(g, "g/"), p, D)
         MO.adam_step_generic(p, grads, state, float(g["lr"]))
     _check_params(p, sub(g, "p2/"))
+    if hp:
+        _check_params(hp, sub(g, "distill/p2/"))
 
 
 def _aug_cfg(g):
@@ -85,7 +107,7 @@ def test_contrastive_views_and_two_steps(case, monkeypatch):
     graph = O.graph_operators(g["adjacency"])
     rot = MO.rotation_table(g["edge_index_local"], N)
     cfg = _aug_cfg(g)
-    state = {}
+    state, hstate, hp = {}, {}, sub(g, "distill/p/")
     monkeypatch.setattr(MO, "SIMILARITY", str(g["similarity_function"]) if "similarity_function" in g else "cosine")
     for step in range(2):
         torch.manual_seed(int(g[f"s{step}/seed"]))
@@ -93,7 +115,8 @@ def test_contrastive_views_and_two_steps(case, monkeypatch):
         logs, grads, out = MO.contrastive_train_step(x_full, p, graph, D, ei, prm, float(g["temperature"]),
                                                      loss_fn=str(g["loss_function"]) if "loss_function" in g else "nce",
                                                      tau_plus=float(g["tau"]) if "tau" in g else 0.1,
-                                                     beta=float(g["beta"]) if "beta" in g else 0.1)
+                                                     beta=float(g["beta"]) if "beta" in g else 0.1,
+                                                     distill=_distill_of(g, hp))
         # the four tensors the reference fed its encoder
         for k in ("x", "a", "x_aug", "a_aug"):
             np.testing.assert_allclose(out[k].numpy(), g[f"s{step}/{k}"], rtol=0, atol=2e-6, err_msg=k)
@@ -101,7 +124,11 @@ def test_contrastive_views_and_two_steps(case, monkeypatch):
         for k in MO.CON_LOG_KEYS:
             ref = float(g[f"s{step}/log/{k}"])
             assert abs(logs[k] - ref) <= 2e-5 * max(1.0, abs(ref)), (step, k, logs[k], ref)
+        if hp:
+            _head_step(g, hp, grads, hstate, step)
         if step == 0:
             _check_grads(grads, sub(g, "g/"), p, D)
         MO.adam_step_generic(p, grads, state, float(g["lr"]))
     _check_params(p, sub(g, "p2/"))
+    if hp:
+        _check_params(hp, sub(g, "distill/p2/"))
