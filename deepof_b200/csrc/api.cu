@@ -1137,9 +1137,23 @@ static int ntx_launch(const NtxArgs& n, int B, cudaStream_t st) {
     }
     const int nb = cdiv(B, NTX_WARPS);
     const double fl = 2.0 * B * (double)B * n.D;
-    { ProfScope ps("ntxent_rows", st, fl, 0.0);
-    ntx_kernel<0, DP><<<nb, NTX_WARPS * 32, smem, st>>>(n); }
-    DOF_LAUNCH_CHECK();
+    if (n.kind == 3) {
+        // fc: every active warp keeps its row of B similarities in shared memory
+        const int bpad = round_up(B, 32);
+        const size_t base = ((size_t)NTX_TILE * (DP + 1) + (size_t)NTX_WARPS * DP) * 4;
+        int rw = (int)((200 * 1024 - base) / ((size_t)bpad * 4));
+        if (rw > NTX_WARPS) rw = NTX_WARPS;
+        if (rw < 1) DOF_FAIL(DOF_ERR_UNSUPPORTED, "fc loss: batch %d does not fit the per-row shared-memory buffer", B);
+        const size_t fsmem = base + (size_t)rw * bpad * 4;
+        DOF_CUDA(cudaFuncSetAttribute(ntx_fc_rows_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        { ProfScope ps("ntxent_fc_rows", st, fl, 0.0);
+        ntx_fc_rows_kernel<DP><<<cdiv(B, rw), NTX_WARPS * 32, fsmem, st>>>(n, rw, bpad); }
+        DOF_LAUNCH_CHECK();
+    } else {
+        { ProfScope ps("ntxent_rows", st, fl, 0.0);
+        ntx_kernel<0, DP><<<nb, NTX_WARPS * 32, smem, st>>>(n); }
+        DOF_LAUNCH_CHECK();
+    }
     { ProfScope ps("ntxent_grad", st, 4.0 * fl, 0.0);
     ntx_kernel<1, DP><<<2 * nb, NTX_WARPS * 32, smem, st>>>(n); }
     DOF_LAUNCH_CHECK();
@@ -1166,8 +1180,8 @@ int dof_contrastive_loss_grad_distill(dof_handle* h, const float* state, float* 
     if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
     if (!state || !grad || !x2 || !a2 || !logs || !(temperature > 0.f)) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
     if (sim_kind < 0 || sim_kind > 1) DOF_FAIL(DOF_ERR_UNSUPPORTED, "similarity kind %d (0 cosine / dot, 1 euclidean / edit)", sim_kind);
-    if (loss_kind < 0 || loss_kind > 2) DOF_FAIL(DOF_ERR_UNSUPPORTED, "contrastive loss kind %d (0 nce, 1 dcl, 2 hard_dcl)", loss_kind);
-    if (loss_kind > 0 && !(tau_plus >= 0.f && tau_plus < 1.f)) DOF_FAIL(DOF_ERR_ARG, "tau_plus must be in [0, 1)");
+    if (loss_kind < 0 || loss_kind > 3) DOF_FAIL(DOF_ERR_UNSUPPORTED, "contrastive loss kind %d (0 nce, 1 dcl, 2 hard_dcl, 3 fc)", loss_kind);
+    if ((loss_kind == 1 || loss_kind == 2) && !(tau_plus >= 0.f && tau_plus < 1.f)) DOF_FAIL(DOF_ERR_ARG, "tau_plus must be in [0, 1)");
     if (c.D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 64", c.D);
     cudaStream_t st = (cudaStream_t)stream;
     DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)h->L.total * 4, st));

@@ -244,7 +244,7 @@ struct NtxArgs {
     float* nrm;         // [2B]
     float* lse;         // [4,B] per-row coefficients of the gradient pass: m_i | A_i | P_i | Dg_i with
                         //   d loss_i / d s_ij = e_ij (A_i + P_i e_ij), e_ij = exp(s_ij - m_i), for j != i;  Dg_i for j == i
-    int kind;           // 0 nce (losses.py:130-141), 1 dcl debiased (:144-173), 2 hard_dcl debiased (:213-249)
+    int kind;           // 0 nce (losses.py:130-141), 1 dcl debiased (:144-173), 2 hard_dcl debiased (:213-249), 3 fc (:176-210)
     int sim;            // 0 cosine / dot on the normalised rows (losses.py:59-67), 1 euclidean / edit 1/(1+|x-y|) (:70-82)
     float tau_plus, beta, temperature;
     float* denc;        // [2B, D] gradient wrt enc
@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
                             rD = col ? tl[3 * NTX_TILE + r] : my_D;
                 const float e = __expf(s - rm);
                 float g = (j0 + r == self) ? rD : e * (rA + rP * e);
+                if (a.kind == 3) g = (j0 + r == self) ? rD : (s < rP ? e * rA : 0.f);     // fc: rP carries the row's cut value
                 g *= gs;
                 if (a.sim != 0) {
                     // d sim / d mine = -(mine - other) / ((1 + dist)^2 dist): accumulate w*other and sum(w)
@@ -406,6 +407,109 @@ __global__ void __launch_bounds__(NTX_WARPS * 32) ntx_kernel(const NtxArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// fc_loss_pt (losses.py:176-210): per row the k = ceil(0.1 N) LARGEST negatives are eliminated, the rest enter
+// -log(pos / (pos + sum exp(neg))).  One warp per row keeps the row's N similarities in shared memory and finds the
+// k-th largest by a 32-step bisection on the order-preserving integer image of the floats (exact, no sort); the
+// gradient pass (ntx_kernel<1>, kind 3) recomputes s_ij with the same arithmetic and keeps s_ij < cut_i.
+// Rows whose k-th and (k+1)-th largest negatives are bit-identical keep the loss exact (ties are counted) but give
+// the tied entries no gradient.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int fc_drop_count(int N) {
+    int k = (int)ceil(0.1 * (double)N);          // elimination_topk = 0.1 at the call site (training.py:545); Python float == double
+    return k == 0 ? 1 : k;
+}
+__device__ __forceinline__ unsigned fc_key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+template <int DP>
+__global__ void __launch_bounds__(NTX_WARPS * 32) ntx_fc_rows_kernel(const NtxArgs a, int rw, int bpad) {
+    extern __shared__ float nsm[];
+    const int D = a.D, B = a.B, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = nsm;                               // [NTX_TILE][DP+1]
+    float* mine = tile + NTX_TILE * (DP + 1) + warp * DP;
+    float* sv = tile + NTX_TILE * (DP + 1) + NTX_WARPS * DP + (size_t)warp * bpad;     // this warp's row of similarities
+    const int self = (int)blockIdx.x * rw + warp;
+    const bool active = warp < rw && self < B;
+    const float* other = a.zn + (size_t)B * D;
+    if (active) for (int d = lane; d < D; d += 32) mine[d] = a.zn[(size_t)self * D + d];
+    __syncwarp();
+    float sdiag = 0.f;
+    for (int j0 = 0; j0 < B; j0 += NTX_TILE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < NTX_TILE * D; i += blockDim.x) {
+            const int r = i / D, d = i - r * D;
+            tile[r * (DP + 1) + d] = (j0 + r < B) ? other[(size_t)(j0 + r) * D + d] : 0.f;
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int r = lane; r < NTX_TILE && j0 + r < B; r += 32) {
+            const float* tr = tile + r * (DP + 1);
+            float dot = 0.f, sim;
+            if (a.sim == 0) {
+#pragma unroll
+                for (int d = 0; d < DP; d++) if (d < D) dot += mine[d] * tr[d];
+                sim = dot;
+            } else {
+#pragma unroll
+                for (int d = 0; d < DP; d++) if (d < D) { const float df = mine[d] - tr[d]; dot += df * df; }
+                sim = 1.0f / (1.0f + sqrtf(fmaxf(dot, 0.f)));
+            }
+            const float s = sim * a.inv_tau;
+            if (j0 + r == self) { sdiag = s; sv[j0 + r] = -INFINITY; }     // the positive never competes with the negatives
+            else sv[j0 + r] = s;
+        }
+    }
+    if (!active) return;
+    __syncwarp();
+    sdiag = warp_sum(sdiag);
+    const int kdrop = fc_drop_count(B), keep = B - 1 - kdrop;
+    float cut = -INFINITY;                                                  // kept iff s < cut
+    double negsum = 0.0, trim = 0.0;                                        // sum exp(s - m), sum s over the kept negatives
+    float m = sdiag;
+    if (keep > 0) {
+        unsigned K = 0;
+        for (int bit = 31; bit >= 0; bit--) {
+            const unsigned cand = K | (1u << bit);
+            int cnt = 0;
+            for (int j = lane; j < B; j += 32) cnt += fc_key(sv[j]) >= cand;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt >= kdrop) K = cand;
+        }
+        int ngt = 0, neq = 0;
+        float vcut = -INFINITY;
+        for (int j = lane; j < B; j += 32) {
+            const unsigned k = fc_key(sv[j]);
+            ngt += k > K; neq += k == K;
+            if (k == K) vcut = sv[j];
+        }
+        ngt = __reduce_add_sync(0xffffffffu, ngt);
+        neq = __reduce_add_sync(0xffffffffu, neq);
+        cut = warp_max(vcut);
+        m = fmaxf(sdiag, cut);
+        float ns = 0.f, ts = 0.f;
+        for (int j = lane; j < B; j += 32) {
+            const float s = sv[j];
+            if (j != self && s < cut) { ns += __expf(s - m); ts += s; }
+        }
+        negsum = (double)warp_sum(ns);
+        trim = (double)warp_sum(ts);
+        const int keep_eq = neq - (kdrop - ngt);                            // copies of the cut value that survive
+        negsum += (double)keep_eq * exp((double)cut - (double)m);
+        trim += (double)keep_eq * (double)cut;
+    }
+    if (lane == 0) {
+        const double pos = exp((double)sdiag - (double)m), den = pos + negsum;
+        const double loss = (double)m + log(den) - (double)sdiag;
+        a.lse[self] = m; a.lse[B + self] = (float)(1.0 / den); a.lse[2 * B + self] = cut; a.lse[3 * B + self] = (float)(-negsum / den);
+        atomicAdd(a.stats + NTX_ST_LOSS, loss);
+        atomicAdd(a.stats + NTX_ST_POS, (double)sdiag);
+        atomicAdd(a.stats + NTX_ST_ALL, trim);
+    }
+}
+
 // logs: 0 total 1 pos_similarity 2 neg_similarity 3 distill 4 seperability (training.py:582-588)
 __global__ void ntx_finalize_kernel(const NtxArgs a, float tau, float lambda_distill) {
     const double B = (double)a.B;
@@ -413,6 +517,10 @@ __global__ void ntx_finalize_kernel(const NtxArgs a, float tau, float lambda_dis
     a.logs[0] = (float)(a.stats[NTX_ST_LOSS] / B + dist);
     a.logs[1] = (float)(a.stats[NTX_ST_POS] / B * tau);
     a.logs[2] = a.B > 1 ? (float)((a.stats[NTX_ST_ALL] - a.stats[NTX_ST_POS]) * tau / (B * (B - 1.0))) : 0.f;
+    if (a.kind == 3) {                                                   // fc: mean of the KEPT negatives (losses.py:207)
+        const int keep = a.B - 1 - fc_drop_count(a.B);
+        a.logs[2] = keep > 0 ? (float)(a.stats[NTX_ST_ALL] * tau / (B * (double)keep)) : 0.f;
+    }
     a.logs[3] = (float)dist;
     a.logs[4] = 0.f;
 }

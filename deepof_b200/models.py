@@ -226,9 +226,9 @@ class ContrastiveB200(VaDEB200):
                  encoder_type: str = "recurrent", use_gnn: bool = True, temperature: float = 0.1,
                  similarity_function: str = "cosine", loss_function: str = "nce", beta: float = 0.1, tau: float = 0.1,
                  edge_index=None, edge_index_local=None, max_batch: int = 4096, **kw):
-        if similarity_function not in ("cosine", "dot", "euclidean", "edit") or loss_function not in ("nce", "dcl", "hard_dcl"):
+        if similarity_function not in ("cosine", "dot", "euclidean", "edit") or loss_function not in ("nce", "dcl", "hard_dcl", "fc"):
             raise NotImplementedError("deepof_b200 implements the cosine / dot / euclidean / edit similarities with the nce / "
-                                      f"dcl / hard_dcl losses (got {similarity_function!r}, {loss_function!r}); fc is not built")
+                                      f"dcl / hard_dcl / fc losses (got {similarity_function!r}, {loss_function!r})")
         self.similarity_function = similarity_function
         self.loss_function, self.beta, self.tau = loss_function, float(beta), float(tau)
         Tf, N, F = (int(v) for v in input_shape)
@@ -346,7 +346,7 @@ class ContrastiveB200(VaDEB200):
             raise _lib.DofError("model was created with training=False")
         x2, a2 = self.views(x_full, prm)
         B = x2.shape[0] // 2
-        kind = {"nce": 0, "dcl": 1, "hard_dcl": 2}[self.loss_function]
+        kind = {"nce": 0, "dcl": 1, "hard_dcl": 2, "fc": 3}[self.loss_function]
         sim = 0 if self.similarity_function in ("cosine", "dot") else 1
         dc = distill.cfg(B) if distill is not None and distill.lambda_distill > 0.0 else None
         check(self.L.dof_contrastive_loss_grad_distill(self.handle, ptr(self.state), ptr(self.grad), ptr(x2), ptr(a2), B, kind, sim,

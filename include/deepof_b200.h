@@ -263,7 +263,8 @@ int dof_contrastive_views(const dof_views_cfg* v, const float* x_full, int B, fl
  * z = encoder(main view), z_aug = encoder(augmented view) (one pass over the 2B windows: the handle needs
  * max_batch >= 2B), F.normalize, cosine similarity / temperature, cross-entropy against the diagonal
  * (loss_kind 0: nce_loss_pt, deepof/clustering/losses.py:130-141), or the debiased losses on the same similarities:
- * loss_kind 1 dcl_loss_pt (losses.py:144-173, tau_plus), 2 hard_loss_pt (losses.py:213-249, tau_plus, beta);
+ * loss_kind 1 dcl_loss_pt (losses.py:144-173, tau_plus), 2 hard_loss_pt (losses.py:213-249, tau_plus, beta),
+ * 3 fc_loss_pt (losses.py:176-210, the ceil(0.1 B) largest negatives of every row eliminated);
  * sim_kind 0 cosine / dot (losses.py:59-67), 1 euclidean / edit = 1 / (1 + |x - y|) (losses.py:70-82).  logs: 0 total_loss 1 pos_similarity 2 neg_similarity
  * 3 distill_loss (= 0) 4 seperability (= 0).  z_out [2B,D] (may be NULL) receives the raw encoder outputs. */
 int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,

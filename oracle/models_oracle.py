@@ -381,6 +381,21 @@ def hard_loss(z: Tensor, z_aug: Tensor, temperature: float, tau_plus: float, bet
     return loss, torch.diag(sim).mean(), neg.mean()
 
 
+def fc_loss(z: Tensor, z_aug: Tensor, temperature: float, elimination_topk: float = 0.1):
+    """fc_loss_pt (losses.py:176-210): the k = ceil(min(topk, 0.5) N) largest negatives of every row are dropped."""
+    n = z.shape[0]
+    k = int(math.ceil(min(elimination_topk, 0.5) * n)) or 1
+    sim = _cos_sim(z, z_aug) / temperature
+    pos = torch.exp(torch.diag(sim))
+    mask = ~torch.eye(n, dtype=torch.bool)
+    neg_raw = sim[mask].reshape(n, n - 1)                                  # _off_diagonal_rows, losses.py:91-101
+    trimmed = torch.sort(neg_raw, dim=1).values[:, :max(n - 1 - k, 0)]
+    neg = torch.exp(trimmed).sum(dim=1) if trimmed.numel() > 0 else torch.zeros(n)
+    loss = (-torch.log(pos / (pos + neg))).mean()
+    mean_neg = trimmed.mean() * temperature if trimmed.numel() > 0 else torch.tensor(0.0)
+    return loss, torch.diag(sim).mean() * temperature, mean_neg
+
+
 def contrastive_loss(z, z_aug, loss_fn: str, temperature: float, tau_plus: float = 0.1, beta: float = 0.1):
     """select_contrastive_loss_pt (losses.py:35-56) for the cosine similarity."""
     if loss_fn == "nce":
@@ -389,6 +404,8 @@ def contrastive_loss(z, z_aug, loss_fn: str, temperature: float, tau_plus: float
         return dcl_loss(z, z_aug, temperature, tau_plus)
     if loss_fn == "hard_dcl":
         return hard_loss(z, z_aug, temperature, tau_plus, beta)
+    if loss_fn == "fc":
+        return fc_loss(z, z_aug, temperature)
     raise ValueError(loss_fn)
 
 

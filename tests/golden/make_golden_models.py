@@ -49,6 +49,8 @@ CON_CASES = {
     # the reference's sqrt backward turns every gradient into NaN (seen with p_noise=0.5, seed 36, step 2)
     "distill": dict(T=50, N=14, D=8, B=16, seed=38, aug=dict(p_interp=0.6),
                     distill=dict(Kt=5, lam=0.9, T=0.5, conf_weight=True, thr=0.25)),
+    "fc": dict(T=50, N=14, D=8, B=16, seed=39, aug=dict(p_interp=0.6), loss="fc"),
+    "fc_euclid": dict(T=24, N=11, D=6, B=9, seed=40, aug=dict(p_interp=0.6, p_noise=1.0, max_shift=3), loss="fc", sim="euclidean"),
     "euclid": dict(T=50, N=14, D=8, B=16, seed=36, aug=dict(p_interp=0.6, p_noise=1.0), loss="nce", sim="euclidean"),
     "dot_dcl": dict(T=24, N=11, D=6, B=9, seed=37, aug=dict(p_interp=0.6), loss="dcl", sim="dot"),
 }

@@ -276,9 +276,9 @@ def test_contrastive_vs_oracle_multi_tile_batch():
     assert not bad, bad
 
 
-@pytest.mark.parametrize("loss_fn,beta", [("dcl", 0.1), ("hard_dcl", 0.1), ("hard_dcl", 0.0), ("hard_dcl", 1.0)])
+@pytest.mark.parametrize("loss_fn,beta", [("dcl", 0.1), ("hard_dcl", 0.1), ("hard_dcl", 0.0), ("hard_dcl", 1.0), ("fc", 0.1)])
 def test_contrastive_debiased_losses_vs_oracle(loss_fn, beta):
-    """dcl / hard_dcl (losses.py:144-249) on a multi-tile batch, incl. beta = 0 (no re-weighting)."""
+    """dcl / hard_dcl / fc (losses.py:144-249) on a multi-tile batch, incl. beta = 0 (no re-weighting)."""
     from deepof_b200 import ContrastiveB200
     Tf, N, D, B = 50, 14, 16, 200
     adj = O.default_adjacency(N)
@@ -303,7 +303,8 @@ def test_contrastive_debiased_losses_vs_oracle(loss_fn, beta):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("sim,loss_fn", [("dot", "nce"), ("euclidean", "nce"), ("edit", "dcl"), ("euclidean", "hard_dcl")])
+@pytest.mark.parametrize("sim,loss_fn", [("dot", "nce"), ("euclidean", "nce"), ("edit", "dcl"), ("euclidean", "hard_dcl"),
+                                         ("euclidean", "fc")])
 def test_contrastive_similarities_vs_oracle(sim, loss_fn):
     """dot / euclidean / edit similarities (losses.py:66-89) under the three losses."""
     from deepof_b200 import ContrastiveB200
