@@ -65,6 +65,10 @@ class DofDistillCfg(C.Structure):
                 ("lambda_", C.c_float), ("sharpen_T", C.c_float), ("conf_weight", C.c_int), ("conf_thresh", C.c_float)]
 
 
+class DofTfmCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("T", "N", "E", "F", "Fe", "D", "key_dim", "heads", "dff", "layers")]
+
+
 class DofError(RuntimeError):
     pass
 
@@ -97,6 +101,12 @@ _SIGS = {
     "dof_vqvae_loss_grad_distill": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.POINTER(DofDistillCfg), _P, _P]),
     "dof_contrastive_loss_grad_distill": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                                     C.POINTER(DofDistillCfg), _P, _P, _P]),
+    "dof_tfm_numel": (C.c_int64, [C.POINTER(DofTfmCfg)]),
+    "dof_tfm_num_entries": (C.c_int, [C.POINTER(DofTfmCfg)]),
+    "dof_tfm_entry": (C.c_int, [C.POINTER(DofTfmCfg), C.c_int, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dof_tfm_workspace_bytes": (C.c_size_t, [C.POINTER(DofTfmCfg), C.c_int]),
+    "dof_tfm_encode": (C.c_int, [C.POINTER(DofTfmCfg), _P, _P, _P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P]),
     "dof_adam_flat": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                 C.c_float, _P]),
     "dof_contrastive_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P,

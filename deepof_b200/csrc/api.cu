@@ -16,6 +16,7 @@
 #include "loss.cuh"
 #include "loader.cuh"
 #include "models.cuh"
+#include "tfm.cuh"
 
 thread_local char g_dof_err[512] = {0};
 DofProf g_prof;
@@ -1120,6 +1121,195 @@ int dof_contrastive_views(const dof_views_cfg* v, const float* x_full, int B, fl
     int grid = cdiv(total, 128) < g_sm_count * 16 ? cdiv(total, 128) : g_sm_count * 16;
     { ProfScope ps("views", (cudaStream_t)stream, 0.0, (double)B * (1.5 * a.Tf * a.N * 3 * 4 + 2.0 * a.Th * (3 * a.N + a.E) * 4));
     views_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+}  // extern "C"
+
+// ---- transformer encoder, eval forward (tfm.cuh) ---------------------------------------------------------------
+struct TfmLayout {
+    std::vector<Entry> e;
+    int64_t total = 0;
+    int64_t lap, elap, inc, core[2], node_kernel, edge_kernel, node_weights, edge_weights, node_bias, edge_bias;
+    int64_t w0, b0, bn2, w3, b3, bn5, w6, b6;
+};
+
+static int64_t tfm_add(TfmLayout& L, const std::string& name, int d0, int d1 = -1) {
+    Entry en;
+    en.name = name; en.off = L.total; en.group = 1;
+    en.shape[0] = d0; en.shape[1] = d1 < 0 ? 0 : d1; en.shape[2] = en.shape[3] = 0;
+    en.ndim = d1 < 0 ? 1 : 2;
+    en.numel = d1 < 0 ? d0 : (int64_t)d0 * d1;
+    L.total += en.numel;
+    L.e.push_back(en);
+    return en.off;
+}
+
+static int check_tfm_cfg(const dof_tfm_cfg* c) {
+    if (!c) DOF_FAIL(DOF_ERR_ARG, "null config");
+    if (c->T < 1 || c->N < 1 || c->E < 1 || c->F < 1 || c->Fe < 1 || c->D < 1 || c->key_dim < 1 || c->heads < 1 || c->dff < 1 || c->layers < 1)
+        DOF_FAIL(DOF_ERR_ARG, "bad transformer geometry");
+    if (c->key_dim % c->heads) DOF_FAIL(DOF_ERR_ARG, "key_dim %d is not a multiple of heads %d", c->key_dim, c->heads);
+    if (c->T > TFM_MAXT) DOF_FAIL(DOF_ERR_UNSUPPORTED, "window length %d > %d", c->T, TFM_MAXT);
+    if (tfm_core_smem_bytes(c->T, c->F > c->Fe ? c->F : c->Fe, c->key_dim, c->dff, 1) > 220 * 1024)
+        DOF_FAIL(DOF_ERR_UNSUPPORTED, "one transformer layer (key_dim %d, dff %d, T %d) does not fit shared memory", c->key_dim, c->dff, c->T);
+    return DOF_OK;
+}
+
+// reference state_dict order of TFMEncoderPT after its first forward (the CensNet parameters are built lazily);
+// the integer num_batches_tracked buffers are not part of the flat float state
+static TfmLayout build_tfm_layout(const dof_tfm_cfg& c) {
+    TfmLayout L;
+    const int N = c.N, E = c.E, D = c.D, dk = c.key_dim;
+    L.lap = tfm_add(L, "laplacian", N, N);
+    L.elap = tfm_add(L, "edge_laplacian", E, E);
+    L.inc = tfm_add(L, "incidence", N, E);
+    const char* cn[2] = {"node_tf.", "edge_tf."};
+    for (int b = 0; b < 2; b++) {
+        std::string p = cn[b];
+        L.core[b] = tfm_add(L, p + "embed.weight", dk, b == 0 ? c.F : c.Fe);
+        tfm_add(L, p + "embed.bias", dk);
+        for (int l = 0; l < c.layers; l++) {
+            std::string q = p + "layers." + std::to_string(l) + ".";
+            tfm_add(L, q + "mha.q_proj.weight", dk, dk); tfm_add(L, q + "mha.k_proj.weight", dk, dk);
+            tfm_add(L, q + "mha.v_proj.weight", dk, dk); tfm_add(L, q + "mha.out_proj.weight", dk, dk);
+            tfm_add(L, q + "norm1.weight", dk); tfm_add(L, q + "norm1.bias", dk);
+            tfm_add(L, q + "ffn.0.weight", c.dff, dk); tfm_add(L, q + "ffn.0.bias", c.dff);
+            tfm_add(L, q + "ffn.2.weight", dk, c.dff); tfm_add(L, q + "ffn.2.bias", dk);
+            tfm_add(L, q + "norm2.weight", dk); tfm_add(L, q + "norm2.bias", dk);
+        }
+    }
+    std::string g = "spatial_gnn_block.";
+    L.node_kernel = tfm_add(L, g + "node_kernel", dk, D);
+    L.edge_kernel = tfm_add(L, g + "edge_kernel", dk, D);
+    L.node_weights = tfm_add(L, g + "node_weights", dk, 1);
+    L.edge_weights = tfm_add(L, g + "edge_weights", dk, 1);
+    L.node_bias = tfm_add(L, g + "node_bias", D);
+    L.edge_bias = tfm_add(L, g + "edge_bias", D);
+    L.w0 = tfm_add(L, "head.0.weight", 2 * D, (N + E) * D);
+    L.b0 = tfm_add(L, "head.0.bias", 2 * D);
+    L.bn2 = tfm_add(L, "head.2.weight", 2 * D); tfm_add(L, "head.2.bias", 2 * D);
+    tfm_add(L, "head.2.running_mean", 2 * D); tfm_add(L, "head.2.running_var", 2 * D);
+    L.w3 = tfm_add(L, "head.3.weight", D, 2 * D);
+    L.b3 = tfm_add(L, "head.3.bias", D);
+    L.bn5 = tfm_add(L, "head.5.weight", D); tfm_add(L, "head.5.bias", D);
+    tfm_add(L, "head.5.running_mean", D); tfm_add(L, "head.5.running_var", D);
+    L.w6 = tfm_add(L, "head.6.weight", D, D);
+    L.b6 = tfm_add(L, "head.6.bias", D);
+    return L;
+}
+
+extern "C" {
+
+int64_t dof_tfm_numel(const dof_tfm_cfg* cfg) {
+    if (check_tfm_cfg(cfg) != DOF_OK) return -1;
+    return build_tfm_layout(*cfg).total;
+}
+
+int dof_tfm_num_entries(const dof_tfm_cfg* cfg) {
+    if (check_tfm_cfg(cfg) != DOF_OK) return -1;
+    return (int)build_tfm_layout(*cfg).e.size();
+}
+
+int dof_tfm_entry(const dof_tfm_cfg* cfg, int index, char* name_out, int64_t* offset_out, int64_t* numel_out, int* ndim_out,
+                  int* shape_out) {
+    DOF_TRY(check_tfm_cfg(cfg));
+    TfmLayout L = build_tfm_layout(*cfg);
+    if (index < 0 || index >= (int)L.e.size()) DOF_FAIL(DOF_ERR_ARG, "entry index %d out of range", index);
+    const Entry& e = L.e[index];
+    if (name_out) { strncpy(name_out, e.name.c_str(), 127); name_out[127] = 0; }
+    if (offset_out) *offset_out = e.off;
+    if (numel_out) *numel_out = e.numel;
+    if (ndim_out) *ndim_out = e.ndim;
+    if (shape_out) for (int i = 0; i < 4; i++) shape_out[i] = e.shape[i];
+    return DOF_OK;
+}
+
+static size_t tfm_plan(const dof_tfm_cfg& c, int B, char* base, float** nodes, float** edges, float** Pn, float** Pe, float** On,
+                       float** Oe, float** ybuf, bool* one_launch) {
+    Bump bp{base, 0, 0, base == nullptr};
+    const int dk = c.key_dim, G = c.N > c.E ? c.N : c.E;
+    float* p;
+    p = bp.get<float>((size_t)B * c.N * dk); if (nodes) *nodes = p;
+    p = bp.get<float>((size_t)B * c.E * dk); if (edges) *edges = p;
+    p = bp.get<float>((size_t)B * c.N * dk); if (Pn) *Pn = p;
+    p = bp.get<float>((size_t)B * c.E * dk); if (Pe) *Pe = p;
+    p = bp.get<float>((size_t)B * c.N * c.D); if (On) *On = p;
+    p = bp.get<float>((size_t)B * c.E * c.D); if (Oe) *Oe = p;
+    const bool one = tfm_core_smem_bytes(c.T, c.F > c.Fe ? c.F : c.Fe, dk, c.dff, c.layers) <= 220 * 1024;
+    if (one_launch) *one_launch = one;
+    p = one ? nullptr : bp.get<float>((size_t)B * G * c.T * dk);
+    if (ybuf) *ybuf = p;
+    return bp.off;
+}
+
+size_t dof_tfm_workspace_bytes(const dof_tfm_cfg* cfg, int B) {
+    if (check_tfm_cfg(cfg) != DOF_OK || B < 1) return 0;
+    return tfm_plan(*cfg, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// TFMEncoderPT.forward in eval mode (models_new.py:1093-1164): x [B,T,N,F], a [B,T,E,Fe] -> enc_out [B,D]; nodes_out
+// [B*N,key_dim] / edges_out [B*E,key_dim] (may be NULL) receive the last-step outputs of the two transformer cores
+int dof_tfm_encode(const dof_tfm_cfg* cfg, const float* state, const float* x, const float* a, int B, void* workspace,
+                   size_t workspace_bytes, float* enc_out, float* nodes_out, float* edges_out, void* stream) {
+    DOF_TRY(check_tfm_cfg(cfg));
+    if (!state || !x || !a || !workspace || !enc_out || B < 1) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    const dof_tfm_cfg& c = *cfg;
+    float *nodes, *edges, *Pn, *Pe, *On, *Oe, *ybuf;
+    bool one;
+    const size_t need = tfm_plan(c, B, (char*)workspace, &nodes, &edges, &Pn, &Pe, &On, &Oe, &ybuf, &one);
+    if (need > workspace_bytes) DOF_FAIL(DOF_ERR_ARG, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const TfmLayout L = build_tfm_layout(c);
+    const int dk = c.key_dim, N = c.N, E = c.E, D = c.D;
+    static bool attr = false;
+    if (!attr) {
+        DOF_CUDA(cudaFuncSetAttribute(tfm_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        DOF_CUDA(cudaFuncSetAttribute(cens_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    for (int b = 0; b < 2; b++) {
+        TfmCoreArgs t;
+        memset(&t, 0, sizeof(t));
+        t.x = b == 0 ? x : a; t.params = state + L.core[b]; t.out = b == 0 ? nodes : edges; t.ybuf = ybuf;
+        t.B = B; t.T = c.T; t.G = b == 0 ? N : E; t.F = b == 0 ? c.F : c.Fe; t.dk = dk; t.heads = c.heads; t.dff = c.dff; t.layers = c.layers;
+        const int S = B * t.G;
+        const int grid = S < g_sm_count ? S : g_sm_count;
+        const int per = one ? c.layers : 1;
+        const double fl = (double)S * c.T * 2.0 * c.layers * (4.0 * dk * dk + 2.0 * dk * c.dff + 2.0 * c.T * dk);
+        for (int l0 = 0; l0 < c.layers; l0 += per) {
+            t.l_begin = l0; t.l_end = l0 + per;
+            ProfScope ps("tfm_core_fwd", st, fl * per / c.layers, (double)S * (c.T * t.F + dk) * 4.0);
+            tfm_core_fwd_kernel<<<grid, TFM_THREADS, tfm_core_smem_bytes(c.T, t.F, dk, c.dff, per), st>>>(t);
+            DOF_LAUNCH_CHECK();
+        }
+    }
+    if (nodes_out) DOF_CUDA(cudaMemcpyAsync(nodes_out, nodes, (size_t)B * N * dk * 4, cudaMemcpyDeviceToDevice, st));
+    if (edges_out) DOF_CUDA(cudaMemcpyAsync(edges_out, edges, (size_t)B * E * dk * 4, cudaMemcpyDeviceToDevice, st));
+    CensArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.node = nodes; ca.edge = edges; ca.lap = state + L.lap; ca.elap = state + L.elap; ca.inc = state + L.inc;
+    ca.wn = state + L.node_weights; ca.we = state + L.edge_weights; ca.Pn = Pn; ca.Pe = Pe; ca.B = B; ca.N = N; ca.E = E; ca.C = dk;
+    const size_t csm = cens_smem_floats(N, E, dk) * 4;
+    if (csm > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "graph too large for the CensNet kernel (%zu B smem)", csm);
+    { ProfScope ps("cens_fwd", st);
+    cens_fwd_kernel<<<B, 128, csm, st>>>(ca); }
+    DOF_LAUNCH_CHECK();
+    GemmArgs g[2];
+    g[0] = gemm_args(mv_plain(Pn, dk), state + L.node_kernel, D, 1, state + L.node_bias, On, D, B * N, D, dk);
+    g[1] = gemm_args(mv_plain(Pe, dk), state + L.edge_kernel, D, 1, state + L.edge_bias, Oe, D, B * E, D, dk);
+    g[0].relu = g[1].relu = 1;
+    if (N == E) DOF_TRY(launch_gemm_rows(g, 2, st));
+    else { DOF_TRY(launch_gemm_rows(g, 1, st)); DOF_TRY(launch_gemm_rows(g + 1, 1, st)); }
+    TfmHeadArgs hargs;
+    hargs.on = On; hargs.oe = Oe; hargs.w0 = state + L.w0; hargs.b0 = state + L.b0; hargs.bn2 = state + L.bn2; hargs.w3 = state + L.w3;
+    hargs.b3 = state + L.b3; hargs.bn5 = state + L.bn5; hargs.w6 = state + L.w6; hargs.b6 = state + L.b6; hargs.out = enc_out;
+    hargs.B = B; hargs.ND = N * D; hargs.ED = E * D; hargs.D = D;
+    const size_t hsm = (size_t)4 * ((N + E) * D + 3 * D) * 4;
+    if (hsm > 48 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "head input of %d floats does not fit the head kernel", (N + E) * D);
+    { ProfScope ps("tfm_head_fwd", st);
+    tfm_head_fwd_kernel<<<cdiv(B, 4), 128, hsm, st>>>(hargs); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }

@@ -1,0 +1,256 @@
+// Transformer encoder of the path, EVAL-mode forward (reference deepof/clustering/models_new.py):
+//   TransformerCorePT.forward :955-982, TransformerEncoderLayerPT :893-919 (post-LN, eps 1e-6), MultiHeadAttentionPT
+//   :843-890 (bias-free projections, key-padding mask), sinusoidal_positional_encoding :832-840, TFMEncoderPT.forward
+//   :1093-1164 (A.1 group scramble, CensNet, RMS normalisation, head MLP with BatchNorm running statistics).
+//
+// tfm_core_fwd_kernel: one CTA per (window, node) sequence at a time, persistent over the sequences; ALL weights of the
+// core (2 layers: 136 KB at key_dim 40, dff 128) stay in shared memory with rows padded by one float (bank-conflict-free
+// row-parallel reads); the sequence (T x key_dim activations, q|k|v, FFN hidden) lives in shared memory, so HBM sees the
+// raw window once and key_dim floats out.  Only the LAST time step leaves the core (:982), so the last layer computes
+// queries, attention output, projections and FFN for that single row (keys / values for all rows).  fp32 SIMT: the
+// per-sequence products are 25 x 40 x {120, 40, 128}: far below a tcgen05 tile, and this is the inference path
+// (embedding_per_video); the training backward of this encoder is not built yet.
+#pragma once
+#include "common.cuh"
+
+#define TFM_MAXT 64
+#define TFM_THREADS 256
+
+struct TfmCoreArgs {
+    const float* x;        // [B, T, G, F] window tensor (x or a)
+    const float* params;   // this core's parameters, reference order (embed.weight first)
+    float* out;            // [B*G, dk]
+    float* ybuf;           // [B*G, T, dk] activations between launches when the layers do not fit one launch, else NULL
+    int B, T, G, F, dk, heads, dff, layers;
+    int l_begin, l_end;    // layers [l_begin, l_end) run in this launch (their weights are the ones held in shared memory)
+};
+
+__host__ __device__ inline int tfm_layer_floats(int dk, int dff) { return 4 * dk * dk + 2 * dk + dff * dk + dff + dk * dff + dk + 2 * dk; }
+__host__ __device__ inline int tfm_core_floats(int F, int dk, int dff, int layers) { return dk * F + dk + layers * tfm_layer_floats(dk, dff); }
+// shared-memory copy: weight matrices with rows padded to (cols + 1)
+__host__ __device__ inline int tfm_layer_smem_floats(int dk, int dff) { return 4 * dk * (dk + 1) + 2 * dk + dff * (dk + 1) + dff + dk * (dff + 1) + dk + 2 * dk; }
+static inline size_t tfm_core_smem_bytes(int T, int F, int dk, int dff, int layers) {      // layers = layers per launch
+    size_t fl = (size_t)dk * F + dk + (size_t)layers * tfm_layer_smem_floats(dk, dff)   // weights
+              + (size_t)T * dk                       // positional encoding
+              + (size_t)T * dk * 2                   // y, att
+              + (size_t)T * 3 * dk                   // q | k | v
+              + (size_t)T * dff                      // FFN hidden
+              + (size_t)T;                           // key mask
+    return fl * 4 + 64;
+}
+
+// out[t][n] = sum_k in[t][k] * W[n][k] (+ bias) (relu) for t in [t0, T), rows of W padded to K + 1
+__device__ __forceinline__ void tfm_linear(const float* in, int ldin, const float* W, const float* bias, float* out, int ldout, int t0,
+                                           int T, int N, int K, bool relu) {
+    const int total = (T - t0) * N;
+    for (int o = threadIdx.x; o < total; o += blockDim.x) {
+        const int t = t0 + o / N, n = o % N;
+        const float* w = W + (size_t)n * (K + 1);
+        const float* v = in + (size_t)t * ldin;
+        float acc = bias ? bias[n] : 0.f;
+        for (int k = 0; k < K; k++) acc += v[k] * w[k];
+        out[(size_t)t * ldout + n] = relu ? fmaxf(acc, 0.f) : acc;
+    }
+}
+
+// y[t] = LayerNorm(y[t] + r[t]) for t in [t0, T): one warp per row
+__device__ __forceinline__ void tfm_add_ln(float* y, const float* r, const float* w, const float* b, int t0, int T, int dk) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int t = t0 + warp; t < T; t += nw) {
+        float s = 0.f;
+        for (int d = lane; d < dk; d += 32) s += y[t * dk + d] + r[t * dk + d];
+        const float mu = warp_sum(s) / dk;
+        float q = 0.f;
+        for (int d = lane; d < dk; d += 32) { const float v = y[t * dk + d] + r[t * dk + d] - mu; q += v * v; }
+        const float rs = rsqrtf(warp_sum(q) / dk + 1e-6f);
+        for (int d = lane; d < dk; d += 32) y[t * dk + d] = (y[t * dk + d] + r[t * dk + d] - mu) * rs * w[d] + b[d];
+    }
+}
+
+__global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCoreArgs a) {
+    extern __shared__ __align__(16) float tfsm[];
+    const int T = a.T, G = a.G, F = a.F, dk = a.dk, dff = a.dff, heads = a.heads, hd = a.dk / a.heads;
+    const int tid = threadIdx.x;
+    float* We = tfsm;                    // [dk][F]
+    float* be = We + dk * F;              // [dk]
+    float* Wl = be + dk;                  // layers x padded layer block
+    const int lsm = tfm_layer_smem_floats(dk, dff);
+    const int nl = a.l_end - a.l_begin;
+    float* pe = Wl + (size_t)nl * lsm;    // [T][dk]
+    float* y = pe + T * dk;               // [T][dk]
+    float* att = y + T * dk;              // [T][dk]
+    float* qkv = att + T * dk;            // [T][3dk]
+    float* ff = qkv + T * 3 * dk;         // [T][dff]
+    float* kmask = ff + T * dff;          // [T] 1 = padded key
+    // ---- weights -> shared memory (padded rows), positional encoding
+    for (int i = tid; i < dk * F + dk; i += blockDim.x) We[i] = __ldg(a.params + i);
+    for (int l = a.l_begin; l < a.l_end; l++) {
+        const float* src = a.params + dk * F + dk + (size_t)l * tfm_layer_floats(dk, dff);
+        float* dst = Wl + (size_t)(l - a.l_begin) * lsm;
+        // q, k, v, out: [dk][dk] -> [dk][dk+1]
+        for (int i = tid; i < 4 * dk * dk; i += blockDim.x) { const int r = i / dk, c = i % dk; dst[r * (dk + 1) + c] = __ldg(src + i); }
+        src += 4 * dk * dk; dst += 4 * dk * (dk + 1);
+        for (int i = tid; i < 2 * dk; i += blockDim.x) dst[i] = __ldg(src + i);                      // norm1 w | b
+        src += 2 * dk; dst += 2 * dk;
+        for (int i = tid; i < dff * dk; i += blockDim.x) { const int r = i / dk, c = i % dk; dst[r * (dk + 1) + c] = __ldg(src + i); }   // ffn.0.weight
+        src += dff * dk; dst += dff * (dk + 1);
+        for (int i = tid; i < dff; i += blockDim.x) dst[i] = __ldg(src + i);                         // ffn.0.bias
+        src += dff; dst += dff;
+        for (int i = tid; i < dk * dff; i += blockDim.x) { const int r = i / dff, c = i % dff; dst[r * (dff + 1) + c] = __ldg(src + i); } // ffn.2.weight
+        src += dk * dff; dst += dk * (dff + 1);
+        for (int i = tid; i < 3 * dk; i += blockDim.x) dst[i] = __ldg(src + i);                      // ffn.2.bias | norm2 w | b
+    }
+    for (int i = tid; i < T * dk; i += blockDim.x) {
+        const int t = i / dk, d = i % dk;
+        const float div = expf((float)(d & ~1) * (-logf(10000.0f) / (float)dk));                     // :835
+        pe[i] = (d & 1) ? cosf((float)t * div) : sinf((float)t * div);
+    }
+    __syncthreads();
+    const float scale = sqrtf((float)dk), qs = rsqrtf((float)hd);
+    const int S = a.B * G;
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const int b = s / G, g = s % G;
+        const float* xw = a.x + (size_t)b * T * G * F;
+        // ---- A.1 gather + padding mask + embedding: y = relu(x We^T + be) * sqrt(dk) + PE
+        for (int i = tid; i < T * dk; i += blockDim.x) {
+            const int t = i / dk, d = i % dk;
+            float acc = be[d];
+            bool allz = true;
+            for (int f = 0; f < F; f++) {
+                const int lin = (f * T + t) * G + g;
+                const float v = __ldg(xw + (size_t)(lin % T) * G * F + lin / T);
+                allz = allz && (v == 0.0f);
+                acc += v * We[d * F + f];
+            }
+            y[i] = a.l_begin == 0 ? fmaxf(acc, 0.f) * scale + pe[i] : a.ybuf[(size_t)s * T * dk + i];
+            if (d == 0) kmask[t] = allz ? 1.f : 0.f;
+        }
+        __syncthreads();
+        for (int l = a.l_begin; l < a.l_end; l++) {
+            const float* P = Wl + (size_t)(l - a.l_begin) * lsm;
+            const float* Wq = P;                               // q | k | v | out, each [dk][dk+1]
+            const float* Wo = P + 3 * dk * (dk + 1);
+            const float* n1 = Wo + dk * (dk + 1);
+            const float* W1 = n1 + 2 * dk;
+            const float* b1 = W1 + dff * (dk + 1);
+            const float* W2 = b1 + dff;
+            const float* b2 = W2 + dk * (dff + 1);
+            const float* n2 = b2 + dk;
+            const int t0 = (l == a.layers - 1) ? T - 1 : 0;    // only the last step leaves the core
+            // keys / values for every step, queries from t0 on (q rows < t0 are computed too when t0 == 0 only)
+            tfm_linear(y, dk, Wq + dk * (dk + 1), nullptr, qkv + dk, 3 * dk, 0, T, 2 * dk, dk, false);     // k | v (rows contiguous in Wq)
+            tfm_linear(y, dk, Wq, nullptr, qkv, 3 * dk, t0, T, dk, dk, false);                             // q
+            __syncthreads();
+            // attention: one thread per (head, query step)
+            for (int o = tid; o < heads * (T - t0); o += blockDim.x) {
+                const int hh = o / (T - t0), tq = t0 + o % (T - t0);
+                const float* q = qkv + (size_t)tq * 3 * dk + hh * hd;
+                float sc[TFM_MAXT];
+                float mx = -INFINITY;
+                for (int tk = 0; tk < T; tk++) {
+                    const float* kk = qkv + (size_t)tk * 3 * dk + dk + hh * hd;
+                    float dot = 0.f;
+                    for (int d = 0; d < hd; d++) dot += q[d] * kk[d];
+                    dot = kmask[tk] != 0.f ? -INFINITY : dot * qs;
+                    sc[tk] = dot;
+                    mx = fmaxf(mx, dot);
+                }
+                float sum = 0.f;
+                for (int tk = 0; tk < T; tk++) { sc[tk] = expf(sc[tk] - mx); sum += sc[tk]; }
+                const float inv = 1.0f / sum;
+                for (int d = 0; d < hd; d++) {
+                    float acc = 0.f;
+                    for (int tk = 0; tk < T; tk++) acc += sc[tk] * qkv[(size_t)tk * 3 * dk + 2 * dk + hh * hd + d];
+                    att[(size_t)tq * dk + hh * hd + d] = acc * inv;
+                }
+            }
+            __syncthreads();
+            tfm_linear(att, dk, Wo, nullptr, qkv, 3 * dk, t0, T, dk, dk, false);          // out projection -> qkv[:, 0:dk] (q is dead)
+            __syncthreads();
+            // y = LN(y + o): gather the projection rows through a strided view
+            {
+                const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+                for (int t = t0 + warp; t < T; t += nw) {
+                    float sm = 0.f;
+                    for (int d = lane; d < dk; d += 32) sm += y[t * dk + d] + qkv[(size_t)t * 3 * dk + d];
+                    const float mu = warp_sum(sm) / dk;
+                    float qv = 0.f;
+                    for (int d = lane; d < dk; d += 32) { const float v = y[t * dk + d] + qkv[(size_t)t * 3 * dk + d] - mu; qv += v * v; }
+                    const float rs = rsqrtf(warp_sum(qv) / dk + 1e-6f);
+                    for (int d = lane; d < dk; d += 32)
+                        y[t * dk + d] = (y[t * dk + d] + qkv[(size_t)t * 3 * dk + d] - mu) * rs * n1[d] + n1[dk + d];
+                }
+            }
+            __syncthreads();
+            tfm_linear(y, dk, W1, b1, ff, dff, t0, T, dff, dk, true);
+            __syncthreads();
+            tfm_linear(ff, dff, W2, b2, att, dk, t0, T, dk, dff, false);
+            __syncthreads();
+            tfm_add_ln(y, att, n2, n2 + dk, t0, T, dk);
+            __syncthreads();
+        }
+        if (a.l_end == a.layers) {
+            for (int d = tid; d < dk; d += blockDim.x) a.out[(size_t)s * dk + d] = y[(size_t)(T - 1) * dk + d];
+        } else {
+            for (int i = tid; i < T * dk; i += blockDim.x) a.ybuf[(size_t)s * T * dk + i] = y[i];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- head: RMS normalisation + Linear/ReLU/BN(eval) x2 + Linear; one warp per window --------------------------
+struct TfmHeadArgs {
+    const float* on; const float* oe;      // CensNet outputs [B, N*D], [B, E*D] (already >= 0)
+    const float* w0; const float* b0; const float* bn2;   // bn: weight | bias | running_mean | running_var
+    const float* w3; const float* b3; const float* bn5;
+    const float* w6; const float* b6;
+    float* out;                            // [B, D]
+    int B, ND, ED, D;
+};
+
+__global__ void __launch_bounds__(128) tfm_head_fwd_kernel(const TfmHeadArgs a) {
+    extern __shared__ __align__(16) float hsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + warp;
+    if (b >= a.B) return;
+    const int KD = a.ND + a.ED, D = a.D;
+    float* v = hsm + (size_t)warp * (KD + 3 * D);      // input | h1 [2D] | h2 [D]
+    float* h1 = v + KD;
+    float* h2 = h1 + 2 * D;
+    float ss = 0.f;
+    for (int k = lane; k < KD; k += 32) {
+        const float x = k < a.ND ? a.on[(size_t)b * a.ND + k] : a.oe[(size_t)b * a.ED + (k - a.ND)];
+        v[k] = x;
+        ss += x * x;
+    }
+    const float rms = sqrtf(warp_sum(ss) / KD);
+    const float inv = 1.0f / fmaxf(rms, 1.0f);                                         // :1150-1151
+    for (int k = lane; k < KD; k += 32) {
+        float x = fminf(fmaxf(v[k] * inv, -1e4f), 1e4f);                               // :1152
+        if (x != x) x = 0.f;                                                           // nan_to_num :1153
+        v[k] = x;
+    }
+    __syncwarp();
+    for (int n = 0; n < 2 * D; n++) {
+        float acc = 0.f;
+        for (int k = lane; k < KD; k += 32) acc += v[k] * __ldg(a.w0 + (size_t)n * KD + k);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float r = fmaxf(acc + a.b0[n], 0.f);
+            h1[n] = (r - a.bn2[2 * 2 * D + n]) * rsqrtf(a.bn2[3 * 2 * D + n] + 1e-3f) * a.bn2[n] + a.bn2[2 * D + n];
+        }
+    }
+    __syncwarp();
+    for (int n = lane; n < D; n += 32) {
+        float acc = a.b3[n];
+        for (int k = 0; k < 2 * D; k++) acc += h1[k] * a.w3[(size_t)n * 2 * D + k];
+        const float r = fmaxf(acc, 0.f);
+        h2[n] = (r - a.bn5[2 * D + n]) * rsqrtf(a.bn5[3 * D + n] + 1e-3f) * a.bn5[n] + a.bn5[D + n];
+    }
+    __syncwarp();
+    for (int n = lane; n < D; n += 32) {
+        float acc = a.b6[n];
+        for (int k = 0; k < D; k++) acc += h2[k] * a.w6[(size_t)n * D + k];
+        a.out[(size_t)b * D + n] = acc;
+    }
+}

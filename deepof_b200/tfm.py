@@ -1,0 +1,134 @@
+"""Host-side mirror of the reference ``TFMEncoderPT`` (``deepof/clustering/models_new.py:985-1164``) for INFERENCE:
+``encoder(x, a) -> [B, latent_dim]`` with the module in ``eval()`` — the call ``embedding_per_video``
+(``model_utils_new.py:545-621``) makes on the transformer model family.  The forward runs in the CUDA library
+(``dof_tfm_encode``, ``csrc/tfm.cuh``); torch is device memory only.  The training step of this encoder is not built
+yet: ``train()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DofTfmCfg, check, lib, ptr
+from .vade import _stream, graph_operators
+
+
+def tfm_layout(cfg: DofTfmCfg):
+    """[(name, offset, numel, shape)] in the reference's state_dict order."""
+    L = lib()
+    n = L.dof_tfm_num_entries(C.byref(cfg))
+    if n < 0:
+        check(-1)
+    out = []
+    name = C.create_string_buffer(128)
+    off, numel, ndim = C.c_int64(), C.c_int64(), C.c_int()
+    shape = (C.c_int * 4)()
+    for i in range(n):
+        check(L.dof_tfm_entry(C.byref(cfg), i, name, C.byref(off), C.byref(numel), C.byref(ndim), shape))
+        out.append((name.value.decode(), off.value, numel.value, tuple(shape[: ndim.value])))
+    return out
+
+
+class TFMEncoderB200:
+    """``TFMEncoderPT(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, use_gnn=True)`` in eval mode."""
+    _BUFFERS = ("laplacian", "edge_laplacian", "incidence", "head.2.running_mean", "head.2.running_var",
+                "head.5.running_mean", "head.5.running_var")
+
+    def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, use_gnn: bool = True,
+                 num_layers: int = 2, num_heads: int = 4, dff: int = 128, key_dim: Optional[int] = None,
+                 device: Optional[int] = None, max_batch: int = 1024, seed: Optional[int] = None):
+        if not use_gnn:
+            raise NotImplementedError("deepof_b200 implements the GNN path of the transformer encoder only")
+        T, N, F = (int(v) for v in input_shape)
+        _, E, Fe = (int(v) for v in edge_feature_shape)
+        adjacency_matrix = np.asarray(adjacency_matrix)
+        assert adjacency_matrix.shape == (N, N), "Adjacency must be NxN and match input nodes."
+        if key_dim is None:                                      # models_new.py:1014-1019
+            key_dim = max((min(64, N * F) // num_heads) * num_heads, num_heads)
+        self.input_shape, self.edge_feature_shape = (T, N, F), (T, E, Fe)
+        self.latent_dim, self.key_dim, self.window_size = int(latent_dim), int(key_dim), T
+        self.cfg = DofTfmCfg(T, N, E, F, Fe, int(latent_dim), int(key_dim), int(num_heads), int(dff), int(num_layers))
+        self.L = lib()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.max_batch = int(max_batch)
+        self.layout = tfm_layout(self.cfg)
+        total = self.L.dof_tfm_numel(C.byref(self.cfg))
+        host = torch.zeros(total)
+        g = torch.Generator().manual_seed(int(seed)) if seed is not None else None
+        lap, elap, inc = graph_operators(adjacency_matrix)
+        if inc.shape[1] != E:
+            raise ValueError(f"edge_feature_shape has {E} edges, the adjacency matrix {inc.shape[1]}")
+        for name, off, numel, shape in self.layout:
+            v = host[off:off + numel].view(shape)
+            if name == "laplacian":
+                v.copy_(torch.from_numpy(lap))
+            elif name == "edge_laplacian":
+                v.copy_(torch.from_numpy(elap))
+            elif name == "incidence":
+                v.copy_(torch.from_numpy(inc))
+            elif name.endswith("running_var") or (name.endswith(".weight") and len(shape) == 1):
+                v.fill_(1.0)                                     # LayerNorm / BatchNorm scales, BN variance
+            elif len(shape) == 2 and shape[1] > 1 or name.endswith("_kernel"):
+                bound = math.sqrt(6.0 / (shape[0] + shape[1]))  # xavier_uniform_
+                v.copy_((torch.rand(shape, generator=g) * 2.0 - 1.0) * bound)
+            elif name.endswith("_weights"):
+                v.copy_((torch.rand(shape, generator=g) * 2.0 - 1.0) * math.sqrt(6.0 / (shape[0] + 1)))
+        self.state = host.to(self.device)
+        self._views = {name: self.state[off:off + numel].view(shape) for name, off, numel, shape in self.layout}
+        self._ws = torch.empty(self.L.dof_tfm_workspace_bytes(C.byref(self.cfg), self.max_batch), dtype=torch.uint8, device=self.device)
+        self.training = False
+
+    # ---- torch.nn.Module-like surface ---------------------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("the training step of the transformer encoder is not built; eval() only")
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: v.clone() for k, v in self._views.items()}
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        """Accepts the reference's ``TFMEncoderPT.state_dict()`` (optionally prefixed with ``encoder.``); the integer
+        ``num_batches_tracked`` buffers are ignored."""
+        sd = {(k[len("encoder."):] if k.startswith("encoder.") else k): v for k, v in sd.items()}
+        missing = [k for k in self._views if k not in sd]
+        if strict and missing:
+            raise KeyError(f"missing keys: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+        for k, v in self._views.items():
+            if k in sd:
+                t = torch.as_tensor(np.asarray(sd[k]) if not torch.is_tensor(sd[k]) else sd[k]).to(torch.float32)
+                if tuple(t.shape) != tuple(v.shape):
+                    raise ValueError(f"{k}: shape {tuple(t.shape)} != {tuple(v.shape)}")
+                v.copy_(t.to(self.device))
+
+    # ---- forward ------------------------------------------------------------------------------------------------
+    def encode(self, x, a, return_cores: bool = False):
+        T, N, F = self.input_shape
+        _, E, Fe = self.edge_feature_shape
+        x = torch.as_tensor(x).to(self.device, torch.float32).contiguous()
+        a = torch.as_tensor(a).to(self.device, torch.float32).contiguous()
+        assert tuple(x.shape[1:]) == (T, N, F), f"Input shape mismatch: got {tuple(x.shape[1:])}, expected {(T, N, F)}"
+        assert tuple(a.shape[1:]) == (T, E, Fe) and a.shape[0] == x.shape[0]
+        B = x.shape[0]
+        out = torch.empty(B, self.latent_dim, device=self.device)
+        nodes = torch.empty(B * N, self.key_dim, device=self.device) if return_cores else None
+        edges = torch.empty(B * E, self.key_dim, device=self.device) if return_cores else None
+        for s in range(0, B, self.max_batch):
+            e = min(B, s + self.max_batch)
+            check(self.L.dof_tfm_encode(C.byref(self.cfg), ptr(self.state), ptr(x[s:e]), ptr(a[s:e]), e - s, ptr(self._ws),
+                                        self._ws.numel(), ptr(out[s:e]), ptr(nodes[s * N:e * N]) if return_cores else None,
+                                        ptr(edges[s * E:e * E]) if return_cores else None, _stream()))
+        return (out, nodes, edges) if return_cores else out
+
+    __call__ = encode

@@ -275,6 +275,27 @@ int dof_contrastive_loss_grad_distill(dof_handle* h, const float* state, float* 
                                       int B, int loss_kind, int sim_kind, float temperature, float tau_plus, float beta,
                                       const dof_distill_cfg* distill, float* logs, float* z_out, void* stream);
 
+/* ---- transformer encoder, EVAL-mode forward -------------------------------------------------
+ * TFMEncoderPT.forward with the module in eval() (deepof/clustering/models_new.py:985-1164): the embedding path
+ * `model.encoder(x, a)` of the transformer model family (embedding_per_video, model_utils_new.py:545-621).  Stateless
+ * calls: `state` is the flat float parameter vector in the reference's state_dict order (dof_tfm_entry enumerates names,
+ * offsets and shapes; the integer num_batches_tracked buffers are not part of it), `workspace` is caller-owned device
+ * memory of dof_tfm_workspace_bytes(cfg, B).  The training step of this encoder is NOT built yet. */
+typedef struct dof_tfm_cfg {
+    int T, N, E, F, Fe, D;
+    int key_dim;   /* min(64, N*F) rounded down to a multiple of heads (models_new.py:1014-1019) */
+    int heads;     /* 4 */
+    int dff;       /* 128 */
+    int layers;    /* 2 */
+} dof_tfm_cfg;
+int64_t dof_tfm_numel(const dof_tfm_cfg* cfg);
+int dof_tfm_num_entries(const dof_tfm_cfg* cfg);
+int dof_tfm_entry(const dof_tfm_cfg* cfg, int index, char* name_out, int64_t* offset_out, int64_t* numel_out,
+                  int* ndim_out, int* shape_out);
+size_t dof_tfm_workspace_bytes(const dof_tfm_cfg* cfg, int B);
+int dof_tfm_encode(const dof_tfm_cfg* cfg, const float* state, const float* x, const float* a, int B, void* workspace,
+                   size_t workspace_bytes, float* enc_out, float* nodes_out, float* edges_out, void* stream);
+
 /* Debug / test access to intermediate activations of the last forward (device pointers into
  * the workspace; NULL if unknown).  Names: "node_out","edge_out","enc","z","z_mean",
  * "z_log_var","q","loc","len_node","len_edge". */
