@@ -107,6 +107,8 @@ _SIGS = {
                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dof_tfm_workspace_bytes": (C.c_size_t, [C.POINTER(DofTfmCfg), C.c_int]),
     "dof_tfm_encode": (C.c_int, [C.POINTER(DofTfmCfg), _P, _P, _P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P]),
+    "dof_latent_eval": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dof_vq_eval": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dof_adam_flat": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                 C.c_float, _P]),
     "dof_contrastive_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P,

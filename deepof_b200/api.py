@@ -26,6 +26,7 @@ import torch
 from .loader import batch_starts
 from .models import (AugParams, CON_LOG_KEYS, ContrastiveAugCfg, ContrastiveB200, DistillHeadB200, Distillation, VQ_LOG_KEYS,
                      VQVAEB200)
+from .tfm import TFMModelB200
 from .training import KLSchedule
 from .vade import VaDEB200, VadeLossCfg
 
@@ -219,10 +220,16 @@ def save_model_info(ckpt_path: str, *, model, rebuild_spec: Dict[str, Any], log_
 def build_model(rebuild_spec: Dict[str, Any], max_batch: int = 4096, training: bool = False, device: Optional[int] = None):
     """Model object from a reference ``rebuild_spec`` (``model_utils_new.py:367-417``)."""
     name = str(rebuild_spec["model_name"]).lower()
-    if rebuild_spec.get("encoder_type", "recurrent") != "recurrent" or not rebuild_spec.get("use_gnn", True):
-        raise NotImplementedError("deepof_b200 implements encoder_type='recurrent', use_gnn=True")
+    etype = rebuild_spec.get("encoder_type", "recurrent")
+    if etype not in ("recurrent", "transformer") or not rebuild_spec.get("use_gnn", True):
+        raise NotImplementedError("deepof_b200 implements encoder_type='recurrent' (training + inference) and 'transformer' "
+                                  "(inference), use_gnn=True")
     xs, as_ = tuple(rebuild_spec["x_shape"]), tuple(rebuild_spec["a_shape"])
     adj, D, K = np.asarray(rebuild_spec["adjacency_matrix"]), int(rebuild_spec["latent_dim"]), int(rebuild_spec.get("n_components", 1))
+    if etype == "transformer":
+        if training:
+            raise NotImplementedError("the training step of the transformer model family is not built (inference only)")
+        return TFMModelB200(name, xs, as_, adj, D, K, max_batch=max_batch, device=device)
     kw = dict(max_batch=max_batch, training=training, device=device)
     if name == "vade":
         return VaDEB200(xs, as_, adj, D, K, kmeans_loss=float(rebuild_spec.get("kmeans_loss", 0.0)), **kw)

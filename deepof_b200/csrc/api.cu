@@ -1249,6 +1249,44 @@ size_t dof_tfm_workspace_bytes(const dof_tfm_cfg* cfg, int B) {
     return tfm_plan(*cfg, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
+// ---- read-outs on an encoder output (the transformer family's embedding path) ----------------------------------
+// GaussianMixtureLatentPT in eval mode (models_new.py:1745-1791): emb = z_mean [B,D], q = GMM posterior [B,K].
+// scratch: 3*B*D floats (softplus pre-activation, log-variance, z — outputs of the shared kernel that eval does not need)
+int dof_latent_eval(const float* enc, const float* Wm, const float* bm, const float* Wv, const float* bv, const float* gmm_mu,
+                    const float* gmm_lv, const float* prior, int B, int D, int K, float* emb, float* q, float* scratch, void* stream) {
+    if (!enc || !Wm || !bm || !Wv || !bv || !gmm_mu || !gmm_lv || !prior || !emb || !q || !scratch || B < 1)
+        DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    if (K > LOSS_MAXK || D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent read-out: K=%d (<= %d), D=%d (<= 64)", K, LOSS_MAXK, D);
+    LatentArgs la;
+    la.enc = enc; la.Wm = Wm; la.bm = bm; la.Wv = Wv; la.bv = bv; la.eps = nullptr; la.gmm_mu = gmm_mu; la.gmm_lv = gmm_lv; la.prior = prior;
+    la.zm = emb; la.pre = scratch; la.lv = scratch + (size_t)B * D; la.z = scratch + (size_t)2 * B * D; la.q = q; la.B = B; la.D = D; la.K = K;
+    const size_t lsm = ((size_t)2 * D * D + 2 * D + 2 * (size_t)K * D + K) * 4;
+    if (lsm > 48 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent head does not fit shared memory");
+    { ProfScope ps("latent_fwd", (cudaStream_t)stream);
+    latent_fwd_kernel<<<cdiv(B, 64), 64, lsm, (cudaStream_t)stream>>>(la); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+// VectorQuantizerPT read-outs (models_new.py:1358-1423): nearest code, soft counts, quantized latents.
+// scratch: (4 + D*D + K) doubles
+int dof_vq_eval(const float* enc, const float* codebook, int B, int D, int K, float* quant, float* soft, int* idx, double* scratch,
+                void* stream) {
+    if (!enc || !codebook || !quant || !soft || !idx || !scratch || B < 1) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    if (D > VQ_MAXD) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > %d", D, VQ_MAXD);
+    cudaStream_t st = (cudaStream_t)stream;
+    VqArgs v;
+    v.z = enc; v.codebook = codebook; v.quant = quant; v.soft = soft; v.idx = idx; v.stats = scratch; v.B = B; v.D = D; v.K = K; v.want_gram = 0;
+    DOF_CUDA(cudaMemsetAsync(scratch, 0, ((size_t)VQ_ST_GRAM + (size_t)D * D + K) * sizeof(double), st));
+    const size_t smem = ((size_t)D * K + K + (size_t)D * D) * 4;
+    if (smem > 96 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "codebook %d x %d does not fit in shared memory", D, K);
+    if (smem > 48 * 1024) DOF_CUDA(cudaFuncSetAttribute(vq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    { ProfScope ps("vq_fwd", st, 0.0, (double)B * (8.0 * D + 4.0 + 4.0 * K));
+    vq_fwd_kernel<<<cdiv(B, 128), 128, smem, st>>>(v); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
 // TFMEncoderPT.forward in eval mode (models_new.py:1093-1164): x [B,T,N,F], a [B,T,E,Fe] -> enc_out [B,D]; nodes_out
 // [B*N,key_dim] / edges_out [B*E,key_dim] (may be NULL) receive the last-step outputs of the two transformer cores
 int dof_tfm_encode(const dof_tfm_cfg* cfg, const float* state, const float* x, const float* a, int B, void* workspace,

@@ -4,8 +4,8 @@
 //   :1093-1164 (A.1 group scramble, CensNet, RMS normalisation, head MLP with BatchNorm running statistics).
 //
 // tfm_core_fwd_kernel: one CTA per (window, node) sequence at a time, persistent over the sequences; ALL weights of the
-// core (2 layers: 136 KB at key_dim 40, dff 128) stay in shared memory with rows padded by one float (bank-conflict-free
-// row-parallel reads); the sequence (T x key_dim activations, q|k|v, FFN hidden) lives in shared memory, so HBM sees the
+// core (2 layers: 136 KB at key_dim 40, dff 128) stay in shared memory, transposed ([K][N]: threads of a warp read
+// consecutive output columns, 5 x 2 register tiles); the sequence (T x key_dim activations, q|k|v, FFN hidden) lives in shared memory, so HBM sees the
 // raw window once and key_dim floats out.  Only the LAST time step leaves the core (:982), so the last layer computes
 // queries, attention output, projections and FFN for that single row (keys / values for all rows).  fp32 SIMT: the
 // per-sequence products are 25 x 40 x {120, 40, 128}: far below a tcgen05 tile, and this is the inference path
@@ -27,8 +27,8 @@ struct TfmCoreArgs {
 
 __host__ __device__ inline int tfm_layer_floats(int dk, int dff) { return 4 * dk * dk + 2 * dk + dff * dk + dff + dk * dff + dk + 2 * dk; }
 __host__ __device__ inline int tfm_core_floats(int F, int dk, int dff, int layers) { return dk * F + dk + layers * tfm_layer_floats(dk, dff); }
-// shared-memory copy: weight matrices with rows padded to (cols + 1)
-__host__ __device__ inline int tfm_layer_smem_floats(int dk, int dff) { return 4 * dk * (dk + 1) + 2 * dk + dff * (dk + 1) + dff + dk * (dff + 1) + dk + 2 * dk; }
+// shared-memory copy: weight matrices TRANSPOSED ([K][N], q|k|v side by side as one [dk][3dk] matrix)
+__host__ __device__ inline int tfm_layer_smem_floats(int dk, int dff) { return tfm_layer_floats(dk, dff); }
 static inline size_t tfm_core_smem_bytes(int T, int F, int dk, int dff, int layers) {      // layers = layers per launch
     size_t fl = (size_t)dk * F + dk + (size_t)layers * tfm_layer_smem_floats(dk, dff)   // weights
               + (size_t)T * dk                       // positional encoding
@@ -39,17 +39,36 @@ static inline size_t tfm_core_smem_bytes(int T, int F, int dk, int dff, int laye
     return fl * 4 + 64;
 }
 
-// out[t][n] = sum_k in[t][k] * W[n][k] (+ bias) (relu) for t in [t0, T), rows of W padded to K + 1
-__device__ __forceinline__ void tfm_linear(const float* in, int ldin, const float* W, const float* bias, float* out, int ldout, int t0,
-                                           int T, int N, int K, bool relu) {
-    const int total = (T - t0) * N;
-    for (int o = threadIdx.x; o < total; o += blockDim.x) {
-        const int t = t0 + o / N, n = o % N;
-        const float* w = W + (size_t)n * (K + 1);
-        const float* v = in + (size_t)t * ldin;
-        float acc = bias ? bias[n] : 0.f;
-        for (int k = 0; k < K; k++) acc += v[k] * w[k];
-        out[(size_t)t * ldout + n] = relu ? fmaxf(acc, 0.f) : acc;
+// out[t][n] = sum_k in[t][k] * Wt[k][n] (+ bias) (relu) for t in [t0, T); Wt is the transposed weight with row pitch ldw.
+// Register tile: 5 rows x 2 columns per thread (one 8-byte weight load + 5 broadcast activation loads per 10 FMAs).
+#define TFM_TT 5
+__device__ __forceinline__ void tfm_linear(const float* in, int ldin, const float* Wt, int ldw, const float* bias, float* out, int ldout,
+                                           int t0, int T, int N, int K, bool relu) {
+    const int nc = N >> 1, ng = (T - t0 + TFM_TT - 1) / TFM_TT;
+    for (int tile = threadIdx.x; tile < nc * ng; tile += blockDim.x) {
+        const int cn = (tile % nc) * 2, tb = t0 + (tile / nc) * TFM_TT;
+        float acc[TFM_TT][2];
+        const float bx = bias ? bias[cn] : 0.f, by = bias ? bias[cn + 1] : 0.f;
+#pragma unroll
+        for (int i = 0; i < TFM_TT; i++) { acc[i][0] = bx; acc[i][1] = by; }
+        const float* v[TFM_TT];
+#pragma unroll
+        for (int i = 0; i < TFM_TT; i++) v[i] = in + (size_t)min(tb + i, T - 1) * ldin;
+        const float* w = Wt + cn;
+#pragma unroll 4
+        for (int k = 0; k < K; k++) {
+            const float2 ww = *reinterpret_cast<const float2*>(w + (size_t)k * ldw);
+#pragma unroll
+            for (int i = 0; i < TFM_TT; i++) { const float x = v[i][k]; acc[i][0] += x * ww.x; acc[i][1] += x * ww.y; }
+        }
+#pragma unroll
+        for (int i = 0; i < TFM_TT; i++) {
+            if (tb + i < T) {
+                float2 o = make_float2(acc[i][0], acc[i][1]);
+                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+                *reinterpret_cast<float2*>(out + (size_t)(tb + i) * ldout + cn) = o;
+            }
+        }
     }
 }
 
@@ -87,17 +106,19 @@ __global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCore
     for (int l = a.l_begin; l < a.l_end; l++) {
         const float* src = a.params + dk * F + dk + (size_t)l * tfm_layer_floats(dk, dff);
         float* dst = Wl + (size_t)(l - a.l_begin) * lsm;
-        // q, k, v, out: [dk][dk] -> [dk][dk+1]
-        for (int i = tid; i < 4 * dk * dk; i += blockDim.x) { const int r = i / dk, c = i % dk; dst[r * (dk + 1) + c] = __ldg(src + i); }
-        src += 4 * dk * dk; dst += 4 * dk * (dk + 1);
+        // q | k | v: three [dk][dk] (out, in) matrices -> one [in = dk][3dk] matrix; out_proj -> [dk][dk] transposed
+        for (int i = tid; i < 3 * dk * dk; i += blockDim.x) { const int m = i / (dk * dk), r = (i / dk) % dk, c = i % dk; dst[c * 3 * dk + m * dk + r] = __ldg(src + i); }
+        src += 3 * dk * dk; dst += 3 * dk * dk;
+        for (int i = tid; i < dk * dk; i += blockDim.x) { const int r = i / dk, c = i % dk; dst[c * dk + r] = __ldg(src + i); }
+        src += dk * dk; dst += dk * dk;
         for (int i = tid; i < 2 * dk; i += blockDim.x) dst[i] = __ldg(src + i);                      // norm1 w | b
         src += 2 * dk; dst += 2 * dk;
-        for (int i = tid; i < dff * dk; i += blockDim.x) { const int r = i / dk, c = i % dk; dst[r * (dk + 1) + c] = __ldg(src + i); }   // ffn.0.weight
-        src += dff * dk; dst += dff * (dk + 1);
+        for (int i = tid; i < dff * dk; i += blockDim.x) { const int r = i / dk, c = i % dk; dst[c * dff + r] = __ldg(src + i); }   // ffn.0.weight -> [dk][dff]
+        src += dff * dk; dst += dff * dk;
         for (int i = tid; i < dff; i += blockDim.x) dst[i] = __ldg(src + i);                         // ffn.0.bias
         src += dff; dst += dff;
-        for (int i = tid; i < dk * dff; i += blockDim.x) { const int r = i / dff, c = i % dff; dst[r * (dff + 1) + c] = __ldg(src + i); } // ffn.2.weight
-        src += dk * dff; dst += dk * (dff + 1);
+        for (int i = tid; i < dk * dff; i += blockDim.x) { const int r = i / dff, c = i % dff; dst[c * dk + r] = __ldg(src + i); }  // ffn.2.weight -> [dff][dk]
+        src += dk * dff; dst += dk * dff;
         for (int i = tid; i < 3 * dk; i += blockDim.x) dst[i] = __ldg(src + i);                      // ffn.2.bias | norm2 w | b
     }
     for (int i = tid; i < T * dk; i += blockDim.x) {
@@ -128,18 +149,21 @@ __global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCore
         __syncthreads();
         for (int l = a.l_begin; l < a.l_end; l++) {
             const float* P = Wl + (size_t)(l - a.l_begin) * lsm;
-            const float* Wq = P;                               // q | k | v | out, each [dk][dk+1]
-            const float* Wo = P + 3 * dk * (dk + 1);
-            const float* n1 = Wo + dk * (dk + 1);
-            const float* W1 = n1 + 2 * dk;
-            const float* b1 = W1 + dff * (dk + 1);
-            const float* W2 = b1 + dff;
-            const float* b2 = W2 + dk * (dff + 1);
+            const float* Wq = P;                               // [dk][3dk]: q | k | v columns
+            const float* Wo = P + 3 * dk * dk;                 // [dk][dk]
+            const float* n1 = Wo + dk * dk;
+            const float* W1 = n1 + 2 * dk;                     // [dk][dff]
+            const float* b1 = W1 + dff * dk;
+            const float* W2 = b1 + dff;                        // [dff][dk]
+            const float* b2 = W2 + dk * dff;
             const float* n2 = b2 + dk;
             const int t0 = (l == a.layers - 1) ? T - 1 : 0;    // only the last step leaves the core
             // keys / values for every step, queries from t0 on (q rows < t0 are computed too when t0 == 0 only)
-            tfm_linear(y, dk, Wq + dk * (dk + 1), nullptr, qkv + dk, 3 * dk, 0, T, 2 * dk, dk, false);     // k | v (rows contiguous in Wq)
-            tfm_linear(y, dk, Wq, nullptr, qkv, 3 * dk, t0, T, dk, dk, false);                             // q
+            if (t0 == 0) tfm_linear(y, dk, Wq, 3 * dk, nullptr, qkv, 3 * dk, 0, T, 3 * dk, dk, false);    // q | k | v
+            else {
+                tfm_linear(y, dk, Wq + dk, 3 * dk, nullptr, qkv + dk, 3 * dk, 0, T, 2 * dk, dk, false);   // k | v for every step
+                tfm_linear(y, dk, Wq, 3 * dk, nullptr, qkv, 3 * dk, t0, T, dk, dk, false);                 // q for the last step
+            }
             __syncthreads();
             // attention: one thread per (head, query step)
             for (int o = tid; o < heads * (T - t0); o += blockDim.x) {
@@ -165,7 +189,7 @@ __global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCore
                 }
             }
             __syncthreads();
-            tfm_linear(att, dk, Wo, nullptr, qkv, 3 * dk, t0, T, dk, dk, false);          // out projection -> qkv[:, 0:dk] (q is dead)
+            tfm_linear(att, dk, Wo, dk, nullptr, qkv, 3 * dk, t0, T, dk, dk, false);          // out projection -> qkv[:, 0:dk] (q is dead)
             __syncthreads();
             // y = LN(y + o): gather the projection rows through a strided view
             {
@@ -182,9 +206,9 @@ __global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCore
                 }
             }
             __syncthreads();
-            tfm_linear(y, dk, W1, b1, ff, dff, t0, T, dff, dk, true);
+            tfm_linear(y, dk, W1, dff, b1, ff, dff, t0, T, dff, dk, true);
             __syncthreads();
-            tfm_linear(ff, dff, W2, b2, att, dk, t0, T, dk, dff, false);
+            tfm_linear(ff, dff, W2, dk, b2, att, dk, t0, T, dk, dff, false);
             __syncthreads();
             tfm_add_ln(y, att, n2, n2 + dk, t0, T, dk);
             __syncthreads();

@@ -132,3 +132,94 @@ class TFMEncoderB200:
         return (out, nodes, edges) if return_cores else out
 
     __call__ = encode
+
+
+class TFMModelB200:
+    """Inference stand-in for the reference models built with ``encoder_type="transformer"`` (``VaDEPT``, ``VQVAEPT``,
+    ``ContrastivePT``): the transformer encoder plus the read-out ``embedding_per_video`` needs — VaDE: ``z_mean`` and the
+    GMM posterior (``GaussianMixtureLatentPT``, models_new.py:1745-1791); VQ-VAE: encoder output and soft counts
+    (``VectorQuantizerPT``, :1358-1423); contrastive: the encoder output.  The transformer decoder and the training step
+    are not built: ``__call__`` / ``train`` raise.  ``load_state_dict`` takes the reference checkpoint's state_dict; the
+    decoder's tensors are kept on the host so that ``state_dict()`` round-trips."""
+
+    def __init__(self, model_name: str, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int,
+                 n_components: int = 1, max_batch: int = 1024, device: Optional[int] = None, seed: Optional[int] = None):
+        self.model_name = str(model_name).lower()
+        if self.model_name not in ("vade", "vqvae", "contrastive"):
+            raise ValueError(f"unknown model_name {model_name!r}")
+        if self.model_name == "contrastive":                     # ContrastivePT encodes half windows (models_new.py:2013)
+            input_shape = (int(input_shape[0]) // 2,) + tuple(input_shape[1:])
+            edge_feature_shape = (int(edge_feature_shape[0]) // 2,) + tuple(edge_feature_shape[1:])
+        self.encoder = TFMEncoderB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, max_batch=max_batch,
+                                      device=device, seed=seed)
+        self.input_shape, self.edge_feature_shape = self.encoder.input_shape, self.encoder.edge_feature_shape
+        self.latent_dim, self.n_components, self.max_batch = int(latent_dim), int(n_components), int(max_batch)
+        self.window_size, self.device, self.L = self.encoder.window_size, self.encoder.device, self.encoder.L
+        self.training_capable = False
+        D, K = self.latent_dim, self.n_components
+        if self.model_name == "vade":
+            shapes = {"latent_space.gmm_means": (K, D), "latent_space.gmm_log_vars": (K, D), "latent_space.prior": (K,),
+                      "latent_space.encoder_mean.weight": (D, D), "latent_space.encoder_mean.bias": (D,),
+                      "latent_space.encoder_log_var.weight": (D, D), "latent_space.encoder_log_var.bias": (D,)}
+        elif self.model_name == "vqvae":
+            shapes = {"vq_layer.codebook": (D, K)}
+        else:
+            shapes = {}
+        self._head = {k: torch.zeros(s, device=self.device) for k, s in shapes.items()}
+        if "latent_space.prior" in self._head:
+            self._head["latent_space.prior"].fill_(1.0 / K)
+        self._other: Dict[str, torch.Tensor] = {}
+
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("the training step of the transformer model family is not built; eval() only")
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {"encoder." + k: v for k, v in self.encoder.state_dict().items()}
+        out.update({k: v.clone() for k, v in self._head.items()})
+        out.update(self._other)
+        return out
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        self.encoder.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=strict)
+        for k, v in self._head.items():
+            if k in sd:
+                v.copy_(torch.as_tensor(sd[k]).to(self.device, torch.float32).reshape(v.shape))
+            elif strict:
+                raise KeyError(k)
+        self._other = {k: torch.as_tensor(v).clone() for k, v in sd.items() if not k.startswith("encoder.") and k not in self._head}
+
+    def encode(self, x, a):
+        return self.encoder(x, a)
+
+    def embed(self, x, a):
+        """``(embedding [B,D], soft assignments [B,K] or None)`` exactly as ``embedding_per_video`` reads them from the
+        reference models (model_utils_new.py:585-612)."""
+        enc = self.encoder(x, a)
+        B, D, K = enc.shape[0], self.latent_dim, self.n_components
+        h = self._head
+        if self.model_name == "vade":
+            emb, q = torch.empty(B, D, device=self.device), torch.empty(B, K, device=self.device)
+            scratch = torch.empty(3 * B * D, device=self.device)
+            check(self.L.dof_latent_eval(ptr(enc), ptr(h["latent_space.encoder_mean.weight"]), ptr(h["latent_space.encoder_mean.bias"]),
+                                         ptr(h["latent_space.encoder_log_var.weight"]), ptr(h["latent_space.encoder_log_var.bias"]),
+                                         ptr(h["latent_space.gmm_means"]), ptr(h["latent_space.gmm_log_vars"]), ptr(h["latent_space.prior"]),
+                                         B, D, K, ptr(emb), ptr(q), ptr(scratch), _stream()))
+            return emb, q
+        if self.model_name == "vqvae":
+            quant, soft = torch.empty(B, D, device=self.device), torch.empty(B, K, device=self.device)
+            idx = torch.empty(B, dtype=torch.int32, device=self.device)
+            scratch = torch.empty(4 + D * D + K, dtype=torch.float64, device=self.device)
+            check(self.L.dof_vq_eval(ptr(enc), ptr(h["vq_layer.codebook"]), B, D, K, ptr(quant), ptr(soft), ptr(idx), ptr(scratch), _stream()))
+            return enc, soft
+        return enc, None
+
+    def __call__(self, *a, **k):
+        raise NotImplementedError("the transformer decoder is not built: use .embed(x, a) / .encoder(x, a)")

@@ -296,6 +296,16 @@ size_t dof_tfm_workspace_bytes(const dof_tfm_cfg* cfg, int B);
 int dof_tfm_encode(const dof_tfm_cfg* cfg, const float* state, const float* x, const float* a, int B, void* workspace,
                    size_t workspace_bytes, float* enc_out, float* nodes_out, float* edges_out, void* stream);
 
+/* Read-outs on an encoder output enc [B,D] (what embedding_per_video needs from the transformer model family):
+ * dof_latent_eval = GaussianMixtureLatentPT in eval mode (models_new.py:1745-1791): emb = z_mean, q = GMM posterior;
+ * scratch 3*B*D floats.  dof_vq_eval = VectorQuantizerPT (models_new.py:1358-1423): quantized latents, soft counts,
+ * code indices; scratch (4 + D*D + K) doubles. */
+int dof_latent_eval(const float* enc, const float* Wm, const float* bm, const float* Wv, const float* bv,
+                    const float* gmm_mu, const float* gmm_lv, const float* prior, int B, int D, int K, float* emb,
+                    float* q, float* scratch, void* stream);
+int dof_vq_eval(const float* enc, const float* codebook, int B, int D, int K, float* quant, float* soft, int* idx,
+                double* scratch, void* stream);
+
 /* Debug / test access to intermediate activations of the last forward (device pointers into
  * the workspace; NULL if unknown).  Names: "node_out","edge_out","enc","z","z_mean",
  * "z_log_var","q","loc","len_node","len_edge". */

@@ -66,8 +66,61 @@ def run(name, c):
     print("tfm", name, "%.1f KB" % (os.path.getsize(path) / 1024), "out", float(out.abs().mean()))
 
 
+MODEL_CASES = {
+    # full reference models with encoder_type="transformer" in eval mode: what embedding_per_video reads from them
+    "vade": dict(model="vade", T=25, N=14, D=8, K=5, B=10, seed=61),
+    "vqvae": dict(model="vqvae", T=24, N=11, D=6, K=7, B=9, seed=62),
+    "contrastive": dict(model="contrastive", T=25, N=14, D=8, K=1, B=8, seed=63),
+}
+
+
+def run_model(name, c):
+    torch.manual_seed(c["seed"])
+    torch.set_num_threads(1)
+    adj = default_adjacency(c["N"])
+    E = int(np.count_nonzero(np.triu(adj)))
+    xs, as_ = (c["T"], c["N"], 3), (c["T"], E, 1)
+    if c["model"] == "vade":
+        model = M.VaDEPT(xs, as_, adj, c["D"], c["K"], encoder_type="transformer")
+    elif c["model"] == "vqvae":
+        model = M.VQVAEPT(xs, as_, adj, c["D"], c["K"], encoder_type="transformer", use_gnn=True)
+    else:
+        model = M.ContrastivePT(xs, as_, adj, c["D"], encoder_type="transformer", use_gnn=True)
+    model.train()
+    Tenc = c["T"] // 2 if c["model"] == "contrastive" else c["T"]     # ContrastivePT encodes half windows (:2013)
+    with torch.no_grad():
+        for i in range(3):                                   # builds the CensNet parameters, moves the BN statistics
+            xi, ai = synthetic_windows(32, Tenc, adj, seed=7000 + 10 * c["seed"] + i)
+            model.encoder(xi, ai)
+        if c["model"] == "vade":
+            model.latent_space.gmm_means.mul_(3.0)
+        if c["model"] == "vqvae":
+            model.vq_layer.codebook.copy_(0.5 * torch.randn(c["D"], c["K"]))
+    model.eval()
+    x, a = synthetic_windows(c["B"], Tenc, adj, seed=8000 + c["seed"])
+    res = {"adjacency": adj, "x": x.numpy(), "a": a.numpy(),
+           "meta": np.array([c["T"], c["N"], E, c["D"], c["K"], c["B"]], dtype=np.int64), "model": np.array(c["model"])}
+    with torch.no_grad():
+        if c["model"] == "vade":
+            out = model(x, a)                                 # (dist, emb, q, kmeans): model_utils_new.py:585-596
+            res["eval/emb"], res["eval/q"] = out[1].numpy(), out[2].numpy()
+        elif c["model"] == "vqvae":
+            out = model(x, a, return_all_outputs=True)        # soft counts [3], encoder output [4]
+            res["eval/emb"], res["eval/q"] = out[4].numpy(), out[3].numpy()
+        else:
+            res["eval/emb"] = model(x, a).numpy()
+    for k, v in model.state_dict().items():
+        res["p/" + k] = v.detach().numpy().copy()
+    path = os.path.join(HERE, f"tfmmodel_{name}.npz")
+    np.savez_compressed(path, **res)
+    print("tfmmodel", name, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for name, c in CASES.items():
         if not only or name in only:
             run(name, c)
+    for name, c in MODEL_CASES.items():
+        if not only or ("model_" + name) in only:
+            run_model(name, c)

@@ -72,3 +72,37 @@ def test_tfm_encoder_wide_key_dim_runs_layer_by_layer():
     assert rel_l2(out.cpu(), ref["out"]) < 1e-4
     with pytest.raises(NotImplementedError):
         m.train()
+
+
+TFMM = golden_cases_of("tfmmodel")
+
+
+@pytest.mark.parametrize("case", TFMM)
+def test_transformer_model_embeddings_from_reference_checkpoint(case, tmp_path):
+    """A reference checkpoint of a transformer-encoder model (state_dict + rebuild_spec, model_utils_new.py:263-329)
+    loads through load_model_from_ckpt and yields the embeddings / soft assignments embedding_per_video reads."""
+    from deepof_b200 import load_model_from_ckpt
+    g = load_golden_of("tfmmodel", case)
+    T, N, E, D, K, B = (int(v) for v in g["meta"])
+    name = str(g["model"])
+    spec = dict(model_name=name, x_shape=(T, N, 3), a_shape=(T, E, 1), adjacency_matrix=g["adjacency"], latent_dim=D, n_components=K,
+                encoder_type="transformer", use_gnn=True, kmeans_loss=0.0, interaction_regularization=0.0, lens_enabled=False)
+    path = tmp_path / "ckpt.pth"
+    torch.save({"state_dict": {k[2:]: torch.from_numpy(np.asarray(g[k])) for k in g if k.startswith("p/")}, "rebuild_spec": spec,
+                "log_summary": {"ok": 1}}, path)
+    m, summary = load_model_from_ckpt(str(path), max_batch=64)
+    assert summary == {"ok": 1} and m.window_size == (T // 2 if name == "contrastive" else T)
+    emb, q = m.embed(torch.from_numpy(g["x"]), torch.from_numpy(g["a"]))
+    assert rel_l2(emb.cpu(), g["eval/emb"]) < 1e-4, rel_l2(emb.cpu(), g["eval/emb"])
+    if name == "contrastive":
+        assert q is None
+    else:
+        assert rel_l2(q.cpu(), g["eval/q"]) < 1e-4
+        assert torch.equal(q.argmax(1).cpu(), torch.from_numpy(g["eval/q"]).argmax(1))
+    # every tensor of the checkpoint survives a state_dict round trip (decoder tensors are carried on the host)
+    sd = m.state_dict()
+    for k in g:
+        if k.startswith("p/") and "num_batches_tracked" not in k:
+            assert k[2:] in sd, k
+    with pytest.raises(NotImplementedError):
+        m(torch.from_numpy(g["x"]), torch.from_numpy(g["a"]))
