@@ -104,9 +104,13 @@ def run_model(name, c):
         if c["model"] == "vade":
             out = model(x, a)                                 # (dist, emb, q, kmeans): model_utils_new.py:585-596
             res["eval/emb"], res["eval/q"] = out[1].numpy(), out[2].numpy()
+            res["eval/loc"] = out[0].base_dist.base_dist.loc.numpy()          # TFMDecoderPT(z = z_mean in eval)
         elif c["model"] == "vqvae":
             out = model(x, a, return_all_outputs=True)        # soft counts [3], encoder output [4]
             res["eval/emb"], res["eval/q"] = out[4].numpy(), out[3].numpy()
+            res["eval/quant"] = out[2].numpy()
+            res["eval/loc_q"] = out[0].base_dist.base_dist.loc.numpy()        # decoder(quantized)
+            res["eval/loc"] = out[1].base_dist.base_dist.loc.numpy()          # decoder(encoder output)
         else:
             res["eval/emb"] = model(x, a).numpy()
     for k, v in model.state_dict().items():

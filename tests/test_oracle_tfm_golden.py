@@ -30,3 +30,20 @@ def test_tfm_encoder_eval(case):
     if case == "padded":      # the key-padding mask is really exercised
         xs = O.group_reshape(x).reshape(B * N, x.shape[1], 3)
         assert bool((xs == 0).all(-1).any())
+
+
+@pytest.mark.parametrize("case", [c for c in golden_cases_of("tfmmodel") if c != "contrastive"])
+def test_tfm_decoder_eval(case):
+    """TFMDecoderPT in eval mode on the latent the reference fed it (VaDE: z_mean, VQ-VAE: encoder output / codes)."""
+    g = load_golden_of("tfmmodel", case)
+    p = sub(g, "p/")
+    x = torch.from_numpy(g["x"])
+    B, T, N, F = x.shape
+    xf = x.reshape(B, T, N * F)
+    with torch.no_grad():
+        loc, mask = TO.decoder_forward_eval(torch.from_numpy(g["eval/emb"]), xf, p)
+        assert rel_l2(loc, g["eval/loc"]) < 1e-5
+        if "eval/loc_q" in g:
+            loc_q, _ = TO.decoder_forward_eval(torch.from_numpy(g["eval/quant"]), xf, p)
+            assert rel_l2(loc_q, g["eval/loc_q"]) < 1e-5
+    assert bool(mask.all())
