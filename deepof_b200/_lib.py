@@ -69,6 +69,10 @@ class DofTfmCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("T", "N", "E", "F", "Fe", "D", "key_dim", "heads", "dff", "layers")]
 
 
+class DofTfmDecCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("T", "Dx", "D", "heads", "dff", "layers")]
+
+
 class DofError(RuntimeError):
     pass
 
@@ -109,6 +113,12 @@ _SIGS = {
     "dof_tfm_encode": (C.c_int, [C.POINTER(DofTfmCfg), _P, _P, _P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P]),
     "dof_latent_eval": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "dof_vq_eval": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "dof_tfm_dec_numel": (C.c_int64, [C.POINTER(DofTfmDecCfg)]),
+    "dof_tfm_dec_num_entries": (C.c_int, [C.POINTER(DofTfmDecCfg)]),
+    "dof_tfm_dec_entry": (C.c_int, [C.POINTER(DofTfmDecCfg), C.c_int, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dof_tfm_dec_workspace_bytes": (C.c_size_t, [C.POINTER(DofTfmDecCfg), C.c_int]),
+    "dof_tfm_decode": (C.c_int, [C.POINTER(DofTfmDecCfg), _P, _P, C.c_int, _P, C.c_size_t, _P, _P]),
     "dof_adam_flat": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                 C.c_float, _P]),
     "dof_contrastive_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P,

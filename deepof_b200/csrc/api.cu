@@ -469,16 +469,16 @@ int dof_destroy(dof_handle* h) {
 // forward
 // ---------------------------------------------------------------------------
 static int ln_fwd(const float* x, const float* w, const float* b, float* y, float* mu, float* rs, long long R,
-                  int W, int sm, cudaStream_t st) {
+                  int W, int sm, cudaStream_t st, float eps = 1e-3f) {
     if (W > 32 * LN_MAXV) DOF_FAIL(DOF_ERR_UNSUPPORTED, "LayerNorm width %d > %d", W, 32 * LN_MAXV);
     long long blocks = (R + 7) / 8;
     int grid = (int)(blocks < (long long)sm * 16 ? blocks : (long long)sm * 16);
     if (grid < 1) return DOF_OK;
     { ProfScope ps("ln_fwd", st, 0.0, 8.0 * R * W);
-    if (W <= 32) ln_fwd_kernel<1, 4><<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W);
-    else if (W <= 64) ln_fwd_kernel<2, 4><<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W);
-    else if (W <= 128) ln_fwd_kernel<4, 2><<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W);
-    else ln_fwd_kernel<8, 1><<<grid, 256, 0, st>>>(x, w, b, 1e-3f, y, mu, rs, R, W); }
+    if (W <= 32) ln_fwd_kernel<1, 4><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W);
+    else if (W <= 64) ln_fwd_kernel<2, 4><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W);
+    else if (W <= 128) ln_fwd_kernel<4, 2><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W);
+    else ln_fwd_kernel<8, 1><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -1349,6 +1349,166 @@ int dof_tfm_encode(const dof_tfm_cfg* cfg, const float* state, const float* x, c
     { ProfScope ps("tfm_head_fwd", st);
     tfm_head_fwd_kernel<<<cdiv(B, 4), 128, hsm, st>>>(hargs); }
     DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+}  // extern "C"
+
+// ---- transformer decoder, eval forward ---------------------------------------------------------------------------
+struct TfmDecLayout {
+    std::vector<Entry> e;
+    int64_t total = 0;
+    int64_t ex_w[3], ex_b[3], layer[8], out_w, out_b, loc_w, loc_b;
+};
+
+static int check_tfm_dec_cfg(const dof_tfm_dec_cfg* c) {
+    if (!c) DOF_FAIL(DOF_ERR_ARG, "null config");
+    if (c->T < 1 || c->Dx < 1 || c->D < 1 || c->heads < 1 || c->dff < 1 || c->layers < 1 || c->layers > 8) DOF_FAIL(DOF_ERR_ARG, "bad decoder geometry");
+    if ((4 * c->D) % c->heads) DOF_FAIL(DOF_ERR_ARG, "model_dim %d is not a multiple of heads %d", 4 * c->D, c->heads);
+    if (c->T > TFM_MAXT) DOF_FAIL(DOF_ERR_UNSUPPORTED, "window length %d > %d", c->T, TFM_MAXT);
+    if ((size_t)c->T * 12 * c->D * 4 > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "sequence of %d x %d does not fit the attention kernel", c->T, 12 * c->D);
+    return DOF_OK;
+}
+
+static TfmDecLayout build_tfm_dec_layout(const dof_tfm_dec_cfg& c) {
+    TfmDecLayout L;
+    auto add = [&](const std::string& name, int d0, int d1 = -1) {
+        Entry en;
+        en.name = name; en.off = L.total; en.group = 2;
+        en.shape[0] = d0; en.shape[1] = d1 < 0 ? 0 : d1; en.shape[2] = en.shape[3] = 0;
+        en.ndim = d1 < 0 ? 1 : 2;
+        en.numel = d1 < 0 ? d0 : (int64_t)d0 * d1;
+        L.total += en.numel;
+        L.e.push_back(en);
+        return en.off;
+    };
+    const int D = c.D, dm = 4 * D;
+    const int ein[3] = {D, D, 2 * D}, eout[3] = {D, 2 * D, 4 * D};
+    for (int i = 0; i < 3; i++) {
+        L.ex_w[i] = add("latent_expand." + std::to_string(2 * i) + ".weight", eout[i], ein[i]);
+        L.ex_b[i] = add("latent_expand." + std::to_string(2 * i) + ".bias", eout[i]);
+    }
+    for (int l = 0; l < c.layers; l++) {
+        std::string q = "layers." + std::to_string(l) + ".";
+        L.layer[l] = add(q + "q_proj.weight", dm, dm); add(q + "k_proj.weight", dm, dm); add(q + "v_proj.weight", dm, dm);
+        add(q + "out_proj.weight", dm, dm);
+        add(q + "norm1.weight", dm); add(q + "norm1.bias", dm); add(q + "norm2.weight", dm); add(q + "norm2.bias", dm);
+        add(q + "ffn.0.weight", c.dff, dm); add(q + "ffn.0.bias", c.dff); add(q + "ffn.3.weight", dm, c.dff); add(q + "ffn.3.bias", dm);
+    }
+    L.out_w = add("output_proj.weight", c.Dx, dm); L.out_b = add("output_proj.bias", c.Dx);
+    L.loc_w = add("prob_decoder.loc_projection.weight", c.Dx, c.Dx); L.loc_b = add("prob_decoder.loc_projection.bias", c.Dx);
+    return L;
+}
+
+extern "C" {
+
+int64_t dof_tfm_dec_numel(const dof_tfm_dec_cfg* cfg) {
+    if (check_tfm_dec_cfg(cfg) != DOF_OK) return -1;
+    return build_tfm_dec_layout(*cfg).total;
+}
+int dof_tfm_dec_num_entries(const dof_tfm_dec_cfg* cfg) {
+    if (check_tfm_dec_cfg(cfg) != DOF_OK) return -1;
+    return (int)build_tfm_dec_layout(*cfg).e.size();
+}
+int dof_tfm_dec_entry(const dof_tfm_dec_cfg* cfg, int index, char* name_out, int64_t* offset_out, int64_t* numel_out, int* ndim_out,
+                      int* shape_out) {
+    DOF_TRY(check_tfm_dec_cfg(cfg));
+    TfmDecLayout L = build_tfm_dec_layout(*cfg);
+    if (index < 0 || index >= (int)L.e.size()) DOF_FAIL(DOF_ERR_ARG, "entry index %d out of range", index);
+    const Entry& e = L.e[index];
+    if (name_out) { strncpy(name_out, e.name.c_str(), 127); name_out[127] = 0; }
+    if (offset_out) *offset_out = e.off;
+    if (numel_out) *numel_out = e.numel;
+    if (ndim_out) *ndim_out = e.ndim;
+    if (shape_out) for (int i = 0; i < 4; i++) shape_out[i] = e.shape[i];
+    return DOF_OK;
+}
+
+struct TfmDecWs { float *g0, *g1, *H, *Xn, *QKV, *A, *Fh, *Y, *mu, *rs; };
+static size_t tfm_dec_plan(const dof_tfm_dec_cfg& c, int B, char* base, TfmDecWs* w) {
+    Bump bp{base, 0, 0, base == nullptr};
+    const size_t R = (size_t)B * c.T, dm = 4 * (size_t)c.D;
+    TfmDecWs t;
+    t.g0 = bp.get<float>((size_t)B * dm); t.g1 = bp.get<float>((size_t)B * dm);
+    t.H = bp.get<float>(R * dm); t.Xn = bp.get<float>(R * dm); t.QKV = bp.get<float>(R * 3 * dm); t.A = bp.get<float>(R * dm);
+    t.Fh = bp.get<float>(R * c.dff); t.Y = bp.get<float>(R * c.Dx); t.mu = bp.get<float>(R); t.rs = bp.get<float>(R);
+    if (w) *w = t;
+    return bp.off;
+}
+
+size_t dof_tfm_dec_workspace_bytes(const dof_tfm_dec_cfg* cfg, int B) {
+    if (check_tfm_dec_cfg(cfg) != DOF_OK || B < 1) return 0;
+    return tfm_dec_plan(*cfg, B, nullptr, nullptr);
+}
+
+static int gelu_inplace(float* x, long long n, cudaStream_t st) {
+    ProfScope ps("gelu", st, 0.0, 8.0 * n);
+    gelu_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, n);
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+// TFMDecoderPT.forward in eval mode: z [B,D] -> loc [B,T,Dx] (the mean of the reconstruction distribution; the validity
+// mask of x_target only scales the distribution, ProbabilisticDecoderPT models_new.py:677-710)
+int dof_tfm_decode(const dof_tfm_dec_cfg* cfg, const float* state, const float* z, int B, void* workspace, size_t workspace_bytes,
+                   float* loc_out, void* stream) {
+    DOF_TRY(check_tfm_dec_cfg(cfg));
+    if (!state || !z || !workspace || !loc_out || B < 1) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    const dof_tfm_dec_cfg& c = *cfg;
+    TfmDecWs w;
+    const size_t need = tfm_dec_plan(c, B, (char*)workspace, &w);
+    if (need > workspace_bytes) DOF_FAIL(DOF_ERR_ARG, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const TfmDecLayout L = build_tfm_dec_layout(c);
+    const int D = c.D, dm = 4 * D, T = c.T, R = B * T;
+    // latent expansion: Linear + GELU three times (:1192-1199)
+    const int ein[3] = {D, D, 2 * D}, eout[3] = {D, 2 * D, 4 * D};
+    const float* cur = z;
+    float* bufs[2] = {w.g0, w.g1};
+    for (int i = 0; i < 3; i++) {
+        float* o = bufs[i & 1];
+        GemmArgs g = gemm_args(mv_plain(cur, ein[i]), state + L.ex_w[i], ein[i], 0, state + L.ex_b[i], o, eout[i], B, eout[i], ein[i]);
+        DOF_TRY(launch_gemm_rows(&g, 1, st));
+        DOF_TRY(gelu_inplace(o, (long long)B * eout[i], st));
+        cur = o;
+    }
+    { ProfScope ps("tfm_dec_input", st);
+    tfm_dec_input_kernel<<<cdiv((long long)R * dm, 256), 256, 0, st>>>(cur, w.H, B, T, dm); }
+    DOF_LAUNCH_CHECK();
+    const size_t asmem = (size_t)T * 3 * dm * 4;
+    if (asmem > 48 * 1024) DOF_CUDA(cudaFuncSetAttribute(tfm_causal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int l = 0; l < c.layers; l++) {
+        const float* P = state + L.layer[l];
+        const float *Wq = P, *Wo = P + (size_t)3 * dm * dm, *n1 = Wo + (size_t)dm * dm, *n2 = n1 + 2 * dm;
+        const float *W1 = n2 + 2 * dm, *b1 = W1 + (size_t)c.dff * dm, *W2 = b1 + c.dff, *b2 = W2 + (size_t)dm * c.dff;
+        DOF_TRY(ln_fwd(w.H, n1, n1 + dm, w.Xn, w.mu, w.rs, R, dm, g_sm_count, st, 1e-6f));
+        if (3 * dm <= 256) {                                   // q | k | v weights are consecutive [dm, dm] tensors = one [3dm, dm]
+            GemmArgs g = gemm_args(mv_plain(w.Xn, dm), Wq, dm, 0, nullptr, w.QKV, 3 * dm, R, 3 * dm, dm);
+            DOF_TRY(launch_gemm_rows(&g, 1, st));
+        } else {
+            for (int m = 0; m < 3; m++) {
+                GemmArgs g = gemm_args(mv_plain(w.Xn, dm), Wq + (size_t)m * dm * dm, dm, 0, nullptr, w.QKV + (size_t)m * dm, 3 * dm, R, dm, dm);
+                DOF_TRY(launch_gemm_rows(&g, 1, st));
+            }
+        }
+        { ProfScope ps("tfm_causal_attn", st, 4.0 * B * T * T * dm / 2.0, (double)R * 4 * dm * 4);
+        tfm_causal_attn_kernel<<<B, 128, asmem, st>>>(w.QKV, w.A, T, dm, c.heads); }
+        DOF_LAUNCH_CHECK();
+        GemmArgs go = gemm_args(mv_plain(w.A, dm), Wo, dm, 0, nullptr, w.H, dm, R, dm, dm);
+        go.accum = 1;                                          // x = x + out_proj(attn)
+        DOF_TRY(launch_gemm_rows(&go, 1, st));
+        DOF_TRY(ln_fwd(w.H, n2, n2 + dm, w.Xn, w.mu, w.rs, R, dm, g_sm_count, st, 1e-6f));
+        GemmArgs g1 = gemm_args(mv_plain(w.Xn, dm), W1, dm, 0, b1, w.Fh, c.dff, R, c.dff, dm);
+        DOF_TRY(launch_gemm_rows(&g1, 1, st));
+        DOF_TRY(gelu_inplace(w.Fh, (long long)R * c.dff, st));
+        GemmArgs g2 = gemm_args(mv_plain(w.Fh, c.dff), W2, c.dff, 0, b2, w.H, dm, R, dm, c.dff);
+        g2.accum = 1;                                          // x = x + ffn(norm2(x))
+        DOF_TRY(launch_gemm_rows(&g2, 1, st));
+    }
+    GemmArgs gy = gemm_args(mv_plain(w.H, dm), state + L.out_w, dm, 0, state + L.out_b, w.Y, c.Dx, R, c.Dx, dm);
+    DOF_TRY(launch_gemm_rows(&gy, 1, st));
+    GemmArgs gl = gemm_args(mv_plain(w.Y, c.Dx), state + L.loc_w, c.Dx, 0, state + L.loc_b, loc_out, c.Dx, R, c.Dx, c.Dx);
+    DOF_TRY(launch_gemm_rows(&gl, 1, st));
     return DOF_OK;
 }
 

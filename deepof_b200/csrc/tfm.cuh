@@ -278,3 +278,53 @@ __global__ void __launch_bounds__(128) tfm_head_fwd_kernel(const TfmHeadArgs a) 
         a.out[(size_t)b * D + n] = acc;
     }
 }
+
+
+// ---------------------------------------------------------------------------
+// transformer decoder (row a13), eval forward, from library GEMM / LayerNorm kernels plus three small kernels
+// (TFMDecoderPT.forward models_new.py:1232-1266, CausalSelfAttentionLayer :1270-1327)
+// ---------------------------------------------------------------------------
+__global__ void gelu_kernel(float* __restrict__ x, long long n) {          // nn.GELU() default: exact erf form
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float v = x[i]; x[i] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+}
+
+// h[b, t, :] = g[b, :] + PE[t, :]  (:1247-1255)
+__global__ void tfm_dec_input_kernel(const float* __restrict__ g, float* __restrict__ h, int B, int T, int dm) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * T * dm) return;
+    const int d = (int)(i % dm), t = (int)((i / dm) % T), b = (int)(i / ((long long)dm * T));
+    const float div = expf((float)(d & ~1) * (-logf(10000.0f) / (float)dm));
+    h[i] = g[(size_t)b * dm + d] + ((d & 1) ? cosf((float)t * div) : sinf((float)t * div));
+}
+
+// softmax(q k^T / sqrt(hd) + causal mask) v for one sequence per CTA; qkv rows are q | k | v (3 dm floats)
+__global__ void __launch_bounds__(128) tfm_causal_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int dm, int heads) {
+    extern __shared__ __align__(16) float asm_[];
+    const int b = blockIdx.x, hd = dm / heads;
+    const float* src = qkv + (size_t)b * T * 3 * dm;
+    for (int i = threadIdx.x; i < T * 3 * dm; i += blockDim.x) asm_[i] = src[i];
+    __syncthreads();
+    const float qs = rsqrtf((float)hd);
+    for (int o = threadIdx.x; o < heads * T; o += blockDim.x) {
+        const int hh = o / T, tq = o % T;
+        const float* q = asm_ + (size_t)tq * 3 * dm + hh * hd;
+        float sc[TFM_MAXT];
+        float mx = -INFINITY;
+        for (int tk = 0; tk <= tq; tk++) {
+            const float* kk = asm_ + (size_t)tk * 3 * dm + dm + hh * hd;
+            float dot = 0.f;
+            for (int d = 0; d < hd; d++) dot += q[d] * kk[d];
+            sc[tk] = dot * qs;
+            mx = fmaxf(mx, sc[tk]);
+        }
+        float sum = 0.f;
+        for (int tk = 0; tk <= tq; tk++) { sc[tk] = expf(sc[tk] - mx); sum += sc[tk]; }
+        const float inv = 1.0f / sum;
+        for (int d = 0; d < hd; d++) {
+            float acc = 0.f;
+            for (int tk = 0; tk <= tq; tk++) acc += sc[tk] * asm_[(size_t)tk * 3 * dm + 2 * dm + hh * hd + d];
+            out[((size_t)b * T + tq) * dm + hh * hd + d] = acc * inv;
+        }
+    }
+}

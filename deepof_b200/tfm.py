@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DofTfmCfg, check, lib, ptr
+from ._lib import DofTfmCfg, DofTfmDecCfg, check, lib, ptr
 from .vade import _stream, graph_operators
 
 
@@ -134,13 +134,67 @@ class TFMEncoderB200:
     __call__ = encode
 
 
+class TFMDecoderB200:
+    """``TFMDecoderPT(output_shape=(T, N*F), latent_dim, num_layers=2, num_heads=8, dff=128)`` in eval mode
+    (``models_new.py:1167-1266``): ``decode(z) -> loc [B, T, N*F]``, the mean of the reconstruction distribution."""
+
+    def __init__(self, output_shape, latent_dim: int, num_layers: int = 2, num_heads: int = 8, dff: int = 128,
+                 device: Optional[int] = None, max_batch: int = 1024):
+        T, Dx = (int(v) for v in output_shape)
+        self.output_shape, self.latent_dim, self.max_batch = (T, Dx), int(latent_dim), int(max_batch)
+        self.cfg = DofTfmDecCfg(T, Dx, int(latent_dim), int(num_heads), int(dff), int(num_layers))
+        self.L = lib()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        n = self.L.dof_tfm_dec_num_entries(C.byref(self.cfg))
+        if n < 0:
+            check(-1)
+        name = C.create_string_buffer(128)
+        off, numel, ndim = C.c_int64(), C.c_int64(), C.c_int()
+        shape = (C.c_int * 4)()
+        self.layout = []
+        for i in range(n):
+            check(self.L.dof_tfm_dec_entry(C.byref(self.cfg), i, name, C.byref(off), C.byref(numel), C.byref(ndim), shape))
+            self.layout.append((name.value.decode(), off.value, numel.value, tuple(shape[: ndim.value])))
+        self.state = torch.zeros(self.L.dof_tfm_dec_numel(C.byref(self.cfg)), device=self.device)
+        self._views = {nm: self.state[o:o + ne].view(sh) for nm, o, ne, sh in self.layout}
+        for nm, v in self._views.items():
+            if nm.endswith("norm1.weight") or nm.endswith("norm2.weight"):
+                v.fill_(1.0)
+        self._ws = torch.empty(self.L.dof_tfm_dec_workspace_bytes(C.byref(self.cfg), self.max_batch), dtype=torch.uint8, device=self.device)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: v.clone() for k, v in self._views.items()}
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        sd = {(k[len("decoder."):] if k.startswith("decoder.") else k): v for k, v in sd.items()}
+        for k, v in self._views.items():
+            if k in sd:
+                v.copy_(torch.as_tensor(sd[k]).to(self.device, torch.float32).reshape(v.shape))
+            elif strict:
+                raise KeyError(k)
+
+    def decode(self, z) -> torch.Tensor:
+        T, Dx = self.output_shape
+        z = torch.as_tensor(z).to(self.device, torch.float32).contiguous()
+        B = z.shape[0]
+        loc = torch.empty(B, T, Dx, device=self.device)
+        for s in range(0, B, self.max_batch):
+            e = min(B, s + self.max_batch)
+            check(self.L.dof_tfm_decode(C.byref(self.cfg), ptr(self.state), ptr(z[s:e]), e - s, ptr(self._ws), self._ws.numel(),
+                                        ptr(loc[s:e]), _stream()))
+        return loc
+
+    __call__ = decode
+
+
 class TFMModelB200:
     """Inference stand-in for the reference models built with ``encoder_type="transformer"`` (``VaDEPT``, ``VQVAEPT``,
     ``ContrastivePT``): the transformer encoder plus the read-out ``embedding_per_video`` needs — VaDE: ``z_mean`` and the
     GMM posterior (``GaussianMixtureLatentPT``, models_new.py:1745-1791); VQ-VAE: encoder output and soft counts
-    (``VectorQuantizerPT``, :1358-1423); contrastive: the encoder output.  The transformer decoder and the training step
-    are not built: ``__call__`` / ``train`` raise.  ``load_state_dict`` takes the reference checkpoint's state_dict; the
-    decoder's tensors are kept on the host so that ``state_dict()`` round-trips."""
+    (``VectorQuantizerPT``, :1358-1423); contrastive: the encoder output.  ``reconstruct`` runs the transformer decoder
+    (``TFMDecoderB200``).  The training step is not built: ``__call__`` / ``train`` raise.  ``load_state_dict`` takes the
+    reference checkpoint's state_dict; tensors the library does not use are kept on the host so that ``state_dict()``
+    round-trips."""
 
     def __init__(self, model_name: str, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int,
                  n_components: int = 1, max_batch: int = 1024, device: Optional[int] = None, seed: Optional[int] = None):
@@ -165,6 +219,10 @@ class TFMModelB200:
             shapes = {"vq_layer.codebook": (D, K)}
         else:
             shapes = {}
+        self.decoder = None
+        if self.model_name != "contrastive":                     # models_new.py:1490-1497: heads 8, dff 128, 2 layers
+            T, N, F = self.input_shape
+            self.decoder = TFMDecoderB200((T, N * F), latent_dim, device=device, max_batch=max_batch)
         self._head = {k: torch.zeros(s, device=self.device) for k, s in shapes.items()}
         if "latent_space.prior" in self._head:
             self._head["latent_space.prior"].fill_(1.0 / K)
@@ -184,6 +242,8 @@ class TFMModelB200:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         out = {"encoder." + k: v for k, v in self.encoder.state_dict().items()}
         out.update({k: v.clone() for k, v in self._head.items()})
+        if self.decoder is not None:
+            out.update({"decoder." + k: v for k, v in self.decoder.state_dict().items()})
         out.update(self._other)
         return out
 
@@ -194,7 +254,10 @@ class TFMModelB200:
                 v.copy_(torch.as_tensor(sd[k]).to(self.device, torch.float32).reshape(v.shape))
             elif strict:
                 raise KeyError(k)
-        self._other = {k: torch.as_tensor(v).clone() for k, v in sd.items() if not k.startswith("encoder.") and k not in self._head}
+        if self.decoder is not None:
+            self.decoder.load_state_dict({k: v for k, v in sd.items() if k.startswith("decoder.")}, strict=strict)
+        self._other = {k: torch.as_tensor(v).clone() for k, v in sd.items()
+                       if not k.startswith("encoder.") and not k.startswith("decoder.") and k not in self._head}
 
     def encode(self, x, a):
         return self.encoder(x, a)
@@ -221,5 +284,13 @@ class TFMModelB200:
             return enc, soft
         return enc, None
 
+    def reconstruct(self, x, a) -> torch.Tensor:
+        """Mean of the reconstruction distribution ``model(x, a)[0]`` in eval mode: VaDE decodes ``z_mean``, VQ-VAE the
+        encoder output (``VQVAEPT.forward`` returns the decode of the quantized latents first; use ``decoder(quant)``)."""
+        if self.decoder is None:
+            raise NotImplementedError("ContrastivePT has no decoder")
+        return self.decoder(self.embed(x, a)[0])
+
     def __call__(self, *a, **k):
-        raise NotImplementedError("the transformer decoder is not built: use .embed(x, a) / .encoder(x, a)")
+        raise NotImplementedError("only inference read-outs are built for the transformer family: .embed(x, a), "
+                                  ".encoder(x, a), .reconstruct(x, a)")

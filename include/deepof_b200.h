@@ -296,6 +296,21 @@ size_t dof_tfm_workspace_bytes(const dof_tfm_cfg* cfg, int B);
 int dof_tfm_encode(const dof_tfm_cfg* cfg, const float* state, const float* x, const float* a, int B, void* workspace,
                    size_t workspace_bytes, float* enc_out, float* nodes_out, float* edges_out, void* stream);
 
+/* ---- transformer decoder, EVAL-mode forward -------------------------------------------------
+ * TFMDecoderPT.forward in eval() (models_new.py:1167-1266; CausalSelfAttentionLayer :1270-1327): latent z [B,D] ->
+ * loc [B,T,Dx], the mean of the reconstruction distribution (Dx = N*F; model_dim = 4*D, heads 8, dff 128, 2 layers in
+ * the reference).  State = the decoder's float parameters in state_dict order (dof_tfm_dec_entry), names without the
+ * "decoder." prefix.  Built from the library's GEMM / LayerNorm kernels plus GELU, positional input and causal
+ * attention kernels.  The training step is NOT built yet. */
+typedef struct dof_tfm_dec_cfg { int T, Dx, D, heads, dff, layers; } dof_tfm_dec_cfg;
+int64_t dof_tfm_dec_numel(const dof_tfm_dec_cfg* cfg);
+int dof_tfm_dec_num_entries(const dof_tfm_dec_cfg* cfg);
+int dof_tfm_dec_entry(const dof_tfm_dec_cfg* cfg, int index, char* name_out, int64_t* offset_out, int64_t* numel_out,
+                      int* ndim_out, int* shape_out);
+size_t dof_tfm_dec_workspace_bytes(const dof_tfm_dec_cfg* cfg, int B);
+int dof_tfm_decode(const dof_tfm_dec_cfg* cfg, const float* state, const float* z, int B, void* workspace,
+                   size_t workspace_bytes, float* loc_out, void* stream);
+
 /* Read-outs on an encoder output enc [B,D] (what embedding_per_video needs from the transformer model family):
  * dof_latent_eval = GaussianMixtureLatentPT in eval mode (models_new.py:1745-1791): emb = z_mean, q = GMM posterior;
  * scratch 3*B*D floats.  dof_vq_eval = VectorQuantizerPT (models_new.py:1358-1423): quantized latents, soft counts,

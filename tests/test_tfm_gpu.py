@@ -106,3 +106,24 @@ def test_transformer_model_embeddings_from_reference_checkpoint(case, tmp_path):
             assert k[2:] in sd, k
     with pytest.raises(NotImplementedError):
         m(torch.from_numpy(g["x"]), torch.from_numpy(g["a"]))
+    # transformer decoder: the mean of the reconstruction distribution
+    if name != "contrastive":
+        loc = m.reconstruct(torch.from_numpy(g["x"]), torch.from_numpy(g["a"]))
+        assert rel_l2(loc.cpu(), g["eval/loc"]) < 1e-4, rel_l2(loc.cpu(), g["eval/loc"])
+        if "eval/loc_q" in g:                                    # VQ-VAE: decode of the quantized latents
+            assert rel_l2(m.decoder(torch.from_numpy(g["eval/quant"])).cpu(), g["eval/loc_q"]) < 1e-4
+
+
+def test_tfm_decoder_vs_oracle_large_batch():
+    """B = 200 (5000 rows: the projections take the tensor-core GEMM kernel) vs the oracle."""
+    from oracle import tfm_oracle as TO
+    g = load_golden_of("tfmmodel", "vade")
+    T, N, E, D, K, B = (int(v) for v in g["meta"])
+    from deepof_b200 import TFMDecoderB200
+    dec = TFMDecoderB200((T, N * 3), D, max_batch=128)
+    dec.load_state_dict({k[2:]: g[k] for k in g if k.startswith("p/decoder.")})
+    z = torch.randn(200, D, generator=torch.Generator().manual_seed(3))
+    loc = dec(z)
+    with torch.no_grad():
+        ref, _ = TO.decoder_forward_eval(z, torch.ones(200, T, N * 3), sub(g, "p/"))
+    assert rel_l2(loc.cpu(), ref) < 1e-4
