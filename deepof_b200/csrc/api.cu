@@ -1152,7 +1152,7 @@ static int check_tfm_cfg(const dof_tfm_cfg* c) {
         DOF_FAIL(DOF_ERR_ARG, "bad transformer geometry");
     if (c->key_dim % c->heads) DOF_FAIL(DOF_ERR_ARG, "key_dim %d is not a multiple of heads %d", c->key_dim, c->heads);
     if (c->T > TFM_MAXT) DOF_FAIL(DOF_ERR_UNSUPPORTED, "window length %d > %d", c->T, TFM_MAXT);
-    if (tfm_core_smem_bytes(c->T, c->F > c->Fe ? c->F : c->Fe, c->key_dim, c->dff, 1) > 220 * 1024)
+    if (tfm_core_smem_bytes(c->T, c->F > c->Fe ? c->F : c->Fe, c->key_dim, c->dff, 1) > 227 * 1024)
         DOF_FAIL(DOF_ERR_UNSUPPORTED, "one transformer layer (key_dim %d, dff %d, T %d) does not fit shared memory", c->key_dim, c->dff, c->T);
     return DOF_OK;
 }
@@ -1237,7 +1237,7 @@ static size_t tfm_plan(const dof_tfm_cfg& c, int B, char* base, float** nodes, f
     p = bp.get<float>((size_t)B * c.E * dk); if (Pe) *Pe = p;
     p = bp.get<float>((size_t)B * c.N * c.D); if (On) *On = p;
     p = bp.get<float>((size_t)B * c.E * c.D); if (Oe) *Oe = p;
-    const bool one = tfm_core_smem_bytes(c.T, c.F > c.Fe ? c.F : c.Fe, dk, c.dff, c.layers) <= 220 * 1024;
+    const bool one = tfm_core_smem_bytes(c.T, c.F > c.Fe ? c.F : c.Fe, dk, c.dff, c.layers) <= 227 * 1024;
     if (one_launch) *one_launch = one;
     p = one ? nullptr : bp.get<float>((size_t)B * G * c.T * dk);
     if (ybuf) *ybuf = p;
@@ -1303,7 +1303,7 @@ int dof_tfm_encode(const dof_tfm_cfg* cfg, const float* state, const float* x, c
     const int dk = c.key_dim, N = c.N, E = c.E, D = c.D;
     static bool attr = false;
     if (!attr) {
-        DOF_CUDA(cudaFuncSetAttribute(tfm_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        DOF_CUDA(cudaFuncSetAttribute(tfm_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DOF_CUDA(cudaFuncSetAttribute(cens_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
@@ -1313,7 +1313,7 @@ int dof_tfm_encode(const dof_tfm_cfg* cfg, const float* state, const float* x, c
         t.x = b == 0 ? x : a; t.params = state + L.core[b]; t.out = b == 0 ? nodes : edges; t.ybuf = ybuf;
         t.B = B; t.T = c.T; t.G = b == 0 ? N : E; t.F = b == 0 ? c.F : c.Fe; t.dk = dk; t.heads = c.heads; t.dff = c.dff; t.layers = c.layers;
         const int S = B * t.G;
-        const int grid = S < g_sm_count ? S : g_sm_count;
+        const int grid = cdiv(S, TFM_GROUPS) < g_sm_count ? cdiv(S, TFM_GROUPS) : g_sm_count;
         const int per = one ? c.layers : 1;
         const double fl = (double)S * c.T * 2.0 * c.layers * (4.0 * dk * dk + 2.0 * dk * c.dff + 2.0 * c.T * dk);
         for (int l0 = 0; l0 < c.layers; l0 += per) {

@@ -14,7 +14,7 @@
 #include "common.cuh"
 
 #define TFM_MAXT 64
-#define TFM_THREADS 256
+#define TFM_THREADS 512
 
 struct TfmCoreArgs {
     const float* x;        // [B, T, G, F] window tensor (x or a)
@@ -32,20 +32,20 @@ __host__ __device__ inline int tfm_layer_smem_floats(int dk, int dff) { return t
 static inline size_t tfm_core_smem_bytes(int T, int F, int dk, int dff, int layers) {      // layers = layers per launch
     size_t fl = (size_t)dk * F + dk + (size_t)layers * tfm_layer_smem_floats(dk, dff)   // weights
               + (size_t)T * dk                       // positional encoding
-              + (size_t)T * dk * 2                   // y, att
-              + (size_t)T * 3 * dk                   // q | k | v
-              + (size_t)T * dff                      // FFN hidden
-              + (size_t)T;                           // key mask
+              + 2 * ((size_t)T * dk * 2              // per group: y, att
+                     + (size_t)T * (3 * dk + 1)      // q | k | v, odd pitch (keys of one head: conflict-free across steps)
+                     + (size_t)T * dff               // FFN hidden
+                     + (size_t)T);                   // key mask
     return fl * 4 + 64;
 }
 
 // out[t][n] = sum_k in[t][k] * Wt[k][n] (+ bias) (relu) for t in [t0, T); Wt is the transposed weight with row pitch ldw.
 // Register tile: 5 rows x 2 columns per thread (one 8-byte weight load + 5 broadcast activation loads per 10 FMAs).
 #define TFM_TT 5
-__device__ __forceinline__ void tfm_linear(const float* in, int ldin, const float* Wt, int ldw, const float* bias, float* out, int ldout,
-                                           int t0, int T, int N, int K, bool relu) {
+__device__ __forceinline__ void tfm_linear(int ltid, int nthr, const float* in, int ldin, const float* Wt, int ldw, const float* bias,
+                                           float* out, int ldout, int t0, int T, int N, int K, bool relu) {
     const int nc = N >> 1, ng = (T - t0 + TFM_TT - 1) / TFM_TT;
-    for (int tile = threadIdx.x; tile < nc * ng; tile += blockDim.x) {
+    for (int tile = ltid; tile < nc * ng; tile += nthr) {
         const int cn = (tile % nc) * 2, tb = t0 + (tile / nc) * TFM_TT;
         float acc[TFM_TT][2];
         const float bx = bias ? bias[cn] : 0.f, by = bias ? bias[cn + 1] : 0.f;
@@ -66,27 +66,34 @@ __device__ __forceinline__ void tfm_linear(const float* in, int ldin, const floa
             if (tb + i < T) {
                 float2 o = make_float2(acc[i][0], acc[i][1]);
                 if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
-                *reinterpret_cast<float2*>(out + (size_t)(tb + i) * ldout + cn) = o;
+                out[(size_t)(tb + i) * ldout + cn] = o.x;            // scalar stores: the q|k|v pitch is odd
+                out[(size_t)(tb + i) * ldout + cn + 1] = o.y;
             }
         }
     }
 }
 
 // y[t] = LayerNorm(y[t] + r[t]) for t in [t0, T): one warp per row
-__device__ __forceinline__ void tfm_add_ln(float* y, const float* r, const float* w, const float* b, int t0, int T, int dk) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+__device__ __forceinline__ void tfm_add_ln(int ltid, int nthr, float* y, const float* r, int ldr, const float* w, const float* b, int t0,
+                                           int T, int dk) {
+    const int warp = ltid >> 5, lane = ltid & 31, nw = nthr >> 5;
     for (int t = t0 + warp; t < T; t += nw) {
         float s = 0.f;
-        for (int d = lane; d < dk; d += 32) s += y[t * dk + d] + r[t * dk + d];
+        for (int d = lane; d < dk; d += 32) s += y[t * dk + d] + r[(size_t)t * ldr + d];
         const float mu = warp_sum(s) / dk;
         float q = 0.f;
-        for (int d = lane; d < dk; d += 32) { const float v = y[t * dk + d] + r[t * dk + d] - mu; q += v * v; }
+        for (int d = lane; d < dk; d += 32) { const float v = y[t * dk + d] + r[(size_t)t * ldr + d] - mu; q += v * v; }
         const float rs = rsqrtf(warp_sum(q) / dk + 1e-6f);
-        for (int d = lane; d < dk; d += 32) y[t * dk + d] = (y[t * dk + d] + r[t * dk + d] - mu) * rs * w[d] + b[d];
+        for (int d = lane; d < dk; d += 32) y[t * dk + d] = (y[t * dk + d] + r[(size_t)t * ldr + d] - mu) * rs * w[d] + b[d];
     }
 }
 
-__global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCoreArgs a) {
+#define TFM_GROUPS 2                                   // independent 256-thread groups per CTA, one sequence each
+__device__ __forceinline__ void tfm_group_sync(int grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(TFM_THREADS / TFM_GROUPS) : "memory");
+}
+
+__global__ void __launch_bounds__(TFM_THREADS, 1) tfm_core_fwd_kernel(const TfmCoreArgs a) {
     extern __shared__ __align__(16) float tfsm[];
     const int T = a.T, G = a.G, F = a.F, dk = a.dk, dff = a.dff, heads = a.heads, hd = a.dk / a.heads;
     const int tid = threadIdx.x;
@@ -96,10 +103,13 @@ __global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCore
     const int lsm = tfm_layer_smem_floats(dk, dff);
     const int nl = a.l_end - a.l_begin;
     float* pe = Wl + (size_t)nl * lsm;    // [T][dk]
-    float* y = pe + T * dk;               // [T][dk]
+    const int grp = tid / (TFM_THREADS / TFM_GROUPS), ltid = tid % (TFM_THREADS / TFM_GROUPS), nthr = TFM_THREADS / TFM_GROUPS;
+    const int ldq = 3 * dk + 1;
+    const size_t gfl = (size_t)T * dk * 2 + (size_t)T * ldq + (size_t)T * dff + T;
+    float* y = pe + T * dk + grp * gfl;   // [T][dk]      (this group's sequence)
     float* att = y + T * dk;              // [T][dk]
-    float* qkv = att + T * dk;            // [T][3dk]
-    float* ff = qkv + T * 3 * dk;         // [T][dff]
+    float* qkv = att + T * dk;            // [T][3dk + 1]
+    float* ff = qkv + T * ldq;            // [T][dff]
     float* kmask = ff + T * dff;          // [T] 1 = padded key
     // ---- weights -> shared memory (padded rows), positional encoding
     for (int i = tid; i < dk * F + dk; i += blockDim.x) We[i] = __ldg(a.params + i);
@@ -129,11 +139,11 @@ __global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCore
     __syncthreads();
     const float scale = sqrtf((float)dk), qs = rsqrtf((float)hd);
     const int S = a.B * G;
-    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    for (int s = blockIdx.x * TFM_GROUPS + grp; s < S; s += gridDim.x * TFM_GROUPS) {
         const int b = s / G, g = s % G;
         const float* xw = a.x + (size_t)b * T * G * F;
         // ---- A.1 gather + padding mask + embedding: y = relu(x We^T + be) * sqrt(dk) + PE
-        for (int i = tid; i < T * dk; i += blockDim.x) {
+        for (int i = ltid; i < T * dk; i += nthr) {
             const int t = i / dk, d = i % dk;
             float acc = be[d];
             bool allz = true;
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCore
             y[i] = a.l_begin == 0 ? fmaxf(acc, 0.f) * scale + pe[i] : a.ybuf[(size_t)s * T * dk + i];
             if (d == 0) kmask[t] = allz ? 1.f : 0.f;
         }
-        __syncthreads();
+        tfm_group_sync(grp);
         for (int l = a.l_begin; l < a.l_end; l++) {
             const float* P = Wl + (size_t)(l - a.l_begin) * lsm;
             const float* Wq = P;                               // [dk][3dk]: q | k | v columns
@@ -159,66 +169,75 @@ __global__ void __launch_bounds__(TFM_THREADS) tfm_core_fwd_kernel(const TfmCore
             const float* n2 = b2 + dk;
             const int t0 = (l == a.layers - 1) ? T - 1 : 0;    // only the last step leaves the core
             // keys / values for every step, queries from t0 on (q rows < t0 are computed too when t0 == 0 only)
-            if (t0 == 0) tfm_linear(y, dk, Wq, 3 * dk, nullptr, qkv, 3 * dk, 0, T, 3 * dk, dk, false);    // q | k | v
+            if (t0 == 0) tfm_linear(ltid, nthr, y, dk, Wq, 3 * dk, nullptr, qkv, ldq, 0, T, 3 * dk, dk, false);    // q | k | v
             else {
-                tfm_linear(y, dk, Wq + dk, 3 * dk, nullptr, qkv + dk, 3 * dk, 0, T, 2 * dk, dk, false);   // k | v for every step
-                tfm_linear(y, dk, Wq, 3 * dk, nullptr, qkv, 3 * dk, t0, T, dk, dk, false);                 // q for the last step
+                tfm_linear(ltid, nthr, y, dk, Wq + dk, 3 * dk, nullptr, qkv + dk, ldq, 0, T, 2 * dk, dk, false);   // k | v for every step
+                tfm_linear(ltid, nthr, y, dk, Wq, 3 * dk, nullptr, qkv, ldq, t0, T, dk, dk, false);                 // q for the last step
             }
-            __syncthreads();
-            // attention: one thread per (head, query step)
-            for (int o = tid; o < heads * (T - t0); o += blockDim.x) {
-                const int hh = o / (T - t0), tq = t0 + o % (T - t0);
-                const float* q = qkv + (size_t)tq * 3 * dk + hh * hd;
-                float sc[TFM_MAXT];
-                float mx = -INFINITY;
-                for (int tk = 0; tk < T; tk++) {
-                    const float* kk = qkv + (size_t)tk * 3 * dk + dk + hh * hd;
-                    float dot = 0.f;
-                    for (int d = 0; d < hd; d++) dot += q[d] * kk[d];
-                    dot = kmask[tk] != 0.f ? -INFINITY : dot * qs;
-                    sc[tk] = dot;
-                    mx = fmaxf(mx, dot);
-                }
-                float sum = 0.f;
-                for (int tk = 0; tk < T; tk++) { sc[tk] = expf(sc[tk] - mx); sum += sc[tk]; }
-                const float inv = 1.0f / sum;
-                for (int d = 0; d < hd; d++) {
-                    float acc = 0.f;
-                    for (int tk = 0; tk < T; tk++) acc += sc[tk] * qkv[(size_t)tk * 3 * dk + 2 * dk + hh * hd + d];
-                    att[(size_t)tq * dk + hh * hd + d] = acc * inv;
-                }
-            }
-            __syncthreads();
-            tfm_linear(att, dk, Wo, dk, nullptr, qkv, 3 * dk, t0, T, dk, dk, false);          // out projection -> qkv[:, 0:dk] (q is dead)
-            __syncthreads();
-            // y = LN(y + o): gather the projection rows through a strided view
+            tfm_group_sync(grp);
+            // attention: one WARP per (head, query step); lanes own keys (scores, softmax by shuffles), then head dims
             {
-                const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-                for (int t = t0 + warp; t < T; t += nw) {
-                    float sm = 0.f;
-                    for (int d = lane; d < dk; d += 32) sm += y[t * dk + d] + qkv[(size_t)t * 3 * dk + d];
-                    const float mu = warp_sum(sm) / dk;
-                    float qv = 0.f;
-                    for (int d = lane; d < dk; d += 32) { const float v = y[t * dk + d] + qkv[(size_t)t * 3 * dk + d] - mu; qv += v * v; }
-                    const float rs = rsqrtf(warp_sum(qv) / dk + 1e-6f);
-                    for (int d = lane; d < dk; d += 32)
-                        y[t * dk + d] = (y[t * dk + d] + qkv[(size_t)t * 3 * dk + d] - mu) * rs * n1[d] + n1[dk + d];
+                const int warp = ltid >> 5, lane = ltid & 31, nw = nthr >> 5;
+                for (int o = warp; o < heads * (T - t0); o += nw) {
+                    const int hh = o / (T - t0), tq = t0 + o % (T - t0);
+                    const float* q = qkv + (size_t)tq * ldq + hh * hd;
+                    float sc[TFM_MAXT / 32];
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < TFM_MAXT / 32; c++) {
+                        const int tk = lane + 32 * c;
+                        float dot = -INFINITY;
+                        if (tk < T && kmask[tk] == 0.f) {
+                            const float* kk = qkv + (size_t)tk * ldq + dk + hh * hd;
+                            dot = 0.f;
+                            for (int d = 0; d < hd; d++) dot += q[d] * kk[d];
+                            dot *= qs;
+                        }
+                        sc[c] = dot;
+                        mx = fmaxf(mx, dot);
+                    }
+                    mx = warp_max(mx);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int c = 0; c < TFM_MAXT / 32; c++) {
+                        const int tk = lane + 32 * c;
+                        sc[c] = tk < T ? expf(sc[c] - mx) : 0.f;          // all keys masked: exp(-inf + inf) = NaN like the reference
+                        sum += sc[c];
+                    }
+                    sum = warp_sum(sum);
+                    const float inv = 1.0f / sum;
+                    for (int d0 = 0; d0 < hd; d0 += 32) {
+                        const int d = d0 + lane;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int c = 0; c < TFM_MAXT / 32; c++) {
+                            for (int j = 0; j < 32 && j + 32 * c < T; j++) {
+                                const float pj = __shfl_sync(0xffffffffu, sc[c], j);
+                                if (d < hd) acc += pj * qkv[(size_t)(j + 32 * c) * ldq + 2 * dk + hh * hd + d];
+                            }
+                        }
+                        if (d < hd) att[(size_t)tq * dk + hh * hd + d] = acc * inv;
+                    }
                 }
             }
-            __syncthreads();
-            tfm_linear(y, dk, W1, dff, b1, ff, dff, t0, T, dff, dk, true);
-            __syncthreads();
-            tfm_linear(ff, dff, W2, dk, b2, att, dk, t0, T, dk, dff, false);
-            __syncthreads();
-            tfm_add_ln(y, att, n2, n2 + dk, t0, T, dk);
-            __syncthreads();
+            tfm_group_sync(grp);
+            tfm_linear(ltid, nthr, att, dk, Wo, dk, nullptr, qkv, ldq, t0, T, dk, dk, false);          // out projection -> qkv[:, 0:dk] (q is dead)
+            tfm_group_sync(grp);
+            tfm_add_ln(ltid, nthr, y, qkv, ldq, n1, n1 + dk, t0, T, dk);        // y = LN(y + out_proj(attention))
+            tfm_group_sync(grp);
+            tfm_linear(ltid, nthr, y, dk, W1, dff, b1, ff, dff, t0, T, dff, dk, true);
+            tfm_group_sync(grp);
+            tfm_linear(ltid, nthr, ff, dff, W2, dk, b2, att, dk, t0, T, dk, dff, false);
+            tfm_group_sync(grp);
+            tfm_add_ln(ltid, nthr, y, att, dk, n2, n2 + dk, t0, T, dk);
+            tfm_group_sync(grp);
         }
         if (a.l_end == a.layers) {
-            for (int d = tid; d < dk; d += blockDim.x) a.out[(size_t)s * dk + d] = y[(size_t)(T - 1) * dk + d];
+            for (int d = ltid; d < dk; d += nthr) a.out[(size_t)s * dk + d] = y[(size_t)(T - 1) * dk + d];
         } else {
-            for (int i = tid; i < T * dk; i += blockDim.x) a.ybuf[(size_t)s * T * dk + i] = y[i];
+            for (int i = ltid; i < T * dk; i += nthr) a.ybuf[(size_t)s * T * dk + i] = y[i];
         }
-        __syncthreads();
+        tfm_group_sync(grp);
     }
 }
 

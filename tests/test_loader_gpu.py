@@ -193,3 +193,24 @@ def test_streaming_embedding_per_video_equals_materialised_windows():
         e_all, q_all = m.embed(x, a)
         assert torch.equal(torch.cat(embs), e_all) and torch.equal(torch.cat([s for s in softs if s is not None]), q_all)
         assert softs[0].shape == (ld.n_windows_per_video[0], K)
+
+
+def test_streaming_embedding_per_video_transformer_checkpoint():
+    """The same streaming path on a transformer-encoder model restored from a reference checkpoint's tensors
+    (TFMModelB200): frames -> windows -> transformer encoder -> latent read-out, never materialising the window table."""
+    from deepof_b200 import TFMModelB200, WindowLoader, embedding_per_video
+    from helpers import load_golden_of, rel_l2
+    g = load_golden_of("tfmmodel", "vade")
+    T, N, E, D, K, B = (int(v) for v in g["meta"])
+    r, c = np.nonzero(np.triu(g["adjacency"]))
+    edges = np.stack([r, c], 1).astype(np.int32)
+    vids = [_synthetic(150, N, 8), _synthetic(T + 3, N, 9)]
+    ld = WindowLoader(vids, edges, T, nose=1, tail_base=2, align_node=0, arena_center=(250.0, 250.0))
+    m = TFMModelB200("vade", (T, N, 3), (T, E, 1), g["adjacency"], D, K, max_batch=64)
+    m.load_state_dict({k[2:]: g[k] for k in g if k.startswith("p/")})
+    embs, softs = embedding_per_video(m, ld, batch_size=50)
+    assert [e.shape[0] for e in embs] == ld.n_windows_per_video
+    x, a = ld.load(0, len(ld))
+    e_all, q_all = m.embed(x, a)
+    assert rel_l2(torch.cat(embs).cpu(), e_all.cpu()) < 1e-6 and rel_l2(torch.cat(softs).cpu(), q_all.cpu()) < 1e-6
+    assert torch.allclose(q_all.sum(1), torch.ones_like(q_all[:, 0]), atol=1e-5)
