@@ -120,8 +120,82 @@ def run_model(name, c):
     print("tfmmodel", name, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+TRAIN_CASES = {
+    # TFMEncoderPT in train(): one forward + backward of sum(out * probe) with every dropout mask recorded
+    "train_small": dict(T=12, N=11, D=6, B=7, seed=71),
+    "train_cfg5": dict(T=25, N=14, D=16, B=5, seed=72),
+}
+
+
+def run_train(name, c):
+    """The reference draws its dropout masks from the global generator inside C++ (scaled_dot_product_attention) and
+    nn.Dropout; they are REPLAYED here: re-seed, then draw bernoulli tensors of the same shapes in the same order with
+    the same kernel (empty_like().bernoulli_(1 - p), what at::dropout does).  The oracle fed with the replayed masks
+    must reproduce the reference's output and gradients — that check runs right here, so a wrong replay cannot be
+    committed."""
+    from oracle import tfm_oracle as TO
+    from oracle import vade_oracle as O
+    torch.manual_seed(c["seed"])
+    torch.set_num_threads(1)
+    adj = default_adjacency(c["N"])
+    E = int(np.count_nonzero(np.triu(adj)))
+    enc = M.TFMEncoderPT((c["T"], c["N"], 3), (c["T"], E, 1), adj, c["D"])
+    enc.train()
+    with torch.no_grad():
+        for i in range(2):
+            xi, ai = synthetic_windows(16, c["T"], adj, seed=9000 + 10 * c["seed"] + i)
+            enc(xi, ai)
+    x, a = synthetic_windows(c["B"], c["T"], adj, seed=9500 + c["seed"])
+    x[1, c["T"] // 2:] = 0.0
+    a[1, c["T"] // 2:] = 0.0
+    probe = torch.randn(c["B"], c["D"])
+    p0 = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    seed = 9900 + c["seed"]
+    torch.manual_seed(seed)
+    out = enc(x, a)
+    (out * probe).sum().backward()
+    # replay
+    torch.manual_seed(seed)
+    masks = {}
+    dk, heads, layers, rate = enc.key_dim, 4, 2, 0.1
+    for core, S in (("node", c["B"] * c["N"]), ("edge", c["B"] * E)):
+        for nm, shp in TO.dropout_mask_shapes(S, c["T"], dk, heads, layers):
+            masks[f"{core}.{nm}"] = torch.empty(shp).bernoulli_(1.0 - rate)
+    graph = O.graph_operators(adj)
+    leaf = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and k in dict(enc.named_parameters()) else v) for k, v in p0.items()}
+    o2, stats = TO.encoder_forward_train(x, a, leaf, graph, masks)
+    assert float((o2 - out).abs().max()) < 2e-5, float((o2 - out).abs().max())
+    names = [k for k, _ in enc.named_parameters()]
+    gl = torch.autograd.grad((o2 * probe).sum(), [leaf[k] for k in names], allow_unused=True)
+    for k, g2 in zip(names, gl):
+        gr = dict(enc.named_parameters())[k].grad
+        assert (gr is None) == (g2 is None), k
+        if gr is not None:
+            assert float((g2 - gr).abs().max()) <= 2e-4 * max(1.0, float(gr.abs().max())), (k, float((g2 - gr).abs().max()))
+    res = {"adjacency": adj, "x": x.numpy(), "a": a.numpy(), "probe": probe.numpy(),
+           "meta": np.array([c["T"], c["N"], E, c["D"], c["B"], dk, heads, 128, layers], dtype=np.int64),
+           "train/out": out.detach().numpy()}
+    for k, v in p0.items():
+        res["p/" + k] = v.numpy().copy()
+    for k, v in enc.state_dict().items():
+        if "running" in k:
+            res["p1/" + k] = v.detach().numpy().copy()       # running statistics after the step
+    for k, prm in enc.named_parameters():
+        if prm.grad is not None:
+            res["g/" + k] = prm.grad.detach().numpy().copy()
+    for k, m in masks.items():
+        res["mask/" + k] = np.packbits(m.numpy().astype(np.uint8).reshape(-1))
+        res["mshape/" + k] = np.array(m.shape, dtype=np.int64)
+    path = os.path.join(HERE, f"tfmtrain_{name}.npz")
+    np.savez_compressed(path, **res)
+    print("tfmtrain", name, "%.1f KB" % (os.path.getsize(path) / 1024), "out", float(out.abs().mean()))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    for name, c in TRAIN_CASES.items():
+        if not only or name in only:
+            run_train(name, c)
     for name, c in CASES.items():
         if not only or name in only:
             run(name, c)

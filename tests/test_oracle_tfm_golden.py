@@ -1,5 +1,6 @@
 """CPU: the transformer-encoder oracle (oracle/tfm_oracle.py, eval mode) vs golden vectors produced by the UNMODIFIED
 reference (tests/golden/make_golden_tfm.py)."""
+import numpy as np
 import pytest
 import torch
 
@@ -47,3 +48,40 @@ def test_tfm_decoder_eval(case):
             loc_q, _ = TO.decoder_forward_eval(torch.from_numpy(g["eval/quant"]), xf, p)
             assert rel_l2(loc_q, g["eval/loc_q"]) < 1e-5
     assert bool(mask.all())
+
+
+def _unpack_masks(g):
+    masks = {}
+    for k in g:
+        if k.startswith("mask/"):
+            shp = tuple(int(v) for v in g["mshape/" + k[5:]])
+            n = int(np.prod(shp))
+            masks[k[5:]] = torch.from_numpy(np.unpackbits(g[k])[:n].astype(np.float32)).reshape(shp)
+    return masks
+
+
+@pytest.mark.parametrize("case", golden_cases_of("tfmtrain"))
+def test_tfm_encoder_train_mode_with_recorded_dropout(case):
+    """TFMEncoderPT in train(): output, parameter gradients of sum(out * probe) and the BatchNorm running statistics
+    after the step, with the reference's dropout masks as inputs (replayed from its generator when the golden was made)."""
+    g = load_golden_of("tfmtrain", case)
+    p = sub(g, "p/")
+    x, a = torch.from_numpy(g["x"]), torch.from_numpy(g["a"])
+    graph = O.graph_operators(g["adjacency"])
+    names = [k[2:] for k in g if k.startswith("g/")]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in p.items()}
+    out, stats = TO.encoder_forward_train(x, a, leaf, graph, _unpack_masks(g), int(g["meta"][6]))
+    assert rel_l2(out.detach(), g["train/out"]) < 1e-5
+    grads = torch.autograd.grad((out * torch.from_numpy(g["probe"])).sum(), [leaf[k] for k in names])
+    flat = torch.cat([v.flatten() for v in grads])
+    ref = torch.cat([torch.from_numpy(g["g/" + k]).flatten() for k in names])
+    assert rel_l2(flat, ref) < 2e-5
+    B = x.shape[0]
+    for i in (2, 5):
+        mu, var = stats[f"head.{i}"]
+        rm = 0.99 * p[f"head.{i}.running_mean"] + 0.01 * mu
+        rv = 0.99 * p[f"head.{i}.running_var"] + 0.01 * var * B / (B - 1)
+        assert rel_l2(rm, g[f"p1/head.{i}.running_mean"]) < 1e-5 and rel_l2(rv, g[f"p1/head.{i}.running_var"]) < 1e-5
+    # about 10 % of every mask is dropped
+    for k, m in _unpack_masks(g).items():
+        assert 0.05 < 1.0 - float(m.mean()) < 0.16, k
