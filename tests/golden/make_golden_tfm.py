@@ -191,8 +191,103 @@ def run_train(name, c):
     print("tfmtrain", name, "%.1f KB" % (os.path.getsize(path) / 1024), "out", float(out.abs().mean()))
 
 
+VADE_TRAIN_CASES = {
+    "vade_main": dict(T=12, N=11, D=6, K=5, B=8, seed=81, phase="main"),
+    "vade_pretrain": dict(T=25, N=14, D=8, K=4, B=6, seed=82, phase="pretrain"),
+}
+
+
+def run_vade_train(name, c):
+    """One reference step_vade on VaDEPT(encoder_type="transformer"): logs and gradients, with the noise tensors recorded
+    (torch.randn / randn_like are wrapped; the wrappers call the originals) and the dropout masks replayed from the
+    generator as in run_train.  The oracle's step must reproduce logs and gradients right here."""
+    import types
+    from make_golden import NoiseTape
+    from oracle import tfm_oracle as TO
+    from oracle import vade_oracle as O
+    torch.manual_seed(c["seed"])
+    torch.set_num_threads(1)
+    adj = default_adjacency(c["N"])
+    E = int(np.count_nonzero(np.triu(adj)))
+    model = M.VaDEPT((c["T"], c["N"], 3), (c["T"], E, 1), adj, c["D"], c["K"], encoder_type="transformer", use_gnn=True, kmeans_loss=1.0)
+    model.train()
+    with torch.no_grad():
+        for i in range(2):
+            xi, ai = synthetic_windows(16, c["T"], adj, seed=9100 + 10 * c["seed"] + i)
+            model.encoder(xi, ai)
+        model.latent_space.gmm_means.mul_(3.0)
+    x, a = synthetic_windows(c["B"], c["T"], adj, seed=9600 + c["seed"])
+    common = U.CommonFitCfg(latent_dim=c["D"], n_components=c["K"])
+    vcfg, tcfg = U.VaDECfg(), U.TurtleTeacherCfg()
+    crit = L.VadeLoss(common, vcfg, tcfg)
+    nb = 10
+    if c["phase"] == "pretrain":
+        sched = L.Dynamic_weight_manager(nb, mode=vcfg.kl_annealing_mode_pretrain, warmup_epochs=vcfg.kl_warmup_pretrain,
+                                         max_weight=vcfg.kl_max_weight_pretrain, cooldown_epochs=vcfg.kl_cooldown_pretrain,
+                                         end_weight=vcfg.kl_end_weight_pretrain)
+        crit.set_kl_scheduler(sched)
+        sched.current_iteration = 90
+    else:
+        model.set_pretrain_mode(False)
+        crit.set_mode("main")
+        sched = L.Dynamic_weight_manager(nb, mode=vcfg.kl_annealing_mode, warmup_epochs=vcfg.kl_warmup, max_weight=vcfg.kl_max_weight,
+                                         cooldown_epochs=vcfg.kl_cooldown, end_weight=vcfg.kl_end_weight)
+        crit.set_kl_scheduler(sched)
+        sched.current_iteration = 30
+    crit.train()
+    ctx = types.SimpleNamespace(criterion=crit, apply_distill=False, train=True)
+    p0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    seed = 9950 + c["seed"]
+    torch.manual_seed(seed)
+    with NoiseTape() as tape:
+        res = T.step_vade(model, (x, a, torch.arange(c["B"])), ctx)
+    res.loss.backward()
+    draws = tape.draws
+    # ---- replay the generator: encoder masks, reparameterisation noise, decoder masks, (MC noise)
+    torch.manual_seed(seed)
+    masks = {}
+    dk = model.encoder.key_dim
+    for core, S in (("node", c["B"] * c["N"]), ("edge", c["B"] * E)):
+        for nm, shp in TO.dropout_mask_shapes(S, c["T"], dk, 4, 2):
+            masks[f"{core}.{nm}"] = torch.empty(shp).bernoulli_(0.9)
+    eps = torch.randn_like(draws[0])
+    assert torch.equal(eps, draws[0]), "the reparameterisation noise is not where the replay expects it"
+    for nm, shp in TO.decoder_mask_shapes(c["B"], c["T"], 4 * c["D"], 8, 128, 2):
+        masks[nm] = torch.empty(shp).bernoulli_(0.8)
+    mc = draws[1] if c["phase"] == "main" else None
+    klw = float(sched.get_weight())
+    ocfg = (O.LossCfg.main_defaults(c["K"], kl_weight=klw) if c["phase"] == "main" else O.LossCfg.pretrain_defaults(c["K"], kl_weight=klw))
+    logs, grads, _ = TO.vade_train_step(x, a, p0, O.graph_operators(adj), ocfg, masks, eps, mc_eps=mc)
+    for k, v in res.logs.items():
+        assert abs(logs[k] - v) <= 5e-5 * max(1.0, abs(v)), (k, logs[k], v)
+    for k, prm in model.named_parameters():
+        if prm.grad is not None:
+            assert float((grads[k] - prm.grad).abs().max()) <= 5e-4 * max(1.0, float(prm.grad.abs().max())), k
+    out = {"adjacency": adj, "x": x.numpy(), "a": a.numpy(), "phase": np.array(c["phase"]), "klw": np.array(klw),
+           "meta": np.array([c["T"], c["N"], E, c["D"], c["K"], c["B"]], dtype=np.int64), "eps": eps.numpy()}
+    if mc is not None:
+        out["mc_eps"] = mc.numpy()
+    for k, v in p0.items():
+        out["p/" + k] = v.numpy().copy()
+    for k, v in res.logs.items():
+        out["log/" + k] = np.array(v, dtype=np.float64)
+    for k, prm in model.named_parameters():
+        if prm.grad is not None:
+            out["g/" + k] = prm.grad.detach().numpy().copy()
+    for k, m in masks.items():
+        out["mask/" + k] = np.packbits(m.numpy().astype(np.uint8).reshape(-1))
+        out["mshape/" + k] = np.array(m.shape, dtype=np.int64)
+    path = os.path.join(HERE, f"tfmvade_{name}.npz")
+    np.savez_compressed(path, **out)
+    print("tfmvade", name, "%.1f KB" % (os.path.getsize(path) / 1024), {k: round(v, 4) for k, v in list(res.logs.items())[:4]})
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    sys.path.insert(0, HERE)
+    for name, c in VADE_TRAIN_CASES.items():
+        if not only or name in only:
+            run_vade_train(name, c)
     for name, c in TRAIN_CASES.items():
         if not only or name in only:
             run_train(name, c)

@@ -85,3 +85,26 @@ def test_tfm_encoder_train_mode_with_recorded_dropout(case):
     # about 10 % of every mask is dropped
     for k, m in _unpack_masks(g).items():
         assert 0.05 < 1.0 - float(m.mean()) < 0.16, k
+
+
+@pytest.mark.parametrize("case", golden_cases_of("tfmvade"))
+def test_vade_transformer_train_step(case):
+    """step_vade on VaDEPT(encoder_type="transformer"): the 13 logged terms and every parameter gradient, with the
+    reference's noise (eps, MC eps) and dropout masks (encoder + causal decoder) as inputs."""
+    g = load_golden_of("tfmvade", case)
+    p = sub(g, "p/")
+    x, a = torch.from_numpy(g["x"]), torch.from_numpy(g["a"])
+    K = int(g["meta"][4])
+    main = str(g["phase"]) == "main"
+    cfg = (O.LossCfg.main_defaults if main else O.LossCfg.pretrain_defaults)(K, kl_weight=float(g["klw"]))
+    logs, grads, _ = TO.vade_train_step(x, a, p, O.graph_operators(g["adjacency"]), cfg, _unpack_masks(g), torch.from_numpy(g["eps"]),
+                                        mc_eps=torch.from_numpy(g["mc_eps"]) if main else None)
+    for k in O.LOG_KEYS:
+        ref = float(g["log/" + k])
+        assert abs(logs[k] - ref) <= 5e-5 * max(1.0, abs(ref)), (k, logs[k], ref)
+    names = [k[2:] for k in g if k.startswith("g/")]
+    flat = torch.cat([grads[k].flatten() for k in names])
+    ref = torch.cat([torch.from_numpy(g["g/" + k]).flatten() for k in names])
+    assert rel_l2(flat, ref) < 5e-5
+    for k, v in grads.items():
+        assert (v is None) == (k not in names), k
