@@ -75,3 +75,42 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"import\s+oracle|from\s+oracle|oracle[/.]\w", src), f
+
+
+def test_transformer_layouts_are_reference_state_dict(built):
+    """dof_tfm_entry / dof_tfm_dec_entry (host-only) enumerate the float tensors of TFMEncoderPT / TFMDecoderPT in the
+    reference's state_dict order with its shapes (goldens tfm_*.npz, tfmmodel_*.npz)."""
+    from helpers import golden_cases_of, load_golden_of
+    from deepof_b200._lib import DofTfmCfg, DofTfmDecCfg
+    from deepof_b200.tfm import tfm_layout
+    L = built.lib()
+    for case in golden_cases_of("tfm"):
+        g = load_golden_of("tfm", case)
+        T, N, E, D, B, dk, heads, dff, layers = (int(v) for v in g["meta"])
+        cfg = DofTfmCfg(T, N, E, 3, 1, D, dk, heads, dff, layers)
+        lay = tfm_layout(cfg)
+        names = [k[2:] for k in g if k.startswith("p/") and "num_batches_tracked" not in k]
+        assert [l[0] for l in lay] == names
+        off = 0
+        for name, o, numel, shape in lay:
+            assert tuple(g["p/" + name].shape) == shape and o == off, name
+            off += numel
+        assert off == L.dof_tfm_numel(C.byref(cfg))
+        assert L.dof_tfm_workspace_bytes(C.byref(cfg), 64) > 0
+    g = load_golden_of("tfmmodel", "vade")
+    T, N, E, D, K, B = (int(v) for v in g["meta"])
+    dcfg = DofTfmDecCfg(T, N * 3, D, 8, 128, 2)
+    n = L.dof_tfm_dec_num_entries(C.byref(dcfg))
+    name = C.create_string_buffer(128)
+    off, numel, ndim = C.c_int64(), C.c_int64(), C.c_int()
+    shape = (C.c_int * 4)()
+    got = []
+    for i in range(n):
+        assert L.dof_tfm_dec_entry(C.byref(dcfg), i, name, C.byref(off), C.byref(numel), C.byref(ndim), shape) == 0
+        got.append((name.value.decode(), tuple(shape[: ndim.value])))
+    ref = [(k[len("p/decoder."):], tuple(g[k].shape)) for k in g if k.startswith("p/decoder.")]
+    assert got == ref
+    # bad geometry is an error code, not a crash
+    bad = DofTfmCfg(T, N, E, 3, 1, D, 42, 4, 128, 2)            # key_dim not a multiple of heads
+    assert L.dof_tfm_num_entries(C.byref(bad)) < 0 and L.dof_tfm_numel(C.byref(bad)) < 0
+    assert "key_dim" in L.dof_last_error().decode()
