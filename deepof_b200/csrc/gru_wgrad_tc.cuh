@@ -29,7 +29,10 @@ struct GruWgradMaps { CUtensorMap P[2], X[2], Hs[2]; };      // per direction: d
 struct GruWgradArgs {
     float* dWih[2]; float* dWhh[2]; float* dbih[2]; float* dbhh[2];
     int M, T, I, H;
-    int nbp, nbx;                   // 32-column blocks of dG (4H / 32) and of x (ceil(I / 32))
+    int nbp, nbx;                   // 32-column blocks of dG (4H / 32; dual: both directions) and of x (ceil(I / 32))
+    int dual;                       // H = 16: BOTH directions in one accumulator (lanes 0-63 forward gates, 64-127 reversed);
+                                    //   x is read once, h_prev comes as two full-width [32-column] blocks of Hout: rows m-1 (its
+                                    //   forward half is used) and rows m+1 (its reversed half); maps.Hs[0] spans all 2H columns
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t saddr, uint32_t lbo_bytes) {
@@ -50,7 +53,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_tc_kernel(const __gri
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gw_raw) + 1023) & ~(uintptr_t)1023);
     const int d = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nbq = a.nbx + 1;                                    // x blocks + the h_prev block
+    const int nhb = a.dual ? 2 : 1;                               // h_prev blocks
+    const int nbq = a.nbx + nhb;                                  // x blocks + the h_prev block(s)
     const int nb = a.nbp + nbq;
     const uint32_t raw_bytes = (uint32_t)(nb + 1) * GW_BLK;       // + the constant-one block (bias gradients)
     const uint32_t lo_bytes = (uint32_t)nb * GW_BLK;
@@ -105,8 +109,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_tc_kernel(const __gri
             for (int i = tid; i < n4; i += GW_LO_WARPS * 32) {
                 float4 v = raw4[i];
                 if (i >= hblk0) {
-                    const int t = (m0 + ((i - hblk0) >> 3)) % a.T;        // 8 float4 per 128-byte row
-                    if (d ? (t == a.T - 1) : (t == 0)) { v = make_float4(0.f, 0.f, 0.f, 0.f); raw4[i] = v; }
+                    const int hb = (i - hblk0) / (GW_BLK / 16);           // dual: block 0 = rows m-1 (forward), 1 = rows m+1 (reversed)
+                    const int t = (m0 + (((i - hblk0) % (GW_BLK / 16)) >> 3)) % a.T;        // 8 float4 per 128-byte row
+                    const bool rev = a.dual ? hb == 1 : d == 1;
+                    if (rev ? (t == a.T - 1) : (t == 0)) { v = make_float4(0.f, 0.f, 0.f, 0.f); raw4[i] = v; }
                 }
                 float4 lo;
                 lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -124,13 +130,15 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_tc_kernel(const __gri
             tc_fence_after();
             const int H = a.H, I = a.I;
             const int n = warp * 32 + lane;
-            const bool valid = n < 4 * H;
-            const int row_hh = n < 3 * H ? n : -1;
-            const int row_ih = n < 2 * H ? n : (n >= 3 * H ? n - H : -1);
+            const int dd = a.dual ? n / (4 * H) : d;           // direction this accumulator lane belongs to
+            const int gcol = a.dual ? n % (4 * H) : n;         // gate column inside the direction's dG
+            const bool valid = a.dual ? true : n < 4 * H;
+            const int row_hh = gcol < 3 * H ? gcol : -1;
+            const int row_ih = gcol < 2 * H ? gcol : (gcol >= 3 * H ? gcol - H : -1);
             const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
             const int hcol0 = 32 * a.nbx, onecol = 32 * nbq;
             // the gradient tensors live at arbitrary float offsets of the flat state: vector reductions only when aligned
-            const bool vih = ((reinterpret_cast<uintptr_t>(a.dWih[d]) & 15) == 0), vhh = ((reinterpret_cast<uintptr_t>(a.dWhh[d]) & 15) == 0);
+            const bool vih = ((reinterpret_cast<uintptr_t>(a.dWih[dd]) & 15) == 0), vhh = ((reinterpret_cast<uintptr_t>(a.dWhh[dd]) & 15) == 0);
             for (int c0 = 0; c0 < tcols; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
@@ -141,7 +149,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_tc_kernel(const __gri
                         for (int q = 0; q < 4; q++) {
                             const int j = c0 + 4 * q;
                             if (j < I) {
-                                float* o = a.dWih[d] + (size_t)row_ih * I + j;
+                                float* o = a.dWih[dd] + (size_t)row_ih * I + j;
                                 if (vih)
                                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[4 * q]), "f"(v[4 * q + 1]),
                                                  "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
@@ -150,12 +158,16 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_tc_kernel(const __gri
                         }
                     }
                 } else if (c0 < onecol) {
-                    if (row_hh >= 0) {
+                    // h_prev columns.  single: block columns [0, H).  dual: block 0 (rows m-1) columns [0, H) belong to the
+                    // forward lanes, block 1 (rows m+1) columns [H, 2H) to the reversed lanes
+                    const int hb = (c0 - hcol0) / 32, jb = (c0 - hcol0) % 32;
+                    const int joff = a.dual ? (hb == 1 ? H : 0) : 0;
+                    if (row_hh >= 0 && (!a.dual || hb == dd)) {
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
-                            const int j = c0 - hcol0 + 4 * q;
-                            if (j < H) {
-                                float* o = a.dWhh[d] + (size_t)row_hh * H + j;
+                            const int j = jb + 4 * q - joff;
+                            if (j >= 0 && j < H) {
+                                float* o = a.dWhh[dd] + (size_t)row_hh * H + j;
                                 if (vhh)
                                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[4 * q]), "f"(v[4 * q + 1]),
                                                  "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
@@ -164,8 +176,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_tc_kernel(const __gri
                         }
                     }
                 } else {
-                    if (row_hh >= 0) atomicAdd(a.dbhh[d] + row_hh, v[0]);
-                    if (row_ih >= 0) atomicAdd(a.dbih[d] + row_ih, v[0]);
+                    if (row_hh >= 0) atomicAdd(a.dbhh[dd] + row_hh, v[0]);
+                    if (row_ih >= 0) atomicAdd(a.dbih[dd] + row_ih, v[0]);
                 }
             }
         }
@@ -178,9 +190,16 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_tc_kernel(const __gri
                 mbar_wait(bar_empty + 8u * s, (uint32_t)(((it / GW_STAGES) & 1) ^ 1));
                 const uint32_t raw = smem_u32(sm + (size_t)s * stage_bytes), bar = bar_full + 8u * s;
                 mbar_expect_tx(bar, lo_bytes);
-                for (int b = 0; b < a.nbp; b++) tma_load_2d(raw + (uint32_t)b * GW_BLK, &maps.P[d], b * 32, m0, bar);
+                const int pper = a.dual ? a.nbp / 2 : a.nbp;               // dG blocks per direction
+                for (int b = 0; b < a.nbp; b++)
+                    tma_load_2d(raw + (uint32_t)b * GW_BLK, &maps.P[a.dual ? b / pper : d], (b % pper) * 32, m0, bar);
                 for (int b = 0; b < a.nbx; b++) tma_load_2d(raw + (uint32_t)(a.nbp + b) * GW_BLK, &maps.X[d], b * 32, m0, bar);
-                tma_load_2d(raw + (uint32_t)(a.nbp + a.nbx) * GW_BLK, &maps.Hs[d], 0, m0 + shift, bar);
+                if (a.dual) {
+                    tma_load_2d(raw + (uint32_t)(a.nbp + a.nbx) * GW_BLK, &maps.Hs[0], 0, m0 - 1, bar);
+                    tma_load_2d(raw + (uint32_t)(a.nbp + a.nbx + 1) * GW_BLK, &maps.Hs[0], 0, m0 + 1, bar);
+                } else {
+                    tma_load_2d(raw + (uint32_t)(a.nbp + a.nbx) * GW_BLK, &maps.Hs[d], 0, m0 + shift, bar);
+                }
             }
         }
     } else if (lane == 0) {
@@ -258,8 +277,12 @@ static int tmap_rows32(const float* base, int rows, int cols, int ld, CUtensorMa
     return DOF_OK;
 }
 
+static bool g_gru_wgrad_dual = getenv("DOF_GRU_WGRAD_NODUAL") == nullptr;     // env switch for A/B measurements
+static inline bool gru_wgrad_dual(int H) { return g_gru_wgrad_dual && H == 16; }
+
 static size_t gru_wgrad_smem(int H, int I) {
-    const int nbp = 4 * H / 32, nbq = cdiv(I, 32) + 1, nb = nbp + nbq;
+    const bool dual = gru_wgrad_dual(H);
+    const int nbp = (dual ? 2 : 1) * 4 * H / 32, nbq = cdiv(I, 32) + (dual ? 2 : 1), nb = nbp + nbq;
     return (size_t)GW_STAGES * ((size_t)(2 * nb + 1) * GW_BLK) + (3 * GW_STAGES + 1) * 8 + 16 + 1024 + 128;
 }
 
@@ -278,26 +301,28 @@ static int launch_gru_wgrad_tc(float* const dG[2], const float* X, int ldx, cons
     GruWgradMaps maps;
     GruWgradArgs a;
     memset(&a, 0, sizeof(a));
+    const bool dual = gru_wgrad_dual(H);
     for (int d = 0; d < 2; d++) {
         DOF_TRY(tmap_rows32(dG[d], M, 4 * H, 4 * H, &maps.P[d]));
         DOF_TRY(tmap_rows32(X, M, I, ldx, &maps.X[d]));
-        DOF_TRY(tmap_rows32(Hout + d * H, M, H, 2 * H, &maps.Hs[d]));
+        if (dual) DOF_TRY(tmap_rows32(Hout, M, 2 * H, 2 * H, &maps.Hs[d]));          // all 2H columns, both halves
+        else DOF_TRY(tmap_rows32(Hout + d * H, M, H, 2 * H, &maps.Hs[d]));
         a.dWih[d] = dWih[d]; a.dWhh[d] = dWhh[d]; a.dbih[d] = dbih[d]; a.dbhh[d] = dbhh[d];
     }
-    a.M = M; a.T = T; a.I = I; a.H = H;
-    a.nbp = 4 * H / 32; a.nbx = cdiv(I, 32);
+    a.M = M; a.T = T; a.I = I; a.H = H; a.dual = dual ? 1 : 0;
+    a.nbp = (dual ? 2 : 1) * 4 * H / 32; a.nbx = cdiv(I, 32);
     const size_t smem = gru_wgrad_smem(H, I);
     static bool attr = false;
     if (!attr) {
         DOF_CUDA(cudaFuncSetAttribute(gru_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    int ctas = sm_count / 2;
+    int ctas = dual ? sm_count : sm_count / 2;
     const int maxsplit = cdiv(M, 8 * GW_BM);
     if (ctas > maxsplit) ctas = maxsplit;
     if (ctas < 1) ctas = 1;
     ProfScope ps("gru_wgrad_tc", st, 2.0 * 2.0 * M * 3.0 * H * (I + H), 2.0 * 4.0 * M * (4.0 * H + I + H));
-    gru_wgrad_tc_kernel<<<dim3(ctas, 1, 2), GW_THREADS, smem, st>>>(maps, a);
+    gru_wgrad_tc_kernel<<<dim3(ctas, 1, dual ? 1 : 2), GW_THREADS, smem, st>>>(maps, a);
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
