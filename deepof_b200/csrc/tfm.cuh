@@ -347,3 +347,145 @@ __global__ void __launch_bounds__(128) tfm_causal_attn_kernel(const float* __res
         }
     }
 }
+
+// ---------------------------------------------------------------------------
+// Building blocks of the transformer TRAINING step (rows a12 / a13; not wired into a product path yet, op-level
+// parity-tested against autograd): multi-head attention over one sequence per CTA with an optional key-padding mask,
+// optional causal mask and inverted dropout on the attention weights (scaled_dot_product_attention with dropout_p,
+// models_new.py:880-884, 1311-1315).  The dropout decisions are an INPUT (keep [S,H,T,T] bytes, 1 = kept) so that the
+// forward and the backward agree and tests can inject the reference's masks; nothing but q|k|v is saved: the
+// backward recomputes the probabilities.
+//   forward : P = softmax(q k^T / sqrt(hd) + masks);  Pd = P * keep / (1 - p);  out = Pd v
+//   backward: dV = Pd^T dOut;  dPd = dOut v^T;  dP = dPd * keep / (1 - p);  dS = P * (dP - rowsum(dP * P));
+//             dQ = dS k / sqrt(hd);  dK = dS^T q / sqrt(hd)
+// ---------------------------------------------------------------------------
+struct TfmAttnArgs {
+    const float* qkv;            // [S, T, 3 dm]  rows q | k | v
+    const unsigned char* kpad;   // [S, T] 1 = padded key, or null
+    const unsigned char* keep;   // [S, H, T, T] dropout keep mask, or null (no dropout)
+    float* out;                  // forward: [S, T, dm]
+    const float* dout;           // backward: [S, T, dm]
+    float* dqkv;                 // backward: [S, T, 3 dm]
+    int S, T, dm, heads, causal;
+    float rate;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(128) tfm_attn_train_kernel(const TfmAttnArgs a) {
+    extern __shared__ __align__(16) float atsm[];
+    const int T = a.T, dm = a.dm, heads = a.heads, hd = dm / heads, s = blockIdx.x;
+    const int ldq = 3 * dm + 1;
+    float* sq = atsm;                          // [T][3dm + 1]
+    float* sdo = sq + (size_t)T * ldq;         // BWD: dOut [T][dm + 1]
+    float* sdq = sdo + (BWD ? (size_t)T * (dm + 1) : 0);   // BWD: dqkv accumulator [T][3dm + 1]
+    const float* src = a.qkv + (size_t)s * T * 3 * dm;
+    for (int i = threadIdx.x; i < T * 3 * dm; i += blockDim.x) sq[(i / (3 * dm)) * ldq + i % (3 * dm)] = src[i];
+    if (BWD) {
+        const float* dsrc = a.dout + (size_t)s * T * dm;
+        for (int i = threadIdx.x; i < T * dm; i += blockDim.x) sdo[(i / dm) * (dm + 1) + i % dm] = dsrc[i];
+        for (int i = threadIdx.x; i < T * ldq; i += blockDim.x) sdq[i] = 0.f;
+    }
+    __syncthreads();
+    const float qs = rsqrtf((float)hd), inv_keep = 1.0f / (1.0f - a.rate);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    // one warp per (head, query step); lanes own keys
+    for (int o = warp; o < heads * T; o += nw) {
+        const int hh = o / T, tq = o % T;
+        const float* q = sq + (size_t)tq * ldq + hh * hd;
+        float p[TFM_MAXT / 32], pd[TFM_MAXT / 32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < TFM_MAXT / 32; c++) {
+            const int tk = lane + 32 * c;
+            float dot = -INFINITY;
+            const bool vis = tk < T && !(a.causal && tk > tq) && !(a.kpad && a.kpad[(size_t)s * T + tk]);
+            if (vis) {
+                const float* kk = sq + (size_t)tk * ldq + dm + hh * hd;
+                dot = 0.f;
+                for (int d = 0; d < hd; d++) dot += q[d] * kk[d];
+                dot *= qs;
+            }
+            p[c] = dot;
+            mx = fmaxf(mx, dot);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < TFM_MAXT / 32; c++) {
+            const int tk = lane + 32 * c;
+            p[c] = tk < T ? expf(p[c] - mx) : 0.f;
+            sum += p[c];
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int c = 0; c < TFM_MAXT / 32; c++) {
+            const int tk = lane + 32 * c;
+            p[c] /= sum;
+            float kp = 1.f;
+            if (a.keep && tk < T) kp = a.keep[(((size_t)s * heads + hh) * T + tq) * T + tk] ? inv_keep : 0.f;
+            pd[c] = p[c] * kp;                 // dropped-out, rescaled weights
+        }
+        if (!BWD) {
+            for (int d0 = 0; d0 < hd; d0 += 32) {
+                const int d = d0 + lane;
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < TFM_MAXT / 32; c++)
+                    for (int j = 0; j < 32 && j + 32 * c < T; j++) {
+                        const float pj = __shfl_sync(0xffffffffu, pd[c], j);
+                        if (d < hd) acc += pj * sq[(size_t)(j + 32 * c) * ldq + 2 * dm + hh * hd + d];
+                    }
+                if (d < hd) a.out[((size_t)s * T + tq) * dm + hh * hd + d] = acc;
+            }
+        } else {
+            const float* dor = sdo + (size_t)tq * (dm + 1) + hh * hd;
+            // dPd[tk] = dOut[tq] . v[tk];  dP = dPd * keep / (1 - p);  dS = P (dP - sum_k dP_k P_k)
+            float dp[TFM_MAXT / 32];
+            float dot_pp = 0.f;
+#pragma unroll
+            for (int c = 0; c < TFM_MAXT / 32; c++) {
+                const int tk = lane + 32 * c;
+                float v = 0.f;
+                if (tk < T) {
+                    const float* vv = sq + (size_t)tk * ldq + 2 * dm + hh * hd;
+                    for (int d = 0; d < hd; d++) v += dor[d] * vv[d];
+                    // dV[tk] += Pd[tq, tk] * dOut[tq]   (different warps share tk: shared-memory atomics)
+                    for (int d = 0; d < hd; d++) atomicAdd(sdq + (size_t)tk * ldq + 2 * dm + hh * hd + d, pd[c] * dor[d]);
+                    float kp = 1.f;
+                    if (a.keep) kp = a.keep[(((size_t)s * heads + hh) * T + tq) * T + tk] ? inv_keep : 0.f;
+                    v *= kp;
+                }
+                dp[c] = v;
+                dot_pp += v * p[c];
+            }
+            dot_pp = warp_sum(dot_pp);
+#pragma unroll
+            for (int c = 0; c < TFM_MAXT / 32; c++) {
+                const int tk = lane + 32 * c;
+                const float ds = (tk < T) ? p[c] * (dp[c] - dot_pp) * qs : 0.f;
+                dp[c] = ds;
+                if (tk < T && ds != 0.f) {
+                    // dK[tk] += dS[tq, tk] * q[tq]
+                    for (int d = 0; d < hd; d++) atomicAdd(sdq + (size_t)tk * ldq + dm + hh * hd + d, ds * q[d]);
+                }
+            }
+            // dQ[tq] = sum_tk dS[tq, tk] * k[tk]: lanes over head dims, keys by shuffle
+            for (int d0 = 0; d0 < hd; d0 += 32) {
+                const int d = d0 + lane;
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < TFM_MAXT / 32; c++)
+                    for (int j = 0; j < 32 && j + 32 * c < T; j++) {
+                        const float dsj = __shfl_sync(0xffffffffu, dp[c], j);
+                        if (d < hd) acc += dsj * sq[(size_t)(j + 32 * c) * ldq + dm + hh * hd + d];
+                    }
+                if (d < hd) sdq[(size_t)tq * ldq + hh * hd + d] = acc;      // each (head, tq) is owned by one warp
+            }
+        }
+    }
+    if (BWD) {
+        __syncthreads();
+        float* dst = a.dqkv + (size_t)s * T * 3 * dm;
+        for (int i = threadIdx.x; i < T * 3 * dm; i += blockDim.x) dst[i] = sdq[(i / (3 * dm)) * ldq + i % (3 * dm)];
+    }
+}

@@ -364,6 +364,12 @@ int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* 
  * db_hh [3H].  Returns DOF_ERR_UNSUPPORTED when the shape is not eligible for the tensor-core kernel. */
 int dof_test_gru_wgrad(const float* dg_f, const float* dg_b, const float* x, int ldx, const float* hout, float* out,
                        int M, int T, int I, int H, void* stream);
+/* multi-head attention of the transformer training step (tfm.cuh): qkv [S,T,3*dm] rows q|k|v, kpad [S,T] bytes (1 =
+ * padded key) or NULL, keep [S,heads,T,T] bytes (1 = kept; inverted dropout with `rate`) or NULL, causal 0/1.
+ * dout == NULL: forward, out [S,T,dm].  dout != NULL: backward, dqkv [S,T,3*dm] (the probabilities are recomputed). */
+int dof_test_tfm_attention(const float* qkv, const unsigned char* kpad, const unsigned char* keep, float rate,
+                           int causal, int S, int T, int dm, int heads, float* out, const float* dout, float* dqkv,
+                           void* stream);
 int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout,
                      const float* gt_f, const float* gt_b, const float* dout, const float* dhn,
                      float* dg_f, float* dg_b, int S, int T, int H, void* stream);

@@ -464,3 +464,38 @@ def test_tc_gemm_wgrad_views(L):
             Hsh[:, :-1] = Hd[:, 1:]
         ref = G[:, :3 * H].double().t() @ Hsh.reshape(M, H).double()
         assert rel(dWh, ref) < 1e-5 and rel(dbh, G[:, :3 * H].double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("S_,T,dm,heads,causal,pad,rate", [(37, 25, 40, 4, 0, True, 0.1), (20, 25, 64, 8, 1, False, 0.2),
+                                                           (9, 12, 32, 4, 0, False, 0.0), (5, 40, 24, 3, 1, True, 0.3)])
+def test_tfm_attention_train_forward_backward(L, S_, T, dm, heads, causal, pad, rate):
+    """Attention block of the transformer training step: key-padding / causal masks, dropout on the weights with an
+    injected keep mask; forward and the recompute-based backward vs autograd in float64."""
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(S_, T, 3 * dm, generator=g).cuda()
+    kpad = None
+    if pad:
+        kp = (torch.rand(S_, T, generator=g) < 0.25)
+        kp[:, 0] = False                                   # never all keys padded (the reference yields NaN there)
+        kpad = kp.to(torch.uint8).cuda()
+    keep = (torch.rand(S_, heads, T, T, generator=g) >= rate).to(torch.uint8).cuda() if rate > 0 else None
+    dout = torch.randn(S_, T, dm, generator=g).cuda()
+    out = torch.zeros(S_, T, dm, device="cuda")
+    dqkv = torch.zeros_like(qkv)
+    assert L.dof_test_tfm_attention(P(qkv), P(kpad), P(keep), rate, causal, S_, T, dm, heads, P(out), None, None, S()) == 0, L.dof_last_error()
+    assert L.dof_test_tfm_attention(P(qkv), P(kpad), P(keep), rate, causal, S_, T, dm, heads, None, P(dout), P(dqkv), S()) == 0, L.dof_last_error()
+    x = qkv.double().requires_grad_(True)
+    hd = dm // heads
+    q, k, v = (x[..., i * dm:(i + 1) * dm].view(S_, T, heads, hd).transpose(1, 2) for i in range(3))
+    sc = q @ k.transpose(-1, -2) / hd ** 0.5
+    if pad:
+        sc = sc.masked_fill(kpad.bool()[:, None, None, :], float("-inf"))
+    if causal:
+        sc = sc.masked_fill(torch.triu(torch.ones(T, T, dtype=torch.bool, device="cuda"), 1), float("-inf"))
+    p = torch.softmax(sc, -1)
+    if keep is not None:
+        p = p * keep.double() / (1.0 - rate)
+    ref = (p @ v).transpose(1, 2).reshape(S_, T, dm)
+    ref.backward(dout.double())
+    assert rel(out, ref.detach()) < 2e-6
+    assert rel(dqkv, x.grad) < 5e-6
