@@ -11,9 +11,9 @@ clip_grad_value_(0.75) + Adam.  Prints ONE JSON line (rank 0).
   value : windows/s with the inputs already resident in HBM as RAW pose frames of a 1M-window video;
           every step = loader kernel (frames -> standardised windows) + the training step on consecutive
           batches (every step touches ~16 GB of activations >> 126 MB L2).
-  e2e   : the same step driven through the public host API (VaDETrainer.train_step) from
-          PINNED HOST buffers, H2D copy of the batch and D2H read of the loss inside the
-          timed region.
+  e2e   : the same step driven through the public host API (VaDETrainer.train_steps, the host epoch
+          loop) from PINNED HOST buffers: every step's H2D copy of its batch (side stream, overlapped
+          with the previous step) and D2H read of its loss are inside the timed region.
   roofline / kernels : per-kernel-class CUDA-event timing (library-side events around every
           launch) taken on extra steps right after the timed region.
   cpu_baseline : the CPU oracle (ATen-GRU variant, oracle/vade_oracle.py) on this host's cores
@@ -293,11 +293,13 @@ def main():
             trainer.train_step_device(xb, ab)
 
     def run_e2e(n, first):
-        last = None
+        # the public host loop: every step copies ITS batch from pinned host memory (on a side stream, overlapped with the
+        # previous step's kernels) and reads ITS loss back (non-blocking D2H); one host synchronisation at the end
+        bl = []
         for i in range(n):
             s = ((first + i) % hb) * B
-            last = trainer.train_step(xh[s:s + B], ah[s:s + B])   # H2D inside, returns host float loss
-        return last
+            bl.append((xh[s:s + B], ah[s:s + B]))
+        return trainer.train_steps(bl)[-1]
 
     # ---- value: device-resident inputs
     run_resident(warmup, 0)

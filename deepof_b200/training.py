@@ -59,7 +59,63 @@ class KLSchedule:
         self.current_iteration += 1
 
 
-class VaDETrainer:
+class _HostPipeline:
+    """``train_steps``: the epoch loop a host caller runs (``train_one_epoch_indexed`` fed by a pinned-memory DataLoader,
+    reference training.py:104-187) with the copies off the critical path: the host->device copy of batch i+1 runs on a
+    side stream while step i computes (two staging buffers, events in both directions), the loss of every step is read
+    back with a non-blocking device->host copy and the host synchronises once at the end.  Needs ``_xs``, ``_as`` (device
+    staging) and ``train_step_device``."""
+
+    def _pipeline_init(self):
+        if getattr(self, "_copy_stream", None) is None:
+            dev = self._xs.device
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [(self._xs, self._as), (torch.empty_like(self._xs), torch.empty_like(self._as) if self._as is not None else None)]
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._free = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def train_steps(self, batches) -> list:
+        """``batches``: sequence of ``(x_host, a_host)`` (pinned) or ``(x_host, a_host, idx)``.  Returns the total_loss of
+        every step as python floats."""
+        self._pipeline_init()
+        batches = list(batches)
+        n = len(batches)
+        if n == 0:
+            return []
+        losses = torch.zeros(n, pin_memory=True)
+        main, side = torch.cuda.current_stream(), self._copy_stream
+        side.wait_stream(main)
+
+        def upload(i):
+            k = i & 1
+            xh, ah = batches[i][0], batches[i][1]
+            B = xh.shape[0]
+            with torch.cuda.stream(side):
+                if i >= 2:
+                    side.wait_event(self._free[k])               # step i-2 has consumed this staging buffer
+                xs, as_ = self._stage[k]
+                xs[:B].copy_(xh, non_blocking=True)
+                if ah is not None and as_ is not None:
+                    as_[:B].copy_(ah, non_blocking=True)
+                self._ready[k].record(side)
+
+        upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            k = i & 1
+            B = batches[i][0].shape[0]
+            main.wait_event(self._ready[k])
+            xs, as_ = self._stage[k]
+            idx = batches[i][2] if len(batches[i]) > 2 else None
+            logs = self.train_step_device(xs[:B], as_[:B] if as_ is not None else None, idx)
+            self._free[k].record(main)
+            losses[i:i + 1].copy_(logs[:1], non_blocking=True)
+        main.synchronize()
+        return losses.tolist()
+
+
+class VaDETrainer(_HostPipeline):
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
                  max_batch: int = 4096, seed: Optional[int] = None, world_size: int = 1, rank: int = 0,
                  kmeans_loss: float = 1.0, device: Optional[int] = None):
@@ -178,7 +234,7 @@ class _GenericTrainer:
         return self.model.logs_dict()
 
 
-class VQVAETrainer(_GenericTrainer):
+class VQVAETrainer(_GenericTrainer, _HostPipeline):
     """``step_vqvae_distill`` + the optimizer step (teacher off)."""
 
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
@@ -204,7 +260,7 @@ class VQVAETrainer(_GenericTrainer):
         return self._read_loss(self.train_step_device(xs, as_))
 
 
-class ContrastiveTrainer(_GenericTrainer):
+class ContrastiveTrainer(_GenericTrainer, _HostPipeline):
     """``step_contrastive_distill`` + the optimizer step (teacher off): per batch draw the augmentation decisions,
     build both views on the device, encode them in one pass, NT-Xent, backward, clip + Adam."""
 
@@ -224,6 +280,7 @@ class ContrastiveTrainer(_GenericTrainer):
         self.host_gen.manual_seed(s)
         Tf, N = m.full_time_steps, m.input_shape[1]
         self._xf = torch.empty(max_batch, Tf, N, 3, device=m.device)
+        self._xs, self._as = self._xf, None          # staging of the pipelined host loop (_HostPipeline): full windows only
 
     def train_step_device(self, x_full: torch.Tensor, a_full=None, idx=None, aug_params=None) -> torch.Tensor:
         """a_full is accepted for signature parity and ignored: the reference recomputes the edge lengths from

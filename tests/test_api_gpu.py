@@ -81,3 +81,25 @@ def test_train_deepof_model_end_to_end(model_name, T, tmp_path):
         assert torch.equal(e1, e2) and torch.equal(q1, q2)                 # save / load round trip
     m3, n, n2, ls = train_deepof_model(pretrained=ckpt, batch_size=64)
     assert n is None and n2 is None and ls["model_name"] == model_name.lower()
+
+
+def test_pipelined_host_loop_equals_step_by_step():
+    """trainer.train_steps (H2D of batch i+1 on a side stream while step i computes, non-blocking loss read-back) gives
+    the losses and the parameters of the plain per-step host loop."""
+    import numpy as np
+    from deepof_b200.training import VQVAETrainer
+    from oracle import vade_oracle as O
+    T, N, D, K, B = 25, 14, 8, 6, 64
+    adj = O.default_adjacency(N)
+    E = int(np.count_nonzero(np.triu(adj)))
+    x, a = O.synthetic_windows(5 * B, T, adj, seed=3)
+    xh, ah = x.pin_memory(), a.pin_memory()
+    batches = [(xh[i * B:(i + 1) * B], ah[i * B:(i + 1) * B]) for i in range(5)]
+    t1 = VQVAETrainer((T, N, 3), (T, E, 1), adj, D, K, max_batch=B, seed=4)
+    t2 = VQVAETrainer((T, N, 3), (T, E, 1), adj, D, K, max_batch=B, seed=4)
+    ref = [t1.train_step(xb, ab) for xb, ab in batches]
+    got = t2.train_steps(batches)
+    # the weight gradients are reduced with floating-point atomics, so two runs agree to rounding, not bitwise
+    assert np.allclose(got, ref, rtol=1e-5, atol=0) and got[0] == ref[0]
+    assert float((t1.model.state - t2.model.state).abs().max()) < 1e-5
+    assert t2.train_steps([]) == []
