@@ -36,6 +36,46 @@ __global__ void __launch_bounds__(256) enc_conv_kernel(const EncConvArgs a) {
     for (int i = threadIdx.x; i < G * T; i += blockDim.x) flag[i] = 0;
     __syncthreads();
     float* out = a.Cv + (size_t)b * G * T * C;
+    if (C == 32 && F <= 4) {
+        // lane = output channel (its F*5 taps live in registers), warp = sequence g: the input window slides through
+        // registers (F broadcast shared-memory loads per step), stores are one full 128-byte line per warp instruction,
+        // the valid length comes from warp votes
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        float wr[4][5];
+#pragma unroll
+        for (int f = 0; f < 4; f++)
+#pragma unroll
+            for (int kk = 0; kk < 5; kk++) wr[f][kk] = f < F ? w[lane * F * 5 + f * 5 + kk] : 0.f;
+        for (int g = warp; g < G; g += nw) {
+            const float* sq = seq + (size_t)g * T * F;
+            float xw[4][5];
+#pragma unroll
+            for (int f = 0; f < 4; f++) {
+                xw[f][0] = 0.f; xw[f][1] = 0.f;
+                xw[f][2] = f < F ? sq[f] : 0.f;
+                xw[f][3] = (f < F && T > 1) ? sq[F + f] : 0.f;
+                xw[f][4] = (f < F && T > 2) ? sq[2 * F + f] : 0.f;
+            }
+            int n = 0;
+            for (int t = 0; t < T; t++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int f = 0; f < 4; f++)
+#pragma unroll
+                    for (int kk = 0; kk < 5; kk++) acc = fmaf(wr[f][kk], xw[f][kk], acc);
+                acc = fmaxf(acc, 0.f);
+                out[((size_t)g * T + t) * C + lane] = acc;
+                n += __any_sync(0xffffffffu, acc > 0.f) ? 1 : 0;
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                    xw[f][0] = xw[f][1]; xw[f][1] = xw[f][2]; xw[f][2] = xw[f][3]; xw[f][3] = xw[f][4];
+                    xw[f][4] = (f < F && t + 3 < T) ? sq[(t + 3) * F + f] : 0.f;
+                }
+            }
+            if (lane == 0) a.len[(size_t)b * G + g] = n;
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < G * T * C; i += blockDim.x) {
         int co = i % C, gt = i / C;
         int t = gt % T, g = gt / T;
