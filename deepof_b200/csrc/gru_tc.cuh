@@ -41,6 +41,10 @@ struct GruTcGeom { int wih_lbo, whh_lbo, tmem_cols, gs, os, xst; uint32_t wih_by
 #define GTC_MMA_WARP 12
 #define GTC_STORE_WARP 13
 #define GTC_NSTORE 3
+// H = 32: the 4 x-producer warps help the 3 store warps drain the staged rows once x_{t+1} is staged (the gate warps were
+// waiting on the drain: 2.63 -> 1.89 ms per step); H = 16 producers stage twice as many x columns per gate column and
+// must not be delayed (helping measured 2.5x slower there)
+#define GTC_NSTORE_ALL (H == 32 ? 7 : GTC_NSTORE)
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
         mbar_init(smem_u32(mbar + 0), 128); mbar_init(smem_u32(mbar + 1), 128);
         mbar_init(smem_u32(mbar + 2), 1); mbar_init(smem_u32(mbar + 3), 1);
         mbar_init(smem_u32(mbar + 4), 1); mbar_init(smem_u32(mbar + 5), 1);
-        mbar_init(smem_u32(mbar + 6), 256); mbar_init(smem_u32(mbar + 7), 256); mbar_init(smem_u32(mbar + 8), GTC_NSTORE * 32);
+        mbar_init(smem_u32(mbar + 6), 256); mbar_init(smem_u32(mbar + 7), 256); mbar_init(smem_u32(mbar + 8), GTC_NSTORE_ALL * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // weights: canonical K-major B operands, row n at n*16 B, K-chunk (4 floats) stride lbo
@@ -128,6 +132,76 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                    bar_h = smem_u32(mbar + 6), bar_sfull = smem_u32(mbar + 7), bar_sfree = smem_u32(mbar + 8);
     const bool want_g = a.Gt[dir] != nullptr, want_o = a.Hout != nullptr;
 
+    // ===================== staged rows -> HBM (store warps + x producers) =====================
+        // ===================== output store warps: staged rows -> HBM =====================
+        // A gate row (4H floats) / an output row (H floats) is contiguous in HBM, so LG = H (resp. H/4) lanes move
+        // one row with one 16-byte access each (full 128-byte lines); the warp instructions of a step are dealt
+        // round-robin to the store warps.
+        float* Gt = a.Gt[dir];
+        constexpr int LG = H, RG = 32 / LG, NG = 128 / RG;       // lanes per gate row, rows / warp instruction, instructions / step
+        constexpr int LO = H / 4, RO = 32 / LO, NO = 128 / RO;
+        constexpr int CH = 8;
+    auto store_step = [&](int step, int sw) {
+            const int t = dir ? (T - 1 - step) : step;
+            mbar_wait(bar_sfull, (uint32_t)(step & 1));
+            if (want_g && TILED) {
+                // chunk-major tiles: one warp instruction = one 16-byte chunk of 32 consecutive rows (512 B contiguous)
+                float* gtile = Gt + ((size_t)blockIdx.x * T + t) * H * 512;
+                for (int q0 = sw; q0 < 4 * H; q0 += GTC_NSTORE_ALL * CH) {
+                    float4 v[CH];
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const int q = q0 + k * GTC_NSTORE_ALL;
+                        const int c = q >> 2, r = (q & 3) * 32 + lane;
+                        if (q < 4 * H) v[k] = *reinterpret_cast<const float4*>(Gs + (size_t)r * geo.gs + c * 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const int q = q0 + k * GTC_NSTORE_ALL;
+                        const int c = q >> 2, r = (q & 3) * 32 + lane;
+                        if (q < 4 * H && t < lens_s[r]) *reinterpret_cast<float4*>(gtile + ((size_t)c * 128 + r) * 4) = v[k];
+                    }
+                }
+            } else if (want_g && !TILED) {
+                for (int c = sw; c < NG; c += GTC_NSTORE_ALL * CH) {
+                    float4 v[CH];
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const int q = c + k * GTC_NSTORE_ALL;
+                        const int r = q * RG + lane / LG;
+                        if (q < NG) v[k] = *reinterpret_cast<const float4*>(Gs + (size_t)r * geo.gs + (lane % LG) * 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const int q = c + k * GTC_NSTORE_ALL;
+                        const int r = q * RG + lane / LG;
+                        if (q < NG) {
+                            const int rl = lens_s[r];
+                            if (t < rl) *reinterpret_cast<float4*>(Gt + ((size_t)(s0 + r) * T + t) * 4 * H + (lane % LG) * 4) = v[k];
+                        }
+                    }
+                }
+            }
+            if (want_o) {
+                for (int c = sw; c < NO; c += GTC_NSTORE_ALL * CH) {
+                    float4 v[CH];
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const int q = c + k * GTC_NSTORE_ALL;
+                        const int r = q * RO + lane / LO;
+                        if (q < NO) v[k] = *reinterpret_cast<const float4*>(Os + (size_t)r * geo.os + (lane % LO) * 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const int q = c + k * GTC_NSTORE_ALL;
+                        const int r = q * RO + lane / LO;
+                        if (q < NO && lens_s[r] >= 0)
+                            *reinterpret_cast<float4*>(a.Hout + ((size_t)(s0 + r) * T + t) * 2 * H + dir * H + (lane % LO) * 4) = v[k];
+                    }
+                }
+            }
+            mbar_arrive(bar_sfree);                       // staged rows consumed: the gate warps may refill them
+    };
     if (warp < 4) {
         // ===================== x_t producers =====================
         // stage x_{step+1} (registers -> hi/lo split -> shared) while the global loads of x_{step+2} are in flight
@@ -162,13 +236,16 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
             fence_async_smem();
             mbar_arrive(bar_xfull + 8u * st);
         };
+        const bool help = (H == 32) && (want_g || want_o);
         load_regs(0);
         stage_x(0);
         if (T > 1) load_regs(1);
         for (int step = 0; step + 1 < T; step++) {
             stage_x(step + 1);
             if (step + 2 < T) load_regs(step + 2);
+            if (help) store_step(step, GTC_NSTORE + warp);         // x_{step+1} is staged: help draining step's rows
         }
+        if (help) store_step(T - 1, GTC_NSTORE + warp);
     } else if (warp < GTC_MMA_WARP) {
         // ===================== gate warps: two threads per sequence =====================
         const int ew = warp & 3, row = ew * 32 + lane, half = (warp - 4) >> 2;
@@ -284,76 +361,7 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
         }
     }
     if (warp >= GTC_STORE_WARP && (want_g || want_o)) {
-        // ===================== output store warps: staged rows -> HBM =====================
-        // A gate row (4H floats) / an output row (H floats) is contiguous in HBM, so LG = H (resp. H/4) lanes move
-        // one row with one 16-byte access each (full 128-byte lines); the warp instructions of a step are dealt
-        // round-robin to the store warps.
-        const int sw = warp - GTC_STORE_WARP;
-        float* Gt = a.Gt[dir];
-        constexpr int LG = H, RG = 32 / LG, NG = 128 / RG;       // lanes per gate row, rows / warp instruction, instructions / step
-        constexpr int LO = H / 4, RO = 32 / LO, NO = 128 / RO;
-        constexpr int CH = 8;
-        for (int step = 0; step < T; step++) {
-            const int t = dir ? (T - 1 - step) : step;
-            mbar_wait(bar_sfull, (uint32_t)(step & 1));
-            if (want_g && TILED) {
-                // chunk-major tiles: one warp instruction = one 16-byte chunk of 32 consecutive rows (512 B contiguous)
-                float* gtile = Gt + ((size_t)blockIdx.x * T + t) * H * 512;
-                for (int q0 = sw; q0 < 4 * H; q0 += GTC_NSTORE * CH) {
-                    float4 v[CH];
-#pragma unroll
-                    for (int k = 0; k < CH; k++) {
-                        const int q = q0 + k * GTC_NSTORE;
-                        const int c = q >> 2, r = (q & 3) * 32 + lane;
-                        if (q < 4 * H) v[k] = *reinterpret_cast<const float4*>(Gs + (size_t)r * geo.gs + c * 16);
-                    }
-#pragma unroll
-                    for (int k = 0; k < CH; k++) {
-                        const int q = q0 + k * GTC_NSTORE;
-                        const int c = q >> 2, r = (q & 3) * 32 + lane;
-                        if (q < 4 * H && t < lens_s[r]) *reinterpret_cast<float4*>(gtile + ((size_t)c * 128 + r) * 4) = v[k];
-                    }
-                }
-            } else if (want_g && !TILED) {
-                for (int c = sw; c < NG; c += GTC_NSTORE * CH) {
-                    float4 v[CH];
-#pragma unroll
-                    for (int k = 0; k < CH; k++) {
-                        const int q = c + k * GTC_NSTORE;
-                        const int r = q * RG + lane / LG;
-                        if (q < NG) v[k] = *reinterpret_cast<const float4*>(Gs + (size_t)r * geo.gs + (lane % LG) * 16);
-                    }
-#pragma unroll
-                    for (int k = 0; k < CH; k++) {
-                        const int q = c + k * GTC_NSTORE;
-                        const int r = q * RG + lane / LG;
-                        if (q < NG) {
-                            const int rl = lens_s[r];
-                            if (t < rl) *reinterpret_cast<float4*>(Gt + ((size_t)(s0 + r) * T + t) * 4 * H + (lane % LG) * 4) = v[k];
-                        }
-                    }
-                }
-            }
-            if (want_o) {
-                for (int c = sw; c < NO; c += GTC_NSTORE * CH) {
-                    float4 v[CH];
-#pragma unroll
-                    for (int k = 0; k < CH; k++) {
-                        const int q = c + k * GTC_NSTORE;
-                        const int r = q * RO + lane / LO;
-                        if (q < NO) v[k] = *reinterpret_cast<const float4*>(Os + (size_t)r * geo.os + (lane % LO) * 16);
-                    }
-#pragma unroll
-                    for (int k = 0; k < CH; k++) {
-                        const int q = c + k * GTC_NSTORE;
-                        const int r = q * RO + lane / LO;
-                        if (q < NO && lens_s[r] >= 0)
-                            *reinterpret_cast<float4*>(a.Hout + ((size_t)(s0 + r) * T + t) * 2 * H + dir * H + (lane % LO) * 4) = v[k];
-                    }
-                }
-            }
-            mbar_arrive(bar_sfree);                       // staged rows consumed: the gate warps may refill them
-        }
+        for (int step = 0; step < T; step++) store_step(step, warp - GTC_STORE_WARP);
     }
     tc_fence_before();
     __syncthreads();
