@@ -41,10 +41,11 @@ struct GruTcGeom { int wih_lbo, whh_lbo, tmem_cols, gs, os, xst; uint32_t wih_by
 #define GTC_MMA_WARP 12
 #define GTC_STORE_WARP 13
 #define GTC_NSTORE 3
-// H = 32: the 4 x-producer warps help the 3 store warps drain the staged rows once x_{t+1} is staged (the gate warps were
-// waiting on the drain: 2.63 -> 1.89 ms per step); H = 16 producers stage twice as many x columns per gate column and
-// must not be delayed (helping measured 2.5x slower there)
-#define GTC_NSTORE_ALL (H == 32 ? 7 : GTC_NSTORE)
+// 7 warps drain the staged rows of a step (the gate warps were stalled on the drain with 3).  H = 32: the 3 store warps +
+// the 4 x-producer warps once x_{t+1} is staged (2.63 -> 1.89 ms per step).  H = 16: producers stage twice as many x
+// columns per gate column and must not be delayed (helping measured 2.5x slower), but one gate thread per sequence is
+// enough there, so warps 8-11 are store warps
+#define GTC_NSTORE_ALL 7
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -62,7 +63,10 @@ __device__ __forceinline__ void tmem_ld_hc(uint32_t taddr, float (&v)[HC]) {
 
 template <int H, int KQM, bool TILED>
 __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs a, const GruTcGeom geo) {
-    constexpr int HC = H / 2;                                         // hidden units per gate thread
+    // H = 32: 8 gate warps (two threads per sequence); H = 16: 4 gate warps (one thread per sequence) — warps 8-11 join
+    // the store warps instead, because the drain of the staged gate rows is what the gate warps wait for
+    constexpr int NGATE = (H == 32) ? 8 : 4;
+    constexpr int HC = H / (NGATE / 4);                               // hidden units per gate thread
     extern __shared__ __align__(128) unsigned char gsm[];
     const int dir = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int I = a.I, T = a.T, KQ = I >> 2;
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
     unsigned char* Gs = Xs + 2 * (size_t)geo.xst * geo.x_bytes;                // [128][gs] staged gate rows r|z|n|hn
     unsigned char* Os = Gs + 128 * (size_t)geo.gs;                   // [128][os] staged output rows
     uint64_t* mbar = reinterpret_cast<uint64_t*>(Os + 128 * (size_t)geo.os);
-    // mbar: [0,2) x_full (128), [2,4) x_empty (1), [4,6) acc_full (1), [6] h_ready (256), [7] stage_full (256), [8] stage_free (96)
+    // mbar: [0,2) x_full (128), [2,4) x_empty (1), [4,6) acc_full (1), [6] h_ready (gate threads), [7] stage_full (gate threads), [8] stage_free (7 draining warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 10);
     float* bs = reinterpret_cast<float*>(tmem_slot + 4);             // [4H]: b_ir+b_hr | b_iz+b_hz | b_in | b_hn
     int* lens_s = reinterpret_cast<int*>(bs + 4 * H);                // [128] valid length of every row, -1 outside the batch
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
         mbar_init(smem_u32(mbar + 0), 128); mbar_init(smem_u32(mbar + 1), 128);
         mbar_init(smem_u32(mbar + 2), 1); mbar_init(smem_u32(mbar + 3), 1);
         mbar_init(smem_u32(mbar + 4), 1); mbar_init(smem_u32(mbar + 5), 1);
-        mbar_init(smem_u32(mbar + 6), 256); mbar_init(smem_u32(mbar + 7), 256); mbar_init(smem_u32(mbar + 8), GTC_NSTORE_ALL * 32);
+        mbar_init(smem_u32(mbar + 6), NGATE * 32); mbar_init(smem_u32(mbar + 7), NGATE * 32); mbar_init(smem_u32(mbar + 8), GTC_NSTORE_ALL * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // weights: canonical K-major B operands, row n at n*16 B, K-chunk (4 floats) stride lbo
@@ -246,8 +250,8 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
             if (help) store_step(step, GTC_NSTORE + warp);         // x_{step+1} is staged: help draining step's rows
         }
         if (help) store_step(T - 1, GTC_NSTORE + warp);
-    } else if (warp < GTC_MMA_WARP) {
-        // ===================== gate warps: two threads per sequence =====================
+    } else if (warp < 4 + NGATE) {
+        // ===================== gate warps: two threads (H = 32) / one thread (H = 16) per sequence =====================
         const int ew = warp & 3, row = ew * 32 + lane, half = (warp - 4) >> 2;
         const int j0 = half * HC;
         const int s = s0 + row;
@@ -360,8 +364,10 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
             }
         }
     }
-    if (warp >= GTC_STORE_WARP && (want_g || want_o)) {
-        for (int step = 0; step < T; step++) store_step(step, warp - GTC_STORE_WARP);
+    {
+        const int swi = warp >= GTC_STORE_WARP ? warp - GTC_STORE_WARP : ((H == 16 && warp >= 4 + NGATE && warp < GTC_MMA_WARP) ? GTC_NSTORE + warp - (4 + NGATE) : -1);
+        if (swi >= 0 && (want_g || want_o))
+            for (int step = 0; step < T; step++) store_step(step, swi);
     }
     tc_fence_before();
     __syncthreads();
