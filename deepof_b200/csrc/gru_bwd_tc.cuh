@@ -35,7 +35,10 @@ struct GruBwdTcArgs {
 
 struct GruBwdTcGeom { int whh_lbo, wih_lbo, tmem_cols; uint32_t whh_bytes, wih_bytes, a_bytes; };
 
-#define GBT_THREADS 416          // warps 0-3 store warps | 4-11 gate warps | 12 MMA issuer
+#define GBT_THREADS 512          // warps 0-3 store warps | 4-11 gate warps | 12 MMA issuer | 13-15 dG-row drain helpers
+                                 // (13 warps are charged registers like 16, so the 3 helpers are free; the gate warps were
+                                 // stalled on the store warps finishing the dG rows of the previous step)
+#define GBT_NDRAIN 7             // warps that stream the dG rows of a step: 0-3 and 13-15
 #define GBT_MMA_WARP 12
 
 __device__ __forceinline__ void split_tf32_exact(float v, float& hi, float& lo) {
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), geo.tmem_cols);
     if (tid == 32) {
         mbar_init(smem_u32(mbar + 0), 256); mbar_init(smem_u32(mbar + 1), 1);
-        mbar_init(smem_u32(mbar + 2), 1); mbar_init(smem_u32(mbar + 3), 128); mbar_init(smem_u32(mbar + 4), 128);
+        mbar_init(smem_u32(mbar + 2), 1); mbar_init(smem_u32(mbar + 3), GBT_NDRAIN * 32); mbar_init(smem_u32(mbar + 4), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -246,16 +249,18 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
                 }
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 4 || warp > GBT_MMA_WARP) {
         // ===================== store warps: dG rows (from the operand planes) and dX rows (from TMEM) =====================
+        // the dG rows of a step are dealt round-robin to the 7 draining warps; only warps 0-3 (TMEM lane groups) do dX
         float* dG = a.dG[dir];
         constexpr int LG = H, RG = 32 / LG;          // lanes per dG row (4H floats = H chunks), rows per warp instruction
+        const int sw = warp < 4 ? warp : 4 + warp - (GBT_MMA_WARP + 1);
         for (int step = 0; step < T; step++) {
             const int t = dir ? step : (T - 1 - step);
             mbar_wait(bar_afull, (uint32_t)(step & 1));
 #pragma unroll 4
-            for (int k = 0; k < 32 / RG; k++) {
-                const int r = warp * 32 + k * RG + lane / LG, c = lane % LG;
+            for (int q = sw; q < 128 / RG; q += GBT_NDRAIN) {
+                const int r = q * RG + lane / LG, c = lane % LG;
                 const uint32_t off = (uint32_t)r * 16 + (uint32_t)c * TC_A_LBO;
                 const float4 hi = *reinterpret_cast<const float4*>(A_hi + off);
                 const float4 lo = *reinterpret_cast<const float4*>(A_lo + off);
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(GBT_THREADS) gru_bwd_tc_kernel(const GruBwdTcA
                         make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
             }
             mbar_arrive(bar_st);                          // the operand tile may be refilled (its MMAs are tracked by dh / dx_full)
-            if (want_dx) {
+            if (want_dx && warp < 4) {
                 mbar_wait(bar_dx, (uint32_t)(step & 1));
                 tc_fence_after();
                 const int r = warp * 32 + lane;
