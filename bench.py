@@ -114,25 +114,71 @@ def synth_frames(n_frames, N, seed, device):
 
 
 class ClockSampler:
+    """SM clock / throttle-reason samples taken DURING the timed regions (B200_PROFILING.md's clocks line).
+    NVML in-process every 10 ms (a 120 ms timed region is too short for `nvidia-smi -lms`, whose first row can
+    arrive after the region has ended); `nvidia-smi` loop as the fallback when pynvml cannot initialise."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.h, self.nv = index, [], None, None, None
+        self.sm, self.pw, self.mx, self.bits, self.source = [], [], None, 0, None
+        self.stop_ev = threading.Event()
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip()]
+        if ids and all(v.strip().isdigit() for v in ids) and self.index < len(ids):
+            return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self._nvml_index()), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_ev.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            self.stop_ev.wait(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_ev.set()
+            self.th.join(timeout=2)
+            nv = self.nv
+            masks = [getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+            reasons = [n for n, m in zip(self.NAMES, masks) if self.bits & m]
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                    "sm_max_mhz": self.mx, "power_w_max": max(self.pw) if self.pw else None, "samples": len(self.sm),
+                    "reasons": reasons, "source": "nvml, 10 ms, value + e2e timed regions"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -143,11 +189,10 @@ class ClockSampler:
             self.proc.kill()
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons, "source": "nvidia-smi -lms 50"}
 
 
 def cpu_reference_arm(steps, warmup, batch=256, workload="cfg2"):
@@ -314,7 +359,6 @@ def main():
     e1.record()
     barrier()
     launches = L.dof_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -333,6 +377,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
     h2d = (xh[:B].numel() + (0 if kind == "contrastive" else ah[:B].numel())) * 4   # contrastive recomputes the edges
     e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "windows/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss}
