@@ -475,7 +475,11 @@ static int ln_fwd(const float* x, const float* w, const float* b, float* y, floa
     int grid = (int)(blocks < (long long)sm * 16 ? blocks : (long long)sm * 16);
     if (grid < 1) return DOF_OK;
     { ProfScope ps("ln_fwd", st, 0.0, 8.0 * R * W);
-    if (W <= 32) ln_fwd_kernel<1, 4><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W);
+    const bool vec = ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)w) | ((uintptr_t)b)) & 15) == 0;
+    if (vec && W == 64) ln_fwd_vec_kernel<64, 4><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R);
+    else if (vec && W == 32) ln_fwd_vec_kernel<32, 4><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R);
+    else if (vec && W == 128) ln_fwd_vec_kernel<128, 4><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R);
+    else if (W <= 32) ln_fwd_kernel<1, 4><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W);
     else if (W <= 64) ln_fwd_kernel<2, 4><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W);
     else if (W <= 128) ln_fwd_kernel<4, 2><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W);
     else ln_fwd_kernel<8, 1><<<grid, 256, 0, st>>>(x, w, b, eps, y, mu, rs, R, W); }
@@ -488,7 +492,11 @@ static int ln_bwd(const float* dy, const float* x, const float* mu, const float*
     int grid = (int)(blocks < (long long)sm * 8 ? blocks : (long long)sm * 8);
     if (grid < 1) return DOF_OK;
     { ProfScope ps("ln_bwd", st, 0.0, 12.0 * R * W);
-    if (W <= 32) ln_bwd_kernel<1, 4><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
+    const bool vec = ((((uintptr_t)dy) | ((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)w)) & 15) == 0;
+    if (vec && W == 64) ln_bwd_vec_kernel<64, 4><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, relu_in);
+    else if (vec && W == 32) ln_bwd_vec_kernel<32, 4><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, relu_in);
+    else if (vec && W == 128) ln_bwd_vec_kernel<128, 2><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, relu_in);
+    else if (W <= 32) ln_bwd_kernel<1, 4><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
     else if (W <= 64) ln_bwd_kernel<2, 4><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
     else if (W <= 128) ln_bwd_kernel<4, 2><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in);
     else ln_bwd_kernel<8, 1><<<grid, 256, 0, st>>>(dy, x, mu, rs, w, dx, dw, db, R, W, relu_in); }

@@ -321,6 +321,153 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 }
 
 // ---------------------------------------------------------------------------
+// Vectorised LayerNorm for W in {32, 64, 128} and 16-byte aligned rows: W/4 lanes per row with one float4 each, so a
+// warp load instruction covers 32/(W/4) CONSECUTIVE rows (512 contiguous bytes) and R of them are in flight per warp.
+// Same arithmetic as the scalar kernels above (two-pass variance, Newton-refined rsqrt).
+// ---------------------------------------------------------------------------
+template <int W, int R>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ b, float eps,
+                                                         float* __restrict__ y, float* __restrict__ mu_out,
+                                                         float* __restrict__ rstd_out, long long Rows) {
+    constexpr int LPR = W / 4, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, c4 = (lane % LPR) * 4;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long groups = (Rows + RPW - 1) / RPW;
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c4));
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(b + c4));
+    for (long long g0 = warp; g0 < groups; g0 += nwarps * R) {
+        float4 v[R];
+        float s[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const long long r = (g0 + q * nwarps) * RPW + sub;
+            v[q] = (r < Rows) ? __ldcs(reinterpret_cast<const float4*>(x + r * W + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s[q] = (v[q].x + v[q].y) + (v[q].z + v[q].w);
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < R; q++) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        float mu[R], var[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            mu[q] = s[q] / W;
+            const float d0 = v[q].x - mu[q], d1 = v[q].y - mu[q], d2 = v[q].z - mu[q], d3 = v[q].w - mu[q];
+            var[q] = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < R; q++) var[q] += __shfl_xor_sync(0xffffffffu, var[q], o);
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const long long r = (g0 + q * nwarps) * RPW + sub;
+            if (r >= Rows) continue;
+            const float vv = var[q] / W;
+            float rstd = rsqrtf(vv + eps);
+            rstd = rstd * (1.5f - 0.5f * (vv + eps) * rstd * rstd);
+            float4 o;
+            o.x = (v[q].x - mu[q]) * rstd * wv.x + bv.x;
+            o.y = (v[q].y - mu[q]) * rstd * wv.y + bv.y;
+            o.z = (v[q].z - mu[q]) * rstd * wv.z + bv.z;
+            o.w = (v[q].w - mu[q]) * rstd * wv.w + bv.w;
+            *reinterpret_cast<float4*>(y + r * W + c4) = o;
+            if (c4 == 0 && mu_out) { mu_out[r] = mu[q]; rstd_out[r] = rstd; }
+        }
+    }
+}
+
+template <int W, int R>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ mu_in,
+                                                         const float* __restrict__ rstd_in,
+                                                         const float* __restrict__ w, float* __restrict__ dx,
+                                                         float* __restrict__ dw, float* __restrict__ db,
+                                                         long long Rows, int relu_in) {
+    constexpr int LPR = W / 4, RPW = 32 / LPR;
+    __shared__ float sdw[W], sdb[W];
+    const int lane = threadIdx.x & 31, sub = lane / LPR, c4 = (lane % LPR) * 4;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) { sdw[i] = 0.f; sdb[i] = 0.f; }
+    __syncthreads();
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long groups = (Rows + RPW - 1) / RPW;
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c4));
+    float4 adw = make_float4(0.f, 0.f, 0.f, 0.f), adb = adw;
+    for (long long g0 = warp; g0 < groups; g0 += nwarps * R) {
+        float4 xv[R], dv[R];
+        float mu[R], rstd[R], s1[R], s2[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const long long r = (g0 + q * nwarps) * RPW + sub;
+            const bool ok = r < Rows;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[q] = ok ? __ldcs(reinterpret_cast<const float4*>(x + r * W + c4)) : z4;
+            dv[q] = ok ? __ldcs(reinterpret_cast<const float4*>(dy + r * W + c4)) : z4;
+            mu[q] = ok ? __ldg(mu_in + r) : 0.f;
+            rstd[q] = ok ? __ldg(rstd_in + r) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            // xhat in place of x (rows beyond the end have x = mu = rstd = 0 -> xhat = 0, dy = 0)
+            const float h0 = (xv[q].x - mu[q]) * rstd[q], h1 = (xv[q].y - mu[q]) * rstd[q];
+            const float h2 = (xv[q].z - mu[q]) * rstd[q], h3 = (xv[q].w - mu[q]) * rstd[q];
+            const float g0_ = dv[q].x * wv.x, g1 = dv[q].y * wv.y, g2 = dv[q].z * wv.z, g3 = dv[q].w * wv.w;
+            s1[q] = (g0_ + g1) + (g2 + g3);
+            s2[q] = (g0_ * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
+            adw.x += dv[q].x * h0; adw.y += dv[q].y * h1; adw.z += dv[q].z * h2; adw.w += dv[q].w * h3;
+            adb.x += dv[q].x; adb.y += dv[q].y; adb.z += dv[q].z; adb.w += dv[q].w;
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
+                s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o);
+            }
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const long long r = (g0 + q * nwarps) * RPW + sub;
+            if (r >= Rows) continue;
+            const float m1 = s1[q] / W, m2 = s2[q] / W;
+            const float h0 = (xv[q].x - mu[q]) * rstd[q], h1 = (xv[q].y - mu[q]) * rstd[q];
+            const float h2 = (xv[q].z - mu[q]) * rstd[q], h3 = (xv[q].w - mu[q]) * rstd[q];
+            float4 o;
+            o.x = rstd[q] * (dv[q].x * wv.x - m1 - h0 * m2);
+            o.y = rstd[q] * (dv[q].y * wv.y - m1 - h1 * m2);
+            o.z = rstd[q] * (dv[q].z * wv.z - m1 - h2 * m2);
+            o.w = rstd[q] * (dv[q].w * wv.w - m1 - h3 * m2);
+            if (relu_in) {
+                if (!(xv[q].x > 0.f)) o.x = 0.f;
+                if (!(xv[q].y > 0.f)) o.y = 0.f;
+                if (!(xv[q].z > 0.f)) o.z = 0.f;
+                if (!(xv[q].w > 0.f)) o.w = 0.f;
+            }
+            *reinterpret_cast<float4*>(dx + r * W + c4) = o;
+        }
+    }
+    // the RPW row slots of a warp hold the same columns: fold them with shuffles before touching shared memory
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        adw.x += __shfl_xor_sync(0xffffffffu, adw.x, o); adw.y += __shfl_xor_sync(0xffffffffu, adw.y, o);
+        adw.z += __shfl_xor_sync(0xffffffffu, adw.z, o); adw.w += __shfl_xor_sync(0xffffffffu, adw.w, o);
+        adb.x += __shfl_xor_sync(0xffffffffu, adb.x, o); adb.y += __shfl_xor_sync(0xffffffffu, adb.y, o);
+        adb.z += __shfl_xor_sync(0xffffffffu, adb.z, o); adb.w += __shfl_xor_sync(0xffffffffu, adb.w, o);
+    }
+    if (sub == 0) {
+        atomicAdd(&sdw[c4 + 0], adw.x); atomicAdd(&sdw[c4 + 1], adw.y); atomicAdd(&sdw[c4 + 2], adw.z); atomicAdd(&sdw[c4 + 3], adw.w);
+        atomicAdd(&sdb[c4 + 0], adb.x); atomicAdd(&sdb[c4 + 1], adb.y); atomicAdd(&sdb[c4 + 2], adb.z); atomicAdd(&sdb[c4 + 3], adb.w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        atomicAdd(dw + c, sdw[c]);
+        atomicAdd(db + c, sdb[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // CensNet aggregation (censNetConv_pt.py:92-136), one CTA per window:
 //   Mv = (T diag(He.we) T^T) o lap ;  Pn = Mv.Hn        Me = (T^T diag(Hn.wn) T) o elap ; Pe = Me.He
 // The dense kernels (Pn.node_kernel + bias, relu) go through gemm_rows.
