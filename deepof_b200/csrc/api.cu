@@ -819,7 +819,12 @@ static int enc_block_backward(dof_handle* h, int bi, const float* state, float* 
         const int pairs = C1 * w.Fin, slots = 256 / pairs, threads = pairs * slots;
         int grid = cdiv(S, slots) < sm * 16 ? cdiv(S, slots) : sm * 16;
         { ProfScope ps("conv_wgrad", st, 2.0 * M * C1 * w.Fin * 5, 4.0 * M * (C1 + w.Fin));
-        conv_wgrad_kernel<<<grid, threads, 0, st>>>(ca); }
+        bool vec = false;
+        if (C1 == 32) vec = launch_conv_wgrad_vec<32>(ca, sm, st);
+        else if (C1 == 16) vec = launch_conv_wgrad_vec<16>(ca, sm, st);
+        else if (C1 == 64) vec = launch_conv_wgrad_vec<64>(ca, sm, st);
+        else if (C1 == 128) vec = launch_conv_wgrad_vec<128>(ca, sm, st);
+        if (!vec) conv_wgrad_kernel<<<grid, threads, 0, st>>>(ca); }
         DOF_LAUNCH_CHECK();
     } else {
         WGradArgs wc = wgrad_args(mv_plain(w.dCv, C1), mv_conv5(w.Xs, w.Fin, T, +1), grad + P.conv, w.Fin * 5, 0, nullptr, M, C1, w.Fin * 5);

@@ -146,6 +146,83 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const ConvWgradArgs a) 
     }
 }
 
+// Same gradient, one WARP per sequence: the [T, C] block of dCv is one contiguous run that the warp streams with
+// float4 loads (C/4 lanes per time step, 32/(C/4) steps per load instruction = 512 contiguous bytes, four of them in
+// flight); each lane keeps the 4 x F x 5 partial sums of its four channels, the few Xs values come from L1.
+template <int C, int F>
+__global__ void __launch_bounds__(256) conv_wgrad_vec_kernel(const ConvWgradArgs a) {
+    constexpr int LPR = C / 4, RPW = 32 / LPR, NW = C * F * 5;
+    __shared__ float sdw[NW];
+    const int lane = threadIdx.x & 31, c4 = (lane % LPR) * 4, toff = lane / LPR, T = a.T;
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) sdw[i] = 0.f;
+    __syncthreads();
+    float acc[4][F][5];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int f = 0; f < F; f++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) acc[j][f][k] = 0.f;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long seq = warp; seq < a.S; seq += nwarps) {
+        const float* __restrict__ dc = a.dCv + seq * T * C + c4;
+        const float* __restrict__ xs = a.Xs + seq * T * F;
+        for (int t0 = toff; t0 < T; t0 += 4 * RPW) {
+            float4 d[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int t = t0 + q * RPW;
+                d[q] = (t < T) ? __ldcs(reinterpret_cast<const float4*>(dc + (size_t)t * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int t = t0 + q * RPW;
+                if (t >= T) continue;
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const int tt = t + k - 2;
+                    if (tt < 0 || tt >= T) continue;
+#pragma unroll
+                    for (int f = 0; f < F; f++) {
+                        const float xv = __ldg(xs + tt * F + f);
+                        acc[0][f][k] = fmaf(d[q].x, xv, acc[0][f][k]);
+                        acc[1][f][k] = fmaf(d[q].y, xv, acc[1][f][k]);
+                        acc[2][f][k] = fmaf(d[q].z, xv, acc[2][f][k]);
+                        acc[3][f][k] = fmaf(d[q].w, xv, acc[3][f][k]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int f = 0; f < F; f++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                float v = acc[j][f][k];
+#pragma unroll
+                for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (toff == 0) atomicAdd(&sdw[(c4 + j) * F * 5 + f * 5 + k], v);
+            }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) atomicAdd(a.dW + i, sdw[i]);
+}
+
+template <int C>
+static bool launch_conv_wgrad_vec(const ConvWgradArgs& ca, int sm, cudaStream_t st) {
+    if ((((uintptr_t)ca.dCv) & 15) != 0) return false;
+    long long want = ((long long)ca.S + 7) / 8;
+    int grid = (int)(want < (long long)sm * 4 ? want : (long long)sm * 4);
+    if (grid < 1) grid = 1;
+    if (ca.F == 1) conv_wgrad_vec_kernel<C, 1><<<grid, 256, 0, st>>>(ca);
+    else if (ca.F == 2) conv_wgrad_vec_kernel<C, 2><<<grid, 256, 0, st>>>(ca);
+    else if (ca.F == 3) conv_wgrad_vec_kernel<C, 3><<<grid, 256, 0, st>>>(ca);
+    else return false;
+    return true;
+}
+
 // decoder validity: len[b] = #time steps whose data row is not all-zero (models_new.py:330-331).
 // One warp per window; a time step's row (Dx floats, contiguous) is read by the whole warp.
 __global__ void row_valid_len_kernel(const float* __restrict__ x, int* __restrict__ len, int B, int T, int Dx) {
