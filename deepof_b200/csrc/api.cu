@@ -768,8 +768,22 @@ static int decoder_backward(dof_handle* h, const float* state, float* grad, cons
     GemmArgs g0 = gemm_args(mv_plain(h->dloc, NF), state + L.loc_w, 2 * D, 1, nullptr, h->dYD3, 2 * D, M, 2 * D, NF);
     DOF_TRY(launch_gemm_rows(&g0, 1, st));
     DOF_TRY(ln_bwd(h->dYD3, h->Cd, h->muD3, h->rsD3, state + L.dn3w, h->dCd, grad + L.dn3w, grad + L.dn3b, M, 2 * D, 1, sm, st));
-    WGradArgs w1 = wgrad_args(mv_plain(h->dCd, 2 * D), mv_conv5(h->YD2, 4 * D, T, +1), grad + L.dconv, 20 * D, 0, nullptr, M, 2 * D, 20 * D);
-    DOF_TRY(launch_gemm_wgrad(&w1, 1, st, sm));
+    // conv weight gradient dW[o][c][kk] = sum_rows dCd[(s,t), o] * YD2[(s, t+kk-2), c]: one time-shifted tensor-core
+    // weight-gradient GEMM per tap (K = 4D, output column stride 5), the five taps batched in one launch; the im2col
+    // GEMM (K = 20 D, SIMT) only for shapes the tensor-core kernel does not take
+    WGradArgs w5[5];
+    bool tc5 = tc_enabled() && (L.dconv & 3) == 0;
+    for (int kk = 0; kk < 5; kk++) {
+        w5[kk] = wgrad_args(mv_plain(h->dCd, 2 * D), mv_tshift(h->YD2, 4 * D, T, kk - 2), grad + L.dconv + kk, 20 * D, 0, nullptr, M, 2 * D, 4 * D);
+        w5[kk].ks = 5;
+        tc5 = tc5 && tc_wgrad_eligible(w5[kk]);
+    }
+    if (tc5) {
+        DOF_TRY(launch_gemm_wgrad_tc(w5, 5, st, sm));
+    } else {
+        WGradArgs w1 = wgrad_args(mv_plain(h->dCd, 2 * D), mv_conv5(h->YD2, 4 * D, T, +1), grad + L.dconv, 20 * D, 0, nullptr, M, 2 * D, 20 * D);
+        DOF_TRY(launch_gemm_wgrad(&w1, 1, st, sm));
+    }
     { ProfScope ps("conv_w_transpose", st);
     conv_w_transpose_kernel<<<cdiv(2 * D * 4 * D * 5, 256), 256, 0, st>>>(state + L.dconv, h->Wt, 2 * D, 4 * D); }
     DOF_LAUNCH_CHECK();

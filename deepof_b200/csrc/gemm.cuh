@@ -219,8 +219,10 @@ struct WGradArgs {
     float* dW; int ldo; int oT;   // oT=0: dW[n*ldo+k]; oT=1: dW[k*ldo+n]
     float* db;                    // [N] or null
     int M, N, K;
+    int ks;                       // tensor-core kernel only, oT=0: column stride of the output, dW[n*ldo + k*ks] (0 = 1)
 };
-struct WGradBatch { WGradArgs g[2]; };
+#define WG_MAXBATCH 5
+struct WGradBatch { WGradArgs g[WG_MAXBATCH]; };
 
 #define WG_RB 32
 __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const WGradBatch wb, int ktiles) {

@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
                 for (int j = 0; j < 16; j++) {
                     int k = c0 + j;
                     if (k < g.K) {
-                        float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + k;
+                        float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + (size_t)k * (g.ks > 0 ? g.ks : 1);
                         atomicAdd(o, v[j]);
                     } else if (k == g.K && g.db) {
                         atomicAdd(g.db + n, v[j]);
@@ -659,6 +659,7 @@ static int launch_gemm_wgrad_tc(const WGradArgs* gs, int nbatch, cudaStream_t st
     WGradBatch wb;
     memset(&wb, 0, sizeof(wb));
     int M = 0;
+    if (nbatch > WG_MAXBATCH) DOF_FAIL(DOF_ERR_ARG, "at most %d batched TC wgrads", WG_MAXBATCH);
     for (int i = 0; i < nbatch; i++) {
         wb.g[i] = gs[i];
         if (gs[i].M > M) M = gs[i].M;
