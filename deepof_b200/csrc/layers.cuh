@@ -147,13 +147,16 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const ConvWgradArgs a) 
 }
 
 // Same gradient, one WARP per sequence: the [T, C] block of dCv is one contiguous run that the warp streams with
-// float4 loads (C/4 lanes per time step, 32/(C/4) steps per load instruction = 512 contiguous bytes, four of them in
-// flight); each lane keeps the 4 x F x 5 partial sums of its four channels, the few Xs values come from L1.
+// float4 loads.  C/4 lanes cover a time step; the 32/(C/4) lane groups of the warp each own a run of consecutive
+// steps, so the 5-tap window of Xs SLIDES through registers (F new values per step instead of 5 F) and every warp load
+// still covers whole 128-byte lines; four loads are in flight per lane.  Each lane keeps the 4 x F x 5 partial sums
+// of its four channels.
 template <int C, int F>
 __global__ void __launch_bounds__(256) conv_wgrad_vec_kernel(const ConvWgradArgs a) {
     constexpr int LPR = C / 4, RPW = 32 / LPR, NW = C * F * 5;
     __shared__ float sdw[NW];
-    const int lane = threadIdx.x & 31, c4 = (lane % LPR) * 4, toff = lane / LPR, T = a.T;
+    const int lane = threadIdx.x & 31, c4 = (lane % LPR) * 4, grp = lane / LPR, T = a.T;
+    const int chunk = (T + RPW - 1) / RPW, tb = grp * chunk, te = min(T, tb + chunk);
     for (int i = threadIdx.x; i < NW; i += blockDim.x) sdw[i] = 0.f;
     __syncthreads();
     float acc[4][F][5];
@@ -168,30 +171,40 @@ __global__ void __launch_bounds__(256) conv_wgrad_vec_kernel(const ConvWgradArgs
     for (long long seq = warp; seq < a.S; seq += nwarps) {
         const float* __restrict__ dc = a.dCv + seq * T * C + c4;
         const float* __restrict__ xs = a.Xs + seq * T * F;
-        for (int t0 = toff; t0 < T; t0 += 4 * RPW) {
+        float w[5][F];              // at step t (after the shift): w[k] = Xs[t + k - 2]
+#pragma unroll
+        for (int k = 1; k < 5; k++) {
+            const int tt = tb + k - 3;
+#pragma unroll
+            for (int f = 0; f < F; f++) w[k][f] = (tt >= 0 && tt < T) ? __ldg(xs + tt * F + f) : 0.f;
+        }
+        for (int t0 = tb; t0 < te; t0 += 4) {
             float4 d[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int t = t0 + q * RPW;
-                d[q] = (t < T) ? __ldcs(reinterpret_cast<const float4*>(dc + (size_t)t * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int t = t0 + q;
+                d[q] = (t < te) ? __ldcs(reinterpret_cast<const float4*>(dc + (size_t)t * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int t = t0 + q * RPW;
-                if (t >= T) continue;
+                const int t = t0 + q;
+                if (t >= te) break;
 #pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const int tt = t + k - 2;
-                    if (tt < 0 || tt >= T) continue;
+                for (int f = 0; f < F; f++) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) w[k][f] = w[k + 1][f];
+                    w[4][f] = (t + 2 < T) ? __ldg(xs + (t + 2) * F + f) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 5; k++)
 #pragma unroll
                     for (int f = 0; f < F; f++) {
-                        const float xv = __ldg(xs + tt * F + f);
+                        const float xv = w[k][f];
                         acc[0][f][k] = fmaf(d[q].x, xv, acc[0][f][k]);
                         acc[1][f][k] = fmaf(d[q].y, xv, acc[1][f][k]);
                         acc[2][f][k] = fmaf(d[q].z, xv, acc[2][f][k]);
                         acc[3][f][k] = fmaf(d[q].w, xv, acc[3][f][k]);
                     }
-                }
             }
         }
     }
@@ -204,7 +217,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_vec_kernel(const ConvWgradArgs
                 float v = acc[j][f][k];
 #pragma unroll
                 for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (toff == 0) atomicAdd(&sdw[(c4 + j) * F * 5 + f * 5 + k], v);
+                if (grp == 0) atomicAdd(&sdw[(c4 + j) * F * 5 + f * 5 + k], v);
             }
     __syncthreads();
     for (int i = threadIdx.x; i < NW; i += blockDim.x) atomicAdd(a.dW + i, sdw[i]);
