@@ -126,7 +126,10 @@ def _oracle_case(T, N, D, K, B, seed, pad=False):
 
 @pytest.mark.parametrize("T,N,D,K,B,pad", [(25, 14, 16, 8, 96, False), (25, 14, 8, 4, 64, False),
                                            (24, 11, 6, 5, 33, False), (25, 14, 16, 8, 40, True),
-                                           (12, 5, 4, 3, 7, False), (25, 14, 32, 16, 16, False)])
+                                           (12, 5, 4, 3, 7, False), (25, 14, 32, 16, 16, False),
+                                           # B*T >= 4096 rows: the decoder's tensor-core weight-gradient GEMMs, incl. the
+                                           # five time-shifted per-tap GEMMs of the Conv1d(k5) weight gradient
+                                           (25, 14, 16, 8, 192, False)])
 def test_eval_and_step_vs_oracle(T, N, D, K, B, pad):
     from deepof_b200 import VaDEB200, VadeLossCfg
     adj, E, x, a = _oracle_case(T, N, D, K, B, seed=100 + D + B, pad=pad)
