@@ -196,6 +196,42 @@ def test_batch_chunking_and_determinism():
     assert torch.equal(emb1, emb3) and torch.equal(q1, q3)
 
 
+def test_full_size_batch_properties():
+    """BASELINE cfg2 batch (4096 windows/GPU), size-independent properties that tie the full-size launch geometry
+    (896-CTA GRU grids, tensor-core GEMM tiles, 1.4 M-row LayerNorm / conv launches) to the sizes pinned to the oracle:
+    (1) embeddings / soft assignments of the full batch equal those of the same windows pushed through in chunks of 96;
+    (2) with the batch-level loss terms switched off the loss is a mean over windows, so the gradient of the full batch
+        equals the mean of the gradients of its 32 chunks of 128 windows (linearity)."""
+    from deepof_b200 import VaDEB200, VadeLossCfg
+    T, N, D, K, B = 25, 14, 16, 8, 4096
+    adj, E, x, a = _oracle_case(T, N, D, K, B, seed=77)
+    m = VaDEB200((T, N, 3), (T, E, 1), adj, D, K, max_batch=B, training=True, seed=3)
+    emb, q = m.embed(x, a)
+    small = VaDEB200((T, N, 3), (T, E, 1), adj, D, K, max_batch=96, training=False, seed=3)
+    small.load_state_dict(m.state_dict())
+    emb_c, q_c = small.embed(x, a)          # 43 chunks
+    assert rel_l2(emb.cpu(), emb_c.cpu()) < 1e-5 and rel_l2(q.cpu(), q_c.cpu()) < 1e-5
+    top2 = q_c.cpu().topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-4
+    assert torch.equal(q.cpu().argmax(1)[clear], q_c.cpu().argmax(1)[clear])
+
+    cfg = VadeLossCfg(pretrain_mode=True, kl_weight=0.15, kmeans_loss_weight=0.0, model_kmeans_weight=0.0,
+                      repel_weight=0.0, nonempty_weight=0.0)
+    eps = torch.randn(B, D, generator=torch.Generator().manual_seed(5))
+    m.loss_grad(x, a, cfg, eps=eps)
+    g_full = m.grad.clone()
+    loss_full = m.logs_dict()["total_loss"] if "total_loss" in m.logs_dict() else None
+    acc = torch.zeros_like(g_full, dtype=torch.float64)
+    CH = 128
+    for s0 in range(0, B, CH):
+        m.loss_grad(x[s0:s0 + CH], a[s0:s0 + CH], cfg, eps=eps[s0:s0 + CH])
+        acc += m.grad.double()
+    acc /= B // CH
+    err = float((g_full.double() - acc).norm() / acc.norm())
+    print("full-size gradient linearity rel-L2", err, "loss", loss_full)
+    assert err < 1e-4, err
+
+
 def test_errors_are_loud():
     from deepof_b200 import VaDEB200, DofError, VadeLossCfg
     adj = O.default_adjacency(5)
