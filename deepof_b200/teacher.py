@@ -73,3 +73,150 @@ def initialize_gmm_from_teacher(model, z_all: torch.Tensor, tau_star: torch.Tens
         ent = float(-(prior * prior.clamp_min(1e-9).log()).sum())
         print("Initialized GMM from teacher τ*: "
               f"mean |μ|={float(means.norm(dim=1).mean()):.3f}, mean σ²={float(log_vars.exp().mean()):.5f}, entropy(π)={ent:.3f}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TURTLE teacher (teacher_model.py:43-351, 710-792; Gadetsky et al., arXiv 2406.07236) on device-resident views.
+#
+# The reference runs V x M tiny autograd graphs per outer step (V views, M = 100-200 inner SGD steps): ~25 kernel
+# launches per head and step.  Here the V per-view heads are ONE batched problem (views zero-padded to a common width,
+# [V, B, Dmax] x [V, Dmax, K] bmm) and the inner SGD uses the closed-form gradient of the soft cross-entropy of a linear
+# head, so an inner step is 6 launches for all views; only the single task-encoder update per outer step goes through
+# autograd.  Batch order and initial weights consume torch's global generator exactly like the reference (same
+# nn.Linear construction order, a DataLoader over window INDICES with the same batch size / shuffle / drop_last), so
+# with the same seed tau* agrees with the reference up to fp32 reassociation.
+# ---------------------------------------------------------------------------------------------------------------------
+class TurtleTeacherB200:
+    """Mirror of ``TurtleTeacher`` (teacher_model.py:152-351): ``fit(batches)``, ``predict(batches)``."""
+
+    def __init__(self, feature_dims, n_components: int, gamma: float = 10.0, alpha_sample_entropy: float = 0.1,
+                 inner_lr: float = 0.1, inner_steps: int = 100, head_wd: float = 1e-4, head_temp: float = 0.5,
+                 task_temp: float = 0.5, normalize_feats: bool = True, lr_theta: float = 5e-3,
+                 delta_death_barrier: float = 40.0, device="cpu"):
+        self.dims = [int(d) for d in feature_dims]
+        self.V, self.K, self.Dmax = len(self.dims), int(n_components), max(self.dims)
+        self.gamma, self.alpha, self.delta = float(gamma), float(alpha_sample_entropy), float(delta_death_barrier)
+        self.inner_lr, self.M, self.head_wd = float(inner_lr), int(inner_steps), float(head_wd)
+        self.head_temp, self.task_temp, self.normalize_feats = float(head_temp), float(task_temp), bool(normalize_feats)
+        self.device = torch.device(device)
+        # same construction order as the reference (heads first, then the task encoder) -> same draws from the global RNG
+        heads = [torch.nn.Linear(d, self.K) for d in self.dims]
+        projs = [torch.nn.Linear(d, self.K) for d in self.dims]
+        self.Wh, self.bh = self._stack(heads)                   # [V, K, Dmax], [V, K]   per-view heads (inner SGD)
+        Wp, bp = self._stack(projs)
+        self.Wp = Wp.requires_grad_(True)                       # task encoder (outer Adam)
+        self.bp = bp.requires_grad_(True)
+        self.opt_theta = torch.optim.Adam([self.Wp, self.bp], lr=lr_theta)
+
+    def _stack(self, linears):
+        W = torch.zeros(self.V, self.K, self.Dmax, device=self.device)
+        b = torch.zeros(self.V, self.K, device=self.device)
+        with torch.no_grad():
+            for v, lin in enumerate(linears):
+                W[v, :, :self.dims[v]] = lin.weight.to(self.device)
+                b[v] = lin.bias.to(self.device)
+        return W, b
+
+    def _pack(self, feats_list):
+        """[V, B, Dmax] zero-padded float32 stack of one batch of views."""
+        B = feats_list[0].shape[0]
+        X = torch.zeros(self.V, B, self.Dmax, device=self.device)
+        for v, f in enumerate(feats_list):
+            X[v, :, :self.dims[v]] = f.to(self.device, non_blocking=True).float()
+        return X
+
+    def _tau(self, X):
+        logits = (torch.baddbmm(self.bp.unsqueeze(1), X, self.Wp.transpose(1, 2)) / self.task_temp).sum(0)
+        return torch.softmax(logits / max(self.V, 1), dim=-1)               # teacher_model.py:132-150
+
+    @torch.no_grad()
+    def _inner_fit(self, Xn, tau):
+        """M SGD steps (lr, weight decay on weight AND bias like torch.optim.SGD over head.parameters()) of every head
+        on  mean_b -sum_k clamp(tau,1e-8,1)_bk log softmax(head(x)/T)_bk  (teacher_model.py:84-105, :32-40)."""
+        t = tau.detach().clamp(min=1e-8, max=1.0)
+        tsum = t.sum(-1, keepdim=True)
+        B = Xn.shape[1]
+        scale = 1.0 / (B * self.head_temp)
+        XT = Xn.transpose(1, 2).contiguous()
+        for _ in range(self.M):
+            p = torch.softmax(torch.baddbmm(self.bh.unsqueeze(1), Xn, self.Wh.transpose(1, 2)) / self.head_temp, dim=-1)
+            g = (p * tsum - t) * scale                                       # d loss / d (x W^T + b)   [V, B, K]
+            dW = torch.bmm(XT, g).transpose(1, 2)                            # [V, K, Dmax]
+            self.Wh.sub_(self.inner_lr * (dW + self.head_wd * self.Wh))
+            self.bh.sub_(self.inner_lr * (g.sum(1) + self.head_wd * self.bh))
+
+    def fit(self, loader, outer_steps: int = 200, rho: float = 0.04, verbose: bool = True):
+        """teacher_model.py:240-351.  ``loader`` yields lists of per-view feature batches [B, D_v] (any device)."""
+        import math
+        ent = lambda p: -(p.clamp_min(1e-9) * p.clamp_min(1e-9).log()).sum(-1)
+        it = iter(loader)
+        K = self.K
+        for step in range(outer_steps):
+            try:
+                feats = next(it)
+            except StopIteration:
+                it = iter(loader)
+                feats = next(it)
+            X = self._pack(feats)
+            Xn = torch.nn.functional.normalize(X, dim=-1) if self.normalize_feats else X
+            tau = self._tau(X)
+            self._inner_fit(Xn, tau)
+            with torch.no_grad():
+                logp = torch.log_softmax(torch.baddbmm(self.bh.unsqueeze(1), Xn, self.Wh.transpose(1, 2)) / self.head_temp, -1)
+            ce = -(tau.clamp(min=1e-8, max=1.0).unsqueeze(0) * logp).sum(-1).mean(1).sum() / max(self.V, 1)
+            sample_entropy = ent(tau).mean()
+            marginal = tau.mean(0)
+            marg_gap = torch.relu(math.log(K) - ent(marginal.unsqueeze(0)).mean())
+            frac = 1.0 - float(step) / float(max(1, outer_steps))
+            gamma_t = self.gamma * frac
+            dead_floor = max(1e-4, 0.1 / K)
+            usage = (tau.clamp_min(1e-8) ** 2.0).mean(0)
+            dead_pen = torch.relu(dead_floor - usage).sum() / (dead_floor * K)
+            delta_t = self.delta * max(0.5, 0.6 + 0.4 * frac)
+            loss = ce + self.alpha * sample_entropy + gamma_t * marg_gap + delta_t * dead_pen
+            if (step % 2) != 0 and rho > 0.0:                                # batch-local smoothness on odd steps
+                loss = loss + rho * (tau[1:] - tau[:-1]).abs().sum(-1).mean()
+            self.opt_theta.zero_grad(set_to_none=True)
+            loss.backward()
+            self.opt_theta.step()
+            if verbose and (step % 20 == 0 or step == outer_steps - 1):
+                print(f"[Teacher] step {step:03d} | loss {float(loss):.4f} | CE {float(ce):.4f} | E[H(τ)] {float(sample_entropy):.4f} | "
+                      f"mean max_p {float(tau.max(1).values.mean()):.3f} | dead_pen {float(dead_pen):.3f}")
+
+    @torch.no_grad()
+    def predict(self, loader) -> torch.Tensor:
+        """Soft assignments [N, K] in loader order (teacher_model.py:219-238); stays on the teacher's device."""
+        return torch.cat([self._tau(self._pack(feats)) for feats in loader], dim=0)
+
+
+def run_turtle_teacher_on_views(views_dict: dict, n_components: int, gamma: float = 6.0, alpha_sample_entropy: float = 1.0,
+                                outer_steps: int = 200, inner_steps: int = 200, normalize_feats: bool = True,
+                                verbose: bool = True, device=None, head_temp: float = 0.3, task_temp: float = 0.3,
+                                batch_size: int = 2048):
+    """Same signature and result as teacher_model.py:710-792: ``(teacher, tau_star [N, K])``.  The views stay resident
+    on ``device``; only window indices go through the (shuffling, drop_last) DataLoader, which keeps the consumption of
+    torch's global generator — hence the batch order — identical to the reference's loader over the view tensors."""
+    from torch.utils.data import DataLoader, TensorDataset
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    views = [v.to(device).float() for v in views_dict.values() if v is not None]
+    assert len(views) > 0, "No active views found."
+    N = views[0].shape[0]
+    index_set = TensorDataset(torch.arange(N))
+    loader = DataLoader(index_set, batch_size=batch_size, shuffle=True, num_workers=0, drop_last=True)
+    teacher = TurtleTeacherB200([v.shape[1] for v in views], n_components, gamma=gamma,
+                                alpha_sample_entropy=alpha_sample_entropy, inner_lr=0.1, inner_steps=inner_steps,
+                                head_wd=1e-4, head_temp=head_temp, task_temp=task_temp, normalize_feats=normalize_feats,
+                                lr_theta=1e-3, device=device)
+
+    class _Gather:
+        def __init__(self, ld):
+            self.ld = ld
+
+        def __iter__(self):
+            for (idx,) in self.ld:
+                idx = idx.to(device)
+                yield [v.index_select(0, idx) for v in views]
+
+    teacher.fit(_Gather(loader), outer_steps=outer_steps, rho=0.04, verbose=verbose)
+    seq = DataLoader(index_set, batch_size=batch_size * 2, shuffle=False, num_workers=0)
+    return teacher, teacher.predict(_Gather(seq))

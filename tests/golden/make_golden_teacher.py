@@ -1,5 +1,6 @@
-"""Golden vectors for deepof_b200.teacher, produced by the UNMODIFIED reference function
-`initialize_gmm_from_teacher` (deepof/clustering/teacher_model.py:394-460).  Run in the build container:
+"""Golden vectors for deepof_b200.teacher, produced by the UNMODIFIED reference functions
+`initialize_gmm_from_teacher` (deepof/clustering/teacher_model.py:394-460) -> teacher_gmm_init.npz and
+`run_turtle_teacher_on_views` (:710-792, TurtleTeacher :152-351) -> teacher_turtle.npz.  Run in the build container:
 
     python tests/golden/make_golden_teacher.py
 
@@ -55,7 +56,7 @@ def case(name, N, D, C, seed):
             f"{name}/prior": m.latent_space.prior.numpy()}
 
 
-if __name__ == "__main__":
+def main_gmm_init():
     out = {}
     out.update(case("dense", 3000, 16, 8, 11))
     out.update(case("empty", 2000, 8, 4, 12))
@@ -63,3 +64,34 @@ if __name__ == "__main__":
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "teacher_gmm_init.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
+def turtle_case(name, N, dims, K, seed, outer, inner, batch):
+    """Reference `run_turtle_teacher_on_views` (teacher_model.py:710-792) on synthetic clustered views; the global
+    generator is seeded right before the call, the test re-seeds it the same way."""
+    g = torch.Generator().manual_seed(seed)
+    lab = torch.randint(0, K, (N,), generator=g)
+    views = {}
+    for i, d in enumerate(dims):
+        centres = torch.randn(K, d, generator=g) * 1.5
+        views[f"view{i}"] = centres[lab] + torch.randn(N, d, generator=g) * 0.7
+    torch.manual_seed(seed + 100)
+    teacher, tau = TM.run_turtle_teacher_on_views(views, K, outer_steps=outer, inner_steps=inner, batch_size=batch, verbose=False)
+    out = {f"{name}/tau_star": tau.numpy(), f"{name}/meta": np.array([N, K, seed, outer, inner, batch] + list(dims))}
+    for i, d in enumerate(dims):
+        out[f"{name}/view{i}"] = views[f"view{i}"].numpy()
+        out[f"{name}/head{i}_w"] = teacher.heads.heads[i].weight.detach().numpy()
+        out[f"{name}/head{i}_b"] = teacher.heads.heads[i].bias.detach().numpy()
+        out[f"{name}/proj{i}_w"] = teacher.task_encoder.projs[i].weight.detach().numpy()
+        out[f"{name}/proj{i}_b"] = teacher.task_encoder.projs[i].bias.detach().numpy()
+    return out
+
+
+if __name__ == "__main__":
+    main_gmm_init()
+    out = {}
+    out.update(turtle_case("three_views", 2000, [16, 12, 8], 6, 21, outer=40, inner=30, batch=512))
+    out.update(turtle_case("one_view", 1500, [10], 4, 22, outer=25, inner=20, batch=256))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "teacher_turtle.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items() if "tau" in k})

@@ -53,3 +53,61 @@ def test_gmm_init_chunking_is_exact_enough_and_parameters_are_written_in_place()
 def test_gmm_init_rejects_mismatched_inputs():
     with pytest.raises(ValueError):
         gmm_moments_from_teacher(torch.zeros(10, 4), torch.zeros(9, 3))
+
+
+# ---- TURTLE teacher: batched closed-form heads vs the reference's per-view autograd loops -------------------------
+from deepof_b200.teacher import TurtleTeacherB200, run_turtle_teacher_on_views  # noqa: E402
+
+T = np.load(os.path.join(os.path.dirname(__file__), "golden", "teacher_turtle.npz"))
+
+
+def _turtle_inputs(name):
+    meta = [int(v) for v in T[f"{name}/meta"]]
+    N, K, seed, outer, inner, batch = meta[:6]
+    dims = meta[6:]
+    views = {f"view{i}": torch.from_numpy(T[f"{name}/view{i}"]) for i in range(len(dims))}
+    return views, dims, K, seed, outer, inner, batch
+
+
+@pytest.mark.parametrize("name", ["three_views", "one_view"])
+def test_turtle_teacher_matches_reference(name):
+    """Same seed -> same initial heads / task encoder and the same shuffled batches as `run_turtle_teacher_on_views`
+    (teacher_model.py:710-792); tau* and every fitted parameter agree to fp32 reassociation (measured 2e-7)."""
+    views, dims, K, seed, outer, inner, batch = _turtle_inputs(name)
+    torch.manual_seed(seed + 100)
+    teacher, tau = run_turtle_teacher_on_views(views, K, outer_steps=outer, inner_steps=inner, batch_size=batch, verbose=False)
+    ref = torch.from_numpy(T[f"{name}/tau_star"])
+    assert tau.shape == ref.shape
+    assert float((tau - ref).abs().max()) < 1e-5
+    assert torch.equal(tau.argmax(1), ref.argmax(1))
+    assert float((tau.sum(1) - 1).abs().max()) < 1e-5
+    for i, d in enumerate(dims):
+        assert float((teacher.Wh[i, :, :d] - torch.from_numpy(T[f"{name}/head{i}_w"])).abs().max()) < 1e-5
+        assert float((teacher.bh[i] - torch.from_numpy(T[f"{name}/head{i}_b"])).abs().max()) < 1e-5
+        assert float((teacher.Wp[i, :, :d].detach() - torch.from_numpy(T[f"{name}/proj{i}_w"])).abs().max()) < 1e-5
+        assert float((teacher.bp[i].detach() - torch.from_numpy(T[f"{name}/proj{i}_b"])).abs().max()) < 1e-5
+        # zero padding of narrower views never leaks into the parameters
+        assert float(teacher.Wh[i, :, d:].abs().sum()) == 0.0 and float(teacher.Wp[i, :, d:].detach().abs().sum()) == 0.0
+
+
+def test_turtle_none_views_are_skipped_and_empty_is_an_error():
+    views, dims, K, seed, outer, inner, batch = _turtle_inputs("one_view")
+    torch.manual_seed(1)
+    _, tau_a = run_turtle_teacher_on_views({"nodes": views["view0"], "angles": None}, K, outer_steps=3, inner_steps=2,
+                                           batch_size=batch, verbose=False)
+    torch.manual_seed(1)
+    _, tau_b = run_turtle_teacher_on_views(views, K, outer_steps=3, inner_steps=2, batch_size=batch, verbose=False)
+    assert torch.equal(tau_a, tau_b)
+    with pytest.raises(AssertionError):
+        run_turtle_teacher_on_views({"nodes": None}, K)
+
+
+def test_turtle_teacher_feeds_gmm_init():
+    """tau* -> initialize_gmm_from_teacher: the plumbing of the VaDE main phase (training.py teacher branch)."""
+    views, dims, K, seed, outer, inner, batch = _turtle_inputs("one_view")
+    ref = torch.from_numpy(T["one_view/tau_star"])
+    z = views["view0"][:, :8].contiguous()
+    m = _stub_model(K, 8)
+    initialize_gmm_from_teacher(m, z, ref, verbose=False)
+    assert torch.isfinite(m.latent_space.gmm_means).all() and torch.isfinite(m.latent_space.gmm_log_vars).all()
+    assert abs(float(m.latent_space.prior.sum()) - 1.0) < 1e-6
