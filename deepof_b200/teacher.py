@@ -220,3 +220,126 @@ def run_turtle_teacher_on_views(views_dict: dict, n_components: int, gamma: floa
     teacher.fit(_Gather(loader), outer_steps=outer_steps, rho=0.04, verbose=verbose)
     seq = DataLoader(index_set, batch_size=batch_size * 2, shuffle=False, num_workers=0)
     return teacher, teacher.predict(_Gather(seq))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The teacher's PCA views (teacher_model.py:464-708): fit_nodes_pca / fit_angles_pca / extract_pca_edges_view run
+# scikit-learn's IncrementalPCA (pinned in this image: scikit-learn 1.9) over the flattened windows in batches and then
+# transform every window.  Restated here on device tensors: the published incremental-SVD update (Ross et al. 2008, as
+# sklearn.decomposition.IncrementalPCA.partial_fit implements it: running column mean, SVD of
+# [diag(S) Vt ; X - batch mean ; sqrt(n_seen n_batch / n_total) (mean - batch mean)], deterministic sign, truncation to
+# n_components) with the same batch partition, in float64 (the reference runs LAPACK in float32; the views agree to
+# ~1e-4 of their scale).  The windows stay where they are (HBM); nothing is materialised on the host.
+# ---------------------------------------------------------------------------------------------------------------------
+class IncrementalPCAB200:
+    """partial_fit / transform of sklearn.decomposition.IncrementalPCA (whiten=False) on torch tensors."""
+
+    def __init__(self, n_components: int):
+        self.n_components = int(n_components)
+        self.components_ = None          # [k, D] float64
+        self.singular_values_ = None
+        self.mean_ = None
+        self.n_samples_seen_ = 0
+
+    @torch.no_grad()
+    def partial_fit(self, X: torch.Tensor):
+        X = X.to(torch.float64)
+        n, D = X.shape
+        k = self.n_components
+        if self.components_ is None and not (1 <= k <= D):
+            raise ValueError(f"n_components={k} invalid for n_features={D}")
+        if k > n:
+            raise ValueError(f"n_components={k} must be less or equal to the batch number of samples {n}")
+        batch_mean = X.mean(0)
+        if self.n_samples_seen_ == 0:
+            col_mean, total = batch_mean, n
+            M = X - batch_mean
+        else:
+            total = self.n_samples_seen_ + n
+            col_mean = (self.mean_ * self.n_samples_seen_ + batch_mean * n) / total
+            corr = (self.n_samples_seen_ / total * n) ** 0.5 * (self.mean_ - batch_mean)
+            M = torch.cat([self.singular_values_.unsqueeze(1) * self.components_, X - batch_mean, corr.unsqueeze(0)], 0)
+        U, S, Vt = torch.linalg.svd(M, full_matrices=False)
+        # sklearn.utils.extmath.svd_flip(u_based_decision=False): the largest-|.| entry of every row of Vt is positive
+        idx = Vt.abs().argmax(dim=1)
+        sign = torch.sign(Vt[torch.arange(Vt.shape[0], device=Vt.device), idx])
+        sign[sign == 0] = 1.0
+        Vt = Vt * sign.unsqueeze(1)
+        self.components_, self.singular_values_ = Vt[:k].contiguous(), S[:k].contiguous()
+        self.mean_, self.n_samples_seen_ = col_mean, total
+        return self
+
+    @torch.no_grad()
+    def transform(self, X: torch.Tensor) -> torch.Tensor:
+        return ((X.to(torch.float64) - self.mean_) @ self.components_.t()).float()
+
+
+@torch.no_grad()
+def pca_view(flat: torch.Tensor, n_components: int, batch_size: int, max_samples: Optional[int] = None):
+    """One teacher view: IncrementalPCA fitted over consecutive batches of ``flat`` [N, D] (truncated to ``max_samples``
+    windows like teacher_model.py:509-516), then every window transformed.  Returns (pca, feats [N, n_components])."""
+    pca = IncrementalPCAB200(n_components)
+    N = flat.shape[0]
+    seen = 0
+    for i in range(0, N, batch_size):
+        Xb = flat[i:i + batch_size]
+        if max_samples is not None and seen >= max_samples:
+            break
+        if max_samples is not None and seen + Xb.shape[0] > max_samples:
+            Xb = Xb[:max(1, max_samples - seen)]
+        pca.partial_fit(Xb)
+        seen += Xb.shape[0]
+    feats = torch.cat([pca.transform(flat[i:i + batch_size]) for i in range(0, N, batch_size)], 0)
+    return pca, feats
+
+
+@torch.no_grad()
+def teacher_views_from_windows(x: torch.Tensor, a: torch.Tensor, angles: Optional[torch.Tensor] = None, *,
+                               pca_nodes_dim: int = 32, pca_edges_dim: int = 16, pca_angles_dim: int = 32,
+                               batch_size_nodes: int = 4096, batch_size_edges: int = 8192, batch_size_angles: int = 8192,
+                               include_nodes_view: bool = True, include_edges_view: bool = True,
+                               latent_view: Optional[torch.Tensor] = None) -> dict:
+    """The ``views`` dict of ``maybe_build_turtle_teacher`` (teacher_model.py:811-905) from resident windows
+    x [N,T,Nn,F>=3], a [N,T,E,Fe] (and angles [N,T,A]): keys z / pca_pos / pca_spd / pca_edges / pca_angles, None = off."""
+    if x.shape[-1] < 3:
+        raise ValueError(f"Expected at least 3 channels (x,y,speed); got F={x.shape[-1]}")
+    N = x.shape[0]
+    views = {"z": latent_view, "pca_pos": None, "pca_spd": None, "pca_edges": None, "pca_angles": None}
+    if include_nodes_view:                                                   # fit_nodes_pca :464-573
+        views["pca_pos"] = pca_view(x[..., :2].reshape(N, -1), pca_nodes_dim, batch_size_nodes)[1]
+        views["pca_spd"] = pca_view(x[..., 2:3].reshape(N, -1), pca_nodes_dim, batch_size_nodes)[1]
+    if include_edges_view:                                                   # extract_pca_edges_view :638-708
+        views["pca_edges"] = pca_view(a.reshape(N, -1), pca_edges_dim, batch_size_edges)[1]
+    if angles is not None:                                                   # fit_angles_pca :576-635
+        views["pca_angles"] = pca_view(angles.reshape(N, -1), pca_angles_dim, batch_size_angles)[1]
+    return views
+
+
+def build_turtle_teacher(x: torch.Tensor, a: torch.Tensor, n_components: int, *, angles: Optional[torch.Tensor] = None,
+                         latent_view: Optional[torch.Tensor] = None, device=None, include_latent_view: bool = True,
+                         include_nodes_view: bool = True, include_edges_view: bool = False,
+                         include_angles_view: bool = False, pca_nodes_dim: int = 32, pca_edges_dim: int = 32,
+                         pca_angles_dim: int = 32, batch_size_nodes: int = 4096, batch_size_edges: int = 8192,
+                         batch_size_angles: int = 8192, teacher_gamma: float = 8.0, teacher_alpha_sample_entropy: float = 2.0,
+                         teacher_outer_steps: int = 500, teacher_inner_steps: int = 100,
+                         teacher_normalize_feats: bool = True, teacher_head_temp: float = 0.35,
+                         teacher_task_temp: float = 0.35, teacher_batch_size: int = 2048, verbose: bool = True):
+    """``maybe_build_turtle_teacher`` (teacher_model.py:811-905) on resident windows, keyword defaults = the reference's
+    ``TurtleTeacherCfg`` (model_utils_new.py:78-125).  Returns ``(teacher, tau_star [N, K], views)``; the view order
+    (z, pca_pos, pca_spd, pca_edges, pca_angles) is the reference's, it fixes which head draws which initial weights."""
+    if include_latent_view and latent_view is None:
+        raise ValueError("include_latent_view=True but latent_view=None")
+    if include_angles_view and angles is None:
+        raise ValueError("include_angles_view=True but angles=None")
+    device = torch.device(device) if device is not None else x.device
+    views = teacher_views_from_windows(
+        x.to(device), a.to(device), angles.to(device) if include_angles_view else None, pca_nodes_dim=pca_nodes_dim,
+        pca_edges_dim=pca_edges_dim, pca_angles_dim=pca_angles_dim, batch_size_nodes=batch_size_nodes,
+        batch_size_edges=batch_size_edges, batch_size_angles=batch_size_angles, include_nodes_view=include_nodes_view,
+        include_edges_view=include_edges_view, latent_view=latent_view.to(device) if include_latent_view else None)
+    teacher, tau_star = run_turtle_teacher_on_views(
+        views, n_components, gamma=teacher_gamma, alpha_sample_entropy=teacher_alpha_sample_entropy,
+        outer_steps=teacher_outer_steps, inner_steps=teacher_inner_steps, normalize_feats=teacher_normalize_feats,
+        verbose=verbose, device=device, head_temp=teacher_head_temp, task_temp=teacher_task_temp,
+        batch_size=teacher_batch_size)
+    return teacher, tau_star.detach(), views

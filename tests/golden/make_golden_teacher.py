@@ -95,3 +95,37 @@ if __name__ == "__main__":
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "teacher_turtle.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items() if "tau" in k})
+
+
+class _StubDataset:
+    """What fit_nodes_pca / extract_pca_edges_view / fit_angles_pca need from BatchDictDataset: make_loader(batch_size=...)
+    yielding (x, a[, angles]) batches in order (h5py is not installed here, the functions themselves run unmodified)."""
+    return_angles = True
+
+    def __init__(self, x, a, ang):
+        self.x, self.a, self.ang = x, a, ang
+
+    def make_loader(self, batch_size, **kw):
+        return [(self.x[i:i + batch_size], self.a[i:i + batch_size], self.ang[i:i + batch_size])
+                for i in range(0, self.x.shape[0], batch_size)]
+
+
+def views_case():
+    g = torch.Generator().manual_seed(31)
+    N, T, Nn, E, A = 1100, 10, 6, 7, 4
+    base = torch.randn(N, 1, Nn, 3, generator=g)
+    x = base + 0.3 * torch.cumsum(torch.randn(N, T, Nn, 3, generator=g), 1)
+    a = torch.randn(N, T, E, 1, generator=g) * torch.linspace(0.5, 2.0, E).view(1, 1, E, 1)
+    ang = torch.randn(N, T, A, generator=g)
+    ds = _StubDataset(x, a, ang)
+    _, pos, _, spd = TM.fit_nodes_pca(ds, n_components_pos=12, n_components_spd=12, batch_size=400)
+    edges = TM.extract_pca_edges_view(ds, n_components=8, batch_size=512)
+    _, angles = TM.fit_angles_pca(ds, n_components=6, batch_size=300)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "teacher_views.npz")
+    np.savez_compressed(path, x=x.numpy(), a=a.numpy(), ang=ang.numpy(), pca_pos=pos.numpy(), pca_spd=spd.numpy(),
+                        pca_edges=edges.numpy(), pca_angles=angles.numpy())
+    print("wrote", path, pos.shape, spd.shape, edges.shape, angles.shape)
+
+
+if __name__ == "__main__":
+    views_case()

@@ -111,3 +111,72 @@ def test_turtle_teacher_feeds_gmm_init():
     initialize_gmm_from_teacher(m, z, ref, verbose=False)
     assert torch.isfinite(m.latent_space.gmm_means).all() and torch.isfinite(m.latent_space.gmm_log_vars).all()
     assert abs(float(m.latent_space.prior.sum()) - 1.0) < 1e-6
+
+
+# ---- the teacher's PCA views ---------------------------------------------------------------------------------------
+from deepof_b200.teacher import IncrementalPCAB200, pca_view, teacher_views_from_windows  # noqa: E402
+
+VW = np.load(os.path.join(os.path.dirname(__file__), "golden", "teacher_views.npz"))
+
+
+def test_teacher_views_match_reference_functions():
+    """fit_nodes_pca / extract_pca_edges_view / fit_angles_pca (teacher_model.py:464-708, run unmodified on a stub
+    dataset by the golden script) vs the device restatement; the reference runs LAPACK in float32, so 2e-4 of scale."""
+    x, a, ang = (torch.from_numpy(VW[k]) for k in ("x", "a", "ang"))
+    v = teacher_views_from_windows(x, a, ang, pca_nodes_dim=12, pca_edges_dim=8, pca_angles_dim=6, batch_size_nodes=400,
+                                   batch_size_edges=512, batch_size_angles=300)
+    assert v["z"] is None
+    for k in ("pca_pos", "pca_spd", "pca_edges", "pca_angles"):
+        ref = torch.from_numpy(VW[k])
+        assert v[k].shape == ref.shape and v[k].dtype == torch.float32
+        assert float((v[k] - ref).abs().max()) <= 2e-4 * float(ref.abs().max()), k
+    off = teacher_views_from_windows(x, a, None, include_nodes_view=False, pca_edges_dim=8, batch_size_edges=512)
+    assert off["pca_pos"] is None and off["pca_spd"] is None and off["pca_angles"] is None and off["pca_edges"] is not None
+
+
+def test_incremental_pca_is_sklearns_algorithm_in_float64():
+    """Pins the restated update to the third-party implementation the reference calls (scikit-learn IncrementalPCA):
+    float64 in, same batch partition -> components, singular values, mean and scores agree to 1e-9."""
+    sk = pytest.importorskip("sklearn.decomposition")
+    g = np.random.default_rng(5)
+    X = g.normal(size=(900, 40)) @ g.normal(size=(40, 40)) + g.normal(size=(1, 40)) * 3.0
+    ref = sk.IncrementalPCA(n_components=9)
+    mine = IncrementalPCAB200(9)
+    for i in range(0, 900, 250):                       # ragged last batch (150 rows)
+        ref.partial_fit(X[i:i + 250])
+        mine.partial_fit(torch.from_numpy(X[i:i + 250]))
+    assert np.abs(mine.components_.numpy() - ref.components_).max() < 1e-9
+    assert np.abs(mine.singular_values_.numpy() - ref.singular_values_).max() < 1e-8
+    assert np.abs(mine.mean_.numpy() - ref.mean_).max() < 1e-12 and mine.n_samples_seen_ == ref.n_samples_seen_
+    Z = ((torch.from_numpy(X) - mine.mean_) @ mine.components_.t()).numpy()
+    assert np.abs(Z - ref.transform(X)).max() < 1e-8
+
+
+def test_pca_view_max_samples_and_errors():
+    X = torch.from_numpy(VW["a"]).reshape(1100, -1)
+    p_all, _ = pca_view(X, 8, 512)
+    p_cut, f_cut = pca_view(X, 8, 512, max_samples=700)          # second batch truncated to 188 rows, third skipped
+    assert p_all.n_samples_seen_ == 1100 and p_cut.n_samples_seen_ == 700 and f_cut.shape == (1100, 8)
+    with pytest.raises(ValueError):
+        IncrementalPCAB200(50).partial_fit(torch.zeros(20, 100))  # fewer rows than components (sklearn raises too)
+    with pytest.raises(ValueError):
+        teacher_views_from_windows(torch.zeros(4, 5, 3, 2), torch.zeros(4, 5, 2, 1))
+
+
+def test_build_turtle_teacher_end_to_end():
+    """windows -> PCA views -> teacher -> tau* -> GMM init, all on one device; view order and defaults of the reference."""
+    from deepof_b200.teacher import build_turtle_teacher
+    x, a = torch.from_numpy(VW["x"]), torch.from_numpy(VW["a"])
+    z = torch.from_numpy(VW["pca_pos"])[:, :8].contiguous()           # stands in for the model's latent view
+    with pytest.raises(ValueError):
+        build_turtle_teacher(x, a, 5)                                 # latent view is on by default, like the reference
+    torch.manual_seed(3)
+    teacher, tau, views = build_turtle_teacher(x, a, 5, latent_view=z, pca_nodes_dim=12, batch_size_nodes=400,
+                                               teacher_outer_steps=6, teacher_inner_steps=5, teacher_batch_size=256,
+                                               verbose=False)
+    assert list(views) == ["z", "pca_pos", "pca_spd", "pca_edges", "pca_angles"]
+    assert views["pca_edges"] is None and views["pca_angles"] is None and teacher.dims == [8, 12, 12]
+    assert tau.shape == (1100, 5) and float((tau.sum(1) - 1).abs().max()) < 1e-5 and not tau.requires_grad
+    m = _stub_model(5, 8)
+    initialize_gmm_from_teacher(m, z, tau, verbose=False)
+    assert torch.isfinite(m.latent_space.gmm_log_vars).all()
