@@ -12,7 +12,8 @@ checkpoint bundle, with the names, argument meaning and return shapes of ``deepo
 * ``save_model_info / load_model_from_ckpt`` (``model_utils_new.py:263-329, 367-417``): ``torch.save({"state_dict",
   "rebuild_spec", "log_summary"})`` with the reference's keys, so checkpoints move between the two implementations.
 
-Unsupported options raise instead of being ignored (``use_turtle_teacher=True``, other encoders, AMP).
+Unsupported options raise instead of being ignored (``use_turtle_teacher=True`` outside the VaDE run, teacher refresh,
+other encoders, AMP).
 """
 from __future__ import annotations
 
@@ -67,6 +68,9 @@ def step_vade(model: VaDEB200, batch, ctx: SimpleNamespace) -> StepResult:
     sched = getattr(ctx, "kl_scheduler", None)
     if sched is not None:
         cfg.kl_weight = sched.get_weight()
+    lsched = getattr(ctx, "lambda_scheduler", None)
+    if lsched is not None:
+        cfg.lambda_distill = float(lsched.get_weight())                       # training.py:264-265
     tau = None
     tau_star = getattr(ctx, "tau_star", None)
     if tau_star is not None and getattr(ctx, "apply_distill", True) and cfg.lambda_distill > 0.0:
@@ -147,6 +151,11 @@ def train_one_epoch_indexed(model, model_name: str, dataloader, optimizer, step_
                 sched.step()
                 if step == n // 2:
                     mid_kl = sched.get_weight()
+            lsched = getattr(ctx, "lambda_scheduler", None)
+            if lsched is not None:                                            # training.py:173-176
+                lsched.step()
+                if step == n // 2:
+                    mid_lambda = lsched.get_weight()
         else:
             model.adam_step(optimizer["lr"], clip=grad_clip_value or 0.0, grad_scale=scale,
                             weight_decay=optimizer.get("weight_decay", 1e-4))
@@ -248,6 +257,12 @@ def load_model_from_ckpt(ckpt_path: str, max_batch: int = 4096, training: bool =
 
 
 # ---- train entry ------------------------------------------------------------------------------------------------
+# teacher / distillation keywords of the reference's train_deepof_model with its defaults (training.py:624-640, 691-692)
+_TEACHER_KWARGS = dict(teacher_gamma=8.0, teacher_outer_steps=500, teacher_inner_steps=100, teacher_normalize_feats=True,
+                       lambda_distill=4.0, lambda_decay_start=10, lambda_end_weight=0.2, lambda_cooldown=10,
+                       teacher_refresh_every=False, teacher_freeze_at=10, teacher_head_temp=0.5, teacher_task_temp=0.5,
+                       teacher_alpha_sample_entropy=2.0, teacher_batch_size=2048, distill_class_reweight_beta=1.0,
+                       distill_class_reweight_cap=3.0)
 def train_deepof_model(preprocessed_object=None, adjacency_matrix=None, meta_info=None, encoder_type: str = "recurrent",
                        batch_size: int = 1024, latent_dim: int = 8, epochs: int = 10, output_path: Optional[str] = None,
                        n_clusters: int = 10, learning_rate: float = 1e-3, pretrained: Optional[str] = None,
@@ -281,8 +296,13 @@ def train_deepof_model(preprocessed_object=None, adjacency_matrix=None, meta_inf
         return model, None, None, log_summary
     if encoder_type != "recurrent":
         raise NotImplementedError("deepof_b200 implements encoder_type='recurrent' only (transformer / TCN: next round)")
-    if use_turtle_teacher:
-        raise NotImplementedError("the TURTLE teacher is not implemented: call with use_turtle_teacher=False")
+    if use_turtle_teacher and model_name.lower() != "vade":
+        raise NotImplementedError("the TURTLE teacher is wired into the VaDE run only: call with use_turtle_teacher=False "
+                                  "(a precomputed tau_star goes through ctx of the step functions)")
+    tk = {k: unsupported.pop(k) for k in list(unsupported) if k in _TEACHER_KWARGS}
+    tcfg = {**_TEACHER_KWARGS, **tk}
+    if tcfg["teacher_refresh_every"]:
+        raise NotImplementedError("teacher_refresh_every is not mirrored (the reference default is no refresh)")
     if use_amp:
         raise NotImplementedError("AMP is not used: the B200 path computes in fp32-class precision (3xTF32)")
     bad = [k for k, v in unsupported.items() if k in ("main_clustering_loss", "reg_scatter_weight") and v]
@@ -336,6 +356,27 @@ def train_deepof_model(preprocessed_object=None, adjacency_matrix=None, meta_inf
             logs, _, _ = train_one_epoch_indexed(model, "vade", loader, opt, step_vade, ep, pretrain_epochs, 0.75, ctx, world)
             log_summary["train_logs"].append({"phase": "pretrain", "epoch": ep, **logs})
         model.set_pretrain_mode(False)                                        # training.py:1643-1653
+        teacher_ctx, teacher_init_model = {}, None
+        if use_turtle_teacher:                                                # training.py:1664-1712
+            from .teacher import build_turtle_teacher, initialize_gmm_from_teacher, teacher_context
+            z_all = model.embed(x, a)[0]                                      # extract_latents: z_mean in eval mode
+            lam = KLSchedule(nb, kl_annealing_mode, 0, tcfg["lambda_distill"], tcfg["lambda_cooldown"],
+                             tcfg["lambda_end_weight"], at_max_epochs=tcfg["lambda_decay_start"])
+            _, tau_star, _ = build_turtle_teacher(
+                x, a, n_clusters, latent_view=z_all, device=dev, include_latent_view=True,
+                teacher_gamma=tcfg["teacher_gamma"], teacher_alpha_sample_entropy=tcfg["teacher_alpha_sample_entropy"],
+                teacher_outer_steps=tcfg["teacher_outer_steps"], teacher_inner_steps=tcfg["teacher_inner_steps"],
+                teacher_normalize_feats=tcfg["teacher_normalize_feats"], teacher_head_temp=tcfg["teacher_head_temp"],
+                teacher_task_temp=tcfg["teacher_task_temp"], teacher_batch_size=min(tcfg["teacher_batch_size"], Nw),
+                batch_size_nodes=min(4096, Nw), pca_nodes_dim=min(32, Nw, T * N), verbose=False)
+            if world > 1:
+                dist.broadcast(tau_star, src=0)                               # one teacher for all ranks
+            initialize_gmm_from_teacher(model, z_all, tau_star, min_var=0.01, verbose=False)
+            tc = teacher_context(tau_star, True, tcfg["distill_class_reweight_beta"], tcfg["distill_class_reweight_cap"])
+            teacher_ctx = dict(tau_star=tc["tau_star"], class_weight=tc["class_weight"], teacher_marginal=tc["teacher_marginal"],
+                               lambda_scheduler=lam, apply_distill=True)
+            teacher_init_model = build_model(rebuild_spec, max_batch=int(batch_size), training=False)
+            teacher_init_model.load_state_dict(model.state_dict())
         crit = VadeLossCfg.main_defaults(n_clusters)
         crit.kmeans_loss_weight, crit.model_kmeans_weight = float(kmeans_loss), float(kmeans_loss_pretrain)   # training.py:1556
         crit.repel_weight, crit.repel_length_scale = float(repel_weight), float(repel_length_scale)
@@ -344,6 +385,7 @@ def train_deepof_model(preprocessed_object=None, adjacency_matrix=None, meta_inf
         crit.temporal_cohesion_weight, crit.reg_cat_clusters_weight = float(temporal_cohesion_weight), float(reg_cat_clusters)
         ctx = SimpleNamespace(criterion=crit, apply_distill=False,
                               kl_scheduler=KLSchedule(nb, kl_annealing_mode, kl_warmup, kl_max_weight, kl_cooldown, kl_end_weight))
+        ctx.__dict__.update(teacher_ctx)
         model.adam_m.zero_(); model.adam_v.zero_(); model.adam_steps = [0, 0, 0, 0]        # the optimizer is rebuilt
         opt = {"lr": learning_rate, "gmm_lr": gmm_learning_rate}
         for ep in range(int(epochs)):
@@ -388,4 +430,4 @@ def train_deepof_model(preprocessed_object=None, adjacency_matrix=None, meta_inf
     log_summary["val_logs"].append(validate(model, step_fn, vctx))
     if output_path and save_weights and rank == 0:
         save_model_info(os.path.join(output_path, f"{name}_final.pth"), model=model, rebuild_spec=rebuild_spec, log_summary=log_summary)
-    return model, model, None, log_summary
+    return model, model, (teacher_init_model if name == "vade" else None), log_summary

@@ -280,9 +280,14 @@ def pca_view(flat: torch.Tensor, n_components: int, batch_size: int, max_samples
     windows like teacher_model.py:509-516), then every window transformed.  Returns (pca, feats [N, n_components])."""
     pca = IncrementalPCAB200(n_components)
     N = flat.shape[0]
+    bounds = list(range(0, N, batch_size)) + [N]
+    if len(bounds) > 2 and bounds[-1] - bounds[-2] < n_components and max_samples is None:
+        # a ragged tail with fewer rows than components makes scikit-learn (and the reference with it) raise; fold it
+        # into the previous batch instead — the only place this deviates from the reference's batch partition
+        del bounds[-2]
     seen = 0
-    for i in range(0, N, batch_size):
-        Xb = flat[i:i + batch_size]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        Xb = flat[lo:hi]
         if max_samples is not None and seen >= max_samples:
             break
         if max_samples is not None and seen + Xb.shape[0] > max_samples:
@@ -343,3 +348,19 @@ def build_turtle_teacher(x: torch.Tensor, a: torch.Tensor, n_components: int, *,
         verbose=verbose, device=device, head_temp=teacher_head_temp, task_temp=teacher_task_temp,
         batch_size=teacher_batch_size)
     return teacher, tau_star.detach(), views
+
+
+@torch.no_grad()
+def teacher_context(tau_star: torch.Tensor, class_reweight: bool = True, class_reweight_beta: float = 1.0,
+                    class_reweight_cap: Optional[float] = 3.0) -> dict:
+    """What ``VadeLoss.set_teacher`` derives from tau* (losses.py:460-491): the inverse-marginal class weights
+    (``pi^-beta`` normalised to mean 1, capped) and the clamped teacher marginal that lifts the non-empty floor."""
+    pi = tau_star.mean(dim=0).clamp_min(1e-8)
+    out = {"tau_star": tau_star, "teacher_marginal": pi, "class_weight": None}
+    if class_reweight:
+        w = pi.pow(-class_reweight_beta)
+        w = w / w.mean()
+        if class_reweight_cap is not None:
+            w = w.clamp_max(class_reweight_cap)
+        out["class_weight"] = w
+    return out

@@ -52,9 +52,22 @@ def test_train_deepof_model_end_to_end(model_name, T, tmp_path):
     from deepof_b200 import train_deepof_model, load_model_from_ckpt
     adj, train_td = _table_dicts(11, T, 2, 96, seed=1)
     _, val_td = _table_dicts(11, T, 1, 64, seed=9)
-    with pytest.raises(NotImplementedError):
-        train_deepof_model((train_td, val_td), adj, None, encoder_type="recurrent", batch_size=64, latent_dim=6, epochs=1,
-                           n_clusters=4, model_name=model_name)          # TURTLE teacher on (the reference default) is refused
+    if model_name != "VaDE":
+        with pytest.raises(NotImplementedError):
+            train_deepof_model((train_td, val_td), adj, None, encoder_type="recurrent", batch_size=64, latent_dim=6, epochs=1,
+                               n_clusters=4, model_name=model_name)      # TURTLE teacher on (the reference default): VaDE only
+    else:
+        # teacher on: latents -> PCA views -> TURTLE -> tau* -> GMM init -> distillation in the main phase
+        mv, ms, tinit, ls = train_deepof_model((train_td, val_td), adj, None, encoder_type="recurrent", batch_size=64,
+                                               latent_dim=6, epochs=1, n_clusters=4, model_name=model_name, pretrain_epochs=1,
+                                               random_seed=3, teacher_outer_steps=4, teacher_inner_steps=3,
+                                               teacher_batch_size=64, save_weights=False)
+        assert tinit is not None and tinit is not mv
+        assert all(np.isfinite(l["total_loss"]) for l in ls["train_logs"]) and len(ls["train_logs"]) == 2
+        assert ls["train_logs"][-1]["distill_loss"] > 0.0                 # the main phase saw tau*
+        # the teacher-init snapshot holds the moment-matched mixture, the trained model moved on from it
+        assert torch.isfinite(tinit.latent_space.gmm_log_vars).all()
+        assert float(tinit.latent_space.gmm_log_vars.min()) >= float(np.log(0.01)) - 1e-5      # min_var = 0.01
     with pytest.raises(ValueError):
         train_deepof_model((train_td, val_td), adj, None, device="tpu", use_turtle_teacher=False)
     out = train_deepof_model((train_td, val_td), adj, None, encoder_type="recurrent", batch_size=64, latent_dim=6, epochs=2,

@@ -180,3 +180,52 @@ def test_build_turtle_teacher_end_to_end():
     m = _stub_model(5, 8)
     initialize_gmm_from_teacher(m, z, tau, verbose=False)
     assert torch.isfinite(m.latent_space.gmm_log_vars).all()
+
+
+def test_pca_view_folds_a_short_tail_into_the_previous_batch():
+    X = torch.from_numpy(VW["a"]).reshape(1100, -1)[:1029]           # batches of 512: 512 + 512 + 5 rows, 8 components
+    p, f = pca_view(X, 8, 512)
+    assert p.n_samples_seen_ == 1029 and f.shape == (1029, 8)
+    ref = IncrementalPCAB200(8).partial_fit(X[:512]).partial_fit(X[512:])
+    assert float((p.components_ - ref.components_).abs().max()) == 0.0
+
+
+def test_teacher_context_matches_reference_set_teacher():
+    """VadeLoss.set_teacher (losses.py:460-491) called unbound on a bare namespace in the build container; elsewhere the
+    closed form is checked."""
+    from deepof_b200.teacher import teacher_context
+    tau = torch.from_numpy(T["three_views/tau_star"])
+    tc = teacher_context(tau, True, 1.0, 3.0)
+    pi = tau.mean(0).clamp_min(1e-8)
+    w = pi.pow(-1.0)
+    w = (w / w.mean()).clamp_max(3.0)
+    assert torch.allclose(tc["class_weight"], w) and torch.allclose(tc["teacher_marginal"], pi)
+    assert teacher_context(tau, False)["class_weight"] is None
+    from oracle import refshim
+    if refshim.available():
+        _, L, _, _ = refshim.load()
+        ns = SimpleNamespace(distill_use_class_reweight=True, distill_class_reweight_beta=1.0, distill_class_reweight_cap=3.0)
+        L.VadeLoss.set_teacher(ns, tau, 4.0, None)
+        assert torch.equal(ns.class_weight, tc["class_weight"]) and torch.equal(ns.teacher_marginal, tc["teacher_marginal"])
+
+
+def test_lambda_schedule_is_the_reference_weight_manager():
+    """The distillation weight of the VaDE main phase (training.py:1672-1676): KLSchedule with warm-up 0, flat for
+    lambda_decay_start epochs, linear cool-down — against Dynamic_weight_manager in the build container."""
+    from deepof_b200.training import KLSchedule
+    nb = 7
+    mine = KLSchedule(nb, "tf_sigmoid", 0, 4.0, 10, 0.2, at_max_epochs=10)
+    vals = []
+    for _ in range(nb * 22):
+        vals.append(mine.get_weight())
+        mine.step()
+    assert vals[0] < 1e-30 and vals[1] == 4.0 and vals[nb * 10] == 4.0 and abs(vals[-1] - 0.2) < 1e-12
+    assert all(b <= a + 1e-12 for a, b in zip(vals[1:], vals[2:]))            # flat, then monotone decay
+    from oracle import refshim
+    if refshim.available():
+        _, L, _, _ = refshim.load()
+        ref = L.Dynamic_weight_manager(nb, mode="tf_sigmoid", warmup_epochs=0, at_max_epochs=10, max_weight=4.0,
+                                       cooldown_epochs=10, end_weight=0.2)
+        for v in vals:
+            assert abs(ref.get_weight() - v) < 1e-12
+            ref.step()
