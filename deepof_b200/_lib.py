@@ -17,10 +17,13 @@ LOG_KEYS = ("total_loss", "reconstruct_loss", "kl_div", "cat_clust_loss", "kmean
 
 
 class DofConfig(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("T", "N", "E", "F", "Fe", "D", "K", "model")]
+    _fields_ = [(n, C.c_int) for n in ("T", "N", "E", "F", "Fe", "D", "K", "model", "encoder")]
 
 
 MODEL_VADE, MODEL_VQVAE, MODEL_CONTRASTIVE = 0, 1, 2
+ENCODER_RECURRENT, ENCODER_TRANSFORMER = 0, 1
+ENCODER_KINDS = {"recurrent": ENCODER_RECURRENT, "transformer": ENCODER_TRANSFORMER}
+ABI_VERSION = 3
 
 
 class DofVadeLossCfg(C.Structure):
@@ -99,6 +102,8 @@ _SIGS = {
                                      C.POINTER(DofVadeLossCfg), _P, _P]),
     "dof_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(DofAdamCfg), _P]),
     "dof_encode": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
+    "dof_dropout_mask_bytes": (C.c_size_t, [C.POINTER(DofConfig), C.c_int, C.c_int, C.c_int]),
+    "dof_set_dropout": (C.c_int, [_P, C.c_ulonglong, _P, C.c_size_t]),
     "dof_vqvae_forward_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "dof_vqvae_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P, _P]),
     "dof_contrastive_views": (C.c_int, [C.POINTER(DofViewsCfg), _P, C.c_int, _P, _P, _P]),
@@ -145,6 +150,7 @@ _SIGS = {
                                          C.c_int, C.c_int, _P]),
     "dof_test_gru_wgrad": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dof_test_tfm_attention": (C.c_int, [_P, _P, _P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dof_test_encoder_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "dof_test_gru_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "dof_test_layernorm": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, C.c_longlong, C.c_int,
                                      C.c_int, _P]),

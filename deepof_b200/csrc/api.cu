@@ -35,11 +35,22 @@ struct Entry {
 
 struct GruP { int64_t w_ih[2], w_hh[2], b_ih[2], b_hh[2]; };
 struct BlockP { int64_t conv; GruP g1, g2; int64_t n1w, n1b, n2w, n2b, pw, pb; };
+#define TFM_MAXL 4
+struct TfmLayerP { int64_t Wqkv, Wo, n1w, n1b, W1, b1, W2, b2, n2w, n2b; };
+struct TfmCoreP { int64_t We, be; TfmLayerP l[TFM_MAXL]; };
+struct TfmBnP { int64_t w, b, mean, var, tracked; };
 struct Layout {
     std::vector<Entry> e;
     int64_t total = 0;
     int64_t lap, elap, inc;
     BlockP blk[2];
+    // transformer family (encoder == DOF_ENCODER_TRANSFORMER)
+    int dk = 0, heads = 4, dff = 128, layers = 2, dec_heads = 8, dec_dff = 128, dec_layers = 2;
+    TfmCoreP tcore[2];
+    int64_t h_w0, h_b0, h_w3, h_b3, h_w6, h_b6;
+    TfmBnP bn2, bn5;
+    int64_t dex_w[3], dex_b[3], dout_w, dout_b;
+    TfmLayerP tdl[TFM_MAXL];
     int64_t node_kernel, edge_kernel, node_weights, edge_weights, node_bias, edge_bias;
     int64_t final_w, final_b;
     GruP dg1, dg2;
@@ -75,9 +86,108 @@ static void add_gru(Layout& L, const std::string& p, int group, int I, int H, Gr
 
 static int dint(const dof_config& c) { return c.D < 64 ? c.D : 64; }
 
-static Layout build_layout(const dof_config& c) {
+static int tfm_key_dim(const dof_config& c) {                 // models_new.py:1014-1019
+    int kd = c.N * c.F < 64 ? c.N * c.F : 64;
+    kd = (kd / 4) * 4;
+    return kd < 4 ? 4 : kd;
+}
+
+static void add_latent_tail(Layout& L, const dof_config& c) {
+    const int D = c.D, K = c.K;
+    if (c.model == DOF_MODEL_VQVAE) {                        // VQVAEPT: vq_layer.codebook [D,K] (models_new.py:1349-1351)
+        L.codebook = add_entry(L, "vq_layer.codebook", 3, D, K);
+        return;
+    }
+    L.gmm_mu = add_entry(L, "latent_space.gmm_means", 3, K, D);
+    L.gmm_lv = add_entry(L, "latent_space.gmm_log_vars", 3, K, D);
+    L.prior = add_entry(L, "latent_space.prior", 0, K);
+    L.pretrain = add_entry(L, "latent_space.pretrain", 0, -1);
+    L.Wm = add_entry(L, "latent_space.encoder_mean.weight", 1, D, D);
+    L.bm = add_entry(L, "latent_space.encoder_mean.bias", 1, D);
+    L.Wv = add_entry(L, "latent_space.encoder_log_var.weight", 1, D, D);
+    L.bv = add_entry(L, "latent_space.encoder_log_var.bias", 1, D);
+    L.lens_w = add_entry(L, "latent_space.lens.weight", 0, D, D);   // never receives a gradient
+    L.lens_b = add_entry(L, "latent_space.lens.bias", 0, D);
+}
+
+// state_dict order of the reference models built with encoder_type="transformer" (TFMEncoderPT after its first
+// forward — the CensNet parameters are created lazily —, TFMDecoderPT, then the latent space / codebook)
+static Layout build_layout_tfm(const dof_config& c) {
     Layout L;
-    const int N = c.N, E = c.E, D = c.D, K = c.K, di = dint(c);
+    const int N = c.N, E = c.E, D = c.D, dk = tfm_key_dim(c);
+    L.dk = dk;
+    L.lap = add_entry(L, "encoder.laplacian", 0, N, N);
+    L.elap = add_entry(L, "encoder.edge_laplacian", 0, E, E);
+    L.inc = add_entry(L, "encoder.incidence", 0, N, E);
+    const char* cn[2] = {"encoder.node_tf.", "encoder.edge_tf."};
+    for (int b = 0; b < 2; b++) {
+        std::string p = cn[b];
+        TfmCoreP& P = L.tcore[b];
+        P.We = add_entry(L, p + "embed.weight", 1, dk, b == 0 ? c.F : c.Fe);
+        P.be = add_entry(L, p + "embed.bias", 1, dk);
+        for (int l = 0; l < L.layers; l++) {
+            std::string q = p + "layers." + std::to_string(l) + ".";
+            TfmLayerP& Q = P.l[l];
+            Q.Wqkv = add_entry(L, q + "mha.q_proj.weight", 1, dk, dk);
+            add_entry(L, q + "mha.k_proj.weight", 1, dk, dk);
+            add_entry(L, q + "mha.v_proj.weight", 1, dk, dk);
+            Q.Wo = add_entry(L, q + "mha.out_proj.weight", 1, dk, dk);
+            Q.n1w = add_entry(L, q + "norm1.weight", 1, dk); Q.n1b = add_entry(L, q + "norm1.bias", 1, dk);
+            Q.W1 = add_entry(L, q + "ffn.0.weight", 1, L.dff, dk); Q.b1 = add_entry(L, q + "ffn.0.bias", 1, L.dff);
+            Q.W2 = add_entry(L, q + "ffn.2.weight", 1, dk, L.dff); Q.b2 = add_entry(L, q + "ffn.2.bias", 1, dk);
+            Q.n2w = add_entry(L, q + "norm2.weight", 1, dk); Q.n2b = add_entry(L, q + "norm2.bias", 1, dk);
+        }
+    }
+    std::string g = "encoder.spatial_gnn_block.";
+    L.node_kernel = add_entry(L, g + "node_kernel", 1, dk, D);
+    L.edge_kernel = add_entry(L, g + "edge_kernel", 1, dk, D);
+    L.node_weights = add_entry(L, g + "node_weights", 1, dk, 1);
+    L.edge_weights = add_entry(L, g + "edge_weights", 1, dk, 1);
+    L.node_bias = add_entry(L, g + "node_bias", 1, D);
+    L.edge_bias = add_entry(L, g + "edge_bias", 1, D);
+    auto add_bn = [&](const std::string& p, int C, TfmBnP& bn) {
+        bn.w = add_entry(L, p + "weight", 1, C); bn.b = add_entry(L, p + "bias", 1, C);
+        bn.mean = add_entry(L, p + "running_mean", 0, C); bn.var = add_entry(L, p + "running_var", 0, C);
+        bn.tracked = add_entry(L, p + "num_batches_tracked", 0, -1);
+    };
+    L.h_w0 = add_entry(L, "encoder.head.0.weight", 1, 2 * D, (N + E) * D);
+    L.h_b0 = add_entry(L, "encoder.head.0.bias", 1, 2 * D);
+    add_bn("encoder.head.2.", 2 * D, L.bn2);
+    L.h_w3 = add_entry(L, "encoder.head.3.weight", 1, D, 2 * D);
+    L.h_b3 = add_entry(L, "encoder.head.3.bias", 1, D);
+    add_bn("encoder.head.5.", D, L.bn5);
+    L.h_w6 = add_entry(L, "encoder.head.6.weight", 1, D, D);
+    L.h_b6 = add_entry(L, "encoder.head.6.bias", 1, D);
+    if (c.model == DOF_MODEL_CONTRASTIVE) return L;
+    const int dm = 4 * D, Dx = N * c.F;
+    const int ein[3] = {D, D, 2 * D}, eout[3] = {D, 2 * D, 4 * D};
+    for (int i = 0; i < 3; i++) {
+        L.dex_w[i] = add_entry(L, "decoder.latent_expand." + std::to_string(2 * i) + ".weight", 2, eout[i], ein[i]);
+        L.dex_b[i] = add_entry(L, "decoder.latent_expand." + std::to_string(2 * i) + ".bias", 2, eout[i]);
+    }
+    for (int l = 0; l < L.dec_layers; l++) {
+        std::string q = "decoder.layers." + std::to_string(l) + ".";
+        TfmLayerP& Q = L.tdl[l];
+        Q.Wqkv = add_entry(L, q + "q_proj.weight", 2, dm, dm); add_entry(L, q + "k_proj.weight", 2, dm, dm);
+        add_entry(L, q + "v_proj.weight", 2, dm, dm);
+        Q.Wo = add_entry(L, q + "out_proj.weight", 2, dm, dm);
+        Q.n1w = add_entry(L, q + "norm1.weight", 2, dm); Q.n1b = add_entry(L, q + "norm1.bias", 2, dm);
+        Q.n2w = add_entry(L, q + "norm2.weight", 2, dm); Q.n2b = add_entry(L, q + "norm2.bias", 2, dm);
+        Q.W1 = add_entry(L, q + "ffn.0.weight", 2, L.dec_dff, dm); Q.b1 = add_entry(L, q + "ffn.0.bias", 2, L.dec_dff);
+        Q.W2 = add_entry(L, q + "ffn.3.weight", 2, dm, L.dec_dff); Q.b2 = add_entry(L, q + "ffn.3.bias", 2, dm);
+    }
+    L.dout_w = add_entry(L, "decoder.output_proj.weight", 2, Dx, dm);
+    L.dout_b = add_entry(L, "decoder.output_proj.bias", 2, Dx);
+    L.loc_w = add_entry(L, "decoder.prob_decoder.loc_projection.weight", 2, Dx, Dx);
+    L.loc_b = add_entry(L, "decoder.prob_decoder.loc_projection.bias", 2, Dx);
+    add_latent_tail(L, c);
+    return L;
+}
+
+static Layout build_layout(const dof_config& c) {
+    if (c.encoder == DOF_ENCODER_TRANSFORMER) return build_layout_tfm(c);
+    Layout L;
+    const int N = c.N, E = c.E, D = c.D, di = dint(c);
     L.lap = add_entry(L, "encoder.laplacian", 0, N, N);
     L.elap = add_entry(L, "encoder.edge_laplacian", 0, E, E);
     L.inc = add_entry(L, "encoder.incidence", 0, N, E);
@@ -118,20 +228,7 @@ static Layout build_layout(const dof_config& c) {
     L.dn3b = add_entry(L, "decoder.norm3.bias", 2, 2 * D);
     L.loc_w = add_entry(L, "decoder.prob_decoder.loc_projection.weight", 2, N * c.F, 2 * D);
     L.loc_b = add_entry(L, "decoder.prob_decoder.loc_projection.bias", 2, N * c.F);
-    if (c.model == DOF_MODEL_VQVAE) {                        // VQVAEPT: vq_layer.codebook [D,K] (models_new.py:1349-1351)
-        L.codebook = add_entry(L, "vq_layer.codebook", 3, D, K);
-        return L;
-    }
-    L.gmm_mu = add_entry(L, "latent_space.gmm_means", 3, K, D);
-    L.gmm_lv = add_entry(L, "latent_space.gmm_log_vars", 3, K, D);
-    L.prior = add_entry(L, "latent_space.prior", 0, K);
-    L.pretrain = add_entry(L, "latent_space.pretrain", 0, -1);
-    L.Wm = add_entry(L, "latent_space.encoder_mean.weight", 1, D, D);
-    L.bm = add_entry(L, "latent_space.encoder_mean.bias", 1, D);
-    L.Wv = add_entry(L, "latent_space.encoder_log_var.weight", 1, D, D);
-    L.bv = add_entry(L, "latent_space.encoder_log_var.bias", 1, D);
-    L.lens_w = add_entry(L, "latent_space.lens.weight", 0, D, D);   // never receives a gradient
-    L.lens_b = add_entry(L, "latent_space.lens.bias", 0, D);
+    add_latent_tail(L, c);
     return L;
 }
 
@@ -143,7 +240,14 @@ static int check_cfg(const dof_config* c) {
     if (c->model < DOF_MODEL_VADE || c->model > DOF_MODEL_CONTRASTIVE) DOF_FAIL(DOF_ERR_ARG, "unknown model kind %d", c->model);
     if (c->model == DOF_MODEL_VADE && c->K > LOSS_MAXK) DOF_FAIL(DOF_ERR_UNSUPPORTED, "n_components %d > %d", c->K, LOSS_MAXK);
     if (c->model == DOF_MODEL_VQVAE && (size_t)c->D * c->K * 4 > 96 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "codebook %d x %d does not fit in shared memory", c->D, c->K);
-    if (c->D > 32) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 32 not supported by the GRU kernels yet", c->D);
+    if (c->encoder != DOF_ENCODER_RECURRENT && c->encoder != DOF_ENCODER_TRANSFORMER) DOF_FAIL(DOF_ERR_ARG, "unknown encoder kind %d", c->encoder);
+    if (c->encoder == DOF_ENCODER_RECURRENT && c->D > 32) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 32 not supported by the GRU kernels yet", c->D);
+    if (c->encoder == DOF_ENCODER_TRANSFORMER) {
+        if (c->D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 64 not supported by the transformer path", c->D);
+        if (c->T > TFM_MAXT) DOF_FAIL(DOF_ERR_UNSUPPORTED, "window length %d > %d", c->T, TFM_MAXT);
+        if (c->F > 4 || c->Fe > 4) DOF_FAIL(DOF_ERR_UNSUPPORTED, "more than 4 features per node / edge");
+        if ((4 * c->D) % 8) DOF_FAIL(DOF_ERR_ARG, "decoder model_dim %d is not a multiple of 8 heads", 4 * c->D);
+    }
     return DOF_OK;
 }
 
@@ -170,9 +274,41 @@ struct BlockWS {
     float *dP, *dY2, *dHn, *dG2[2], *dY1, *dH1, *dG1[2], *dCv;
 };
 
+// transformer family: per (node | edge) core activations.  R = S * T rows; the last layer keeps its post-attention
+// tensors for the final step of every sequence only ([S, *]).
+struct TfmLayerWS { float *QKV, *ATT, *U1, *mu1, *rs1, *Y1, *FF, *U2, *mu2, *rs2, *Y2; };
+struct TfmCoreWS {
+    int S, G, Fin;
+    int* gidx;
+    float* Xs; unsigned char* kpad; float* Y0;
+    TfmLayerWS l[TFM_MAXL];
+    float *dA, *dB, *dC, *dFF, *dQKV;        // [R, *] gradient scratch
+    float *sA, *sB, *sC, *sFF, *dOut;        // [S, *] gradient scratch of the last layer, dOut = d(core output)
+};
+struct TfmDecLayerWS { float *Xn1, *QKV, *ATT, *Hmid, *Xn2, *PRE, *FH, *Hout, *muA, *rsA, *muB, *rsB; };
+struct TfmDecWS {
+    float *P[3], *G[3];                      // latent expansion: pre-activations and GELU outputs [B, *]
+    float *H0, *tmpA, *tmpB, *tmpF, *Y;      // [R, dm] x3, [R, dff], [R, Dx]
+    TfmDecLayerWS l[TFM_MAXL];
+    float *dH, *dQKV, *dY, *dP[3], *dG[3];
+};
+
 struct dof_handle {
     dof_config cfg;
     Layout L;
+    // transformer family
+    TfmCoreWS tc[2];
+    TfmDecWS td;
+    float *pe_enc, *pe_dec;                  // positional encodings [T, dk], [T, 4D]
+    float *hIn, *hRms, *h1r, *h1, *h2r, *h2, *h3, *dh3, *dh2, *dh2r, *dh1, *dh1r, *dhIn;   // encoder head
+    float *bnm[3], *bns[3], *bnstat[2]; unsigned char* bclamp;
+    int enc_groups = 1;                      // statistics groups of the last encoder pass (contrastive: 2)
+    int next_groups = 1;                     // statistics groups of the NEXT training-mode encoder pass
+    int dec_pass = 0;                        // which decoder pass of the step comes next (VQ-VAE decodes twice)
+    int bn_pending = 0;                      // batch statistics of the last training step wait for dof_clip_adam
+    unsigned long long drop_seed = 0;
+    const unsigned char* drop_masks = nullptr;
+    size_t drop_mask_bytes = 0;
     int device, sm_count, max_batch, training;
     int di, H1, H2, C1;
     BlockWS blk[2];
@@ -213,13 +349,91 @@ static int fork_join_blocks(dof_handle* h, cudaStream_t st, F fn) {
     return r0 != DOF_OK ? r0 : r1;
 }
 
+static void plan_workspace_tfm_encoder(dof_handle* h, Bump& bp) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int B = h->max_batch, T = c.T, D = c.D, dk = L.dk, dff = L.dff;
+    const bool tr = h->training != 0;
+    h->pe_enc = bp.get<float>((size_t)T * dk);
+    for (int b = 0; b < 2; b++) {
+        TfmCoreWS& w = h->tc[b];
+        w.G = b == 0 ? c.N : c.E;
+        w.Fin = b == 0 ? c.F : c.Fe;
+        w.S = B * w.G;
+        const size_t S = (size_t)w.S, R = S * T;
+        w.gidx = bp.get<int>((size_t)w.G * T * w.Fin);
+        w.Xs = bp.get<float>(R * w.Fin);
+        w.kpad = bp.get<unsigned char>(R);
+        w.Y0 = bp.get<float>(R * dk);
+        for (int l = 0; l < L.layers; l++) {
+            TfmLayerWS& q = w.l[l];
+            const size_t Rl = (l == L.layers - 1) ? S : R;       // rows of the post-attention tensors
+            q.QKV = bp.get<float>(R * 3 * dk);
+            q.ATT = bp.get<float>(Rl * dk);
+            q.U1 = bp.get<float>(Rl * dk); q.mu1 = bp.get<float>(Rl); q.rs1 = bp.get<float>(Rl);
+            q.Y1 = bp.get<float>(Rl * dk);
+            q.FF = bp.get<float>(Rl * dff);
+            q.U2 = bp.get<float>(Rl * dk); q.mu2 = bp.get<float>(Rl); q.rs2 = bp.get<float>(Rl);
+            q.Y2 = bp.get<float>(Rl * dk);
+        }
+        if (tr) {
+            w.dA = bp.get<float>(R * dk); w.dB = bp.get<float>(R * dk); w.dC = bp.get<float>(R * dk);
+            w.dFF = bp.get<float>(R * dff); w.dQKV = bp.get<float>(R * 3 * dk);
+            w.sA = bp.get<float>(S * dk); w.sB = bp.get<float>(S * dk); w.sC = bp.get<float>(S * dk);
+            w.sFF = bp.get<float>(S * dff); w.dOut = bp.get<float>(S * dk);
+        }
+    }
+    const size_t Bz = (size_t)B, KD = (size_t)(c.N + c.E) * D;
+    h->hIn = bp.get<float>(Bz * KD); h->hRms = bp.get<float>(Bz);
+    h->h1r = bp.get<float>(Bz * 2 * D); h->h1 = bp.get<float>(Bz * 2 * D);
+    h->h2r = bp.get<float>(Bz * D); h->h2 = bp.get<float>(Bz * D); h->h3 = bp.get<float>(Bz * D);
+    const int cw[3] = {2 * D, D, D};
+    for (int i = 0; i < 3; i++) { h->bnm[i] = bp.get<float>((size_t)2 * cw[i]); h->bns[i] = bp.get<float>((size_t)2 * cw[i]); }
+    h->bnstat[0] = bp.get<float>((size_t)2 * 2 * 2 * D); h->bnstat[1] = bp.get<float>((size_t)2 * 2 * D);
+    h->bclamp = bp.get<unsigned char>((size_t)2 * D);
+    if (tr) {
+        h->dh3 = bp.get<float>(Bz * D); h->dh2 = bp.get<float>(Bz * D); h->dh2r = bp.get<float>(Bz * D);
+        h->dh1 = bp.get<float>(Bz * 2 * D); h->dh1r = bp.get<float>(Bz * 2 * D); h->dhIn = bp.get<float>(Bz * KD);
+    }
+}
+
+static void plan_workspace_tfm_decoder(dof_handle* h, Bump& bp) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int B = h->max_batch, T = c.T, D = c.D, dm = 4 * D, dff = L.dec_dff, Dx = c.N * c.F;
+    const bool tr = h->training != 0;
+    const size_t Bz = (size_t)B, R = Bz * T;
+    TfmDecWS& w = h->td;
+    const int eout[3] = {D, 2 * D, 4 * D};
+    h->pe_dec = bp.get<float>((size_t)T * dm);
+    for (int i = 0; i < 3; i++) { w.P[i] = bp.get<float>(Bz * eout[i]); w.G[i] = bp.get<float>(Bz * eout[i]); }
+    w.H0 = bp.get<float>(R * dm); w.tmpA = bp.get<float>(R * dm); w.tmpB = bp.get<float>(R * dm);
+    w.tmpF = bp.get<float>(R * dff); w.Y = bp.get<float>(R * Dx);
+    for (int l = 0; l < L.dec_layers; l++) {
+        TfmDecLayerWS& q = w.l[l];
+        const bool keep = tr || l == 0;                          // eval: every layer reuses layer 0's buffers
+        if (!keep) { q = w.l[0]; continue; }
+        q.Xn1 = bp.get<float>(R * dm); q.QKV = bp.get<float>(R * 3 * dm); q.ATT = bp.get<float>(R * dm);
+        q.Hmid = bp.get<float>(R * dm); q.Xn2 = bp.get<float>(R * dm); q.PRE = bp.get<float>(R * dff);
+        q.FH = bp.get<float>(R * dff); q.Hout = bp.get<float>(R * dm);
+        q.muA = bp.get<float>(R); q.rsA = bp.get<float>(R); q.muB = bp.get<float>(R); q.rsB = bp.get<float>(R);
+    }
+    if (tr) {
+        w.dH = bp.get<float>(R * dm); w.dQKV = bp.get<float>(R * 3 * dm); w.dY = bp.get<float>(R * Dx);
+        for (int i = 0; i < 3; i++) { w.dP[i] = bp.get<float>(Bz * eout[i]); w.dG[i] = bp.get<float>(Bz * eout[i]); }
+    }
+}
+
 static void plan_workspace(dof_handle* h, Bump& bp) {
     const dof_config& c = h->cfg;
     const int B = h->max_batch, T = c.T, D = c.D, K = c.K, N = c.N, E = c.E;
     const int H1 = h->H1, H2 = h->H2, C1 = h->C1;
     const bool tr = h->training != 0;
+    const bool tfm = c.encoder == DOF_ENCODER_TRANSFORMER;
+    const int CC = tfm ? h->L.dk : 2 * D;                        // CensNet input channels
     h->group = bp.get<unsigned char>((size_t)h->L.total);
-    for (int b = 0; b < 2; b++) {
+    if (tfm) plan_workspace_tfm_encoder(h, bp);
+    for (int b = 0; b < 2 && !tfm; b++) {
         BlockWS& w = h->blk[b];
         w.G = b == 0 ? N : E;
         w.Fin = b == 0 ? c.F : c.Fe;
@@ -254,12 +468,12 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
     }
     const size_t Bz = (size_t)B, BT = Bz * T;
     const int model = c.model;
-    h->Pn = bp.get<float>(Bz * N * 2 * D); h->Pe = bp.get<float>(Bz * E * 2 * D);
+    h->Pn = bp.get<float>(Bz * N * CC); h->Pe = bp.get<float>(Bz * E * CC);
     h->On = bp.get<float>(Bz * N * D); h->Oe = bp.get<float>(Bz * E * D);
     h->enc = bp.get<float>(Bz * D);
     if (tr) {
         h->dOn = bp.get<float>(Bz * N * D); h->dOe = bp.get<float>(Bz * E * D);
-        h->dPn = bp.get<float>(Bz * N * 2 * D); h->dPe = bp.get<float>(Bz * E * 2 * D);
+        h->dPn = bp.get<float>(Bz * N * CC); h->dPe = bp.get<float>(Bz * E * CC);
         h->denc = bp.get<float>(Bz * D);
     }
     if (model == DOF_MODEL_CONTRASTIVE) {
@@ -275,6 +489,8 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
         h->vstats = bp.get<double>((size_t)VQ_ST_GRAM + (size_t)D * D + K);
     }
     h->lenD = bp.get<int>(Bz);
+    if (tfm) plan_workspace_tfm_decoder(h, bp);
+    else {
     for (int d = 0; d < 2; d++) h->GiD1[d] = bp.get<float>(Bz * 3 * D);
     h->HD1 = bp.get<float>(BT * 2 * D);
     for (int d = 0; d < 2; d++) h->GtD1[d] = tr ? bp.get<float>((size_t)round_up(B, 128) * T * 4 * D) : nullptr;
@@ -288,11 +504,13 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
     h->Cd = bp.get<float>(BT * 2 * D);
     h->muD3 = bp.get<float>(BT); h->rsD3 = bp.get<float>(BT);
     h->YD3 = bp.get<float>(BT * 2 * D);
+    }
     h->loc = bp.get<float>(BT * N * c.F);
     if (tr) {
         if (model == DOF_MODEL_VADE) { h->dzm = bp.get<float>(Bz * D); h->dpre = bp.get<float>(Bz * D); }
         h->dz_dec = bp.get<float>(Bz * D);
         h->dloc = bp.get<float>(BT * N * c.F);
+        if (!tfm) {
         h->dYD3 = bp.get<float>(BT * 2 * D); h->dCd = bp.get<float>(BT * 2 * D);
         h->dYD2 = bp.get<float>(BT * 4 * D); h->dHD2 = bp.get<float>(BT * 4 * D);
         for (int d = 0; d < 2; d++) h->dGD2[d] = bp.get<float>(BT * 8 * D);
@@ -300,6 +518,7 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
         for (int d = 0; d < 2; d++) h->dGD1[d] = bp.get<float>(BT * 4 * D);
         for (int d = 0; d < 2; d++) h->dGs[d] = bp.get<float>(Bz * 4 * D);
         h->Wt = bp.get<float>((size_t)4 * D * 2 * D * 5);
+        }
         if (model != DOF_MODEL_VADE) return;
         StatsLayout SL = stats_layout(D, K);
         CoefLayout CL = coef_layout(D, K);
@@ -434,10 +653,17 @@ int dof_create(const dof_config* cfg, int device, int max_batch, int training, v
     for (const Entry& e : h->L.e)
         for (int64_t i = 0; i < e.numel; i++) grp[(size_t)(e.off + i)] = (unsigned char)e.group;
     cudaError_t ce = cudaMemcpy(h->group, grp.data(), grp.size(), cudaMemcpyHostToDevice);
+    const bool tfm = cfg->encoder == DOF_ENCODER_TRANSFORMER;
     for (int b = 0; b < 2 && ce == cudaSuccess; b++) {
         std::vector<int> gi;
-        build_gidx(cfg->T, h->blk[b].G, h->blk[b].Fin, gi);
-        ce = cudaMemcpy(h->blk[b].gidx, gi.data(), gi.size() * sizeof(int), cudaMemcpyHostToDevice);
+        const int G = tfm ? h->tc[b].G : h->blk[b].G, Fin = tfm ? h->tc[b].Fin : h->blk[b].Fin;
+        build_gidx(cfg->T, G, Fin, gi);
+        ce = cudaMemcpy(tfm ? h->tc[b].gidx : h->blk[b].gidx, gi.data(), gi.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (tfm && ce == cudaSuccess) {
+        tfm_pe_kernel<<<cdiv(cfg->T * h->L.dk, 256), 256>>>(h->pe_enc, cfg->T, h->L.dk);
+        if (cfg->model != DOF_MODEL_CONTRASTIVE) tfm_pe_kernel<<<cdiv(cfg->T * 4 * cfg->D, 256), 256>>>(h->pe_dec, cfg->T, 4 * cfg->D);
+        ce = cudaDeviceSynchronize();
     }
     if (ce != cudaSuccess) { delete h; DOF_FAIL(DOF_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(ce)); }
     const char* ss = getenv("DOF_SINGLE_STREAM");
@@ -584,8 +810,8 @@ static CensArgs cens_args(dof_handle* h, const float* state, int B) {
     return a;
 }
 
-static int encoder_forward(dof_handle* h, const float* state, const float* x, const float* a, int B, bool train,
-                           cudaStream_t st) {
+static int rec_encoder_forward(dof_handle* h, const float* state, const float* x, const float* a, int B, bool train,
+                               cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int N = c.N, E = c.E, D = c.D;
@@ -644,8 +870,8 @@ static int vade_latent_forward(dof_handle* h, const float* state, int B, const f
     return DOF_OK;
 }
 
-static int decoder_forward(dof_handle* h, const float* state, const float* zin, const float* x, int B, bool train,
-                           cudaStream_t st) {
+static int rec_decoder_forward(dof_handle* h, const float* state, const float* zin, const float* x, int B, bool train,
+                               cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T;
@@ -669,6 +895,25 @@ static int decoder_forward(dof_handle* h, const float* state, const float* zin, 
 static void register_debug(dof_handle* h, int B) {
     const dof_config& c = h->cfg;
     h->dbg.clear();
+    const bool tfm = c.encoder == DOF_ENCODER_TRANSFORMER;
+    if (tfm) {
+        const int ll = h->L.layers - 1, dk = h->L.dk;
+        h->dbg["node_out"] = {h->tc[0].l[ll].Y2, (int64_t)B * c.N * dk};
+        h->dbg["edge_out"] = {h->tc[1].l[ll].Y2, (int64_t)B * c.E * dk};
+        h->dbg["node_y0"] = {h->tc[0].Y0, (int64_t)B * c.N * c.T * dk};
+        h->dbg["node_l0"] = {h->tc[0].l[0].Y2, (int64_t)B * c.N * (ll == 0 ? 1 : c.T) * dk};
+        h->dbg["head_in"] = {h->hIn, (int64_t)B * (c.N + c.E) * c.D};
+        h->dbg["head_h1"] = {h->h1, (int64_t)B * 2 * c.D};
+        h->dbg["head_h3"] = {h->h3, (int64_t)B * c.D};
+        h->dbg["bn2_stat"] = {h->bnstat[0], (int64_t)4 * c.D};
+        h->dbg["bn5_stat"] = {h->bnstat[1], (int64_t)2 * c.D};
+        if (h->training) {
+            h->dbg["dnode_out"] = {h->tc[0].dOut, (int64_t)B * c.N * dk};
+            h->dbg["dedge_out"] = {h->tc[1].dOut, (int64_t)B * c.E * dk};
+            h->dbg["dhead_in"] = {h->dhIn, (int64_t)B * (c.N + c.E) * c.D};
+            h->dbg["dnode_y0"] = {h->tc[0].dA, (int64_t)B * c.N * c.T * dk};
+        }
+    } else {
     h->dbg["node_out"] = {h->blk[0].P, (int64_t)B * c.N * 2 * c.D};
     h->dbg["edge_out"] = {h->blk[1].P, (int64_t)B * c.E * 2 * c.D};
     h->dbg["node_conv"] = {h->blk[0].Cv, (int64_t)B * c.N * c.T * h->C1};
@@ -676,6 +921,7 @@ static void register_debug(dof_handle* h, int B) {
     h->dbg["node_hn"] = {h->blk[0].Hn, (int64_t)B * c.N * 2 * h->H2};
     h->dbg["len_node"] = {h->blk[0].len, (int64_t)B * c.N};
     h->dbg["len_edge"] = {h->blk[1].len, (int64_t)B * c.E};
+    }
     h->dbg["cens_node"] = {h->On, (int64_t)B * c.N * c.D};
     h->dbg["cens_edge"] = {h->Oe, (int64_t)B * c.E * c.D};
     h->dbg["enc"] = {h->enc, (int64_t)B * c.D};
@@ -692,8 +938,10 @@ static void register_debug(dof_handle* h, int B) {
         h->dbg["dzm"] = {h->dzm, (int64_t)B * c.D};
         h->dbg["dpre"] = {h->dpre, (int64_t)B * c.D};
         h->dbg["denc"] = {h->denc, (int64_t)B * c.D};
-        h->dbg["dnode_out"] = {h->blk[0].dP, (int64_t)B * c.N * 2 * c.D};
-        h->dbg["dedge_out"] = {h->blk[1].dP, (int64_t)B * c.E * 2 * c.D};
+        if (!tfm) {
+            h->dbg["dnode_out"] = {h->blk[0].dP, (int64_t)B * c.N * 2 * c.D};
+            h->dbg["dedge_out"] = {h->blk[1].dP, (int64_t)B * c.E * 2 * c.D};
+        }
     }
 }
 
@@ -759,7 +1007,7 @@ static int gru_layer_backward(const float* state, const GruP& g, int S, int T, i
     return launch_gru_bwd(b, st);
 }
 
-static int decoder_backward(dof_handle* h, const float* state, float* grad, const float* zin, int B, cudaStream_t st) {
+static int rec_decoder_backward(dof_handle* h, const float* state, float* grad, const float* zin, int B, cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T, sm = h->sm_count;
@@ -865,7 +1113,7 @@ static int vade_latent_backward(dof_handle* h, const float* state, float* grad, 
 }
 
 // backward of RecurrentEncoderPT from h->denc (gradient wrt the encoder output)
-static int encoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
+static int rec_encoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int N = c.N, E = c.E, D = c.D, sm = h->sm_count;
@@ -899,6 +1147,27 @@ static int encoder_backward(dof_handle* h, const float* state, float* grad, int 
     DOF_LAUNCH_CHECK();
     DOF_TRY(fork_join_blocks(h, st, [&](int b, cudaStream_t s) { return enc_block_backward(h, b, state, grad, B, s); }));
     return DOF_OK;
+}
+
+#include "tfm_step.cuh"
+
+// ---- encoder / decoder family dispatch (dof_config.encoder) ----------------------------------------------------------
+static inline bool is_tfm(const dof_handle* h) { return h->cfg.encoder == DOF_ENCODER_TRANSFORMER; }
+static int encoder_forward(dof_handle* h, const float* state, const float* x, const float* a, int B, bool train, cudaStream_t st) {
+    if (is_tfm(h)) return tfm_encoder_forward(h, state, x, a, B, train, train ? h->next_groups : 1, st);
+    return rec_encoder_forward(h, state, x, a, B, train, st);
+}
+static int encoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
+    if (is_tfm(h)) return tfm_encoder_backward(h, state, grad, B, st);
+    return rec_encoder_backward(h, state, grad, B, st);
+}
+static int decoder_forward(dof_handle* h, const float* state, const float* zin, const float* x, int B, bool train, cudaStream_t st) {
+    if (is_tfm(h)) return tfm_decoder_forward(h, state, zin, B, train, h->dec_pass, st);
+    return rec_decoder_forward(h, state, zin, x, B, train, st);
+}
+static int decoder_backward(dof_handle* h, const float* state, float* grad, const float* zin, int B, cudaStream_t st) {
+    if (is_tfm(h)) return tfm_decoder_backward(h, state, grad, zin, B, h->dec_pass, st);
+    return rec_decoder_backward(h, state, grad, zin, B, st);
 }
 
 static int check_batch(dof_handle* h, int B) {
@@ -1093,6 +1362,7 @@ int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, 
     int rgrid = (int)((nrec + 255) / 256 < (long long)h->sm_count * 8 ? (nrec + 255) / 256 : (long long)h->sm_count * 8);
     for (int pass = 0; pass < 2; pass++) {
         const float* zin = pass == 0 ? h->quant : h->enc;
+        h->dec_pass = pass;
         DOF_TRY(decoder_forward(h, state, zin, x, B, true, st));
         { ProfScope ps("recon", st, 0.0, 12.0 * nrec);
         recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->vstats + (pass == 0 ? VQ_ST_REC_Q : VQ_ST_REC_E)); }
@@ -1104,6 +1374,7 @@ int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, 
             DOF_LAUNCH_CHECK();
         }
     }
+    h->dec_pass = 0;
     DOF_CUDA(cudaMemcpyAsync(h->denc, h->dz_dec, (size_t)B * D * 4, cudaMemcpyDeviceToDevice, st));
     const bool dist_on = distill && distill->lambda > 0.f;               // training.py:346
     if (dist_on) DOF_TRY(distill_head_step(h, distill, B, h->vstats + VQ_ST_DISTILL, false, st));
@@ -1600,7 +1871,9 @@ int dof_contrastive_loss_grad_distill(dof_handle* h, const float* state, float* 
     if (c.D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 64", c.D);
     cudaStream_t st = (cudaStream_t)stream;
     DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)h->L.total * 4, st));
+    h->next_groups = 2;                 // the reference encodes the two views in two passes: separate batch statistics
     DOF_TRY(encoder_forward(h, state, x2, a2, 2 * B, true, st));
+    h->next_groups = 1;
     if (z_out) DOF_CUDA(cudaMemcpyAsync(z_out, h->enc, (size_t)2 * B * c.D * 4, cudaMemcpyDeviceToDevice, st));
     NtxArgs n;
     n.enc = h->enc; n.zn = h->zn; n.nrm = h->nrm; n.lse = h->lse; n.denc = h->denc; n.stats = h->nstats; n.logs = logs;
@@ -1644,6 +1917,20 @@ int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m,
     { ProfScope ps("clip_adam", (cudaStream_t)stream, 0.0, 28.0 * a.n);
     clip_adam_kernel<<<cdiv(a.n, 256), 256, 0, (cudaStream_t)stream>>>(a); }
     DOF_LAUNCH_CHECK();
+    if (is_tfm(h) && h->bn_pending) DOF_TRY(tfm_bn_apply(h, state, (cudaStream_t)stream));
+    return DOF_OK;
+}
+
+size_t dof_dropout_mask_bytes(const dof_config* cfg, int Bw, int B, int dec_passes) {
+    if (check_cfg(cfg) != DOF_OK || cfg->encoder != DOF_ENCODER_TRANSFORMER || Bw < 1 || B < 0 || dec_passes < 0 || dec_passes > 2) return 0;
+    const Layout L = build_layout(*cfg);
+    return drop_plan(*cfg, L, Bw, B, dec_passes).total;
+}
+
+int dof_set_dropout(dof_handle* h, unsigned long long seed, const unsigned char* masks, size_t mask_bytes) {
+    if (!h) DOF_FAIL(DOF_ERR_ARG, "null handle");
+    if (!is_tfm(h)) DOF_FAIL(DOF_ERR_ARG, "dropout only exists in the transformer family");
+    h->drop_seed = seed; h->drop_masks = masks; h->drop_mask_bytes = masks ? mask_bytes : 0;
     return DOF_OK;
 }
 
@@ -1885,6 +2172,27 @@ int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* 
     return launch_gru_bwd_tc(b, (cudaStream_t)stream);
 }
 
+// test hook: the encoder alone in TRAIN mode, backward from a given d(loss)/d(encoder output) (any model kind, any
+// encoder family): grad is overwritten, enc_out [B, D] receives the train-mode encoder output.
+int dof_test_encoder_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B, int groups,
+                          const float* denc, float* enc_out, void* stream) {
+    DOF_TRY(check_batch(h, B));
+    if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
+    if (!state || !grad || !x || !a || !denc) DOF_FAIL(DOF_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)h->L.total * 4, st));
+    h->next_groups = groups > 0 ? groups : 1;
+    int rc = encoder_forward(h, state, x, a, B, true, st);
+    h->next_groups = 1;
+    DOF_TRY(rc);
+    if (enc_out) DOF_CUDA(cudaMemcpyAsync(enc_out, h->enc, (size_t)B * h->cfg.D * 4, cudaMemcpyDeviceToDevice, st));
+    DOF_CUDA(cudaMemcpyAsync(h->denc, denc, (size_t)B * h->cfg.D * 4, cudaMemcpyDeviceToDevice, st));
+    DOF_TRY(encoder_backward(h, state, grad, B, st));
+    h->lastB = B;
+    register_debug(h, B);
+    return DOF_OK;
+}
+
 // test hook: multi-head attention with key-padding / causal masks and dropout on the weights, forward or backward
 // (building block of the transformer training step, tfm.cuh).  backward = (dout != NULL): writes dqkv.
 int dof_test_tfm_attention(const float* qkv, const unsigned char* kpad, const unsigned char* keep, float rate, int causal, int S,
@@ -1894,8 +2202,9 @@ int dof_test_tfm_attention(const float* qkv, const unsigned char* kpad, const un
     const bool bwd = dout != nullptr;
     if (bwd ? !dqkv : !out) DOF_FAIL(DOF_ERR_ARG, "null output");
     TfmAttnArgs a;
-    a.qkv = qkv; a.kpad = kpad; a.keep = keep; a.out = out; a.dout = dout; a.dqkv = dqkv; a.S = S; a.T = T; a.dm = dm; a.heads = heads;
-    a.causal = causal; a.rate = keep ? rate : 0.f;
+    a.qkv = qkv; a.kpad = kpad; a.out = out; a.dout = dout; a.dqkv = dqkv; a.S = S; a.T = T; a.dm = dm; a.heads = heads;
+    a.causal = causal; a.q_from = 0;
+    a.drop = drop_none(); a.drop.keep = keep; a.drop.rate = keep ? rate : 0.f;
     const size_t smem = ((size_t)T * (3 * dm + 1) * (bwd ? 2 : 1) + (bwd ? (size_t)T * (dm + 1) : 0)) * 4;
     if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "sequence of %d x %d does not fit shared memory", T, 3 * dm);
     cudaStream_t st = (cudaStream_t)stream;

@@ -12,6 +12,7 @@
 // (embedding_per_video); the training backward of this encoder is not built yet.
 #pragma once
 #include "common.cuh"
+#include "tfm_train.cuh"
 
 #define TFM_MAXT 64
 #define TFM_THREADS 512
@@ -362,12 +363,12 @@ __global__ void __launch_bounds__(128) tfm_causal_attn_kernel(const float* __res
 struct TfmAttnArgs {
     const float* qkv;            // [S, T, 3 dm]  rows q | k | v
     const unsigned char* kpad;   // [S, T] 1 = padded key, or null
-    const unsigned char* keep;   // [S, H, T, T] dropout keep mask, or null (no dropout)
-    float* out;                  // forward: [S, T, dm]
-    const float* dout;           // backward: [S, T, dm]
+    DropSite drop;               // dropout on the attention weights, element index ((s * H + h) * T + tq) * T + tk
+    float* out;                  // forward: [S, T, dm]   (q_from > 0: [S, T - q_from, dm], rows tq - q_from)
+    const float* dout;           // backward: same shape as out
     float* dqkv;                 // backward: [S, T, 3 dm]
     int S, T, dm, heads, causal;
-    float rate;
+    int q_from;                  // only queries tq >= q_from are computed (the last layer of the encoder core needs tq = T - 1)
 };
 
 template <bool BWD>
@@ -381,16 +382,18 @@ __global__ void __launch_bounds__(128) tfm_attn_train_kernel(const TfmAttnArgs a
     const float* src = a.qkv + (size_t)s * T * 3 * dm;
     for (int i = threadIdx.x; i < T * 3 * dm; i += blockDim.x) sq[(i / (3 * dm)) * ldq + i % (3 * dm)] = src[i];
     if (BWD) {
-        const float* dsrc = a.dout + (size_t)s * T * dm;
-        for (int i = threadIdx.x; i < T * dm; i += blockDim.x) sdo[(i / dm) * (dm + 1) + i % dm] = dsrc[i];
+        const int TQl = T - a.q_from;
+        const float* dsrc = a.dout + (size_t)s * TQl * dm;
+        for (int i = threadIdx.x; i < TQl * dm; i += blockDim.x) sdo[(a.q_from + i / dm) * (dm + 1) + i % dm] = dsrc[i];
         for (int i = threadIdx.x; i < T * ldq; i += blockDim.x) sdq[i] = 0.f;
     }
     __syncthreads();
-    const float qs = rsqrtf((float)hd), inv_keep = 1.0f / (1.0f - a.rate);
+    const float qs = rsqrtf((float)hd);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int q0 = a.q_from, TQ = T - q0;
     // one warp per (head, query step); lanes own keys
-    for (int o = warp; o < heads * T; o += nw) {
-        const int hh = o / T, tq = o % T;
+    for (int o = warp; o < heads * TQ; o += nw) {
+        const int hh = o / TQ, tq = q0 + o % TQ;
         const float* q = sq + (size_t)tq * ldq + hh * hd;
         float p[TFM_MAXT / 32], pd[TFM_MAXT / 32];
         float mx = -INFINITY;
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(128) tfm_attn_train_kernel(const TfmAttnArgs a
             const int tk = lane + 32 * c;
             p[c] /= sum;
             float kp = 1.f;
-            if (a.keep && tk < T) kp = a.keep[(((size_t)s * heads + hh) * T + tq) * T + tk] ? inv_keep : 0.f;
+            if (tk < T) kp = drop_mul1(a.drop, (((unsigned long long)s * heads + hh) * T + tq) * T + tk);
             pd[c] = p[c] * kp;                 // dropped-out, rescaled weights
         }
         if (!BWD) {
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(128) tfm_attn_train_kernel(const TfmAttnArgs a
                         const float pj = __shfl_sync(0xffffffffu, pd[c], j);
                         if (d < hd) acc += pj * sq[(size_t)(j + 32 * c) * ldq + 2 * dm + hh * hd + d];
                     }
-                if (d < hd) a.out[((size_t)s * T + tq) * dm + hh * hd + d] = acc;
+                if (d < hd) a.out[((size_t)s * TQ + (tq - q0)) * dm + hh * hd + d] = acc;
             }
         } else {
             const float* dor = sdo + (size_t)tq * (dm + 1) + hh * hd;
@@ -451,9 +454,7 @@ __global__ void __launch_bounds__(128) tfm_attn_train_kernel(const TfmAttnArgs a
                     for (int d = 0; d < hd; d++) v += dor[d] * vv[d];
                     // dV[tk] += Pd[tq, tk] * dOut[tq]   (different warps share tk: shared-memory atomics)
                     for (int d = 0; d < hd; d++) atomicAdd(sdq + (size_t)tk * ldq + 2 * dm + hh * hd + d, pd[c] * dor[d]);
-                    float kp = 1.f;
-                    if (a.keep) kp = a.keep[(((size_t)s * heads + hh) * T + tq) * T + tk] ? inv_keep : 0.f;
-                    v *= kp;
+                    v *= drop_mul1(a.drop, (((unsigned long long)s * heads + hh) * T + tq) * T + tk);
                 }
                 dp[c] = v;
                 dot_pp += v * p[c];

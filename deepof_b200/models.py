@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import DofViewsCfg, check, ptr
-from .vade import VaDEB200, _stream
+from .vade import TFM_BUFFERS, VaDEB200, _stream
 
 VQ_LOG_KEYS = ("total_loss", "enc_rec_loss", "reconstruct_loss", "vq_loss", "kmeans_loss",
                "number_of_populated_clusters", "distill_loss")       # step_vqvae_distill, training.py:380-388
@@ -95,7 +95,8 @@ class Distillation:
 class VQVAEB200(VaDEB200):
     """Stand-in for ``VQVAEPT(encoder_type="recurrent", use_gnn=True)``."""
     _MODEL = _lib.MODEL_VQVAE
-    _BUFFERS = ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence")
+    _BUFFERS = ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence") + TFM_BUFFERS
+    _DEC_PASSES = 2          # decoder(quantized) and decoder(encoder output), models_new.py:1603-1612
 
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
                  encoder_type: str = "recurrent", use_gnn: bool = True, kmeans_loss: float = 0.0,
@@ -139,10 +140,11 @@ class VQVAEB200(VaDEB200):
         enc, quant, soft, idx, _, _ = self.forward_eval(x, a, want_loc=False)
         return enc, soft
 
-    def loss_grad(self, x, a, distill: Optional["Distillation"] = None):
+    def loss_grad(self, x, a, distill: Optional["Distillation"] = None, dropout_masks=None):
         if not self.training_capable:
             raise _lib.DofError("model was created with training=False")
         x, a = self._prep(x, a)
+        self._set_dropout(x.shape[0], dropout_masks)
         dc = distill.cfg(x.shape[0]) if distill is not None and distill.lambda_distill > 0.0 else None
         check(self.L.dof_vqvae_loss_grad_distill(self.handle, ptr(self.state), ptr(self.grad), ptr(x), ptr(a), x.shape[0],
                                                  self.beta, self.kmeans_weight, C.byref(dc) if dc is not None else None,
@@ -220,7 +222,8 @@ class ContrastiveB200(VaDEB200):
     """Stand-in for ``ContrastivePT(encoder_type="recurrent", use_gnn=True, similarity_function="cosine",
     loss_function="nce")``.  ``input_shape`` holds the FULL window length; the encoder sees ``T // 2``."""
     _MODEL = _lib.MODEL_CONTRASTIVE
-    _BUFFERS = ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence")
+    _BUFFERS = ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence") + TFM_BUFFERS
+    _DEC_PASSES = 0
 
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int = 8,
                  encoder_type: str = "recurrent", use_gnn: bool = True, temperature: float = 0.1,
@@ -339,13 +342,14 @@ class ContrastiveB200(VaDEB200):
         self._keep = (start, th, t0, ln, nz)      # keep the device arrays alive until the stream has consumed them
         return x2, a2
 
-    def loss_grad(self, x_full, prm: AugParams, distill: Optional["Distillation"] = None):
+    def loss_grad(self, x_full, prm: AugParams, distill: Optional["Distillation"] = None, dropout_masks=None):
         """views + encoder on both + NT-Xent (+ distillation head on the main view) + backward into ``self.grad``;
         returns the device log vector."""
         if not self.training_capable:
             raise _lib.DofError("model was created with training=False")
         x2, a2 = self.views(x_full, prm)
         B = x2.shape[0] // 2
+        self._set_dropout(0, dropout_masks, encoder_windows=2 * B)
         kind = {"nce": 0, "dcl": 1, "hard_dcl": 2, "fc": 3}[self.loss_function]
         sim = 0 if self.similarity_function in ("cosine", "dot") else 1
         dc = distill.cfg(B) if distill is not None and distill.lambda_distill > 0.0 else None

@@ -121,19 +121,25 @@ class _Named:
         return self._rep
 
 
+TFM_BUFFERS = ("encoder.head.2.running_mean", "encoder.head.2.running_var", "encoder.head.2.num_batches_tracked",
+               "encoder.head.5.running_mean", "encoder.head.5.running_var", "encoder.head.5.num_batches_tracked")
+
+
 class VaDEB200:
-    """B200-native stand-in for ``VaDEPT(encoder_type="recurrent", use_gnn=True)``."""
+    """B200-native stand-in for ``VaDEPT(encoder_type="recurrent" | "transformer", use_gnn=True)``."""
     _MODEL = _lib.MODEL_VADE
     _BUFFERS = ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence", "latent_space.prior",
-                "latent_space.pretrain")
+                "latent_space.pretrain") + TFM_BUFFERS
+    _DEC_PASSES = 1          # decoder passes per training step (dropout mask layout of the transformer family)
 
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
                  encoder_type: str = "recurrent", use_gnn: bool = True, kmeans_loss: float = 1.0,
                  interaction_regularization: float = 0.0, device: Optional[int] = None, max_batch: int = 4096,
                  training: bool = True, seed: Optional[int] = None):
-        if encoder_type != "recurrent" or not use_gnn:
-            raise NotImplementedError("deepof_b200 implements the recurrent GNN VaDE path only "
+        if encoder_type not in _lib.ENCODER_KINDS or not use_gnn:
+            raise NotImplementedError("deepof_b200 implements the recurrent and the transformer GNN encoders "
                                       f"(got encoder_type={encoder_type!r}, use_gnn={use_gnn})")
+        self.encoder_type = encoder_type
         if not torch.cuda.is_available():
             raise _lib.DofError("deepof_b200 needs a CUDA device (no CPU fallback)")
         self.L = lib()
@@ -144,7 +150,10 @@ class VaDEB200:
         self.adjacency_matrix = np.asarray(adjacency_matrix, dtype=np.float64)
         lap, elap, inc = graph_operators(self.adjacency_matrix)
         assert inc.shape[1] == E, f"adjacency has {inc.shape[1]} edges, edge_feature_shape says {E}"
-        self.cfg = DofConfig(T, N, E, F, Fe, int(latent_dim), int(n_components), self._MODEL)
+        self.cfg = DofConfig(T, N, E, F, Fe, int(latent_dim), int(n_components), self._MODEL,
+                             _lib.ENCODER_KINDS[encoder_type])
+        self._drop_step = 0
+        self._drop_seed = int(seed) if seed is not None else 0
         self.window_size = T
         self.latent_dim, self.n_components = int(latent_dim), int(n_components)
         self.kmeans_weight = float(kmeans_loss)
@@ -231,15 +240,29 @@ class VaDEB200:
             leaf = name.rsplit(".", 1)[-1]
             if name in ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence"):
                 continue
-            if name == "latent_space.prior":
+            if name.endswith("num_batches_tracked") or name.endswith("running_mean"):
+                val = torch.zeros(shape)
+            elif name.endswith("running_var"):
+                val = torch.ones(shape)
+            elif name == "latent_space.prior":
                 val = torch.full(shape, 1.0 / K)
             elif name == "latent_space.pretrain":
                 val = torch.zeros(())
             elif ".gru" in name:      # nn.GRU: U(+-1/sqrt(hidden))
                 hidden = shape[0] // 3
                 val = uni(shape, 1.0 / math.sqrt(hidden))
-            elif ".norm" in name:
-                val = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+            elif ".norm" in name or (name.startswith("encoder.head.") and len(shape) == 1 and name.split(".")[2] in ("2", "5")):
+                val = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)        # LayerNorm / BatchNorm affine
+            elif self.encoder_type == "transformer" and ("_tf." in name or name.startswith("encoder.head.") or name.startswith("decoder.")):
+                # xavier_uniform_ weights, zero biases (models_new.py:868-871, 1085-1089, 1225-1230); embed / prob_decoder keep
+                # nn.Linear's default init
+                if ".embed." in name or "prob_decoder" in name:
+                    fan_in = self._views[name[:-4] + "weight"].shape[1] if leaf == "bias" else shape[1]
+                    val = uni(shape, 1.0 / math.sqrt(fan_in))
+                elif leaf == "weight":
+                    val = uni(shape, math.sqrt(6.0 / (shape[0] + shape[1])))
+                else:
+                    val = torch.zeros(shape)
             elif "conv1d.weight" in name:   # kaiming_uniform(a=sqrt5) == U(+-1/sqrt(fan_in))
                 val = uni(shape, 1.0 / math.sqrt(shape[1] * shape[2]))
             elif "spatial_gnn_block" in name:
@@ -263,7 +286,8 @@ class VaDEB200:
                 v.copy_(val.to(self.device))
 
     def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
-        return OrderedDict((k, v.detach().clone()) for k, v in self._views.items())
+        return OrderedDict((k, v.detach().clone().to(torch.int64) if k.endswith("num_batches_tracked") else v.detach().clone())
+                           for k, v in self._views.items())
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
         missing = [k for k in self._views if k not in sd]
@@ -350,8 +374,30 @@ class VaDEB200:
         return loc, emb, q, torch.zeros((), device=self.device)
 
     # ---- training
+    def dropout_mask_bytes(self, B: int, encoder_windows: Optional[int] = None) -> int:
+        return int(self.L.dof_dropout_mask_bytes(C.byref(self.cfg), int(encoder_windows or B), int(B if self._DEC_PASSES else 0),
+                                                 self._DEC_PASSES))
+
+    def _set_dropout(self, B: int, masks=None, encoder_windows: Optional[int] = None):
+        """Transformer family: explicit keep masks (uint8 on the device, reference draw order — see ``dof_set_dropout``)
+        for parity runs, else a fresh Philox stream per step (seed advances with every call)."""
+        if self.encoder_type != "transformer":
+            return
+        if masks is not None:
+            m = torch.as_tensor(masks).to(self.device, torch.uint8).contiguous()
+            need = self.dropout_mask_bytes(B, encoder_windows)
+            if m.numel() != need:
+                raise ValueError(f"dropout masks: {m.numel()} bytes, the step needs {need}")
+            self._drop_keep = m
+            check(self.L.dof_set_dropout(self.handle, 0, ptr(m), m.numel()))
+        else:
+            self._drop_step += 1
+            self._drop_keep = None
+            seed = (self._drop_seed * 0x9E3779B97F4A7C15 + self._drop_step) & 0xFFFFFFFFFFFFFFFF
+            check(self.L.dof_set_dropout(self.handle, seed, None, 0))
+
     def loss_grad(self, x, a, loss_cfg: VadeLossCfg, eps=None, mc_eps=None, tau_batch=None, class_weight=None,
-                  teacher_marginal=None):
+                  teacher_marginal=None, dropout_masks=None):
         """forward + VadeLoss + backward into ``self.grad``; returns the device log vector."""
         if not self.training_capable:
             raise _lib.DofError("model was created with training=False")
@@ -368,6 +414,7 @@ class VaDEB200:
         if teacher_marginal is not None:   # reference losses.py:672-678
             floor = torch.maximum(floor, 0.9 * f32(teacher_marginal))
         c = loss_cfg.to_c()
+        self._set_dropout(B, dropout_masks)
         check(self.L.dof_vade_loss_grad(self.handle, ptr(self.state), ptr(self.grad), ptr(x), ptr(a), B, ptr(eps),
                                         ptr(mc_eps), ptr(tau_batch), ptr(class_weight), ptr(floor), C.byref(c),
                                         ptr(self.logs), _stream()))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DOF_ABI_VERSION 2
+#define DOF_ABI_VERSION 3
 
 /* Model geometry.  Mirrors the constructor arguments of VaDEPT / RecurrentEncoderPT /
  * RecurrentDecoderPT (deepof/clustering/models_new.py:37-105, 281-324, 1794-1839). */
@@ -43,7 +43,19 @@ typedef struct {
     int D;   /* latent_dim                                          */
     int K;   /* n_components (GMM clusters / VQ codebook size)      */
     int model; /* DOF_MODEL_*: which reference model the state buffer lays out */
+    int encoder; /* DOF_ENCODER_*: encoder_type of the reference model builders (models_new.py:1432-1508) */
 } dof_config;
+
+/* Encoder / decoder family (the reference's `encoder_type`):
+ *  RECURRENT    RecurrentEncoderPT + RecurrentDecoderPT (models_new.py:37-373): Conv1d + 2 BiGRU + LayerNorm per node / edge
+ *  TRANSFORMER  TFMEncoderPT + TFMDecoderPT (models_new.py:985-1327): per node / edge TransformerCorePT (key_dim =
+ *               min(64, N*F) rounded down to a multiple of 4 heads, dff 128, 2 post-LN layers, dropout 0.1), CensNet, RMS
+ *               normalisation, head MLP with BatchNorm (eps 1e-3, momentum 0.01), train-mode batch standardisation;
+ *               decoder: latent expansion MLP (GELU) to 4*D, 2 pre-LN causal self-attention layers (8 heads, dff 128,
+ *               dropout 0.2).  The state layout follows the reference state_dict of that model; the integer
+ *               num_batches_tracked buffers are carried as one float each. */
+#define DOF_ENCODER_RECURRENT 0
+#define DOF_ENCODER_TRANSFORMER 1
 
 /* Model kinds (all with encoder_type="recurrent", use_gnn=True):
  *  VADE         VaDEPT        deepof/clustering/models_new.py:1794-1976  encoder + decoder + latent_space
@@ -197,6 +209,25 @@ int dof_loader_moments(const dof_loader_cfg* cfg, const float* frames, long long
 /* ---- encoder only: model.encoder(x, a) -> enc [B,D] (RecurrentEncoderPT.forward, models_new.py:140-181);
  * this is ContrastivePT.forward (models_new.py:2063-2069) and VQVAEPT.encode (:1637-1640).  Any model kind. */
 int dof_encode(dof_handle* h, const float* state, const float* x, const float* a, int B, float* enc, void* stream);
+
+/* ---- dropout and BatchNorm state of the transformer family (DOF_ENCODER_TRANSFORMER) ------------------------------
+ * Every dropout decision of a training step (nn.Dropout / scaled_dot_product_attention(dropout_p), models_new.py:880-884,
+ * 914-917, 972, 1311-1325) comes from a counter-based Philox4x32-10 stream keyed by `seed` (one counter block per
+ * dropout site and element, so forward and backward regenerate the same decisions and nothing is stored), or — for
+ * parity runs against the reference — from explicit keep masks (`masks` != NULL, DEVICE bytes, 1 = kept), concatenated in
+ * the order the reference draws them for ONE encoder pass over the Bw windows handed to the step and `dec_passes`
+ * decoder passes over B windows (VaDE 1, VQ-VAE 2, contrastive 0 with Bw = 2B: rows 0..B-1 the main view):
+ *   for core in (node, edge), S = Bw * (N or E):  embed [S,T,key_dim];  per layer: attention weights [S,4,T,T],
+ *       dropout1 [S,T,key_dim], dropout2 [S,T,key_dim]
+ *   per decoder pass, per layer: attention weights [B,8,T,T], out-projection dropout [B,T,4D], FFN hidden [B,T,128],
+ *       FFN output [B,T,4D].
+ * dof_dropout_mask_bytes returns the total for Bw encoder windows and dec_passes passes over B decoder windows.  The
+ * setting persists until the next call; the default is Philox with seed 0 — callers advance the seed every step.
+ * BatchNorm running statistics (BatchNorm1dKerasFP32, models_new.py:508-516) are updated by dof_clip_adam from the
+ * batch statistics of the preceding *_loss_grad call (rank-local, as under the reference's DDP with
+ * broadcast_buffers=False). */
+size_t dof_dropout_mask_bytes(const dof_config* cfg, int Bw, int B, int dec_passes);
+int dof_set_dropout(dof_handle* h, unsigned long long seed, const unsigned char* masks, size_t mask_bytes);
 
 /* ---- VQ-VAE (DOF_MODEL_VQVAE) ------------------------------------------------------------------------
  * Eval forward of VQVAEPT(x, a, return_all_outputs=True) (models_new.py:1575-1635): enc [B,D] encoder output,
@@ -370,6 +401,10 @@ int dof_test_gru_wgrad(const float* dg_f, const float* dg_b, const float* x, int
 int dof_test_tfm_attention(const float* qkv, const unsigned char* kpad, const unsigned char* keep, float rate,
                            int causal, int S, int T, int dm, int heads, float* out, const float* dout, float* dqkv,
                            void* stream);
+/* the encoder alone in train mode + its backward from denc [B,D] = d(loss)/d(encoder output); `groups` = row ranges with
+ * separate batch statistics (transformer head; 1 otherwise).  grad is overwritten, enc_out [B,D] may be NULL. */
+int dof_test_encoder_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B, int groups,
+                          const float* denc, float* enc_out, void* stream);
 int dof_test_gru_bwd(const float* whh_f, const float* whh_b, const int* len, const float* hout,
                      const float* gt_f, const float* gt_b, const float* dout, const float* dhn,
                      float* dg_f, float* dg_b, int S, int T, int H, void* stream);

@@ -30,7 +30,7 @@ def test_header_symbols_exported(built):
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in the header but not exported"
     assert declared == set(built.EXPORTS), declared ^ set(built.EXPORTS)
-    assert built.lib().dof_abi_version() == 2
+    assert built.lib().dof_abi_version() == 3
 
 
 @pytest.mark.parametrize("case", golden_cases())

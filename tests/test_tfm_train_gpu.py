@@ -1,0 +1,263 @@
+"""GPU: the transformer-family TRAINING step through the C-ABI vs
+(1) the goldens produced by the UNMODIFIED reference — ``tfmtrain_*.npz`` (TFMEncoderPT in train(): output, parameter
+    gradients, BatchNorm running statistics) and ``tfmvade_*.npz`` (step_vade on VaDEPT(encoder_type="transformer"): 13
+    logs and every parameter gradient) — with the reference's dropout masks replayed as explicit keep masks;
+(2) the CPU oracle on fresh seeds at sizes that take the tensor-core GEMM paths (cfg3 / cfg5 geometry);
+(3) properties of the in-kernel Philox dropout (rate, determinism per seed, forward / backward agreement).
+Tolerances: logs |d| <= 1e-4 max(1, |v|), flat gradient rel-L2 <= 2e-4, embeddings rel-L2 <= 1e-4."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_cases_of, load_golden_of, sub, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _unpack_masks(g):
+    masks = {}
+    for k in g:
+        if k.startswith("mask/"):
+            shp = tuple(int(v) for v in g["mshape/" + k[5:]])
+            n = int(np.prod(shp))
+            masks[k[5:]] = torch.from_numpy(np.unpackbits(g[k])[:n].astype(np.float32)).reshape(shp)
+    return masks
+
+
+def _flat_masks(masks, B, N, E, T, dk, D, dec_passes=1, with_decoder=True):
+    """Concatenate keep masks in the order dof_set_dropout documents (= the order the reference draws them)."""
+    from oracle import tfm_oracle as TO
+    parts = []
+    for core, S in (("node", B * N), ("edge", B * E)):
+        for nm, shp in TO.dropout_mask_shapes(S, T, dk, 4, 2):
+            m = masks[f"{core}.{nm}"]
+            assert tuple(m.shape) == tuple(shp)
+            parts.append(m.reshape(-1))
+    if with_decoder:
+        for p in range(dec_passes):
+            for nm, shp in TO.decoder_mask_shapes(B, T, 4 * D, 8, 128, 2):
+                key = nm if p == 0 else nm.replace("dec.", f"dec{p}.")
+                m = masks[key]
+                assert tuple(m.shape) == tuple(shp)
+                parts.append(m.reshape(-1))
+    return torch.cat(parts).to(torch.uint8)
+
+
+def _random_masks(B, N, E, T, dk, D, seed, dec_passes=1):
+    from oracle import tfm_oracle as TO
+    g = torch.Generator().manual_seed(seed)
+    masks = {}
+    for core, S in (("node", B * N), ("edge", B * E)):
+        for nm, shp in TO.dropout_mask_shapes(S, T, dk, 4, 2):
+            masks[f"{core}.{nm}"] = (torch.rand(shp, generator=g) >= 0.1).float()
+    for p in range(dec_passes):
+        for nm, shp in TO.decoder_mask_shapes(B, T, 4 * D, 8, 128, 2):
+            masks[nm if p == 0 else nm.replace("dec.", f"dec{p}.")] = (torch.rand(shp, generator=g) >= 0.2).float()
+    return masks
+
+
+def _grad_cmp(gd, ref, names):
+    num = sum(float((gd[k].cpu().double() - ref[k].double()).pow(2).sum()) for k in names)
+    den = sum(float(ref[k].double().pow(2).sum()) for k in names)
+    worst = max(names, key=lambda k: float((gd[k].cpu().double() - ref[k].double()).norm() / ref[k].double().norm().clamp_min(1e-12)))
+    return (num / max(den, 1e-300)) ** 0.5, worst
+
+
+@pytest.mark.parametrize("case", golden_cases_of("tfmtrain"))
+def test_encoder_train_vs_reference_golden(case):
+    from deepof_b200 import VaDEB200, _lib
+    g = load_golden_of("tfmtrain", case)
+    T, N, E, D, B, dk, heads, dff, layers = (int(v) for v in g["meta"])
+    m = VaDEB200((T, N, 3), (T, E, 1), g["adjacency"], D, 4, encoder_type="transformer", max_batch=B, training=True, seed=1)
+    names = [k for k, *_ in m.layout]
+    enc_names = [k for k in names if k.startswith("encoder.")]
+    assert [k[len("encoder."):] for k in enc_names] == [k[2:] for k in g if k.startswith("p/")]       # reference state_dict order
+    m.load_state_dict({"encoder." + k: v for k, v in sub(g, "p/").items()}, strict=False)
+    masks = _flat_masks(_unpack_masks(g), B, N, E, T, dk, D, with_decoder=False).cuda()
+    x, a = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["a"]).cuda()
+    probe = torch.from_numpy(g["probe"]).cuda().contiguous()
+    out = torch.empty(B, D, device="cuda")
+    _lib.check(m.L.dof_set_dropout(m.handle, 0, _lib.ptr(masks), masks.numel()))
+    _lib.check(m.L.dof_test_encoder_grad(m.handle, _lib.ptr(m.state), _lib.ptr(m.grad), _lib.ptr(x), _lib.ptr(a), B, 1, _lib.ptr(probe),
+                                         _lib.ptr(out), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    e_out = rel_l2(out.cpu(), g["train/out"])
+    gd = m.grad_dict()
+    gnames = [k[2:] for k in g if k.startswith("g/")]
+    ref = {k: torch.from_numpy(g["g/" + k]) for k in gnames}
+    err, worst = _grad_cmp({k: gd["encoder." + k] for k in gnames}, ref, gnames)
+    print(case, "out", e_out, "grad", err, "worst", worst)
+    assert e_out < 1e-4, e_out
+    assert err < 2e-4, (err, worst)
+    scale = max(float(v.norm()) for v in ref.values())
+    for k in gnames:       # per tensor, except gradients that are analytically zero (biases in front of a batch standardisation)
+        if float(ref[k].norm()) > 1e-5 * scale:
+            assert rel_l2(gd["encoder." + k].cpu(), ref[k]) < 2e-3, k
+        else:
+            assert float(gd["encoder." + k].abs().max()) < 1e-5 * scale, k
+    # running statistics move in dof_clip_adam (lr 0: parameters stay)
+    before = m.state.clone()
+    m.adam_step(0.0, 0.0)
+    sd = m.state_dict()
+    for i in (2, 5):
+        for s in ("running_mean", "running_var"):
+            assert rel_l2(sd[f"encoder.head.{i}.{s}"].cpu(), g[f"p1/head.{i}.{s}"]) < 1e-5, (i, s)
+        assert int(sd[f"encoder.head.{i}.num_batches_tracked"]) == int(g[f"p/head.{i}.num_batches_tracked"]) + 1
+    changed = (m.state != before).nonzero().flatten().cpu().numpy()
+    lay = {k: (off, n) for k, off, n, *_ in m.layout}
+    ok = np.zeros(m.state.numel(), bool)
+    for i in (2, 5):
+        for s in ("running_mean", "running_var", "num_batches_tracked"):
+            off, n = lay[f"encoder.head.{i}.{s}"]
+            ok[off:off + n] = True
+    assert ok[changed].all()
+
+
+@pytest.mark.parametrize("case", golden_cases_of("tfmvade"))
+def test_vade_transformer_step_vs_reference_golden(case):
+    from deepof_b200 import VaDEB200, VadeLossCfg
+    from deepof_b200._lib import LOG_KEYS
+    g = load_golden_of("tfmvade", case)
+    T, N, E, D, K, B = (int(v) for v in g["meta"])
+    m = VaDEB200((T, N, 3), (T, E, 1), g["adjacency"], D, K, encoder_type="transformer", max_batch=B, training=True, seed=1)
+    assert [k for k, *_ in m.layout] == [k[2:] for k in g if k.startswith("p/")]
+    m.load_state_dict(sub(g, "p/"))
+    dk = m._views["encoder.node_tf.embed.weight"].shape[0]
+    masks = _flat_masks(_unpack_masks(g), B, N, E, T, dk, D)
+    main = str(g["phase"]) == "main"
+    cfg = (VadeLossCfg.main_defaults if main else VadeLossCfg.pretrain_defaults)(K, kl_weight=float(g["klw"]))
+    m.set_pretrain_mode(not main)
+    m.loss_grad(torch.from_numpy(g["x"]), torch.from_numpy(g["a"]), cfg, eps=torch.from_numpy(g["eps"]),
+                mc_eps=torch.from_numpy(g["mc_eps"]) if main else None, dropout_masks=masks)
+    logs = m.logs_dict()
+    for k in LOG_KEYS:
+        ref = float(g["log/" + k])
+        assert abs(logs[k] - ref) <= 1e-4 * max(1.0, abs(ref)), (k, logs[k], ref)
+    gd = m.grad_dict()
+    gnames = [k[2:] for k in g if k.startswith("g/")]
+    ref = {k: torch.from_numpy(g["g/" + k]) for k in gnames}
+    err, worst = _grad_cmp(gd, ref, gnames)
+    print(case, "grad", err, "worst", worst, rel_l2(gd[worst].cpu(), ref[worst]))
+    assert err < 2e-4, (err, worst)
+    # parameters the reference leaves without a gradient stay at zero
+    for k, off, n, shape, grp in m.layout:
+        if k not in gnames:
+            assert float(m.grad[off:off + n].abs().max()) == 0.0, k
+
+
+@pytest.mark.parametrize("case", golden_cases_of("tfmmodel"))
+def test_transformer_models_eval_through_the_handle(case):
+    """eval-mode embeddings / soft assignments / reconstructions of the reference's transformer checkpoints through the
+    trainable model objects (the composed tcgen05 path), vs the reference outputs."""
+    from deepof_b200 import ContrastiveB200, VaDEB200, VQVAEB200
+    g = load_golden_of("tfmmodel", case)
+    T, N, E, D, K, B = (int(v) for v in g["meta"])
+    kind = str(g["model"])
+    x, a = torch.from_numpy(g["x"]), torch.from_numpy(g["a"])
+    if kind == "vade":
+        m = VaDEB200((T, N, 3), (T, E, 1), g["adjacency"], D, K, encoder_type="transformer", max_batch=16, training=False)
+        m.load_state_dict(sub(g, "p/"))
+        enc, emb, q, loc = m.forward_eval(x, a)
+        assert rel_l2(emb.cpu(), g["eval/emb"]) < 1e-4 and rel_l2(q.cpu(), g["eval/q"]) < 1e-4
+        assert torch.equal(q.cpu().argmax(1), torch.from_numpy(g["eval/q"]).argmax(1))
+        assert rel_l2(loc.cpu(), g["eval/loc"]) < 1e-4
+    elif kind == "vqvae":
+        m = VQVAEB200((T, N, 3), (T, E, 1), g["adjacency"], D, K, encoder_type="transformer", max_batch=16, training=False)
+        m.load_state_dict(sub(g, "p/"))
+        enc, quant, soft, idx, lq, le = m.forward_eval(x, a)
+        assert rel_l2(enc.cpu(), g["eval/emb"]) < 1e-4 and rel_l2(soft.cpu(), g["eval/q"]) < 1e-4
+        assert rel_l2(quant.cpu(), g["eval/quant"]) < 1e-5
+        assert rel_l2(lq.cpu(), g["eval/loc_q"]) < 1e-4 and rel_l2(le.cpu(), g["eval/loc"]) < 1e-4
+    else:
+        m = ContrastiveB200((T, N, 3), (T, E, 1), g["adjacency"], D, encoder_type="transformer", max_batch=16, training=False)
+        m.load_state_dict(sub(g, "p/"))
+        assert rel_l2(m(x, a).cpu(), g["eval/emb"]) < 1e-4
+
+
+@pytest.mark.parametrize("geom", ["cfg3", "cfg5"])
+def test_vade_transformer_step_vs_oracle_tensor_core_sizes(geom):
+    """Fresh seeds, B large enough that every per-row GEMM of the encoder cores and the decoder takes the tcgen05 path
+    (>= 2048 rows; weight gradients >= 4096): logs and the flat gradient against the oracle with shared dropout masks."""
+    from deepof_b200 import VaDEB200, VadeLossCfg
+    from deepof_b200._lib import LOG_KEYS
+    from oracle import tfm_oracle as TO
+    from oracle import vade_oracle as O
+    T, N = 25, 14
+    D, K, B = (16, 8, 192) if geom == "cfg3" else (64, 16, 176)
+    adj = O.default_adjacency(N)
+    E = int(np.count_nonzero(np.triu(adj)))
+    x, a = O.synthetic_windows(B, T, adj, seed=77)
+    m = VaDEB200((T, N, 3), (T, E, 1), adj, D, K, encoder_type="transformer", max_batch=B, training=True, seed=11)
+    with torch.no_grad():
+        m.latent_space.gmm_means.mul_(3.0)
+        for k, v in m._views.items():                       # move the affine parameters off their init so that they matter
+            if k.endswith("bias") and v.dim() == 1:
+                v.add_(0.05 * torch.randn(v.shape, device=v.device, generator=None))
+    m.set_pretrain_mode(False)
+    p = {k: v.cpu() for k, v in m.state_dict().items()}
+    dk = p["encoder.node_tf.embed.weight"].shape[0]
+    masks = _random_masks(B, N, E, T, dk, D, seed=5)
+    gen = torch.Generator().manual_seed(3)
+    eps, mc = torch.randn(B, D, generator=gen), torch.randn(32, B, D, generator=gen)
+    cfg = VadeLossCfg.main_defaults(K, kl_weight=0.6)
+    m.loss_grad(x, a, cfg, eps=eps, mc_eps=mc, dropout_masks=_flat_masks(masks, B, N, E, T, dk, D))
+    logs = m.logs_dict()
+    ologs, ograds, _ = TO.vade_train_step(x, a, p, O.graph_operators(adj), O.LossCfg.main_defaults(K, kl_weight=0.6), masks, eps, mc_eps=mc)
+    for k in LOG_KEYS:
+        assert abs(logs[k] - ologs[k]) <= 1e-4 * max(1.0, abs(ologs[k])), (k, logs[k], ologs[k])
+    names = [k for k, v in ograds.items() if v is not None]
+    err, worst = _grad_cmp(m.grad_dict(), ograds, names)
+    print(geom, "grad", err, "worst", worst)
+    assert err < 2e-4, (err, worst)
+
+
+def test_philox_dropout_properties():
+    """No explicit masks: decisions come from the in-kernel Philox stream.  Same seed -> identical step; different seed ->
+    different step; the step is finite; with the Philox stream the gradient is still the gradient of the loss (finite
+    difference along a random direction of one weight matrix, same seed for both evaluations)."""
+    from deepof_b200 import VaDEB200, VadeLossCfg, _lib
+    from oracle import vade_oracle as O
+    T, N, D, K, B = 25, 14, 8, 4, 24
+    adj = O.default_adjacency(N)
+    E = int(np.count_nonzero(np.triu(adj)))
+    x, a = O.synthetic_windows(B, T, adj, seed=4)
+    m = VaDEB200((T, N, 3), (T, E, 1), adj, D, K, encoder_type="transformer", max_batch=B, training=True, seed=2)
+    m.set_pretrain_mode(True)
+    cfg = VadeLossCfg.pretrain_defaults(K, kl_weight=0.1)
+    gen = torch.Generator().manual_seed(0)
+    eps = torch.randn(B, D, generator=gen)
+
+    def step(seed):
+        _lib.check(m.L.dof_set_dropout(m.handle, seed, None, 0))
+        c = cfg.to_c()
+        floor = torch.full((K,), float(cfg.nonempty_floor), device="cuda")
+        xs, as_ = x.cuda(), a.cuda()
+        e = eps.cuda()
+        _lib.check(m.L.dof_vade_loss_grad(m.handle, _lib.ptr(m.state), _lib.ptr(m.grad), _lib.ptr(xs), _lib.ptr(as_), B, _lib.ptr(e), None, None,
+                                          None, _lib.ptr(floor), C.byref(c), _lib.ptr(m.logs), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        return float(m.logs[0]), m.grad.clone()
+
+    l1, g1 = step(1234)
+    l1b, g1b = step(1234)
+    l2, g2 = step(99)
+    assert abs(l1 - l1b) <= 1e-5 * abs(l1) and rel_l2(g1b.cpu(), g1.cpu()) < 1e-5      # atomics reorder the sums, nothing else
+    assert l1 != l2 and rel_l2(g2.cpu(), g1.cpu()) > 1e-2
+    assert np.isfinite(l1) and bool(torch.isfinite(g1).all())
+    # directional derivative on encoder.node_tf.layers.0.ffn.0.weight
+    lay = {k: (off, n) for k, off, n, *_ in m.layout}
+    off, n = lay["encoder.node_tf.layers.0.ffn.0.weight"]
+    d = torch.randn(n, device="cuda")
+    d /= d.norm()
+    h = 2e-2
+    base = m.state.clone()
+    m.state[off:off + n] = base[off:off + n] + h * d
+    lp, _ = step(1234)
+    m.state[off:off + n] = base[off:off + n] - h * d
+    lm, _ = step(1234)
+    m.state.copy_(base)
+    fd = (lp - lm) / (2 * h)
+    an = float((g1[off:off + n] * d).sum())
+    assert abs(fd - an) <= 0.05 * max(abs(an), 1e-3) + 2e-3, (fd, an)
