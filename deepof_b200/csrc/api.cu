@@ -2201,24 +2201,9 @@ int dof_test_tfm_attention(const float* qkv, const unsigned char* kpad, const un
     if (!(rate >= 0.f && rate < 1.f)) DOF_FAIL(DOF_ERR_ARG, "dropout rate must be in [0, 1)");
     const bool bwd = dout != nullptr;
     if (bwd ? !dqkv : !out) DOF_FAIL(DOF_ERR_ARG, "null output");
-    TfmAttnArgs a;
-    a.qkv = qkv; a.kpad = kpad; a.out = out; a.dout = dout; a.dqkv = dqkv; a.S = S; a.T = T; a.dm = dm; a.heads = heads;
-    a.causal = causal; a.q_from = 0;
-    a.drop = drop_none(); a.drop.keep = keep; a.drop.rate = keep ? rate : 0.f;
-    const size_t smem = ((size_t)T * (3 * dm + 1) * (bwd ? 2 : 1) + (bwd ? (size_t)T * (dm + 1) : 0)) * 4;
-    if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "sequence of %d x %d does not fit shared memory", T, 3 * dm);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (bwd) {
-        DOF_CUDA(cudaFuncSetAttribute(tfm_attn_train_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        ProfScope ps("tfm_attn_bwd", st);
-        tfm_attn_train_kernel<true><<<S, 128, smem, st>>>(a);
-    } else {
-        DOF_CUDA(cudaFuncSetAttribute(tfm_attn_train_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        ProfScope ps("tfm_attn_fwd", st);
-        tfm_attn_train_kernel<false><<<S, 128, smem, st>>>(a);
-    }
-    DOF_LAUNCH_CHECK();
-    return DOF_OK;
+    DropSite drop = drop_none();
+    drop.keep = keep; drop.rate = keep ? rate : 0.f;
+    return tfm_attention(qkv, kpad, drop, causal, S, T, dm, heads, 0, out, dout, dqkv, (cudaStream_t)stream);
 }
 
 int dof_test_gru_wgrad(const float* dg_f, const float* dg_b, const float* x, int ldx, const float* hout, float* out, int M, int T,

@@ -490,3 +490,192 @@ __global__ void __launch_bounds__(128) tfm_attn_train_kernel(const TfmAttnArgs a
         for (int i = threadIdx.x; i < T * 3 * dm; i += blockDim.x) dst[i] = sdq[(i / (3 * dm)) * ldq + i % (3 * dm)];
     }
 }
+
+// ---------------------------------------------------------------------------
+// Attention of the training step, second generation: one CTA per sequence, one WARP per head, one LANE per query step
+// (T <= 32).  q | k | v are staged head-major with the head dimension padded to HDP floats, so a lane walks the keys
+// with broadcast LDS.128 loads and keeps its whole row (scores, probabilities, output accumulator) in registers: no
+// shuffles, no shared-memory atomics.  Backward: phase A (lane = query) recomputes the probabilities, forms dS and dQ and
+// parks Pd / dS in shared memory; phase B (lane = key) reduces dV = Pd^T dO and dK = dS^T q over the queries.
+// Dropout: explicit keep masks use the reference's dense [S,H,T,T] element order; the Philox stream numbers a row's
+// keys from a 32-aligned base (element (row, tk) -> row * 32 + tk), one counter block per 4 keys.
+// ---------------------------------------------------------------------------
+#define TFM2_MAXT 32
+
+__device__ __forceinline__ uint32_t attn_keep_bits(const DropSite& d, unsigned long long row, int T) {
+    if (d.rate <= 0.f) return 0xffffffffu;
+    uint32_t bits = 0;
+    if (d.keep) {
+        const unsigned char* k = d.keep + row * T;
+        for (int tk = 0; tk < T; tk++) bits |= (k[tk] ? 1u : 0u) << tk;
+        return bits;
+    }
+    const uint32_t thr = (uint32_t)((double)d.rate * 4294967296.0);
+    const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+    for (int b4 = 0; b4 * 4 < T; b4++) {
+        const unsigned long long blk = row * 8 + b4;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), d.site, 1u), key);
+        bits |= ((r.x >= thr ? 1u : 0u) | (r.y >= thr ? 2u : 0u) | (r.z >= thr ? 4u : 0u) | (r.w >= thr ? 8u : 0u)) << (4 * b4);
+    }
+    return bits;
+}
+
+template <int HDP, bool BWD>
+__global__ void __launch_bounds__(256) tfm_attn2_kernel(const TfmAttnArgs a) {
+    extern __shared__ __align__(16) float a2sm[];
+    const int T = a.T, dm = a.dm, H = a.heads, hd = dm / H, s = blockIdx.x;
+    const int nthr = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+    const int HT = H * T;
+    float* sQ = a2sm;                       // [H][T][HDP]
+    float* sK = sQ + (size_t)HT * HDP;
+    float* sV = sK + (size_t)HT * HDP;
+    float* sdO = sV + (size_t)HT * HDP;     // BWD
+    float* sP = sdO + (BWD ? (size_t)HT * HDP : 0);      // BWD: [H][T][T + 1]  dropped probabilities
+    float* sdS = sP + (BWD ? (size_t)HT * (T + 1) : 0);  // BWD: [H][T][T + 1]
+    const int nz = (BWD ? 4 : 3) * HT * HDP;
+    if (hd < HDP) { for (int i = tid; i < nz; i += nthr) a2sm[i] = 0.f; __syncthreads(); }
+    const float* src = a.qkv + (size_t)s * T * 3 * dm;
+    for (int i = tid; i < T * 3 * dm; i += nthr) {
+        const int t = i / (3 * dm), c = i - t * 3 * dm, m = c / dm, cc = c - m * dm, h = cc / hd, d = cc - h * hd;
+        (m == 0 ? sQ : m == 1 ? sK : sV)[((size_t)h * T + t) * HDP + d] = __ldg(src + i);
+    }
+    if (BWD) {
+        const float* dsrc = a.dout + (size_t)s * T * dm;
+        for (int i = tid; i < T * dm; i += nthr) {
+            const int t = i / dm, cc = i - t * dm, h = cc / hd, d = cc - h * hd;
+            sdO[((size_t)h * T + t) * HDP + d] = __ldg(dsrc + i);
+        }
+    }
+    __syncthreads();
+    const float qs = rsqrtf((float)hd);
+    const float inv_keep = a.drop.rate > 0.f ? 1.0f / (1.0f - a.drop.rate) : 1.0f;
+    uint32_t padbits = 0;                                  // bit tk = key tk is padded
+    if (a.kpad) for (int tk = 0; tk < T; tk++) padbits |= (a.kpad[(size_t)s * T + tk] ? 1u : 0u) << tk;
+    for (int h = warp; h < H; h += nw) {
+        const int tq = lane;
+        const bool live = tq < T;
+        const int tqc = live ? tq : T - 1;
+        const float* qrow = sQ + ((size_t)h * T + tqc) * HDP;
+        float q[HDP];
+#pragma unroll
+        for (int d = 0; d < HDP; d += 4) { const float4 v = *reinterpret_cast<const float4*>(qrow + d); q[d] = v.x; q[d + 1] = v.y; q[d + 2] = v.z; q[d + 3] = v.w; }
+        float p[TFM2_MAXT];
+        float mx = -INFINITY;
+        uint32_t vis = ~padbits;
+        if (a.causal) vis &= (tqc >= 31 ? 0xffffffffu : ((2u << tqc) - 1u));
+#pragma unroll
+        for (int tk = 0; tk < TFM2_MAXT; tk++) {
+            p[tk] = -INFINITY;
+            if (tk < T) {
+                const float* kr = sK + ((size_t)h * T + tk) * HDP;
+                float dot = 0.f;
+#pragma unroll
+                for (int d = 0; d < HDP; d += 4) {
+                    const float4 kv = *reinterpret_cast<const float4*>(kr + d);
+                    dot = fmaf(q[d], kv.x, dot); dot = fmaf(q[d + 1], kv.y, dot); dot = fmaf(q[d + 2], kv.z, dot); dot = fmaf(q[d + 3], kv.w, dot);
+                }
+                if ((vis >> tk) & 1u) { p[tk] = dot * qs; mx = fmaxf(mx, p[tk]); }
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int tk = 0; tk < TFM2_MAXT; tk++) {
+            if (tk < T) { p[tk] = expf(p[tk] - mx); sum += p[tk]; } else p[tk] = 0.f;     // all keys masked: NaN like the reference
+        }
+        const float isum = 1.0f / sum;
+        const uint32_t keep = attn_keep_bits(a.drop, ((unsigned long long)s * H + h) * T + tqc, T);
+        if (!BWD) {
+            float acc[HDP];
+#pragma unroll
+            for (int d = 0; d < HDP; d++) acc[d] = 0.f;
+#pragma unroll
+            for (int tk = 0; tk < TFM2_MAXT; tk++) {
+                if (tk < T) {
+                    const float w = ((keep >> tk) & 1u) ? p[tk] * isum * inv_keep : 0.f;
+                    const float* vr = sV + ((size_t)h * T + tk) * HDP;
+#pragma unroll
+                    for (int d = 0; d < HDP; d += 4) {
+                        const float4 vv = *reinterpret_cast<const float4*>(vr + d);
+                        acc[d] = fmaf(w, vv.x, acc[d]); acc[d + 1] = fmaf(w, vv.y, acc[d + 1]); acc[d + 2] = fmaf(w, vv.z, acc[d + 2]); acc[d + 3] = fmaf(w, vv.w, acc[d + 3]);
+                    }
+                }
+            }
+            if (live) {
+                float* o = a.out + ((size_t)s * T + tq) * dm + h * hd;
+#pragma unroll
+                for (int d = 0; d < HDP; d++) if (d < hd) o[d] = acc[d];
+            }
+        } else {
+            const float* dor = sdO + ((size_t)h * T + tqc) * HDP;
+            float dO[HDP];
+#pragma unroll
+            for (int d = 0; d < HDP; d += 4) { const float4 v = *reinterpret_cast<const float4*>(dor + d); dO[d] = v.x; dO[d + 1] = v.y; dO[d + 2] = v.z; dO[d + 3] = v.w; }
+            float dp[TFM2_MAXT];
+            float delta = 0.f;
+#pragma unroll
+            for (int tk = 0; tk < TFM2_MAXT; tk++) {
+                dp[tk] = 0.f;
+                if (tk < T) {
+                    p[tk] *= isum;
+                    const float* vr = sV + ((size_t)h * T + tk) * HDP;
+                    float dot = 0.f;
+#pragma unroll
+                    for (int d = 0; d < HDP; d += 4) {
+                        const float4 vv = *reinterpret_cast<const float4*>(vr + d);
+                        dot = fmaf(dO[d], vv.x, dot); dot = fmaf(dO[d + 1], vv.y, dot); dot = fmaf(dO[d + 2], vv.z, dot); dot = fmaf(dO[d + 3], vv.w, dot);
+                    }
+                    const float m = ((keep >> tk) & 1u) ? inv_keep : 0.f;
+                    dp[tk] = dot * m;
+                    delta = fmaf(dp[tk], p[tk], delta);
+                    if (live) sP[((size_t)h * T + tq) * (T + 1) + tk] = p[tk] * m;
+                }
+            }
+            float dq[HDP];
+#pragma unroll
+            for (int d = 0; d < HDP; d++) dq[d] = 0.f;
+#pragma unroll
+            for (int tk = 0; tk < TFM2_MAXT; tk++) {
+                if (tk < T) {
+                    const float ds = p[tk] * (dp[tk] - delta) * qs;
+                    if (live) sdS[((size_t)h * T + tq) * (T + 1) + tk] = ds;
+                    const float* kr = sK + ((size_t)h * T + tk) * HDP;
+#pragma unroll
+                    for (int d = 0; d < HDP; d += 4) {
+                        const float4 kv = *reinterpret_cast<const float4*>(kr + d);
+                        dq[d] = fmaf(ds, kv.x, dq[d]); dq[d + 1] = fmaf(ds, kv.y, dq[d + 1]); dq[d + 2] = fmaf(ds, kv.z, dq[d + 2]); dq[d + 3] = fmaf(ds, kv.w, dq[d + 3]);
+                    }
+                }
+            }
+            float* go = a.dqkv + ((size_t)s * T + tqc) * 3 * dm + h * hd;
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < HDP; d++) if (d < hd) go[d] = dq[d];
+            }
+            __syncwarp();
+            // phase B: lane = key
+            float dk[HDP], dv[HDP];
+#pragma unroll
+            for (int d = 0; d < HDP; d++) dk[d] = dv[d] = 0.f;
+            for (int t2 = 0; t2 < T; t2++) {
+                const float pd = sP[((size_t)h * T + t2) * (T + 1) + tqc], ds = sdS[((size_t)h * T + t2) * (T + 1) + tqc];
+                const float* d2 = sdO + ((size_t)h * T + t2) * HDP;
+                const float* q2 = sQ + ((size_t)h * T + t2) * HDP;
+#pragma unroll
+                for (int d = 0; d < HDP; d += 4) {
+                    const float4 ov = *reinterpret_cast<const float4*>(d2 + d), qv = *reinterpret_cast<const float4*>(q2 + d);
+                    dv[d] = fmaf(pd, ov.x, dv[d]); dv[d + 1] = fmaf(pd, ov.y, dv[d + 1]); dv[d + 2] = fmaf(pd, ov.z, dv[d + 2]); dv[d + 3] = fmaf(pd, ov.w, dv[d + 3]);
+                    dk[d] = fmaf(ds, qv.x, dk[d]); dk[d + 1] = fmaf(ds, qv.y, dk[d + 1]); dk[d + 2] = fmaf(ds, qv.z, dk[d + 2]); dk[d + 3] = fmaf(ds, qv.w, dk[d + 3]);
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < HDP; d++) if (d < hd) { go[dm + d] = dk[d]; go[2 * dm + d] = dv[d]; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+static inline size_t tfm_attn2_smem(int T, int heads, int hdp, bool bwd) {
+    return ((size_t)(bwd ? 4 : 3) * heads * T * hdp + (bwd ? (size_t)2 * heads * T * (T + 1) : 0)) * 4;
+}

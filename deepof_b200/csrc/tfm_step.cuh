@@ -150,12 +150,43 @@ static int tfm_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW
     return DOF_OK;
 }
 
+template <int HDP>
+static int tfm_attn2_launch(const TfmAttnArgs& a, bool bwd, cudaStream_t st) {
+    const size_t smem = tfm_attn2_smem(a.T, a.heads, HDP, bwd);
+    static size_t attr[2] = {48 * 1024, 48 * 1024};
+    if (smem > attr[bwd ? 1 : 0]) {
+        if (bwd) DOF_CUDA(cudaFuncSetAttribute(tfm_attn2_kernel<HDP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else DOF_CUDA(cudaFuncSetAttribute(tfm_attn2_kernel<HDP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr[bwd ? 1 : 0] = smem;
+    }
+    const int threads = 32 * (a.heads < 8 ? a.heads : 8);
+    if (bwd) tfm_attn2_kernel<HDP, true><<<a.S, threads, smem, st>>>(a);
+    else tfm_attn2_kernel<HDP, false><<<a.S, threads, smem, st>>>(a);
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
 static int tfm_attention(const float* qkv, const unsigned char* kpad, DropSite drop, int causal, int S, int T, int dm, int heads,
                          int q_from, float* out, const float* dout, float* dqkv, cudaStream_t st) {
     const bool bwd = dout != nullptr;
     TfmAttnArgs a;
     a.qkv = qkv; a.kpad = kpad; a.drop = drop; a.out = out; a.dout = dout; a.dqkv = dqkv; a.S = S; a.T = T; a.dm = dm; a.heads = heads;
     a.causal = causal; a.q_from = q_from;
+    const int TQ = T - q_from, hd = dm / heads;
+    const double fl = (bwd ? 2.5 : 1.0) * 4.0 * (double)S * TQ * T * dm / (causal ? 2.0 : 1.0);
+    const double by = 4.0 * (double)S * (bwd ? (6.0 * T * dm + TQ * dm) : (3.0 * T * dm + TQ * dm));
+    // all queries, T <= 32: lane-per-query kernel; otherwise (last-step-only layers, long windows) the warp-per-query kernel
+    const int hdp = hd <= 4 ? 4 : hd <= 8 ? 8 : hd <= 12 ? 12 : hd <= 16 ? 16 : hd <= 32 ? 32 : 0;
+    if (q_from == 0 && T <= TFM2_MAXT && hdp && tfm_attn2_smem(T, heads, hdp, bwd) <= 200 * 1024) {
+        ProfScope ps(bwd ? "tfm_attn_bwd" : "tfm_attn_fwd", st, fl, by);
+        switch (hdp) {
+            case 4: return tfm_attn2_launch<4>(a, bwd, st);
+            case 8: return tfm_attn2_launch<8>(a, bwd, st);
+            case 12: return tfm_attn2_launch<12>(a, bwd, st);
+            case 16: return tfm_attn2_launch<16>(a, bwd, st);
+            default: return tfm_attn2_launch<32>(a, bwd, st);
+        }
+    }
     const size_t smem = ((size_t)T * (3 * dm + 1) * (bwd ? 2 : 1) + (bwd ? (size_t)T * (dm + 1) : 0)) * 4;
     if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "sequence of %d x %d does not fit shared memory", T, 3 * dm);
     static bool attr = false;
@@ -164,14 +195,11 @@ static int tfm_attention(const float* qkv, const unsigned char* kpad, DropSite d
         DOF_CUDA(cudaFuncSetAttribute(tfm_attn_train_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    const int TQ = T - q_from;
-    const double fl = (bwd ? 2.5 : 1.0) * 4.0 * (double)S * TQ * T * dm / (causal ? 2.0 : 1.0);
-    const double by = 4.0 * (double)S * (bwd ? (6.0 * T * dm + TQ * dm) : (3.0 * T * dm + TQ * dm));
     if (bwd) {
-        ProfScope ps("tfm_attn_bwd", st, fl, by);
+        ProfScope ps("tfm_attn_last_bwd", st, fl, by);
         tfm_attn_train_kernel<true><<<S, 128, smem, st>>>(a);
     } else {
-        ProfScope ps("tfm_attn_fwd", st, fl, by);
+        ProfScope ps("tfm_attn_last_fwd", st, fl, by);
         tfm_attn_train_kernel<false><<<S, 128, smem, st>>>(a);
     }
     DOF_LAUNCH_CHECK();

@@ -118,9 +118,10 @@ class _HostPipeline:
 class VaDETrainer(_HostPipeline):
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
                  max_batch: int = 4096, seed: Optional[int] = None, world_size: int = 1, rank: int = 0,
-                 kmeans_loss: float = 1.0, device: Optional[int] = None):
+                 kmeans_loss: float = 1.0, device: Optional[int] = None, encoder_type: str = "recurrent"):
         self.model = VaDEB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, n_components,
-                              kmeans_loss=kmeans_loss, device=device, max_batch=max_batch, training=True, seed=seed)
+                              encoder_type=encoder_type, kmeans_loss=kmeans_loss, device=device, max_batch=max_batch,
+                              training=True, seed=seed)
         self.world_size, self.rank = int(world_size), int(rank)
         self.loss_cfg = VadeLossCfg.pretrain_defaults(n_components)
         self.loss_cfg.model_kmeans_weight = float(kmeans_loss)
@@ -239,10 +240,11 @@ class VQVAETrainer(_GenericTrainer, _HostPipeline):
 
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, n_components: int,
                  max_batch: int = 4096, seed: Optional[int] = None, world_size: int = 1, rank: int = 0,
-                 kmeans_loss: float = 0.0, beta: float = 1.0, lr: float = 1e-3, device: Optional[int] = None):
+                 kmeans_loss: float = 0.0, beta: float = 1.0, lr: float = 1e-3, device: Optional[int] = None,
+                 encoder_type: str = "recurrent"):
         from .models import VQVAEB200
-        m = VQVAEB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, n_components, kmeans_loss=kmeans_loss,
-                      beta=beta, device=device, max_batch=max_batch, training=True, seed=seed)
+        m = VQVAEB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, n_components, encoder_type=encoder_type,
+                      kmeans_loss=kmeans_loss, beta=beta, device=device, max_batch=max_batch, training=True, seed=seed)
         super().__init__(m, world_size, rank, lr)
         T, N, F = m.input_shape
         _, E, Fe = m.edge_feature_shape
@@ -266,9 +268,11 @@ class ContrastiveTrainer(_GenericTrainer, _HostPipeline):
 
     def __init__(self, input_shape, edge_feature_shape, adjacency_matrix, latent_dim: int, max_batch: int = 4096,
                  seed: Optional[int] = None, world_size: int = 1, rank: int = 0, temperature: float = 0.1,
-                 aug=None, lr: float = 1e-3, edge_index=None, edge_index_local=None, device: Optional[int] = None):
+                 aug=None, lr: float = 1e-3, edge_index=None, edge_index_local=None, device: Optional[int] = None,
+                 encoder_type: str = "recurrent"):
         from .models import ContrastiveAugCfg, ContrastiveB200
-        m = ContrastiveB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, temperature=temperature,
+        m = ContrastiveB200(input_shape, edge_feature_shape, adjacency_matrix, latent_dim, encoder_type=encoder_type,
+                            temperature=temperature,
                             edge_index=edge_index, edge_index_local=edge_index_local, device=device, max_batch=max_batch,
                             training=True, seed=seed)
         super().__init__(m, world_size, rank, lr)

@@ -282,9 +282,127 @@ def run_vade_train(name, c):
     print("tfmvade", name, "%.1f KB" % (os.path.getsize(path) / 1024), {k: round(v, 4) for k, v in list(res.logs.items())[:4]})
 
 
+STEP_CASES = {
+    # step_vqvae_distill / step_contrastive_distill (teacher off) on the transformer model family
+    "vq_small": dict(model="vqvae", T=12, N=11, D=6, K=7, B=8, seed=91, beta=1.0),
+    "vq_cfg3": dict(model="vqvae", T=25, N=14, D=16, K=64, B=6, seed=92, beta=0.25),
+    "con_small": dict(model="contrastive", T=24, N=11, D=6, K=1, B=8, seed=93),
+    "con_cfg": dict(model="contrastive", T=50, N=14, D=8, K=1, B=6, seed=94),
+}
+
+
+def run_step(name, c):
+    """One reference training step of VQVAEPT / ContrastivePT with encoder_type="transformer".  Dropout masks are replayed
+    from the generator state captured right before every encoder / decoder call (hooks record torch.get_rng_state());
+    the oracle fed with the replayed masks must reproduce logs and gradients before anything is written."""
+    import types
+    from oracle import tfm_oracle as TO
+    from oracle import vade_oracle as O
+    torch.manual_seed(c["seed"])
+    torch.set_num_threads(1)
+    adj = default_adjacency(c["N"])
+    rows, cols = np.nonzero(np.triu(adj))
+    E = len(rows)
+    xs, as_ = (c["T"], c["N"], 3), (c["T"], E, 1)
+    con = c["model"] == "contrastive"
+    if con:
+        model = M.ContrastivePT(xs, as_, adj, c["D"], encoder_type="transformer", use_gnn=True, temperature=0.1)
+    else:
+        model = M.VQVAEPT(xs, as_, adj, c["D"], c["K"], encoder_type="transformer", use_gnn=True, kmeans_loss=0.0, beta=c["beta"])
+    Tenc = c["T"] // 2 if con else c["T"]
+    model.train()
+    with torch.no_grad():
+        for i in range(2):
+            xi, ai = synthetic_windows(16, Tenc, adj, seed=9200 + 10 * c["seed"] + i)
+            model.encoder(xi, ai)
+        if not con:
+            xi, ai = synthetic_windows(c["B"], Tenc, adj, seed=9700 + c["seed"])
+            model.eval()
+            e0 = model.encoder(xi, ai)
+            model.train()
+            model.vq_layer.codebook.copy_(e0.mean(0, keepdim=True).t() + e0.std() * 1.5 * torch.randn(c["D"], c["K"]))
+    x, a = synthetic_windows(c["B"], c["T"], adj, seed=9700 + c["seed"])
+    p0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    states = []
+    hooks = [model.encoder.register_forward_pre_hook(lambda m, i: states.append(("enc", torch.get_rng_state(), [t.detach().clone() for t in i])))]
+    if not con:
+        hooks.append(model.decoder.register_forward_pre_hook(lambda m, i: states.append(("dec", torch.get_rng_state(), None))))
+    seed = 9960 + c["seed"]
+    torch.manual_seed(seed)
+    if con:
+        names = [f"B_n{i}" for i in range(c["N"])]
+        meta = {"node_columns": [(n, "x") for n in names] + [(n, "y") for n in names] + names,
+                "edge_columns": [(names[i], names[j]) for i, j in zip(rows, cols)]}
+        eg, el, _ = T._build_edge_from_metainfo(meta, torch.device("cpu"), c["N"])
+        rot = T.build_rotation_precomp(edge_index=el, n_nodes=c["N"], device=torch.device("cpu"))
+        ccfg = U.ContrastiveCfg()
+        ccfg.aug_p_interp = 0.6
+        ctx = types.SimpleNamespace(apply_distill=False, edge_index=eg, edge_index_local=el, contrastive_cfg=ccfg, rot_precomp=rot)
+        res = T.step_contrastive_distill(model, (x, a, torch.arange(c["B"])), ctx)
+    else:
+        ctx = types.SimpleNamespace(apply_distill=False)
+        res = T.step_vqvae_distill(model, (x, a, torch.arange(c["B"])), ctx)
+    res.loss.backward()
+    for h in hooks:
+        h.remove()
+    dk = model.encoder.key_dim
+    graph = O.graph_operators(adj)
+
+    def enc_masks(state, B):
+        torch.set_rng_state(state)
+        mk = {}
+        for core, S in (("node", B * c["N"]), ("edge", B * E)):
+            for nm, shp in TO.dropout_mask_shapes(S, Tenc, dk, 4, 2):
+                mk[f"{core}.{nm}"] = torch.empty(shp).bernoulli_(0.9)
+        return mk
+
+    def dec_masks(state, prefix):
+        torch.set_rng_state(state)
+        return {nm.replace("dec.", prefix): torch.empty(shp).bernoulli_(0.8)
+                for nm, shp in TO.decoder_mask_shapes(c["B"], c["T"], 4 * c["D"], 8, 128, 2)}
+
+    out = {"adjacency": adj, "model": np.array(c["model"]), "meta": np.array([c["T"], c["N"], E, c["D"], c["K"], c["B"]], dtype=np.int64)}
+    if con:
+        assert [s[0] for s in states] == ["enc", "enc"], [s[0] for s in states]
+        (xv, av), (xav, aav) = states[0][2], states[1][2]
+        m0, m1 = enc_masks(states[0][1], c["B"]), enc_masks(states[1][1], c["B"])
+        logs, grads, _ = TO.contrastive_views_step(xv, av, xav, aav, p0, graph, m0, m1, 0.1)
+        out.update({"x": xv.numpy(), "a": av.numpy(), "x_aug": xav.numpy(), "a_aug": aav.numpy()})
+        masks = {**m0, **{"aug." + k: v for k, v in m1.items()}}
+    else:
+        assert [s[0] for s in states] == ["enc", "dec", "dec"], [s[0] for s in states]
+        masks = {**enc_masks(states[0][1], c["B"]), **dec_masks(states[1][1], "dec."), **dec_masks(states[2][1], "dec1.")}
+        logs, grads, _ = TO.vqvae_train_step(x, a, p0, graph, masks, c["beta"], 0.0)
+        out.update({"x": x.numpy(), "a": a.numpy(), "beta": np.array(c["beta"])})
+    for k, v in res.logs.items():
+        assert abs(logs[k] - v) <= 5e-5 * max(1.0, abs(v)), (k, logs[k], v)
+    for k, prm in model.named_parameters():
+        if prm.grad is not None:
+            assert float((grads[k] - prm.grad).abs().max()) <= 5e-4 * max(1.0, float(prm.grad.abs().max())), k
+    for k, v in p0.items():
+        out["p/" + k] = v.numpy().copy()
+    for k, v in model.state_dict().items():
+        if "running" in k:
+            out["p1/" + k] = v.detach().numpy().copy()
+    for k, v in res.logs.items():
+        out["log/" + k] = np.array(v, dtype=np.float64)
+    for k, prm in model.named_parameters():
+        if prm.grad is not None:
+            out["g/" + k] = prm.grad.detach().numpy().copy()
+    for k, m in masks.items():
+        out["mask/" + k] = np.packbits(m.numpy().astype(np.uint8).reshape(-1))
+        out["mshape/" + k] = np.array(m.shape, dtype=np.int64)
+    path = os.path.join(HERE, f"tfmstep_{name}.npz")
+    np.savez_compressed(path, **out)
+    print("tfmstep", name, "%.1f KB" % (os.path.getsize(path) / 1024), {k: round(v, 4) for k, v in list(res.logs.items())[:4]})
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     sys.path.insert(0, HERE)
+    for name, c in STEP_CASES.items():
+        if not only or name in only:
+            run_step(name, c)
     for name, c in VADE_TRAIN_CASES.items():
         if not only or name in only:
             run_vade_train(name, c)

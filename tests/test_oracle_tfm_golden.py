@@ -108,3 +108,27 @@ def test_vade_transformer_train_step(case):
     assert rel_l2(flat, ref) < 5e-5
     for k, v in grads.items():
         assert (v is None) == (k not in names), k
+
+
+@pytest.mark.parametrize("case", golden_cases_of("tfmstep"))
+def test_vqvae_and_contrastive_transformer_steps(case):
+    """step_vqvae_distill / step_contrastive_distill (teacher off) of the transformer family: logs and gradients of the
+    reference with its dropout masks replayed (two decoder passes for VQ-VAE; two encoder passes with separate batch
+    statistics for the contrastive model)."""
+    g = load_golden_of("tfmstep", case)
+    p = sub(g, "p/")
+    graph = O.graph_operators(g["adjacency"])
+    masks = _unpack_masks(g)
+    if str(g["model"]) == "vqvae":
+        logs, grads, _ = TO.vqvae_train_step(torch.from_numpy(g["x"]), torch.from_numpy(g["a"]), p, graph, masks, float(g["beta"]), 0.0)
+    else:
+        m0 = {k: v for k, v in masks.items() if not k.startswith("aug.")}
+        m1 = {k[4:]: v for k, v in masks.items() if k.startswith("aug.")}
+        logs, grads, _ = TO.contrastive_views_step(*(torch.from_numpy(g[k]) for k in ("x", "a", "x_aug", "a_aug")), p, graph, m0, m1, 0.1)
+    for k in logs:
+        ref = float(g["log/" + k])
+        assert abs(logs[k] - ref) <= 5e-5 * max(1.0, abs(ref)), (k, logs[k], ref)
+    names = [k[2:] for k in g if k.startswith("g/")]
+    flat = torch.cat([grads[k].flatten() for k in names])
+    ref = torch.cat([torch.from_numpy(g["g/" + k]).flatten() for k in names])
+    assert rel_l2(flat, ref) < 5e-5

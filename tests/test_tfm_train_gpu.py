@@ -62,6 +62,8 @@ def _grad_cmp(gd, ref, names):
     num = sum(float((gd[k].cpu().double() - ref[k].double()).pow(2).sum()) for k in names)
     den = sum(float(ref[k].double().pow(2).sum()) for k in names)
     worst = max(names, key=lambda k: float((gd[k].cpu().double() - ref[k].double()).norm() / ref[k].double().norm().clamp_min(1e-12)))
+    contrib = sorted(((float((gd[k].cpu().double() - ref[k].double()).norm()) / max(den, 1e-300) ** 0.5, k) for k in names), reverse=True)[:4]
+    print("largest contributions to the flat error:", [(round(c, 7), k) for c, k in contrib])
     return (num / max(den, 1e-300)) ** 0.5, worst
 
 
@@ -190,11 +192,12 @@ def test_vade_transformer_step_vs_oracle_tensor_core_sizes(geom):
     E = int(np.count_nonzero(np.triu(adj)))
     x, a = O.synthetic_windows(B, T, adj, seed=77)
     m = VaDEB200((T, N, 3), (T, E, 1), adj, D, K, encoder_type="transformer", max_batch=B, training=True, seed=11)
+    pg = torch.Generator().manual_seed(17)
     with torch.no_grad():
         m.latent_space.gmm_means.mul_(3.0)
         for k, v in m._views.items():                       # move the affine parameters off their init so that they matter
             if k.endswith("bias") and v.dim() == 1:
-                v.add_(0.05 * torch.randn(v.shape, device=v.device, generator=None))
+                v.add_(0.05 * torch.randn(v.shape, generator=pg).to(v.device))
     m.set_pretrain_mode(False)
     p = {k: v.cpu() for k, v in m.state_dict().items()}
     dk = p["encoder.node_tf.embed.weight"].shape[0]
@@ -261,3 +264,48 @@ def test_philox_dropout_properties():
     fd = (lp - lm) / (2 * h)
     an = float((g1[off:off + n] * d).sum())
     assert abs(fd - an) <= 0.05 * max(abs(an), 1e-3) + 2e-3, (fd, an)
+
+
+@pytest.mark.parametrize("case", golden_cases_of("tfmstep"))
+def test_vqvae_and_contrastive_transformer_steps_vs_reference_golden(case):
+    """cfg3's model family: step_vqvae_distill (two decoder passes) and step_contrastive_distill (two encoder passes =
+    two statistics groups in one launch sequence over 2B windows) of the transformer models vs the reference."""
+    from deepof_b200 import ContrastiveB200, VQVAEB200, _lib
+    from deepof_b200.models import CON_LOG_KEYS, VQ_LOG_KEYS
+    g = load_golden_of("tfmstep", case)
+    T, N, E, D, K, B = (int(v) for v in g["meta"])
+    masks = _unpack_masks(g)
+    gnames = [k[2:] for k in g if k.startswith("g/")]
+    ref = {k: torch.from_numpy(g["g/" + k]) for k in gnames}
+    if str(g["model"]) == "vqvae":
+        m = VQVAEB200((T, N, 3), (T, E, 1), g["adjacency"], D, K, encoder_type="transformer", beta=float(g["beta"]), max_batch=B, training=True, seed=1)
+        assert [k for k, *_ in m.layout] == [k[2:] for k in g if k.startswith("p/")]
+        m.load_state_dict(sub(g, "p/"))
+        dk = m._views["encoder.node_tf.embed.weight"].shape[0]
+        m.loss_grad(torch.from_numpy(g["x"]), torch.from_numpy(g["a"]), dropout_masks=_flat_masks(masks, B, N, E, T, dk, D, dec_passes=2))
+        keys = VQ_LOG_KEYS
+    else:
+        m = ContrastiveB200((T, N, 3), (T, E, 1), g["adjacency"], D, encoder_type="transformer", max_batch=B, training=True, seed=1)
+        assert [k for k, *_ in m.layout] == [k[2:] for k in g if k.startswith("p/")]
+        m.load_state_dict(sub(g, "p/"))
+        dk = m._views["encoder.node_tf.embed.weight"].shape[0]
+        both = {k: torch.cat([masks[k], masks["aug." + k]], 0) for k in masks if not k.startswith("aug.")}
+        flat = _flat_masks(both, 2 * B, N, E, T // 2, dk, D, with_decoder=False).cuda()
+        x2 = torch.cat([torch.from_numpy(g["x"]), torch.from_numpy(g["x_aug"])]).cuda().contiguous()
+        a2 = torch.cat([torch.from_numpy(g["a"]), torch.from_numpy(g["a_aug"])]).cuda().contiguous()
+        _lib.check(m.L.dof_set_dropout(m.handle, 0, _lib.ptr(flat), flat.numel()))
+        _lib.check(m.L.dof_contrastive_loss_grad(m.handle, _lib.ptr(m.state), _lib.ptr(m.grad), _lib.ptr(x2), _lib.ptr(a2), B, 0, 0, 0.1, 0.1, 0.1,
+                                                 _lib.ptr(m.logs), None, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        keys = CON_LOG_KEYS
+    logs = m.logs_dict()
+    for k in keys:
+        r = float(g["log/" + k])
+        assert abs(logs[k] - r) <= 1e-4 * max(1.0, abs(r)), (k, logs[k], r)
+    err, worst = _grad_cmp(m.grad_dict(), ref, gnames)
+    print(case, "grad", err, "worst", worst)
+    assert err < 2e-4, (err, worst)
+    m.adam_step(0.0)
+    sd = m.state_dict()
+    for k in g:
+        if k.startswith("p1/"):
+            assert rel_l2(sd[k[3:]].cpu(), g[k]) < 1e-5, k
