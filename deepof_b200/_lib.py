@@ -100,6 +100,9 @@ _SIGS = {
     "dof_vade_forward_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "dof_vade_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P,
                                      C.POINTER(DofVadeLossCfg), _P, _P]),
+    "dof_vade_loss_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.POINTER(DofVadeLossCfg), _P, _P]),
+    "dof_vqvae_loss_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P, _P]),
+    "dof_contrastive_loss_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
     "dof_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(DofAdamCfg), _P]),
     "dof_encode": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
     "dof_dropout_mask_bytes": (C.c_size_t, [C.POINTER(DofConfig), C.c_int, C.c_int, C.c_int]),

@@ -1202,12 +1202,12 @@ int dof_vade_embed(dof_handle* h, const float* state, const float* x, const floa
     return dof_vade_forward_eval(h, state, x, a, B, nullptr, emb, q, nullptr, stream);
 }
 
-int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B,
-                       const float* eps, const float* mc_eps, const float* tau_batch, const float* class_weight,
-                       const float* floor_c, const dof_vade_loss_cfg* loss, float* logs, void* stream) {
+static int vade_step(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B,
+                     const float* eps, const float* mc_eps, const float* tau_batch, const float* class_weight,
+                     const float* floor_c, const dof_vade_loss_cfg* loss, float* logs, void* stream, bool train) {
     DOF_TRY(check_batch(h, B));
     if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
-    if (!state || !grad || !x || !a || !eps || !loss || !logs || !floor_c) DOF_FAIL(DOF_ERR_ARG, "null argument");
+    if (!state || (train && (!grad || !eps)) || !x || !a || !loss || !logs || !floor_c) DOF_FAIL(DOF_ERR_ARG, "null argument");
     if (!loss->pretrain_mode && !mc_eps) DOF_FAIL(DOF_ERR_ARG, "mc_eps is required in main mode");
     if (!loss->pretrain_mode && loss->mc_samples != 32) DOF_FAIL(DOF_ERR_UNSUPPORTED, "mc_samples must be 32, got %d", loss->mc_samples);
     if (loss->tf_cluster_weight != 0.f) DOF_FAIL(DOF_ERR_UNSUPPORTED, "tf_cluster_weight != 0 is not supported");
@@ -1216,18 +1216,18 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int D = c.D, K = c.K, T = c.T, NF = c.N * c.F;
-    DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)L.total * 4, st));
+    if (train) DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)L.total * 4, st));
     if (c.model != DOF_MODEL_VADE) DOF_FAIL(DOF_ERR_ARG, "handle is not a VaDE model");
-    DOF_TRY(encoder_forward(h, state, x, a, B, true, st));
-    DOF_TRY(vade_latent_forward(h, state, B, eps, st));
-    DOF_TRY(decoder_forward(h, state, h->z, x, B, true, st));
+    DOF_TRY(encoder_forward(h, state, x, a, B, train, st));
+    DOF_TRY(vade_latent_forward(h, state, B, train ? eps : nullptr, st));
+    DOF_TRY(decoder_forward(h, state, h->z, x, B, train, st));
     // ---- loss
     StatsLayout SL = stats_layout(D, K);
     DOF_CUDA(cudaMemsetAsync(h->stats, 0, (size_t)SL.total * sizeof(double), st));
     const long long nrec = (long long)B * T * NF;
     int rgrid = (int)((nrec + 255) / 256 < (long long)h->sm_count * 8 ? (nrec + 255) / 256 : (long long)h->sm_count * 8);
     { ProfScope ps("recon", st, 0.0, 12.0 * nrec);
-    recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->stats + ST_RECON); }
+    recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, train ? h->dloc : nullptr, nrec, 1.0f / ((float)B * T), h->stats + ST_RECON); }
     DOF_LAUNCH_CHECK();
     LossArgs la;
     memset(&la, 0, sizeof(la));
@@ -1237,7 +1237,7 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
     la.tau = (loss->lambda_distill > 0.f) ? tau_batch : nullptr;
     la.class_weight = class_weight; la.floor_c = floor_c;
     la.stats = h->stats; la.coef = h->coef; la.dzm_kl = h->dzm_kl; la.dlv_kl = h->dlv_kl; la.distw = h->distw;
-    la.dz_dec = h->dz_dec; la.dzm = h->dzm; la.dpre = h->dpre; la.g_mu = grad + L.gmm_mu; la.g_lv = grad + L.gmm_lv;
+    la.dz_dec = h->dz_dec; la.dzm = h->dzm; la.dpre = h->dpre; la.g_mu = train ? grad + L.gmm_mu : nullptr; la.g_lv = train ? grad + L.gmm_lv : nullptr;
     la.logs = logs; la.B = B; la.D = D; la.K = K; la.T = T; la.Dx = NF;
     static bool attr = false;
     if (!attr) {
@@ -1253,6 +1253,7 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
     { ProfScope ps("loss_finalize", st);
     loss_finalize_kernel<<<1, 256, loss_finalize_smem_bytes(D, K), st>>>(la); }
     DOF_LAUNCH_CHECK();
+    if (!train) { h->lastB = B; register_debug(h, B); return DOF_OK; }
     // ---- backward
     DOF_TRY(decoder_backward(h, state, grad, h->z, B, st));
     { ProfScope ps("loss_grad", st);
@@ -1263,6 +1264,20 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
     h->lastB = B;
     register_debug(h, B);
     return DOF_OK;
+}
+
+int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B,
+                       const float* eps, const float* mc_eps, const float* tau_batch, const float* class_weight,
+                       const float* floor_c, const dof_vade_loss_cfg* loss, float* logs, void* stream) {
+    return vade_step(h, state, grad, x, a, B, eps, mc_eps, tau_batch, class_weight, floor_c, loss, logs, stream, true);
+}
+
+// validate_one_epoch_indexed's step (training.py:190-229): model.eval() -> z = z_mean, no dropout, BatchNorm running
+// statistics; the criterion's terms and the 13 logs, no gradient
+int dof_vade_loss_eval(dof_handle* h, const float* state, const float* x, const float* a, int B, const float* mc_eps,
+                       const float* tau_batch, const float* class_weight, const float* floor_c, const dof_vade_loss_cfg* loss,
+                       float* logs, void* stream) {
+    return vade_step(h, state, nullptr, x, a, B, nullptr, mc_eps, tau_batch, class_weight, floor_c, loss, logs, stream, false);
 }
 
 // ---- encoder only: model.encoder(x, a)  (RecurrentEncoderPT.forward, models_new.py:140-181) -------------
@@ -1345,28 +1360,29 @@ int dof_vqvae_loss_grad(dof_handle* h, const float* state, float* grad, const fl
     return dof_vqvae_loss_grad_distill(h, state, grad, x, a, B, beta, kmeans_weight, nullptr, logs, stream);
 }
 
-int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B, float beta,
-                                float kmeans_weight, const dof_distill_cfg* distill, float* logs, void* stream) {
+static int vqvae_step(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B, float beta,
+                      float kmeans_weight, const dof_distill_cfg* distill, float* logs, void* stream, bool train) {
     DOF_TRY(check_batch(h, B));
     const dof_config& c = h->cfg;
     if (c.model != DOF_MODEL_VQVAE) DOF_FAIL(DOF_ERR_ARG, "handle is not a VQ-VAE model");
     if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
-    if (!state || !grad || !x || !a || !logs) DOF_FAIL(DOF_ERR_ARG, "null argument");
+    if (!state || (train && !grad) || !x || !a || !logs) DOF_FAIL(DOF_ERR_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const Layout& L = h->L;
     const int D = c.D, K = c.K, T = c.T, NF = c.N * c.F;
-    DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)L.total * 4, st));
-    DOF_TRY(encoder_forward(h, state, x, a, B, true, st));
+    if (train) DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)L.total * 4, st));
+    DOF_TRY(encoder_forward(h, state, x, a, B, train, st));
     DOF_TRY(vq_forward(h, state, B, kmeans_weight != 0.f, st));
     const long long nrec = (long long)B * T * NF;
     int rgrid = (int)((nrec + 255) / 256 < (long long)h->sm_count * 8 ? (nrec + 255) / 256 : (long long)h->sm_count * 8);
     for (int pass = 0; pass < 2; pass++) {
         const float* zin = pass == 0 ? h->quant : h->enc;
         h->dec_pass = pass;
-        DOF_TRY(decoder_forward(h, state, zin, x, B, true, st));
+        DOF_TRY(decoder_forward(h, state, zin, x, B, train, st));
         { ProfScope ps("recon", st, 0.0, 12.0 * nrec);
-        recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, h->dloc, nrec, 1.0f / ((float)B * T), h->vstats + (pass == 0 ? VQ_ST_REC_Q : VQ_ST_REC_E)); }
+        recon_kernel<<<rgrid, 256, 0, st>>>(h->loc, x, train ? h->dloc : nullptr, nrec, 1.0f / ((float)B * T), h->vstats + (pass == 0 ? VQ_ST_REC_Q : VQ_ST_REC_E)); }
         DOF_LAUNCH_CHECK();
+        if (!train) continue;
         DOF_TRY(decoder_backward(h, state, grad, zin, B, st));
         if (pass == 0) {
             { ProfScope ps("vq_codebook_grad", st);
@@ -1375,10 +1391,12 @@ int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, 
         }
     }
     h->dec_pass = 0;
-    DOF_CUDA(cudaMemcpyAsync(h->denc, h->dz_dec, (size_t)B * D * 4, cudaMemcpyDeviceToDevice, st));
-    const bool dist_on = distill && distill->lambda > 0.f;               // training.py:346
-    if (dist_on) DOF_TRY(distill_head_step(h, distill, B, h->vstats + VQ_ST_DISTILL, false, st));
-    DOF_TRY(encoder_backward(h, state, grad, B, st));
+    const bool dist_on = train && distill && distill->lambda > 0.f;      // training.py:346
+    if (train) {
+        DOF_CUDA(cudaMemcpyAsync(h->denc, h->dz_dec, (size_t)B * D * 4, cudaMemcpyDeviceToDevice, st));
+        if (dist_on) DOF_TRY(distill_head_step(h, distill, B, h->vstats + VQ_ST_DISTILL, false, st));
+        DOF_TRY(encoder_backward(h, state, grad, B, st));
+    }
     VqFinalArgs f;
     f.stats = h->vstats; f.logs = logs; f.B = B; f.T = T; f.Dx = NF; f.D = D; f.K = K; f.beta = beta; f.kmeans_w = kmeans_weight;
     f.lambda_distill = dist_on ? distill->lambda : 0.f;
@@ -1388,6 +1406,17 @@ int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, 
     h->lastB = B;
     register_debug(h, B);
     return DOF_OK;
+}
+
+int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B, float beta,
+                                float kmeans_weight, const dof_distill_cfg* distill, float* logs, void* stream) {
+    return vqvae_step(h, state, grad, x, a, B, beta, kmeans_weight, distill, logs, stream, true);
+}
+
+// the validation step of fit_VQVAE (training.py:1165-1170): eval-mode forward, the loss terms, no gradient, teacher off
+int dof_vqvae_loss_eval(dof_handle* h, const float* state, const float* x, const float* a, int B, float beta, float kmeans_weight,
+                        float* logs, void* stream) {
+    return vqvae_step(h, state, nullptr, x, a, B, beta, kmeans_weight, nullptr, logs, stream, false);
 }
 
 // ---- contrastive -------------------------------------------------------------------------------------------
@@ -1857,23 +1886,40 @@ int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, co
                                              logs, z_out, stream);
 }
 
+static int contrastive_step(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
+                            int loss_kind, int sim_kind, float temperature, float tau_plus, float beta,
+                            const dof_distill_cfg* distill, float* logs, float* z_out, void* stream, bool train);
+
 int dof_contrastive_loss_grad_distill(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
                                       int loss_kind, int sim_kind, float temperature, float tau_plus, float beta,
                                       const dof_distill_cfg* distill, float* logs, float* z_out, void* stream) {
+    return contrastive_step(h, state, grad, x2, a2, B, loss_kind, sim_kind, temperature, tau_plus, beta, distill, logs, z_out, stream, true);
+}
+
+// the validation step of fit_contrastive: eval-mode encoder on both views, the loss, no gradient, teacher off
+int dof_contrastive_loss_eval(dof_handle* h, const float* state, const float* x2, const float* a2, int B, int loss_kind, int sim_kind,
+                              float temperature, float tau_plus, float beta, float* logs, float* z_out, void* stream) {
+    return contrastive_step(h, state, nullptr, x2, a2, B, loss_kind, sim_kind, temperature, tau_plus, beta, nullptr, logs, z_out, stream, false);
+}
+
+static int contrastive_step(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2, int B,
+                            int loss_kind, int sim_kind, float temperature, float tau_plus, float beta,
+                            const dof_distill_cfg* distill, float* logs, float* z_out, void* stream, bool train) {
     DOF_TRY(check_batch(h, 2 * B));
     const dof_config& c = h->cfg;
     if (c.model != DOF_MODEL_CONTRASTIVE) DOF_FAIL(DOF_ERR_ARG, "handle is not a contrastive model");
     if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
-    if (!state || !grad || !x2 || !a2 || !logs || !(temperature > 0.f)) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
+    if (!state || (train && !grad) || !x2 || !a2 || !logs || !(temperature > 0.f)) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
     if (sim_kind < 0 || sim_kind > 1) DOF_FAIL(DOF_ERR_UNSUPPORTED, "similarity kind %d (0 cosine / dot, 1 euclidean / edit)", sim_kind);
     if (loss_kind < 0 || loss_kind > 3) DOF_FAIL(DOF_ERR_UNSUPPORTED, "contrastive loss kind %d (0 nce, 1 dcl, 2 hard_dcl, 3 fc)", loss_kind);
     if ((loss_kind == 1 || loss_kind == 2) && !(tau_plus >= 0.f && tau_plus < 1.f)) DOF_FAIL(DOF_ERR_ARG, "tau_plus must be in [0, 1)");
     if (c.D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 64", c.D);
     cudaStream_t st = (cudaStream_t)stream;
-    DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)h->L.total * 4, st));
+    if (train) DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)h->L.total * 4, st));
     h->next_groups = 2;                 // the reference encodes the two views in two passes: separate batch statistics
-    DOF_TRY(encoder_forward(h, state, x2, a2, 2 * B, true, st));
+    int erc = encoder_forward(h, state, x2, a2, 2 * B, train, st);
     h->next_groups = 1;
+    DOF_TRY(erc);
     if (z_out) DOF_CUDA(cudaMemcpyAsync(z_out, h->enc, (size_t)2 * B * c.D * 4, cudaMemcpyDeviceToDevice, st));
     NtxArgs n;
     n.enc = h->enc; n.zn = h->zn; n.nrm = h->nrm; n.lse = h->lse; n.denc = h->denc; n.stats = h->nstats; n.logs = logs;
@@ -1888,12 +1934,12 @@ int dof_contrastive_loss_grad_distill(dof_handle* h, const float* state, float* 
     else if (c.D <= 32) DOF_TRY(ntx_launch<32>(n, B, st));
     else DOF_TRY(ntx_launch<64>(n, B, st));
     // training.py:533-557: the head sees the row-NORMALISED embedding of the MAIN view (z is reassigned before z_main = z)
-    const bool dist_on = distill && distill->lambda > 0.f;
+    const bool dist_on = train && distill && distill->lambda > 0.f;
     if (dist_on) DOF_TRY(distill_head_step(h, distill, B, h->nstats + NTX_ST_DISTILL, true, st));
     { ProfScope ps("ntxent_finalize", st);
     ntx_finalize_kernel<<<1, 1, 0, st>>>(n, temperature, dist_on ? distill->lambda : 0.f); }
     DOF_LAUNCH_CHECK();
-    DOF_TRY(encoder_backward(h, state, grad, 2 * B, st));
+    if (train) DOF_TRY(encoder_backward(h, state, grad, 2 * B, st));
     h->lastB = 2 * B;
     register_debug(h, 2 * B);
     return DOF_OK;

@@ -151,6 +151,15 @@ class VQVAEB200(VaDEB200):
                                                  ptr(self.logs), _stream()))
         return self.logs
 
+    def loss_eval(self, x, a):
+        """The validation step of ``fit_VQVAE`` (training.py:1165-1170): eval-mode forward + loss terms, teacher off."""
+        if not self.training_capable:
+            raise _lib.DofError("model was created with training=False")
+        x, a = self._prep(x, a)
+        check(self.L.dof_vqvae_loss_eval(self.handle, ptr(self.state), ptr(x), ptr(a), x.shape[0], self.beta, self.kmeans_weight,
+                                         ptr(self.logs), _stream()))
+        return self.logs
+
     def adam_step(self, lr: float, clip: float = 0.75, grad_scale: float = 1.0, weight_decay: float = 1e-4, **kw):
         """clip_grad_value_(0.75) + build_optimizer_generic's Adam(lr, weight_decay=1e-4) (losses.py:805-814)."""
         super().adam_step(lr, lr, clip=clip, grad_scale=grad_scale, weight_decay=weight_decay, **kw)
@@ -358,6 +367,26 @@ class ContrastiveB200(VaDEB200):
                                                        C.byref(dc) if dc is not None else None, ptr(self.logs),
                                                        ptr(self.z_all[:2 * B]), _stream()))
         return self.logs
+
+    def loss_eval(self, x_full, prm: AugParams):
+        """The validation step of ``fit_contrastive``: views, eval-mode encoder on both, the loss; teacher off."""
+        if not self.training_capable:
+            raise _lib.DofError("model was created with training=False")
+        x2, a2 = self.views(x_full, prm)
+        B = x2.shape[0] // 2
+        kind = {"nce": 0, "dcl": 1, "hard_dcl": 2, "fc": 3}[self.loss_function]
+        sim = 0 if self.similarity_function in ("cosine", "dot") else 1
+        check(self.L.dof_contrastive_loss_eval(self.handle, ptr(self.state), ptr(x2), ptr(a2), B, kind, sim, self.temperature, self.tau,
+                                               self.beta, ptr(self.logs), ptr(self.z_all[:2 * B]), _stream()))
+        return self.logs
+
+    def main_view(self, x_full):
+        """The middle half window and its recomputed edge lengths (training.py:518-525; ``get_q_contrastive``,
+        logging.py:83-115): what the distillation head sees."""
+        B = x_full.shape[0]
+        prm = AugParams(start=torch.full((B,), (self.full_time_steps // 2) // 2, dtype=torch.int32, device=self.device))
+        x2, a2 = self.views(x_full, prm)
+        return x2[:B], a2[:B]
 
     def adam_step(self, lr: float, clip: float = 0.75, grad_scale: float = 1.0, weight_decay: float = 1e-4, **kw):
         super().adam_step(lr, lr, clip=clip, grad_scale=grad_scale, weight_decay=weight_decay, **kw)

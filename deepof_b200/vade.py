@@ -420,6 +420,46 @@ class VaDEB200:
                                         ptr(self.logs), _stream()))
         return self.logs
 
+    def loss_eval(self, x, a, loss_cfg: VadeLossCfg, mc_eps=None, tau_batch=None, class_weight=None, teacher_marginal=None):
+        """The validation step (``validate_one_epoch_indexed``, training.py:190-229): eval-mode forward (z = z_mean, no
+        dropout, BatchNorm running statistics) + the criterion's terms; returns the device log vector.  No gradient,
+        ``self.grad`` is left untouched."""
+        if not self.training_capable:
+            raise _lib.DofError("model was created with training=False")
+        x, a = self._prep(x, a)
+        B = x.shape[0]
+        D, K = self.latent_dim, self.n_components
+        if mc_eps is None and not loss_cfg.pretrain_mode:
+            mc_eps = torch.randn(loss_cfg.mc_samples, B, D, device=self.device)
+        f32 = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).to(self.device).contiguous()
+        mc_eps, tau_batch, class_weight = f32(mc_eps), f32(tau_batch), f32(class_weight)
+        floor = torch.full((K,), float(loss_cfg.nonempty_floor), device=self.device)
+        if teacher_marginal is not None:
+            floor = torch.maximum(floor, 0.9 * f32(teacher_marginal))
+        c = loss_cfg.to_c()
+        check(self.L.dof_vade_loss_eval(self.handle, ptr(self.state), ptr(x), ptr(a), B, ptr(mc_eps), ptr(tau_batch),
+                                        ptr(class_weight), ptr(floor), C.byref(c), ptr(self.logs), _stream()))
+        return self.logs
+
+    def initialize_gmm_from_data(self, data_loader, n_samples: int = 10000):
+        """``VaDEPT.initialize_gmm_from_data`` (models_new.py:1907-1947): z_mean of the first ``n_samples`` windows in
+        loader order (eval mode), a scikit-learn diagonal GaussianMixture (reg_covar 1e-4, numpy's global RNG like the
+        reference) on them, its means / log-covariances written into the latent space.  ``data_loader`` yields
+        ``(x, a, ...)`` batches.  The GMM fit is the reference's own third-party call, off the step path."""
+        from .gmm_init import gmm_from_embeddings
+        embs, got = [], 0
+        for batch in data_loader:
+            z = self.embed(batch[0], batch[1])[0]
+            embs.append(z.detach().cpu())
+            got += z.shape[0]
+            if got >= n_samples:
+                break
+        means, log_vars = gmm_from_embeddings(torch.cat(embs).numpy()[:n_samples], self.n_components)
+        with torch.no_grad():
+            self.latent_space.gmm_means.copy_(torch.from_numpy(means).float().to(self.device))
+            self.latent_space.gmm_log_vars.copy_(torch.from_numpy(log_vars).float().to(self.device))
+        return means, log_vars
+
     def adam_step(self, lr_base: float, lr_gmm: float, lr_decoder: Optional[float] = None, clip: float = 0.75,
                   grad_scale: float = 1.0, active=(True, True, True), betas=(0.9, 0.999), eps: float = 1e-8,
                   weight_decay: float = 0.0):

@@ -163,6 +163,13 @@ int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const flo
                        int B, const float* eps, const float* mc_eps, const float* tau_batch,
                        const float* class_weight, const float* floor_c, const dof_vade_loss_cfg* loss,
                        float* logs, void* stream);
+/* The step validate_one_epoch_indexed runs (deepof/clustering/training.py:190-229): the model in eval() — z = z_mean, no
+ * dropout, BatchNorm running statistics, no batch standardisation — and the criterion's terms; logs as above, no
+ * gradient, parameters and optimizer state untouched.  The handle must have been created with training=1 (the loss
+ * workspace). */
+int dof_vade_loss_eval(dof_handle* h, const float* state, const float* x, const float* a, int B, const float* mc_eps,
+                       const float* tau_batch, const float* class_weight, const float* floor_c, const dof_vade_loss_cfg* loss,
+                       float* logs, void* stream);
 int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m, float* adam_v,
                   const dof_adam_cfg* opt, void* stream);
 
@@ -241,6 +248,10 @@ int dof_vqvae_forward_eval(dof_handle* h, const float* state, const float* x, co
 int dof_vqvae_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a, int B,
                         float beta, float kmeans_weight, float* logs, void* stream);
 
+/* validation step of fit_VQVAE (training.py:1165-1170): eval-mode forward + loss terms, teacher off, no gradient */
+int dof_vqvae_loss_eval(dof_handle* h, const float* state, const float* x, const float* a, int B, float beta, float kmeans_weight,
+                        float* logs, void* stream);
+
 /* ---- distillation head of step_vqvae_distill / step_contrastive_distill -------------------------------
  * (deepof/clustering/training.py:341-370, 550-578): DiscriminativeHead (teacher_model.py:795-808) = one Linear(D, K) on
  * the encoder output (VQ-VAE: z_e; contrastive: the row-normalised z of the MAIN view, training.py:533, 556), soft cross-entropy (_soft_ce_logits,
@@ -305,6 +316,10 @@ int dof_contrastive_loss_grad(dof_handle* h, const float* state, float* grad, co
 int dof_contrastive_loss_grad_distill(dof_handle* h, const float* state, float* grad, const float* x2, const float* a2,
                                       int B, int loss_kind, int sim_kind, float temperature, float tau_plus, float beta,
                                       const dof_distill_cfg* distill, float* logs, float* z_out, void* stream);
+
+/* validation step of fit_contrastive: eval-mode encoder on both views + loss, teacher off, no gradient */
+int dof_contrastive_loss_eval(dof_handle* h, const float* state, const float* x2, const float* a2, int B, int loss_kind, int sim_kind,
+                              float temperature, float tau_plus, float beta, float* logs, float* z_out, void* stream);
 
 /* ---- transformer encoder, EVAL-mode forward -------------------------------------------------
  * TFMEncoderPT.forward with the module in eval() (deepof/clustering/models_new.py:985-1164): the embedding path
