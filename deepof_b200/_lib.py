@@ -106,6 +106,7 @@ _SIGS = {
     "dof_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(DofAdamCfg), _P]),
     "dof_encode": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
     "dof_dropout_mask_bytes": (C.c_size_t, [C.POINTER(DofConfig), C.c_int, C.c_int, C.c_int]),
+    "dof_set_noise_seed": (C.c_int, [_P, C.c_ulonglong]),
     "dof_set_dropout": (C.c_int, [_P, C.c_ulonglong, _P, C.c_size_t]),
     "dof_vqvae_forward_eval": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "dof_vqvae_loss_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P, _P]),

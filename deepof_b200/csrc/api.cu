@@ -309,6 +309,7 @@ struct dof_handle {
     unsigned long long drop_seed = 0;
     const unsigned char* drop_masks = nullptr;
     size_t drop_mask_bytes = 0;
+    unsigned long long noise_seed = 0x9E3779B97F4A7C15ull;   // Philox key of the VaDE noise when eps / mc_eps are NULL
     int device, sm_count, max_batch, training;
     int di, H1, H2, C1;
     BlockWS blk[2];
@@ -855,13 +856,14 @@ static int rec_encoder_forward(dof_handle* h, const float* state, const float* x
 }
 
 // GaussianMixtureLatentPT (models_new.py:1679-1791): latent heads, reparameterisation, GMM posterior
-static int vade_latent_forward(dof_handle* h, const float* state, int B, const float* eps, cudaStream_t st) {
+static int vade_latent_forward(dof_handle* h, const float* state, int B, const float* eps, cudaStream_t st, bool sample = false) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int D = c.D, K = c.K;
     LatentArgs la;
     la.enc = h->enc; la.Wm = state + L.Wm; la.bm = state + L.bm; la.Wv = state + L.Wv; la.bv = state + L.bv;
-    la.eps = eps; la.gmm_mu = state + L.gmm_mu; la.gmm_lv = state + L.gmm_lv; la.prior = state + L.prior;
+    la.eps = eps; la.noise_seed = (sample && !eps) ? h->noise_seed : 0ull;
+    la.gmm_mu = state + L.gmm_mu; la.gmm_lv = state + L.gmm_lv; la.prior = state + L.prior;
     la.zm = h->zm; la.pre = h->pre; la.lv = h->lv; la.z = h->z; la.q = h->q; la.B = B; la.D = D; la.K = K;
     size_t lsm = ((size_t)2 * D * D + 2 * D + 2 * (size_t)K * D + K) * 4;
     { ProfScope ps("latent_fwd", st);
@@ -1207,8 +1209,7 @@ static int vade_step(dof_handle* h, const float* state, float* grad, const float
                      const float* floor_c, const dof_vade_loss_cfg* loss, float* logs, void* stream, bool train) {
     DOF_TRY(check_batch(h, B));
     if (!h->training) DOF_FAIL(DOF_ERR_ARG, "handle was created with training=0");
-    if (!state || (train && (!grad || !eps)) || !x || !a || !loss || !logs || !floor_c) DOF_FAIL(DOF_ERR_ARG, "null argument");
-    if (!loss->pretrain_mode && !mc_eps) DOF_FAIL(DOF_ERR_ARG, "mc_eps is required in main mode");
+    if (!state || (train && !grad) || !x || !a || !loss || !logs || !floor_c) DOF_FAIL(DOF_ERR_ARG, "null argument");
     if (!loss->pretrain_mode && loss->mc_samples != 32) DOF_FAIL(DOF_ERR_UNSUPPORTED, "mc_samples must be 32, got %d", loss->mc_samples);
     if (loss->tf_cluster_weight != 0.f) DOF_FAIL(DOF_ERR_UNSUPPORTED, "tf_cluster_weight != 0 is not supported");
     if (loss->reg_scatter_weight != 0.f) DOF_FAIL(DOF_ERR_UNSUPPORTED, "reg_scatter_weight != 0 is not supported");
@@ -1219,7 +1220,7 @@ static int vade_step(dof_handle* h, const float* state, float* grad, const float
     if (train) DOF_CUDA(cudaMemsetAsync(grad, 0, (size_t)L.total * 4, st));
     if (c.model != DOF_MODEL_VADE) DOF_FAIL(DOF_ERR_ARG, "handle is not a VaDE model");
     DOF_TRY(encoder_forward(h, state, x, a, B, train, st));
-    DOF_TRY(vade_latent_forward(h, state, B, train ? eps : nullptr, st));
+    DOF_TRY(vade_latent_forward(h, state, B, train ? eps : nullptr, st, train));
     DOF_TRY(decoder_forward(h, state, h->z, x, B, train, st));
     // ---- loss
     StatsLayout SL = stats_layout(D, K);
@@ -1233,6 +1234,7 @@ static int vade_step(dof_handle* h, const float* state, float* grad, const float
     memset(&la, 0, sizeof(la));
     la.cfg = *loss;
     la.z = h->z; la.zm = h->zm; la.lv = h->lv; la.pre = h->pre; la.q = h->q; la.eps = eps; la.mc_eps = mc_eps;
+    la.noise_seed = h->noise_seed;
     la.gmm_mu = state + L.gmm_mu; la.gmm_lv = state + L.gmm_lv; la.prior = state + L.prior;
     la.tau = (loss->lambda_distill > 0.f) ? tau_batch : nullptr;
     la.class_weight = class_weight; la.floor_c = floor_c;
@@ -1298,13 +1300,15 @@ static int vq_forward(dof_handle* h, const float* state, int B, bool want_gram, 
     VqArgs v;
     v.z = h->enc; v.codebook = state + h->L.codebook; v.quant = h->quant; v.soft = h->soft; v.idx = h->vidx;
     v.stats = h->vstats; v.B = B; v.D = c.D; v.K = c.K; v.want_gram = want_gram ? 1 : 0;
-    if (c.D > VQ_MAXD) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > %d", c.D, VQ_MAXD);
+    if (c.D > VQ_MAXD || c.K > VQ_MAXK) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > %d or codebook %d > %d", c.D, VQ_MAXD, c.K, VQ_MAXK);
     DOF_CUDA(cudaMemsetAsync(h->vstats, 0, ((size_t)VQ_ST_GRAM + (size_t)c.D * c.D + c.K) * sizeof(double), st));
-    size_t smem = ((size_t)c.D * c.K + c.K + (size_t)c.D * c.D) * 4;
+    const size_t smem = vq_fwd_smem(c.D, c.K, want_gram);
+    if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "codebook %d x %d does not fit in shared memory", c.D, c.K);
     static size_t attr = 48 * 1024;
     if (smem > attr) { DOF_CUDA(cudaFuncSetAttribute(vq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    const int grid = cdiv(B, VQ_WARPS) < 2 * h->sm_count ? cdiv(B, VQ_WARPS) : 2 * h->sm_count;
     { ProfScope ps("vq_fwd", st, 0.0, (double)B * (8.0 * c.D + 4.0 + 4.0 * c.K));
-    vq_fwd_kernel<<<cdiv(B, 128), 128, smem, st>>>(v); }
+    vq_fwd_kernel<<<grid, VQ_WARPS * 32, smem, st>>>(v); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -1585,7 +1589,7 @@ int dof_latent_eval(const float* enc, const float* Wm, const float* bm, const fl
         DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
     if (K > LOSS_MAXK || D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent read-out: K=%d (<= %d), D=%d (<= 64)", K, LOSS_MAXK, D);
     LatentArgs la;
-    la.enc = enc; la.Wm = Wm; la.bm = bm; la.Wv = Wv; la.bv = bv; la.eps = nullptr; la.gmm_mu = gmm_mu; la.gmm_lv = gmm_lv; la.prior = prior;
+    la.enc = enc; la.Wm = Wm; la.bm = bm; la.Wv = Wv; la.bv = bv; la.eps = nullptr; la.noise_seed = 0ull; la.gmm_mu = gmm_mu; la.gmm_lv = gmm_lv; la.prior = prior;
     la.zm = emb; la.pre = scratch; la.lv = scratch + (size_t)B * D; la.z = scratch + (size_t)2 * B * D; la.q = q; la.B = B; la.D = D; la.K = K;
     const size_t lsm = ((size_t)2 * D * D + 2 * D + 2 * (size_t)K * D + K) * 4;
     if (lsm > 48 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent head does not fit shared memory");
@@ -1600,16 +1604,17 @@ int dof_latent_eval(const float* enc, const float* Wm, const float* bm, const fl
 int dof_vq_eval(const float* enc, const float* codebook, int B, int D, int K, float* quant, float* soft, int* idx, double* scratch,
                 void* stream) {
     if (!enc || !codebook || !quant || !soft || !idx || !scratch || B < 1) DOF_FAIL(DOF_ERR_ARG, "null / bad argument");
-    if (D > VQ_MAXD) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > %d", D, VQ_MAXD);
+    if (D > VQ_MAXD || K > VQ_MAXK) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > %d or codebook %d > %d", D, VQ_MAXD, K, VQ_MAXK);
     cudaStream_t st = (cudaStream_t)stream;
     VqArgs v;
     v.z = enc; v.codebook = codebook; v.quant = quant; v.soft = soft; v.idx = idx; v.stats = scratch; v.B = B; v.D = D; v.K = K; v.want_gram = 0;
     DOF_CUDA(cudaMemsetAsync(scratch, 0, ((size_t)VQ_ST_GRAM + (size_t)D * D + K) * sizeof(double), st));
-    const size_t smem = ((size_t)D * K + K + (size_t)D * D) * 4;
+    const size_t smem = vq_fwd_smem(D, K, false);
     if (smem > 96 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "codebook %d x %d does not fit in shared memory", D, K);
     if (smem > 48 * 1024) DOF_CUDA(cudaFuncSetAttribute(vq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    const int grid = cdiv(B, VQ_WARPS) < 2 * g_sm_count ? cdiv(B, VQ_WARPS) : 2 * g_sm_count;
     { ProfScope ps("vq_fwd", st, 0.0, (double)B * (8.0 * D + 4.0 + 4.0 * K));
-    vq_fwd_kernel<<<cdiv(B, 128), 128, smem, st>>>(v); }
+    vq_fwd_kernel<<<grid, VQ_WARPS * 32, smem, st>>>(v); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -1971,6 +1976,12 @@ size_t dof_dropout_mask_bytes(const dof_config* cfg, int Bw, int B, int dec_pass
     if (check_cfg(cfg) != DOF_OK || cfg->encoder != DOF_ENCODER_TRANSFORMER || Bw < 1 || B < 0 || dec_passes < 0 || dec_passes > 2) return 0;
     const Layout L = build_layout(*cfg);
     return drop_plan(*cfg, L, Bw, B, dec_passes).total;
+}
+
+int dof_set_noise_seed(dof_handle* h, unsigned long long seed) {
+    if (!h) DOF_FAIL(DOF_ERR_ARG, "null handle");
+    h->noise_seed = seed ? seed : 0x9E3779B97F4A7C15ull;
+    return DOF_OK;
 }
 
 int dof_set_dropout(dof_handle* h, unsigned long long seed, const unsigned char* masks, size_t mask_bytes) {

@@ -83,8 +83,38 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// ---- counter-based random numbers (Philox4x32-10): the same (seed, site, element) always gives the same number, so a
+// forward and a backward kernel regenerate identical noise and nothing is stored in HBM ---------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// standard normal number `idx` of stream (seed, site): Box-Muller on one Philox block per 4 consecutive elements
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned int site, unsigned long long idx) {
+    const unsigned long long blk = idx >> 2;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), site, 2u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t a = (idx & 2) ? r.z : r.x, b = (idx & 2) ? r.w : r.y;
+    const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;          // (0, 1]
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif((float)b * 4.656612873077393e-10f, &sn, &cs);                // angle = 2 pi b / 2^32
+    return rad * ((idx & 1) ? sn : cs);
 }

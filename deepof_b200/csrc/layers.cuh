@@ -720,13 +720,16 @@ __global__ void __launch_bounds__(128) cens_bwd_kernel(const CensArgs a) {
 struct LatentArgs {
     const float* enc;                      // [B,D]
     const float *Wm, *bm, *Wv, *bv;        // encoder_mean / encoder_log_var Linear
-    const float* eps;                      // [B,D] reparam noise, null => eval (z = z_mean)
+    const float* eps;                      // [B,D] reparam noise; null => eval (z = z_mean) unless noise_seed != 0
+    unsigned long long noise_seed;         // != 0 with eps == null: eps comes from the Philox stream (seed, DOF_SITE_EPS)
     const float *gmm_mu, *gmm_lv, *prior;  // [K,D],[K,D],[K]
     float *zm, *pre, *lv, *z, *q;          // [B,D] x4, [B,K]
     int B, D, K;
 };
 
 #define LOG_2PI_F 1.8378770664093453f
+#define DOF_SITE_EPS 201u      // Philox sites of the VaDE noise: reparameterisation eps [B,D] ...
+#define DOF_SITE_MC 200u       // ... and the Monte-Carlo KL samples [S,B,D]
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
@@ -760,7 +763,9 @@ __global__ void __launch_bounds__(64) latent_fwd_kernel(const LatentArgs a) {
             s2 = fmaf(Wv[d * D + k], ev, s2);
         }
         float lv = softplus_f(s2);
-        float zz = a.eps ? s1 + expf(0.5f * lv) * a.eps[(size_t)b * D + d] : s1;
+        float zz = s1;
+        if (a.eps) zz = s1 + expf(0.5f * lv) * a.eps[(size_t)b * D + d];
+        else if (a.noise_seed) zz = s1 + expf(0.5f * lv) * philox_normal(a.noise_seed, DOF_SITE_EPS, (unsigned long long)b * D + d);
         a.zm[(size_t)b * D + d] = s1;
         a.pre[(size_t)b * D + d] = s2;
         a.lv[(size_t)b * D + d] = lv;

@@ -78,6 +78,7 @@ struct LossArgs {
     const float *z, *zm, *lv, *pre, *q;        // [B,D]x4, [B,K]
     const float *eps;                          // [B,D] reparam noise
     const float *mc_eps;                       // [S,B,D]
+    unsigned long long noise_seed;             // eps / mc_eps == null: the Philox streams (seed, DOF_SITE_EPS / DOF_SITE_MC)
     const float *gmm_mu, *gmm_lv, *prior;
     const float *tau;                          // [B,K] tau_star rows of this batch, or null
     const float *class_weight;                 // [K] or null
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) loss_stats_kernel(const LossArg
     float* ciglv = cglv + K * D;                    // exp(-glv)
     float* clp = ciglv + K * D;                     // [K] log prior
     float* wsc = clp + K;                           // per-warp scratch
-    const int per_warp = D * 3 + K + 32 * (D + 1) + 32 * (K + 1);
+    const int per_warp = D * 3 + K + 2 * 32 * (D + 1) + 32 * (K + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* zsh = wsc + warp * per_warp;             // [D] z
     float* sqsh = zsh + D;                          // [D] exp(.5 lvc)
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) loss_stats_kernel(const LossArg
     float* qnsh = lvcsh + D;                        // [K]
     float* zs = qnsh + K;                           // [32][D+1]
     float* gam = zs + 32 * (D + 1);                 // [32][K+1]
+    float* mcn = gam + 32 * (K + 1);                // [32][D+1] Monte-Carlo noise of the window
     for (int i = threadIdx.x; i < SL.total; i += blockDim.x) acc[i] = 0.f;
     for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
         cmu[i] = __ldg(a.gmm_mu + i);
@@ -189,11 +191,13 @@ __global__ void __launch_bounds__(LS_WARPS * 32) loss_stats_kernel(const LossArg
             const int S = a.cfg.mc_samples;     // == 32 (checked on the host)
             float* myz = zs + lane * (D + 1);
             float* myg = gam + lane * (K + 1);
-            const float* me = a.mc_eps + ((size_t)lane * B + b) * D;
+            const float* me = a.mc_eps ? a.mc_eps + ((size_t)lane * B + b) * D : nullptr;
+            float* mye = mcn + lane * (D + 1);       // this sample's noise row (read twice)
             float logq = 0.f;
             for (int d = 0; d < D; d++) {
+                mye[d] = me ? me[d] : philox_normal(a.noise_seed, DOF_SITE_MC, ((unsigned long long)lane * B + b) * D + d);
                 float zmv = a.zm[(size_t)b * D + d];
-                float zv = zmv + me[d] * sqsh[d];
+                float zv = zmv + mye[d] * sqsh[d];
                 myz[d] = zv;
                 float df = zv - zmv;
                 logq += LOG_2PI_F + lvcsh[d] + df * df * expf(-lvcsh[d]);
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) loss_stats_kernel(const LossArg
                 float g = 0.f;
                 for (int c = 0; c < K; c++) g += myg[c] * (myz[d] - cmu[c * D + d]) * ciglv[c * D + d];
                 float gz = warp_sum(g);
-                float gl = warp_sum(-0.5f + 0.5f * g * me[d] * sqsh[d]);
+                float gl = warp_sum(-0.5f + 0.5f * g * mye[d] * sqsh[d]);
                 if (lane == 0) { a.dzm_kl[(size_t)b * D + d] = gz; a.dlv_kl[(size_t)b * D + d] = gl; }
             }
             __syncwarp();
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) loss_stats_kernel(const LossArg
 
 static inline size_t loss_stats_smem_floats(int D, int K) {
     StatsLayout SL = stats_layout(D, K);
-    size_t per_warp = (size_t)D * 3 + K + 32 * (D + 1) + 32 * (K + 1);
+    size_t per_warp = (size_t)D * 3 + K + 2 * 32 * (D + 1) + 32 * (K + 1);
     return (size_t)SL.total + 3 * (size_t)K * D + K + LS_WARPS * per_warp;
 }
 
@@ -564,7 +568,8 @@ __global__ void __launch_bounds__(LS_WARPS * 32) loss_grad_kernel(const LossArgs
             float pre = a.pre[(size_t)b * D + d];
             float zmv = a.zm[(size_t)b * D + d];
             float dzm = dz;
-            float dlv = dz * 0.5f * expf(0.5f * lv) * a.eps[(size_t)b * D + d];
+            const float epsv = a.eps ? a.eps[(size_t)b * D + d] : philox_normal(a.noise_seed, DOF_SITE_EPS, (unsigned long long)b * D + d);
+            float dlv = dz * 0.5f * expf(0.5f * lv) * epsv;
             dlv += actc * (lv > 0.f ? 1.f : (lv < 0.f ? -1.f : 0.f));
             const bool inclamp = (lv >= -4.f && lv <= 2.f);
             if (!main_mode) {

@@ -34,63 +34,91 @@ struct VqArgs {
     int B, D, K, want_gram;
 };
 
-// one thread per window; codebook and its column norms in shared memory
-__global__ void __launch_bounds__(128) vq_fwd_kernel(const VqArgs a) {
+// VectorQuantizerPT (models_new.py:1358-1423): one WARP per window, lanes own codes (k = lane + 32 c).  The codebook
+// [D][K] sits in shared memory so a lane's reads are conflict-free and the soft-count stores are coalesced; the nearest
+// code is a warp-min over the lanes' distances followed by a BALLOT on (distance == minimum) whose first set bit is the
+// first minimum in code order (argmin keeps the first one).  Gram sums for the k-means term accumulate in a per-warp
+// shared tile without atomics (one owner lane per entry) and are folded once per CTA.
+#define VQ_WARPS 8
+#define VQ_MAXK 256
+__global__ void __launch_bounds__(VQ_WARPS * 32) vq_fwd_kernel(const VqArgs a) {
     extern __shared__ float vsm[];
-    float* cb = vsm;                  // [D][K]
-    float* ee = cb + a.D * a.K;       // [K]
-    float* gram = ee + a.K;           // [D][D] block partial (want_gram)
-    const int D = a.D, K = a.K, tid = threadIdx.x;
+    const int D = a.D, K = a.K, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* cb = vsm;                        // [D][K]
+    float* ee = cb + D * K;                 // [K]
+    float* zs = ee + K;                     // [VQ_WARPS][D]
+    float* gram = zs + VQ_WARPS * D;        // [VQ_WARPS][D*D] (want_gram)
     for (int i = tid; i < D * K; i += blockDim.x) cb[i] = __ldg(a.codebook + i);
-    if (a.want_gram) for (int i = tid; i < D * D; i += blockDim.x) gram[i] = 0.f;
+    if (a.want_gram) for (int i = tid; i < VQ_WARPS * D * D; i += blockDim.x) gram[i] = 0.f;
     __syncthreads();
     for (int k = tid; k < K; k += blockDim.x) {
         float s = 0.f;
-        for (int d = 0; d < D; d++) s += cb[d * K + k] * cb[d * K + k];
+        for (int d = 0; d < D; d++) s = fmaf(cb[d * K + k], cb[d * K + k], s);
         ee[k] = s;
     }
     __syncthreads();
-    const int b = blockIdx.x * blockDim.x + tid;
+    float* z = zs + warp * D;
+    float* gw = gram + (size_t)warp * D * D;
     double sq = 0.0;
-    float z[VQ_MAXD];
-    if (b < a.B) {
+    const int nchunk = (K + 31) >> 5;
+    for (int b = blockIdx.x * VQ_WARPS + warp; b < a.B; b += gridDim.x * VQ_WARPS) {
         float zz = 0.f;
-#pragma unroll 4
-        for (int d = 0; d < D; d++) { z[d] = __ldg(a.z + (size_t)b * D + d); zz += z[d] * z[d]; }
-        int best = 0;
-        float bestd = INFINITY, ssum = 0.f;
-        for (int k = 0; k < K; k++) {
-            float dot = 0.f;
-            for (int d = 0; d < D; d++) dot += z[d] * cb[d * K + k];
-            const float dist = zz + ee[k] - 2.f * dot;                    // models_new.py:1407-1411
-            if (dist < bestd) { bestd = dist; best = k; }                 // argmin keeps the first minimum
-            const float inv = 1.f / dist;
-            ssum += inv * inv;                                            // :1416
+        for (int d = lane; d < D; d += 32) { const float v = __ldg(a.z + (size_t)b * D + d); z[d] = v; zz = fmaf(v, v, zz); }
+        zz = warp_sum(zz);
+        __syncwarp();
+        float dist[VQ_MAXK / 32];
+        float mn = INFINITY, ssum = 0.f;
+#pragma unroll
+        for (int c = 0; c < VQ_MAXK / 32; c++) {
+            dist[c] = INFINITY;
+            const int k = lane + 32 * c;
+            if (c < nchunk && k < K) {
+                float dot = 0.f;
+                for (int d = 0; d < D; d++) dot = fmaf(z[d], cb[d * K + k], dot);
+                dist[c] = zz + ee[k] - 2.f * dot;                         // models_new.py:1407-1411
+                mn = fminf(mn, dist[c]);
+                const float inv = 1.f / dist[c];
+                ssum = fmaf(inv, inv, ssum);                              // :1416
+            }
         }
-        for (int k = 0; k < K; k++) {
-            float dot = 0.f;
-            for (int d = 0; d < D; d++) dot += z[d] * cb[d * K + k];
-            const float inv = 1.f / (zz + ee[k] - 2.f * dot);
-            a.soft[(size_t)b * K + k] = inv * inv / ssum;
+        mn = warp_min(mn);
+        ssum = warp_sum(ssum);
+        int best = -1;
+#pragma unroll
+        for (int c = 0; c < VQ_MAXK / 32; c++) {
+            const unsigned hit = __ballot_sync(0xffffffffu, dist[c] == mn);
+            if (best < 0 && hit) best = 32 * c + __ffs(hit) - 1;         // first minimum in code order
+            const int k = lane + 32 * c;
+            if (c < nchunk && k < K) { const float inv = 1.f / dist[c]; a.soft[(size_t)b * K + k] = inv * inv / ssum; }
         }
-        a.idx[b] = best;
-        for (int d = 0; d < D; d++) {
+        if (lane == 0) {
+            a.idx[b] = best;
+            a.stats[VQ_ST_GRAM + D * D + best] = 1.0;                     // benign race: all writers store 1
+        }
+        for (int d = lane; d < D; d += 32) {
             const float q = cb[d * K + best];
             a.quant[(size_t)b * D + d] = q;
             const float df = q - z[d];
             sq += (double)(df * df);
         }
-        a.stats[VQ_ST_GRAM + D * D + best] = 1.0;                         // benign race: all writers store 1
         if (a.want_gram)
-            for (int i = 0; i < D; i++)
-                for (int j = 0; j < D; j++) atomicAdd(gram + i * D + j, z[i] * z[j]);
+            for (int e = lane; e < D * D; e += 32) gw[e] = fmaf(z[e / D], z[e % D], gw[e]);
+        __syncwarp();
     }
     sq = warp_sum_d(sq);
-    if ((tid & 31) == 0 && sq != 0.0) atomicAdd(a.stats + VQ_ST_SQ, sq);
+    if (lane == 0 && sq != 0.0) atomicAdd(a.stats + VQ_ST_SQ, sq);
     if (a.want_gram) {
         __syncthreads();
-        for (int i = tid; i < D * D; i += blockDim.x) atomicAdd(a.stats + VQ_ST_GRAM + i, (double)gram[i]);
+        for (int i = tid; i < D * D; i += blockDim.x) {
+            float s = 0.f;
+            for (int w = 0; w < VQ_WARPS; w++) s += gram[(size_t)w * D * D + i];
+            atomicAdd(a.stats + VQ_ST_GRAM + i, (double)s);
+        }
     }
+}
+
+static inline size_t vq_fwd_smem(int D, int K, bool gram) {
+    return ((size_t)D * K + K + (size_t)VQ_WARPS * D + (gram ? (size_t)VQ_WARPS * D * D : 0)) * 4;
 }
 
 __global__ void vq_codebook_grad_kernel(const float* __restrict__ dquant, const int* __restrict__ idx, float* __restrict__ gcb,

@@ -21,17 +21,6 @@ struct DropSite {
 
 static inline DropSite drop_none() { DropSite d; d.keep = nullptr; d.seed = 0; d.site = 0; d.rate = 0.f; return d; }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
 // multipliers (0 or 1/(1-rate)) of the 4 consecutive elements idx4 .. idx4+3 (idx4 % 4 == 0)
 __device__ __forceinline__ void drop_mul4(const DropSite& d, unsigned long long idx4, float (&m)[4]) {
     if (d.rate <= 0.f) { m[0] = m[1] = m[2] = m[3] = 1.f; return; }

@@ -404,12 +404,12 @@ class VaDEB200:
         x, a = self._prep(x, a)
         B = x.shape[0]
         D, K = self.latent_dim, self.n_components
-        if eps is None:
-            eps = torch.randn(B, D, device=self.device)
-        if mc_eps is None and not loss_cfg.pretrain_mode:
-            mc_eps = torch.randn(loss_cfg.mc_samples, B, D, device=self.device)
+        # eps / mc_eps None: the kernels draw the noise themselves (Philox, keyed per step) — nothing is materialised
         f32 = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).to(self.device).contiguous()
         eps, mc_eps, tau_batch, class_weight = f32(eps), f32(mc_eps), f32(tau_batch), f32(class_weight)
+        if eps is None or (mc_eps is None and not loss_cfg.pretrain_mode):
+            self._noise_step = getattr(self, "_noise_step", 0) + 1
+            check(self.L.dof_set_noise_seed(self.handle, ((self._drop_seed + 1) * 0xD1B54A32D192ED03 + self._noise_step) & 0xFFFFFFFFFFFFFFFF))
         floor = torch.full((K,), float(loss_cfg.nonempty_floor), device=self.device)
         if teacher_marginal is not None:   # reference losses.py:672-678
             floor = torch.maximum(floor, 0.9 * f32(teacher_marginal))
@@ -429,10 +429,11 @@ class VaDEB200:
         x, a = self._prep(x, a)
         B = x.shape[0]
         D, K = self.latent_dim, self.n_components
-        if mc_eps is None and not loss_cfg.pretrain_mode:
-            mc_eps = torch.randn(loss_cfg.mc_samples, B, D, device=self.device)
         f32 = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).to(self.device).contiguous()
         mc_eps, tau_batch, class_weight = f32(mc_eps), f32(tau_batch), f32(class_weight)
+        if mc_eps is None and not loss_cfg.pretrain_mode:
+            self._noise_step = getattr(self, "_noise_step", 0) + 1
+            check(self.L.dof_set_noise_seed(self.handle, ((self._drop_seed + 1) * 0xD1B54A32D192ED03 + self._noise_step) & 0xFFFFFFFFFFFFFFFF))
         floor = torch.full((K,), float(loss_cfg.nonempty_floor), device=self.device)
         if teacher_marginal is not None:
             floor = torch.maximum(floor, 0.9 * f32(teacher_marginal))

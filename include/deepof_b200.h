@@ -156,7 +156,10 @@ int dof_vade_forward_eval(dof_handle* h, const float* state, const float* x, con
  *                       (deepof/clustering/training.py:231-309, 159-163)
  * dof_clip_adam       = clip_grad_value_(0.75) + optimizer.step()  (training.py:164-166)
  * grad is overwritten (zeroed first).  eps [B,D] is the reparameterisation noise, mc_eps
- * [32,B,D] the Monte-Carlo KL noise (main mode only; may be NULL in pretrain mode),
+ * [32,B,D] the Monte-Carlo KL noise (main mode only).  Either may be NULL: the kernels then draw
+ * it themselves from a counter-based Philox4x32-10 stream (standard normal by Box-Muller) keyed by
+ * dof_set_noise_seed — nothing is materialised in HBM; pass explicit tensors to reproduce a
+ * reference run (parity tests).
  * tau_batch [B,K] = tau_star[batch_indices] or NULL, class_weight [K] or NULL,
  * floor_c [K] = per-cluster non-empty floor (losses.py:672-680). */
 int dof_vade_loss_grad(dof_handle* h, const float* state, float* grad, const float* x, const float* a,
@@ -233,6 +236,9 @@ int dof_encode(dof_handle* h, const float* state, const float* x, const float* a
  * BatchNorm running statistics (BatchNorm1dKerasFP32, models_new.py:508-516) are updated by dof_clip_adam from the
  * batch statistics of the preceding *_loss_grad call (rank-local, as under the reference's DDP with
  * broadcast_buffers=False). */
+/* Philox key of the in-kernel VaDE noise (eps, MC-KL samples) used when the noise pointers are NULL; callers advance
+ * it every step.  0 selects the default key. */
+int dof_set_noise_seed(dof_handle* h, unsigned long long seed);
 size_t dof_dropout_mask_bytes(const dof_config* cfg, int Bw, int B, int dec_passes);
 int dof_set_dropout(dof_handle* h, unsigned long long seed, const unsigned char* masks, size_t mask_bytes);
 

@@ -182,6 +182,55 @@ def test_eval_and_step_vs_oracle(T, N, D, K, B, pad):
         assert not bad and fr < 2e-4, (phase, fr, bad)
 
 
+@pytest.mark.parametrize("phase", ["main", "pretrain"])
+def test_full_size_step_vs_oracle(phase):
+    """BASELINE cfg2 at the benchmarked size — B = 4096 windows in ONE step, every default batch-level term of the phase
+    on (main: MC-KL S = 32, non-empty floor; pretrain: Gram-SVD k-means loss, repel between soft centroids, non-empty
+    floor) — directly against the CPU oracle: 13 logs (1e-4), flat gradient (2e-4), eval embeddings / q (1e-4) and the
+    argmax flip count over all 4096 windows (flips only inside numerical ties)."""
+    from deepof_b200 import VaDEB200, VadeLossCfg
+    O.USE_ATEN_GRU = True                      # the reference's nn.GRU kernels: the python-loop GRU of the oracle is 20x slower
+    try:
+        T, N, D, K, B = 25, 14, 16, 8, 4096
+        adj, E, x, a = _oracle_case(T, N, D, K, B, seed=4096)
+        m = VaDEB200((T, N, 3), (T, E, 1), adj, D, K, max_batch=B, training=True, seed=21)
+        with torch.no_grad():
+            m.latent_space.gmm_means.mul_(3.0)
+        p = {k: v.cpu() for k, v in m.state_dict().items()}
+        graph = O.graph_operators(adj)
+        gen = torch.Generator().manual_seed(6)
+        eps, mc = torch.randn(B, D, generator=gen), torch.randn(32, B, D, generator=gen)
+        if phase == "main":
+            cfg, ocfg = VadeLossCfg.main_defaults(K, 0.8), O.LossCfg.main_defaults(K, 0.8)
+        else:
+            cfg, ocfg = VadeLossCfg.pretrain_defaults(K, 0.15), O.LossCfg.pretrain_defaults(K, 0.15)
+            m.set_pretrain_mode(True)
+            p = {k: v.cpu() for k, v in m.state_dict().items()}
+        m.loss_grad(x, a, cfg, eps=eps, mc_eps=mc)
+        logs = m.logs_dict()
+        ologs, ograds, _ = O.train_step(x, a, p, graph, D, ocfg, eps=eps, mc_eps=mc)
+        for k, v in ologs.items():
+            assert abs(logs[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, logs[k], v)
+        gd = m.grad_dict()
+        names = [k for k, gv in ograds.items() if gv is not None]
+        fr = rel_l2(torch.cat([gd[k].cpu().flatten() for k in names]), torch.cat([ograds[k].flatten() for k in names]))
+        print(phase, "B=4096 flat grad rel-L2", fr)
+        assert fr < 2e-4, fr
+        if phase == "main":
+            enc, emb, q, _ = m.forward_eval(x, a, want_loc=False)
+            with torch.no_grad():
+                ref = O.vade_forward(x, a, p, graph, D, training=False)
+            assert rel_l2(emb.cpu(), ref["z"]) < 1e-4 and rel_l2(q.cpu(), ref["q"]) < 1e-4
+            flips = q.cpu().argmax(1) != ref["q"].argmax(1)
+            top2 = ref["q"].topk(2, dim=1).values
+            margin = top2[:, 0] - top2[:, 1]
+            print("argmax(q) flips at B=4096 (unconstrained data):", int(flips.sum()), "of", B,
+                  "; smallest reference top-2 margin:", float(margin.min()))
+            assert bool((margin[flips] < 1e-4).all())
+    finally:
+        O.USE_ATEN_GRU = False
+
+
 def test_batch_chunking_and_determinism():
     from deepof_b200 import VaDEB200
     T, N, D, K, B = 25, 14, 16, 8, 70
@@ -246,3 +295,36 @@ def test_errors_are_loud():
     cfg.tf_cluster_weight = 1.0
     with pytest.raises(DofError):
         m3.loss_grad(x[:4], a[:4], cfg)
+
+
+def test_in_kernel_philox_noise():
+    """eps / mc_eps = None: the kernels draw the reparameterisation noise and the 32 Monte-Carlo samples from the
+    counter-based Philox stream (nothing materialised).  The recovered eps = (z - z_mean) / exp(lv / 2) is standard
+    normal, changes with the step, and forward / backward use the SAME noise: the step equals the step with that eps fed
+    back explicitly (MC noise pinned by feeding explicit samples to both)."""
+    from deepof_b200 import VaDEB200, VadeLossCfg
+    T, N, D, K, B = 25, 14, 16, 8, 2048
+    adj, E, x, a = _oracle_case(T, N, D, K, B, seed=77)
+    m = VaDEB200((T, N, 3), (T, E, 1), adj, D, K, max_batch=B, training=True, seed=5)
+    cfg = VadeLossCfg.main_defaults(K, 0.8)
+    mc = torch.randn(32, B, D, generator=torch.Generator().manual_seed(1))
+
+    def eps_of_step():
+        z, zm, lv = m.debug("z").view(B, D), m.debug("z_mean").view(B, D), m.debug("z_log_var").view(B, D)
+        return ((z - zm) / torch.exp(0.5 * lv)).cpu()
+
+    m.loss_grad(x, a, cfg, mc_eps=mc)                      # eps from Philox
+    e1, g1, l1 = eps_of_step(), m.grad.clone(), m.logs_dict()
+    m.loss_grad(x, a, cfg, mc_eps=mc)
+    e2 = eps_of_step()
+    assert abs(float(e1.mean())) < 0.02 and abs(float(e1.std()) - 1.0) < 0.02
+    assert abs(float((e1 ** 4).mean()) - 3.0) < 0.15        # kurtosis of a normal
+    assert float((e1 - e2).abs().mean()) > 0.5              # a new stream every step
+    m.loss_grad(x, a, cfg, eps=e1, mc_eps=mc)               # same noise, explicit
+    l3 = m.logs_dict()
+    for k in l1:
+        assert abs(l1[k] - l3[k]) <= 2e-5 * max(1.0, abs(l1[k])), (k, l1[k], l3[k])
+    assert rel_l2(m.grad.cpu(), g1.cpu()) < 2e-4            # eps recovered through exp / division: ~1e-6 relative
+    m.loss_grad(x, a, cfg)                                  # MC noise from Philox too
+    lm = m.logs_dict()
+    assert np.isfinite(lm["total_loss"]) and abs(lm["kl_div"] - l1["kl_div"]) < 0.05 * max(1.0, abs(l1["kl_div"]))
