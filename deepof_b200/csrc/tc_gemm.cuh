@@ -698,12 +698,21 @@ static int launch_gemm_wgrad_tc(const WGradArgs* gs, int nbatch, cudaStream_t st
 // dispatch: tensor-core path when every problem of the batch is eligible, SIMT otherwise
 // ---------------------------------------------------------------------------
 static int g_sm_count = 148;
+static bool tc_big_eligible(const GemmArgs& g);                                  // tc_gemm_big.cuh
+static int launch_gemm_big_tc(const GemmArgs& g, cudaStream_t st, int sm_count);
 
 static int launch_gemm_rows(const GemmArgs* gs, int nbatch, cudaStream_t st) {
     bool tc = tc_enabled();
     for (int i = 0; i < nbatch && tc; i++)
         tc = tc_rows_eligible(gs[i]) && gs[i].N == gs[0].N && gs[i].K == gs[0].K;
     if (tc) return launch_gemm_rows_tc(gs, nbatch, st, g_sm_count);
+    // shapes whose weights do not fit the weight-resident kernel: both operands streamed (tc_gemm_big.cuh)
+    bool big = tc_enabled();
+    for (int i = 0; i < nbatch && big; i++) big = tc_big_eligible(gs[i]);
+    if (big) {
+        for (int i = 0; i < nbatch; i++) DOF_TRY(launch_gemm_big_tc(gs[i], st, g_sm_count));
+        return DOF_OK;
+    }
     bool any2 = false;
     for (int i = 0; i < nbatch; i++) any2 = any2 || gs[i].nkb == 2;
     if (!any2) return launch_gemm_rows_simt(gs, nbatch, st);
@@ -726,3 +735,5 @@ static int launch_gemm_wgrad(const WGradArgs* gs, int nbatch, cudaStream_t st, i
     if (tc) return launch_gemm_wgrad_tc(gs, nbatch, st, sm_count);
     return launch_gemm_wgrad_simt(gs, nbatch, st, sm_count);
 }
+
+#include "tc_gemm_big.cuh"

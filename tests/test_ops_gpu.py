@@ -37,7 +37,10 @@ def rnd(*shape, seed=0):
 
 
 @pytest.mark.parametrize("M,N,K,wT", [(1000, 96, 32, 0), (777, 48, 64, 0), (300, 16, 448, 0), (515, 18, 12, 0),
-                                      (640, 224, 16, 1), (129, 32, 96, 1), (4096, 42, 32, 0), (50, 6, 6, 1)])
+                                      (640, 224, 16, 1), (129, 32, 96, 1), (4096, 42, 32, 0), (50, 6, 6, 1),
+                                      # both operands streamed (tc_gemm_big.cuh): K > 128 / weights too large to stay resident
+                                      (4096, 256, 256, 0), (2304, 200, 160, 1), (4096, 128, 1792, 0), (3000, 36, 264, 1),
+                                      (2500, 768, 256, 0), (5000, 300, 44, 1)])
 def test_gemm_rows_plain(L, M, N, K, wT):
     A = rnd(M, K, seed=1)
     W = rnd(N, K, seed=2) if wT == 0 else rnd(K, N, seed=2)
@@ -47,7 +50,8 @@ def test_gemm_rows_plain(L, M, N, K, wT):
                               None, S())
     assert rc == 0, L.dof_last_error()
     ref = A.double() @ (W.double().t() if wT == 0 else W.double()) + bias.double()
-    assert rel(Cout, ref) < 2e-6
+    tol = 2e-6 if K <= 128 else 4e-6           # fp32 accumulation over a longer K
+    assert rel(Cout, ref) < tol
     # relu + accumulate + mask
     C2 = rnd(M, N, seed=4)
     base = C2.clone()
@@ -56,7 +60,7 @@ def test_gemm_rows_plain(L, M, N, K, wT):
                               P(mask), S())
     assert rc == 0
     ref2 = torch.relu(ref + base.double()) * (mask > 0)
-    assert rel(C2, ref2) < 2e-6
+    assert rel(C2, ref2) < tol
 
 
 def test_gemm_rows_views(L):
