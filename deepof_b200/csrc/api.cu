@@ -12,6 +12,7 @@
 #include "gru_tc.cuh"
 #include "gru_bwd_tc.cuh"
 #include "gru_wgrad_tc.cuh"
+#include "gru_bwdw_tc.cuh"
 #include "layers.cuh"
 #include "loss.cuh"
 #include "loader.cuh"
@@ -989,11 +990,28 @@ static int gru_param_grads(dof_handle* h, const GruP& g, float* grad, const floa
 }
 
 // BPTT of one bidirectional GRU layer -> dG[dir] (and, on the fused path, the input gradient dX).  Returns through
-// *dx_done whether dX has been produced (otherwise gru_param_grads runs the input-gradient GEMM).
+// *dx_done whether dX has been produced (otherwise gru_param_grads runs the input-gradient GEMM) and through *w_done
+// whether the four parameter gradients have been accumulated as well (second-generation fused kernel, gru_bwdw_tc.cuh:
+// dG never reaches HBM; taken when the layer input changes per step and `grad` is given).
 static int gru_layer_backward(const float* state, const GruP& g, int S, int T, int I, int H, const int* len, const float* Hout,
                               float* const Gt[2], const float* dOut, const float* dHn, float* const dG[2], float* dX,
-                              const float* dXmask, bool* dx_done, cudaStream_t st) {
+                              const float* dXmask, bool* dx_done, cudaStream_t st, const float* X = nullptr, long long x_ss = 0,
+                              int x_st = 0, float* grad = nullptr, bool* w_done = nullptr) {
     *dx_done = false;
+    if (w_done) *w_done = false;
+    if (w_done && grad && X && x_st != 0 && dX && gru_bwdw_tc_eligible(H, I)) {
+        GruBwdwArgs b;
+        memset(&b, 0, sizeof(b));
+        for (int d = 0; d < 2; d++) {
+            b.Whh[d] = state + g.w_hh[d]; b.Wih[d] = state + g.w_ih[d]; b.GtT[d] = Gt[d];
+            b.dWih[d] = grad + g.w_ih[d]; b.dWhh[d] = grad + g.w_hh[d]; b.dbih[d] = grad + g.b_ih[d]; b.dbhh[d] = grad + g.b_hh[d];
+        }
+        b.len = len; b.X = X; b.x_ss = x_ss; b.x_st = x_st; b.Hout = Hout; b.dOut = dOut; b.dHn = dHn; b.dX = dX; b.dXmask = dXmask;
+        b.S = S; b.T = T; b.H = H; b.I = I;
+        DOF_CUDA(cudaMemsetAsync(dX, 0, (size_t)S * T * I * 4, st));
+        *dx_done = true; *w_done = true;
+        return launch_gru_bwdw_tc(b, st);
+    }
     if (gru_bwd_tc_eligible(H, I)) {
         GruBwdTcArgs b;
         memset(&b, 0, sizeof(b));
@@ -1041,9 +1059,12 @@ static int rec_decoder_backward(dof_handle* h, const float* state, float* grad, 
     DOF_TRY(launch_gemm_rows(&g1, 1, st));
     DOF_TRY(ln_bwd(h->dYD2, h->HD2, h->muD2, h->rsD2, state + L.dn2w, h->dHD2, grad + L.dn2w, grad + L.dn2b, M, 4 * D, 0, sm, st));
     bool dxd = false;
-    DOF_TRY(gru_layer_backward(state, L.dg2, B, T, 2 * D, 2 * D, h->lenD, h->HD2, h->GtD2, h->dHD2, nullptr, h->dGD2, h->dYD1, nullptr, &dxd, st));
-    DOF_TRY(gru_param_grads(h, L.dg2, grad, state, h->dGD2, mv_plain(h->YD1, 2 * D), M, h->dGD2, h->HD2, M, T, 2 * D, 2 * D,
-                            dxd ? nullptr : h->dYD1, nullptr, st));
+    bool wd = false;
+    DOF_TRY(gru_layer_backward(state, L.dg2, B, T, 2 * D, 2 * D, h->lenD, h->HD2, h->GtD2, h->dHD2, nullptr, h->dGD2, h->dYD1, nullptr, &dxd, st,
+                               h->YD1, (long long)T * 2 * D, 2 * D, grad, &wd));
+    if (!wd)
+        DOF_TRY(gru_param_grads(h, L.dg2, grad, state, h->dGD2, mv_plain(h->YD1, 2 * D), M, h->dGD2, h->HD2, M, T, 2 * D, 2 * D,
+                                dxd ? nullptr : h->dYD1, nullptr, st));
     DOF_TRY(ln_bwd(h->dYD1, h->HD1, h->muD1, h->rsD1, state + L.dn1w, h->dHD1, grad + L.dn1w, grad + L.dn1b, M, 2 * D, 0, sm, st));
     // the decoder's first GRU sees the SAME input (z) at every step: its input gradient is the sum over time and
     // stays on the GEMM path below (dGs), only dG comes from the fused kernel
@@ -1071,12 +1092,17 @@ static int enc_block_backward(dof_handle* h, int bi, const float* state, float* 
     }
     DOF_TRY(ln_bwd(w.dY2, w.Hn, w.mu2, w.rs2, state + P.n2w, w.dHn, grad + P.n2w, grad + P.n2b, S, 2 * H2, 0, sm, st));
     bool dxd = false;
-    DOF_TRY(gru_layer_backward(state, P.g2, S, T, 2 * H1, H2, w.len, w.H2, w.Gt2, nullptr, w.dHn, w.dG2, w.dY1, nullptr, &dxd, st));
-    DOF_TRY(gru_param_grads(h, P.g2, grad, state, w.dG2, mv_plain(w.Y1, 2 * H1), M, w.dG2, w.H2, M, T, 2 * H1, H2,
-                            dxd ? nullptr : w.dY1, nullptr, st));
+    bool wd = false;
+    DOF_TRY(gru_layer_backward(state, P.g2, S, T, 2 * H1, H2, w.len, w.H2, w.Gt2, nullptr, w.dHn, w.dG2, w.dY1, nullptr, &dxd, st,
+                               w.Y1, (long long)T * 2 * H1, 2 * H1, grad, &wd));
+    if (!wd)
+        DOF_TRY(gru_param_grads(h, P.g2, grad, state, w.dG2, mv_plain(w.Y1, 2 * H1), M, w.dG2, w.H2, M, T, 2 * H1, H2,
+                                dxd ? nullptr : w.dY1, nullptr, st));
     DOF_TRY(ln_bwd(w.dY1, w.H1, w.mu1, w.rs1, state + P.n1w, w.dH1, grad + P.n1w, grad + P.n1b, M, 2 * H1, 0, sm, st));
-    DOF_TRY(gru_layer_backward(state, P.g1, S, T, C1, H1, w.len, w.H1, w.Gt1, w.dH1, nullptr, w.dG1, w.dCv, w.Cv, &dxd, st));
-    DOF_TRY(gru_param_grads(h, P.g1, grad, state, w.dG1, mv_plain(w.Cv, C1), M, w.dG1, w.H1, M, T, C1, H1, dxd ? nullptr : w.dCv, w.Cv, st));
+    DOF_TRY(gru_layer_backward(state, P.g1, S, T, C1, H1, w.len, w.H1, w.Gt1, w.dH1, nullptr, w.dG1, w.dCv, w.Cv, &dxd, st,
+                               w.Cv, (long long)T * C1, C1, grad, &wd));
+    if (!wd)
+        DOF_TRY(gru_param_grads(h, P.g1, grad, state, w.dG1, mv_plain(w.Cv, C1), M, w.dG1, w.H1, M, T, C1, H1, dxd ? nullptr : w.dCv, w.Cv, st));
     if (C1 * w.Fin <= 256) {
         ConvWgradArgs ca;
         ca.dCv = w.dCv; ca.Xs = w.Xs; ca.dW = grad + P.conv; ca.S = S; ca.T = T; ca.C = C1; ca.F = w.Fin;
@@ -2227,6 +2253,25 @@ int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* 
     b.len = len; b.Hout = hout; b.dOut = dout; b.dHn = dhn; b.dX = dx; b.dXmask = dxmask; b.S = S; b.T = T; b.H = H; b.I = I;
     if (dx) DOF_CUDA(cudaMemsetAsync(dx, 0, (size_t)S * T * I * 4, (cudaStream_t)stream));
     return launch_gru_bwd_tc(b, (cudaStream_t)stream);
+}
+
+// second-generation fused backward: BPTT + dX + the four parameter gradients of both directions in one kernel.
+// out = per direction [dW_ih (3H x I) | dW_hh (3H x H) | db_ih (3H) | db_hh (3H)], accumulated into (zero it first)
+int dof_test_gru_layer_bwdw(const float* X, const float* const* w8, const int* len, const float* hout, const float* gtT_f,
+                            const float* gtT_b, const float* dout, const float* dhn, float* dx, const float* dxmask, float* out,
+                            int S, int T, int H, int I, void* stream) {
+    if (!gru_bwdw_tc_eligible(H, I)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "shape H=%d I=%d is not eligible for the fused GRU backward + weight-gradient kernel", H, I);
+    GruBwdwArgs b;
+    memset(&b, 0, sizeof(b));
+    const size_t per = (size_t)3 * H * I + (size_t)3 * H * H + 6 * H;
+    for (int d = 0; d < 2; d++) {
+        b.Wih[d] = w8[d]; b.Whh[d] = w8[2 + d];
+        b.dWih[d] = out + d * per; b.dWhh[d] = b.dWih[d] + 3 * H * I; b.dbih[d] = b.dWhh[d] + 3 * H * H; b.dbhh[d] = b.dbih[d] + 3 * H;
+    }
+    b.GtT[0] = gtT_f; b.GtT[1] = gtT_b; b.X = X; b.x_ss = (long long)T * I; b.x_st = I;
+    b.len = len; b.Hout = hout; b.dOut = dout; b.dHn = dhn; b.dX = dx; b.dXmask = dxmask; b.S = S; b.T = T; b.H = H; b.I = I;
+    DOF_CUDA(cudaMemsetAsync(dx, 0, (size_t)S * T * I * 4, (cudaStream_t)stream));
+    return launch_gru_bwdw_tc(b, (cudaStream_t)stream);
 }
 
 // test hook: the encoder alone in TRAIN mode, backward from a given d(loss)/d(encoder output) (any model kind, any

@@ -411,6 +411,13 @@ int dof_test_gru_layer_fwd(const float* X, long long x_ss, int x_st, const float
 int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* hout, const float* gtT_f,
                            const float* gtT_b, const float* dout, const float* dhn, float* dg_f, float* dg_b, float* dx,
                            const float* dxmask, int S, int T, int H, int I, void* stream);
+/* second-generation fused backward (gru_bwdw_tc.cuh): BPTT + input gradient + the four parameter gradients of both
+ * directions in ONE kernel (the gate gradients never reach HBM).  X [S,T,I] layer input; gates tiled as above; dx [S,T,I]
+ * (required); out (zeroed by the caller, accumulated into) laid out like dof_test_gru_wgrad's.  Replaces autograd of
+ * torch.nn.GRU (deepof/clustering/models_new.py:217-278, 326-373). */
+int dof_test_gru_layer_bwdw(const float* X, const float* const* w8, const int* len, const float* hout, const float* gtT_f,
+                            const float* gtT_b, const float* dout, const float* dhn, float* dx, const float* dxmask,
+                            float* out, int S, int T, int H, int I, void* stream);
 /* merged GRU parameter gradients (gru_wgrad_tc.cuh): dg_f / dg_b [M,4H] = [dr, dz, dn*r, dn], x [M,I] (pitch ldx),
  * hout [M,2H]; out (zeroed by the caller, accumulated into) = per direction dW_ih [3H,I] | dW_hh [3H,H] | db_ih [3H] |
  * db_hh [3H].  Returns DOF_ERR_UNSUPPORTED when the shape is not eligible for the tensor-core kernel. */

@@ -50,7 +50,8 @@ def test_gemm_rows_plain(L, M, N, K, wT):
                               None, S())
     assert rc == 0, L.dof_last_error()
     ref = A.double() @ (W.double().t() if wT == 0 else W.double()) + bias.double()
-    tol = 2e-6 if K <= 128 else 4e-6           # fp32 accumulation over a longer K
+    # the TMEM accumulator TRUNCATES on every tcgen05.mma accumulate (3 per 8 columns of K): the error grows linearly with K
+    tol = 2e-6 if K <= 128 else max(4e-6, 1e-8 * K)
     assert rel(Cout, ref) < tol
     # relu + accumulate + mask
     C2 = rnd(M, N, seed=4)
@@ -364,6 +365,60 @@ def test_gru_fused_tc_backward(L, S_, T, I, H, packed, final_only, mask):
         dx_ref = dx_ref * (mk > 0)
     print("fused bwd dX", rel(dx, dx_ref))
     assert rel(dx, dx_ref) < 1e-5
+
+
+@pytest.mark.parametrize("S_,T,I,H,packed,final_only,mask,off", [(300, 25, 32, 32, False, False, True, 0), (1000, 25, 64, 16, True, True, False, 0),
+                                                                  (257, 7, 32, 32, True, False, False, 1), (130, 24, 16, 16, True, False, False, 0),
+                                                                  (113, 25, 32, 16, False, False, False, 3), (4000, 25, 32, 32, True, False, True, 0)])
+def test_gru_fused_backward_with_weight_gradients(L, S_, T, I, H, packed, final_only, mask, off):
+    """Second-generation fused backward (gru_bwdw_tc.cuh: BPTT + dX + the four parameter gradients in one kernel, dG never
+    in HBM) vs the fp64 autograd of the oracle's GRU fed with the same inputs."""
+    dev = "cuda"
+    X = rnd(S_, T, I, seed=80)
+    k = 1.0 / H ** 0.5
+    names = ["weight_ih_l0", "weight_ih_l0_reverse", "weight_hh_l0", "weight_hh_l0_reverse", "bias_ih_l0", "bias_ih_l0_reverse",
+             "bias_hh_l0", "bias_hh_l0_reverse"]
+    prm = {n: rnd(*((3 * H, I) if "weight_ih" in n else (3 * H, H) if "weight_hh" in n else (3 * H,)), seed=81 + i) * k for i, n in enumerate(names)}
+    w8 = (C.c_void_p * 8)(*[prm[n].data_ptr() for n in names])
+    if packed:
+        g = torch.Generator().manual_seed(3)
+        lens = torch.randint(0, T + 1, (S_,), generator=g)
+        lens[0], lens[1], lens[2] = 0, 1, T
+        len_t = lens.to(dev).int()
+    else:
+        len_t = torch.full((S_,), T, dtype=torch.int32, device=dev)
+    Sp = (S_ + 127) // 128 * 128
+    hout = torch.zeros(S_, T, 2 * H, device=dev)
+    hn = torch.zeros(S_, 2 * H, device=dev)
+    gt_ti = [torch.zeros(Sp * T * 4 * H, device=dev) for _ in range(2)]
+    check_rc(L, L.dof_test_gru_layer_fwd(P(X), T * I, I, w8, P(len_t), P(hout), P(gt_ti[0]), P(gt_ti[1]), P(hn), S_, T, H, I, 1, S()))
+    dout = None if final_only else rnd(S_, T, 2 * H, seed=90)
+    dhn = rnd(S_, 2 * H, seed=91) if final_only else None
+    mk = (rnd(S_, T, I, seed=92) if mask else None)
+    dx = torch.full((S_, T, I), 9.0, device=dev)
+    per = 3 * H * I + 3 * H * H + 6 * H
+    out = torch.zeros(2 * per + off, device=dev)[off:]          # off != 0: gradient tensors that are not 16-byte aligned
+    ran = _ran(L, lambda: check_rc(L, L.dof_test_gru_layer_bwdw(P(X), w8, P(len_t), P(hout), P(gt_ti[0]), P(gt_ti[1]), P(dout), P(dhn),
+                                                                P(dx), P(mk), P(out), S_, T, H, I, S())))
+    assert any(n.startswith("gru_bwdw_tc") for n in ran), ran
+    torch.cuda.synchronize()
+    # fp64 reference: autograd through the oracle's bidirectional GRU
+    Xd = X.double().requires_grad_(True)
+    pd = {k_: v.double().requires_grad_(True) for k_, v in prm.items()}
+    out_ref, hn_ref = O.bigru(Xd, len_t.long(), pd, "")
+    loss = (hn_ref * dhn.double()).sum() if final_only else (out_ref * dout.double()).sum()
+    loss.backward()
+    dx_ref = Xd.grad * (mk > 0) if mask else Xd.grad
+    print("fused bwdw dX", (S_, T, I, H), rel(dx, dx_ref))
+    assert rel(dx, dx_ref) < 1e-5
+    for d, sfx in enumerate(("", "_reverse")):
+        o = out[d * per:(d + 1) * per]
+        got = {"weight_ih_l0": o[:3 * H * I].view(3 * H, I), "weight_hh_l0": o[3 * H * I:3 * H * I + 3 * H * H].view(3 * H, H),
+               "bias_ih_l0": o[-6 * H:-3 * H], "bias_hh_l0": o[-3 * H:]}
+        for n, v in got.items():
+            e = rel(v, pd[n + sfx].grad)
+            print("fused bwdw", n + sfx, e)
+            assert e < 1e-5, (n + sfx, e)
 
 
 def check_rc(L, rc):
