@@ -154,6 +154,7 @@ _SIGS = {
                                          C.c_int, C.c_int, _P]),
     "dof_test_gru_layer_bwdw": (C.c_int, [_P, C.POINTER(C.c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int,
                                           C.c_int, C.c_int, _P]),
+    "dof_test_gru_bwdw_timeline": (C.c_int, [_P]),
     "dof_test_gru_wgrad": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dof_test_tfm_attention": (C.c_int, [_P, _P, _P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "dof_test_encoder_grad": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),

@@ -2255,6 +2255,7 @@ int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* 
     return launch_gru_bwd_tc(b, (cudaStream_t)stream);
 }
 
+static long long* g_gru_bwdw_dbg = nullptr;
 // second-generation fused backward: BPTT + dX + the four parameter gradients of both directions in one kernel.
 // out = per direction [dW_ih (3H x I) | dW_hh (3H x H) | db_ih (3H) | db_hh (3H)], accumulated into (zero it first)
 int dof_test_gru_layer_bwdw(const float* X, const float* const* w8, const int* len, const float* hout, const float* gtT_f,
@@ -2270,9 +2271,14 @@ int dof_test_gru_layer_bwdw(const float* X, const float* const* w8, const int* l
     }
     b.GtT[0] = gtT_f; b.GtT[1] = gtT_b; b.X = X; b.x_ss = (long long)T * I; b.x_st = I;
     b.len = len; b.Hout = hout; b.dOut = dout; b.dHn = dhn; b.dX = dx; b.dXmask = dxmask; b.S = S; b.T = T; b.H = H; b.I = I;
+    b.dbg = g_gru_bwdw_dbg;
     DOF_CUDA(cudaMemsetAsync(dx, 0, (size_t)S * T * I * 4, (cudaStream_t)stream));
     return launch_gru_bwdw_tc(b, (cudaStream_t)stream);
 }
+
+// test / profiling hook: device buffer [8][T][4] of clock64 stamps written by CTA (0, 0) of the next dof_test_gru_layer_bwdw
+// launches (NULL = off)
+int dof_test_gru_bwdw_timeline(long long* dbg) { g_gru_bwdw_dbg = dbg; return DOF_OK; }
 
 // test hook: the encoder alone in TRAIN mode, backward from a given d(loss)/d(encoder output) (any model kind, any
 // encoder family): grad is overwritten, enc_out [B, D] receives the train-mode encoder output.

@@ -37,6 +37,7 @@ struct GruBwdwArgs {
     const float* dXmask;      // [S,T,I] or null: dX is kept only where mask > 0 (ReLU backward)
     float* dWih[2]; float* dWhh[2]; float* dbih[2]; float* dbhh[2];   // accumulated (+=)
     int S, T, H, I;
+    long long* dbg;           // null, or [8 roles][T][4] clock64 stamps of CTA (0, 0) (tools/prof_gru_bwdw.py)
 };
 
 struct GruBwdwGeom { int whh_lbo, wih_lbo, tmem_cols; uint32_t whh_bytes, wih_bytes, dg_bytes, xh_bytes; };
@@ -60,19 +61,30 @@ __device__ __forceinline__ uint32_t sw32_unit(int r, int c8) {
 }
 // the two 16-byte halves of one unit, hi / lo planes.  `sel` (= (row >> 2) & 1) swaps the order of the two stores so that
 // rows r and r + 4 of a quarter-warp (same unit position) never hit the same banks in the same instruction
+// one elected lane of a CONVERGED warp (elect.sync): the tcgen05.mma / commit below it are then issued once per warp with
+// warp-uniform operands straight from uniform registers (inside an `if (lane == 0)` region every tcgen05.mma is wrapped
+// in an ELECT / BRA.U.ANY waterfall loop and the issuing thread needs ~80 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// the two 16-byte halves of one 32-byte unit, hi / lo planes.  Threads with sel = (row >> 2) & 1 own their column chunks in
+// swapped order inside every pair (logical chunk q = physical chunk q ^ sel, see the gate warps), so v0 goes to half `sel`
+// and v1 to the other half: rows r and r + 4 of a quarter-warp (same unit position) never hit the same banks in one
+// instruction, without any data-dependent select
 __device__ __forceinline__ void st_unit(uint32_t hi_s, uint32_t lo_s, uint32_t off, const float (&v0)[4], const float (&v1)[4], int sel) {
     float4 h0, l0, h1, l1;
     split_tf32_exact(v0[0], h0.x, l0.x); split_tf32_exact(v0[1], h0.y, l0.y); split_tf32_exact(v0[2], h0.z, l0.z); split_tf32_exact(v0[3], h0.w, l0.w);
     split_tf32_exact(v1[0], h1.x, l1.x); split_tf32_exact(v1[1], h1.y, l1.y); split_tf32_exact(v1[2], h1.z, l1.z); split_tf32_exact(v1[3], h1.w, l1.w);
     const uint32_t oa = off + (sel ? 16u : 0u), ob = off + (sel ? 0u : 16u);
-    const float4 ha = sel ? h1 : h0, hb = sel ? h0 : h1, la = sel ? l1 : l0, lb = sel ? l0 : l1;
-    sts128(hi_s + oa, ha);
-    sts128(lo_s + oa, la);
-    sts128(hi_s + ob, hb);
-    sts128(lo_s + ob, lb);
+    sts128(hi_s + oa, h0);
+    sts128(lo_s + oa, l0);
+    sts128(hi_s + ob, h1);
+    sts128(lo_s + ob, l1);
 }
 
 // register budget per role (setmaxnreg, per warpgroup): the gate warps keep a whole step of saved gates in flight
@@ -102,6 +114,8 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 6);
     int* lens_s = reinterpret_cast<int*>(tmem_slot + 4);              // [128]; -1 outside the tile / batch
     const int s0 = blockIdx.x * R;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define GBW_STAMP(role, step, slot) do { if (dbg_on) a.dbg[((role) * T + (step)) * 4 + (slot)] = clock64(); } while (0)
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), geo.tmem_cols);
     if (tid == 32) {
@@ -137,7 +151,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __reduce_or_sync(0xffffffffu, *tmem_slot);   // REDUX: the compiler now knows the address is warp-uniform (no per-MMA waterfall)
     const uint32_t bar_afull = smem_u32(mbar), bar_dh = smem_u32(mbar + 1), bar_dx = smem_u32(mbar + 2), bar_w = smem_u32(mbar + 3),
                    bar_dxr = smem_u32(mbar + 4);
     // TMEM columns: acc_dh [H] | acc_dx [I] | weight-gradient accumulators.  The TMEM accumulator TRUNCATES on every
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
         if (a.dHn && len > 0) {
 #pragma unroll
             for (int q = 0; q < HC / 4; q++) {
-                const float4 d = __ldg(reinterpret_cast<const float4*>(a.dHn + (size_t)s * 2 * H + dir * H + j0 + q * 4));
+                const float4 d = __ldg(reinterpret_cast<const float4*>(a.dHn + (size_t)s * 2 * H + dir * H + j0 + (q ^ sel) * 4));
                 part[q * 4] = d.x; part[q * 4 + 1] = d.y; part[q * 4 + 2] = d.z; part[q * 4 + 3] = d.w;
             }
         }
@@ -176,42 +190,68 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
             const int t = dir ? step_ : (T - 1 - step_);
             const int tp = dir ? t + 1 : t - 1;
             const float* gt = GtT + (size_t)t * H * 512;
-            const int cq = (j0 >> 2) + q;
+            const int pq = q ^ sel;                                   // physical chunk of logical chunk q
+            const int cq = (j0 >> 2) + pq;
             hp4[q] = make_float4(0.f, 0.f, 0.f, 0.f); do4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t < len) {
                 r4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)cq * 512));
                 z4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(H / 4 + cq) * 512));
                 n4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(2 * (H / 4) + cq) * 512));
                 q4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(3 * (H / 4) + cq) * 512));
-                if (tp >= 0 && tp < len) hp4[q] = __ldg(reinterpret_cast<const float4*>(a.Hout + ((size_t)s * T + tp) * 2 * H + dir * H + j0 + q * 4));
-                if (a.dOut) do4[q] = __ldg(reinterpret_cast<const float4*>(a.dOut + ((size_t)s * T + t) * 2 * H + dir * H + j0 + q * 4));
+                if (tp >= 0 && tp < len) hp4[q] = __ldg(reinterpret_cast<const float4*>(a.Hout + ((size_t)s * T + tp) * 2 * H + dir * H + j0 + pq * 4));
+                if (a.dOut) do4[q] = __ldg(reinterpret_cast<const float4*>(a.dOut + ((size_t)s * T + t) * 2 * H + dir * H + j0 + pq * 4));
             } else {
                 r4[q] = z4[q] = n4[q] = q4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
+        // DRAM -> L2 two steps ahead (no registers held): one SM can only keep ~30 KB of loads in flight, so a step's 100 KB
+        // of saved gates / h_prev / dOut / x must already sit in L2 when the register loads above are issued
+        auto prefetch_step = [&](int step_) {
+            const int t = dir ? step_ : (T - 1 - step_);
+            const int tp = dir ? t + 1 : t - 1;
+            if (t >= len) return;
+            if ((lane & 7) == 0) {                                          // one lane per 128-byte line of the tiled gates
+                const float* gn = GtT + ((size_t)t * H + (j0 >> 2)) * 512;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; g4++)
+#pragma unroll
+                    for (int qq = 0; qq < HC / 4; qq++)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)(g4 * (H / 4) + qq) * 512));
+            }
+            if (half == 0) {
+                if (tp >= 0 && tp < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Hout + ((size_t)s * T + tp) * 2 * H + dir * H));
+                if (a.dOut) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dOut + ((size_t)s * T + t) * 2 * H + dir * H));
+            }
+        };
 #pragma unroll
         for (int q = 0; q < HC / 4; q++) load_q(q, 0);
+        if (H == 32 && T > 1) prefetch_step(1);       // measured: helps H = 32 (1.87 -> 1.81 ms), hurts H = 16 (1.12 -> 1.38 ms)
         for (int step = 0; step < T; step++) {
             const int t = dir ? step : (T - 1 - step);
             const bool valid = t < len;
+            if (H == 32 && step + 2 < T) prefetch_step(step + 2);
             // recurrent term of the previous step: dh = part + dG_{prev} . W_hh
             float dh[HC];
+            const int grole = warp == 4 ? 0 : (warp == 11 ? 1 : -1);
+            if (grole >= 0 && lane == 0) GBW_STAMP(grole, step, 0);
             if (step > 0) {
                 mbar_wait(bar_dh, (uint32_t)((step - 1) & 1));
                 tc_fence_after();
                 float v[HC];
                 tmem_ld_hc<HC>(acc_dh + ((uint32_t)(ew * 32) << 16) + (uint32_t)j0, v);
 #pragma unroll
-                for (int j = 0; j < HC; j++) dh[j] = part[j] + v[j];
+                for (int j = 0; j < HC; j++) dh[j] = part[j] + (sel ? v[j ^ 4] : v[j]);       // TMEM columns are in physical order
             } else {
 #pragma unroll
                 for (int j = 0; j < HC; j++) dh[j] = part[j];
             }
+            if (grole >= 0 && lane == 0) GBW_STAMP(grole, step, 1);
             // the tiles are free again once every MMA of the previous step retired
             if (step > 0) {
                 mbar_wait(bar_dx, (uint32_t)((step - 1) & 1));
                 mbar_wait(bar_w, (uint32_t)((step - 1) & 1));
             }
+            if (grole >= 0 && lane == 0) GBW_STAMP(grole, step, 2);
             if (in_tile) {
 #pragma unroll
                 for (int p = 0; p < HC / 8; p++) {
@@ -241,7 +281,6 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                             }
                         }
                     }
-                    if (step + 1 < T) { load_q(2 * p, step + 1); load_q(2 * p + 1, step + 1); }     // registers just consumed
                     const int c8 = j0 + 8 * p;                               // column inside a gate block
                     st_unit(dg_hi, dg_lo, sw32_unit<R>(row, c8), o_r[0], o_r[1], sel);
                     st_unit(dg_hi, dg_lo, sw32_unit<R>(row, H + c8), o_z[0], o_z[1], sel);
@@ -253,46 +292,61 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar_afull);
+            if (grole >= 0 && lane == 0) GBW_STAMP(grole, step, 3);
+            if (step + 1 < T) {                                       // next step's loads: in flight during the MMA round trip
+#pragma unroll
+                for (int q = 0; q < HC / 4; q++) load_q(q, step + 1);
+            }
         }
     } else if (warp == GBW_MMA_A) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GbwRegs<H>::OTHER));
-        if (lane == 0) {
-            // ===================== MMA issuer A: dh and dX =====================
+        {
+            // ===================== MMA issuer A: dh and dX (whole warp converged, one elected lane issues) =====================
             const uint32_t id_h = umma_idesc_tf32(H, 0, 0), id_x = umma_idesc_tf32(I, 0, 0);
             const uint32_t a_hi = smem_u32(DG_hi), a_lo = smem_u32(DG_lo);
             const uint32_t whh_hi = smem_u32(Whh_hi), whh_lo = smem_u32(Whh_lo), wih_hi = smem_u32(Wih_hi), wih_lo = smem_u32(Wih_lo);
             for (int step = 0; step < T; step++) {
+                if (lane == 0) GBW_STAMP(2, step, 0);
                 mbar_wait(bar_afull, (uint32_t)(step & 1));
                 tc_fence_after();
+                if (lane == 0) GBW_STAMP(2, step, 1);
                 // dh: K = 3H = tile columns [0, 3H)
-#pragma unroll 2
-                for (int ks = 0; ks < (3 * H) >> 3; ks++) {
-                    const uint32_t ao = (uint32_t)(ks >> 2) * (uint32_t)(R * 128) + (uint32_t)(ks & 3) * 32, wo = (uint32_t)ks * 2 * geo.whh_lbo;
-                    const uint64_t dah = umma_desc_k32(a_hi + ao), dal = umma_desc_k32(a_lo + ao);
-                    const uint64_t dbh = umma_desc(whh_hi + wo, geo.whh_lbo, 128), dbl = umma_desc(whh_lo + wo, geo.whh_lbo, 128);
-                    umma_tf32(acc_dh, dah, dbh, id_h, ks > 0 ? 1u : 0u);
-                    umma_tf32(acc_dh, dal, dbh, id_h, 1u);
-                    umma_tf32(acc_dh, dah, dbl, id_h, 1u);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < (3 * H) >> 3; ks++) {
+                        const uint32_t ao = (uint32_t)(ks >> 2) * (uint32_t)(R * 128) + (uint32_t)(ks & 3) * 32, wo = (uint32_t)ks * 2 * geo.whh_lbo;
+                        const uint64_t dah = umma_desc_k32(a_hi + ao), dal = umma_desc_k32(a_lo + ao);
+                        const uint64_t dbh = umma_desc(whh_hi + wo, geo.whh_lbo, 128), dbl = umma_desc(whh_lo + wo, geo.whh_lbo, 128);
+                        umma_tf32(acc_dh, dah, dbh, id_h, ks > 0 ? 1u : 0u);
+                        umma_tf32(acc_dh, dal, dbh, id_h, 1u);
+                        umma_tf32(acc_dh, dah, dbl, id_h, 1u);
+                    }
+                    umma_commit(bar_dh);
                 }
-                umma_commit(bar_dh);
+                __syncwarp();
+                if (lane == 0) GBW_STAMP(2, step, 2);
                 if (step > 0) { mbar_wait(bar_dxr, (uint32_t)((step - 1) & 1)); tc_fence_after(); }   // acc_dx of the previous step read out
                 // dX: tile columns [0, 2H) (da_r, da_z) and [3H, 4H) (da_n) against W_ih rows r, z, n
-#pragma unroll 2
-                for (int ks = 0; ks < (3 * H) >> 3; ks++) {
-                    const int kc = ks < ((2 * H) >> 3) ? ks : ks + (H >> 3);                  // 8-column group of the tile
-                    const uint32_t ao = (uint32_t)(kc >> 2) * (uint32_t)(R * 128) + (uint32_t)(kc & 3) * 32, wo = (uint32_t)ks * 2 * geo.wih_lbo;
-                    const uint64_t dah = umma_desc_k32(a_hi + ao), dal = umma_desc_k32(a_lo + ao);
-                    const uint64_t dbh = umma_desc(wih_hi + wo, geo.wih_lbo, 128), dbl = umma_desc(wih_lo + wo, geo.wih_lbo, 128);
-                    umma_tf32(acc_dx, dah, dbh, id_x, ks > 0 ? 1u : 0u);
-                    umma_tf32(acc_dx, dal, dbh, id_x, 1u);
-                    umma_tf32(acc_dx, dah, dbl, id_x, 1u);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < (3 * H) >> 3; ks++) {
+                        const int kc = ks < ((2 * H) >> 3) ? ks : ks + (H >> 3);                  // 8-column group of the tile
+                        const uint32_t ao = (uint32_t)(kc >> 2) * (uint32_t)(R * 128) + (uint32_t)(kc & 3) * 32, wo = (uint32_t)ks * 2 * geo.wih_lbo;
+                        const uint64_t dah = umma_desc_k32(a_hi + ao), dal = umma_desc_k32(a_lo + ao);
+                        const uint64_t dbh = umma_desc(wih_hi + wo, geo.wih_lbo, 128), dbl = umma_desc(wih_lo + wo, geo.wih_lbo, 128);
+                        umma_tf32(acc_dx, dah, dbh, id_x, ks > 0 ? 1u : 0u);
+                        umma_tf32(acc_dx, dal, dbh, id_x, 1u);
+                        umma_tf32(acc_dx, dah, dbl, id_x, 1u);
+                    }
+                    umma_commit(bar_dx);
                 }
-                umma_commit(bar_dx);
+                __syncwarp();
+                if (lane == 0) GBW_STAMP(2, step, 3);
             }
         }
     } else if (warp == GBW_MMA_B) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GbwRegs<H>::OTHER));
-        if (lane == 0) {
+        {
             // ===================== MMA issuer B: weight / bias gradients, accumulated over all T steps =====================
             const uint32_t id_w = umma_idesc_tf32(I + H, 1, 1), id_b = umma_idesc_tf32(16, 1, 0);
             const uint32_t a_hi = smem_u32(DG_hi), a_lo = smem_u32(DG_lo), x_hi = smem_u32(XH_hi), x_lo = smem_u32(XH_lo);
@@ -300,20 +354,25 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
             for (int step = 0; step < T; step++) {
                 mbar_wait(bar_afull, (uint32_t)(step & 1));
                 tc_fence_after();
-#pragma unroll 2
-                for (int ks = 0; ks < R / 8; ks++) {
-                    const uint32_t o = (uint32_t)ks * 1024u;
-                    const uint64_t dah = umma_desc_mn32(a_hi + o, R * 128), dal = umma_desc_mn32(a_lo + o, R * 128);
-                    const uint64_t dbh = umma_desc_mn32(x_hi + o, R * 128), dbl = umma_desc_mn32(x_lo + o, R * 128);
-                    const uint32_t first = (step == 0 && ks == 0) ? 0u : 1u, firstp = (step < 2 && ks == 0) ? 0u : 1u;
-                    const uint32_t par = (uint32_t)(step & 1);
-                    umma_tf32(acc_w + par * NW, dah, dbh, id_w, firstp);
-                    umma_tf32(acc_wlo, dal, dbh, id_w, first);
-                    umma_tf32(acc_wlo, dah, dbl, id_w, 1u);
-                    umma_tf32(acc_b + par * 16, dah, d1, id_b, firstp);
-                    umma_tf32(acc_blo, dal, d1, id_b, first);
+                if (lane == 0) GBW_STAMP(3, step, 0);
+                const uint32_t par = (uint32_t)(step & 1);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < R / 8; ks++) {
+                        const uint32_t o = (uint32_t)ks * 1024u;
+                        const uint64_t dah = umma_desc_mn32(a_hi + o, R * 128), dal = umma_desc_mn32(a_lo + o, R * 128);
+                        const uint64_t dbh = umma_desc_mn32(x_hi + o, R * 128), dbl = umma_desc_mn32(x_lo + o, R * 128);
+                        const uint32_t first = (step == 0 && ks == 0) ? 0u : 1u, firstp = (step < 2 && ks == 0) ? 0u : 1u;
+                        umma_tf32(acc_w + par * NW, dah, dbh, id_w, firstp);
+                        umma_tf32(acc_wlo, dal, dbh, id_w, first);
+                        umma_tf32(acc_wlo, dah, dbl, id_w, 1u);
+                        umma_tf32(acc_b + par * 16, dah, d1, id_b, firstp);
+                        umma_tf32(acc_blo, dal, d1, id_b, first);
+                    }
+                    umma_commit(bar_w);
                 }
-                umma_commit(bar_w);
+                __syncwarp();
+                if (lane == 0) GBW_STAMP(3, step, 1);
             }
         }
     } else {
@@ -347,13 +406,29 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                 sts128(xh_lo + off, lo);
             }
         };
+        auto prefetch_x = [&](int step_) {
+            const int t = dir ? step_ : (T - 1 - step_);
+#pragma unroll
+            for (int j = 0; j < KQM; j++) {
+                const int i = ltid + j * GBW_NXL;
+                const int r = i / KQ, kq = i - r * KQ;
+                if (i < R * KQ && s0 + r < a.S && (kq & 7) == 0)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.X + (size_t)(s0 + r) * a.x_ss + (size_t)t * a.x_st + kq * 4));
+            }
+        };
         load_x(0);
+        if (H == 32 && T > 1) prefetch_x(1);
         for (int step = 0; step < T; step++) {
             const int t = dir ? step : (T - 1 - step);
+            if (H == 32 && step + 2 < T) prefetch_x(step + 2);
+            const int lrole = warp == 0 ? 4 : (warp == 14 ? 5 : -1);
+            if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 0);
             if (step > 0) mbar_wait(bar_w, (uint32_t)((step - 1) & 1));      // the weight-gradient MMAs of the previous step read XH
+            if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 1);
             stage_x();
             fence_async_smem();
             mbar_arrive(bar_afull);
+            if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 2);
             if (step + 1 < T) load_x(step + 1);
             if (warp < 4) {
                 // dX_t rows from TMEM -> HBM (vector reductions: both directions add into the same rows)
@@ -380,6 +455,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                 }
                 tc_fence_before();
                 mbar_arrive(bar_dxr);
+                if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 3);
             }
         }
         if (warp < 4) {

@@ -418,6 +418,9 @@ int dof_test_gru_layer_bwd(const float* const* w8, const int* len, const float* 
 int dof_test_gru_layer_bwdw(const float* X, const float* const* w8, const int* len, const float* hout, const float* gtT_f,
                             const float* gtT_b, const float* dout, const float* dhn, float* dx, const float* dxmask,
                             float* out, int S, int T, int H, int I, void* stream);
+/* profiling hook: dbg = device buffer of 8 * T * 4 int64 clock stamps written by CTA (0, 0) of the following
+ * dof_test_gru_layer_bwdw launches (roles: two gate warps, the two MMA issuers, two loader warps); NULL switches it off */
+int dof_test_gru_bwdw_timeline(long long* dbg);
 /* merged GRU parameter gradients (gru_wgrad_tc.cuh): dg_f / dg_b [M,4H] = [dr, dz, dn*r, dn], x [M,I] (pitch ldx),
  * hout [M,2H]; out (zeroed by the caller, accumulated into) = per direction dW_ih [3H,I] | dW_hh [3H,H] | db_ih [3H] |
  * db_hh [3H].  Returns DOF_ERR_UNSUPPORTED when the shape is not eligible for the tensor-core kernel. */
