@@ -411,9 +411,12 @@ def run_workload(c, steps, warmup, world, rank, local, dev, sample_clocks=True, 
             sustained = peaks.get("bf16_tflops_sustained", 1400.0)
             roof["step_useful_tflops"] = c["flops"] * B / (ms / 1e3) / 1e12
             roof["step_tensor_frac"] = roof["step_useful_tflops"] / sustained
-    del trainer, loader, frames, xh, ah
+    exch = getattr(trainer, "exchange", None)
+    allreduce = exch.kind if exch is not None else None
+    del trainer, loader, frames, xh, ah, exch
     torch.cuda.empty_cache()
-    return dict(value=value, ms=ms, e2e=e2e, launches=int(launches), clocks=clocks, kernels=kernels, roof=roof, pool_n=pool_n)
+    return dict(value=value, ms=ms, e2e=e2e, launches=int(launches), clocks=clocks, kernels=kernels, roof=roof, pool_n=pool_n,
+                allreduce=allreduce)
 
 
 def main():
@@ -489,6 +492,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(c, B, world, m["pool_n"]),
                 "e2e": m["e2e"], "gpu_launches": m["launches"], "clocks": m["clocks"], "roofline": m["roof"], "kernels": m["kernels"],
+                "allreduce": m["allreduce"] and {"kind": m["allreduce"], "note": "peer_memory = barrier + one-shot reduce over NVLink peer "
+                                                 "memory + barrier (csrc/peer.cuh) instead of an NCCL call; nccl = torch.distributed.all_reduce"},
                 "kernels_note": "per-kernel-class CUDA-event times of 3 extra steps run on ONE stream (kernels do not overlap); the timed "
                                 "steps run the node and edge encoder blocks concurrently on two streams, so ms_per_step is below their sum",
                 "cpu_baseline": cpu, "secondary": secondary}

@@ -154,6 +154,8 @@ _SIGS = {
                                          C.c_int, C.c_int, _P]),
     "dof_test_gru_layer_bwdw": (C.c_int, [_P, C.POINTER(C.c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int,
                                           C.c_int, C.c_int, _P]),
+    "dof_peer_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, _P]),
+    "dof_peer_reduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, _P, C.c_longlong, _P]),
     "dof_test_gru_bwdw_timeline": (C.c_int, [_P]),
     "dof_test_gru_wgrad": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dof_test_tfm_attention": (C.c_int, [_P, _P, _P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),

@@ -13,6 +13,7 @@
 #include "gru_bwd_tc.cuh"
 #include "gru_wgrad_tc.cuh"
 #include "gru_bwdw_tc.cuh"
+#include "peer.cuh"
 #include "layers.cuh"
 #include "loss.cuh"
 #include "loader.cuh"
@@ -2032,6 +2033,39 @@ int dof_adam_flat(float* param, const float* grad, float* adam_m, float* adam_v,
     a.clip = 0.f; a.gscale = grad_scale; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
     { ProfScope ps("clip_adam", (cudaStream_t)stream, 0.0, 28.0 * n);
     clip_adam_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+// ---- gradient exchange over NVLink peer memory (peer.cuh) ----
+int dof_peer_barrier(const void* const* pads, int world, int rank, int epoch, void* stream) {
+    if (!pads || world < 1 || world > DOF_PEER_MAX || rank < 0 || rank >= world) DOF_FAIL(DOF_ERR_ARG, "bad peer barrier arguments (world %d rank %d)", world, rank);
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof(pp));
+    for (int i = 0; i < world; i++) {
+        if (!pads[i]) DOF_FAIL(DOF_ERR_ARG, "null signal pad of peer %d", i);
+        pp.p[i] = const_cast<void*>(pads[i]);
+    }
+    { ProfScope ps("peer_barrier", (cudaStream_t)stream);
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch); }
+    DOF_LAUNCH_CHECK();
+    return DOF_OK;
+}
+
+int dof_peer_reduce(const void* const* peers, int world, float* out, long long n, void* stream) {
+    if (!peers || !out || world < 1 || world > DOF_PEER_MAX || n < 4 || (n & 3)) DOF_FAIL(DOF_ERR_ARG, "bad peer reduce arguments (world %d n %lld)", world, n);
+    if (!aligned16(out)) DOF_FAIL(DOF_ERR_ARG, "peer reduce output must be 16-byte aligned");
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof(pp));
+    for (int i = 0; i < world; i++) {
+        if (!peers[i] || !aligned16(peers[i])) DOF_FAIL(DOF_ERR_ARG, "peer %d: null or misaligned gradient buffer", i);
+        pp.p[i] = const_cast<void*>(peers[i]);
+    }
+    const long long n4 = n / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > 4 * g_sm_count) grid = 4 * g_sm_count;
+    { ProfScope ps("peer_reduce", (cudaStream_t)stream, 0.0, 4.0 * n * (world + 1));
+    peer_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp, world, reinterpret_cast<float4*>(out), n4); }
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }

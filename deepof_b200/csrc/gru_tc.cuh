@@ -56,6 +56,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
+// one elected lane of a CONVERGED warp (elect.sync)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 template <int HC>
 __device__ __forceinline__ void tmem_ld_hc(uint32_t taddr, float (&v)[HC]) {
     if constexpr (HC == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __reduce_or_sync(0xffffffffu, *tmem_slot);   // REDUX: provably warp-uniform -> lives in a uniform register
     const uint32_t bar_xfull = smem_u32(mbar), bar_xempty = smem_u32(mbar + 2), bar_acc = smem_u32(mbar + 4),
                    bar_h = smem_u32(mbar + 6), bar_sfull = smem_u32(mbar + 7), bar_sfree = smem_u32(mbar + 8);
     const bool want_g = a.Gt[dir] != nullptr, want_o = a.Hout != nullptr;
@@ -318,8 +324,9 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                 *reinterpret_cast<float4*>(a.Hn + (size_t)s * 2 * H + dir * H + j0 + q * 4) = make_float4(h[q * 4], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
         }
     } else if (warp == GTC_MMA_WARP) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
+        {
+            // ===================== MMA issuer: the whole warp runs the loop converged, one elected lane issues =====================
+            // (inside an `if (lane == 0)` region every tcgen05.mma is wrapped in an ELECT / BRA.U.ANY waterfall loop)
             const uint32_t id_x = umma_idesc_tf32(3 * H, 0, 0), id_rz = umma_idesc_tf32(2 * H, 0, 0), id_n = umma_idesc_tf32(H, 0, 0);
             const uint32_t wih_hi = smem_u32(Wih_hi), wih_lo = smem_u32(Wih_lo), whh_hi = smem_u32(Whh_hi), whh_lo = smem_u32(Whh_lo);
             const uint32_t hs_hi = smem_u32(Hs_hi), hs_lo = smem_u32(Hs_lo);
@@ -329,15 +336,18 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                 tc_fence_after();
                 const uint32_t x_hi = smem_u32(Xs + (size_t)st * 2 * geo.x_bytes), x_lo = x_hi + geo.x_bytes;
                 const uint32_t acc = tmem + (uint32_t)((step & 1) * 4 * H);
-                for (int ks = 0; ks < (I >> 3); ks++) {
-                    const uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * geo.wih_lbo;
-                    const uint64_t dah = umma_desc(x_hi + ao, TC_A_LBO, 128), dal = umma_desc(x_lo + ao, TC_A_LBO, 128);
-                    const uint64_t dbh = umma_desc(wih_hi + wo, geo.wih_lbo, 128), dbl = umma_desc(wih_lo + wo, geo.wih_lbo, 128);
-                    umma_tf32(acc, dah, dbh, id_x, ks > 0 ? 1u : 0u);
-                    umma_tf32(acc, dal, dbh, id_x, 1u);
-                    umma_tf32(acc, dah, dbl, id_x, 1u);
+                if (elect_one_sync()) {
+                    for (int ks = 0; ks < (I >> 3); ks++) {
+                        const uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * geo.wih_lbo;
+                        const uint64_t dah = umma_desc(x_hi + ao, TC_A_LBO, 128), dal = umma_desc(x_lo + ao, TC_A_LBO, 128);
+                        const uint64_t dbh = umma_desc(wih_hi + wo, geo.wih_lbo, 128), dbl = umma_desc(wih_lo + wo, geo.wih_lbo, 128);
+                        umma_tf32(acc, dah, dbh, id_x, ks > 0 ? 1u : 0u);
+                        umma_tf32(acc, dal, dbh, id_x, 1u);
+                        umma_tf32(acc, dah, dbl, id_x, 1u);
+                    }
+                    umma_commit(bar_xempty + 8u * st);                 // x stage reusable once these MMAs retire
                 }
-                umma_commit(bar_xempty + 8u * st);                 // x stage reusable once these MMAs retire
+                __syncwarp();
             };
             issue_x(0);
             for (int step = 0; step < T; step++) {
@@ -345,21 +355,25 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                 mbar_wait(bar_h, (uint32_t)(step & 1));            // h_{step-1} published (phase step)
                 tc_fence_after();
                 const uint32_t acc = tmem + (uint32_t)(buf * 4 * H);
-                for (int ks = 0; ks < (H >> 3); ks++) {
-                    const uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * geo.whh_lbo;
-                    const uint64_t dah = umma_desc(hs_hi + ao, TC_A_LBO, 128), dal = umma_desc(hs_lo + ao, TC_A_LBO, 128);
-                    const uint64_t dbh = umma_desc(whh_hi + wo, geo.whh_lbo, 128), dbl = umma_desc(whh_lo + wo, geo.whh_lbo, 128);
-                    // r,z gates accumulate on top of the x part
-                    umma_tf32(acc, dah, dbh, id_rz, 1u);
-                    umma_tf32(acc, dal, dbh, id_rz, 1u);
-                    umma_tf32(acc, dah, dbl, id_rz, 1u);
-                    // W_hn . h goes to its own columns [3H, 4H)
-                    const uint64_t dnh = umma_desc(whh_hi + wo + 2 * H * 16, geo.whh_lbo, 128), dnl = umma_desc(whh_lo + wo + 2 * H * 16, geo.whh_lbo, 128);
-                    umma_tf32(acc + 3 * H, dah, dnh, id_n, ks > 0 ? 1u : 0u);
-                    umma_tf32(acc + 3 * H, dal, dnh, id_n, 1u);
-                    umma_tf32(acc + 3 * H, dah, dnl, id_n, 1u);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int ks = 0; ks < (H >> 3); ks++) {
+                        const uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * geo.whh_lbo;
+                        const uint64_t dah = umma_desc(hs_hi + ao, TC_A_LBO, 128), dal = umma_desc(hs_lo + ao, TC_A_LBO, 128);
+                        const uint64_t dbh = umma_desc(whh_hi + wo, geo.whh_lbo, 128), dbl = umma_desc(whh_lo + wo, geo.whh_lbo, 128);
+                        // r,z gates accumulate on top of the x part
+                        umma_tf32(acc, dah, dbh, id_rz, 1u);
+                        umma_tf32(acc, dal, dbh, id_rz, 1u);
+                        umma_tf32(acc, dah, dbl, id_rz, 1u);
+                        // W_hn . h goes to its own columns [3H, 4H)
+                        const uint64_t dnh = umma_desc(whh_hi + wo + 2 * H * 16, geo.whh_lbo, 128), dnl = umma_desc(whh_lo + wo + 2 * H * 16, geo.whh_lbo, 128);
+                        umma_tf32(acc + 3 * H, dah, dnh, id_n, ks > 0 ? 1u : 0u);
+                        umma_tf32(acc + 3 * H, dal, dnh, id_n, 1u);
+                        umma_tf32(acc + 3 * H, dah, dnl, id_n, 1u);
+                    }
+                    umma_commit(bar_acc + 8u * buf);
                 }
-                umma_commit(bar_acc + 8u * buf);
+                __syncwarp();
                 if (step + 1 < T) issue_x(step + 1);
             }
         }

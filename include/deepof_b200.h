@@ -284,6 +284,17 @@ int dof_vqvae_loss_grad_distill(dof_handle* h, const float* state, float* grad, 
 int dof_adam_flat(float* param, const float* grad, float* adam_m, float* adam_v, long long n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (csrc/peer.cuh) -------------------------
+ * Replaces the per-step gradient all-reduce DistributedDataParallel runs for the reference (deepof/clustering/
+ * training.py:1567 DDP wrap, :164 loss.backward()).  Every rank owns one symmetric buffer [gradient | signal pad] that
+ * is mapped into all peers; `pads` / `peers` are HOST arrays of `world` DEVICE pointers as seen from THIS process
+ * (pads[r] = rank r's signal pad, >= world int32, zero-initialised; peers[r] = rank r's gradient, 16-byte aligned).
+ * dof_peer_barrier: rank-to-rank barrier on the stream; `epoch` must increase by one with every call on all ranks.
+ * dof_peer_reduce:  out[i] = sum over r = 0..world-1 (in that order: bit-identical on every rank) of peers[r][i];
+ *                   n floats, multiple of 4.  Call order per step: barrier, reduce, barrier. */
+int dof_peer_barrier(const void* const* pads, int world, int rank, int epoch, void* stream);
+int dof_peer_reduce(const void* const* peers, int world, float* out, long long n, void* stream);
+
 /* ---- contrastive (DOF_MODEL_CONTRASTIVE) --------------------------------------------------------------
  * dof_contrastive_views builds what step_contrastive_distill feeds its encoder (training.py:497-525): from
  * x_full [B,T_full,N,3] the middle half window and the augmented view of _make_augmented_view (training.py:2128-2402)

@@ -71,6 +71,8 @@ def main():
             worst = max(worst, float((state1[off:off + n].cpu().view(shape) - p1[k]).abs().max()))
         res["post_adam_worst_abs_diff"] = worst
         res["world"] = world
+        res["allreduce"] = tr.exchange.kind
+        res["allreduce_fallback_reason"] = tr.exchange.why
         res["nccl_version"] = ".".join(str(v) for v in torch.cuda.nccl.version())
         with open(out, "w") as f:
             json.dump(res, f)

@@ -14,15 +14,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_step_matches_oracle_mean_gradient(tmp_path):
+@pytest.mark.parametrize("allreduce", ["peer", "nccl"])
+def test_two_rank_step_matches_oracle_mean_gradient(tmp_path, allreduce):
+    """allreduce = "peer": the gradient exchange over NVLink peer memory (csrc/peer.cuh, the default); "nccl": the
+    torch.distributed.all_reduce it replaces.  Same assertions for both."""
     out = str(tmp_path / "verdict.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29531", os.path.join(HERE, "mp_step_worker.py"), out]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", "29531" if allreduce == "peer" else "29532", os.path.join(HERE, "mp_step_worker.py"), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, DOF_ALLREDUCE=allreduce))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     v = json.load(open(out))
     print(v)
     assert v["world"] == 2
+    assert v["allreduce"] == ("peer_memory" if allreduce == "peer" else "nccl"), v
     assert v["params_bit_identical_after_3_steps"] is True
     assert v["allreduced_grad_rel_l2_vs_oracle_mean"] < 2e-4, v
     assert v["post_adam_worst_abs_diff"] < 1.1e-3, v      # Adam step 1 = lr * sign(g): a near-zero gradient may flip (2 * lr_base)
