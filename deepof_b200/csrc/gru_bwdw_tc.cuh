@@ -61,14 +61,6 @@ __device__ __forceinline__ uint32_t sw32_unit(int r, int c8) {
 }
 // the two 16-byte halves of one unit, hi / lo planes.  `sel` (= (row >> 2) & 1) swaps the order of the two stores so that
 // rows r and r + 4 of a quarter-warp (same unit position) never hit the same banks in the same instruction
-// one elected lane of a CONVERGED warp (elect.sync): the tcgen05.mma / commit below it are then issued once per warp with
-// warp-uniform operands straight from uniform registers (inside an `if (lane == 0)` region every tcgen05.mma is wrapped
-// in an ELECT / BRA.U.ANY waterfall loop and the issuing thread needs ~80 cycles per MMA)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ void sts128(uint32_t saddr, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -151,7 +143,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = __reduce_or_sync(0xffffffffu, *tmem_slot);   // REDUX: the compiler now knows the address is warp-uniform (no per-MMA waterfall)
+    const uint32_t tmem = tmem_base_uniform(tmem_slot);
     const uint32_t bar_afull = smem_u32(mbar), bar_dh = smem_u32(mbar + 1), bar_dx = smem_u32(mbar + 2), bar_w = smem_u32(mbar + 3),
                    bar_dxr = smem_u32(mbar + 4);
     // TMEM columns: acc_dh [H] | acc_dx [I] | weight-gradient accumulators.  The TMEM accumulator TRUNCATES on every
@@ -311,7 +303,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                 tc_fence_after();
                 if (lane == 0) GBW_STAMP(2, step, 1);
                 // dh: K = 3H = tile columns [0, 3H)
-                if (elect_one()) {
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int ks = 0; ks < (3 * H) >> 3; ks++) {
                         const uint32_t ao = (uint32_t)(ks >> 2) * (uint32_t)(R * 128) + (uint32_t)(ks & 3) * 32, wo = (uint32_t)ks * 2 * geo.whh_lbo;
@@ -327,7 +319,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                 if (lane == 0) GBW_STAMP(2, step, 2);
                 if (step > 0) { mbar_wait(bar_dxr, (uint32_t)((step - 1) & 1)); tc_fence_after(); }   // acc_dx of the previous step read out
                 // dX: tile columns [0, 2H) (da_r, da_z) and [3H, 4H) (da_n) against W_ih rows r, z, n
-                if (elect_one()) {
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int ks = 0; ks < (3 * H) >> 3; ks++) {
                         const int kc = ks < ((2 * H) >> 3) ? ks : ks + (H >> 3);                  // 8-column group of the tile
@@ -356,7 +348,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                 tc_fence_after();
                 if (lane == 0) GBW_STAMP(3, step, 0);
                 const uint32_t par = (uint32_t)(step & 1);
-                if (elect_one()) {
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int ks = 0; ks < R / 8; ks++) {
                         const uint32_t o = (uint32_t)ks * 1024u;

@@ -56,12 +56,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
-// one elected lane of a CONVERGED warp (elect.sync)
-__device__ __forceinline__ bool elect_one_sync() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
 template <int HC>
 __device__ __forceinline__ void tmem_ld_hc(uint32_t taddr, float (&v)[HC]) {
     if constexpr (HC == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
@@ -137,7 +131,7 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = __reduce_or_sync(0xffffffffu, *tmem_slot);   // REDUX: provably warp-uniform -> lives in a uniform register
+    const uint32_t tmem = tmem_base_uniform(tmem_slot);
     const uint32_t bar_xfull = smem_u32(mbar), bar_xempty = smem_u32(mbar + 2), bar_acc = smem_u32(mbar + 4),
                    bar_h = smem_u32(mbar + 6), bar_sfull = smem_u32(mbar + 7), bar_sfree = smem_u32(mbar + 8);
     const bool want_g = a.Gt[dir] != nullptr, want_o = a.Hout != nullptr;

@@ -82,6 +82,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// One elected lane of a CONVERGED warp (elect.sync).  The MMA-issuing warps run their loops with all 32 lanes and guard only
+// the tcgen05.mma / commit with this: the operands are then warp-uniform values in uniform registers.  Inside an
+// `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// TMEM base address as a provably warp-uniform value (REDUX result)
+__device__ __forceinline__ uint32_t tmem_base_uniform(const uint32_t* slot) { return __reduce_or_sync(0xffffffffu, *slot); }
+
 // shared-memory matrix descriptor, SWIZZLE_NONE, sm_100 version field = 1
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = tmem_base_uniform(tmem_slot);
     const uint32_t bar_full = smem_u32(mbar), bar_empty = smem_u32(mbar + S);
     const uint32_t bar_tfull = smem_u32(mbar + 2 * S), bar_tempty = smem_u32(mbar + 2 * S + 2);
 
@@ -303,8 +314,8 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
             tc_fence_before();
             mbar_arrive(bar_tempty + 8u * a);
         }
-    } else if (lane == 0) {
-        // ===================== MMA issuer (one thread) =====================
+    } else {
+        // ===================== MMA issuer: warp 8 runs the loop converged, one elected lane issues =====================
         const uint32_t idesc = umma_idesc_tf32(NP, 0, 0);
         const uint32_t w_hi_s = smem_u32(W_hi), w_lo_s = smem_u32(W_lo);
         int it = 0, wk = 0;
@@ -318,17 +329,20 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                 tc_fence_after();
                 const uint32_t a_hi_s = smem_u32(A_base + (size_t)s * 2 * geo.a_bytes), a_lo_s = a_hi_s + geo.a_bytes;
                 const uint32_t wkb = (uint32_t)kb * 2 * geo.w_bytes;
-                for (int ks = 0; ks < (KP >> 3); ks++) {
-                    uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = wkb + (uint32_t)ks * 2 * geo.w_lbo;
-                    uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
-                    uint64_t dbh = umma_desc(w_hi_s + wo, geo.w_lbo, 128), dbl = umma_desc(w_lo_s + wo, geo.w_lbo, 128);
-                    umma_tf32(acc, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                    umma_tf32(acc, dal, dbh, idesc, 1u);
-                    umma_tf32(acc, dah, dbl, idesc, 1u);
+                if (elect_one_sync()) {
+                    for (int ks = 0; ks < (KP >> 3); ks++) {
+                        uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = wkb + (uint32_t)ks * 2 * geo.w_lbo;
+                        uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
+                        uint64_t dbh = umma_desc(w_hi_s + wo, geo.w_lbo, 128), dbl = umma_desc(w_lo_s + wo, geo.w_lbo, 128);
+                        umma_tf32(acc, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(acc, dal, dbh, idesc, 1u);
+                        umma_tf32(acc, dah, dbl, idesc, 1u);
+                    }
+                    umma_commit(bar_empty + 8u * s);    // smem stage may be refilled once these MMAs retire
+                    if (kb == nkb - 1) umma_commit(bar_tfull + 8u * a);        // accumulator ready for the epilogue warps
                 }
-                umma_commit(bar_empty + 8u * s);    // smem stage may be refilled once these MMAs retire
+                __syncwarp();
             }
-            umma_commit(bar_tfull + 8u * a);        // accumulator ready for the epilogue warps
         }
     }
     tc_fence_before();
@@ -492,7 +506,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = tmem_base_uniform(tmem_slot);
     const uint32_t bar_full = smem_u32(mbar), bar_empty = smem_u32(mbar + TCW_STAGES), bar_done = smem_u32(mbar + 2 * TCW_STAGES);
 
     if (warp < TCW_PW) {
@@ -602,8 +616,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
             }
         }
         }
-    } else if (lane == 0) {
-        // ===================== MMA issuer (one thread) =====================
+    } else {
+        // ===================== MMA issuer: warp 8 runs the loop converged, one elected lane issues =====================
         const uint32_t idesc = umma_idesc_tf32(geo.KWP, 0, 0);
         for (int it = 0; it < nstage; it++) {
             const int s = it % TCW_STAGES;
@@ -611,17 +625,21 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
             tc_fence_after();
             const uint32_t p_hi_s = smem_u32(tsm + (size_t)s * stage_bytes), p_lo_s = p_hi_s + geo.p_bytes;
             const uint32_t q_hi_s = p_lo_s + geo.p_bytes, q_lo_s = q_hi_s + geo.q_bytes;
-            for (int kb = 0; kb < TCW_BM / 8; kb++) {
-                uint32_t o = (uint32_t)kb * 2 * TCW_LBO;
-                uint64_t dah = umma_desc(p_hi_s + o, TCW_LBO, TCW_SBO), dal = umma_desc(p_lo_s + o, TCW_LBO, TCW_SBO);
-                uint64_t dbh = umma_desc(q_hi_s + o, TCW_LBO, TCW_SBO), dbl = umma_desc(q_lo_s + o, TCW_LBO, TCW_SBO);
-                umma_tf32(tmem, dah, dbh, idesc, (it == 0 && kb == 0) ? 0u : 1u);
-                umma_tf32(tmem, dal, dbh, idesc, 1u);
-                umma_tf32(tmem, dah, dbl, idesc, 1u);
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int kb = 0; kb < TCW_BM / 8; kb++) {
+                    uint32_t o = (uint32_t)kb * 2 * TCW_LBO;
+                    uint64_t dah = umma_desc(p_hi_s + o, TCW_LBO, TCW_SBO), dal = umma_desc(p_lo_s + o, TCW_LBO, TCW_SBO);
+                    uint64_t dbh = umma_desc(q_hi_s + o, TCW_LBO, TCW_SBO), dbl = umma_desc(q_lo_s + o, TCW_LBO, TCW_SBO);
+                    umma_tf32(tmem, dah, dbh, idesc, (it == 0 && kb == 0) ? 0u : 1u);
+                    umma_tf32(tmem, dal, dbh, idesc, 1u);
+                    umma_tf32(tmem, dah, dbl, idesc, 1u);
+                }
+                umma_commit(bar_empty + 8u * s);
+                if (it == nstage - 1) umma_commit(bar_done);
             }
-            umma_commit(bar_empty + 8u * s);
+            __syncwarp();
         }
-        umma_commit(bar_done);
     }
     tc_fence_before();
     __syncthreads();

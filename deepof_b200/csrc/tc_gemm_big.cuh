@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) gemm_big_tc_kernel(const GemmA
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = tmem_base_uniform(tmem_slot);
     const uint32_t bar_full = smem_u32(mbar), bar_empty = smem_u32(mbar + S);
     const uint32_t bar_tfull = smem_u32(mbar + 2 * S), bar_tempty = smem_u32(mbar + 2 * S + 2);
 
@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) gemm_big_tc_kernel(const GemmA
             tc_fence_before();
             mbar_arrive(bar_tempty + 8u * a);
         }
-    } else if (lane == 0) {
-        // ===================== MMA issuer (one thread) =====================
+    } else {
+        // ===================== MMA issuer: warp 8 runs the loop converged, one elected lane issues =====================
         const uint32_t idesc = umma_idesc_tf32(TCB_NT, 0, 0);
         int it = 0, wk = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
@@ -231,17 +231,20 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) gemm_big_tc_kernel(const GemmA
                 const uint32_t w_hi_s = a_lo_s + TCB_A_BYTES, w_lo_s = w_hi_s + TCB_W_BYTES;
                 const int kcols = g.K - kb * TCB_KB < TCB_KB ? g.K - kb * TCB_KB : TCB_KB;
                 const int ksteps = (kcols + 7) >> 3;
-                for (int ks = 0; ks < ksteps; ks++) {
-                    const uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * TCB_W_LBO;
-                    const uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
-                    const uint64_t dbh = umma_desc(w_hi_s + wo, TCB_W_LBO, 128), dbl = umma_desc(w_lo_s + wo, TCB_W_LBO, 128);
-                    umma_tf32(acc, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                    umma_tf32(acc, dal, dbh, idesc, 1u);
-                    umma_tf32(acc, dah, dbl, idesc, 1u);
+                if (elect_one_sync()) {
+                    for (int ks = 0; ks < ksteps; ks++) {
+                        const uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = (uint32_t)ks * 2 * TCB_W_LBO;
+                        const uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
+                        const uint64_t dbh = umma_desc(w_hi_s + wo, TCB_W_LBO, 128), dbl = umma_desc(w_lo_s + wo, TCB_W_LBO, 128);
+                        umma_tf32(acc, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(acc, dal, dbh, idesc, 1u);
+                        umma_tf32(acc, dah, dbl, idesc, 1u);
+                    }
+                    umma_commit(bar_empty + 8u * s);    // the stage may be refilled once these MMAs retire
+                    if (kb == nkb - 1) umma_commit(bar_tfull + 8u * a);        // accumulator ready for the epilogue warps
                 }
-                umma_commit(bar_empty + 8u * s);    // the stage may be refilled once these MMAs retire
+                __syncwarp();
             }
-            umma_commit(bar_tfull + 8u * a);        // accumulator ready for the epilogue warps
         }
     }
     tc_fence_before();

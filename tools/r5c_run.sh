@@ -1,19 +1,12 @@
 mkdir -p gpurun_out
-nvidia-smi topo -m 2>&1 | head -8 > gpurun_out/r5n_topo.txt
-timeout 900 python -m pytest tests/test_multigpu_gpu.py -m gpu -q --no-header -p no:cacheprovider -s > gpurun_out/r5n_tests_mgpu.log 2>&1
-tail -12 gpurun_out/r5n_tests_mgpu.log
-for ar in peer nccl; do
-DOF_ALLREDUCE=$ar timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 5 --no-secondary > gpurun_out/r5n_bench_n2_$ar.json 2> gpurun_out/r5n_bench_n2_$ar.err
+timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_tfm_train_gpu.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/r5o_tests.log 2>&1
+tail -4 gpurun_out/r5o_tests.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r5o_bench.json 2> gpurun_out/r5o_bench.err
 python - <<PY
 import json
-try:
-    d = json.loads(open("gpurun_out/r5n_bench_n2_$ar.json").read().strip().splitlines()[-1])
-    print("$ar", "value", round(d["value"]), "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), d.get("allreduce"))
-    print({k: round(v["ms_per_step"],4) for k,v in d["kernels"].items() if "peer" in k or "adam" in k})
-except Exception as e:
-    print("parse failed", e); print(open("gpurun_out/r5n_bench_n2_$ar.err").read()[-3000:])
+d = json.loads(open("gpurun_out/r5o_bench.json").read().strip().splitlines()[-1])
+print("value", round(d["value"]), "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), "launches", d["gpu_launches"])
+for s in d["secondary"]:
+    print(s.get("workload","")[:30], round(s.get("value",0)), s.get("ms_per_step"), s.get("error"))
+    km=s["kernels_ms"]; print("    ", sorted(km.items(), key=lambda kv:-kv[1])[:6])
 PY
-done
-timeout 600 python bench.py --steps 20 --warmup 5 --no-secondary --no-cpu-baseline | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=1', round(d['value']), round(d['ms_per_step'],3))"
