@@ -16,8 +16,8 @@
 // MN-major (M = gate column, K = sequence: the weight gradients) — tools/probe_kmajor_sw32.cu pins both readings.
 // All products are 3xTF32 (hi.hi + lo.hi + hi.lo, lo = exact remainder); the bias column multiplies an all-ones tile.
 //
-// Shared memory at H = 32, I = 32: dG 2 x 4 blocks + XH 2 x 2 blocks of R x 128 B, weights 50 KB -> R = 112 rows per tile
-// (57 344 sequences = 512 tiles exactly); H = 16 uses R = 128.
+// Shared memory at H = 32, I = 32: dG 2 x 4 blocks + XH 2 x 2 blocks of R x 128 B, the two TMA staging tiles (h_prev, dOut)
+// of R x 128 B, weights 50 KB -> R = 96 rows per tile; H = 16 uses R = 128.
 #pragma once
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -40,7 +40,9 @@ struct GruBwdwArgs {
     long long* dbg;           // null, or [8 roles][T][4] clock64 stamps of CTA (0, 0) (tools/prof_gru_bwdw.py)
 };
 
-struct GruBwdwGeom { int whh_lbo, wih_lbo, tmem_cols; uint32_t whh_bytes, wih_bytes, dg_bytes, xh_bytes; };
+struct GruBwdwGeom { int whh_lbo, wih_lbo, tmem_cols; uint32_t whh_bytes, wih_bytes, dg_bytes, xh_bytes, st_bytes; };
+// TMA views of Hout and dOut: [2H columns (contiguous), T steps, S sequences]; box = [H columns of one direction, 1 step, R sequences]
+struct GruBwdwMaps { CUtensorMap Hout, dOut; };
 
 #define GBW_THREADS 512          // warps 0-3 x loaders + dX drain + epilogue | 4-11 gate warps | 12 MMA issuer A (dh, dX) |
                                  // 13 MMA issuer B (weight gradients) | 14-15 x loaders
@@ -61,6 +63,15 @@ __device__ __forceinline__ uint32_t sw32_unit(int r, int c8) {
 }
 // the two 16-byte halves of one unit, hi / lo planes.  `sel` (= (row >> 2) & 1) swaps the order of the two stores so that
 // rows r and r + 4 of a quarter-warp (same unit position) never hit the same banks in the same instruction
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -81,10 +92,10 @@ __device__ __forceinline__ void st_unit(uint32_t hi_s, uint32_t lo_s, uint32_t o
 
 // register budget per role (setmaxnreg, per warpgroup): the gate warps keep a whole step of saved gates in flight
 // (24 x 16-byte loads per thread at H = 32); 8 x 32 x GATE + 8 x 32 x OTHER = 64 K registers
-template <int H> struct GbwRegs { static constexpr int GATE = H == 32 ? 176 : 136, OTHER = H == 32 ? 80 : 120; };
+template <int H> struct GbwRegs { static constexpr int GATE = H == 32 ? 184 : 136, OTHER = H == 32 ? 72 : 120; };
 
 template <int H, int R, int KQM>
-__global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBwdwArgs a, const GruBwdwGeom geo) {
+__global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __grid_constant__ GruBwdwMaps maps, const GruBwdwArgs a, const GruBwdwGeom geo) {
     constexpr int HC = H / 2;                                         // hidden units per gate thread
     constexpr int NBP = 4 * H / 32;                                   // 32-column blocks of the dG tile
     extern __shared__ unsigned char bw_raw[];
@@ -95,15 +106,20 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
     unsigned char* DG_lo = DG_hi + geo.dg_bytes;
     unsigned char* XH_hi = DG_lo + geo.dg_bytes;                      // columns [0, I) x_t | [I, I+H) h_prev
     unsigned char* XH_lo = XH_hi + geo.xh_bytes;
-    unsigned char* Whh_hi = XH_lo + geo.xh_bytes;                     // B operand [N = H][K = 3H]:  W_hh[c][j] at (n = j, k = c)
+    // h_prev / dOut tiles of ONE step, [R rows][H floats], written by TMA (hardware swizzle: 16-byte chunk c of row r sits at
+    // chunk c ^ (r & 7) for 128-byte rows, c ^ ((r >> 1) & 3) for 64-byte rows): a row-per-lane global load touches 32
+    // lines per warp instruction and the gate warps spent a third of every step issuing them
+    unsigned char* ST_hp = XH_lo + geo.xh_bytes;
+    unsigned char* ST_do = ST_hp + geo.st_bytes;
+    unsigned char* Whh_hi = ST_do + geo.st_bytes;                     // B operand [N = H][K = 3H]:  W_hh[c][j] at (n = j, k = c)
     unsigned char* Whh_lo = Whh_hi + geo.whh_bytes;
     unsigned char* Wih_hi = Whh_lo + geo.whh_bytes;                   // B operand [N = I][K = 3H]:  W_ih[c][i] at (n = i, k = c)
     unsigned char* Wih_lo = Wih_hi + geo.wih_bytes;
     float* ones = reinterpret_cast<float*>(Wih_lo + geo.wih_bytes);   // B operand [N = 16][K = 8] of 1.0f: every K step reads it
     uint64_t* mbar = reinterpret_cast<uint64_t*>(ones + 128);
     // mbar: [0] a_full (gate threads + x loaders) [1] dh_full (commit A) [2] dx_full (commit A) [3] w_done (commit B)
-    //       [4] dx_read (128 drain threads: acc_dx read out of TMEM)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 6);
+    //       [4] dx_read (128 drain threads: acc_dx read out of TMEM) [5] st_full (TMA bytes) [6] st_free (256 gate threads)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 8);
     int* lens_s = reinterpret_cast<int*>(tmem_slot + 4);              // [128]; -1 outside the tile / batch
     const int s0 = blockIdx.x * R;
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
@@ -113,6 +129,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
     if (tid == 32) {
         mbar_init(smem_u32(mbar + 0), 256 + GBW_NXL); mbar_init(smem_u32(mbar + 1), 1);
         mbar_init(smem_u32(mbar + 2), 1); mbar_init(smem_u32(mbar + 3), 1); mbar_init(smem_u32(mbar + 4), 128);
+        mbar_init(smem_u32(mbar + 5), 1); mbar_init(smem_u32(mbar + 6), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -145,7 +162,18 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
     tc_fence_after();
     const uint32_t tmem = tmem_base_uniform(tmem_slot);
     const uint32_t bar_afull = smem_u32(mbar), bar_dh = smem_u32(mbar + 1), bar_dx = smem_u32(mbar + 2), bar_w = smem_u32(mbar + 3),
-                   bar_dxr = smem_u32(mbar + 4);
+                   bar_dxr = smem_u32(mbar + 4), bar_stfull = smem_u32(mbar + 5), bar_stfree = smem_u32(mbar + 6);
+    // TMA of the h_prev / dOut tiles of `step_` (one thread); a step without either tile still completes the phase
+    auto issue_stage = [&](int step_) {
+        const int t = dir ? step_ : (T - 1 - step_);
+        const int tp = dir ? t + 1 : t - 1;
+        const bool hp_on = tp >= 0 && tp < T, do_on = a.dOut != nullptr;
+        const uint32_t bytes = (hp_on ? geo.st_bytes : 0u) + (do_on ? geo.st_bytes : 0u);
+        if (bytes) mbar_expect_tx(bar_stfull, bytes); else mbar_arrive(bar_stfull);
+        if (hp_on) tma_load_3d(smem_u32(ST_hp), &maps.Hout, dir * H, tp, s0, bar_stfull);
+        if (do_on) tma_load_3d(smem_u32(ST_do), &maps.dOut, dir * H, t, s0, bar_stfull);
+    };
+    if (tid == 14 * 32) issue_stage(0);
     // TMEM columns: acc_dh [H] | acc_dx [I] | weight-gradient accumulators.  The TMEM accumulator TRUNCATES on every
     // tcgen05.mma accumulate, a bias that grows with the number of accumulates (T * R/8 * 3 = 1050 at T = 25: 2e-5
     // relative, measured), so the hi.hi products alternate between two accumulators by step parity and the small lo
@@ -180,27 +208,38 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
         float4 r4[HC / 4], z4[HC / 4], n4[HC / 4], q4[HC / 4], hp4[HC / 4], do4[HC / 4];
         auto load_q = [&](int q, int step_) {
             const int t = dir ? step_ : (T - 1 - step_);
-            const int tp = dir ? t + 1 : t - 1;
             const float* gt = GtT + (size_t)t * H * 512;
             const int pq = q ^ sel;                                   // physical chunk of logical chunk q
             const int cq = (j0 >> 2) + pq;
-            hp4[q] = make_float4(0.f, 0.f, 0.f, 0.f); do4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t < len) {
                 r4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)cq * 512));
                 z4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(H / 4 + cq) * 512));
                 n4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(2 * (H / 4) + cq) * 512));
                 q4[q] = __ldg(reinterpret_cast<const float4*>(gt + (size_t)(3 * (H / 4) + cq) * 512));
-                if (tp >= 0 && tp < len) hp4[q] = __ldg(reinterpret_cast<const float4*>(a.Hout + ((size_t)s * T + tp) * 2 * H + dir * H + j0 + pq * 4));
-                if (a.dOut) do4[q] = __ldg(reinterpret_cast<const float4*>(a.dOut + ((size_t)s * T + t) * 2 * H + dir * H + j0 + pq * 4));
             } else {
                 r4[q] = z4[q] = n4[q] = q4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        // h_prev / dOut chunks of this thread's row from the TMA-staged tiles
+        const uint32_t st_hp = smem_u32(ST_hp), st_do = smem_u32(ST_do);
+        const uint32_t st_row = (uint32_t)row * (uint32_t)(H * 4);
+        const int st_x = (H == 32) ? (row & 7) : ((row >> 1) & 3);
+        auto read_stage = [&](int step_) {
+            const int t = dir ? step_ : (T - 1 - step_);
+            const int tp = dir ? t + 1 : t - 1;
+            mbar_wait(bar_stfull, (uint32_t)(step_ & 1));
+#pragma unroll
+            for (int q = 0; q < HC / 4; q++) {
+                const uint32_t off = st_row + (uint32_t)((((j0 >> 2) + (q ^ sel)) ^ st_x) << 4);
+                hp4[q] = (t < len && tp >= 0 && tp < len) ? lds128(st_hp + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                do4[q] = (t < len && a.dOut) ? lds128(st_do + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            mbar_arrive(bar_stfree);
         };
         // DRAM -> L2 two steps ahead (no registers held): one SM can only keep ~30 KB of loads in flight, so a step's 100 KB
         // of saved gates / h_prev / dOut / x must already sit in L2 when the register loads above are issued
         auto prefetch_step = [&](int step_) {
             const int t = dir ? step_ : (T - 1 - step_);
-            const int tp = dir ? t + 1 : t - 1;
             if (t >= len) return;
             if ((lane & 7) == 0) {                                          // one lane per 128-byte line of the tiled gates
                 const float* gn = GtT + ((size_t)t * H + (j0 >> 2)) * 512;
@@ -210,10 +249,6 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                     for (int qq = 0; qq < HC / 4; qq++)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)(g4 * (H / 4) + qq) * 512));
             }
-            if (half == 0) {
-                if (tp >= 0 && tp < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Hout + ((size_t)s * T + tp) * 2 * H + dir * H));
-                if (a.dOut) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dOut + ((size_t)s * T + t) * 2 * H + dir * H));
-            }
         };
 #pragma unroll
         for (int q = 0; q < HC / 4; q++) load_q(q, 0);
@@ -222,6 +257,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
             const int t = dir ? step : (T - 1 - step);
             const bool valid = t < len;
             if (H == 32 && step + 2 < T) prefetch_step(step + 2);
+            read_stage(step);
             // recurrent term of the previous step: dh = part + dG_{prev} . W_hh
             float dh[HC];
             const int grole = warp == 4 ? 0 : (warp == 11 ? 1 : -1);
@@ -238,6 +274,36 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                 for (int j = 0; j < HC; j++) dh[j] = part[j];
             }
             if (grole >= 0 && lane == 0) GBW_STAMP(grole, step, 1);
+            // gate gradients of the whole row segment into registers BEFORE waiting for the tiles: only the stores need them
+            float o_r[HC / 4][4], o_z[HC / 4][4], o_h[HC / 4][4], o_n[HC / 4][4];
+#pragma unroll
+            for (int q = 0; q < HC / 4; q++) {
+                const float r[4] = {r4[q].x, r4[q].y, r4[q].z, r4[q].w}, z[4] = {z4[q].x, z4[q].y, z4[q].z, z4[q].w};
+                const float n[4] = {n4[q].x, n4[q].y, n4[q].z, n4[q].w}, hn[4] = {q4[q].x, q4[q].y, q4[q].z, q4[q].w};
+                const float hp[4] = {hp4[q].x, hp4[q].y, hp4[q].z, hp4[q].w}, dov[4] = {do4[q].x, do4[q].y, do4[q].z, do4[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (valid) {
+                        const float d = dh[q * 4 + e] + dov[e];
+                        const float dn = d * (1.0f - z[e]);
+                        const float dz = d * (hp[e] - n[e]);
+                        const float dan = dn * (1.0f - n[e] * n[e]);
+                        o_z[q][e] = dz * z[e] * (1.0f - z[e]);
+                        o_r[q][e] = dan * hn[e] * r[e] * (1.0f - r[e]);
+                        o_h[q][e] = dan * r[e];
+                        o_n[q][e] = dan;
+                        part[q * 4 + e] = d * z[e];
+                    } else {
+                        o_z[q][e] = o_r[q][e] = o_h[q][e] = o_n[q][e] = 0.f;
+                        part[q * 4 + e] = dh[q * 4 + e];
+                    }
+                }
+            }
+            // the saved-gate registers are dead now: next step's loads go out here, a whole MMA round trip ahead of their use
+            if (step + 1 < T) {
+#pragma unroll
+                for (int q = 0; q < HC / 4; q++) load_q(q, step + 1);
+            }
             // the tiles are free again once every MMA of the previous step retired
             if (step > 0) {
                 mbar_wait(bar_dx, (uint32_t)((step - 1) & 1));
@@ -247,48 +313,20 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
             if (in_tile) {
 #pragma unroll
                 for (int p = 0; p < HC / 8; p++) {
-                    float o_r[2][4], o_z[2][4], o_h[2][4], o_n[2][4], hpv[2][4];
-#pragma unroll
-                    for (int e2 = 0; e2 < 2; e2++) {
-                        const int q = 2 * p + e2;
-                        const float r[4] = {r4[q].x, r4[q].y, r4[q].z, r4[q].w}, z[4] = {z4[q].x, z4[q].y, z4[q].z, z4[q].w};
-                        const float n[4] = {n4[q].x, n4[q].y, n4[q].z, n4[q].w}, hn[4] = {q4[q].x, q4[q].y, q4[q].z, q4[q].w};
-                        const float hp[4] = {hp4[q].x, hp4[q].y, hp4[q].z, hp4[q].w}, dov[4] = {do4[q].x, do4[q].y, do4[q].z, do4[q].w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            hpv[e2][e] = hp[e];
-                            if (valid) {
-                                const float d = dh[q * 4 + e] + dov[e];
-                                const float dn = d * (1.0f - z[e]);
-                                const float dz = d * (hp[e] - n[e]);
-                                const float dan = dn * (1.0f - n[e] * n[e]);
-                                o_z[e2][e] = dz * z[e] * (1.0f - z[e]);
-                                o_r[e2][e] = dan * hn[e] * r[e] * (1.0f - r[e]);
-                                o_h[e2][e] = dan * r[e];
-                                o_n[e2][e] = dan;
-                                part[q * 4 + e] = d * z[e];
-                            } else {
-                                o_z[e2][e] = o_r[e2][e] = o_h[e2][e] = o_n[e2][e] = 0.f;
-                                part[q * 4 + e] = dh[q * 4 + e];
-                            }
-                        }
-                    }
                     const int c8 = j0 + 8 * p;                               // column inside a gate block
-                    st_unit(dg_hi, dg_lo, sw32_unit<R>(row, c8), o_r[0], o_r[1], sel);
-                    st_unit(dg_hi, dg_lo, sw32_unit<R>(row, H + c8), o_z[0], o_z[1], sel);
-                    st_unit(dg_hi, dg_lo, sw32_unit<R>(row, 2 * H + c8), o_h[0], o_h[1], sel);
-                    st_unit(dg_hi, dg_lo, sw32_unit<R>(row, 3 * H + c8), o_n[0], o_n[1], sel);
-                    st_unit(xh_hi, xh_lo, sw32_unit<R>(row, I + c8), hpv[0], hpv[1], sel);
+                    const float hp0[4] = {hp4[2 * p].x, hp4[2 * p].y, hp4[2 * p].z, hp4[2 * p].w};
+                    const float hp1[4] = {hp4[2 * p + 1].x, hp4[2 * p + 1].y, hp4[2 * p + 1].z, hp4[2 * p + 1].w};
+                    st_unit(dg_hi, dg_lo, sw32_unit<R>(row, c8), o_r[2 * p], o_r[2 * p + 1], sel);
+                    st_unit(dg_hi, dg_lo, sw32_unit<R>(row, H + c8), o_z[2 * p], o_z[2 * p + 1], sel);
+                    st_unit(dg_hi, dg_lo, sw32_unit<R>(row, 2 * H + c8), o_h[2 * p], o_h[2 * p + 1], sel);
+                    st_unit(dg_hi, dg_lo, sw32_unit<R>(row, 3 * H + c8), o_n[2 * p], o_n[2 * p + 1], sel);
+                    st_unit(xh_hi, xh_lo, sw32_unit<R>(row, I + c8), hp0, hp1, sel);
                 }
             }
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar_afull);
             if (grole >= 0 && lane == 0) GBW_STAMP(grole, step, 3);
-            if (step + 1 < T) {                                       // next step's loads: in flight during the MMA round trip
-#pragma unroll
-                for (int q = 0; q < HC / 4; q++) load_q(q, step + 1);
-            }
         }
     } else if (warp == GBW_MMA_A) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GbwRegs<H>::OTHER));
@@ -345,6 +383,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
             const uint64_t d1 = umma_desc(smem_u32(ones), 256, 128);
             for (int step = 0; step < T; step++) {
                 mbar_wait(bar_afull, (uint32_t)(step & 1));
+                mbar_wait(bar_dh, (uint32_t)(step & 1));                     // dh first: it is on the serial chain and the pipe is shared
                 tc_fence_after();
                 if (lane == 0) GBW_STAMP(3, step, 0);
                 const uint32_t par = (uint32_t)(step & 1);
@@ -408,20 +447,31 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.X + (size_t)(s0 + r) * a.x_ss + (size_t)t * a.x_st + kq * 4));
             }
         };
+        // x_{step+1} is staged BEFORE dX_step is drained: both wait for MMAs of `step` that retire at about the same time, and
+        // only the staging is on the path to the next a_full (the drain has until the dX MMAs of step + 1)
+        const int lrole = warp == 0 ? 4 : (warp == 14 ? 5 : -1);
         load_x(0);
         if (H == 32 && T > 1) prefetch_x(1);
+        stage_x();
+        fence_async_smem();
+        mbar_arrive(bar_afull);
         for (int step = 0; step < T; step++) {
             const int t = dir ? step : (T - 1 - step);
             if (H == 32 && step + 2 < T) prefetch_x(step + 2);
-            const int lrole = warp == 0 ? 4 : (warp == 14 ? 5 : -1);
             if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 0);
-            if (step > 0) mbar_wait(bar_w, (uint32_t)((step - 1) & 1));      // the weight-gradient MMAs of the previous step read XH
-            if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 1);
-            stage_x();
-            fence_async_smem();
-            mbar_arrive(bar_afull);
-            if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 2);
             if (step + 1 < T) load_x(step + 1);
+            if (tid == 14 * 32 && step + 1 < T) {
+                mbar_wait(bar_stfree, (uint32_t)(step & 1));
+                issue_stage(step + 1);
+            }
+            if (step + 1 < T) {
+                mbar_wait(bar_w, (uint32_t)(step & 1));                      // the weight-gradient MMAs of this step read XH
+                if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 1);
+                stage_x();
+                fence_async_smem();
+                mbar_arrive(bar_afull);
+                if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 2);
+            }
             if (warp < 4) {
                 // dX_t rows from TMEM -> HBM (vector reductions: both directions add into the same rows)
                 mbar_wait(bar_dx, (uint32_t)(step & 1));
@@ -507,7 +557,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const GruBw
     if (warp == 0) tmem_dealloc(tmem, geo.tmem_cols);
 }
 
-static inline int gru_bwdw_rows(int H) { return H == 32 ? 112 : 128; }
+static inline int gru_bwdw_rows(int H) { return H == 32 ? 96 : 128; }
 
 static bool gru_bwdw_geom(int H, int I, GruBwdwGeom& g, size_t& smem) {
     const int R = gru_bwdw_rows(H);
@@ -517,8 +567,9 @@ static bool gru_bwdw_geom(int H, int I, GruBwdwGeom& g, size_t& smem) {
     g.wih_bytes = (uint32_t)(3 * H / 4) * g.wih_lbo;
     g.dg_bytes = (uint32_t)(4 * H / 32) * R * 128;
     g.xh_bytes = (uint32_t)((I + H + 31) / 32) * R * 128;
+    g.st_bytes = (uint32_t)R * H * 4;
     g.tmem_cols = tmem_cols_for(H + I + 3 * (I + H) + 48);
-    smem = 1024 + 2 * (size_t)g.dg_bytes + 2 * (size_t)g.xh_bytes + 2 * (size_t)g.whh_bytes + 2 * (size_t)g.wih_bytes + 512 + 6 * 8 + 16 + 128 * 4 + 64;
+    smem = 1024 + 2 * (size_t)g.dg_bytes + 2 * (size_t)g.xh_bytes + 2 * (size_t)g.st_bytes + 2 * (size_t)g.whh_bytes + 2 * (size_t)g.wih_bytes + 512 + 6 * 8 + 16 + 128 * 4 + 64;
     return smem <= 227 * 1024;
 }
 
@@ -529,15 +580,42 @@ static bool gru_bwdw_tc_eligible(int H, int I) {
     return g_gru_bwdw && gru_bwd_tc_eligible(H, I) && ((I + H) % 16 == 0) && (I % 16 == 0) && gru_bwdw_geom(H, I, g, smem);
 }
 
+// 3-D TMA view of a [S, T, 2H] fp32 activation: box = [H columns, 1 step, R sequences], hardware swizzle of the row width
+struct Tmap3Key { const void* base; int S, T, H, R; };
+struct Tmap3Entry { Tmap3Key k; CUtensorMap m; };
+static std::vector<Tmap3Entry> g_tmaps3;
+
+static int tmap_seq3d(const float* base, int S, int T, int H, int R, CUtensorMap* out) {
+    for (const Tmap3Entry& e : g_tmaps3)
+        if (e.k.base == base && e.k.S == S && e.k.T == T && e.k.H == H && e.k.R == R) { *out = e.m; return DOF_OK; }
+    dof_tmap_encode_fn enc = tmap_encoder();
+    if (!enc) DOF_FAIL(DOF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    Tmap3Entry e;
+    e.k = Tmap3Key{base, S, T, H, R};
+    memset(&e.m, 0, sizeof(e.m));
+    cuuint64_t dims[3] = {(cuuint64_t)(2 * H), (cuuint64_t)T, (cuuint64_t)S};
+    cuuint64_t strides[2] = {(cuuint64_t)2 * H * 4, (cuuint64_t)T * 2 * H * 4};
+    cuuint32_t box[3] = {(cuuint32_t)H, 1, (cuuint32_t)R};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&e.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, H == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DOF_FAIL(DOF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a [%d, %d, %d] view", (int)r, S, T, 2 * H);
+    if (g_tmaps3.size() >= 64) g_tmaps3.clear();
+    g_tmaps3.push_back(e);
+    *out = e.m;
+    return DOF_OK;
+}
+
 template <int H, int R, int KQM>
-static int gru_bwdw_launch_t(const GruBwdwArgs& a, const GruBwdwGeom& geo, size_t smem, cudaStream_t st) {
+static int gru_bwdw_launch_t(const GruBwdwMaps& maps, const GruBwdwArgs& a, const GruBwdwGeom& geo, size_t smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         DOF_CUDA(cudaFuncSetAttribute(gru_bwdw_tc_kernel<H, R, KQM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     dim3 grid(cdiv(a.S, R), 2);
-    gru_bwdw_tc_kernel<H, R, KQM><<<grid, GBW_THREADS, smem, st>>>(a, geo);
+    gru_bwdw_tc_kernel<H, R, KQM><<<grid, GBW_THREADS, smem, st>>>(maps, a, geo);
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -552,14 +630,18 @@ static int launch_gru_bwdw_tc(const GruBwdwArgs& a, cudaStream_t st) {
                  rows * 4.0 * a.H * (4 + 1 + (a.dOut ? 1 : 0)) + rows * 4.0 * a.I * (a.dXmask ? 3 : 2));
     const int KQ = a.I / 4, R = gru_bwdw_rows(a.H);
     const int kqm = cdiv(R * KQ, GBW_NXL);
+    if (!aligned16(a.Hout) || (a.dOut && !aligned16(a.dOut))) DOF_FAIL(DOF_ERR_ARG, "fused GRU backward: Hout / dOut must be 16-byte aligned");
+    GruBwdwMaps maps;
+    DOF_TRY(tmap_seq3d(a.Hout, a.S, a.T, a.H, R, &maps.Hout));
+    if (a.dOut) DOF_TRY(tmap_seq3d(a.dOut, a.S, a.T, a.H, R, &maps.dOut)); else maps.dOut = maps.Hout;
     if (a.H == 32) {
-        if (kqm <= 3) return gru_bwdw_launch_t<32, 112, 3>(a, geo, smem, st);
-        if (kqm <= 5) return gru_bwdw_launch_t<32, 112, 5>(a, geo, smem, st);
-        if (kqm <= 7) return gru_bwdw_launch_t<32, 112, 7>(a, geo, smem, st);
-        return gru_bwdw_launch_t<32, 112, 10>(a, geo, smem, st);
+        if (kqm <= 3) return gru_bwdw_launch_t<32, 96, 3>(maps, a, geo, smem, st);
+        if (kqm <= 5) return gru_bwdw_launch_t<32, 96, 5>(maps, a, geo, smem, st);
+        if (kqm <= 7) return gru_bwdw_launch_t<32, 96, 7>(maps, a, geo, smem, st);
+        return gru_bwdw_launch_t<32, 96, 10>(maps, a, geo, smem, st);
     }
-    if (kqm <= 3) return gru_bwdw_launch_t<16, 128, 3>(a, geo, smem, st);
-    if (kqm <= 6) return gru_bwdw_launch_t<16, 128, 6>(a, geo, smem, st);
-    if (kqm <= 8) return gru_bwdw_launch_t<16, 128, 8>(a, geo, smem, st);
-    return gru_bwdw_launch_t<16, 128, 11>(a, geo, smem, st);
+    if (kqm <= 3) return gru_bwdw_launch_t<16, 128, 3>(maps, a, geo, smem, st);
+    if (kqm <= 6) return gru_bwdw_launch_t<16, 128, 6>(maps, a, geo, smem, st);
+    if (kqm <= 8) return gru_bwdw_launch_t<16, 128, 8>(maps, a, geo, smem, st);
+    return gru_bwdw_launch_t<16, 128, 11>(maps, a, geo, smem, st);
 }

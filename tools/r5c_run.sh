@@ -1,12 +1,16 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_tfm_train_gpu.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/r5o_tests.log 2>&1
-tail -4 gpurun_out/r5o_tests.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r5o_bench.json 2> gpurun_out/r5o_bench.err
+python tools/prof_gru_bwdw.py 32 32 > gpurun_out/r5r_timeline_h32.txt 2>&1; python tools/prof_gru_bwdw.py 16 64 > gpurun_out/r5r_timeline_h16.txt 2>&1
+grep "fused gru\|cycles per step" gpurun_out/r5r_timeline_h32.txt gpurun_out/r5r_timeline_h16.txt
+timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/r5r_tests.log 2>&1
+tail -4 gpurun_out/r5r_tests.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r5r_bench.json 2> gpurun_out/r5r_bench.err
 python - <<PY
 import json
-d = json.loads(open("gpurun_out/r5o_bench.json").read().strip().splitlines()[-1])
+d = json.loads(open("gpurun_out/r5r_bench.json").read().strip().splitlines()[-1])
 print("value", round(d["value"]), "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), "launches", d["gpu_launches"])
+for k, v in sorted(d["kernels"].items(), key=lambda kv: -kv[1]["ms_per_step"])[:8]:
+    print("  %-16s n=%4.0f %8.3f ms %5.1f%% tf=%s gbs=%s" % (k, v["launches_per_step"], v["ms_per_step"], 100 * v["share"], round(v.get("tflops", 0), 1), round(v.get("gbs", 0))))
+print("bytes/step GB", sum(v["bytes_per_step"] for v in d["kernels"].values())/1e9)
 for s in d["secondary"]:
     print(s.get("workload","")[:30], round(s.get("value",0)), s.get("ms_per_step"), s.get("error"))
-    km=s["kernels_ms"]; print("    ", sorted(km.items(), key=lambda kv:-kv[1])[:6])
 PY
