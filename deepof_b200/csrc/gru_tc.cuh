@@ -20,6 +20,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include "tmap.cuh"
 
 struct GruTcArgs {
     const float* X; long long x_ss; int x_st;     // x_t of sequence s: X + s*x_ss + t*x_st, I floats (x_st = 0: repeated input)
@@ -29,6 +30,7 @@ struct GruTcArgs {
     float* Gt[2];        // [S,T,4H] = r|z|n|hn per direction, or null
     float* Hn;           // [S,2H] final states [fwd|bwd] or null
     int S, T, H, I;
+    long long* dbg;      // null, or [6 roles][T][4] clock64 stamps of CTA (0, 0) (tools/prof_gru.py)
     int gt_tiled;        // 1: Gt is written in the tiled layout the fused backward kernel reads (gru_bwd_tc.cuh):
                          //    Gt[((tile*T + t) * H + c) * 128 + row][4 floats], c = 16-byte chunk of r|z|n|hn
 };
@@ -62,10 +64,14 @@ __device__ __forceinline__ void tmem_ld_hc(uint32_t taddr, float (&v)[HC]) {
 }
 
 template <int H, int KQM, bool TILED>
-__global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs a, const GruTcGeom geo) {
+__global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap hmap, const GruTcArgs a, const GruTcGeom geo) {
     // H = 32: 8 gate warps (two threads per sequence); H = 16: 4 gate warps (one thread per sequence) — warps 8-11 join
     // the store warps instead, because the drain of the staged gate rows is what the gate warps wait for
     constexpr int NGATE = (H == 32) ? 8 : 4;
+    // H = 16, TILED (training): the drain is one thread, so warps 8-11 are free and join the x producers — at I = 64 four
+    // warps needed 5.3 k cycles per step for x_{t+1} (16 loads + 32 shared stores per thread) and the MMA warp waited for them
+    constexpr int NPROD = (TILED && H == 16) ? 256 : 128;
+    constexpr int PJ = KQM * 128 / NPROD;
     constexpr int HC = H / (NGATE / 4);                               // hidden units per gate thread
     extern __shared__ __align__(128) unsigned char gsm[];
     const int dir = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -78,20 +84,26 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
     unsigned char* Hs_lo = Hs_hi + geo.h_bytes;
     unsigned char* Xs = Hs_lo + geo.h_bytes;                         // 2 stages x (hi | lo)
     unsigned char* Gs = Xs + 2 * (size_t)geo.xst * geo.x_bytes;                // [128][gs] staged gate rows r|z|n|hn
-    unsigned char* Os = Gs + 128 * (size_t)geo.gs;                   // [128][os] staged output rows
+    // TILED (training): Gs is CHUNK-major, [(chunk c of r|z|n|hn) * 128 + row][16 B] = exactly the 128 x 4H block of the tiled
+    // gate layout, so ONE bulk copy drains it; Os is a dense [128][H] tile in the TMA swizzle of its row width (1024-byte
+    // aligned), drained by ONE tensor store.  Otherwise: padded row-major tiles drained by the store warps.
+    unsigned char* Os = TILED ? reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(Gs + 128 * (size_t)geo.gs) + 1023) & ~(uintptr_t)1023)
+                              : Gs + 128 * (size_t)geo.gs;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(Os + 128 * (size_t)geo.os);
     // mbar: [0,2) x_full (128), [2,4) x_empty (1), [4,6) acc_full (1), [6] h_ready (gate threads), [7] stage_full (gate threads), [8] stage_free (7 draining warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 10);
     float* bs = reinterpret_cast<float*>(tmem_slot + 4);             // [4H]: b_ir+b_hr | b_iz+b_hz | b_in | b_hn
     int* lens_s = reinterpret_cast<int*>(bs + 4 * H);                // [128] valid length of every row, -1 outside the batch
     const int s0 = blockIdx.x * 128;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define GTC_STAMP(role, step, slot) do { if (dbg_on) a.dbg[((role) * a.T + (step)) * 4 + (slot)] = clock64(); } while (0)
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), geo.tmem_cols);
     if (tid == 32) {
-        mbar_init(smem_u32(mbar + 0), 128); mbar_init(smem_u32(mbar + 1), 128);
+        mbar_init(smem_u32(mbar + 0), NPROD); mbar_init(smem_u32(mbar + 1), NPROD);
         mbar_init(smem_u32(mbar + 2), 1); mbar_init(smem_u32(mbar + 3), 1);
         mbar_init(smem_u32(mbar + 4), 1); mbar_init(smem_u32(mbar + 5), 1);
-        mbar_init(smem_u32(mbar + 6), NGATE * 32); mbar_init(smem_u32(mbar + 7), NGATE * 32); mbar_init(smem_u32(mbar + 8), GTC_NSTORE_ALL * 32);
+        mbar_init(smem_u32(mbar + 6), NGATE * 32); mbar_init(smem_u32(mbar + 7), NGATE * 32); mbar_init(smem_u32(mbar + 8), TILED ? 1 : GTC_NSTORE_ALL * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // weights: canonical K-major B operands, row n at n*16 B, K-chunk (4 floats) stride lbo
@@ -147,7 +159,9 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
         constexpr int CH = 8;
     auto store_step = [&](int step, int sw) {
             const int t = dir ? (T - 1 - step) : step;
+            if (warp == GTC_STORE_WARP && lane == 0) GTC_STAMP(3, step, 0);
             mbar_wait(bar_sfull, (uint32_t)(step & 1));
+            if (warp == GTC_STORE_WARP && lane == 0) GTC_STAMP(3, step, 1);
             if (want_g && TILED) {
                 // chunk-major tiles: one warp instruction = one 16-byte chunk of 32 consecutive rows (512 B contiguous)
                 float* gtile = Gt + ((size_t)blockIdx.x * T + t) * H * 512;
@@ -205,16 +219,18 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                 }
             }
             mbar_arrive(bar_sfree);                       // staged rows consumed: the gate warps may refill them
+            if (warp == GTC_STORE_WARP && lane == 0) GTC_STAMP(3, step, 2);
     };
-    if (warp < 4) {
+    if (warp < 4 || (NPROD == 256 && warp >= 8 && warp < 12)) {
+        const int ptid = warp < 4 ? tid : tid - 128;
         // ===================== x_t producers =====================
         // stage x_{step+1} (registers -> hi/lo split -> shared) while the global loads of x_{step+2} are in flight
-        float4 pre[KQM];
+        float4 pre[PJ];
         auto load_regs = [&](int step) {
             const int t = dir ? (T - 1 - step) : step;
 #pragma unroll
-            for (int j = 0; j < KQM; j++) {
-                const int i = tid + j * 128;
+            for (int j = 0; j < PJ; j++) {
+                const int i = ptid + j * NPROD;
                 const int row = i / KQ, kq = i - row * KQ;
                 const int s = s0 + row;
                 pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -227,8 +243,8 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
             unsigned char* X_hi = Xs + (size_t)st * 2 * geo.x_bytes;
             unsigned char* X_lo = X_hi + geo.x_bytes;
 #pragma unroll
-            for (int j = 0; j < KQM; j++) {
-                const int i = tid + j * 128;
+            for (int j = 0; j < PJ; j++) {
+                const int i = ptid + j * NPROD;
                 const int row = i / KQ, kq = i - row * KQ;
                 if (i >= 128 * KQ) continue;
                 float4 hi, lo;
@@ -240,14 +256,17 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
             fence_async_smem();
             mbar_arrive(bar_xfull + 8u * st);
         };
-        const bool help = (H == 32) && (want_g || want_o);
+        const bool help = !TILED && (H == 32) && (want_g || want_o);
         load_regs(0);
         stage_x(0);
         if (T > 1) load_regs(1);
         for (int step = 0; step + 1 < T; step++) {
+            if (warp == 0 && lane == 0) GTC_STAMP(4, step, 0);
             stage_x(step + 1);
+            if (warp == 0 && lane == 0) GTC_STAMP(4, step, 1);
             if (step + 2 < T) load_regs(step + 2);
             if (help) store_step(step, GTC_NSTORE + warp);         // x_{step+1} is staged: help draining step's rows
+            if (warp == 0 && lane == 0) GTC_STAMP(4, step, 2);
         }
         if (help) store_step(T - 1, GTC_NSTORE + warp);
     } else if (warp < 4 + NGATE) {
@@ -261,13 +280,16 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
         for (int j = 0; j < HC; j++) h[j] = 0.f;
         float* grow = reinterpret_cast<float*>(Gs + (size_t)row * geo.gs);
         float* orow = reinterpret_cast<float*>(Os + (size_t)row * geo.os);
+        const int ox = (H == 32) ? (row & 7) : ((row >> 1) & 3);   // TMA swizzle of the output tile: chunk c of row r sits at c ^ ox
         mbar_arrive(bar_h);                                   // h_0 (zeros) is in place
         for (int step = 0; step < T; step++) {
             const int t = dir ? (T - 1 - step) : step;
             const int buf = step & 1;
             const bool valid = t < len;
+            if (warp == 4 && lane == 0) GTC_STAMP(0, step, 0);
             mbar_wait(bar_acc + 8u * buf, (uint32_t)((step >> 1) & 1));
             tc_fence_after();
+            if (warp == 4 && lane == 0) GTC_STAMP(0, step, 1);
             const uint32_t trow = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 4 * H + j0);
             float vr[HC], vz[HC], vn[HC], vh[HC];
             tmem_ld_hc<HC>(trow, vr);
@@ -285,9 +307,20 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                 h[j] = valid ? hnew : h[j];
                 vr[j] = r; vz[j] = z; vn[j] = n; vh[j] = hn;
             }
+            if (warp == 4 && lane == 0) GTC_STAMP(0, step, 2);
             // the staging rows of the previous step must have left shared memory
             if (step > 0 && (want_g || want_o)) mbar_wait(bar_sfree, (uint32_t)((step - 1) & 1));
-            if (want_g) {
+            if (warp == 4 && lane == 0) GTC_STAMP(0, step, 3);
+            if (want_g && TILED) {
+#pragma unroll
+                for (int q = 0; q < HC / 4; q++) {
+                    float4* g4 = reinterpret_cast<float4*>(Gs) + (size_t)((j0 >> 2) + q) * 128 + row;      // chunk-major: 32 rows = 512 contiguous bytes
+                    g4[0] = make_float4(vr[q * 4], vr[q * 4 + 1], vr[q * 4 + 2], vr[q * 4 + 3]);
+                    g4[(H / 4) * 128] = make_float4(vz[q * 4], vz[q * 4 + 1], vz[q * 4 + 2], vz[q * 4 + 3]);
+                    g4[2 * (H / 4) * 128] = make_float4(vn[q * 4], vn[q * 4 + 1], vn[q * 4 + 2], vn[q * 4 + 3]);
+                    g4[3 * (H / 4) * 128] = make_float4(vh[q * 4], vh[q * 4 + 1], vh[q * 4 + 2], vh[q * 4 + 3]);
+                }
+            } else if (want_g) {
 #pragma unroll
                 for (int q = 0; q < HC / 4; q++) {
                     *reinterpret_cast<float4*>(grow + j0 + q * 4) = make_float4(vr[q * 4], vr[q * 4 + 1], vr[q * 4 + 2], vr[q * 4 + 3]);
@@ -305,12 +338,16 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                 const uint32_t off = (uint32_t)row * 16 + (uint32_t)(j0 / 4 + q) * TC_A_LBO;
                 *reinterpret_cast<float4*>(Hs_hi + off) = hi;
                 *reinterpret_cast<float4*>(Hs_lo + off) = lo;
-                if (want_o) *reinterpret_cast<float4*>(orow + j0 + q * 4) = valid ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (want_o) {
+                    const int oc = TILED ? (((j0 >> 2) + q) ^ ox) : ((j0 >> 2) + q);
+                    *reinterpret_cast<float4*>(orow + oc * 4) = valid ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar_h);
             if (want_g || want_o) mbar_arrive(bar_sfull);
+            if (warp == 4 && lane == 0) GTC_STAMP(1, step, 0);
         }
         if (a.Hn && s < a.S) {
 #pragma unroll
@@ -346,8 +383,10 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
             issue_x(0);
             for (int step = 0; step < T; step++) {
                 const int buf = step & 1;
+                if (lane == 0) GTC_STAMP(2, step, 0);
                 mbar_wait(bar_h, (uint32_t)(step & 1));            // h_{step-1} published (phase step)
                 tc_fence_after();
+                if (lane == 0) GTC_STAMP(2, step, 1);
                 const uint32_t acc = tmem + (uint32_t)(buf * 4 * H);
                 if (elect_one_sync()) {
 #pragma unroll
@@ -368,11 +407,34 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
                     umma_commit(bar_acc + 8u * buf);
                 }
                 __syncwarp();
+                if (lane == 0) GTC_STAMP(2, step, 2);
                 if (step + 1 < T) issue_x(step + 1);
+                if (lane == 0) GTC_STAMP(2, step, 3);
             }
         }
     }
-    {
+    if (TILED) {
+        // ===================== drain (one thread): the staged gate block and output tile leave through the copy engine =====================
+        if (tid == GTC_STORE_WARP * 32 && (want_g || want_o)) {
+            for (int step = 0; step < T; step++) {
+                const int t = dir ? (T - 1 - step) : step;
+                GTC_STAMP(3, step, 0);
+                mbar_wait(bar_sfull, (uint32_t)(step & 1));        // the gate threads fenced their writes for the async proxy
+                GTC_STAMP(3, step, 1);
+                if (want_g)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(a.Gt[dir] + ((size_t)blockIdx.x * T + t) * H * 512), "r"(smem_u32(Gs)), "r"((uint32_t)(128 * 4 * H * 4)) : "memory");
+                if (want_o)
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(&hmap), "r"(smem_u32(Os)), "r"(dir * H), "r"(t), "r"(s0) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the staging tiles have been read
+                mbar_arrive(bar_sfree);
+                GTC_STAMP(3, step, 2);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");               // writes complete before the CTA exits
+        }
+    } else {
         const int swi = warp >= GTC_STORE_WARP ? warp - GTC_STORE_WARP : ((H == 16 && warp >= 4 + NGATE && warp < GTC_MMA_WARP) ? GTC_NSTORE + warp - (4 + NGATE) : -1);
         if (swi >= 0 && (want_g || want_o))
             for (int step = 0; step < T; step++) store_step(step, swi);
@@ -382,14 +444,14 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const GruTcArgs
     if (warp == 0) tmem_dealloc(tmem, geo.tmem_cols);
 }
 
-static bool gru_tc_geom(int H, int I, GruTcGeom& g, size_t& smem);
+static bool gru_tc_geom(int H, int I, GruTcGeom& g, size_t& smem, bool tiled = false);
 static bool gru_tc_eligible(int S, int H, int I) {
     (void)S;   // independent of the batch size: chunked and unchunked batches must take the same arithmetic path
     GruTcGeom g; size_t smem;
     return tc_enabled() && (H == 16 || H == 32) && (I % 8 == 0) && I >= 8 && I <= 64 && gru_tc_geom(H, I, g, smem);
 }
 
-static bool gru_tc_geom(int H, int I, GruTcGeom& g, size_t& smem) {
+static bool gru_tc_geom(int H, int I, GruTcGeom& g, size_t& smem, bool tiled) {
     g.wih_lbo = 3 * H * 16 + 16;
     g.whh_lbo = 3 * H * 16 + 16;
     g.wih_bytes = (uint32_t)(I / 4) * g.wih_lbo;
@@ -397,49 +459,58 @@ static bool gru_tc_geom(int H, int I, GruTcGeom& g, size_t& smem) {
     g.x_bytes = (uint32_t)(I / 4) * TC_A_LBO;
     g.h_bytes = (uint32_t)(H / 4) * TC_A_LBO;
     g.tmem_cols = tmem_cols_for(8 * H);
-    g.gs = 4 * H * 4 + 16;          // padded row strides: conflict-free 16-byte stores, 16-byte aligned bulk-copy sources
-    g.os = H * 4 + 16;
+    g.gs = 4 * H * 4 + (tiled ? 0 : 16);     // row-major staging: padded row strides (conflict-free 16-byte stores); tiled: dense
+    g.os = H * 4 + (tiled ? 0 : 16);
     for (g.xst = 2; g.xst >= 1; g.xst--) {
         smem = 2 * (size_t)g.wih_bytes + 2 * (size_t)g.whh_bytes + 2 * (size_t)g.h_bytes + 2 * (size_t)g.xst * g.x_bytes +
-               128 * (size_t)(g.gs + g.os) + 10 * 8 + 16 + (size_t)4 * H * 4 + 128 * 4 + 128;
+               128 * (size_t)(g.gs + g.os) + 10 * 8 + 16 + (size_t)4 * H * 4 + 128 * 4 + 128 + (tiled ? 1024 : 0);
         if (smem <= 227 * 1024) return true;
     }
     return false;
 }
 
 template <int H, int KQM, bool TILED>
-static int gru_tc_launch_tt(const GruTcArgs& a, const GruTcGeom& geo, size_t smem, cudaStream_t st) {
+static int gru_tc_launch_tt(const CUtensorMap& hmap, const GruTcArgs& a, const GruTcGeom& geo, size_t smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         DOF_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<H, KQM, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     dim3 grid(cdiv(a.S, 128), 2);
-    gru_fwd_tc_kernel<H, KQM, TILED><<<grid, GTC_THREADS, smem, st>>>(a, geo);
+    gru_fwd_tc_kernel<H, KQM, TILED><<<grid, GTC_THREADS, smem, st>>>(hmap, a, geo);
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
 template <int H, int KQM>
-static int gru_tc_launch_t(const GruTcArgs& a, const GruTcGeom& geo, size_t smem, cudaStream_t st) {
-    return a.gt_tiled ? gru_tc_launch_tt<H, KQM, true>(a, geo, smem, st) : gru_tc_launch_tt<H, KQM, false>(a, geo, smem, st);
+static int gru_tc_launch_t(const CUtensorMap& hmap, const GruTcArgs& a, const GruTcGeom& geo, size_t smem, cudaStream_t st) {
+    return a.gt_tiled ? gru_tc_launch_tt<H, KQM, true>(hmap, a, geo, smem, st) : gru_tc_launch_tt<H, KQM, false>(hmap, a, geo, smem, st);
 }
 
 // one bidirectional GRU layer, both directions (blockIdx.y)
 static int launch_gru_fwd_tc(const GruTcArgs& a, cudaStream_t st) {
     GruTcGeom geo;
     size_t smem = 0;
-    if (!gru_tc_geom(a.H, a.I, geo, smem)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "fused GRU tile does not fit (H=%d I=%d)", a.H, a.I);
+    if (!gru_tc_geom(a.H, a.I, geo, smem, a.gt_tiled != 0)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "fused GRU tile does not fit (H=%d I=%d)", a.H, a.I);
+    CUtensorMap hmap;
+    memset(&hmap, 0, sizeof(hmap));
+    if (a.gt_tiled) {
+        if (!a.Gt[0] || !a.Gt[1] || !aligned16(a.Gt[0]) || !aligned16(a.Gt[1])) DOF_FAIL(DOF_ERR_ARG, "tiled gates need both 16-byte aligned gate buffers");
+        if (a.Hout) {
+            if (!aligned16(a.Hout)) DOF_FAIL(DOF_ERR_ARG, "fused GRU output must be 16-byte aligned");
+            DOF_TRY(tmap_seq3d(a.Hout, a.S, a.T, a.H, 128, &hmap));
+        }
+    }
     if ((a.x_ss & 3) || (a.x_st & 3) || !aligned16(a.X)) DOF_FAIL(DOF_ERR_ARG, "fused GRU input must be 16-byte aligned");
     const double rows = (double)a.S * a.T * 2;
     ProfScope ps(a.H == 32 ? "gru_fwd_tc_h32" : "gru_fwd_tc_h16", st, rows * 2.0 * 3 * a.H * (a.I + a.H),
                  (double)a.S * a.T * 4.0 * a.I + rows * 4.0 * a.H * ((a.Hout ? 1 : 0) + (a.Gt[0] ? 4 : 0)));
     const int KQ = a.I / 4;
     if (a.H == 32) {
-        if (KQ <= 4) return gru_tc_launch_t<32, 4>(a, geo, smem, st);
-        if (KQ <= 8) return gru_tc_launch_t<32, 8>(a, geo, smem, st);
-        return gru_tc_launch_t<32, 16>(a, geo, smem, st);
+        if (KQ <= 4) return gru_tc_launch_t<32, 4>(hmap, a, geo, smem, st);
+        if (KQ <= 8) return gru_tc_launch_t<32, 8>(hmap, a, geo, smem, st);
+        return gru_tc_launch_t<32, 16>(hmap, a, geo, smem, st);
     }
-    if (KQ <= 4) return gru_tc_launch_t<16, 4>(a, geo, smem, st);
-    if (KQ <= 8) return gru_tc_launch_t<16, 8>(a, geo, smem, st);
-    return gru_tc_launch_t<16, 16>(a, geo, smem, st);
+    if (KQ <= 4) return gru_tc_launch_t<16, 4>(hmap, a, geo, smem, st);
+    if (KQ <= 8) return gru_tc_launch_t<16, 8>(hmap, a, geo, smem, st);
+    return gru_tc_launch_t<16, 16>(hmap, a, geo, smem, st);
 }

@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda.h>
 #include "tc_gemm.cuh"
+#include "tmap.cuh"
 
 #define GW_BM 32                    // rows (MMA K) per stage
 #define GW_BLK (GW_BM * 128)        // bytes of one [GW_BM rows][32 columns] block
@@ -232,24 +233,6 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gru_wgrad_tc_kernel(const __gri
 // ---------------------------------------------------------------------------
 // host side: tensor maps (cached per buffer), eligibility, launch
 // ---------------------------------------------------------------------------
-typedef CUresult (*dof_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static dof_tmap_encode_fn tmap_encoder() {
-    static dof_tmap_encode_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<dof_tmap_encode_fn>(p);
-        cudaGetLastError();
-    }
-    return fn;
-}
-
 struct TmapKey { const void* base; int rows, cols, ld; };
 struct TmapEntry { TmapKey k; CUtensorMap m; };
 static std::vector<TmapEntry> g_tmaps;

@@ -26,7 +26,9 @@ gt = [torch.empty(S_, T, 4 * H, device=dev) for _ in range(2)]
 hn = torch.empty(S_, 2 * H, device=dev)
 P = lambda t: C.c_void_p(t.data_ptr())
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+dbg = torch.zeros(8 * T * 4, dtype=torch.int64, device=dev)
 for it in range(3):
+    L.dof_test_gru_bwdw_timeline(P(dbg) if it == 2 else None)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -36,3 +38,13 @@ for it in range(3):
     torch.cuda.synchronize()
     assert rc == 0, L.dof_last_error()
     print("fused gru layer H=%d I=%d S=%d mode=%s tiled=%d: %.3f ms" % (H, I, S_, MODE, TILED, e0.elapsed_time(e1)))
+L.dof_test_gru_bwdw_timeline(None)
+d = dbg.view(8, T, 4).cpu()
+t0 = int(d[0, 0, 0])
+names = ["gate w4 : loop top | acc ready | math done | staging free", "gate w4 : published h + staged rows", "MMA     : loop top | h ready | h-part issued | x-part of next step issued",
+         "store w13: loop top | rows staged | drained", "prod w0 : loop top | x staged | helped draining"]
+for r, nm in enumerate(names):
+    print(nm)
+    for s in (0, 1, 2, 10, 11, 24):
+        print("   step %2d:" % s, " ".join("%7d" % (int(v) - t0) if int(v) else "      -" for v in d[r, s]))
+print("cycles per step (gate w4, loop top to loop top), steps 2..24: %.0f" % ((int(d[0, 24, 0]) - int(d[0, 2, 0])) / 22))
