@@ -69,7 +69,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t saddr, const float4 v) {
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(bw_raw) + 1023) & ~(uintptr_t)1023);
     const int dir = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int I = a.I, T = a.T, KQ = I >> 2;
+    const bool oxh = ((I + H) & 31) == 16;                           // a constant-one column fits into the XH tile (see below)
     unsigned char* DG_hi = sm;                                        // [NBP blocks][R rows][128 B]
     unsigned char* DG_lo = DG_hi + geo.dg_bytes;
     unsigned char* XH_hi = DG_lo + geo.dg_bytes;                      // columns [0, I) x_t | [I, I+H) h_prev
@@ -151,6 +152,15 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
             *reinterpret_cast<float*>(Wih_hi + off) = hi;
             *reinterpret_cast<float*>(Wih_lo + off) = lo;
         }
+        if (oxh) {
+            // columns [I+H, I+H+16) of every XH row: 1, 0, 0, ... (hi plane), zeros (lo plane); written once, nobody else touches them
+            for (int i = tid; i < R * 4; i += GBW_THREADS) {
+                const int r = i >> 2, q = i & 3;
+                const uint32_t off = sw32_unit<R>(r, (I + H + 4 * q) & ~7) + (uint32_t)(q & 1) * 16;
+                *reinterpret_cast<float4*>(XH_hi + off) = make_float4(q == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(XH_lo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         for (int i = tid; i < 128; i += GBW_THREADS) {
             ones[i] = 1.0f;
             lens_s[i] = (i < R && s0 + i < a.S) ? (a.len ? __ldg(a.len + s0 + i) : T) : -1;
@@ -178,7 +188,10 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
     // tcgen05.mma accumulate, a bias that grows with the number of accumulates (T * R/8 * 3 = 1050 at T = 25: 2e-5
     // relative, measured), so the hi.hi products alternate between two accumulators by step parity and the small lo
     // terms go to a third: 175 accumulates each on the large terms; the epilogue adds the three in fp32 registers.
-    const uint32_t NW = (uint32_t)(I + H);
+    // When the XH tile has 16 spare columns in its last 32-column block (I + H = 16 mod 32: every H = 16 shape but I = 16) a
+    // constant-one column rides along as column I + H of the B operand and the bias gradients come out of the same MMAs
+    // (N = I + H + 16); otherwise two extra MMAs per K step multiply dG with a separate all-ones tile.
+    const uint32_t NW = (uint32_t)(I + H) + (oxh ? 16u : 0u);
     const uint32_t acc_dh = tmem, acc_dx = tmem + H, acc_w = tmem + H + I, acc_wlo = acc_w + 2 * NW, acc_b = acc_w + 3 * NW, acc_blo = acc_b + 32;
 
     if (warp >= 4 && warp < GBW_MMA_A) {
@@ -234,6 +247,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
                 hp4[q] = (t < len && tp >= 0 && tp < len) ? lds128(st_hp + off) : make_float4(0.f, 0.f, 0.f, 0.f);
                 do4[q] = (t < len && a.dOut) ? lds128(st_do + off) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            fence_async_smem();          // generic-proxy reads above vs. the TMA (async proxy) that refills the tiles right after this arrive
             mbar_arrive(bar_stfree);
         };
         // DRAM -> L2 two steps ahead (no registers held): one SM can only keep ~30 KB of loads in flight, so a step's 100 KB
@@ -337,6 +351,14 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
             const uint32_t whh_hi = smem_u32(Whh_hi), whh_lo = smem_u32(Whh_lo), wih_hi = smem_u32(Wih_hi), wih_lo = smem_u32(Wih_lo);
             for (int step = 0; step < T; step++) {
                 if (lane == 0) GBW_STAMP(2, step, 0);
+                // TMA of the NEXT step's h_prev / dOut tiles as soon as the gate threads have copied this step's (they do that at
+                // the top of their step, long before a_full): this warp is idle until a_full anyway, and the tiles get a whole
+                // step of lead (issued from a loader warp they arrived when they were needed: 4 - 7 k cycles exposed per step)
+                if (step + 1 < T) {
+                    mbar_wait(bar_stfree, (uint32_t)(step & 1));
+                    if (elect_one_sync()) issue_stage(step + 1);
+                    __syncwarp();
+                }
                 mbar_wait(bar_afull, (uint32_t)(step & 1));
                 tc_fence_after();
                 if (lane == 0) GBW_STAMP(2, step, 1);
@@ -378,7 +400,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GbwRegs<H>::OTHER));
         {
             // ===================== MMA issuer B: weight / bias gradients, accumulated over all T steps =====================
-            const uint32_t id_w = umma_idesc_tf32(I + H, 1, 1), id_b = umma_idesc_tf32(16, 1, 0);
+            const uint32_t id_w = umma_idesc_tf32((int)NW, 1, 1), id_b = umma_idesc_tf32(16, 1, 0);
             const uint32_t a_hi = smem_u32(DG_hi), a_lo = smem_u32(DG_lo), x_hi = smem_u32(XH_hi), x_lo = smem_u32(XH_lo);
             const uint64_t d1 = umma_desc(smem_u32(ones), 256, 128);
             for (int step = 0; step < T; step++) {
@@ -397,8 +419,10 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
                         umma_tf32(acc_w + par * NW, dah, dbh, id_w, firstp);
                         umma_tf32(acc_wlo, dal, dbh, id_w, first);
                         umma_tf32(acc_wlo, dah, dbl, id_w, 1u);
-                        umma_tf32(acc_b + par * 16, dah, d1, id_b, firstp);
-                        umma_tf32(acc_blo, dal, d1, id_b, first);
+                        if (!oxh) {
+                            umma_tf32(acc_b + par * 16, dah, d1, id_b, firstp);
+                            umma_tf32(acc_blo, dal, d1, id_b, first);
+                        }
                     }
                     umma_commit(bar_w);
                 }
@@ -460,10 +484,6 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
             if (H == 32 && step + 2 < T) prefetch_x(step + 2);
             if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 0);
             if (step + 1 < T) load_x(step + 1);
-            if (tid == 14 * 32 && step + 1 < T) {
-                mbar_wait(bar_stfree, (uint32_t)(step & 1));
-                issue_stage(step + 1);
-            }
             if (step + 1 < T) {
                 mbar_wait(bar_w, (uint32_t)(step & 1));                      // the weight-gradient MMAs of this step read XH
                 if (lrole >= 0 && lane == 0) GBW_STAMP(lrole, step, 1);
@@ -512,7 +532,7 @@ __global__ void __launch_bounds__(GBW_THREADS, 1) gru_bwdw_tc_kernel(const __gri
             const bool vih = ((reinterpret_cast<uintptr_t>(a.dWih[dir]) & 15) == 0), vhh = ((reinterpret_cast<uintptr_t>(a.dWhh[dir]) & 15) == 0);
             for (int c0 = 0; c0 < I + H + 8; c0 += 8) {
                 float v[8], v1[8];
-                const bool bias = c0 >= I + H;
+                const bool bias = !oxh && c0 >= I + H;
                 tmem_ld8((bias ? acc_blo : acc_wlo + (uint32_t)c0) + trow, v);
                 tmem_ld8((bias ? acc_b : acc_w + (uint32_t)c0) + trow, v1);
 #pragma unroll
@@ -568,7 +588,7 @@ static bool gru_bwdw_geom(int H, int I, GruBwdwGeom& g, size_t& smem) {
     g.dg_bytes = (uint32_t)(4 * H / 32) * R * 128;
     g.xh_bytes = (uint32_t)((I + H + 31) / 32) * R * 128;
     g.st_bytes = (uint32_t)R * H * 4;
-    g.tmem_cols = tmem_cols_for(H + I + 3 * (I + H) + 48);
+    g.tmem_cols = tmem_cols_for(H + I + 3 * (I + H + 16) + 48);
     smem = 1024 + 2 * (size_t)g.dg_bytes + 2 * (size_t)g.xh_bytes + 2 * (size_t)g.st_bytes + 2 * (size_t)g.whh_bytes + 2 * (size_t)g.wih_bytes + 512 + 6 * 8 + 16 + 128 * 4 + 64;
     return smem <= 227 * 1024;
 }
