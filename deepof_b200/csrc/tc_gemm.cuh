@@ -365,7 +365,7 @@ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0;
 
 #define TC_SMEM_MAX (200 * 1024)
 
-static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem, int nkb = 1) {
+static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem, int nkb = 1, int max_stages = 2) {
     geo.KP = round_up(K, 8);
     geo.NP = round_up(N, 16);
     if (2 * geo.NP > 512) return false;
@@ -373,7 +373,7 @@ static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem, int nkb = 
     geo.w_lbo = geo.NP * 16 + 16;
     geo.a_bytes = (uint32_t)(geo.KP / 4) * TC_A_LBO;
     geo.w_bytes = (uint32_t)(geo.KP / 4) * geo.w_lbo;
-    for (int S = 2; S >= 1; S--) {
+    for (int S = max_stages; S >= 1; S--) {
         smem = (size_t)nkb * 2 * geo.w_bytes + (size_t)S * 2 * geo.a_bytes + (2 * S + 4) * 8 + 16 + (size_t)geo.NP * 4 +
                4 * 32 * 36 * 4 + 128;
         if (smem <= TC_SMEM_MAX) { geo.stages = S; return true; }
@@ -430,10 +430,21 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     const int nkb = nmat * ksp;
     if (!tc_rows_geom(gs[0].N, gs[0].K / ksp, geo, smem, nkb)) DOF_FAIL(DOF_ERR_UNSUPPORTED, "TC GEMM tile does not fit");
     const int KQ = geo.KP / 4;
+    // 8 < K/4 <= 16 (the transformer's K = 40 projections): two register sets of 16 float4 per producer thread cap the CTA at one
+    // per SM.  One stage + one register set fits TWO CTAs per SM (all roles doubled), which hides the producers' load -> split
+    // -> store latency better than the deeper pipeline of a single CTA (DOF_ROWS_OCC2=0 restores the old choice for A/B runs).
+    static const bool occ2_on = !(getenv("DOF_ROWS_OCC2") && getenv("DOF_ROWS_OCC2")[0] == '0');
+    bool occ2 = false;
+    if (occ2_on && KQ > 8 && KQ <= 16) {
+        TcRowsGeom g1; size_t sm1 = 0;
+        if (tc_rows_geom(gs[0].N, gs[0].K / ksp, g1, sm1, nkb, 1) && 2 * (sm1 + 1024) <= 228 * 1024 && 2 * g1.tmem_cols <= 512) {
+            geo = g1; smem = sm1; occ2 = true;
+        }
+    }
     int occ = (int)((228 * 1024) / (smem + 1024));
     int by_tmem = 512 / geo.tmem_cols;
     if (occ > by_tmem) occ = by_tmem;
-    int by_regs = KQ <= 8 ? 2 : 1;                     // register budget of the 288-thread CTA
+    int by_regs = (KQ <= 8 || occ2) ? 2 : 1;           // register budget of the 288-thread CTA
     if (occ > by_regs) occ = by_regs;
     if (occ < 1) occ = 1;
     int ntiles = cdiv(M, 128);
@@ -448,6 +459,7 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     ProfScope ps("gemm_rows_tc", st, fl, by);
     dim3 grid(ctas, 1, nbatch);
     if (KQ <= 8) return launch_rows_tc_t<8, 2>(gb, geo, smem, grid, st);
+    if (KQ <= 16 && occ2) return launch_rows_tc_t<16, 1>(gb, geo, smem, grid, st);
     if (KQ <= 16) return launch_rows_tc_t<16, 2>(gb, geo, smem, grid, st);
     return launch_rows_tc_t<32, 1>(gb, geo, smem, grid, st);
 }

@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-( echo "compute-sanitizer --tool memcheck python -m pytest tests/test_ops_gpu.py tests/test_multigpu_gpu.py -x -q -k 'gru or gemm'   (B200, round 2, r6d: after gru_bwdw_tc, the TMA drains of gru_fwd_tc, the elect.sync MMA issue and peer.cuh)"; timeout 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_ops_gpu.py -x -q --no-header -p no:cacheprovider -k 'gru or gemm' 2>&1 | tail -6 ) > gpurun_out/r6d_sanitizer_memcheck.txt 2>&1
-( echo "compute-sanitizer --tool racecheck python -m pytest tests/test_ops_gpu.py -x -q -k 'gru'   (B200, round 2, r6d: gru_fwd_tc, gru_bwdw_tc, gru_bwd_tc, gru_wgrad_tc; racecheck tracks generic-proxy shared-memory accesses and barriers, not the async proxy)"; timeout 1500 compute-sanitizer --tool racecheck python -m pytest tests/test_ops_gpu.py -x -q --no-header -p no:cacheprovider -k 'gru' 2>&1 | tail -6 ) > gpurun_out/r6d_sanitizer_racecheck.txt 2>&1
-cat gpurun_out/r6d_sanitizer_memcheck.txt gpurun_out/r6d_sanitizer_racecheck.txt
+timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_tfm_train_gpu.py -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -2
+for occ in 0 1; do for wl in cfg3 cfg5; do
+DOF_ROWS_OCC2=$occ timeout 600 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline --no-secondary | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('occ2=$occ $wl', round(d['value']), round(d['ms_per_step'],2), {k: round(v['ms_per_step'],2) for k,v in sorted(d['kernels'].items(), key=lambda kv:-kv[1]['ms_per_step'])[:5]})"
+done; done
