@@ -1,7 +1,13 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_tfm_train_gpu.py -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -2
-for occ in 0 1; do for wl in cfg3 cfg5; do
-DOF_ROWS_OCC2=$occ timeout 600 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline --no-secondary | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('occ2=$occ $wl', round(d['value']), round(d['ms_per_step'],2), {k: round(v['ms_per_step'],2) for k,v in sorted(d['kernels'].items(), key=lambda kv:-kv[1]['ms_per_step'])[:5]})"
-done; done
+nvidia-smi -L | wc -l
+for n in 8 4; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2955$n bench.py --gpus $n --steps 20 --warmup 5 --no-secondary > gpurun_out/r6f_bench_n$n.json 2> gpurun_out/r6f_bench_n$n.err
+python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/r6f_bench_n$n.json").read().strip().splitlines()[-1])
+    print("N=$n value", round(d["value"]), "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), d.get("allreduce", {}).get("kind"))
+except Exception as e:
+    print("N=$n parse failed", e); print(open("gpurun_out/r6f_bench_n$n.err").read()[-2500:])
+PY
+done
