@@ -85,6 +85,7 @@ _lib = None
 _P = C.c_void_p
 _SIGS = {
     "dof_abi_version": (C.c_int, []),
+    "dof_source_hash": (C.c_char_p, []),
     "dof_last_error": (C.c_char_p, []),
     "dof_state_numel": (C.c_int64, [C.POINTER(DofConfig)]),
     "dof_state_num_entries": (C.c_int, [C.POINTER(DofConfig)]),

@@ -552,6 +552,13 @@ static void build_gidx(int T, int G, int F, std::vector<int>& out) {
 extern "C" {
 
 int dof_abi_version(void) { return DOF_ABI_VERSION; }
+#ifndef DOF_SOURCE_HASH
+#define DOF_SOURCE_HASH "unknown"
+#endif
+// sha256 (first 16 hex digits) of csrc/* and include/deepof_b200.h at build time: __graft_entry__.build() rebuilds when the
+// sources on disk hash differently, so a prebuilt library can never silently disagree with the tree it ships in
+static const char g_source_hash[] = "DOF_SOURCE_HASH=" DOF_SOURCE_HASH;      // the marker lets build() read it without dlopen
+const char* dof_source_hash(void) { return g_source_hash + 16; }
 const char* dof_last_error(void) { return g_dof_err; }
 
 int64_t dof_state_numel(const dof_config* cfg) {

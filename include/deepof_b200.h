@@ -115,6 +115,8 @@ typedef struct {
 typedef struct dof_handle dof_handle;
 
 int dof_abi_version(void);
+/* first 16 hex digits of the sha256 over csrc/ and this header the library was built from (build provenance) */
+const char* dof_source_hash(void);
 const char* dof_last_error(void);
 
 /* ---- flat state buffer ----------------------------------------------------------------
