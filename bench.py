@@ -54,6 +54,10 @@ WORKLOADS = {
                  name="cfg5: VaDE transformer encoder / causal transformer decoder, synthetic windows (25x14x3 + 25x14x1), latent=64, "
                       "16 clusters, batch 4096/GPU, main phase (MC-KL S=32), dropout on (in-kernel Philox)",
                  metric="pose-windows/sec trained (VaDE transformer, win=25x28)"),
+    "tcn": dict(CFG, kind="vade", encoder="TCN", flops=279.4e6,
+                name="tcn: VaDE TCN encoder / TCN decoder (cfg2 geometry with encoder_type=TCN), 1M synthetic windows (25x14x3 + 25x14x1), "
+                     "latent=16, 8 clusters, batch 4096/GPU, main phase (MC-KL S=32)",
+                metric="pose-windows/sec trained (VaDE TCN, win=25x28)"),
     "cfg4": dict(T=50, N=22, E=26, F=3, Fe=1, D=16, K=1, batch=4096, pool_windows=1 << 19, kind="contrastive", flops=290.4e6,
                  name="cfg4: contrastive NT-Xent (nce, cosine, tau=0.1), recurrent encoder, 2 animals x 11 body parts (N=22, E=26), "
                       "win=50 (encoder sees 25), latent=16, batch 4096/GPU, reference-default augmentations",
@@ -241,7 +245,12 @@ def cpu_reference_arm(steps, warmup, batch=256, workload="cfg2"):
     for i in range(warmup + steps):
         s = (i % 4) * batch
         t0 = time.perf_counter()
-        if enc == "transformer":
+        if enc == "TCN":
+            from oracle import tcn_oracle as TCO
+            eps, mc = torch.randn(batch, c["D"], generator=gen), torch.randn(32, batch, c["D"], generator=gen)
+            logs, grads, _ = TCO.vade_train_step(x[s:s + batch], a[s:s + batch], p, graph, cfg, eps, mc_eps=mc)
+            O.adam_step(p, grads, state, 5e-4, 2e-4)
+        elif enc == "transformer":
             mk = tfm_masks()                       # the reference draws its dropout masks inside the step as well
             if kind == "vade":
                 eps, mc = torch.randn(batch, c["D"], generator=gen), torch.randn(32, batch, c["D"], generator=gen)
@@ -467,7 +476,7 @@ def main():
     # short runs of the other BASELINE configs (same contract, fewer steps): driver-visible, not the headline
     secondary = []
     if not args.no_secondary and args.workload == "cfg2":
-        for wl in ("cfg3", "cfg4", "cfg5", "vqvae"):
+        for wl in ("cfg3", "cfg4", "cfg5", "vqvae", "tcn"):
             c2 = dict(WORKLOADS[wl])
             try:
                 r2 = run_workload(c2, min(args.steps, 5), 3, world, rank, local, dev, sample_clocks=False)

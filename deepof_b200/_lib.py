@@ -21,8 +21,8 @@ class DofConfig(C.Structure):
 
 
 MODEL_VADE, MODEL_VQVAE, MODEL_CONTRASTIVE = 0, 1, 2
-ENCODER_RECURRENT, ENCODER_TRANSFORMER = 0, 1
-ENCODER_KINDS = {"recurrent": ENCODER_RECURRENT, "transformer": ENCODER_TRANSFORMER}
+ENCODER_RECURRENT, ENCODER_TRANSFORMER, ENCODER_TCN = 0, 1, 2
+ENCODER_KINDS = {"recurrent": ENCODER_RECURRENT, "transformer": ENCODER_TRANSFORMER, "TCN": ENCODER_TCN}
 ABI_VERSION = 3
 
 

@@ -1,7 +1,7 @@
 """Reference-facing entry points of the B200 path: the step functions, the epoch loop, ``train_deepof_model`` and the
 checkpoint bundle, with the names, argument meaning and return shapes of ``deepof/clustering/training.py`` and
 ``model_utils_new.py``, for the configurations this library implements
-(``encoder_type="recurrent" | "transformer"``, GNN path).
+(``encoder_type="recurrent" | "transformer" | "TCN"``, GNN path).
 
 * ``step_vade / step_vqvae_distill / step_contrastive_distill(model, (x, a, idx), ctx) -> StepResult(loss, logs)``
   (reference ``training.py:231-309, 312-389, 482-589``).  The CUDA library fuses forward, loss and backward, so the
@@ -444,8 +444,8 @@ def build_model(rebuild_spec: Dict[str, Any], max_batch: int = 4096, training: b
     """Model object from a reference ``rebuild_spec`` (``model_utils_new.py:367-417``)."""
     name = str(rebuild_spec["model_name"]).lower()
     etype = rebuild_spec.get("encoder_type", "recurrent")
-    if etype not in ("recurrent", "transformer") or not rebuild_spec.get("use_gnn", True):
-        raise NotImplementedError("deepof_b200 implements encoder_type='recurrent' and 'transformer', use_gnn=True")
+    if etype not in ("recurrent", "transformer", "TCN") or not rebuild_spec.get("use_gnn", True):
+        raise NotImplementedError("deepof_b200 implements encoder_type='recurrent', 'transformer' and 'TCN', use_gnn=True")
     xs, as_ = tuple(rebuild_spec["x_shape"]), tuple(rebuild_spec["a_shape"])
     adj, D, K = np.asarray(rebuild_spec["adjacency_matrix"]), int(rebuild_spec["latent_dim"]), int(rebuild_spec.get("n_components", 1))
     kw = dict(max_batch=max_batch, training=training, device=device, encoder_type=etype)
@@ -582,9 +582,9 @@ def train_deepof_model(preprocessed_object=None, adjacency_matrix=None, meta_inf
         model, log_summary = load_model_from_ckpt(pretrained, max_batch=int(batch_size or 4096))
         return model, None, None, log_summary
     name = str(model_name).lower()
-    encoder_type = str(encoder_type or "recurrent").lower()
-    if encoder_type not in ("recurrent", "transformer"):
-        raise NotImplementedError(f"encoder_type={encoder_type!r}: deepof_b200 implements 'recurrent' and 'transformer' (TCN is not built)")
+    encoder_type = {"recurrent": "recurrent", "transformer": "transformer", "tcn": "TCN"}.get(str(encoder_type or "recurrent").lower())
+    if encoder_type is None:
+        raise NotImplementedError('invalid encoder type, try "recurrent", "TCN" or "transformer"')         # models_new.py:1499-1502
     unsupported = {"use_amp": use_amp, "bootstrap_training": bootstrap_training, "reg_scatter_weight": reg_scatter_weight,
                    "main_clustering_loss": main_clustering_loss, "prior_loss_weight": prior_loss_weight,
                    "include_angles_view": include_angles_view}

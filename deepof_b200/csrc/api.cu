@@ -19,6 +19,7 @@
 #include "loader.cuh"
 #include "models.cuh"
 #include "tfm.cuh"
+#include "tcn.cuh"
 
 thread_local char g_dof_err[512] = {0};
 DofProf g_prof;
@@ -41,6 +42,11 @@ struct BlockP { int64_t conv; GruP g1, g2; int64_t n1w, n1b, n2w, n2b, pw, pb; }
 struct TfmLayerP { int64_t Wqkv, Wo, n1w, n1b, W1, b1, W2, b2, n2w, n2b; };
 struct TfmCoreP { int64_t We, be; TfmLayerP l[TFM_MAXL]; };
 struct TfmBnP { int64_t w, b, mean, var, tracked; };
+// TCN family: one TemporalBlockPT (two dilated causal Conv1d + BatchNorm, optional 1x1 residual projection) and one TCN1DPT
+#define TCN_MAXB 8
+#define TCN_TAPS 4
+struct TcnBlockP { int64_t c1w, c1b, c2w, c2b, dsw, dsb; TfmBnP bn1, bn2; int cin, dil, has_ds; };
+struct TcnStackP { int nb, C, cin0; TcnBlockP blk[TCN_MAXB]; };
 struct Layout {
     std::vector<Entry> e;
     int64_t total = 0;
@@ -53,6 +59,10 @@ struct Layout {
     TfmBnP bn2, bn5;
     int64_t dex_w[3], dex_b[3], dout_w, dout_b;
     TfmLayerP tdl[TFM_MAXL];
+    // TCN family (encoder == DOF_ENCODER_TCN): node / edge / decoder stacks, decoder front MLP (fc0..2 + bn0..2)
+    TcnStackP tstack[3];
+    int64_t dfc_w[3], dfc_b[3];
+    TfmBnP dbn[3];
     int64_t node_kernel, edge_kernel, node_weights, edge_weights, node_bias, edge_bias;
     int64_t final_w, final_b;
     GruP dg1, dg2;
@@ -186,8 +196,74 @@ static Layout build_layout_tfm(const dof_config& c) {
     return L;
 }
 
+static void add_bn_entries(Layout& L, const std::string& p, int group, int C, TfmBnP& bn) {
+    bn.w = add_entry(L, p + "weight", group, C); bn.b = add_entry(L, p + "bias", group, C);
+    bn.mean = add_entry(L, p + "running_mean", 0, C); bn.var = add_entry(L, p + "running_var", 0, C);
+    bn.tracked = add_entry(L, p + "num_batches_tracked", 0, -1);
+}
+
+static void add_tcn_stack(Layout& L, const std::string& p, int group, int cin0, int C, const int* dils, int nb, TcnStackP& S) {
+    S.nb = nb; S.C = C; S.cin0 = cin0;
+    int cin = cin0;
+    for (int i = 0; i < nb; i++) {
+        const std::string q = p + "blocks." + std::to_string(i) + ".";
+        TcnBlockP& B = S.blk[i];
+        B.cin = cin; B.dil = dils[i]; B.has_ds = cin != C ? 1 : 0;
+        B.c1w = add_entry(L, q + "conv1.weight", group, C, cin, TCN_TAPS); B.c1b = add_entry(L, q + "conv1.bias", group, C);
+        add_bn_entries(L, q + "bn1.", group, C, B.bn1);
+        B.c2w = add_entry(L, q + "conv2.weight", group, C, C, TCN_TAPS); B.c2b = add_entry(L, q + "conv2.bias", group, C);
+        add_bn_entries(L, q + "bn2.", group, C, B.bn2);
+        B.dsw = B.dsb = -1;
+        if (B.has_ds) { B.dsw = add_entry(L, q + "downsample.weight", group, C, cin, 1); B.dsb = add_entry(L, q + "downsample.bias", group, C); }
+        cin = C;
+    }
+}
+
+// state_dict order of the reference models built with encoder_type="TCN" (TCNEncoderPT models_new.py:574-607 after its first
+// forward, TCNDecoderPT :745-775, then the latent space / codebook)
+static Layout build_layout_tcn(const dof_config& c) {
+    Layout L;
+    const int N = c.N, E = c.E, D = c.D;
+    const int enc_d[8] = {1, 2, 4, 8, 1, 2, 4, 8}, dec_d[4] = {8, 4, 2, 1};
+    L.dk = 32;                                            // conv_filters of the encoder = CensNet input channels
+    L.lap = add_entry(L, "encoder.laplacian", 0, N, N);
+    L.elap = add_entry(L, "encoder.edge_laplacian", 0, E, E);
+    L.inc = add_entry(L, "encoder.incidence", 0, N, E);
+    add_tcn_stack(L, "encoder.node_tcn.", 1, c.F, 32, enc_d, 8, L.tstack[0]);
+    add_tcn_stack(L, "encoder.edge_tcn.", 1, c.Fe, 32, enc_d, 8, L.tstack[1]);
+    std::string g = "encoder.spatial_gnn_block.";
+    L.node_kernel = add_entry(L, g + "node_kernel", 1, L.dk, D);
+    L.edge_kernel = add_entry(L, g + "edge_kernel", 1, L.dk, D);
+    L.node_weights = add_entry(L, g + "node_weights", 1, L.dk, 1);
+    L.edge_weights = add_entry(L, g + "edge_weights", 1, L.dk, 1);
+    L.node_bias = add_entry(L, g + "node_bias", 1, D);
+    L.edge_bias = add_entry(L, g + "edge_bias", 1, D);
+    L.h_w0 = add_entry(L, "encoder.head.0.weight", 1, 2 * D, (N + E) * D);
+    L.h_b0 = add_entry(L, "encoder.head.0.bias", 1, 2 * D);
+    add_bn_entries(L, "encoder.head.2.", 1, 2 * D, L.bn2);
+    L.h_w3 = add_entry(L, "encoder.head.3.weight", 1, D, 2 * D);
+    L.h_b3 = add_entry(L, "encoder.head.3.bias", 1, D);
+    add_bn_entries(L, "encoder.head.5.", 1, D, L.bn5);
+    L.h_w6 = add_entry(L, "encoder.head.6.weight", 1, D, D);
+    L.h_b6 = add_entry(L, "encoder.head.6.bias", 1, D);
+    if (c.model == DOF_MODEL_CONTRASTIVE) return L;
+    const int fin[3] = {D, D, 2 * D}, fout[3] = {D, 2 * D, 4 * D};
+    for (int i = 0; i < 3; i++) {
+        const std::string s = std::to_string(i);
+        L.dfc_w[i] = add_entry(L, "decoder.fc" + s + ".weight", 2, fout[i], fin[i]);
+        L.dfc_b[i] = add_entry(L, "decoder.fc" + s + ".bias", 2, fout[i]);
+        add_bn_entries(L, "decoder.bn" + s + ".", 2, fout[i], L.dbn[i]);
+    }
+    add_tcn_stack(L, "decoder.tcn.", 2, 4 * D, 64, dec_d, 4, L.tstack[2]);
+    L.loc_w = add_entry(L, "decoder.prob_decoder.loc_projection.weight", 2, N * c.F, 64);
+    L.loc_b = add_entry(L, "decoder.prob_decoder.loc_projection.bias", 2, N * c.F);
+    add_latent_tail(L, c);
+    return L;
+}
+
 static Layout build_layout(const dof_config& c) {
     if (c.encoder == DOF_ENCODER_TRANSFORMER) return build_layout_tfm(c);
+    if (c.encoder == DOF_ENCODER_TCN) return build_layout_tcn(c);
     Layout L;
     const int N = c.N, E = c.E, D = c.D, di = dint(c);
     L.lap = add_entry(L, "encoder.laplacian", 0, N, N);
@@ -242,7 +318,9 @@ static int check_cfg(const dof_config* c) {
     if (c->model < DOF_MODEL_VADE || c->model > DOF_MODEL_CONTRASTIVE) DOF_FAIL(DOF_ERR_ARG, "unknown model kind %d", c->model);
     if (c->model == DOF_MODEL_VADE && c->K > LOSS_MAXK) DOF_FAIL(DOF_ERR_UNSUPPORTED, "n_components %d > %d", c->K, LOSS_MAXK);
     if (c->model == DOF_MODEL_VQVAE && (size_t)c->D * c->K * 4 > 96 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "codebook %d x %d does not fit in shared memory", c->D, c->K);
-    if (c->encoder != DOF_ENCODER_RECURRENT && c->encoder != DOF_ENCODER_TRANSFORMER) DOF_FAIL(DOF_ERR_ARG, "unknown encoder kind %d", c->encoder);
+    if (c->encoder != DOF_ENCODER_RECURRENT && c->encoder != DOF_ENCODER_TRANSFORMER && c->encoder != DOF_ENCODER_TCN)
+        DOF_FAIL(DOF_ERR_ARG, "unknown encoder kind %d", c->encoder);
+    if (c->encoder == DOF_ENCODER_TCN && c->D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 64 not supported by the TCN path", c->D);
     if (c->encoder == DOF_ENCODER_RECURRENT && c->D > 32) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 32 not supported by the GRU kernels yet", c->D);
     if (c->encoder == DOF_ENCODER_TRANSFORMER) {
         if (c->D > 64) DOF_FAIL(DOF_ERR_UNSUPPORTED, "latent_dim %d > 64 not supported by the transformer path", c->D);
@@ -295,9 +373,30 @@ struct TfmDecWS {
     float *dH, *dQKV, *dY, *dP[3], *dG[3];
 };
 
+// TCN family: activations of one TCN1DPT stack.  R = sequences * T rows; A1 / A2 are the pre-BatchNorm convolution outputs,
+// Y1 = relu(bn1(A1)), OUT the block output (input of the next block), RES the 1x1 residual projection of block 0.
+struct TcnBlockWS { float *A1, *Y1, *A2, *OUT, *RES; int st1, st2; };     // st*: offsets of the BatchNorm sums in a statistics pass
+struct TcnStackWS {
+    int S, G, Fin;                           // encoder stacks: sequences at max_batch, graph size, features
+    int* gidx;
+    long long rows;                          // rows at max_batch
+    float* X0;                               // [rows, cin0]
+    TcnBlockWS b[TCN_MAXB];
+    float *SKIP, *FIN;                       // skip sum and relu(skip sum): [S, C] (encoder, last step only) or [rows, C]
+    float *GS, *DA, *DB, *DX, *DX0;          // backward scratch
+};
+
 struct dof_handle {
     dof_config cfg;
     Layout L;
+    // TCN family
+    TcnStackWS ts[3];
+    double *tstat = nullptr, *tbstat = nullptr;   // [2 passes][tstat_stride] sums | sums of squares; backward sums
+    long long tstat_stride = 0;
+    TcnBnDesc* tdesc = nullptr; int tn_desc = 0;
+    int tcn_enc_windows = 0, tcn_dec_passes = 0, tcn_dec_windows = 0;
+    float *dgz, *drms, *dfo[3], *dzo[3], *ddz[3], *ddf[3], *ddg;   // decoder front MLP: fc outputs, BatchNorm outputs, their gradients
+    float *dbnm[3], *dbns[3], *dbnstat[3];
     // transformer family
     TfmCoreWS tc[2];
     TfmDecWS td;
@@ -352,6 +451,7 @@ static int fork_join_blocks(dof_handle* h, cudaStream_t st, F fn) {
     return r0 != DOF_OK ? r0 : r1;
 }
 
+static void plan_workspace_head(dof_handle* h, Bump& bp);
 static void plan_workspace_tfm_encoder(dof_handle* h, Bump& bp) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
@@ -386,6 +486,14 @@ static void plan_workspace_tfm_encoder(dof_handle* h, Bump& bp) {
             w.sFF = bp.get<float>(S * dff); w.dOut = bp.get<float>(S * dk);
         }
     }
+    plan_workspace_head(h, bp);
+}
+
+// encoder head shared by the transformer and the TCN encoders (RMS normalisation, Dense + BatchNorm x 2, Dense)
+static void plan_workspace_head(dof_handle* h, Bump& bp) {
+    const dof_config& c = h->cfg;
+    const int B = h->max_batch, D = c.D;
+    const bool tr = h->training != 0;
     const size_t Bz = (size_t)B, KD = (size_t)(c.N + c.E) * D;
     h->hIn = bp.get<float>(Bz * KD); h->hRms = bp.get<float>(Bz);
     h->h1r = bp.get<float>(Bz * 2 * D); h->h1 = bp.get<float>(Bz * 2 * D);
@@ -427,15 +535,86 @@ static void plan_workspace_tfm_decoder(dof_handle* h, Bump& bp) {
     }
 }
 
+// one TCN1DPT stack: eval keeps one set of block buffers (every block reuses them), training keeps all of them
+static void plan_tcn_stack(dof_handle* h, Bump& bp, int si, long long rows, long long seqs, bool last_only, bool need_dx0, int& stat_off) {
+    const TcnStackP& P = h->L.tstack[si];
+    TcnStackWS& w = h->ts[si];
+    const bool tr = h->training != 0;
+    const size_t R = (size_t)rows, C = (size_t)P.C;
+    w.rows = rows;
+    w.X0 = bp.get<float>(R * P.cin0);
+    for (int i = 0; i < P.nb; i++) {
+        TcnBlockWS& q = w.b[i];
+        if (!tr && i >= 2) { q = w.b[i & 1]; }
+        else {
+            if (!tr && i == 1) { q.A1 = w.b[0].A1; q.Y1 = w.b[0].Y1; q.A2 = w.b[0].A2; q.RES = nullptr; }
+            else {
+                q.A1 = bp.get<float>(R * C); q.Y1 = bp.get<float>(R * C); q.A2 = bp.get<float>(R * C);
+                q.RES = P.blk[i].has_ds ? bp.get<float>(R * C) : nullptr;
+            }
+            q.OUT = bp.get<float>(R * C);
+        }
+        q.st1 = stat_off; stat_off += 3 * P.C;
+        q.st2 = stat_off; stat_off += 3 * P.C;
+    }
+    const size_t SR = last_only ? (size_t)seqs : R;
+    w.SKIP = bp.get<float>(SR * C); w.FIN = bp.get<float>(SR * C);
+    w.GS = w.DA = w.DB = w.DX = w.DX0 = nullptr;
+    if (tr) {
+        w.GS = bp.get<float>(SR * C);
+        w.DA = bp.get<float>(R * C); w.DB = bp.get<float>(R * C); w.DX = bp.get<float>(R * C);
+        if (need_dx0) w.DX0 = bp.get<float>(R * P.cin0);
+    }
+}
+
+static void plan_workspace_tcn(dof_handle* h, Bump& bp) {
+    const dof_config& c = h->cfg;
+    const int B = h->max_batch, T = c.T, D = c.D;
+    const bool tr = h->training != 0;
+    int stat_off = 0;
+    for (int b = 0; b < 2; b++) {
+        TcnStackWS& w = h->ts[b];
+        w.G = b == 0 ? c.N : c.E;
+        w.Fin = b == 0 ? c.F : c.Fe;
+        w.S = B * w.G;
+        w.gidx = bp.get<int>((size_t)w.G * T * w.Fin);
+        plan_tcn_stack(h, bp, b, (long long)w.S * T, w.S, true, false, stat_off);
+    }
+    if (c.model != DOF_MODEL_CONTRASTIVE) {
+        h->ts[2].S = B; h->ts[2].G = 1; h->ts[2].Fin = 4 * D; h->ts[2].gidx = nullptr;
+        plan_tcn_stack(h, bp, 2, (long long)B * T, B, false, true, stat_off);
+        const size_t Bz = (size_t)B;
+        const int fout[3] = {D, 2 * D, 4 * D};
+        h->dgz = bp.get<float>(Bz * D); h->drms = bp.get<float>(Bz);
+        for (int i = 0; i < 3; i++) {
+            h->dfo[i] = bp.get<float>(Bz * fout[i]); h->dzo[i] = bp.get<float>(Bz * fout[i]);
+            h->dbnm[i] = bp.get<float>((size_t)fout[i]); h->dbns[i] = bp.get<float>((size_t)fout[i]);
+            h->dbnstat[i] = bp.get<float>((size_t)2 * 2 * fout[i]);
+            if (tr) { h->ddz[i] = bp.get<float>(Bz * fout[i]); h->ddf[i] = bp.get<float>(Bz * fout[i]); }
+        }
+        if (tr) h->ddg = bp.get<float>(Bz * D);
+    }
+    h->tstat_stride = stat_off;
+    h->tstat = bp.get<double>((size_t)2 * stat_off);
+    h->tbstat = bp.get<double>((size_t)stat_off);
+    int nd = 0;
+    for (int si = 0; si < 3; si++) if (si < 2 || c.model != DOF_MODEL_CONTRASTIVE) nd += 2 * h->L.tstack[si].nb;
+    h->tn_desc = nd;
+    h->tdesc = bp.get<TcnBnDesc>((size_t)nd);
+    plan_workspace_head(h, bp);
+}
+
 static void plan_workspace(dof_handle* h, Bump& bp) {
     const dof_config& c = h->cfg;
     const int B = h->max_batch, T = c.T, D = c.D, K = c.K, N = c.N, E = c.E;
     const int H1 = h->H1, H2 = h->H2, C1 = h->C1;
     const bool tr = h->training != 0;
-    const bool tfm = c.encoder == DOF_ENCODER_TRANSFORMER;
+    const bool tcn = c.encoder == DOF_ENCODER_TCN;
+    const bool tfm = c.encoder == DOF_ENCODER_TRANSFORMER || tcn;     // "not recurrent": the transformer-style head and buffers
     const int CC = tfm ? h->L.dk : 2 * D;                        // CensNet input channels
     h->group = bp.get<unsigned char>((size_t)h->L.total);
-    if (tfm) plan_workspace_tfm_encoder(h, bp);
+    if (tcn) plan_workspace_tcn(h, bp);
+    else if (tfm) plan_workspace_tfm_encoder(h, bp);
     for (int b = 0; b < 2 && !tfm; b++) {
         BlockWS& w = h->blk[b];
         w.G = b == 0 ? N : E;
@@ -492,7 +671,8 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
         h->vstats = bp.get<double>((size_t)VQ_ST_GRAM + (size_t)D * D + K);
     }
     h->lenD = bp.get<int>(Bz);
-    if (tfm) plan_workspace_tfm_decoder(h, bp);
+    if (tcn) {}
+    else if (tfm) plan_workspace_tfm_decoder(h, bp);
     else {
     for (int d = 0; d < 2; d++) h->GiD1[d] = bp.get<float>(Bz * 3 * D);
     h->HD1 = bp.get<float>(BT * 2 * D);
@@ -663,12 +843,29 @@ int dof_create(const dof_config* cfg, int device, int max_batch, int training, v
     for (const Entry& e : h->L.e)
         for (int64_t i = 0; i < e.numel; i++) grp[(size_t)(e.off + i)] = (unsigned char)e.group;
     cudaError_t ce = cudaMemcpy(h->group, grp.data(), grp.size(), cudaMemcpyHostToDevice);
-    const bool tfm = cfg->encoder == DOF_ENCODER_TRANSFORMER;
+    const bool tfm = cfg->encoder == DOF_ENCODER_TRANSFORMER, tcn = cfg->encoder == DOF_ENCODER_TCN;
     for (int b = 0; b < 2 && ce == cudaSuccess; b++) {
         std::vector<int> gi;
-        const int G = tfm ? h->tc[b].G : h->blk[b].G, Fin = tfm ? h->tc[b].Fin : h->blk[b].Fin;
+        const int G = tcn ? h->ts[b].G : tfm ? h->tc[b].G : h->blk[b].G, Fin = tcn ? h->ts[b].Fin : tfm ? h->tc[b].Fin : h->blk[b].Fin;
         build_gidx(cfg->T, G, Fin, gi);
-        ce = cudaMemcpy(tfm ? h->tc[b].gidx : h->blk[b].gidx, gi.data(), gi.size() * sizeof(int), cudaMemcpyHostToDevice);
+        ce = cudaMemcpy(tcn ? h->ts[b].gidx : tfm ? h->tc[b].gidx : h->blk[b].gidx, gi.data(), gi.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (tcn && ce == cudaSuccess) {                      // BatchNorm descriptor table of the TCN blocks (running-buffer update)
+        std::vector<TcnBnDesc> dv;
+        for (int si = 0; si < 3; si++) {
+            if (si == 2 && cfg->model == DOF_MODEL_CONTRASTIVE) break;
+            const TcnStackP& P = h->L.tstack[si];
+            for (int i = 0; i < P.nb; i++)
+                for (int k = 0; k < 2; k++) {
+                    const TfmBnP& bn = k == 0 ? P.blk[i].bn1 : P.blk[i].bn2;
+                    TcnBnDesc d;
+                    d.mean = bn.mean; d.var = bn.var; d.tracked = bn.tracked; d.C = P.C; d.decoder = si == 2 ? 1 : 0;
+                    d.stat = k == 0 ? h->ts[si].b[i].st1 : h->ts[si].b[i].st2;
+                    d.rows_per_window = (si == 0 ? cfg->N : si == 1 ? cfg->E : 1) * cfg->T;
+                    dv.push_back(d);
+                }
+        }
+        ce = cudaMemcpy(h->tdesc, dv.data(), dv.size() * sizeof(TcnBnDesc), cudaMemcpyHostToDevice);
     }
     if (tfm && ce == cudaSuccess) {
         tfm_pe_kernel<<<cdiv(cfg->T * h->L.dk, 256), 256>>>(h->pe_enc, cfg->T, h->L.dk);
@@ -906,8 +1103,23 @@ static int rec_decoder_forward(dof_handle* h, const float* state, const float* z
 static void register_debug(dof_handle* h, int B) {
     const dof_config& c = h->cfg;
     h->dbg.clear();
-    const bool tfm = c.encoder == DOF_ENCODER_TRANSFORMER;
-    if (tfm) {
+    const bool tcn = c.encoder == DOF_ENCODER_TCN;
+    const bool tfm = c.encoder == DOF_ENCODER_TRANSFORMER || tcn;
+    if (tcn) {
+        const int C = h->L.dk;
+        h->dbg["node_out"] = {h->ts[0].FIN, (int64_t)B * c.N * C};
+        h->dbg["edge_out"] = {h->ts[1].FIN, (int64_t)B * c.E * C};
+        h->dbg["node_a1"] = {h->ts[0].b[0].A1, (int64_t)B * c.N * c.T * C};
+        h->dbg["node_out0"] = {h->ts[0].b[0].OUT, (int64_t)B * c.N * c.T * C};
+        h->dbg["edge_a1"] = {h->ts[1].b[0].A1, (int64_t)B * c.E * c.T * C};
+        h->dbg["edge_a2"] = {h->ts[1].b[0].A2, (int64_t)B * c.E * c.T * C};
+        h->dbg["head_in"] = {h->hIn, (int64_t)B * (c.N + c.E) * c.D};
+        h->dbg["tcn_stat"] = {h->tstat, (int64_t)4 * h->tstat_stride};      // doubles viewed as floats
+        if (c.model != DOF_MODEL_CONTRASTIVE) {
+            h->dbg["dec_fin"] = {h->ts[2].FIN, (int64_t)B * c.T * h->L.tstack[2].C};
+            h->dbg["dec_x0"] = {h->ts[2].X0, (int64_t)B * c.T * 4 * c.D};
+        }
+    } else if (tfm) {
         const int ll = h->L.layers - 1, dk = h->L.dk;
         h->dbg["node_out"] = {h->tc[0].l[ll].Y2, (int64_t)B * c.N * dk};
         h->dbg["edge_out"] = {h->tc[1].l[ll].Y2, (int64_t)B * c.E * dk};
@@ -1186,23 +1398,29 @@ static int rec_encoder_backward(dof_handle* h, const float* state, float* grad, 
 }
 
 #include "tfm_step.cuh"
+#include "tcn_step.cuh"
 
 // ---- encoder / decoder family dispatch (dof_config.encoder) ----------------------------------------------------------
 static inline bool is_tfm(const dof_handle* h) { return h->cfg.encoder == DOF_ENCODER_TRANSFORMER; }
+static inline bool is_tcn(const dof_handle* h) { return h->cfg.encoder == DOF_ENCODER_TCN; }
 static int encoder_forward(dof_handle* h, const float* state, const float* x, const float* a, int B, bool train, cudaStream_t st) {
     if (is_tfm(h)) return tfm_encoder_forward(h, state, x, a, B, train, train ? h->next_groups : 1, st);
+    if (is_tcn(h)) return tcn_encoder_forward(h, state, x, a, B, train, train ? h->next_groups : 1, st);
     return rec_encoder_forward(h, state, x, a, B, train, st);
 }
 static int encoder_backward(dof_handle* h, const float* state, float* grad, int B, cudaStream_t st) {
     if (is_tfm(h)) return tfm_encoder_backward(h, state, grad, B, st);
+    if (is_tcn(h)) return tcn_encoder_backward(h, state, grad, B, st);
     return rec_encoder_backward(h, state, grad, B, st);
 }
 static int decoder_forward(dof_handle* h, const float* state, const float* zin, const float* x, int B, bool train, cudaStream_t st) {
     if (is_tfm(h)) return tfm_decoder_forward(h, state, zin, B, train, h->dec_pass, st);
+    if (is_tcn(h)) return tcn_decoder_forward(h, state, zin, B, train, h->dec_pass, st);
     return rec_decoder_forward(h, state, zin, x, B, train, st);
 }
 static int decoder_backward(dof_handle* h, const float* state, float* grad, const float* zin, int B, cudaStream_t st) {
     if (is_tfm(h)) return tfm_decoder_backward(h, state, grad, zin, B, h->dec_pass, st);
+    if (is_tcn(h)) return tcn_decoder_backward(h, state, grad, zin, B, h->dec_pass, st);
     return rec_decoder_backward(h, state, grad, zin, B, st);
 }
 
@@ -2002,7 +2220,8 @@ int dof_clip_adam(dof_handle* h, float* state, const float* grad, float* adam_m,
     { ProfScope ps("clip_adam", (cudaStream_t)stream, 0.0, 28.0 * a.n);
     clip_adam_kernel<<<cdiv(a.n, 256), 256, 0, (cudaStream_t)stream>>>(a); }
     DOF_LAUNCH_CHECK();
-    if (is_tfm(h) && h->bn_pending) DOF_TRY(tfm_bn_apply(h, state, (cudaStream_t)stream));
+    if (is_tcn(h) && h->bn_pending) DOF_TRY(tcn_bn_apply(h, state, (cudaStream_t)stream));
+    if ((is_tfm(h) || is_tcn(h)) && h->bn_pending) DOF_TRY(tfm_bn_apply(h, state, (cudaStream_t)stream));
     return DOF_OK;
 }
 

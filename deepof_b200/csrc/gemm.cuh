@@ -10,7 +10,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { A_PLAIN = 0, A_SPLIT = 1, A_CONV5 = 2, A_TSHIFT = 3 };
+enum { A_PLAIN = 0, A_SPLIT = 1, A_CONV5 = 2, A_TSHIFT = 3, A_TAPS = 4 };
 
 struct MatView {
     const float* p;
@@ -20,6 +20,9 @@ struct MatView {
     int T;            // A_CONV5 / A_TSHIFT: rows are (seq, t) with t = row % T
     int sgn;          // A_CONV5: col = c*5+kk reads row (seq, t + sgn*(kk-2)), channel c
     int shift;        // A_TSHIFT: reads row (seq, t + shift); zero outside [0,T)
+    // A_TAPS (dilated causal Conv1d as a GEMM, TCN family): column j*cc + c reads channel c of row
+    // (seq, t + dil*(taps-1-j)), zero outside [0,T).  dil = -dilation: the convolution; dil = +dilation: its input gradient
+    int taps, cc, dil;
 };
 
 static inline MatView mv_plain(const float* p, int ld) {
@@ -33,6 +36,9 @@ static inline MatView mv_conv5(const float* p, int ld, int T, int sgn) {
 }
 static inline MatView mv_tshift(const float* p, int ld, int T, int shift) {
     MatView v = mv_plain(p, ld); v.mode = A_TSHIFT; v.T = T; v.shift = shift; return v;
+}
+static inline MatView mv_taps(const float* p, int ld, int T, int taps, int cc, int dil) {
+    MatView v = mv_plain(p, ld); v.mode = A_TAPS; v.T = T; v.taps = taps; v.cc = cc; v.dil = dil; return v;
 }
 
 __device__ __forceinline__ float mv_load(const MatView& a, int m, int k) {
@@ -49,6 +55,13 @@ __device__ __forceinline__ float mv_load(const MatView& a, int m, int k) {
             int tt = t + a.sgn * (kk - 2);
             if (tt < 0 || tt >= a.T) return 0.f;
             return __ldg(a.p + (size_t)(m - t + tt) * a.ld + c);
+        }
+        case A_TAPS: {
+            int j = k / a.cc, c = k - j * a.cc;
+            int t = m % a.T;
+            int sh = a.dil * (a.taps - 1 - j);
+            if (t + sh < 0 || t + sh >= a.T) return 0.f;
+            return __ldg(a.p + (size_t)(m + sh) * a.ld + c);
         }
         default: {  // A_TSHIFT
             int t = m % a.T;
@@ -74,7 +87,22 @@ struct GemmArgs {
     MatView A2; const float* W2;
     int ksplit;                        // tensor-core kernel only: K of every matrix is staged in `ksplit` column
                                        // blocks (smaller smem stages -> double buffering for K > 64); 0/1 = off
+    // W is a torch Conv1d weight [C_out, wcin, wtaps] (ldw = wcin * wtaps) addressed for an A_TAPS operand:
+    //   wconv = 1 (forward):        n = c_out, k = j * wcin + c_in
+    //   wconv = 2 (input gradient): n = c_in,  k = j * C_out + c_out   (C_out = K / wtaps)
+    int wconv, wcin, wtaps;
 };
+
+__device__ __forceinline__ float gemm_w_at(const GemmArgs& g, const float* Wp, int n, int k) {
+    if (g.wconv == 0) return g.wT == 0 ? __ldg(Wp + (size_t)n * g.ldw + k) : __ldg(Wp + (size_t)k * g.ldw + n);
+    if (g.wconv == 1) {
+        const int j = k / g.wcin, ci = k - j * g.wcin;
+        return __ldg(Wp + (size_t)n * g.ldw + ci * g.wtaps + j);
+    }
+    const int co_n = g.K / g.wtaps;
+    const int j = k / co_n, co = k - j * co_n;
+    return __ldg(Wp + (size_t)co * g.ldw + n * g.wtaps + j);
+}
 struct GemmBatch { GemmArgs g[2]; };
 
 #define GEMM_BM 128
@@ -112,14 +140,14 @@ gemm_rows_kernel(const GemmBatch gb) {
             for (int i = tid; i < BN * GEMM_BK; i += NT) {
                 int k = i % GEMM_BK, n = i / GEMM_BK;
                 float v = 0.f;
-                if (n0 + n < g.N && k0 + k < g.K) v = __ldg(g.W + (size_t)(n0 + n) * g.ldw + k0 + k);
+                if (n0 + n < g.N && k0 + k < g.K) v = gemm_w_at(g, g.W, n0 + n, k0 + k);
                 Ws[k][n] = v;
             }
         } else {
             for (int i = tid; i < BN * GEMM_BK; i += NT) {
                 int n = i % BN, k = i / BN;
                 float v = 0.f;
-                if (n0 + n < g.N && k0 + k < g.K) v = __ldg(g.W + (size_t)(k0 + k) * g.ldw + n0 + n);
+                if (n0 + n < g.N && k0 + k < g.K) v = gemm_w_at(g, g.W, n0 + n, k0 + k);
                 Ws[k][n] = v;
             }
         }
@@ -219,7 +247,7 @@ struct WGradArgs {
     float* dW; int ldo; int oT;   // oT=0: dW[n*ldo+k]; oT=1: dW[k*ldo+n]
     float* db;                    // [N] or null
     int M, N, K;
-    int ks;                       // tensor-core kernel only, oT=0: column stride of the output, dW[n*ldo + k*ks] (0 = 1)
+    int ks;                       // oT=0: column stride of the output, dW[n*ldo + k*ks] (0 = 1)
 };
 #define WG_MAXBATCH 5
 struct WGradBatch { WGradArgs g[WG_MAXBATCH]; };
@@ -284,7 +312,7 @@ __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const WGradBatch wb, in
         for (int j = 0; j < 4; j++) {
             int k = k0 + tx * 4 + j;
             if (k >= g.K) continue;
-            float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + k;
+            float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + (size_t)k * (g.ks > 0 ? g.ks : 1);
             atomicAdd(o, acc[i][j]);
         }
         if (do_bias) atomicAdd(g.db + n, bsum[i]);

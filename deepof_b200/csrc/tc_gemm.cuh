@@ -112,6 +112,21 @@ __device__ __forceinline__ void split_tf32x4(const float4 v, float4& hi, float4&
     split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
     split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
 }
+// Same split with the remainder ROUNDED to nearest tf32 (add half an ulp of the 10-bit mantissa, then truncate): what is lost is
+// at most 2^-22 |v| and has no preferred sign.  The truncated remainder of split_tf32 always errs towards zero (mean 2^-22 |v| per
+// operand), which showed up as a 6e-7 relative error of K = 128 products; the general-purpose GEMM kernels use this one.
+__device__ __forceinline__ void split_tf32_rn(float v, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+#ifdef DOF_AB_OLD_SPLIT
+    lo = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
+#else
+    lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xFFFFE000u);
+#endif
+}
+__device__ __forceinline__ void split_tf32x4_rn(const float4 v, float4& hi, float4& lo) {
+    split_tf32_rn(v.x, hi.x, lo.x); split_tf32_rn(v.y, hi.y, lo.y);
+    split_tf32_rn(v.z, hi.z, lo.z); split_tf32_rn(v.w, hi.w, lo.w);
+}
 
 __host__ __device__ static inline int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -159,9 +174,9 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
             int n, k;
             if (g.wT == 0) { n = i / KP; k = i % KP; } else { k = i / NP; n = i % NP; }
             float v = 0.f;
-            if (n < g.N && k < Kb) v = g.wT == 0 ? __ldg(Wp + (size_t)n * g.ldw + k0 + k) : __ldg(Wp + (size_t)(k0 + k) * g.ldw + n);
+            if (n < g.N && k < Kb) v = gemm_w_at(g, Wp, n, k0 + k);
             float hi, lo;
-            split_tf32(v, hi, lo);
+            split_tf32_rn(v, hi, lo);
             uint32_t off = (uint32_t)kb * 2 * geo.w_bytes + (uint32_t)n * 16 + (uint32_t)(k >> 2) * geo.w_lbo + (k & 3) * 4;
             *reinterpret_cast<float*>(W_hi + off) = hi;
             *reinterpret_cast<float*>(W_lo + off) = lo;
@@ -178,7 +193,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
 
     if (warp < 4) {
         // ===================== producers =====================
-        const bool split = g.A.mode == A_SPLIT;
+        const bool split = g.A.mode == A_SPLIT, taps = g.A.mode == A_TAPS;
         float4 pre[NSET][KQM];
         // work item w = (local tile index) * nkb + kb
         auto load_regs = [&](float4 (&r)[KQM], int w) {
@@ -196,8 +211,14 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                     int m = m0 + row, c = kq * 4;
                     if (m < g.M && c < Kb) {
                         c += k0;
-                        if (split && c >= Av.split) c += Av.skip;
-                        r[j] = __ldg(reinterpret_cast<const float4*>(Av.p + (size_t)m * Av.ld + c));
+                        if (taps) {                 // dilated causal convolution: column block j reads the row `sh` steps away
+                            const int tj = c / Av.cc, ch = c - tj * Av.cc, t = m % Av.T, sh = Av.dil * (Av.taps - 1 - tj);
+                            if (t + sh >= 0 && t + sh < Av.T)
+                                r[j] = __ldg(reinterpret_cast<const float4*>(Av.p + (size_t)(m + sh) * Av.ld + ch));
+                        } else {
+                            if (split && c >= Av.split) c += Av.skip;
+                            r[j] = __ldg(reinterpret_cast<const float4*>(Av.p + (size_t)m * Av.ld + c));
+                        }
                     }
                 }
             }
@@ -211,7 +232,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                     int i = tid + j * 128;
                     int row = i / KQ, kq = i - row * KQ;
                     float4 hi, lo;
-                    split_tf32x4(r[j], hi, lo);
+                    split_tf32x4_rn(r[j], hi, lo);
                     uint32_t off = (uint32_t)row * 16 + (uint32_t)kq * TC_A_LBO;
                     *reinterpret_cast<float4*>(A_hi + off) = hi;
                     *reinterpret_cast<float4*>(A_lo + off) = lo;
@@ -330,13 +351,22 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                 const uint32_t a_hi_s = smem_u32(A_base + (size_t)s * 2 * geo.a_bytes), a_lo_s = a_hi_s + geo.a_bytes;
                 const uint32_t wkb = (uint32_t)kb * 2 * geo.w_bytes;
                 if (elect_one_sync()) {
+                    // The TMEM accumulator TRUNCATES on every accumulate (an error of up to one ulp of its current value): the
+                    // two correction terms of the 3xTF32 split (2^-11 of the result) go in first, while the accumulator is
+                    // still small, so only the K/8 hi.hi accumulates cost precision (measured: 1.3e-6 -> relative error of a
+                    // K = 128 product with the three terms interleaved).
                     for (int ks = 0; ks < (KP >> 3); ks++) {
                         uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = wkb + (uint32_t)ks * 2 * geo.w_lbo;
                         uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128), dal = umma_desc(a_lo_s + ao, TC_A_LBO, 128);
                         uint64_t dbh = umma_desc(w_hi_s + wo, geo.w_lbo, 128), dbl = umma_desc(w_lo_s + wo, geo.w_lbo, 128);
-                        umma_tf32(acc, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                        umma_tf32(acc, dal, dbh, idesc, 1u);
+                        umma_tf32(acc, dal, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
                         umma_tf32(acc, dah, dbl, idesc, 1u);
+                    }
+                    for (int ks = 0; ks < (KP >> 3); ks++) {
+                        uint32_t ao = (uint32_t)ks * 2 * TC_A_LBO, wo = wkb + (uint32_t)ks * 2 * geo.w_lbo;
+                        uint64_t dah = umma_desc(a_hi_s + ao, TC_A_LBO, 128);
+                        uint64_t dbh = umma_desc(w_hi_s + wo, geo.w_lbo, 128);
+                        umma_tf32(acc, dah, dbh, idesc, 1u);
                     }
                     umma_commit(bar_empty + 8u * s);    // smem stage may be refilled once these MMAs retire
                     if (kb == nkb - 1) umma_commit(bar_tfull + 8u * a);        // accumulator ready for the epilogue warps
@@ -383,9 +413,10 @@ static bool tc_rows_geom(int N, int K, TcRowsGeom& geo, size_t& smem, int nkb = 
 
 static bool tc_rows_eligible(const GemmArgs& g) {
     if (g.M < 2048 || g.N > 256 || g.K > 128 * (g.ksplit > 1 ? g.ksplit : 1) || g.N < 8) return false;
-    if (g.A.mode != A_PLAIN && g.A.mode != A_SPLIT) return false;
+    if (g.A.mode != A_PLAIN && g.A.mode != A_SPLIT && g.A.mode != A_TAPS) return false;
     if ((g.A.ld & 3) || (g.K & 3) || !aligned16(g.A.p)) return false;
     if (g.A.mode == A_SPLIT && ((g.A.split & 3) || (g.A.skip & 3))) return false;
+    if (g.A.mode == A_TAPS && ((g.A.cc & 3) || g.nkb == 2)) return false;
     if (!aligned16(g.C) || (g.mask && !aligned16(g.mask))) return false;
     if (g.nkb == 2) {
         if (g.A2.mode != g.A.mode || g.A2.ld != g.A.ld || g.A2.split != g.A.split || g.A2.skip != g.A.skip) return false;
@@ -575,7 +606,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
                     int ml = mblk * 8 + r8, cq = cb * 4 + c4;
                     if (cq < (isP ? NQ : KQ)) {
                         float4 hi, lo;
-                        split_tf32x4(r[j], hi, lo);
+                        split_tf32x4_rn(r[j], hi, lo);
                         // rows 4cq..4cq+3 of the transposed tile: 8-row group cq>>1, row-in-group 4*(cq&1)+e
                         uint32_t off = (uint32_t)(cq >> 1) * TCW_SBO + (uint32_t)(4 * (cq & 1)) * 16 + (uint32_t)(ml >> 2) * TCW_LBO + (ml & 3) * 4;
                         unsigned char* bh = (isP ? P_hi : Q_hi) + off;

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) gemm_big_tc_kernel(const GemmA
 static bool tc_big_eligible(const GemmArgs& g) {
     // same row threshold as the weight-resident kernel (tc_rows_eligible): batches chunked below it stay on ONE arithmetic path
     if (!tc_enabled() || g.M < 2048 || g.N < 8 || g.K < 8 || (g.K & 3)) return false;
-    if (g.A.mode != A_PLAIN || (g.A.ld & 3) || !aligned16(g.A.p) || g.nkb == 2) return false;
+    if (g.A.mode != A_PLAIN || (g.A.ld & 3) || !aligned16(g.A.p) || g.nkb == 2 || g.wconv) return false;
     return true;
 }
 

@@ -323,12 +323,12 @@ static int tfm_col(dof_handle* h, bool bwd, int kind, const float* x, float* y, 
     return DOF_OK;
 }
 
-static CensArgs tfm_cens_args(dof_handle* h, const float* state, int B) {
+static CensArgs tfm_cens_args(dof_handle* h, const float* state, const float* node, const float* edge, int B) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     CensArgs a;
     memset(&a, 0, sizeof(a));
-    a.node = h->tc[0].l[L.layers - 1].Y2; a.edge = h->tc[1].l[L.layers - 1].Y2;
+    a.node = node; a.edge = edge;
     a.lap = state + L.lap; a.elap = state + L.elap; a.inc = state + L.inc;
     a.wn = state + L.node_weights; a.we = state + L.edge_weights;
     a.Pn = h->Pn; a.Pe = h->Pe;
@@ -336,6 +336,8 @@ static CensArgs tfm_cens_args(dof_handle* h, const float* state, int B) {
     return a;
 }
 
+static int enc_tail_forward(dof_handle* h, const float* state, const float* node, const float* edge, int Bw, bool train, int groups,
+                            bool standardise, cudaStream_t st);
 // TFMEncoderPT.forward: Bw windows -> h->enc [Bw, D].  `groups`: row ranges with separate batch statistics (train only).
 static int tfm_encoder_forward(dof_handle* h, const float* state, const float* x, const float* a, int Bw, bool train, int groups,
                                cudaStream_t st) {
@@ -347,7 +349,18 @@ static int tfm_encoder_forward(dof_handle* h, const float* state, const float* x
     const DropPlan dp = drop_plan(c, L, Bw, 0, 0);
     if (train && h->drop_masks && h->drop_mask_bytes < dp.total) DOF_FAIL(DOF_ERR_ARG, "dropout masks: %zu bytes < %zu", h->drop_mask_bytes, dp.total);
     DOF_TRY(fork_join_blocks(h, st, [&](int b, cudaStream_t s) { return tfm_core_forward(h, b, state, b == 0 ? x : a, Bw, train, dp, s); }));
-    CensArgs ca = tfm_cens_args(h, state, Bw);
+    return enc_tail_forward(h, state, h->tc[0].l[L.layers - 1].Y2, h->tc[1].l[L.layers - 1].Y2, Bw, train, groups, true, st);
+}
+
+// What follows the per-node / per-edge sequence models in TFMEncoderPT (:1123-1164) AND TCNEncoderPT (:630-657): CensNet, ReLU,
+// per-sample RMS normalisation, the head MLP with two BatchNorm layers, and (transformer only) the batch standardisation.
+// node [Bw * N, L.dk], edge [Bw * E, L.dk] -> h->enc [Bw, D]
+static int enc_tail_forward(dof_handle* h, const float* state, const float* node, const float* edge, int Bw, bool train, int groups,
+                            bool standardise, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int N = c.N, E = c.E, D = c.D, dk = L.dk, KD = (N + E) * D;
+    CensArgs ca = tfm_cens_args(h, state, node, edge, Bw);
     const size_t smem = cens_smem_floats(N, E, dk) * 4;
     if (smem > 200 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "graph too large for the CensNet kernel (%zu B smem)", smem);
     static bool attr = false;
@@ -374,8 +387,8 @@ static int tfm_encoder_forward(dof_handle* h, const float* state, const float* x
     DOF_TRY(tfm_gemm(h->h1, 2 * D, state + L.h_w3, 2 * D, 0, state + L.h_b3, h->h2r, D, Bw, D, 2 * D, 1, 0, nullptr, 0, st));
     DOF_TRY(tfm_col(h, false, kind, h->h2r, h->h2, state + L.bn5.w, state + L.bn5.b, state + L.bn5.mean, state + L.bn5.var, 1, h->bnstat[1],
                     nullptr, nullptr, nullptr, nullptr, nullptr, Bw, D, groups, st));
-    DOF_TRY(tfm_gemm(h->h2, D, state + L.h_w6, D, 0, state + L.h_b6, train ? h->h3 : h->enc, D, Bw, D, D, 0, 0, nullptr, 0, st));
-    if (train)      // batch standardisation (:1161-1162)
+    DOF_TRY(tfm_gemm(h->h2, D, state + L.h_w6, D, 0, state + L.h_b6, (train && standardise) ? h->h3 : h->enc, D, Bw, D, D, 0, 0, nullptr, 0, st));
+    if (train && standardise)      // batch standardisation (:1161-1162)
         DOF_TRY(tfm_col(h, false, 2, h->h3, h->enc, nullptr, nullptr, nullptr, nullptr, 2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                         Bw, D, groups, st));
     h->enc_groups = groups;
@@ -384,15 +397,31 @@ static int tfm_encoder_forward(dof_handle* h, const float* state, const float* x
 }
 
 // backward of the transformer encoder from h->denc [Bw, D]
+static int enc_tail_backward(dof_handle* h, const float* state, float* grad, const float* node, const float* edge, float* dnode, float* dedge,
+                             int Bw, bool standardise, cudaStream_t st);
 static int tfm_encoder_backward(dof_handle* h, const float* state, float* grad, int Bw, cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
-    const int N = c.N, E = c.E, D = c.D, dk = L.dk, KD = (N + E) * D, sm = h->sm_count, groups = h->enc_groups;
     const DropPlan dp = drop_plan(c, L, Bw, 0, 0);
-    DOF_TRY(tfm_col(h, true, 2, h->h3, nullptr, nullptr, nullptr, nullptr, nullptr, 2, nullptr, h->denc, h->dh3, nullptr, nullptr, nullptr, Bw, D,
-                    groups, st));
-    DOF_TRY(tfm_wgrad(h->dh3, D, h->h2, D, grad + L.h_w6, D, 0, grad + L.h_b6, Bw, D, D, sm, st));
-    DOF_TRY(tfm_gemm(h->dh3, D, state + L.h_w6, D, 1, nullptr, h->dh2, D, Bw, D, D, 0, 0, nullptr, 0, st));
+    DOF_TRY(enc_tail_backward(h, state, grad, h->tc[0].l[L.layers - 1].Y2, h->tc[1].l[L.layers - 1].Y2, h->tc[0].dOut, h->tc[1].dOut, Bw, true, st));
+    DOF_TRY(fork_join_blocks(h, st, [&](int b, cudaStream_t s) { return tfm_core_backward(h, b, state, grad, Bw, dp, s); }));
+    return DOF_OK;
+}
+
+// backward of enc_tail_forward from h->denc [Bw, D]: parameter gradients of the head and CensNet, dnode [Bw * N, dk], dedge
+static int enc_tail_backward(dof_handle* h, const float* state, float* grad, const float* node, const float* edge, float* dnode, float* dedge,
+                             int Bw, bool standardise, cudaStream_t st) {
+    const dof_config& c = h->cfg;
+    const Layout& L = h->L;
+    const int N = c.N, E = c.E, D = c.D, dk = L.dk, KD = (N + E) * D, sm = h->sm_count, groups = h->enc_groups;
+    const float* dh3 = h->denc;
+    if (standardise) {
+        DOF_TRY(tfm_col(h, true, 2, h->h3, nullptr, nullptr, nullptr, nullptr, nullptr, 2, nullptr, h->denc, h->dh3, nullptr, nullptr, nullptr, Bw, D,
+                        groups, st));
+        dh3 = h->dh3;
+    }
+    DOF_TRY(tfm_wgrad(dh3, D, h->h2, D, grad + L.h_w6, D, 0, grad + L.h_b6, Bw, D, D, sm, st));
+    DOF_TRY(tfm_gemm(dh3, D, state + L.h_w6, D, 1, nullptr, h->dh2, D, Bw, D, D, 0, 0, nullptr, 0, st));
     DOF_TRY(tfm_col(h, true, 0, h->h2r, nullptr, state + L.bn5.w, nullptr, nullptr, nullptr, 1, nullptr, h->dh2, h->dh2r, grad + L.bn5.w,
                     grad + L.bn5.b, h->h2r, Bw, D, groups, st));
     DOF_TRY(tfm_wgrad(h->dh2r, D, h->h1, 2 * D, grad + L.h_w3, 2 * D, 0, grad + L.h_b3, Bw, D, 2 * D, sm, st));
@@ -413,15 +442,14 @@ static int tfm_encoder_backward(dof_handle* h, const float* state, float* grad, 
     DOF_TRY(tfm_wgrad(h->dOe, D, h->Pe, dk, grad + L.edge_kernel, D, 1, grad + L.edge_bias, Bw * E, D, dk, sm, st));
     DOF_TRY(tfm_gemm(h->dOn, D, state + L.node_kernel, D, 0, nullptr, h->dPn, dk, Bw * N, dk, D, 0, 0, nullptr, 0, st));
     DOF_TRY(tfm_gemm(h->dOe, D, state + L.edge_kernel, D, 0, nullptr, h->dPe, dk, Bw * E, dk, D, 0, 0, nullptr, 0, st));
-    CensArgs ca = tfm_cens_args(h, state, Bw);
-    ca.dPn = h->dPn; ca.dPe = h->dPe; ca.dnode = h->tc[0].dOut; ca.dedge = h->tc[1].dOut;
+    CensArgs ca = tfm_cens_args(h, state, node, edge, Bw);
+    ca.dPn = h->dPn; ca.dPe = h->dPe; ca.dnode = dnode; ca.dedge = dedge;
     ca.dwn = grad + L.node_weights; ca.dwe = grad + L.edge_weights;
     const size_t smem = (cens_smem_floats(N, E, dk) + (size_t)(N + E) * dk + (size_t)N * N + (size_t)E * E + N + E) * 4;
     if (smem > 220 * 1024) DOF_FAIL(DOF_ERR_UNSUPPORTED, "graph too large for the CensNet backward kernel");
     { ProfScope ps("cens_bwd", st);
     cens_bwd_kernel<<<Bw, 128, smem, st>>>(ca); }
     DOF_LAUNCH_CHECK();
-    DOF_TRY(fork_join_blocks(h, st, [&](int b, cudaStream_t s) { return tfm_core_backward(h, b, state, grad, Bw, dp, s); }));
     return DOF_OK;
 }
 

@@ -402,6 +402,7 @@ struct TfmRmsArgs {
     const float* dh;                    // backward
     float* don; float* doe;
     int B, ND, ED;
+    int norelu;                         // backward: the inputs are NOT ReLU outputs (TCN decoder latent): no mask
 };
 
 __global__ void __launch_bounds__(256) tfm_rms_fwd_kernel(const TfmRmsArgs a) {
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(256) tfm_rms_bwd_kernel(const TfmRmsArgs a) {
         float d = a.dh[(size_t)warp * KD + k];
         if (fabsf(hv) > 1e4f) d = 0.f;
         if (rms > 1.0f) d = (d - hv * dot) * inv;
-        if (k < a.ND) a.don[(size_t)warp * a.ND + k] = a.on[(size_t)warp * a.ND + k] > 0.f ? d : 0.f;
+        if (k < a.ND) a.don[(size_t)warp * a.ND + k] = (a.norelu || a.on[(size_t)warp * a.ND + k] > 0.f) ? d : 0.f;
         else a.doe[(size_t)warp * a.ED + (k - a.ND)] = a.oe[(size_t)warp * a.ED + (k - a.ND)] > 0.f ? d : 0.f;
     }
 }

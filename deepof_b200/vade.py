@@ -126,7 +126,7 @@ TFM_BUFFERS = ("encoder.head.2.running_mean", "encoder.head.2.running_var", "enc
 
 
 class VaDEB200:
-    """B200-native stand-in for ``VaDEPT(encoder_type="recurrent" | "transformer", use_gnn=True)``."""
+    """B200-native stand-in for ``VaDEPT(encoder_type="recurrent" | "transformer" | "TCN", use_gnn=True)``."""
     _MODEL = _lib.MODEL_VADE
     _BUFFERS = ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence", "latent_space.prior",
                 "latent_space.pretrain") + TFM_BUFFERS
@@ -137,7 +137,7 @@ class VaDEB200:
                  interaction_regularization: float = 0.0, device: Optional[int] = None, max_batch: int = 4096,
                  training: bool = True, seed: Optional[int] = None):
         if encoder_type not in _lib.ENCODER_KINDS or not use_gnn:
-            raise NotImplementedError("deepof_b200 implements the recurrent and the transformer GNN encoders "
+            raise NotImplementedError("deepof_b200 implements the recurrent, transformer and TCN GNN encoders "
                                       f"(got encoder_type={encoder_type!r}, use_gnn={use_gnn})")
         self.encoder_type = encoder_type
         if not torch.cuda.is_available():
@@ -253,6 +253,14 @@ class VaDEB200:
                 val = uni(shape, 1.0 / math.sqrt(hidden))
             elif ".norm" in name or (name.startswith("encoder.head.") and len(shape) == 1 and name.split(".")[2] in ("2", "5")):
                 val = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)        # LayerNorm / BatchNorm affine
+            elif ".bn" in name and leaf in ("weight", "bias"):                 # BatchNorm affine of the TCN blocks / decoder
+                val = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+            elif self.encoder_type == "TCN" and (".conv1." in name or ".conv2." in name or ".downsample." in name):
+                # nn.init.normal_(std=0.05) weights, zero biases (models_new.py:420-428)
+                val = torch.randn(shape, generator=g) * 0.05 if leaf == "weight" else torch.zeros(shape)
+            elif self.encoder_type == "TCN" and (name.startswith("encoder.head.") or name.startswith("decoder.fc")):
+                # xavier_uniform_ weights, zero biases (models_new.py:604-607, 776-779)
+                val = uni(shape, math.sqrt(6.0 / (shape[0] + shape[1]))) if leaf == "weight" else torch.zeros(shape)
             elif self.encoder_type == "transformer" and ("_tf." in name or name.startswith("encoder.head.") or name.startswith("decoder.")):
                 # xavier_uniform_ weights, zero biases (models_new.py:868-871, 1085-1089, 1225-1230); embed / prob_decoder keep
                 # nn.Linear's default init
@@ -307,7 +315,8 @@ class VaDEB200:
         return [v for (name, *_r, grp), v in zip(self.layout, self._views.values()) if grp > 0]
 
     def named_parameters(self):
-        return [(name, v) for (name, *_r, grp), v in zip(self.layout, self._views.values()) if name not in self._BUFFERS]
+        return [(name, v) for (name, *_r, grp), v in zip(self.layout, self._views.values())
+                if name not in self._BUFFERS and not name.endswith(("running_mean", "running_var", "num_batches_tracked"))]
 
     def to(self, *a, **k):
         return self

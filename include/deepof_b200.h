@@ -54,8 +54,16 @@ typedef struct {
  *               decoder: latent expansion MLP (GELU) to 4*D, 2 pre-LN causal self-attention layers (8 heads, dff 128,
  *               dropout 0.2).  The state layout follows the reference state_dict of that model; the integer
  *               num_batches_tracked buffers are carried as one float each. */
+/*  TCN          TCNEncoderPT + TCNDecoderPT (models_new.py:376-657, 713-819): per node / edge TCN1DPT (2 stacks of dilations
+ *               1,2,4,8; 32 filters, kernel 4, causal padding, skip connections, train-mode BatchNorm eps 1e-3 momentum 0.1,
+ *               no dropout), last step -> CensNet -> the same RMS normalisation and head MLP as the transformer encoder (no
+ *               batch standardisation); decoder: RMS normalisation, three Dense + BatchNorm (momentum 0.01) layers to 4*D,
+ *               repeated over the window, TCN1DPT (dilations 8,4,2,1; 64 filters) and the probabilistic head.  The dilated
+ *               causal convolutions run as tcgen05 GEMMs over time-shifted views; BatchNorm running buffers are updated by
+ *               dof_clip_adam from the batch statistics of every encoder / decoder pass of the preceding step. */
 #define DOF_ENCODER_RECURRENT 0
 #define DOF_ENCODER_TRANSFORMER 1
+#define DOF_ENCODER_TCN 2
 
 /* Model kinds (all with encoder_type="recurrent", use_gnn=True):
  *  VADE         VaDEPT        deepof/clustering/models_new.py:1794-1976  encoder + decoder + latent_space

@@ -108,10 +108,54 @@ def transformer_shapes(kind, N, E, F, Fe, D, K, heads=4, dff=128, layers=2, dec_
     return d
 
 
+def _bn(d, pre, C):
+    for nm in ("weight", "bias", "running_mean", "running_var"):
+        d[pre + nm] = (C,)
+    d[pre + "num_batches_tracked"] = ()
+
+
+def _tcn_stack(d, pre, cin, C, nb):
+    for i in range(nb):
+        q = pre + f"blocks.{i}."
+        d[q + "conv1.weight"], d[q + "conv1.bias"] = (C, cin, 4), (C,)
+        _bn(d, q + "bn1.", C)
+        d[q + "conv2.weight"], d[q + "conv2.bias"] = (C, C, 4), (C,)
+        _bn(d, q + "bn2.", C)
+        if cin != C:
+            d[q + "downsample.weight"], d[q + "downsample.bias"] = (C, cin, 1), (C,)
+        cin = C
+
+
+def tcn_shapes(kind, N, E, F, Fe, D, K):
+    """TCNEncoderPT :574-607, TCNDecoderPT :745-775 (models_new.py)."""
+    d = OrderedDict()
+    d["encoder.laplacian"], d["encoder.edge_laplacian"], d["encoder.incidence"] = (N, N), (E, E), (N, E)
+    _tcn_stack(d, "encoder.node_tcn.", F, 32, 8)
+    _tcn_stack(d, "encoder.edge_tcn.", Fe, 32, 8)
+    g = "encoder.spatial_gnn_block."
+    d[g + "node_kernel"], d[g + "edge_kernel"] = (32, D), (32, D)
+    d[g + "node_weights"], d[g + "edge_weights"] = (32, 1), (32, 1)
+    d[g + "node_bias"], d[g + "edge_bias"] = (D,), (D,)
+    d["encoder.head.0.weight"], d["encoder.head.0.bias"] = (2 * D, (N + E) * D), (2 * D,)
+    _bn(d, "encoder.head.2.", 2 * D)
+    d["encoder.head.3.weight"], d["encoder.head.3.bias"] = (D, 2 * D), (D,)
+    _bn(d, "encoder.head.5.", D)
+    d["encoder.head.6.weight"], d["encoder.head.6.bias"] = (D, D), (D,)
+    if kind == "contrastive":
+        return d
+    for i, (o, k) in enumerate(((D, D), (2 * D, D), (4 * D, 2 * D))):
+        d[f"decoder.fc{i}.weight"], d[f"decoder.fc{i}.bias"] = (o, k), (o,)
+        _bn(d, f"decoder.bn{i}.", o)
+    _tcn_stack(d, "decoder.tcn.", 4 * D, 64, 4)
+    d["decoder.prob_decoder.loc_projection.weight"], d["decoder.prob_decoder.loc_projection.bias"] = (N * F, 64), (N * F,)
+    _tail(d, kind, D, K)
+    return d
+
+
 def random_params(kind, encoder, N, E, F, Fe, D, K, graph, seed=0, scale=0.1):
     """A parameter dictionary with N(0, scale^2) weights, unit LayerNorm / BatchNorm scales, the graph operators of
     `graph` = (laplacian, edge_laplacian, incidence) and a uniform GMM prior: enough for timing and property tests."""
-    shapes = (transformer_shapes if encoder == "transformer" else recurrent_shapes)(kind, N, E, F, Fe, D, K)
+    shapes = {"transformer": transformer_shapes, "TCN": tcn_shapes}.get(encoder, recurrent_shapes)(kind, N, E, F, Fe, D, K)
     g = torch.Generator().manual_seed(seed)
     p = OrderedDict()
     for name, shape in shapes.items():
@@ -119,7 +163,7 @@ def random_params(kind, encoder, N, E, F, Fe, D, K, graph, seed=0, scale=0.1):
             p[name] = torch.zeros((), dtype=torch.int64)
         elif name.endswith("running_mean"):
             p[name] = torch.zeros(shape)
-        elif name.endswith("running_var") or ((".norm" in name or ".head.2." in name or ".head.5." in name) and name.endswith("weight")):
+        elif name.endswith("running_var") or ((".norm" in name or ".head.2." in name or ".head.5." in name or ".bn" in name) and name.endswith("weight") and len(shape) == 1):
             p[name] = torch.ones(shape)
         elif name == "latent_space.prior":
             p[name] = torch.full(shape, 1.0 / K)

@@ -196,7 +196,7 @@ def run_vade(name, c):
 
 STEP_CASES = {
     "vq_small": dict(model="vqvae", T=12, N=11, D=6, K=7, B=8, seed=191, beta=1.0),
-    "vq_cfg3": dict(model="vqvae", T=25, N=14, D=16, K=64, B=6, seed=192, beta=0.25),
+    "vq_cfg3": dict(model="vqvae", T=25, N=14, D=16, K=64, B=16, seed=196, beta=0.25),
     "con_small": dict(model="contrastive", T=24, N=11, D=6, K=1, B=8, seed=193),
     "con_cfg": dict(model="contrastive", T=50, N=14, D=8, K=1, B=6, seed=194),
 }

@@ -114,3 +114,25 @@ def test_transformer_layouts_are_reference_state_dict(built):
     bad = DofTfmCfg(T, N, E, 3, 1, D, 42, 4, 128, 2)            # key_dim not a multiple of heads
     assert L.dof_tfm_num_entries(C.byref(bad)) < 0 and L.dof_tfm_numel(C.byref(bad)) < 0
     assert "key_dim" in L.dof_last_error().decode()
+
+
+def test_tcn_state_layout_is_the_reference_state_dict():
+    """dof_state_entry for DOF_ENCODER_TCN lists exactly the reference's state_dict (names, order, shapes) of the three models built
+    with encoder_type="TCN" (goldens from the unmodified reference), and the workspace query works without a device."""
+    import ctypes as C
+    from deepof_b200 import _lib
+    from deepof_b200.vade import state_layout
+    from helpers import load_golden_of
+    for kind, case, model in (("tcnvade", "cfg2", _lib.MODEL_VADE), ("tcnvade", "main", _lib.MODEL_VADE), ("tcnstep", "vq_small", _lib.MODEL_VQVAE),
+                              ("tcnstep", "con_cfg", _lib.MODEL_CONTRASTIVE)):
+        g = load_golden_of(kind, case)
+        T, N, E, D, K, B = (int(v) for v in g["meta"])
+        cfg = _lib.DofConfig(T // 2 if model == _lib.MODEL_CONTRASTIVE else T, N, E, 3, 1, D, K, model, _lib.ENCODER_KINDS["TCN"])
+        lay = state_layout(cfg)
+        assert [k for k, *_ in lay] == [k[2:] for k in g if k.startswith("p/")]
+        for k, off, numel, shape, grp in lay:
+            assert tuple(shape) == tuple(g["p/" + k].shape), k
+            assert (grp == 0) == (k.endswith(("running_mean", "running_var", "num_batches_tracked")) or k in
+                                  ("encoder.laplacian", "encoder.edge_laplacian", "encoder.incidence", "latent_space.prior", "latent_space.pretrain",
+                                   "latent_space.lens.weight", "latent_space.lens.bias")), k
+        assert _lib.lib().dof_workspace_bytes(C.byref(cfg), 256, 1) > _lib.lib().dof_workspace_bytes(C.byref(cfg), 256, 0) > 0

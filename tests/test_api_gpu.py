@@ -49,9 +49,10 @@ def _table_dicts(N, T, n_videos, nw, seed):
 
 @pytest.mark.parametrize("model_name,T,enc", [("VaDE", 25, "recurrent"), ("VaDE", 12, "transformer"), ("VQVAE", 25, "recurrent"),
                                               ("VQVAE", 12, "transformer"), ("Contrastive", 24, "recurrent"),
-                                              ("Contrastive", 24, "transformer")])
+                                              ("Contrastive", 24, "transformer"), ("VaDE", 12, "TCN"), ("VQVAE", 12, "TCN"),
+                                              ("Contrastive", 24, "TCN")])
 def test_train_deepof_model_end_to_end(model_name, T, enc, tmp_path):
-    """The reference's run for the three model kinds and both encoder families, TURTLE teacher ON (the reference default):
+    """The reference's run for the three model kinds and the three encoder families, TURTLE teacher ON (the reference default):
     per-epoch validation + diagnostics, log_summary in the reference's structure, best-val / best-score checkpoints under
     the reference's paths, the (model_val, model_score, teacher_init_model, log_summary) tuple, checkpoint round trip."""
     from deepof_b200 import train_deepof_model, load_model_from_ckpt
@@ -61,7 +62,7 @@ def test_train_deepof_model_end_to_end(model_name, T, enc, tmp_path):
     with pytest.raises(ValueError):
         train_deepof_model((train_td, val_td), adj, None, device="tpu", batch_size=64, latent_dim=6, epochs=1)
     with pytest.raises(NotImplementedError):
-        train_deepof_model((train_td, val_td), adj, None, encoder_type="TCN", batch_size=64, latent_dim=6, epochs=1)
+        train_deepof_model((train_td, val_td), adj, None, encoder_type="LSTM", batch_size=64, latent_dim=6, epochs=1)
     with pytest.raises(NotImplementedError):
         train_deepof_model((train_td, val_td), adj, None, encoder_type=enc, batch_size=64, latent_dim=6, epochs=1, use_amp=True)
     epochs = 6

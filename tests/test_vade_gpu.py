@@ -285,7 +285,7 @@ def test_errors_are_loud():
     from deepof_b200 import VaDEB200, DofError, VadeLossCfg
     adj = O.default_adjacency(5)
     with pytest.raises(NotImplementedError):
-        VaDEB200((12, 5, 3), (12, 5, 1), adj, 4, 3, encoder_type="TCN")
+        VaDEB200((12, 5, 3), (12, 4, 1), adj, 4, 3, encoder_type="LSTM")
     m = VaDEB200((12, 5, 3), (12, 4, 1), adj, 4, 3, max_batch=4, training=False)
     x, a = O.synthetic_windows(8, 12, adj, seed=1)
     with pytest.raises(DofError):
