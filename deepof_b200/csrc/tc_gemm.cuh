@@ -195,47 +195,66 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
         // ===================== producers =====================
         const bool split = g.A.mode == A_SPLIT, taps = g.A.mode == A_TAPS;
         float4 pre[NSET][KQM];
-        // work item w = (local tile index) * nkb + kb
+        // work item w = (local tile index) * nkb + kb.  Thread tid owns the float4 items i = tid + 128 j of a [128 x KQ] block:
+        // (row, kq) = (i / KQ, i % KQ) advance by (128 / KQ, 128 % KQ) per j — tracked incrementally, no division per item
+        // (the per-item divisions by runtime KQ / T / channel count were 190 instructions per float4: the producers of the
+        // K = 128 TCN convolution issued 24 k warp instructions per tile and bound the kernel at 1.03 ms per 1.4 M rows).
+        const int rstep = 128 / KQ, kstep = 128 - rstep * KQ;
+        const int row_t = tid / KQ, kq_t = tid - row_t * KQ;
         auto load_regs = [&](float4 (&r)[KQM], int w) {
             const int tile = blockIdx.x + (w / nkb) * gridDim.x;
             const int kb = w % nkb;
             const MatView& Av = (kb / ksp) ? g.A2 : g.A;
             const int k0 = (kb % ksp) * Kb;
             const int m0 = tile * 128;
+            int row = row_t, kq = kq_t;
+            int t = taps ? (m0 + row) % Av.T : 0, ch = 0, sh = 0;
+            if (taps && kstep == 0) {           // KQ divides 128: this thread's column (tap, channel) never changes
+                const int c0 = kq * 4 + k0, tj = c0 / Av.cc;
+                ch = c0 - tj * Av.cc; sh = Av.dil * (Av.taps - 1 - tj);
+            }
 #pragma unroll
             for (int j = 0; j < KQM; j++) {
-                int i = tid + j * 128;
                 r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < KQ) {
-                    int row = i / KQ, kq = i - row * KQ;
-                    int m = m0 + row, c = kq * 4;
-                    if (m < g.M && c < Kb) {
-                        c += k0;
-                        if (taps) {                 // dilated causal convolution: column block j reads the row `sh` steps away
-                            const int tj = c / Av.cc, ch = c - tj * Av.cc, t = m % Av.T, sh = Av.dil * (Av.taps - 1 - tj);
-                            if (t + sh >= 0 && t + sh < Av.T)
-                                r[j] = __ldg(reinterpret_cast<const float4*>(Av.p + (size_t)(m + sh) * Av.ld + ch));
-                        } else {
-                            if (split && c >= Av.split) c += Av.skip;
-                            r[j] = __ldg(reinterpret_cast<const float4*>(Av.p + (size_t)m * Av.ld + c));
+                    const int m = m0 + row;
+                    int c = kq * 4;
+                    bool ok = m < g.M && c < Kb;
+                    const float* ptr;
+                    c += k0;
+                    if (taps) {                 // dilated causal convolution: column block tj reads the row `sh` steps away
+                        if (kstep != 0) {
+                            const int tj = c / Av.cc;
+                            ch = c - tj * Av.cc; sh = Av.dil * (Av.taps - 1 - tj);
                         }
+                        ok = ok && (unsigned)(t + sh) < (unsigned)Av.T;
+                        ptr = Av.p + (long long)(m + sh) * Av.ld + ch;
+                    } else {
+                        if (split && c >= Av.split) c += Av.skip;
+                        ptr = Av.p + (size_t)m * Av.ld + c;
                     }
+                    if (ok) r[j] = __ldg(reinterpret_cast<const float4*>(ptr));
+                    int dr = rstep;
+                    row += rstep; kq += kstep;
+                    if (kq >= KQ) { kq -= KQ; row++; dr++; }
+                    if (taps) { t += dr; while (t >= Av.T) t -= Av.T; }
                 }
             }
         };
         auto store_smem = [&](const float4 (&r)[KQM], int stage) {
             unsigned char* A_hi = A_base + (size_t)stage * 2 * geo.a_bytes;
             unsigned char* A_lo = A_hi + geo.a_bytes;
+            int row = row_t, kq = kq_t;
 #pragma unroll
             for (int j = 0; j < KQM; j++) {
                 if (j < KQ) {
-                    int i = tid + j * 128;
-                    int row = i / KQ, kq = i - row * KQ;
                     float4 hi, lo;
                     split_tf32x4_rn(r[j], hi, lo);
                     uint32_t off = (uint32_t)row * 16 + (uint32_t)kq * TC_A_LBO;
                     *reinterpret_cast<float4*>(A_hi + off) = hi;
                     *reinterpret_cast<float4*>(A_lo + off) = lo;
+                    row += rstep; kq += kstep;
+                    if (kq >= KQ) { kq -= KQ; row++; }
                 }
             }
         };

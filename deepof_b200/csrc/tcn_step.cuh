@@ -34,11 +34,24 @@ static TcnBn tcn_bn_ref(const dof_handle* h, const float* state, const TfmBnP& b
     return r;
 }
 
+// K = 4 * channels > 128 (the decoder's 64-channel convolutions, K = 256) only fits the weight-resident tensor-core kernel when it is
+// staged in 32-column blocks (GemmArgs.ksplit).  For K = 128 the single 128-column stage is faster than four 32-column stages
+// (measured at 1.4 M rows: 0.82 vs 0.95 ms per launch — the per-stage barrier round trips outweigh two CTAs per SM), so the
+// encoder convolutions keep one stage.  DOF_TCN_KSPLIT=<columns> forces a block width for A/B runs (0: never split).
+static void tcn_pick_ksplit(GemmArgs& g) {
+    static const int forced = getenv("DOF_TCN_KSPLIT") ? atoi(getenv("DOF_TCN_KSPLIT")) : -1;
+    const int width = forced >= 0 ? forced : (g.K > 128 ? 32 : 0);
+    if (width <= 0 || g.K <= width || (g.K % width) || (g.A.cc & 3)) return;
+    g.ksplit = g.K / width;
+    if (!tc_rows_eligible(g)) g.ksplit = 0;
+}
+
 // A [R, C] = conv(X [R, cin]) + bias, dilated causal
 static int tcn_conv_fwd(const float* X, int cin, int T, int dil, const float* W, const float* bias, float* A, int C, long long R,
                         cudaStream_t st) {
     GemmArgs g = gemm_args(mv_taps(X, cin, T, TCN_TAPS, cin, -dil), W, cin * TCN_TAPS, 0, bias, A, C, (int)R, C, TCN_TAPS * cin);
     g.wconv = 1; g.wcin = cin; g.wtaps = TCN_TAPS;
+    tcn_pick_ksplit(g);
     return launch_gemm_rows(&g, 1, st);
 }
 
@@ -48,6 +61,7 @@ static int tcn_conv_dgrad(const float* dA, int C, int T, int dil, const float* W
     GemmArgs g = gemm_args(mv_taps(dA, C, T, TCN_TAPS, C, +dil), W, cin * TCN_TAPS, 0, nullptr, dX, cin, (int)R, cin, TCN_TAPS * C);
     g.wconv = 2; g.wcin = cin; g.wtaps = TCN_TAPS; g.accum = accum;
     if (mask) { g.mask = mask; g.ldmask = cin; }
+    tcn_pick_ksplit(g);
     return launch_gemm_rows(&g, 1, st);
 }
 
