@@ -201,17 +201,22 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
         // K = 128 TCN convolution issued 24 k warp instructions per tile and bound the kernel at 1.03 ms per 1.4 M rows).
         const int rstep = 128 / KQ, kstep = 128 - rstep * KQ;
         const int row_t = tid / KQ, kq_t = tid - row_t * KQ;
+        // the operand description in registers: `g` is an element of a by-value kernel argument selected by blockIdx.z, every
+        // access to it is an indexed constant load (LDC) — 880 of them per tile in the K = 128 convolution before this
+        const float* const ap0 = g.A.p; const float* const ap1 = g.nkb == 2 ? g.A2.p : g.A.p;
+        const int a_ld = g.A.ld, a_T = g.A.T, a_cc = g.A.cc, a_dil = g.A.dil, a_taps = g.A.taps, a_split = g.A.split, a_skip = g.A.skip;
+        const int gM = g.M, n_grid = gridDim.x, bx = blockIdx.x;
         auto load_regs = [&](float4 (&r)[KQM], int w) {
-            const int tile = blockIdx.x + (w / nkb) * gridDim.x;
+            const int tile = bx + (w / nkb) * n_grid;
             const int kb = w % nkb;
-            const MatView& Av = (kb / ksp) ? g.A2 : g.A;
+            const float* const ap = (kb / ksp) ? ap1 : ap0;
             const int k0 = (kb % ksp) * Kb;
             const int m0 = tile * 128;
             int row = row_t, kq = kq_t;
-            int t = taps ? (m0 + row) % Av.T : 0, ch = 0, sh = 0;
+            int t = taps ? (m0 + row) % a_T : 0, ch = 0, sh = 0;
             if (taps && kstep == 0) {           // KQ divides 128: this thread's column (tap, channel) never changes
-                const int c0 = kq * 4 + k0, tj = c0 / Av.cc;
-                ch = c0 - tj * Av.cc; sh = Av.dil * (Av.taps - 1 - tj);
+                const int c0 = kq * 4 + k0, tj = c0 / a_cc;
+                ch = c0 - tj * a_cc; sh = a_dil * (a_taps - 1 - tj);
             }
 #pragma unroll
             for (int j = 0; j < KQM; j++) {
@@ -219,25 +224,25 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
                 if (j < KQ) {
                     const int m = m0 + row;
                     int c = kq * 4;
-                    bool ok = m < g.M && c < Kb;
+                    bool ok = m < gM && c < Kb;
                     const float* ptr;
                     c += k0;
                     if (taps) {                 // dilated causal convolution: column block tj reads the row `sh` steps away
                         if (kstep != 0) {
-                            const int tj = c / Av.cc;
-                            ch = c - tj * Av.cc; sh = Av.dil * (Av.taps - 1 - tj);
+                            const int tj = c / a_cc;
+                            ch = c - tj * a_cc; sh = a_dil * (a_taps - 1 - tj);
                         }
-                        ok = ok && (unsigned)(t + sh) < (unsigned)Av.T;
-                        ptr = Av.p + (long long)(m + sh) * Av.ld + ch;
+                        ok = ok && (unsigned)(t + sh) < (unsigned)a_T;
+                        ptr = ap + (long long)(m + sh) * a_ld + ch;
                     } else {
-                        if (split && c >= Av.split) c += Av.skip;
-                        ptr = Av.p + (size_t)m * Av.ld + c;
+                        if (split && c >= a_split) c += a_skip;
+                        ptr = ap + (size_t)m * a_ld + c;
                     }
                     if (ok) r[j] = __ldg(reinterpret_cast<const float4*>(ptr));
                     int dr = rstep;
                     row += rstep; kq += kstep;
                     if (kq >= KQ) { kq -= KQ; row++; dr++; }
-                    if (taps) { t += dr; while (t >= Av.T) t -= Av.T; }
+                    if (taps) { t += dr; while (t >= a_T) t -= a_T; }
                 }
             }
         };
