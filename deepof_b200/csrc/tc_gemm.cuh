@@ -138,9 +138,13 @@ __host__ __device__ static inline int tmem_cols_for(int n) { return n <= 32 ? 32
 
 struct TcRowsGeom { int KP, NP, tmem_cols, w_lbo, stages; uint32_t a_bytes, w_bytes; };
 
-// KQM: float4 chunks per row held in registers per producer thread and per set; NSET register sets
-template <int KQM, int NSET>
-__global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBatch gb, const TcRowsGeom geo) {
+// KQM: float4 items held in registers per producer thread and per set; NSET register sets; PW producer warps (4, or 8 for the
+// K > 64 shapes: one producer warp per scheduler cannot hide its own instruction latency — the K = 128 TCN convolution spent
+// 8.4 us per tile in 4.4 k dependent instructions per producer warp).  Warps [0, PW) produce, [PW, PW + 4) drain TMEM (lane
+// group = warp & 3), warp PW + 4 issues the MMAs.
+template <int KQM, int NSET, int PW = 4>
+__global__ void __launch_bounds__(PW * 32 + 160) gemm_rows_tc_kernel(const GemmBatch gb, const TcRowsGeom geo) {
+    constexpr int PT = PW * 32;
     const GemmArgs& g = gb.g[blockIdx.z];
     extern __shared__ __align__(128) unsigned char tsm[];
     const int S = geo.stages;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), geo.tmem_cols);
     if (tid == 32) {
-        for (int i = 0; i < S; i++) { mbar_init(smem_u32(mbar + i), 128); mbar_init(smem_u32(mbar + S + i), 1); }
+        for (int i = 0; i < S; i++) { mbar_init(smem_u32(mbar + i), PT); mbar_init(smem_u32(mbar + S + i), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(smem_u32(mbar + 2 * S + i), 1); mbar_init(smem_u32(mbar + 2 * S + 2 + i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
     for (int kb = 0; kb < nkb; kb++) {
         const float* Wp = (kb / ksp) ? g.W2 : g.W;
         const int k0 = (kb % ksp) * Kb;
-        for (int i = tid; i < NP * KP; i += TCR_THREADS) {
+        for (int i = tid; i < NP * KP; i += PT + 160) {
             int n, k;
             if (g.wT == 0) { n = i / KP; k = i % KP; } else { k = i / NP; n = i % NP; }
             float v = 0.f;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
             *reinterpret_cast<float*>(W_lo + off) = lo;
         }
     }
-    for (int i = tid; i < NP; i += TCR_THREADS) bias_s[i] = (g.bias && i < g.N) ? __ldg(g.bias + i) : 0.f;
+    for (int i = tid; i < NP; i += PT + 160) bias_s[i] = (g.bias && i < g.N) ? __ldg(g.bias + i) : 0.f;
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -191,15 +195,16 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
     const uint32_t bar_full = smem_u32(mbar), bar_empty = smem_u32(mbar + S);
     const uint32_t bar_tfull = smem_u32(mbar + 2 * S), bar_tempty = smem_u32(mbar + 2 * S + 2);
 
-    if (warp < 4) {
+    if (warp < PW) {
         // ===================== producers =====================
         const bool split = g.A.mode == A_SPLIT, taps = g.A.mode == A_TAPS;
+        const int items = (128 * KQ + PT - 1) / PT;                       // float4 items per producer thread and block
         float4 pre[NSET][KQM];
         // work item w = (local tile index) * nkb + kb.  Thread tid owns the float4 items i = tid + 128 j of a [128 x KQ] block:
         // (row, kq) = (i / KQ, i % KQ) advance by (128 / KQ, 128 % KQ) per j — tracked incrementally, no division per item
         // (the per-item divisions by runtime KQ / T / channel count were 190 instructions per float4: the producers of the
         // K = 128 TCN convolution issued 24 k warp instructions per tile and bound the kernel at 1.03 ms per 1.4 M rows).
-        const int rstep = 128 / KQ, kstep = 128 - rstep * KQ;
+        const int rstep = PT / KQ, kstep = PT - rstep * KQ;
         const int row_t = tid / KQ, kq_t = tid - row_t * KQ;
         // the operand description in registers: `g` is an element of a by-value kernel argument selected by blockIdx.z, every
         // access to it is an indexed constant load (LDC) — 880 of them per tile in the K = 128 convolution before this
@@ -221,10 +226,10 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
 #pragma unroll
             for (int j = 0; j < KQM; j++) {
                 r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < KQ) {
+                if (j < items) {
                     const int m = m0 + row;
                     int c = kq * 4;
-                    bool ok = m < gM && c < Kb;
+                    bool ok = row < 128 && m < gM && c < Kb;
                     const float* ptr;
                     c += k0;
                     if (taps) {                 // dilated causal convolution: column block tj reads the row `sh` steps away
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
             int row = row_t, kq = kq_t;
 #pragma unroll
             for (int j = 0; j < KQM; j++) {
-                if (j < KQ) {
+                if (j < items && row < 128) {
                     float4 hi, lo;
                     split_tf32x4_rn(r[j], hi, lo);
                     uint32_t off = (uint32_t)row * 16 + (uint32_t)kq * TC_A_LBO;
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(TCR_THREADS) gemm_rows_tc_kernel(const GemmBat
             fence_async_smem();
             mbar_arrive(bar_full + 8u * s);
         }
-    } else if (warp < 8) {
+    } else if (warp < PW + 4) {
         // ===================== epilogue =====================
         // TMEM lane = row.  Each warp moves its 32 rows in 32-column chunks through a private padded
         // smem buffer so that every global access is a full 128 B line per row (4 rows / instruction).
@@ -452,14 +457,14 @@ static bool tc_rows_eligible(const GemmArgs& g) {
     return tc_rows_geom(g.N, g.K / ksp, geo, smem, (g.nkb == 2 ? 2 : 1) * ksp);
 }
 
-template <int KQM, int NSET>
+template <int KQM, int NSET, int PW = 4>
 static int launch_rows_tc_t(const GemmBatch& gb, const TcRowsGeom& geo, size_t smem, dim3 grid, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        DOF_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<KQM, NSET>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        DOF_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<KQM, NSET, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         attr = true;
     }
-    gemm_rows_tc_kernel<KQM, NSET><<<grid, TCR_THREADS, smem, st>>>(gb, geo);
+    gemm_rows_tc_kernel<KQM, NSET, PW><<<grid, PW * 32 + 160, smem, st>>>(gb, geo);
     DOF_LAUNCH_CHECK();
     return DOF_OK;
 }
@@ -513,9 +518,20 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     }
     ProfScope ps("gemm_rows_tc", st, fl, by);
     dim3 grid(ctas, 1, nbatch);
+    static const int pws = getenv("DOF_ROWS_PW_SMALL") ? atoi(getenv("DOF_ROWS_PW_SMALL")) : 4;
+    if (pws == 8) {
+        if (KQ <= 8) return launch_rows_tc_t<4, 2, 8>(gb, geo, smem, grid, st);
+        if (KQ <= 16 && occ2) return launch_rows_tc_t<8, 1, 8>(gb, geo, smem, grid, st);
+        if (KQ <= 16) return launch_rows_tc_t<8, 2, 8>(gb, geo, smem, grid, st);
+    }
     if (KQ <= 8) return launch_rows_tc_t<8, 2>(gb, geo, smem, grid, st);
     if (KQ <= 16 && occ2) return launch_rows_tc_t<16, 1>(gb, geo, smem, grid, st);
     if (KQ <= 16) return launch_rows_tc_t<16, 2>(gb, geo, smem, grid, st);
+    // K > 64: eight producer warps with 16 items each (DOF_ROWS_PW8=0 restores four warps with 32 items for A/B runs)
+    static const int pw = getenv("DOF_ROWS_PW") ? atoi(getenv("DOF_ROWS_PW")) : 16;
+    if (pw == 16) return launch_rows_tc_t<8, 1, 16>(gb, geo, smem, grid, st);
+    if (pw == 12) return launch_rows_tc_t<11, 1, 12>(gb, geo, smem, grid, st);
+    if (pw == 8) return launch_rows_tc_t<16, 1, 8>(gb, geo, smem, grid, st);
     return launch_rows_tc_t<32, 1>(gb, geo, smem, grid, st);
 }
 
