@@ -518,7 +518,7 @@ static int launch_gemm_rows_tc(const GemmArgs* gs, int nbatch, cudaStream_t st, 
     }
     ProfScope ps("gemm_rows_tc", st, fl, by);
     dim3 grid(ctas, 1, nbatch);
-    static const int pws = getenv("DOF_ROWS_PW_SMALL") ? atoi(getenv("DOF_ROWS_PW_SMALL")) : 4;
+    static const int pws = getenv("DOF_ROWS_PW_SMALL") ? atoi(getenv("DOF_ROWS_PW_SMALL")) : 8;
     if (pws == 8) {
         if (KQ <= 8) return launch_rows_tc_t<4, 2, 8>(gb, geo, smem, grid, st);
         if (KQ <= 16 && occ2) return launch_rows_tc_t<8, 1, 8>(gb, geo, smem, grid, st);
