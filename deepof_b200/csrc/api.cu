@@ -422,6 +422,7 @@ struct dof_handle {
     int* lenD;
     float *GiD1[2], *HD1, *GtD1[2], *muD1, *rsD1, *YD1;
     float *GiD2[2], *HD2, *GtD2[2], *muD2, *rsD2, *YD2, *Cd, *muD3, *rsD3, *YD3, *loc;
+    float *dlocP = nullptr;    // dloc with its row pitch padded to a multiple of 4 floats (tensor-core weight gradients), or null
     float *dloc, *dYD3, *dCd, *dYD2, *dHD2, *dGD2[2], *dYD1, *dHD1, *dGD1[2], *dGs[2], *Wt;
     // loss
     double* stats; float *coef, *dzm_kl, *dlv_kl, *distw;
@@ -519,7 +520,7 @@ static void plan_workspace_tfm_decoder(dof_handle* h, Bump& bp) {
     h->pe_dec = bp.get<float>((size_t)T * dm);
     for (int i = 0; i < 3; i++) { w.P[i] = bp.get<float>(Bz * eout[i]); w.G[i] = bp.get<float>(Bz * eout[i]); }
     w.H0 = bp.get<float>(R * dm); w.tmpA = bp.get<float>(R * dm); w.tmpB = bp.get<float>(R * dm);
-    w.tmpF = bp.get<float>(R * dff); w.Y = bp.get<float>(R * Dx);
+    w.tmpF = bp.get<float>(R * dff); w.Y = bp.get<float>(R * round_up(Dx, 4));
     for (int l = 0; l < L.dec_layers; l++) {
         TfmDecLayerWS& q = w.l[l];
         const bool keep = tr || l == 0;                          // eval: every layer reuses layer 0's buffers
@@ -530,7 +531,7 @@ static void plan_workspace_tfm_decoder(dof_handle* h, Bump& bp) {
         q.muA = bp.get<float>(R); q.rsA = bp.get<float>(R); q.muB = bp.get<float>(R); q.rsB = bp.get<float>(R);
     }
     if (tr) {
-        w.dH = bp.get<float>(R * dm); w.dQKV = bp.get<float>(R * 3 * dm); w.dY = bp.get<float>(R * Dx);
+        w.dH = bp.get<float>(R * dm); w.dQKV = bp.get<float>(R * 3 * dm); w.dY = bp.get<float>(R * round_up(Dx, 4));
         for (int i = 0; i < 3; i++) { w.dP[i] = bp.get<float>(Bz * eout[i]); w.dG[i] = bp.get<float>(Bz * eout[i]); }
     }
 }
@@ -693,6 +694,7 @@ static void plan_workspace(dof_handle* h, Bump& bp) {
         if (model == DOF_MODEL_VADE) { h->dzm = bp.get<float>(Bz * D); h->dpre = bp.get<float>(Bz * D); }
         h->dz_dec = bp.get<float>(Bz * D);
         h->dloc = bp.get<float>(BT * N * c.F);
+        h->dlocP = (N * c.F) & 3 ? bp.get<float>(BT * round_up(N * c.F, 4)) : nullptr;
         if (!tfm) {
         h->dYD3 = bp.get<float>(BT * 2 * D); h->dCd = bp.get<float>(BT * 2 * D);
         h->dYD2 = bp.get<float>(BT * 4 * D); h->dHD2 = bp.get<float>(BT * 4 * D);
@@ -1247,11 +1249,22 @@ static int gru_layer_backward(const float* state, const GruP& g, int S, int T, i
     return launch_gru_bwd(b, st);
 }
 
+// h->dloc [R, N * F] with its row pitch padded to a multiple of 4 floats (zero columns); h->dloc itself when it already is
+static const float* padded_dloc(dof_handle* h, long long R, cudaStream_t st) {
+    const int Dx = h->cfg.N * h->cfg.F, DxP = round_up(Dx, 4);
+    if (DxP == Dx) return h->dloc;
+    ProfScope ps("pad_cols", st, 0.0, 4.0 * R * (Dx + DxP));
+    pad_cols_kernel<<<cdiv(R * DxP, 256), 256, 0, st>>>(h->dloc, Dx, h->dlocP, DxP, R, Dx);
+    return h->dlocP;
+}
+
 static int rec_decoder_backward(dof_handle* h, const float* state, float* grad, const float* zin, int B, cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
     const int T = c.T, D = c.D, NF = c.N * c.F, M = B * T, sm = h->sm_count;
-    WGradArgs w0 = wgrad_args(mv_plain(h->dloc, NF), mv_plain(h->YD3, 2 * D), grad + L.loc_w, 2 * D, 0, grad + L.loc_b, M, NF, 2 * D);
+    const int NFP = round_up(NF, 4);
+    WGradArgs w0 = wgrad_args(mv_plain(padded_dloc(h, M, st), NFP), mv_plain(h->YD3, 2 * D), grad + L.loc_w, 2 * D, 0, grad + L.loc_b, M, NFP, 2 * D);
+    w0.nv = NF;
     DOF_TRY(launch_gemm_wgrad(&w0, 1, st, sm));
     GemmArgs g0 = gemm_args(mv_plain(h->dloc, NF), state + L.loc_w, 2 * D, 1, nullptr, h->dYD3, 2 * D, M, 2 * D, NF);
     DOF_TRY(launch_gemm_rows(&g0, 1, st));

@@ -248,6 +248,8 @@ struct WGradArgs {
     float* db;                    // [N] or null
     int M, N, K;
     int ks;                       // oT=0: column stride of the output, dW[n*ldo + k*ks] (0 = 1)
+    int nv, kv;                   // only rows n < nv / columns k < kv of dW (and db) are written (0 = all): operands whose row
+                                  // pitch was padded to a multiple of 4 floats with zero columns (N * F = 42 -> 44)
 };
 #define WG_MAXBATCH 5
 struct WGradBatch { WGradArgs g[WG_MAXBATCH]; };
@@ -304,14 +306,15 @@ __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const WGradBatch wb, in
         }
         __syncthreads();
     }
+    const int nvl = g.nv > 0 ? g.nv : g.N, kvl = g.kv > 0 ? g.kv : g.K;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         int n = n0 + ty * 4 + i;
-        if (n >= g.N) continue;
+        if (n >= nvl) continue;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int k = k0 + tx * 4 + j;
-            if (k >= g.K) continue;
+            if (k >= kvl) continue;
             float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + (size_t)k * (g.ks > 0 ? g.ks : 1);
             atomicAdd(o, acc[i][j]);
         }

@@ -800,6 +800,16 @@ __global__ void sum_over_t_kernel(const float* __restrict__ in, float* __restric
     out[i] = s;
 }
 
+// dst [R, ldd] = src [R, W] with the columns W .. ldd-1 set to zero: a row pitch that is a multiple of 4 floats makes the operand
+// eligible for the float4 producers of the tensor-core GEMMs (N * F = 42 -> 44)
+__global__ void pad_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, long long R, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * ldd) return;
+    const long long r = i / ldd;
+    const int c = (int)(i - r * ldd);
+    dst[i] = c < W ? __ldg(src + r * lds + c) : 0.f;
+}
+
 // dst[n][c*5+kk] = src[c][n][kk]   (Conv1d weight [Cout=c, Cin=n, 5] -> transposed-conv operand)
 __global__ void conv_w_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -681,15 +681,16 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
         mbar_wait(bar_done, 0u);
         tc_fence_after();
         const int n = warp * 32 + lane;
+        const int nvl = g.nv > 0 ? g.nv : g.N, kvl = g.kv > 0 ? g.kv : g.K;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         for (int c0 = 0; c0 < geo.KWP; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
-            if (n < g.N) {
+            if (n < nvl) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     int k = c0 + j;
-                    if (k < g.K) {
+                    if (k < kvl) {
                         float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + (size_t)k * (g.ks > 0 ? g.ks : 1);
                         atomicAdd(o, v[j]);
                     } else if (k == g.K && g.db) {

@@ -302,7 +302,8 @@ static int tcn_decoder_backward(dof_handle* h, const float* state, float* grad, 
     const TcnStackWS& w = h->ts[2];
     const int T = c.T, D = c.D, Dx = c.N * c.F, C = L.tstack[2].C, sm = h->sm_count;
     const long long R = (long long)B * T;
-    DOF_TRY(tfm_wgrad(h->dloc, Dx, w.FIN, C, grad + L.loc_w, C, 0, grad + L.loc_b, (int)R, Dx, C, sm, st));
+    const int DxP = round_up(Dx, 4);
+    DOF_TRY(tfm_wgrad(padded_dloc(h, R, st), DxP, w.FIN, C, grad + L.loc_w, C, 0, grad + L.loc_b, (int)R, DxP, C, sm, st, Dx, 0));
     DOF_TRY(tfm_gemm(h->dloc, Dx, state + L.loc_w, C, 1, nullptr, w.GS, C, (int)R, C, Dx, 0, 0, w.FIN, C, st));      // mask: FIN > 0
     const float* dx0 = nullptr;
     DOF_TRY(tcn_stack_backward(h, 2, state, grad, 0, R, pass, false, true, &dx0, st));

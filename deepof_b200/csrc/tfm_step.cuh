@@ -129,16 +129,28 @@ static int tfm_gemm(const float* A, int lda, const float* W, int ldw, int wT, co
 }
 
 // dW[N, K] += P^T Q, db[N] += sum P, chunked so that the tensor-core kernel (N <= 128, K <= 252) takes every piece
+// nv / kv > 0: only the first nv rows / kv columns of dW exist (P / Q carry zero columns up to N / K, a pitch padded to 4 floats)
 static int tfm_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW, int ldo, int oT, float* db, int M, int N, int K, int sm,
-                     cudaStream_t st) {
+                     cudaStream_t st, int nv = 0, int kv = 0) {
     if (M <= 0) return DOF_OK;
-    const int nchunk = N <= 128 ? N : 128, kchunk = K <= 252 ? K : 128;
+    int nchunk = N <= 128 ? N : 128, kchunk = K <= 252 ? K : 128;
+    // the tensor-core kernel prefetches (N/4 + K/4) / 4 float4 column blocks per 8-row group and holds at most 12 of them in its
+    // producers' registers: 128 x 128 pieces do not fit (they fell back to the SIMT kernel: 8.5 ms per cfg5 step), 128 x 64 do
+    auto fits = [](int nn, int kk) { return cdiv(nn >> 2, 4) + cdiv(kk >> 2, 4) <= (TCW_PW * TCW_MAXPRE) / (TCW_BM / 8); };
+    if (!fits(nchunk, kchunk)) {
+        if (kchunk > 64 && fits(nchunk, 64)) kchunk = 64;
+        else if (nchunk > 64 && fits(64, kchunk)) nchunk = 64;
+        else if (nchunk > 64 && kchunk > 64) nchunk = kchunk = 64;
+    }
     std::vector<WGradArgs> v;
     for (int n0 = 0; n0 < N; n0 += nchunk)
         for (int k0 = 0; k0 < K; k0 += kchunk) {
             const int nn = N - n0 < nchunk ? N - n0 : nchunk, kk = K - k0 < kchunk ? K - k0 : kchunk;
             float* o = oT ? dW + (size_t)k0 * ldo + n0 : dW + (size_t)n0 * ldo + k0;
-            v.push_back(wgrad_args(mv_plain(P + n0, ldp), mv_plain(Q + k0, ldq), o, ldo, oT, (db && k0 == 0) ? db + n0 : nullptr, M, nn, kk));
+            WGradArgs wa = wgrad_args(mv_plain(P + n0, ldp), mv_plain(Q + k0, ldq), o, ldo, oT, (db && k0 == 0) ? db + n0 : nullptr, M, nn, kk);
+            if (nv > 0) { wa.nv = nv - n0 < nn ? nv - n0 : nn; if (wa.nv <= 0) continue; }
+            if (kv > 0) { wa.kv = kv - k0 < kk ? kv - k0 : kk; if (wa.kv <= 0) continue; }
+            v.push_back(wa);
         }
     size_t i = 0;
     while (i < v.size()) {                                   // batch runs of equal (N, K)
@@ -495,8 +507,10 @@ static int tfm_decoder_forward(dof_handle* h, const float* state, const float* z
         DOF_TRY(tfm_ew(0, q.Hmid, w.tmpA, q.Hout, drop_site(h, train, TFM_DEC_RATE, mo[3], site0 + 4 * l + 3), R * dm, sm, st));
         Hin = q.Hout;
     }
-    DOF_TRY(tfm_gemm(Hin, dm, state + L.dout_w, dm, 0, state + L.dout_b, w.Y, Dx, (int)R, Dx, dm, 0, 0, nullptr, 0, st));
-    DOF_TRY(tfm_gemm(w.Y, Dx, state + L.loc_w, Dx, 0, state + L.loc_b, h->loc, Dx, (int)R, Dx, Dx, 0, 0, nullptr, 0, st));
+    const int DxP = round_up(Dx, 4);       // pitch of Y / dY: zero pad columns keep their weight gradients on the tensor-core kernel
+    if (train && DxP != Dx) DOF_CUDA(cudaMemsetAsync(w.Y, 0, (size_t)R * DxP * 4, st));
+    DOF_TRY(tfm_gemm(Hin, dm, state + L.dout_w, dm, 0, state + L.dout_b, w.Y, DxP, (int)R, Dx, dm, 0, 0, nullptr, 0, st));
+    DOF_TRY(tfm_gemm(w.Y, DxP, state + L.loc_w, Dx, 0, state + L.loc_b, h->loc, Dx, (int)R, Dx, Dx, 0, 0, nullptr, 0, st));
     return DOF_OK;
 }
 
@@ -510,10 +524,13 @@ static int tfm_decoder_backward(dof_handle* h, const float* state, float* grad, 
     const DropPlan dp = drop_plan(c, L, B, B, pass + 1);
     const unsigned int site0 = 100 + 32 * pass;
     const float* Hlast = w.l[L.dec_layers - 1].Hout;
-    DOF_TRY(tfm_wgrad(h->dloc, Dx, w.Y, Dx, grad + L.loc_w, Dx, 0, grad + L.loc_b, (int)R, Dx, Dx, sm, st));
-    DOF_TRY(tfm_gemm(h->dloc, Dx, state + L.loc_w, Dx, 1, nullptr, w.dY, Dx, (int)R, Dx, Dx, 0, 0, nullptr, 0, st));
-    DOF_TRY(tfm_wgrad(w.dY, Dx, Hlast, dm, grad + L.dout_w, dm, 0, grad + L.dout_b, (int)R, Dx, dm, sm, st));
-    DOF_TRY(tfm_gemm(w.dY, Dx, state + L.dout_w, dm, 1, nullptr, w.dH, dm, (int)R, dm, Dx, 0, 0, nullptr, 0, st));
+    const int DxP = round_up(Dx, 4);
+    const float* dlp = padded_dloc(h, R, st);                       // [R, DxP], zero pad columns
+    if (DxP != Dx) DOF_CUDA(cudaMemsetAsync(w.dY, 0, (size_t)R * DxP * 4, st));
+    DOF_TRY(tfm_wgrad(dlp, DxP, w.Y, DxP, grad + L.loc_w, Dx, 0, grad + L.loc_b, (int)R, DxP, DxP, sm, st, Dx, Dx));
+    DOF_TRY(tfm_gemm(h->dloc, Dx, state + L.loc_w, Dx, 1, nullptr, w.dY, DxP, (int)R, Dx, Dx, 0, 0, nullptr, 0, st));
+    DOF_TRY(tfm_wgrad(w.dY, DxP, Hlast, dm, grad + L.dout_w, dm, 0, grad + L.dout_b, (int)R, DxP, dm, sm, st, Dx, 0));
+    DOF_TRY(tfm_gemm(w.dY, DxP, state + L.dout_w, dm, 1, nullptr, w.dH, dm, (int)R, dm, Dx, 0, 0, nullptr, 0, st));
     for (int l = L.dec_layers - 1; l >= 0; l--) {
         const TfmDecLayerWS& q = w.l[l];
         const TfmLayerP& Q = L.tdl[l];
