@@ -380,7 +380,8 @@ struct TcnStackWS {
     int S, G, Fin;                           // encoder stacks: sequences at max_batch, graph size, features
     int* gidx;
     long long rows;                          // rows at max_batch
-    float* X0;                               // [rows, cin0]
+    int x0_ld;                               // row pitch of X0: cin0 rounded up to a multiple of 4 (zero pad columns)
+    float* X0;                               // [rows, x0_ld]
     TcnBlockWS b[TCN_MAXB];
     float *SKIP, *FIN;                       // skip sum and relu(skip sum): [S, C] (encoder, last step only) or [rows, C]
     float *GS, *DA, *DB, *DX, *DX0;          // backward scratch
@@ -543,7 +544,8 @@ static void plan_tcn_stack(dof_handle* h, Bump& bp, int si, long long rows, long
     const bool tr = h->training != 0;
     const size_t R = (size_t)rows, C = (size_t)P.C;
     w.rows = rows;
-    w.X0 = bp.get<float>(R * P.cin0);
+    w.x0_ld = round_up(P.cin0, 4);
+    w.X0 = bp.get<float>(R * w.x0_ld);
     for (int i = 0; i < P.nb; i++) {
         TcnBlockWS& q = w.b[i];
         if (!tr && i >= 2) { q = w.b[i & 1]; }

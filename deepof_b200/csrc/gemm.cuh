@@ -91,13 +91,15 @@ struct GemmArgs {
     //   wconv = 1 (forward):        n = c_out, k = j * wcin + c_in
     //   wconv = 2 (input gradient): n = c_in,  k = j * C_out + c_out   (C_out = K / wtaps)
     int wconv, wcin, wtaps;
+    int wcpad;                         // wconv = 1: channels per tap of the A operand when its pitch is padded (> wcin; 0 = wcin)
 };
 
 __device__ __forceinline__ float gemm_w_at(const GemmArgs& g, const float* Wp, int n, int k) {
     if (g.wconv == 0) return g.wT == 0 ? __ldg(Wp + (size_t)n * g.ldw + k) : __ldg(Wp + (size_t)k * g.ldw + n);
     if (g.wconv == 1) {
-        const int j = k / g.wcin, ci = k - j * g.wcin;
-        return __ldg(Wp + (size_t)n * g.ldw + ci * g.wtaps + j);
+        const int cp = g.wcpad > 0 ? g.wcpad : g.wcin;
+        const int j = k / cp, ci = k - j * cp;
+        return ci < g.wcin ? __ldg(Wp + (size_t)n * g.ldw + ci * g.wtaps + j) : 0.f;
     }
     const int co_n = g.K / g.wtaps;
     const int j = k / co_n, co = k - j * co_n;
@@ -248,6 +250,8 @@ struct WGradArgs {
     float* db;                    // [N] or null
     int M, N, K;
     int ks;                       // oT=0: column stride of the output, dW[n*ldo + k*ks] (0 = 1)
+    int otaps, ocv;               // Q is an A_TAPS view (K = otaps * cc columns, column = tap * cc + channel) and dW a Conv1d weight
+                                  // [N, ocv, otaps]: dW[n*ldo + channel*otaps + tap] for channel < ocv (0: plain output)
     int nv, kv;                   // only rows n < nv / columns k < kv of dW (and db) are written (0 = all): operands whose row
                                   // pitch was padded to a multiple of 4 floats with zero columns (N * F = 42 -> 44)
 };
@@ -316,6 +320,11 @@ __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const WGradBatch wb, in
             int k = k0 + tx * 4 + j;
             if (k >= kvl) continue;
             float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + (size_t)k * (g.ks > 0 ? g.ks : 1);
+            if (g.otaps > 0) {
+                const int cc = g.K / g.otaps, tj = k / cc, ch = k - tj * cc;
+                if (ch >= g.ocv) continue;
+                o = g.dW + (size_t)n * g.ldo + ch * g.otaps + tj;
+            }
             atomicAdd(o, acc[i][j]);
         }
         if (do_bias) atomicAdd(g.db + n, bsum[i]);

@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
         // ===================== producers =====================
         const int NQ = g.N >> 2, KQ = g.K >> 2;
         const bool psplit = g.P.mode == A_SPLIT;
-        const bool qshift = g.Q.mode == A_TSHIFT;
+        const bool qshift = g.Q.mode == A_TSHIFT, qtaps = g.Q.mode == A_TAPS;
         const int r8 = lane & 7, c4 = lane >> 3;
         const int ntask = geo.ptasks + geo.qtasks;
         // task t: operand (P if t < ptasks), 8-row block mblk = t % (BM/8), 4-float4 column block cb
@@ -619,7 +619,12 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
                                 r[j] = __ldg(reinterpret_cast<const float4*>(g.P.p + (size_t)m * g.P.ld + c));
                             }
                         } else if (cq < KQ) {
-                            if (qshift) {
+                            if (qtaps) {            // all taps of a dilated causal convolution in one operand (see mv_taps)
+                                const int c = cq * 4, tj = c / g.Q.cc, ch = c - tj * g.Q.cc, sh = g.Q.dil * (g.Q.taps - 1 - tj);
+                                const int t2 = m % g.Q.T + sh;
+                                if (t2 >= 0 && t2 < g.Q.T)
+                                    r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (long long)(m + sh) * g.Q.ld + ch));
+                            } else if (qshift) {
                                 int tq = m % g.Q.T, t2 = tq + g.Q.shift;
                                 if (t2 >= 0 && t2 < g.Q.T)
                                     r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (size_t)(m + g.Q.shift) * g.Q.ld + cq * 4));
@@ -692,6 +697,11 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
                     int k = c0 + j;
                     if (k < kvl) {
                         float* o = g.oT ? g.dW + (size_t)k * g.ldo + n : g.dW + (size_t)n * g.ldo + (size_t)k * (g.ks > 0 ? g.ks : 1);
+                        if (g.otaps > 0) {              // Conv1d weight [N, ocv, otaps] from an A_TAPS operand (column = tap * cc + channel)
+                            const int cc = g.K / g.otaps, tj = k / cc, ch = k - tj * cc;
+                            if (ch >= g.ocv) continue;
+                            o = g.dW + (size_t)n * g.ldo + ch * g.otaps + tj;
+                        }
                         atomicAdd(o, v[j]);
                     } else if (k == g.K && g.db) {
                         atomicAdd(g.db + n, v[j]);
@@ -747,7 +757,8 @@ static bool tc_wgrad_eligible(const WGradArgs& g) {
     if (g.M < 4096 || g.N > 128 || g.K + 1 > 256 || g.N < 4 || g.K < 4) return false;
     if ((g.N & 3) || (g.K & 3)) return false;
     if (g.P.mode != A_PLAIN && g.P.mode != A_SPLIT) return false;
-    if (g.Q.mode != A_PLAIN && g.Q.mode != A_TSHIFT) return false;
+    if (g.Q.mode != A_PLAIN && g.Q.mode != A_TSHIFT && g.Q.mode != A_TAPS) return false;
+    if (g.Q.mode == A_TAPS && (g.Q.cc & 3)) return false;
     if ((g.P.ld & 3) || (g.Q.ld & 3) || !aligned16(g.P.p) || !aligned16(g.Q.p)) return false;
     if (g.P.mode == A_SPLIT && ((g.P.split & 3) || (g.P.skip & 3))) return false;
     TcWgradGeom geo;

@@ -251,14 +251,18 @@ __global__ void __launch_bounds__(256) tcn_bn_bwd_apply_kernel(float* __restrict
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
 // Xs[s, t, f] = x[b, gidx[g, t, f]]  (the reference's tf_style reshape of a window), s = b * G + g
-__global__ void tcn_gather_kernel(const float* __restrict__ x, const int* __restrict__ gidx, float* __restrict__ Xs, long long n, int G, int TF) {
+// rows of Xs have pitch ldx >= F (padded to a multiple of 4 floats for the float4 GEMM producers; the pad columns are zeroed by the caller)
+__global__ void tcn_gather_kernel(const float* __restrict__ x, const int* __restrict__ gidx, float* __restrict__ Xs, long long n, int G, int TF,
+                                  int F, int ldx) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long s = i / TF;
     const int rem = (int)(i - s * TF);
     const long long b = s / G;
     const int g = (int)(s - b * G);
-    Xs[i] = __ldg(x + b * (long long)G * TF + gidx[g * TF + rem]);
+    const long long row = i / F;
+    const int f = (int)(i - row * F);
+    Xs[row * ldx + f] = __ldg(x + b * (long long)G * TF + gidx[g * TF + rem]);
 }
 
 // out[b * T + t, :] = in[b, :]

@@ -47,10 +47,11 @@ static void tcn_pick_ksplit(GemmArgs& g) {
 }
 
 // A [R, C] = conv(X [R, cin]) + bias, dilated causal
-static int tcn_conv_fwd(const float* X, int cin, int T, int dil, const float* W, const float* bias, float* A, int C, long long R,
+// (ldx = row pitch of X; when it exceeds cin the pad columns are zero and every tap spans ldx columns of the operand)
+static int tcn_conv_fwd(const float* X, int ldx, int cin, int T, int dil, const float* W, const float* bias, float* A, int C, long long R,
                         cudaStream_t st) {
-    GemmArgs g = gemm_args(mv_taps(X, cin, T, TCN_TAPS, cin, -dil), W, cin * TCN_TAPS, 0, bias, A, C, (int)R, C, TCN_TAPS * cin);
-    g.wconv = 1; g.wcin = cin; g.wtaps = TCN_TAPS;
+    GemmArgs g = gemm_args(mv_taps(X, ldx, T, TCN_TAPS, ldx, -dil), W, cin * TCN_TAPS, 0, bias, A, C, (int)R, C, TCN_TAPS * ldx);
+    g.wconv = 1; g.wcin = cin; g.wtaps = TCN_TAPS; g.wcpad = ldx;
     tcn_pick_ksplit(g);
     return launch_gemm_rows(&g, 1, st);
 }
@@ -66,11 +67,19 @@ static int tcn_conv_dgrad(const float* dA, int C, int T, int dil, const float* W
 }
 
 // dW [C, cin, 4] += sum_rows dA[(s, t), :]^T X[(s, t - (3 - j) dil), :];  db += sum_rows dA
-static int tcn_conv_wgrad(const float* dA, int C, const float* X, int cin, int T, int dil, float* dW, float* db, long long R, int sm,
+static int tcn_conv_wgrad(const float* dA, int C, const float* X, int ldx, int cin, int T, int dil, float* dW, float* db, long long R, int sm,
                           cudaStream_t st) {
+    // all four taps in ONE weight-gradient GEMM when K = 4 * cin fits the tensor-core kernel: Q = the A_TAPS view of X (dA is read
+    // once instead of once per tap), the epilogue scatters column (tap, channel) to the Conv1d layout [C, cin, 4]
+    static const bool fused = !(getenv("DOF_TCN_WGRAD_FUSED") && getenv("DOF_TCN_WGRAD_FUSED")[0] == '0');
+    if (fused && (ldx & 3) == 0) {
+        WGradArgs f = wgrad_args(mv_plain(dA, C), mv_taps(X, ldx, T, TCN_TAPS, ldx, -dil), dW, cin * TCN_TAPS, 0, db, (int)R, C, TCN_TAPS * ldx);
+        f.otaps = TCN_TAPS; f.ocv = cin;
+        if (tc_enabled() && tc_wgrad_eligible(f)) return launch_gemm_wgrad_tc(&f, 1, st, sm);
+    }
     WGradArgs w[TCN_TAPS];
     for (int j = 0; j < TCN_TAPS; j++) {
-        w[j] = wgrad_args(mv_plain(dA, C), mv_tshift(X, cin, T, -(TCN_TAPS - 1 - j) * dil), dW + j, cin * TCN_TAPS, 0,
+        w[j] = wgrad_args(mv_plain(dA, C), mv_tshift(X, ldx, T, -(TCN_TAPS - 1 - j) * dil), dW + j, cin * TCN_TAPS, 0,
                           j == TCN_TAPS - 1 ? db : nullptr, (int)R, C, cin);
         w[j].ks = TCN_TAPS;
     }
@@ -101,20 +110,21 @@ static int tcn_stack_forward(dof_handle* h, int si, const float* state, long lon
     for (int i = 0; i < P.nb; i++) {
         const TcnBlockP& B = P.blk[i];
         const TcnBlockWS& q = w.b[i];
-        const float* Xin = (i == 0 ? w.X0 : w.b[i - 1].OUT) + r0 * B.cin;
+        const int ldx = i == 0 ? w.x0_ld : C;
+        const float* Xin = (i == 0 ? w.X0 : w.b[i - 1].OUT) + r0 * ldx;
         float *A1 = q.A1 + r0 * C, *Y1 = q.Y1 + r0 * C, *A2 = q.A2 + r0 * C;
-        DOF_TRY(tcn_conv_fwd(Xin, B.cin, T, B.dil, state + B.c1w, state + B.c1b, A1, C, R, st));
+        DOF_TRY(tcn_conv_fwd(Xin, ldx, B.cin, T, B.dil, state + B.c1w, state + B.c1b, A1, C, R, st));
         const TcnBn bn1 = tcn_bn_ref(h, state, B.bn1, train, pass, q.st1, R);
         if (train) DOF_TRY(tcn_stats(A1, R, C, const_cast<double*>(bn1.stat), sm, st));
         { ProfScope ps("tcn_bnrelu", st, 0.0, 8.0 * R * C);
         tcn_bnrelu_kernel<<<tcn_ew_grid(R, C, sm, 8), 256, 0, st>>>(A1, Y1, R, C, bn1); }
         DOF_LAUNCH_CHECK();
-        DOF_TRY(tcn_conv_fwd(Y1, C, T, B.dil, state + B.c2w, state + B.c2b, A2, C, R, st));
+        DOF_TRY(tcn_conv_fwd(Y1, C, C, T, B.dil, state + B.c2w, state + B.c2b, A2, C, R, st));
         const TcnBn bn2 = tcn_bn_ref(h, state, B.bn2, train, pass, q.st2, R);
         if (train) DOF_TRY(tcn_stats(A2, R, C, const_cast<double*>(bn2.stat), sm, st));
         const float* res = Xin;
         if (B.has_ds) {                                   // 1x1 residual projection (:418, :442)
-            GemmArgs g = gemm_args(mv_plain(Xin, B.cin), state + B.dsw, B.cin, 0, state + B.dsb, q.RES + r0 * C, C, (int)R, C, B.cin);
+            GemmArgs g = gemm_args(mv_plain(Xin, ldx), state + B.dsw, B.cin, 0, state + B.dsb, q.RES + r0 * C, C, (int)R, C, B.cin);
             DOF_TRY(launch_gemm_rows(&g, 1, st));
             res = q.RES + r0 * C;
         }
@@ -146,7 +156,8 @@ static int tcn_stack_backward(dof_handle* h, int si, const float* state, float* 
     for (int i = P.nb - 1; i >= 0; i--) {
         const TcnBlockP& B = P.blk[i];
         const TcnBlockWS& q = w.b[i];
-        const float* Xin = (i == 0 ? w.X0 : w.b[i - 1].OUT) + r0 * B.cin;
+        const int ldx = i == 0 ? w.x0_ld : C;
+        const float* Xin = (i == 0 ? w.X0 : w.b[i - 1].OUT) + r0 * ldx;
         const float *A1 = q.A1 + r0 * C, *Y1 = q.Y1 + r0 * C, *A2 = q.A2 + r0 * C;
         const bool last = i == P.nb - 1;
         const TcnBn bn1 = tcn_bn_ref(h, state, B.bn1, true, pass, q.st1, R), bn2 = tcn_bn_ref(h, state, B.bn2, true, pass, q.st2, R);
@@ -162,7 +173,7 @@ static int tcn_stack_backward(dof_handle* h, int si, const float* state, float* 
         { ProfScope ps("tcn_bn_bwd_apply", st, 0.0, 12.0 * R * C);
         tcn_bn_bwd_apply_kernel<<<tcn_ew_grid(R, C, sm, 8), 256, 0, st>>>(DA, A2, R, C, bn2, bs2, grad + B.bn2.w, grad + B.bn2.b); }
         DOF_LAUNCH_CHECK();
-        DOF_TRY(tcn_conv_wgrad(DA, C, Y1, C, T, B.dil, grad + B.c2w, grad + B.c2b, R, sm, st));
+        DOF_TRY(tcn_conv_wgrad(DA, C, Y1, C, C, T, B.dil, grad + B.c2w, grad + B.c2b, R, sm, st));
         DOF_TRY(tcn_conv_dgrad(DA, C, T, B.dil, state + B.c2w, C, DB, R, 0, Y1, st));     // mask: relu(bn1(A1)) > 0
         a.mode = 1; a.D = DB; a.A = A1; a.bstat = bs1; a.bn = bn1; a.dOUT = a.OUT = a.GS = nullptr; a.DS = nullptr;
         { ProfScope ps("tcn_bwd_reduce", st, 0.0, 8.0 * R * C);
@@ -171,9 +182,10 @@ static int tcn_stack_backward(dof_handle* h, int si, const float* state, float* 
         { ProfScope ps("tcn_bn_bwd_apply", st, 0.0, 12.0 * R * C);
         tcn_bn_bwd_apply_kernel<<<tcn_ew_grid(R, C, sm, 8), 256, 0, st>>>(DB, A1, R, C, bn1, bs1, grad + B.bn1.w, grad + B.bn1.b); }
         DOF_LAUNCH_CHECK();
-        DOF_TRY(tcn_conv_wgrad(DB, C, Xin, B.cin, T, B.dil, grad + B.c1w, grad + B.c1b, R, sm, st));
+        DOF_TRY(tcn_conv_wgrad(DB, C, Xin, ldx, B.cin, T, B.dil, grad + B.c1w, grad + B.c1b, R, sm, st));
         if (B.has_ds) {
-            WGradArgs wd = wgrad_args(mv_plain(DX, C), mv_plain(Xin, B.cin), grad + B.dsw, B.cin, 0, grad + B.dsb, (int)R, C, B.cin);
+            WGradArgs wd = wgrad_args(mv_plain(DX, C), mv_plain(Xin, ldx), grad + B.dsw, B.cin, 0, grad + B.dsb, (int)R, C, ldx);
+            wd.kv = B.cin;
             DOF_TRY(launch_gemm_wgrad(&wd, 1, st, sm));
         }
         if (i > 0 || need_dx0) {
@@ -200,8 +212,9 @@ static int tcn_core_forward(dof_handle* h, int b, const float* state, const floa
     const TcnStackWS& w = h->ts[b];
     const int T = c.T, TF = T * w.Fin;
     const long long S = (long long)Bw * w.G, n = S * TF;
+    if (w.x0_ld != w.Fin) DOF_CUDA(cudaMemsetAsync(w.X0, 0, (size_t)S * T * w.x0_ld * 4, st));
     { ProfScope ps("tcn_gather", st, 0.0, 8.0 * n);
-    tcn_gather_kernel<<<cdiv(n, 256), 256, 0, st>>>(xin, w.gidx, w.X0, n, w.G, TF); }
+    tcn_gather_kernel<<<cdiv(n, 256), 256, 0, st>>>(xin, w.gidx, w.X0, n, w.G, TF, w.Fin, w.x0_ld); }
     DOF_LAUNCH_CHECK();
     const long long Rg = S / groups * T;
     for (int g = 0; g < groups; g++) DOF_TRY(tcn_stack_forward(h, b, state, g * Rg, Rg, train, g, true, st));
