@@ -601,6 +601,13 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
         const int ntask = geo.ptasks + geo.qtasks;
         // task t: operand (P if t < ptasks), 8-row block mblk = t % (BM/8), 4-float4 column block cb
         float4 pre[2][TCW_MAXPRE];
+        // scalars of the operand description in registers (g is an indexed element of the by-value argument: every access is
+        // an LDC); step index and tap of a time-shifted Q item by multiply-high with precomputed reciprocals instead of the
+        // ~20-instruction runtime division (exact for m < 2^32 / T and c < 2^32 / cc — rows are int, T and cc are small)
+        // (only the two reciprocals live in registers: the kernel sits at its register budget for two CTAs per SM — keeping the
+        // whole operand description in registers spilled and cost the plain weight gradients of the transformer 65 %)
+        const uint32_t magic_T = g.Q.T > 0 ? (uint32_t)((0x100000000ull + (uint32_t)g.Q.T - 1) / (uint32_t)g.Q.T) : 0u;
+        const uint32_t magic_c = g.Q.cc > 0 ? (uint32_t)((0x100000000ull + (uint32_t)g.Q.cc - 1) / (uint32_t)g.Q.cc) : 0u;
         auto load_regs = [&](float4 (&r)[TCW_MAXPRE], int mb0) {
 #pragma unroll
             for (int j = 0; j < TCW_MAXPRE; j++) {
@@ -620,14 +627,14 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
                             }
                         } else if (cq < KQ) {
                             if (qtaps) {            // all taps of a dilated causal convolution in one operand (see mv_taps)
-                                const int c = cq * 4, tj = c / g.Q.cc, ch = c - tj * g.Q.cc, sh = g.Q.dil * (g.Q.taps - 1 - tj);
-                                const int t2 = m % g.Q.T + sh;
+                                const int c = cq * 4, tj = (int)__umulhi((uint32_t)c, magic_c), ch = c - tj * g.Q.cc, sh = g.Q.dil * (g.Q.taps - 1 - tj);
+                                const int t2 = m - (int)__umulhi((uint32_t)m, magic_T) * g.Q.T + sh;
                                 if (t2 >= 0 && t2 < g.Q.T)
                                     r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (long long)(m + sh) * g.Q.ld + ch));
                             } else if (qshift) {
-                                int tq = m % g.Q.T, t2 = tq + g.Q.shift;
+                                const int t2 = m - (int)__umulhi((uint32_t)m, magic_T) * g.Q.T + g.Q.shift;
                                 if (t2 >= 0 && t2 < g.Q.T)
-                                    r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (size_t)(m + g.Q.shift) * g.Q.ld + cq * 4));
+                                    r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (long long)(m + g.Q.shift) * g.Q.ld + cq * 4));
                             } else {
                                 r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (size_t)m * g.Q.ld + cq * 4));
                             }
@@ -759,6 +766,8 @@ static bool tc_wgrad_eligible(const WGradArgs& g) {
     if (g.P.mode != A_PLAIN && g.P.mode != A_SPLIT) return false;
     if (g.Q.mode != A_PLAIN && g.Q.mode != A_TSHIFT && g.Q.mode != A_TAPS) return false;
     if (g.Q.mode == A_TAPS && (g.Q.cc & 3)) return false;
+    // the producers divide by T with a multiply-high reciprocal: exact while M * T < 2^32
+    if ((g.Q.mode == A_TAPS || g.Q.mode == A_TSHIFT) && (g.Q.T < 1 || (long long)g.M * g.Q.T >= (1ll << 32))) return false;
     if ((g.P.ld & 3) || (g.Q.ld & 3) || !aligned16(g.P.p) || !aligned16(g.Q.p)) return false;
     if (g.P.mode == A_SPLIT && ((g.P.split & 3) || (g.P.skip & 3))) return false;
     TcWgradGeom geo;
