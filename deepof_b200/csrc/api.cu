@@ -1095,8 +1095,15 @@ static int rec_decoder_forward(dof_handle* h, const float* state, const float* z
     DOF_TRY(gru_layer_forward(state, L.dg2, h->YD1, (long long)T * 2 * D, 2 * D, 2 * D, 2 * D, B, T, h->lenD, h->HD2,
                               train ? h->GtD2 : nullptr, nullptr, h->GiD2, st));
     DOF_TRY(ln_fwd(h->HD2, state + L.dn2w, state + L.dn2b, h->YD2, h->muD2, h->rsD2, M, 4 * D, h->sm_count, st));
-    GemmArgs gc = gemm_args(mv_conv5(h->YD2, 4 * D, T, +1), state + L.dconv, 20 * D, 0, nullptr, h->Cd, 2 * D, M, 2 * D, 20 * D);
-    gc.relu = 1;
+    // Conv1d(k = 5, "same") + ReLU: on the tensor-core kernel as a 5-tap A_TAPS operand staged one tap (4 D columns) per K block,
+    // the torch weight [2D, 4D, 5] addressed in place; the im2col view on the SIMT kernel for shapes that kernel does not take
+    GemmArgs gc = gemm_args(mv_taps(h->YD2, 4 * D, T, 5, 4 * D, -1, +2), state + L.dconv, 20 * D, 0, nullptr, h->Cd, 2 * D, M, 2 * D, 20 * D);
+    gc.relu = 1; gc.wconv = 1; gc.wcin = 4 * D; gc.wtaps = 5; gc.ksplit = 5;
+    static const bool conv_tc = !(getenv("DOF_DEC_CONV_TC") && getenv("DOF_DEC_CONV_TC")[0] == '0');
+    if (!(conv_tc && tc_enabled() && tc_rows_eligible(gc))) {
+        gc = gemm_args(mv_conv5(h->YD2, 4 * D, T, +1), state + L.dconv, 20 * D, 0, nullptr, h->Cd, 2 * D, M, 2 * D, 20 * D);
+        gc.relu = 1;
+    }
     DOF_TRY(launch_gemm_rows(&gc, 1, st));
     DOF_TRY(ln_fwd(h->Cd, state + L.dn3w, state + L.dn3b, h->YD3, h->muD3, h->rsD3, M, 2 * D, h->sm_count, st));
     GemmArgs gl = gemm_args(mv_plain(h->YD3, 2 * D), state + L.loc_w, 2 * D, 0, state + L.loc_b, h->loc, NF, M, NF, 2 * D);
@@ -1287,10 +1294,16 @@ static int rec_decoder_backward(dof_handle* h, const float* state, float* grad, 
         WGradArgs w1 = wgrad_args(mv_plain(h->dCd, 2 * D), mv_conv5(h->YD2, 4 * D, T, +1), grad + L.dconv, 20 * D, 0, nullptr, M, 2 * D, 20 * D);
         DOF_TRY(launch_gemm_wgrad(&w1, 1, st, sm));
     }
-    { ProfScope ps("conv_w_transpose", st);
-    conv_w_transpose_kernel<<<cdiv(2 * D * 4 * D * 5, 256), 256, 0, st>>>(state + L.dconv, h->Wt, 2 * D, 4 * D); }
-    DOF_LAUNCH_CHECK();
-    GemmArgs g1 = gemm_args(mv_conv5(h->dCd, 2 * D, T, -1), h->Wt, 10 * D, 0, nullptr, h->dYD2, 4 * D, M, 4 * D, 10 * D);
+    // input gradient of the Conv1d: the same 5-tap operand over dCd with the taps mirrored (row t + 2 - j), weight addressed in place
+    GemmArgs g1 = gemm_args(mv_taps(h->dCd, 2 * D, T, 5, 2 * D, +1, -2), state + L.dconv, 20 * D, 0, nullptr, h->dYD2, 4 * D, M, 4 * D, 10 * D);
+    g1.wconv = 2; g1.wcin = 4 * D; g1.wtaps = 5; g1.ksplit = 5;
+    static const bool conv_tc = !(getenv("DOF_DEC_CONV_TC") && getenv("DOF_DEC_CONV_TC")[0] == '0');
+    if (!(conv_tc && tc_enabled() && tc_rows_eligible(g1))) {
+        { ProfScope ps("conv_w_transpose", st);
+        conv_w_transpose_kernel<<<cdiv(2 * D * 4 * D * 5, 256), 256, 0, st>>>(state + L.dconv, h->Wt, 2 * D, 4 * D); }
+        DOF_LAUNCH_CHECK();
+        g1 = gemm_args(mv_conv5(h->dCd, 2 * D, T, -1), h->Wt, 10 * D, 0, nullptr, h->dYD2, 4 * D, M, 4 * D, 10 * D);
+    }
     DOF_TRY(launch_gemm_rows(&g1, 1, st));
     DOF_TRY(ln_bwd(h->dYD2, h->HD2, h->muD2, h->rsD2, state + L.dn2w, h->dHD2, grad + L.dn2w, grad + L.dn2b, M, 4 * D, 0, sm, st));
     bool dxd = false;

@@ -23,6 +23,7 @@ struct MatView {
     // A_TAPS (dilated causal Conv1d as a GEMM, TCN family): column j*cc + c reads channel c of row
     // (seq, t + dil*(taps-1-j)), zero outside [0,T).  dil = -dilation: the convolution; dil = +dilation: its input gradient
     int taps, cc, dil;
+    int off;          // A_TAPS: added to every tap's row shift (a "same"-padded Conv1d(k=5): dil = -1, off = +2)
 };
 
 static inline MatView mv_plain(const float* p, int ld) {
@@ -37,8 +38,8 @@ static inline MatView mv_conv5(const float* p, int ld, int T, int sgn) {
 static inline MatView mv_tshift(const float* p, int ld, int T, int shift) {
     MatView v = mv_plain(p, ld); v.mode = A_TSHIFT; v.T = T; v.shift = shift; return v;
 }
-static inline MatView mv_taps(const float* p, int ld, int T, int taps, int cc, int dil) {
-    MatView v = mv_plain(p, ld); v.mode = A_TAPS; v.T = T; v.taps = taps; v.cc = cc; v.dil = dil; return v;
+static inline MatView mv_taps(const float* p, int ld, int T, int taps, int cc, int dil, int off = 0) {
+    MatView v = mv_plain(p, ld); v.mode = A_TAPS; v.T = T; v.taps = taps; v.cc = cc; v.dil = dil; v.off = off; return v;
 }
 
 __device__ __forceinline__ float mv_load(const MatView& a, int m, int k) {
@@ -59,7 +60,7 @@ __device__ __forceinline__ float mv_load(const MatView& a, int m, int k) {
         case A_TAPS: {
             int j = k / a.cc, c = k - j * a.cc;
             int t = m % a.T;
-            int sh = a.dil * (a.taps - 1 - j);
+            int sh = a.dil * (a.taps - 1 - j) + a.off;
             if (t + sh < 0 || t + sh >= a.T) return 0.f;
             return __ldg(a.p + (size_t)(m + sh) * a.ld + c);
         }

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(PW * 32 + 160) gemm_rows_tc_kernel(const GemmB
         // the operand description in registers: `g` is an element of a by-value kernel argument selected by blockIdx.z, every
         // access to it is an indexed constant load (LDC) — 880 of them per tile in the K = 128 convolution before this
         const float* const ap0 = g.A.p; const float* const ap1 = g.nkb == 2 ? g.A2.p : g.A.p;
-        const int a_ld = g.A.ld, a_T = g.A.T, a_cc = g.A.cc, a_dil = g.A.dil, a_taps = g.A.taps, a_split = g.A.split, a_skip = g.A.skip;
+        const int a_ld = g.A.ld, a_T = g.A.T, a_cc = g.A.cc, a_dil = g.A.dil, a_taps = g.A.taps, a_off = g.A.off, a_split = g.A.split, a_skip = g.A.skip;
         const int gM = g.M, n_grid = gridDim.x, bx = blockIdx.x;
         auto load_regs = [&](float4 (&r)[KQM], int w) {
             const int tile = bx + (w / nkb) * n_grid;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(PW * 32 + 160) gemm_rows_tc_kernel(const GemmB
             int t = taps ? (m0 + row) % a_T : 0, ch = 0, sh = 0;
             if (taps && kstep == 0) {           // KQ divides 128: this thread's column (tap, channel) never changes
                 const int c0 = kq * 4 + k0, tj = c0 / a_cc;
-                ch = c0 - tj * a_cc; sh = a_dil * (a_taps - 1 - tj);
+                ch = c0 - tj * a_cc; sh = a_dil * (a_taps - 1 - tj) + a_off;
             }
 #pragma unroll
             for (int j = 0; j < KQM; j++) {
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(PW * 32 + 160) gemm_rows_tc_kernel(const GemmB
                     if (taps) {                 // dilated causal convolution: column block tj reads the row `sh` steps away
                         if (kstep != 0) {
                             const int tj = c / a_cc;
-                            ch = c - tj * a_cc; sh = a_dil * (a_taps - 1 - tj);
+                            ch = c - tj * a_cc; sh = a_dil * (a_taps - 1 - tj) + a_off;
                         }
                         ok = ok && (unsigned)(t + sh) < (unsigned)a_T;
                         ptr = ap + (long long)(m + sh) * a_ld + ch;
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 2) gemm_wgrad_tc_kernel(const WGr
                             }
                         } else if (cq < KQ) {
                             if (qtaps) {            // all taps of a dilated causal convolution in one operand (see mv_taps)
-                                const int c = cq * 4, tj = (int)__umulhi((uint32_t)c, magic_c), ch = c - tj * g.Q.cc, sh = g.Q.dil * (g.Q.taps - 1 - tj);
+                                const int c = cq * 4, tj = (int)__umulhi((uint32_t)c, magic_c), ch = c - tj * g.Q.cc, sh = g.Q.dil * (g.Q.taps - 1 - tj) + g.Q.off;
                                 const int t2 = m - (int)__umulhi((uint32_t)m, magic_T) * g.Q.T + sh;
                                 if (t2 >= 0 && t2 < g.Q.T)
                                     r[j] = __ldg(reinterpret_cast<const float4*>(g.Q.p + (long long)(m + sh) * g.Q.ld + ch));
