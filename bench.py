@@ -416,7 +416,7 @@ def run_workload(c, steps, warmup, world, rank, local, dev, sample_clocks=True, 
             except Exception:
                 pass
             top = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
-            roof = roofline_for(top, kernels[top], peaks)
+            roof = roofline_for(top, kernels[top], peaks, wl="tcn" if enc == "TCN" else None)
             sustained = peaks.get("bf16_tflops_sustained", 1400.0)
             roof["step_useful_tflops"] = c["flops"] * B / (ms / 1e3) / 1e12
             roof["step_tensor_frac"] = roof["step_useful_tflops"] / sustained
@@ -514,7 +514,7 @@ def main():
 TENSOR_CLASSES = ("gru_", "gemm_", "tfm_attn", "ntxent")   # step GEMMs (GRU, attention, FFN, Linear, conv-as-GEMM), NT-Xent
 
 
-def roofline_for(name, k, peaks):
+def roofline_for(name, k, peaks, wl=None):
     """Roofline of the dominant kernel class on the roof SURVEY 8(d) assigns to its row: the tensor pipe (useful
     FLOPs / sustained dense bf16 peak) for the GEMM-class kernels — fused GRU layers, tall-skinny GEMMs, attention —
     and HBM bandwidth for everything else.  FLOPs and bytes are ALGORITHMIC (unpadded), counted by the library at launch
@@ -529,8 +529,9 @@ def roofline_for(name, k, peaks):
     traffic, tnote = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if name in tj:
-            traffic, tnote = tj[name]["dram_bytes_per_launch"], tj[name]["note"]
+        key = f"{wl}:{name}" if wl and f"{wl}:{name}" in tj else name        # workload-specific capture of the class's dominant launch
+        if key in tj:
+            traffic, tnote = tj[key]["dram_bytes_per_launch"], tj[key]["note"]
     except Exception:
         pass
     common = {"kernel": name, "traffic": traffic, "traffic_note": tnote, "launch_ms": k["ms_per_step"] / n,
