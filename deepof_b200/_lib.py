@@ -164,6 +164,7 @@ _SIGS = {
     "dof_test_gru_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "dof_test_layernorm": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, C.c_longlong, C.c_int,
                                      C.c_int, _P]),
+    "dof_test_tcn_conv": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_longlong, _P, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS.keys())
 

@@ -2603,6 +2603,26 @@ int dof_test_tfm_attention(const float* qkv, const unsigned char* kpad, const un
     return tfm_attention(qkv, kpad, drop, causal, S, T, dm, heads, 0, out, dout, dqkv, (cudaStream_t)stream);
 }
 
+int dof_test_tcn_conv(int mode, const float* X, int ldx, int cin, int T, int dilation, const float* W, const float* bias, float* A,
+                      int C, long long R, float* dX, float* dW, float* db, void* stream) {
+    if (!X || !W || !A || ldx < cin || cin < 1 || T < 1 || dilation < 1 || C < 1 || R < 1 || R % T) DOF_FAIL(DOF_ERR_ARG, "bad convolution arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    g_sm_count = sm;
+    if (mode == 0) return tcn_conv_fwd(X, ldx, cin, T, dilation, W, bias, A, C, R, st);
+    if (mode == 1) {
+        if (!dX || ldx != cin) DOF_FAIL(DOF_ERR_ARG, "input gradient: dX required, ldx == cin");
+        return tcn_conv_dgrad(A, C, T, dilation, W, cin, dX, R, 0, nullptr, st);
+    }
+    if (mode == 2) {
+        if (!dW) DOF_FAIL(DOF_ERR_ARG, "weight gradient: dW required");
+        return tcn_conv_wgrad(A, C, X, ldx, cin, T, dilation, dW, db, R, sm, st);
+    }
+    DOF_FAIL(DOF_ERR_ARG, "mode %d", mode);
+}
+
 int dof_test_gru_wgrad(const float* dg_f, const float* dg_b, const float* x, int ldx, const float* hout, float* out, int M, int T,
                        int I, int H, void* stream) {
     if (!gru_wgrad_tc_eligible(M, H, I, ldx, dg_f, dg_b, x, hout))

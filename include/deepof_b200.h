@@ -464,6 +464,14 @@ int dof_test_layernorm(const float* x, const float* w, const float* b, float eps
                        float* rstd, const float* dy, float* dx, float* dw, float* db, long long R, int W,
                        int relu_in, void* stream);
 
+/* test hook: one dilated causal Conv1d(k = 4) of a TemporalBlockPT (models_new.py:408-437) as the library runs it — rows are
+ * (sequence, step) pairs, X [R, ldx] (ldx >= cin, pad columns zero), W the torch weight [C, cin, 4], T steps per sequence.
+ *   mode 0: A [R, C] = conv(X) + bias                       (tensor-core kernel when R >= 2048 and ldx % 4 == 0)
+ *   mode 1: dX [R, cin] = conv^T(A)   (A holds d(loss)/d(conv output); requires ldx == cin, cin % 4 == 0 for the fast path)
+ *   mode 2: dW [C, cin, 4] += A^T (taps of X), db [C] += sum A   (one fused tensor-core GEMM when R >= 4096) */
+int dof_test_tcn_conv(int mode, const float* X, int ldx, int cin, int T, int dilation, const float* W, const float* bias, float* A,
+                      int C, long long R, float* dX, float* dW, float* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -558,3 +558,33 @@ def test_tfm_attention_train_forward_backward(L, S_, T, dm, heads, causal, pad, 
     ref.backward(dout.double())
     assert rel(out, ref.detach()) < 2e-6
     assert rel(dqkv, x.grad) < 5e-6
+
+
+@pytest.mark.parametrize("S_,T,cin,C,dil", [(180, 25, 32, 32, 1), (180, 25, 32, 32, 8), (170, 25, 3, 32, 2), (170, 25, 1, 32, 4),
+                                            (200, 25, 64, 64, 4), (176, 24, 24, 64, 8), (40, 12, 32, 32, 2), (7, 5, 8, 16, 1)])
+def test_tcn_dilated_causal_conv_vs_torch(L, S_, T, cin, C, dil):
+    """The TCN family's Conv1d(k = 4, causal, dilated) as the library runs it — a GEMM over an A_TAPS view of [rows, channels]
+    activations, its input gradient and its fused-tap weight gradient — against torch.nn.functional.conv1d + autograd in fp64.
+    Sizes with >= 2048 / 4096 rows take the tcgen05 kernels (incl. the 3 / 1-channel inputs padded to pitch 4 and the K = 256
+    decoder shape staged in 32-column blocks), the small ones the SIMT kernels.  3xTF32: 1e-5 rel-L2."""
+    R = S_ * T
+    ldx = (cin + 3) // 4 * 4
+    x = rnd(S_, T, cin, seed=1)
+    X = torch.zeros(R, ldx, device="cuda")
+    X[:, :cin] = x.reshape(R, cin)
+    W, b = rnd(C, cin, 4, seed=2) * 0.2, rnd(C, seed=3)
+    dA = rnd(S_, T, C, seed=4)
+    xd, Wd, bd = x.double().requires_grad_(True), W.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.nn.functional.conv1d(torch.nn.functional.pad(xd.transpose(1, 2), (3 * dil, 0)), Wd, bd, dilation=dil).transpose(1, 2)
+    (ref * dA.double()).sum().backward()
+    A = torch.zeros(R, C, device="cuda")
+    assert L.dof_test_tcn_conv(0, P(X), ldx, cin, T, dil, P(W), P(b), P(A), C, R, None, None, None, S()) == 0, L.dof_last_error()
+    assert rel(A, ref.reshape(R, C)) < 1e-5
+    dAf = dA.reshape(R, C).contiguous()
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    assert L.dof_test_tcn_conv(2, P(X), ldx, cin, T, dil, P(W), None, P(dAf), C, R, None, P(dW), P(db), S()) == 0, L.dof_last_error()
+    assert rel(dW, Wd.grad) < 1e-5 and rel(db, bd.grad) < 1e-5
+    if ldx == cin:
+        dX = torch.zeros(R, cin, device="cuda")
+        assert L.dof_test_tcn_conv(1, P(X), ldx, cin, T, dil, P(W), None, P(dAf), C, R, P(dX), None, None, S()) == 0, L.dof_last_error()
+        assert rel(dX, xd.grad.reshape(R, cin)) < 1e-5
