@@ -457,7 +457,7 @@ static void plan_workspace_head(dof_handle* h, Bump& bp);
 static void plan_workspace_tfm_encoder(dof_handle* h, Bump& bp) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
-    const int B = h->max_batch, T = c.T, D = c.D, dk = L.dk, dff = L.dff;
+    const int B = h->max_batch, T = c.T, dk = L.dk, dff = L.dff;
     const bool tr = h->training != 0;
     h->pe_enc = bp.get<float>((size_t)T * dk);
     for (int b = 0; b < 2; b++) {

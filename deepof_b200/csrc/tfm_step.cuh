@@ -355,7 +355,6 @@ static int tfm_encoder_forward(dof_handle* h, const float* state, const float* x
                                cudaStream_t st) {
     const dof_config& c = h->cfg;
     const Layout& L = h->L;
-    const int N = c.N, E = c.E, D = c.D, dk = L.dk, KD = (N + E) * D;
     if (groups < 1 || Bw % groups) DOF_FAIL(DOF_ERR_ARG, "batch %d is not a multiple of %d statistics groups", Bw, groups);
     if (train && Bw / groups < 2) DOF_FAIL(DOF_ERR_UNSUPPORTED, "train-mode BatchNorm needs at least 2 windows per pass");
     const DropPlan dp = drop_plan(c, L, Bw, 0, 0);
