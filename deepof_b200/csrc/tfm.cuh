@@ -534,16 +534,25 @@ __global__ void __launch_bounds__(256) tfm_attn2_kernel(const TfmAttnArgs a) {
     float* sdS = sP + (BWD ? (size_t)HT * (T + 1) : 0);  // BWD: [H][T][T + 1]
     const int nz = (BWD ? 4 : 3) * HT * HDP;
     if (hd < HDP) { for (int i = tid; i < nz; i += nthr) a2sm[i] = 0.f; __syncthreads(); }
+    // staging: a thread owns COLUMNS of the [T, 3 dm] block (its head / offset decomposition is computed once, not per element —
+    // the per-element version spent five integer divisions on every one of the 3000 floats of a cfg3 sequence); for a fixed step
+    // consecutive threads read consecutive floats
     const float* src = a.qkv + (size_t)s * T * 3 * dm;
-    for (int i = tid; i < T * 3 * dm; i += nthr) {
-        const int t = i / (3 * dm), c = i - t * 3 * dm, m = c / dm, cc = c - m * dm, h = cc / hd, d = cc - h * hd;
-        (m == 0 ? sQ : m == 1 ? sK : sV)[((size_t)h * T + t) * HDP + d] = __ldg(src + i);
+    for (int c = tid; c < 3 * dm; c += nthr) {
+        const int m = c / dm, cc = c - m * dm, h = cc / hd, d = cc - h * hd;
+        float* dst = (m == 0 ? sQ : m == 1 ? sK : sV) + (size_t)h * T * HDP + d;
+        const float* sp = src + c;
+#pragma unroll 5
+        for (int t = 0; t < T; t++) dst[t * HDP] = __ldg(sp + (size_t)t * 3 * dm);
     }
     if (BWD) {
         const float* dsrc = a.dout + (size_t)s * T * dm;
-        for (int i = tid; i < T * dm; i += nthr) {
-            const int t = i / dm, cc = i - t * dm, h = cc / hd, d = cc - h * hd;
-            sdO[((size_t)h * T + t) * HDP + d] = __ldg(dsrc + i);
+        for (int c = tid; c < dm; c += nthr) {
+            const int h = c / hd, d = c - h * hd;
+            float* dst = sdO + (size_t)h * T * HDP + d;
+            const float* sp = dsrc + c;
+#pragma unroll 5
+            for (int t = 0; t < T; t++) dst[t * HDP] = __ldg(sp + (size_t)t * dm);
         }
     }
     __syncthreads();
