@@ -380,11 +380,16 @@ __global__ void __launch_bounds__(128) tfm_attn_train_kernel(const TfmAttnArgs a
     float* sdo = sq + (size_t)T * ldq;         // BWD: dOut [T][dm + 1]
     float* sdq = sdo + (BWD ? (size_t)T * (dm + 1) : 0);   // BWD: dqkv accumulator [T][3dm + 1]
     const float* src = a.qkv + (size_t)s * T * 3 * dm;
-    for (int i = threadIdx.x; i < T * 3 * dm; i += blockDim.x) sq[(i / (3 * dm)) * ldq + i % (3 * dm)] = src[i];
+    // a thread owns columns of the [T, 3 dm] block: no per-element division, consecutive threads read consecutive floats of a step
+    for (int c = threadIdx.x; c < 3 * dm; c += blockDim.x) {
+#pragma unroll 5
+        for (int t = 0; t < T; t++) sq[t * ldq + c] = __ldg(src + (size_t)t * 3 * dm + c);
+    }
     if (BWD) {
         const int TQl = T - a.q_from;
         const float* dsrc = a.dout + (size_t)s * TQl * dm;
-        for (int i = threadIdx.x; i < TQl * dm; i += blockDim.x) sdo[(a.q_from + i / dm) * (dm + 1) + i % dm] = dsrc[i];
+        for (int c = threadIdx.x; c < dm; c += blockDim.x)
+            for (int t = 0; t < TQl; t++) sdo[(a.q_from + t) * (dm + 1) + c] = __ldg(dsrc + (size_t)t * dm + c);
         for (int i = threadIdx.x; i < T * ldq; i += blockDim.x) sdq[i] = 0.f;
     }
     __syncthreads();
@@ -487,7 +492,10 @@ __global__ void __launch_bounds__(128) tfm_attn_train_kernel(const TfmAttnArgs a
     if (BWD) {
         __syncthreads();
         float* dst = a.dqkv + (size_t)s * T * 3 * dm;
-        for (int i = threadIdx.x; i < T * 3 * dm; i += blockDim.x) dst[i] = sdq[(i / (3 * dm)) * ldq + i % (3 * dm)];
+        for (int c = threadIdx.x; c < 3 * dm; c += blockDim.x) {
+#pragma unroll 5
+            for (int t = 0; t < T; t++) dst[(size_t)t * 3 * dm + c] = sdq[t * ldq + c];
+        }
     }
 }
 
