@@ -308,28 +308,8 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const __grid_co
                 vr[j] = r; vz[j] = z; vn[j] = n; vh[j] = hn;
             }
             if (warp == 4 && lane == 0) GTC_STAMP(0, step, 2);
-            // the staging rows of the previous step must have left shared memory
-            if (step > 0 && (want_g || want_o)) mbar_wait(bar_sfree, (uint32_t)((step - 1) & 1));
-            if (warp == 4 && lane == 0) GTC_STAMP(0, step, 3);
-            if (want_g && TILED) {
-#pragma unroll
-                for (int q = 0; q < HC / 4; q++) {
-                    float4* g4 = reinterpret_cast<float4*>(Gs) + (size_t)((j0 >> 2) + q) * 128 + row;      // chunk-major: 32 rows = 512 contiguous bytes
-                    g4[0] = make_float4(vr[q * 4], vr[q * 4 + 1], vr[q * 4 + 2], vr[q * 4 + 3]);
-                    g4[(H / 4) * 128] = make_float4(vz[q * 4], vz[q * 4 + 1], vz[q * 4 + 2], vz[q * 4 + 3]);
-                    g4[2 * (H / 4) * 128] = make_float4(vn[q * 4], vn[q * 4 + 1], vn[q * 4 + 2], vn[q * 4 + 3]);
-                    g4[3 * (H / 4) * 128] = make_float4(vh[q * 4], vh[q * 4 + 1], vh[q * 4 + 2], vh[q * 4 + 3]);
-                }
-            } else if (want_g) {
-#pragma unroll
-                for (int q = 0; q < HC / 4; q++) {
-                    *reinterpret_cast<float4*>(grow + j0 + q * 4) = make_float4(vr[q * 4], vr[q * 4 + 1], vr[q * 4 + 2], vr[q * 4 + 3]);
-                    *reinterpret_cast<float4*>(grow + H + j0 + q * 4) = make_float4(vz[q * 4], vz[q * 4 + 1], vz[q * 4 + 2], vz[q * 4 + 3]);
-                    *reinterpret_cast<float4*>(grow + 2 * H + j0 + q * 4) = make_float4(vn[q * 4], vn[q * 4 + 1], vn[q * 4 + 2], vn[q * 4 + 3]);
-                    *reinterpret_cast<float4*>(grow + 3 * H + j0 + q * 4) = make_float4(vh[q * 4], vh[q * 4 + 1], vh[q * 4 + 2], vh[q * 4 + 3]);
-                }
-            }
-            // publish h_t as the A operand of the next step (hi / lo planes); stage the output row
+            // publish h_t as the A operand of the next step (hi / lo planes) FIRST: the next step's h-part MMAs are the
+            // serial chain of the layer, the staging of this step's gates / output rows below then overlaps them
 #pragma unroll
             for (int q = 0; q < HC / 4; q++) {
                 const float4 v = make_float4(h[q * 4], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
@@ -338,15 +318,43 @@ __global__ void __launch_bounds__(GTC_THREADS) gru_fwd_tc_kernel(const __grid_co
                 const uint32_t off = (uint32_t)row * 16 + (uint32_t)(j0 / 4 + q) * TC_A_LBO;
                 *reinterpret_cast<float4*>(Hs_hi + off) = hi;
                 *reinterpret_cast<float4*>(Hs_lo + off) = lo;
-                if (want_o) {
-                    const int oc = TILED ? (((j0 >> 2) + q) ^ ox) : ((j0 >> 2) + q);
-                    *reinterpret_cast<float4*>(orow + oc * 4) = valid ? v : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
             }
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar_h);
-            if (want_g || want_o) mbar_arrive(bar_sfull);
+            if (warp == 4 && lane == 0) GTC_STAMP(0, step, 3);
+            if (want_g || want_o) {
+                // the staging rows of the previous step must have left shared memory
+                if (step > 0) mbar_wait(bar_sfree, (uint32_t)((step - 1) & 1));
+                if (want_g && TILED) {
+#pragma unroll
+                    for (int q = 0; q < HC / 4; q++) {
+                        float4* g4 = reinterpret_cast<float4*>(Gs) + (size_t)((j0 >> 2) + q) * 128 + row;      // chunk-major: 32 rows = 512 contiguous bytes
+                        g4[0] = make_float4(vr[q * 4], vr[q * 4 + 1], vr[q * 4 + 2], vr[q * 4 + 3]);
+                        g4[(H / 4) * 128] = make_float4(vz[q * 4], vz[q * 4 + 1], vz[q * 4 + 2], vz[q * 4 + 3]);
+                        g4[2 * (H / 4) * 128] = make_float4(vn[q * 4], vn[q * 4 + 1], vn[q * 4 + 2], vn[q * 4 + 3]);
+                        g4[3 * (H / 4) * 128] = make_float4(vh[q * 4], vh[q * 4 + 1], vh[q * 4 + 2], vh[q * 4 + 3]);
+                    }
+                } else if (want_g) {
+#pragma unroll
+                    for (int q = 0; q < HC / 4; q++) {
+                        *reinterpret_cast<float4*>(grow + j0 + q * 4) = make_float4(vr[q * 4], vr[q * 4 + 1], vr[q * 4 + 2], vr[q * 4 + 3]);
+                        *reinterpret_cast<float4*>(grow + H + j0 + q * 4) = make_float4(vz[q * 4], vz[q * 4 + 1], vz[q * 4 + 2], vz[q * 4 + 3]);
+                        *reinterpret_cast<float4*>(grow + 2 * H + j0 + q * 4) = make_float4(vn[q * 4], vn[q * 4 + 1], vn[q * 4 + 2], vn[q * 4 + 3]);
+                        *reinterpret_cast<float4*>(grow + 3 * H + j0 + q * 4) = make_float4(vh[q * 4], vh[q * 4 + 1], vh[q * 4 + 2], vh[q * 4 + 3]);
+                    }
+                }
+                if (want_o) {
+#pragma unroll
+                    for (int q = 0; q < HC / 4; q++) {
+                        const int oc = TILED ? (((j0 >> 2) + q) ^ ox) : ((j0 >> 2) + q);
+                        *reinterpret_cast<float4*>(orow + oc * 4) =
+                            valid ? make_float4(h[q * 4], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(bar_sfull);
+            }
             if (warp == 4 && lane == 0) GTC_STAMP(1, step, 0);
         }
         if (a.Hn && s < a.S) {

@@ -41,7 +41,7 @@ for it in range(3):
 L.dof_test_gru_bwdw_timeline(None)
 d = dbg.view(8, T, 4).cpu()
 t0 = int(d[0, 0, 0])
-names = ["gate w4 : loop top | acc ready | math done | staging free", "gate w4 : published h + staged rows", "MMA     : loop top | h ready | h-part issued | x-part of next step issued",
+names = ["gate w4 : loop top | acc ready | math done | h published", "gate w4 : gates + output rows staged", "MMA     : loop top | h ready | h-part issued | x-part of next step issued",
          "store w13: loop top | rows staged | drained", "prod w0 : loop top | x staged | helped draining"]
 for r, nm in enumerate(names):
     print(nm)
