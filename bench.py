@@ -43,7 +43,7 @@ WORKLOAD = "cfg2: VaDE GRU encoder, 1M synthetic windows (25x14x3 + 25x14x1), la
 WORKLOADS = {
     "cfg2": dict(CFG, kind="vade", flops=88.6e6, name=WORKLOAD, metric="pose-windows/sec trained (VaDE, win=25x28)"),
     "vqvae": dict(CFG, K=64, kind="vqvae", flops=92.6e6,
-                  name="cfg3r: VQ-VAE with the RECURRENT encoder/decoder (the transformer of cfg3 is not built yet), 1M synthetic "
+                  name="cfg3r: VQ-VAE with the RECURRENT encoder/decoder (the transformer cfg3 is its own line), 1M synthetic "
                        "windows (25x14x3 + 25x14x1), latent=16, codebook=64, batch 4096/GPU",
                   metric="pose-windows/sec trained (VQ-VAE recurrent, win=25x28)"),
     "cfg3": dict(CFG, K=64, kind="vqvae", encoder="transformer", flops=180.1e6,

@@ -9,7 +9,7 @@
 // raw window once and key_dim floats out.  Only the LAST time step leaves the core (:982), so the last layer computes
 // queries, attention output, projections and FFN for that single row (keys / values for all rows).  fp32 SIMT: the
 // per-sequence products are 25 x 40 x {120, 40, 128}: far below a tcgen05 tile, and this is the inference path
-// (embedding_per_video); the training backward of this encoder is not built yet.
+// (embedding_per_video); training runs the composed tcgen05 path in tfm_step.cuh / tfm_train.cuh instead.
 #pragma once
 #include "common.cuh"
 #include "tfm_train.cuh"
