@@ -135,7 +135,13 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc, self.h, self.nv = index, [], None, None, None
         self.sm, self.pw, self.mx, self.bits, self.source = [], [], None, 0, None
-        self.stop_ev = threading.Event()
+        self.stop_ev, self.armed = threading.Event(), threading.Event()
+
+    def arm(self):
+        """Samples count from here on.  start() (NVML initialisation / the nvidia-smi fork: 100+ ms on a multi-GPU box) runs
+        BEFORE the barrier that opens the timed region — done after it on rank 0 only, the other ranks' first timed step waited
+        for rank 0 inside the gradient exchange and the max-over-ranks step time carried the delay."""
+        self.armed.set()
 
     def _nvml_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
@@ -168,6 +174,9 @@ class ClockSampler:
     def _poll(self):
         nv = self.nv
         while not self.stop_ev.is_set():
+            if not self.armed.is_set():
+                self.armed.wait(0.01)
+                continue
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
@@ -178,7 +187,8 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            if self.armed.is_set():
+                self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.nv is not None:
@@ -352,9 +362,11 @@ def run_workload(c, steps, warmup, world, rank, local, dev, sample_clocks=True, 
     # ---- value: device-resident inputs
     run_resident(warmup, 0)
     sampler = ClockSampler(local) if sample_clocks else None
+    if rank == 0 and sampler:
+        sampler.start()                  # slow part (NVML init / fork) outside the timed region and before the barrier
     barrier()
     if rank == 0 and sampler:
-        sampler.start()
+        sampler.arm()
     l0 = L.dof_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
